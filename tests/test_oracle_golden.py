@@ -1,0 +1,167 @@
+"""Pins oracle/sdnq_oracle.py against fixtures produced by the unmodified reference
+(tests/golden/generate.py).  CPU only."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import sdnq_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+LAYER_FILES = sorted(glob.glob(os.path.join(GOLDEN, "layer_*.npz")))
+
+
+def ulp_diff_bf16(a, b):
+    """difference in bf16 ulps between two bf16-valued float32 arrays (sign-magnitude aware)."""
+    ia = O.bf16_bits(a).astype(np.int32)
+    ib = O.bf16_bits(b).astype(np.int32)
+    ia = np.where(ia & 0x8000, -(ia & 0x7FFF), ia)
+    ib = np.where(ib & 0x8000, -(ib & 0x7FFF), ib)
+    return np.abs(ia - ib)
+
+
+def test_dtype_table_matches_reference():
+    table = json.load(open(os.path.join(GOLDEN, "dtype_table.json")))
+    checked = 0
+    for name, row in table.items():
+        if "alias_of" in row or name.endswith(("fnuz", "e8m0fnu")) or name in ("bool", "int1", "uint1"):
+            continue
+        info = O.dtype_info(name)
+        for k in ("num_bits", "is_unsigned", "is_integer", "is_packed", "exponent", "mantissa"):
+            assert info[k] == row[k], (name, k, info[k], row[k])
+        assert np.isclose(info["max"], row["max"], rtol=1e-5) and np.isclose(info["min"], row["min"], rtol=1e-5), name
+        checked += 1
+    assert checked >= 172
+
+
+@pytest.mark.parametrize("bits", [1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15])
+def test_pack_unpack_known_answers(bits):
+    z = np.load(os.path.join(GOLDEN, "pack_kat.npz"))
+    codes, packed = z[f"uint{bits}_codes"], z[f"uint{bits}_packed"]
+    mine = O.pack_uint(codes, bits)
+    ref = packed.astype(np.int64) & (0xFF if bits < 8 else 0xFFFF)
+    assert np.array_equal(mine.astype(np.int64).reshape(ref.shape), ref)
+    assert np.array_equal(O.unpack_uint(packed, bits, codes.shape), codes)
+    if bits > 1:
+        lo = -(2 ** (bits - 1))
+        assert np.array_equal(O.unpack_int(packed, f"int{bits}", codes.shape), codes + lo)
+        assert np.array_equal(O.pack_int(codes + lo, f"int{bits}").reshape(-1), mine.reshape(-1))
+
+
+def test_pack_survey_vectors():
+    z = np.load(os.path.join(GOLDEN, "pack_kat.npz"))
+    expect = {"uint4": [0x10], "uint2": [0xE4], "uint3": [0x98, 0xE1, 0xEA], "uint5": [0x8B, 0x30, 0xD5, 0x1A, 0xBF],
+              "uint6": [0xCB, 0xB0, 0x95], "uint7": [0x0B, 0x30, 0x55, 0xFA, 0x9F, 0xC4, 0x69]}
+    for name, out in expect.items():
+        bits = int(name[4:])
+        assert list(z[f"kat_{name}_out"]) == out
+        assert list(O.pack_uint(z[f"kat_{name}_in"], bits).reshape(-1)) == out
+
+
+def test_minifloat_decode_tables():
+    z = np.load(os.path.join(GOLDEN, "float_tables.npz"))
+    names = [str(n) for n in z["names"]]
+    assert len(names) == 55
+    for name in names:
+        ref = z[f"{name}_decode"]
+        mine = O.decode_minifloat(np.arange(ref.size), name)
+        assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32)), name
+    # spot values from SURVEY.md 8c
+    assert list(O.decode_minifloat(np.arange(16), "float4_e2m1fn")) == [0, .5, 1, 1.5, 2, 3, 4, 6, 0, -.5, -1, -1.5, -2, -3, -4, -6]
+    assert list(O.decode_minifloat([0x01, 0x08, 0x38, 0x7E, 0x7F, 0xFF], "float8_e4m3fn_sdnq")) == [2.0 ** -9, 2.0 ** -6, 1, 448, 480, -480]
+
+
+def test_e4m3fn_model_roundtrip():
+    import torch
+    x = torch.randn(20000) * 100
+    x = x.clamp(-448, 448)
+    ref = x.to(torch.float8_e4m3fn).view(torch.uint8).numpy()
+    assert np.array_equal(O.e4m3fn_bits(x.numpy()), ref)
+    allb = np.arange(256, dtype=np.uint8)
+    reff = torch.from_numpy(allb).view(torch.float8_e4m3fn).float().numpy()
+    mine = O.from_e4m3fn_bits(allb)
+    assert np.array_equal(np.isnan(mine), np.isnan(reff)) and np.array_equal(mine[~np.isnan(mine)], reff[~np.isnan(reff)])
+    xb = torch.randn(20000) * 3
+    assert np.array_equal(O.bf16_bits(xb.numpy()), xb.to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16))
+
+
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 128, 256, 512])
+def test_hadamard(n):
+    z = np.load(os.path.join(GOLDEN, "hadamard.npz"))
+    assert np.array_equal(O.hadamard_matrix(n, "float32"), z[f"H{n}_f32"])
+    assert np.array_equal(O.bf16_bits(O.hadamard_matrix(n, "bfloat16")), z[f"H{n}_bf16"])
+    y = O.rotate_hadamard(z[f"x{n}_f32"], n, "float32")
+    np.testing.assert_allclose(y, z[f"y{n}_f32"], rtol=0, atol=3e-6)
+    yb = O.rotate_hadamard(O.bf16_round(z[f"x{n}_f32"]), n, "bfloat16")
+    assert ulp_diff_bf16(yb, O.from_bf16_bits(z[f"y{n}_bf16"])).max() <= 1
+    # self-inverse (H symmetric orthogonal)
+    np.testing.assert_allclose(O.rotate_hadamard(y, n, "float32"), z[f"x{n}_f32"], atol=1e-5)
+
+
+@pytest.mark.parametrize("path", LAYER_FILES, ids=[os.path.basename(p)[6:-4] for p in LAYER_FILES])
+def test_layer_against_reference(path):
+    layer, arr, meta = O.load_fixture(path)
+    x = O.from_bf16_bits(arr["x"])
+    d = meta["dequantizer"]
+    exact_dequant = layer.svd_up is None and not layer.use_hadamard
+    # ---- dequantised weight
+    Wref = O.from_bf16_bits(arr["w_dequant"])
+    W = O.dequantize(layer, skip_quantized_matmul=d["use_quantized_matmul"])
+    assert W.shape == Wref.shape
+    du = ulp_diff_bf16(W, Wref)
+    if exact_dequant:
+        assert du.max() == 0, f"dequant differs: max {du.max()} ulp"
+    else:
+        # svd addmm / hadamard sums cancel, so bound the error against the row magnitude as well as in ulps
+        big = np.abs(W - Wref) > 2.0 ** -8 * np.abs(Wref).max(axis=-1, keepdims=True)
+        assert not big.any() and (du > 1).mean() < 1e-3 and (du > 0).mean() < 0.02, f"dequant: max {du.max()} ulp, frac {(du > 0).mean()}"
+    # ---- re-quantised weights for matmul: bit-exact integers
+    if "rq_weight" in arr:
+        r = O.re_quantize_matmul(layer)
+        rq = arr["rq_weight"]
+        if rq.dtype == np.uint8:   # fp8 bits
+            assert np.array_equal(O.e4m3fn_bits(r[0]), rq)
+        else:
+            assert np.array_equal(r[0], rq)
+        assert np.array_equal(r[1].astype(np.float32), arr["rq_scale"])
+        if "rq_zero_point" in arr:
+            assert np.array_equal(r[2].astype(np.float32), arr["rq_zero_point"])
+    # ---- activation quantisation + matmul operands
+    if "mm_xq" in arr:
+        p = O.matmul_inputs(layer, x)
+        fp8 = arr["mm_xq"].dtype == np.uint8 and not meta["forward_func"].endswith("int8_matmul")
+        xq_ref = O.from_e4m3fn_bits(arr["mm_xq"]) if fp8 else arr["mm_xq"].astype(np.int32)
+        xq = p["xq"].astype(np.float32 if fp8 else np.int32)
+        if layer.use_hadamard:
+            xr = O.from_bf16_bits(arr["x_rot"])
+            assert ulp_diff_bf16(p["x_rot"], xr).max() <= 1
+            mism = (xq != xq_ref).mean()
+            assert mism < 5e-3, mism
+        else:
+            assert np.array_equal(xq, xq_ref)
+            assert np.array_equal(p["sx"].reshape(-1), arr["mm_sx"].reshape(-1))
+        wq_ref = O.from_e4m3fn_bits(arr["mm_wq"]) if fp8 else arr["mm_wq"]
+        assert np.array_equal(np.asarray(p["wq"]).astype(np.float32), np.asarray(wq_ref).astype(np.float32))
+        assert np.array_equal(np.asarray(p["sw"], np.float32).reshape(-1), arr["mm_sw"].reshape(-1))
+        if "mm_bias" in arr:
+            bref = arr["mm_bias"]
+            bref = O.from_bf16_bits(bref) if bref.dtype == np.uint16 else bref
+            b = np.broadcast_to(np.asarray(p["bias"], np.float32), bref.shape) if bref.ndim == 2 else np.asarray(p["bias"], np.float32)
+            np.testing.assert_allclose(b, bref, rtol=2e-2, atol=2e-2 * np.abs(bref).max())
+    # ---- output
+    yref = O.from_bf16_bits(arr["y"])
+    y = O.linear_forward(layer, x)
+    assert y.shape == yref.shape
+    finite = np.isfinite(yref)
+    assert np.array_equal(finite, np.isfinite(y))
+    err = np.abs(y[finite] - yref[finite])
+    scale = np.abs(yref[finite]).max()
+    is_mm = d["use_quantized_matmul"] and meta["M"] >= 32
+    if is_mm and not layer.use_hadamard and layer.svd_up is None:
+        # integer/fp8 contraction is exact; only the f32 epilogue order (fma vs mul+add) can move a bf16 ulp
+        assert ulp_diff_bf16(y[finite], yref[finite]).max() <= 1
+    else:
+        assert err.max() <= 2e-2 * scale, (err.max(), scale)
+        assert np.sqrt((err ** 2).mean()) <= 3e-3 * scale
