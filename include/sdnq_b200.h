@@ -1,0 +1,167 @@
+/*
+ * sdnq_b200.h -- C ABI of the B200-native SDNQ quantized-Linear kernels.
+ *
+ * Every entry point is what a binding of the reference's kernel layer for this
+ * path would call; the reference interface each one replaces is cited as
+ * file:line under /root/reference/src/sdnq/.  Plain pointers and sizes only (no
+ * torch / C++ types).  All pointers are DEVICE pointers unless the name ends in
+ * `_host`; the caller owns every buffer including outputs and workspaces; no
+ * entry point allocates, frees, or synchronises; all of them are asynchronous on
+ * `stream` (a `cudaStream_t` passed as `void*`) and CUDA-graph capturable.
+ *
+ * Return value: 0 on success, negative `sdnq_status` otherwise; the message of
+ * the last failure on the calling thread is returned by `sdnq_b200_last_error()`.
+ * There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef SDNQ_B200_H
+#define SDNQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDNQ_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SDNQ_API __attribute__((visibility("default")))
+#else
+#define SDNQ_API
+#endif
+
+typedef enum sdnq_status {
+    SDNQ_OK = 0,
+    SDNQ_EINVAL = -1,       /* bad argument (shape / alignment / enum) */
+    SDNQ_EUNSUPPORTED = -2, /* valid request the kernels do not cover (message says which) */
+    SDNQ_ECUDA = -3,        /* a CUDA runtime / driver call failed */
+    SDNQ_EARCH = -4         /* device is not sm_100 */
+} sdnq_status;
+
+/* element types of activations / outputs / scales */
+typedef enum sdnq_dtype {
+    SDNQ_F32 = 0,
+    SDNQ_BF16 = 1,
+    SDNQ_F16 = 2,
+    SDNQ_I8 = 3,
+    SDNQ_U8 = 4,
+    SDNQ_F8E4M3 = 5,
+    SDNQ_I32 = 6
+} sdnq_dtype;
+
+/* storage format of a quantised weight: one row of reference common.py:16-267 (`dtype_dict`) */
+typedef enum sdnq_wkind {
+    SDNQ_W_INT = 0,       /* intN / uintN, N = 1..8; N < 8 packed as packed_int/pack.py lays it out;
+                             signed types are stored offset-binary (packed_int/__init__.py:76-88) */
+    SDNQ_W_MINIFLOAT = 1, /* floatB_eXmY "fn"/"fnu", B = 1..8, packed like uintB (packed_float.py:26-132) */
+    SDNQ_W_FP8_E4M3FN = 2, /* torch.float8_e4m3fn, unpacked */
+    SDNQ_W_FP8_E5M2 = 3    /* torch.float8_e5m2, unpacked */
+} sdnq_wkind;
+
+typedef struct sdnq_weight_format {
+    int32_t kind;        /* sdnq_wkind */
+    int32_t bits;        /* 1..8 */
+    int32_t is_unsigned; /* uintN / "fnu" */
+    int32_t exponent;    /* minifloat exponent bits */
+    int32_t mantissa;    /* minifloat mantissa bits */
+    int32_t word_bytes;  /* bytes per storage word: 1, or 8 for uint1 (the reference stores one int64 per
+                            packed byte because bool shifts promote, packed_int/pack.py:309-321) */
+} sdnq_weight_format;
+
+/* ---- library ------------------------------------------------------------------------------- */
+SDNQ_API int sdnq_b200_abi_version(void);
+SDNQ_API const char* sdnq_b200_last_error(void);
+/* 0 if device `device` can run these kernels (compute capability 10.x), SDNQ_EARCH otherwise */
+SDNQ_API int sdnq_b200_check_device(int device);
+
+/* ---- unpack:  packed_int.unpack_int (packed_int/__init__.py:83-88) and
+ *               packed_float.unpack_float (packed_float.py:85-132) ------------------------------
+ * packed storage -> `numel` codes / values in flattened row-major order.
+ * out_dtype: SDNQ_I8 / SDNQ_U8 / SDNQ_I32 / SDNQ_F32 for integer formats (signed offset removed),
+ *            SDNQ_F32 / SDNQ_BF16 / SDNQ_F8E4M3 for minifloat formats.  numel % 8 == 0. */
+SDNQ_API int sdnq_b200_unpack(const void* packed, const sdnq_weight_format* fmt, void* out, int out_dtype,
+                     int64_t numel, void* stream);
+
+/* ---- K3 dequant:  SDNQDequantizer.__call__ / dequantize_weight (dequantizer.py:135-162, 389-429)
+ * W[N,K] = cast( unpack(weight) * scale [+ zero_point] ) [+ svd_up @ svd_down] [un-rotate]
+ *   weight      physical [N,K]-ordered storage (packed or not; a K-major [K,N] matmul-layout tensor
+ *               of the reference is physically this, quant_utils.py:239-249)
+ *   scale/zp    f32, one per (row, K-group): physical [N, K/group]; group_size = K for row-wise,
+ *               group_size = -2 tensor-wise (a single scalar).  zp NULL for symmetric formats.
+ *   codebook    if non-zero, `scale` holds levels [N, K/group, 2^bits] and codes index it
+ *               (dequantize_codebook, dequantizer.py:88-131)
+ *   svd_up      rank-r factor, element (n, j) at svd_up[n*up_stride_n + j*up_stride_r]; NULL if none
+ *   svd_down    element (j, k) at svd_down[j*down_stride_r + k*down_stride_k]
+ *   svd_dtype   SDNQ_BF16 / SDNQ_F16 / SDNQ_F32; the sum is rounded to svd_dtype as addmm_ does
+ *   hadamard_group  0 = none, else un-rotate along K in groups of this size (power of two, 4..256)
+ *   out         [N,K] row-major, out_dtype SDNQ_BF16 / SDNQ_F16 / SDNQ_F32 */
+SDNQ_API int sdnq_b200_dequant(const void* weight, const sdnq_weight_format* fmt, const float* scale, const float* zero_point,
+                      int codebook, int64_t N, int64_t K, int64_t group_size,
+                      const void* svd_up, int64_t up_stride_n, int64_t up_stride_r,
+                      const void* svd_down, int64_t down_stride_r, int64_t down_stride_k,
+                      int svd_rank, int svd_dtype, int hadamard_group,
+                      void* out, int out_dtype, void* stream);
+
+/* ---- K4 re-quantise for matmul:  SDNQDequantizer.re_quantize_matmul (dequantizer.py:204-239, 353-386)
+ * dequant to f32 (no SVD, no un-rotate) then row-wise re-quantise to the matmul dtype.
+ *   mm_dtype  SDNQ_I8 (symmetric, quantize_int_mm), SDNQ_U8 (asymmetric int8 codes + zero point,
+ *             quantize_uint_mm) or SDNQ_F8E4M3 (quantize_fp_mm)
+ *   wq        [N,K] 1-byte codes (the K-major [K,N] operand), sw [N] f32, zw [N] f32 (SDNQ_U8 only)
+ *   colsum    optional int32 [N] column sums of wq (needed by the uint8 forward, linear_uint8.py:66-73) */
+SDNQ_API int sdnq_b200_requant(const void* weight, const sdnq_weight_format* fmt, const float* scale, const float* zero_point,
+                      int codebook, int64_t N, int64_t K, int64_t group_size, int mm_dtype,
+                      void* wq, float* sw, float* zw, int32_t* colsum, void* stream);
+
+/* ---- K2 activation pre-pass:  rotate_hadamard + quantize_{int,uint,fp}_mm
+ *      (quant_utils.py:193-209, 264-299; linear_int8.py:14-22, 55-56, 63-69)
+ * x [M,K] row-major (row stride ldx elements) of x_dtype (SDNQ_BF16 / SDNQ_F16 / SDNQ_F32)
+ *   -> optional rotation in groups of hadamard_group (0 = none), rounded back to x_dtype
+ *   -> per-row scale sx[M] = amax/127 (I8), (max-min)/255 + zx[M] (U8), amax/448 (F8E4M3)
+ *   -> xq [M,K] 1-byte codes
+ *   rowsum  optional int32 [M] sum of codes per row (zero-point term); x_rot optional [M,K] x_dtype copy of the
+ *           rotated activations (operand of the SVD branch).  K % 8 == 0. */
+SDNQ_API int sdnq_b200_act_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx, int hadamard_group,
+                        int mm_dtype, void* xq, float* sx, float* zx, int32_t* rowsum, void* x_rot, void* stream);
+
+/* ---- K1 scaled matmul:  int_scaled_mm_func / fp8_scaled_mm_func (kernel_wrappers.py:193-204) ->
+ *      sdnq_scaled_mm (kernels/triton_scaled_mm.py:239-275)
+ * out[M,N] = cast( fma( f32(A @ B) * sx[m], sw[n], bias ) )        (no bias: (acc*sx)*sw)
+ *   a   [M,K] row-major 1-byte codes (SDNQ_I8 or SDNQ_F8E4M3), row stride K
+ *   b   the [K,N] operand stored K-major, i.e. physically [N,K] row-major, same dtype as a
+ *   sx  f32 [M], sw f32 [N]
+ *   bias        NULL, or [N] (bias_ld = 0), or [M,N] (bias_ld = row stride in elements); bias_dtype f32/bf16/f16
+ *   zero-point rank-1 terms, all optional (NULL = absent), added to bias in f32 before the fma in the
+ *   reference's order (linear_int8.py:65-69, linear_uint8.py:66-73):
+ *       rowsum[M] (int32) with zp[N]  :  (f32(rowsum[m]) * sx[m]) * zp[n]
+ *       colsum[N] (int32) with zx[M]  :  (f32(colsum[n]) * sw[n]) * zx[m]   and   K * (zx[m] * zp[n])
+ *   out  [M,N] row-major, out_dtype SDNQ_BF16 / SDNQ_F16 / SDNQ_F32.  K % 16 == 0, N % 8 == 0.
+ *   workspace: none. */
+SDNQ_API int sdnq_b200_scaled_mm(const void* a, const void* b, int ab_dtype, const float* sx, const float* sw,
+                        const void* bias, int bias_dtype, int64_t bias_ld,
+                        const int32_t* rowsum, const float* zp, const int32_t* colsum, const float* zx,
+                        void* out, int out_dtype, int64_t M, int64_t N, int64_t K, void* stream);
+
+/* ---- plain matmul:  int_mm_func / fp8_mm_func (kernel_wrappers.py:160-181) -> sdnq_triton_mm
+ *      (kernels/triton_mm.py:119-150).  out[M,N] = A @ B as int32 (I8) or f32 (F8E4M3). */
+SDNQ_API int sdnq_b200_mm(const void* a, const void* b, int ab_dtype, void* out, int64_t M, int64_t N, int64_t K, void* stream);
+
+/* ---- fused W8A8 Linear:  quantized_linear_forward_{int8,uint8,fp8}_matmul for layers whose stored
+ *      weight is already the matmul operand (linear_int8.py:100-125 with re_quantize_for_matmul cached).
+ * One call = K2 + K1 on `stream`; workspace holds xq / sx / zx / rowsum.
+ *   mm_dtype SDNQ_I8 / SDNQ_U8 / SDNQ_F8E4M3; wq physical [N,K]; zp / colsum as in scaled_mm. */
+SDNQ_API size_t sdnq_b200_linear_w8a8_workspace_bytes(int64_t M, int64_t K);
+SDNQ_API int sdnq_b200_linear_w8a8(const void* x, int x_dtype, int64_t ldx, const void* wq, int mm_dtype,
+                          const float* sw, const float* zp, const int32_t* colsum,
+                          const void* bias, int bias_dtype, int hadamard_group,
+                          void* out, int out_dtype, int64_t M, int64_t N, int64_t K,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* number of kernels launched by this library on the calling thread since the last reset
+ * (bench.py reports it as gpu_launches) */
+SDNQ_API int64_t sdnq_b200_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDNQ_B200_H */

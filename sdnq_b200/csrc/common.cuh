@@ -1,0 +1,258 @@
+// Shared host/device helpers for the sdnq_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/sdnq_b200.h"
+
+namespace sdnq {
+
+// ---------------------------------------------------------------- host: errors / launch accounting
+int set_error(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define SDNQ_REQUIRE(cond, code, ...)                                  \
+    do {                                                               \
+        if (!(cond)) return ::sdnq::set_error((code), __VA_ARGS__);    \
+    } while (0)
+
+#define SDNQ_CUDA_OK(expr)                                                                          \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return ::sdnq::set_error(SDNQ_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));   \
+    } while (0)
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(SDNQ_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    }
+    count_launch();
+    return SDNQ_OK;
+}
+
+int num_sms();
+
+// ---------------------------------------------------------------- device: small numerics
+__device__ __forceinline__ float bf16_to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> struct ElemTraits;
+template <> struct ElemTraits<float> {
+    static constexpr int kDtype = SDNQ_F32;
+    __device__ static __forceinline__ float load(float v) { return v; }
+    __device__ static __forceinline__ float round(float v) { return v; }
+};
+template <> struct ElemTraits<__nv_bfloat16> {
+    static constexpr int kDtype = SDNQ_BF16;
+    __device__ static __forceinline__ float load(__nv_bfloat16 v) { return __bfloat162float(v); }
+    __device__ static __forceinline__ float round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+};
+template <> struct ElemTraits<__half> {
+    static constexpr int kDtype = SDNQ_F16;
+    __device__ static __forceinline__ float load(__half v) { return __half2float(v); }
+    __device__ static __forceinline__ float round(float v) { return __half2float(__float2half_rn(v)); }
+};
+
+// 8 consecutive elements of T held as floats <-> global memory (16 B for 2-byte types, 32 B for float)
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+}
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float (&v)[8]) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __half22float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = r;
+}
+template <>
+__device__ __forceinline__ void store8<__half>(__half* p, const float (&v)[8]) {
+    uint4 r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = r;
+}
+
+// float -> e4m3fn byte, round-to-nearest-even, input already clamped to +-448 (matches torch's cast)
+__device__ __forceinline__ uint8_t f32_to_e4m3(float v) {
+    return static_cast<uint8_t>(__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3));
+}
+__device__ __forceinline__ float e4m3_to_f32(uint8_t b) {
+    __half_raw h = __nv_cvt_fp8_to_halfraw(static_cast<__nv_fp8_storage_t>(b), __NV_E4M3);
+    return __half2float(*reinterpret_cast<__half*>(&h));
+}
+__device__ __forceinline__ float e5m2_to_f32(uint8_t b) {
+    __half_raw h = __nv_cvt_fp8_to_halfraw(static_cast<__nv_fp8_storage_t>(b), __NV_E5M2);
+    return __half2float(*reinterpret_cast<__half*>(&h));
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------- device: Hadamard over a warp
+// A warp holds a 256-element chunk of one row: lane l owns elements [8l, 8l+8).  The transform is
+// applied independently to each aligned sub-block of `G` elements (G = 4..256, power of two).
+//   G a power of 4 : kron^k(H4), H4 = [[1,1,1,-1],[1,1,-1,1],[1,-1,1,1],[-1,1,1,1]]; per base-4 digit
+//                    y_i = (x0+x1+x2+x3) - 2*x_{3-i}                      (reference quant_utils.py:155-165)
+//   otherwise      : Sylvester kron^k([[1,1],[1,-1]]); per bit y = (a+b, a-b)   (quant_utils.py:144-152)
+// The 1/sqrt(G) factor is applied by the caller (it is rounded to the activation dtype upstream).
+__device__ __forceinline__ void h4_inlane(float& a, float& b, float& c, float& d) {
+    const float s = (a + b) + (c + d);
+    const float a2 = s - 2.f * d, b2 = s - 2.f * c, c2 = s - 2.f * b, d2 = s - 2.f * a;
+    a = a2; b = b2; c = c2; d = d2;
+}
+
+template <int G>
+__device__ __forceinline__ void hadamard_warp(float (&v)[8]) {
+    static_assert(G >= 4 && G <= 256 && (G & (G - 1)) == 0, "hadamard group must be a power of two in [4,256]");
+    constexpr int LOG = (G == 4) ? 2 : (G == 8) ? 3 : (G == 16) ? 4 : (G == 32) ? 5 : (G == 64) ? 6 : (G == 128) ? 7 : 8;
+    const int lane = threadIdx.x & 31;
+    if constexpr ((LOG & 1) == 0) {
+        // ---- base-4 digits.  digit 0 = element bits 0-1 (in lane)
+#pragma unroll
+        for (int j = 0; j < 8; j += 4) h4_inlane(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if constexpr (LOG >= 4) {
+            // digit 1 = element bit 2 (in lane) + element bit 3 (lane bit 0)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float lo = v[j], hi = v[j + 4];
+                const float part = lo + hi;
+                const float s = part + __shfl_xor_sync(0xffffffffu, part, 1);
+                const float rev_lo = __shfl_xor_sync(0xffffffffu, hi, 1);  // complement of (bit3, bit2=0) is (!bit3, 1)
+                const float rev_hi = __shfl_xor_sync(0xffffffffu, lo, 1);
+                v[j] = s - 2.f * rev_lo;
+                v[j + 4] = s - 2.f * rev_hi;
+            }
+        }
+        if constexpr (LOG >= 6) {
+            // digit 2 = lane bits 1-2
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float t = v[j] + __shfl_xor_sync(0xffffffffu, v[j], 2);
+                const float s = t + __shfl_xor_sync(0xffffffffu, t, 4);
+                const float rev = __shfl_xor_sync(0xffffffffu, v[j], 6);
+                v[j] = s - 2.f * rev;
+            }
+        }
+        if constexpr (LOG >= 8) {
+            // digit 3 = lane bits 3-4
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float t = v[j] + __shfl_xor_sync(0xffffffffu, v[j], 8);
+                const float s = t + __shfl_xor_sync(0xffffffffu, t, 16);
+                const float rev = __shfl_xor_sync(0xffffffffu, v[j], 24);
+                v[j] = s - 2.f * rev;
+            }
+        }
+    } else {
+        // ---- Sylvester: element bits 0..2 in lane, bits 3.. across lanes
+#pragma unroll
+        for (int b = 1; b < 8; b <<= 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if ((j & b) == 0) {
+                    const float x = v[j], y = v[j | b];
+                    v[j] = x + y;
+                    v[j | b] = x - y;
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 3; b < LOG; ++b) {
+            const int m = 1 << (b - 3);
+            const bool upper = (lane & m) != 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float o = __shfl_xor_sync(0xffffffffu, v[j], m);
+                v[j] = upper ? (o - v[j]) : (v[j] + o);
+            }
+        }
+    }
+}
+
+// runtime dispatch; returns false if G is not supported
+__device__ __forceinline__ void hadamard_warp_dyn(int G, float (&v)[8]) {
+    switch (G) {
+        case 4: hadamard_warp<4>(v); break;
+        case 8: hadamard_warp<8>(v); break;
+        case 16: hadamard_warp<16>(v); break;
+        case 32: hadamard_warp<32>(v); break;
+        case 64: hadamard_warp<64>(v); break;
+        case 128: hadamard_warp<128>(v); break;
+        case 256: hadamard_warp<256>(v); break;
+        default: break;
+    }
+}
+
+// 1/sqrt(G) as the reference applies it: H.div_(n**0.5) in the activation dtype, so the factor is
+// f32(1/sqrt(n)) rounded to T (exact power of two for G a power of 4).
+template <typename T>
+__device__ __forceinline__ float hadamard_factor(int G) {
+    return ElemTraits<T>::round(__fdiv_rn(1.0f, sqrtf(static_cast<float>(G))));
+}
+
+}  // namespace sdnq

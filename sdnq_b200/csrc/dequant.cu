@@ -1,0 +1,380 @@
+// K3 (dequant-only HBM kernel), the unpack-only kernel and K4 (re-quantise for matmul).
+//
+// Reference behaviour restated here:
+//   dequantize_symmetric / _asymmetric / _codebook   dequantizer.py:15-131
+//   dequantize_weight / SDNQDequantizer.__call__      dequantizer.py:135-162, 389-429
+//   re_quantize_{int,uint,fp}_mm / re_quantize_matmul dequantizer.py:166-239
+//   quantize_{int,uint,fp}_mm                         quant_utils.py:264-299
+//
+// Data movement: one lane owns one *octet* (8 consecutive values of a row = `bits` storage bytes), so a warp
+// reads 32*bits contiguous bytes and writes 256 contiguous outputs (512 B of bf16) per step -- every global
+// access is a full-sector, fully-coalesced transaction and there is no reuse to stage in shared memory.
+#include "unpack.cuh"
+
+namespace sdnq {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+struct DequantArgs {
+    const uint8_t* weight;
+    const float* scale;
+    const float* zp;
+    int64_t N, K;
+    int64_t group;          // elements per scale along K (K for row-wise); -2 tensor-wise handled as group = K with stride 0
+    int64_t groups_per_row; // K / group (0 stride for tensor-wise)
+    int64_t scale_row_stride;
+    int codebook;           // scale holds 2^bits levels per group
+    WFormat f;
+    // svd
+    const void* up; int64_t up_sn, up_sr;
+    const void* down; int64_t down_sr, down_sk;
+    int rank; int svd_dtype;
+    int hadamard;
+};
+
+__device__ __forceinline__ float load_any(const void* p, int64_t i, int dtype) {
+    if (dtype == SDNQ_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+    if (dtype == SDNQ_F16) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+    return reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ float round_any(float v, int dtype) {
+    if (dtype == SDNQ_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+    if (dtype == SDNQ_F16) return __half2float(__float2half_rn(v));
+    return v;
+}
+
+// unpack + scale (+ zero point | codebook) of the octet starting at (row n, column k): f32 values, reference op order
+template <int BITS>
+__device__ __forceinline__ void dequant_octet(const DequantArgs& a, int64_t n, int64_t k, float (&w)[8]) {
+    uint32_t codes[8];
+    float q[8];
+    const int64_t oct = (n * a.K + k) >> 3;
+    octet_values<BITS>(a.weight, oct, a.f, q, codes);
+    if ((a.group & 7) == 0 || a.group >= a.K) {
+        const int64_t g = (a.groups_per_row > 0) ? (k / a.group) : 0;
+        const int64_t si = n * a.scale_row_stride + g;
+        if (a.codebook) {
+            const float* lv = a.scale + si * (int64_t(1) << a.f.bits);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = lv[codes[i]];
+        } else {
+            const float s = a.scale[si];
+            if (a.zp != nullptr) {
+                const float z = a.zp[si];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = fmaf(q[i], s, z);      // addcmul(zp, q, scale): one fused op in ATen
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = __fmul_rn(q[i], s);
+            }
+        }
+    } else {   // group sizes that are not a multiple of 8: per-element scale lookup
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t si = n * a.scale_row_stride + (k + i) / a.group;
+            if (a.codebook) w[i] = a.scale[si * (int64_t(1) << a.f.bits) + codes[i]];
+            else if (a.zp != nullptr) w[i] = fmaf(q[i], a.scale[si], a.zp[si]);
+            else w[i] = __fmul_rn(q[i], a.scale[si]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+// grid: (N, ceil(K / (256 * kWarps * ITERS))); each warp walks 256-element chunks of row blockIdx.x.
+template <int BITS, typename OutT, int ITERS>
+__global__ void __launch_bounds__(kThreads) dequant_kernel(const DequantArgs a, OutT* __restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = blockIdx.x;
+    const int64_t k_cta = int64_t(blockIdx.y) * (256 * kWarps * ITERS);
+    extern __shared__ float s_up[];   // [rank] svd_up row n as f32
+    if (a.up != nullptr) {
+        for (int j = threadIdx.x; j < a.rank; j += kThreads) s_up[j] = load_any(a.up, n * a.up_sn + j * a.up_sr, a.svd_dtype);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int64_t k = k_cta + (int64_t(it) * kWarps + warp) * 256 + lane * 8;
+        const bool valid = k < a.K;
+        if (!a.hadamard && !valid) continue;
+        if (a.hadamard && k - lane * 8 >= a.K) continue;   // whole chunk out of range (warp-uniform)
+        float w[8];
+        if (valid) {
+            dequant_octet<BITS>(a, n, k, w);
+            if (a.up != nullptr) {
+                // result.to(svd dtype).addmm_(svd_up, svd_down): f32 accumulate, one rounding (dequantizer.py:69-79)
+                float acc[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = round_any(w[i], a.svd_dtype);
+                for (int j = 0; j < a.rank; ++j) {
+                    const float u = s_up[j];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] = fmaf(u, load_any(a.down, j * a.down_sr + (k + i) * a.down_sk, a.svd_dtype), acc[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = round_any(acc[i], a.svd_dtype);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = ElemTraits<OutT>::round(w[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = 0.f;
+        }
+        if (a.hadamard) {   // un-rotate in the result dtype (dequantizer.py:82-83)
+            hadamard_warp_dyn(a.hadamard, w);
+            const float h = hadamard_factor<OutT>(a.hadamard);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = w[i] * h;
+        }
+        if (valid) store8<OutT>(out + n * a.K + k, w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ unpack only
+template <int BITS>
+__global__ void __launch_bounds__(kThreads) unpack_kernel(const uint8_t* __restrict__ packed, WFormat f, void* __restrict__ out,
+                                                          int out_dtype, int64_t octets) {
+    const int64_t oct = int64_t(blockIdx.x) * kThreads + threadIdx.x;
+    if (oct >= octets) return;
+    uint32_t codes[8];
+    float q[8];
+    octet_values<BITS>(packed, oct, f, q, codes);
+    const int64_t e = oct * 8;
+    if (out_dtype == SDNQ_I8 || out_dtype == SDNQ_U8) {
+        uint2 r;
+        uint8_t* b = reinterpret_cast<uint8_t*>(&r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[i] = static_cast<uint8_t>(static_cast<int>(q[i]));
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(out) + e) = r;
+    } else if (out_dtype == SDNQ_F8E4M3) {
+        uint2 r;
+        uint8_t* b = reinterpret_cast<uint8_t*>(&r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[i] = f32_to_e4m3(fminf(fmaxf(q[i], -448.f), 448.f));
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(out) + e) = r;
+    } else if (out_dtype == SDNQ_I32) {
+        int* o = reinterpret_cast<int*>(out) + e;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = static_cast<int>(q[i]);
+    } else if (out_dtype == SDNQ_BF16) {
+        store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(out) + e, q);
+    } else if (out_dtype == SDNQ_F16) {
+        store8<__half>(reinterpret_cast<__half*>(out) + e, q);
+    } else {
+        store8<float>(reinterpret_cast<float*>(out) + e, q);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4
+// One CTA per output row n: dequant the row to f32 registers, block-reduce amax (or min/max), re-quantise.
+constexpr int kRequantMaxOct = 8;   // octets per thread: K <= 8 * 8 * 256 = 16384
+
+__device__ __forceinline__ float block_reduce_max(float v, float* s) {
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = s[0];
+#pragma unroll
+    for (int i = 1; i < kWarps; ++i) r = fmaxf(r, s[i]);
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ float block_reduce_min(float v, float* s) {
+    v = warp_min(v);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = s[0];
+#pragma unroll
+    for (int i = 1; i < kWarps; ++i) r = fminf(r, s[i]);
+    __syncthreads();
+    return r;
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(kThreads) requant_kernel(const DequantArgs a, int mm_dtype, uint8_t* __restrict__ wq,
+                                                           float* __restrict__ sw, float* __restrict__ zw,
+                                                           int32_t* __restrict__ colsum) {
+    __shared__ float s_red[kWarps];
+    __shared__ int s_sum[kWarps];
+    const int64_t n = blockIdx.x;
+    float w[kRequantMaxOct][8];
+    float vmax = -INFINITY, vmin = INFINITY, amax = 0.f;
+#pragma unroll
+    for (int o = 0; o < kRequantMaxOct; ++o) {
+        const int64_t k = (int64_t(o) * kThreads + threadIdx.x) * 8;
+        if (k < a.K) {
+            dequant_octet<BITS>(a, n, k, w[o]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                amax = fmaxf(amax, fabsf(w[o][i]));
+                vmax = fmaxf(vmax, w[o][i]);
+                vmin = fminf(vmin, w[o][i]);
+            }
+        }
+    }
+    float scale, zero = 0.f;
+    if (mm_dtype == SDNQ_U8) {          // quantize_uint_mm -> get_scale_asymmetric(.., "int8")  quant_utils.py:9-19, 276-286
+        vmax = block_reduce_max(vmax, s_red);
+        vmin = block_reduce_min(vmin, s_red);
+        scale = __fdiv_rn(__fsub_rn(vmax, vmin), 255.f);
+        zero = __fsub_rn(vmin, __fmul_rn(scale, -128.f));
+    } else {                            // get_scale_symmetric                                      quant_utils.py:22-24
+        amax = block_reduce_max(amax, s_red);
+        scale = __fdiv_rn(amax, mm_dtype == SDNQ_F8E4M3 ? 448.f : 127.f);
+    }
+    int local_sum = 0;
+#pragma unroll
+    for (int o = 0; o < kRequantMaxOct; ++o) {
+        const int64_t k = (int64_t(o) * kThreads + threadIdx.x) * 8;
+        if (k < a.K) {
+            uint2 r;
+            uint8_t* b = reinterpret_cast<uint8_t*>(&r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float v = w[o][i];
+                if (mm_dtype == SDNQ_U8) v = __fsub_rn(v, zero);
+                v = __fdiv_rn(v, scale);
+                if (mm_dtype == SDNQ_F8E4M3) {
+                    if (v != v) v = 0.f;                                        // nan_to_num
+                    v = fminf(fmaxf(v, -448.f), 448.f);
+                    b[i] = f32_to_e4m3(v);
+                } else {
+                    v = rintf(v);
+                    const int c = (v != v) ? 0 : static_cast<int>(fminf(fmaxf(v, -128.f), 127.f));
+                    b[i] = static_cast<uint8_t>(static_cast<int8_t>(c));
+                    local_sum += c;
+                }
+            }
+            *reinterpret_cast<uint2*>(wq + n * a.K + k) = r;
+        }
+    }
+    if (colsum != nullptr) {
+        local_sum = warp_sum(local_sum);
+        if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = local_sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+#pragma unroll
+            for (int i = 0; i < kWarps; ++i) t += s_sum[i];
+            colsum[n] = t;
+        }
+    }
+    if (threadIdx.x == 0) {
+        sw[n] = scale;
+        if (zw != nullptr) zw[n] = zero;
+    }
+}
+
+int fill_args(DequantArgs& a, const void* weight, const sdnq_weight_format* fmt, const float* scale, const float* zp,
+              int codebook, int64_t N, int64_t K, int64_t group_size) {
+    int rc = make_wformat(fmt, &a.f);
+    if (rc != SDNQ_OK) return rc;
+    SDNQ_REQUIRE(weight != nullptr && scale != nullptr, SDNQ_EINVAL, "weight/scale pointer is NULL");
+    SDNQ_REQUIRE(N > 0 && K > 0, SDNQ_EINVAL, "empty weight: N=%lld K=%lld", (long long)N, (long long)K);
+    SDNQ_REQUIRE(K % 8 == 0, SDNQ_EUNSUPPORTED, "K (=%lld) must be a multiple of 8", (long long)K);
+    SDNQ_REQUIRE((reinterpret_cast<uintptr_t>(weight) & 7) == 0, SDNQ_EINVAL, "weight pointer must be 8-byte aligned");
+    SDNQ_REQUIRE(N <= 0x7fffffffLL && K <= 65535LL * 4096, SDNQ_EUNSUPPORTED, "weight too large: N=%lld K=%lld", (long long)N, (long long)K);
+    a.weight = reinterpret_cast<const uint8_t*>(weight);
+    a.scale = scale;
+    a.zp = zp;
+    a.N = N;
+    a.K = K;
+    a.codebook = codebook;
+    if (group_size == -2) {              // tensor-wise: one scalar
+        a.group = K; a.groups_per_row = 0; a.scale_row_stride = 0;
+    } else {
+        if (group_size <= 0 || group_size > K) group_size = K;
+        SDNQ_REQUIRE(K % group_size == 0, SDNQ_EINVAL, "group_size %lld does not divide K %lld", (long long)group_size, (long long)K);
+        a.group = group_size; a.groups_per_row = K / group_size; a.scale_row_stride = K / group_size;
+    }
+    if (codebook) SDNQ_REQUIRE(a.f.kind == SDNQ_W_INT && a.f.is_unsigned, SDNQ_EINVAL, "codebook needs an unsigned integer format");
+    a.up = a.down = nullptr;
+    a.up_sn = a.up_sr = a.down_sr = a.down_sk = 0;
+    a.rank = 0; a.svd_dtype = SDNQ_BF16; a.hadamard = 0;
+    return SDNQ_OK;
+}
+
+bool hadamard_ok(int g) { return g == 0 || (g >= 4 && g <= 256 && (g & (g - 1)) == 0); }
+
+}  // namespace
+
+template <typename OutT>
+static int launch_dequant(const DequantArgs& a, void* out, cudaStream_t st) {
+    constexpr int ITERS = 2;
+    dim3 grid(static_cast<unsigned>(a.N), static_cast<unsigned>((a.K + 256 * kWarps * ITERS - 1) / (256 * kWarps * ITERS)));
+    const size_t smem = a.up ? sizeof(float) * a.rank : 0;
+    SDNQ_DISPATCH_BITS(a.f.bits, (dequant_kernel<BITS, OutT, ITERS><<<grid, kThreads, smem, st>>>(a, reinterpret_cast<OutT*>(out))));
+    return check_launch("dequant_kernel");
+}
+
+}  // namespace sdnq
+
+using namespace sdnq;
+
+extern "C" int sdnq_b200_unpack(const void* packed, const sdnq_weight_format* fmt, void* out, int out_dtype, int64_t numel,
+                                void* stream) {
+    WFormat f;
+    int rc = make_wformat(fmt, &f);
+    if (rc != SDNQ_OK) return rc;
+    SDNQ_REQUIRE(packed && out, SDNQ_EINVAL, "NULL pointer");
+    SDNQ_REQUIRE(numel >= 0 && numel % 8 == 0, SDNQ_EINVAL, "numel (=%lld) must be a non-negative multiple of 8", (long long)numel);
+    const bool is_float = f.kind != SDNQ_W_INT;
+    if (is_float)
+        SDNQ_REQUIRE(out_dtype == SDNQ_F32 || out_dtype == SDNQ_BF16 || out_dtype == SDNQ_F16 || out_dtype == SDNQ_F8E4M3, SDNQ_EINVAL,
+                     "float formats unpack to f32/bf16/f16/f8e4m3");
+    else
+        SDNQ_REQUIRE(out_dtype == SDNQ_I8 || out_dtype == SDNQ_U8 || out_dtype == SDNQ_I32 || out_dtype == SDNQ_F32 ||
+                         out_dtype == SDNQ_BF16 || out_dtype == SDNQ_F16, SDNQ_EINVAL, "bad out_dtype %d for an integer format", out_dtype);
+    if (numel == 0) return SDNQ_OK;
+    const int64_t octets = numel / 8;
+    const unsigned blocks = static_cast<unsigned>((octets + kThreads - 1) / kThreads);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    SDNQ_DISPATCH_BITS(f.bits, (unpack_kernel<BITS><<<blocks, kThreads, 0, st>>>(reinterpret_cast<const uint8_t*>(packed), f, out, out_dtype, octets)));
+    return check_launch("unpack_kernel");
+}
+
+extern "C" int sdnq_b200_dequant(const void* weight, const sdnq_weight_format* fmt, const float* scale, const float* zero_point,
+                                 int codebook, int64_t N, int64_t K, int64_t group_size, const void* svd_up, int64_t up_stride_n,
+                                 int64_t up_stride_r, const void* svd_down, int64_t down_stride_r, int64_t down_stride_k,
+                                 int svd_rank, int svd_dtype, int hadamard_group, void* out, int out_dtype, void* stream) {
+    DequantArgs a;
+    int rc = fill_args(a, weight, fmt, scale, zero_point, codebook, N, K, group_size);
+    if (rc != SDNQ_OK) return rc;
+    SDNQ_REQUIRE(out != nullptr && (reinterpret_cast<uintptr_t>(out) & 15) == 0, SDNQ_EINVAL, "out must be a 16-byte aligned pointer");
+    SDNQ_REQUIRE(hadamard_ok(hadamard_group), SDNQ_EUNSUPPORTED, "hadamard group %d: only powers of two in [4,256] are implemented", hadamard_group);
+    if (hadamard_group) SDNQ_REQUIRE(K % hadamard_group == 0, SDNQ_EINVAL, "hadamard group %d does not divide K", hadamard_group);
+    if (svd_up != nullptr) {
+        SDNQ_REQUIRE(svd_down != nullptr && svd_rank > 0 && svd_rank <= 1024, SDNQ_EINVAL, "bad svd arguments (rank %d)", svd_rank);
+        SDNQ_REQUIRE(svd_dtype == SDNQ_BF16 || svd_dtype == SDNQ_F16 || svd_dtype == SDNQ_F32, SDNQ_EINVAL, "bad svd dtype");
+        a.up = svd_up; a.up_sn = up_stride_n; a.up_sr = up_stride_r;
+        a.down = svd_down; a.down_sr = down_stride_r; a.down_sk = down_stride_k;
+        a.rank = svd_rank; a.svd_dtype = svd_dtype;
+    }
+    a.hadamard = hadamard_group;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (out_dtype) {
+        case SDNQ_BF16: return launch_dequant<__nv_bfloat16>(a, out, st);
+        case SDNQ_F16: return launch_dequant<__half>(a, out, st);
+        case SDNQ_F32: return launch_dequant<float>(a, out, st);
+        default: return set_error(SDNQ_EINVAL, "bad out_dtype %d", out_dtype);
+    }
+}
+
+extern "C" int sdnq_b200_requant(const void* weight, const sdnq_weight_format* fmt, const float* scale, const float* zero_point,
+                                 int codebook, int64_t N, int64_t K, int64_t group_size, int mm_dtype, void* wq, float* sw, float* zw,
+                                 int32_t* colsum, void* stream) {
+    DequantArgs a;
+    int rc = fill_args(a, weight, fmt, scale, zero_point, codebook, N, K, group_size);
+    if (rc != SDNQ_OK) return rc;
+    SDNQ_REQUIRE(mm_dtype == SDNQ_I8 || mm_dtype == SDNQ_U8 || mm_dtype == SDNQ_F8E4M3, SDNQ_EINVAL, "bad matmul dtype %d", mm_dtype);
+    SDNQ_REQUIRE(wq && sw && (mm_dtype != SDNQ_U8 || zw), SDNQ_EINVAL, "NULL output pointer");
+    SDNQ_REQUIRE((reinterpret_cast<uintptr_t>(wq) & 7) == 0, SDNQ_EINVAL, "wq must be 8-byte aligned");
+    SDNQ_REQUIRE(K <= int64_t(kRequantMaxOct) * 8 * kThreads, SDNQ_EUNSUPPORTED, "requant: K=%lld exceeds %d", (long long)K,
+                 kRequantMaxOct * 8 * kThreads);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    SDNQ_DISPATCH_BITS(a.f.bits, (requant_kernel<BITS><<<static_cast<unsigned>(N), kThreads, 0, st>>>(
+                                     a, mm_dtype, reinterpret_cast<uint8_t*>(wq), sw, mm_dtype == SDNQ_U8 ? zw : nullptr, colsum)));
+    return check_launch("requant_kernel");
+}

@@ -1,0 +1,380 @@
+// K1: W8A8 scaled matmul on the 5th-gen tensor cores (tcgen05), int8 x int8 -> s32 and e4m3 x e4m3 -> f32.
+//
+// Reference behaviour restated here:
+//   int_scaled_mm_func / fp8_scaled_mm_func    kernel_wrappers.py:193-204
+//   sdnq_scaled_mm (Triton)                    kernels/triton_scaled_mm.py:112-275  (acc*sx, then fma(.,sw,bias), cast)
+//   int_mm_func / fp8_mm_func -> sdnq_triton_mm kernel_wrappers.py:160-181, kernels/triton_mm.py:13-150
+//   zero-point rank-1 terms                    layers/linear/linear_int8.py:65-69, linear_uint8.py:66-73
+//
+// Structure (one persistent CTA per SM, 6 warps, warp-specialised):
+//   warp 0  TMA producer : A tile [128 x 128 B] and B tile [BN x 128 B] per k-block, both K-major, 128 B swizzle,
+//                          into a STAGES-deep shared-memory ring (full/empty mbarriers)
+//   warp 1  MMA issuer   : one thread issues 4 x tcgen05.mma (K = 32 B each) per k-block into a TMEM accumulator
+//                          [128 lanes x BN columns]; two accumulator stages so the epilogue of tile i overlaps
+//                          the main loop of tile i+1; tcgen05.commit releases smem slots / publishes the accumulator
+//   warps 2-5 epilogue   : tcgen05.ld (lane = output row), f32 epilogue in the reference's operation order,
+//                          16 B vector stores
+// A = activations [M,K] (row-major, K contiguous); B = weight, the reference's K-major [K,N] operand, i.e.
+// physically [N,K] with K contiguous -- exactly the "TN" shape tcgen05 wants, so no transposes anywhere.
+#include <mutex>
+
+#include "ptx.cuh"
+
+namespace sdnq {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 128;       // bytes (= elements) of K per stage row: one 128 B swizzle span
+constexpr int UMMA_K = 32;    // 8-bit operands: 32 elements per tcgen05.mma
+constexpr int kThreads = 192;
+constexpr int kEpiWarps = 4;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct GemmParams {
+    const float* sx;
+    const float* sw;
+    const void* bias;
+    int bias_dtype;
+    int64_t bias_ld;
+    const int32_t* rowsum;
+    const float* zp;
+    const int32_t* colsum;
+    const float* zx;
+    void* out;
+    int out_dtype;
+    int M, N, K;
+    int raw;   // plain mm: store the accumulator (s32 / f32) untouched
+};
+
+template <int BN>
+struct Cfg {
+    static constexpr int kStageA = BM * BK;
+    static constexpr int kStageB = BN * BK;
+    static constexpr int kStageBytes = kStageA + kStageB;
+    static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
+};
+
+__device__ __forceinline__ float load_bias(const void* p, int64_t i, int dtype) {
+    if (dtype == SDNQ_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+    if (dtype == SDNQ_F16) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+    return reinterpret_cast<const float*>(p)[i];
+}
+
+template <int BN, bool kInt8>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_a = smem_base;
+    const uint32_t smem_b = smem_base + C::kStages * C::kStageA;
+    const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+        for (int s = 0; s < C::kStages; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(tfull_bar(s), 1);
+            ptx::mbar_init(tempty_bar(s), kEpiWarps);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, C::kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ======================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
+                    ptx::tma_load_2d(smem_a + stage * C::kStageA, &tmap_a, full_bar(stage), kb * BK, m0);
+                    ptx::tma_load_2d(smem_b + stage * C::kStageB, &tmap_b, full_bar(stage), kb * BK, n0);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = kInt8 ? ptx::make_idesc(2, 1, 1, BM, BN) : ptx::make_idesc(1, 0, 0, BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1u;
+                ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);     // epilogue has drained this accumulator stage
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(full_bar(stage), phase);       // TMA bytes have landed
+                    ptx::tc_fence_after();
+                    const uint64_t a_desc = ptx::make_smem_desc_sw128(smem_a + stage * C::kStageA);
+                    const uint64_t b_desc = ptx::make_smem_desc_sw128(smem_b + stage * C::kStageB);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advancing K inside the 128 B swizzle span = advancing the start address (>>4 units)
+                        ptx::umma_ss<kInt8>(d_tmem, a_desc + uint64_t(k * UMMA_K >> 4), b_desc + uint64_t(k * UMMA_K >> 4), idesc,
+                                            (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(empty_bar(stage));           // smem slot free once these MMAs retire
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                }
+                ptx::umma_commit(tfull_bar(as));                  // accumulator complete
+            }
+        }
+    } else {
+        // ======================================================== epilogue (warps 2..5)
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1u;
+            const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+            const int m = m0 + q * 32 + lane;
+            const bool m_ok = m < p.M;
+            float sxm = 0.f, zxm = 0.f, rsx = 0.f;
+            if (!p.raw && m_ok) {
+                sxm = p.sx[m];
+                if (p.zx) zxm = p.zx[m];
+                if (p.rowsum) rsx = __fmul_rn(static_cast<float>(p.rowsum[m]), sxm);   // (rowsum -> f32) * sx
+            }
+            ptx::mbar_wait(tfull_bar(as), aphase);
+            ptx::tc_fence_after();
+            const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 16) {
+                uint32_t r[16];
+                ptx::tmem_ld16(t_row + c, r);
+                ptx::tmem_ld_wait();
+                const int n = n0 + c;
+                if (!m_ok || n >= p.N) continue;
+                if (p.raw) {
+                    // plain mm: accumulator bits as they are (s32 or f32), 4 B each
+                    uint32_t* o = reinterpret_cast<uint32_t*>(p.out) + int64_t(m) * p.N + n;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        if (n + j < p.N) *reinterpret_cast<uint4*>(o + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                    continue;
+                }
+                float y[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int nj = (n + j < p.N) ? n + j : p.N - 1;
+                    const float acc = kInt8 ? static_cast<float>(static_cast<int>(r[j])) : __uint_as_float(r[j]);
+                    const float t = __fmul_rn(acc, sxm);
+                    const float swn = p.sw[nj];
+                    bool has_b = false;
+                    float b = 0.f;
+                    if (p.zp) {                     // zero_bias = (rowsum*sx)*zp            linear_int8.py:66
+                        b = __fmul_rn(rsx, p.zp[nj]);
+                        has_b = true;
+                    }
+                    if (p.colsum) {                 // (+)= (colsum*sw)*zx ; += K*(zx*zp)    linear_uint8.py:67-72
+                        const float wt = __fmul_rn(__fmul_rn(static_cast<float>(p.colsum[nj]), swn), zxm);
+                        b = has_b ? __fadd_rn(b, wt) : wt;
+                        if (p.zp) b = fmaf(static_cast<float>(p.K), __fmul_rn(zxm, p.zp[nj]), b);
+                        has_b = true;
+                    }
+                    if (p.bias) {
+                        const float bv = load_bias(p.bias, p.bias_ld ? int64_t(m) * p.bias_ld + nj : int64_t(nj), p.bias_dtype);
+                        b = has_b ? __fadd_rn(b, bv) : bv;
+                        has_b = true;
+                    }
+                    y[j] = has_b ? fmaf(t, swn, b) : __fmul_rn(t, swn);
+                }
+                if (p.out_dtype == SDNQ_BF16) {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + int64_t(m) * p.N + n;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (n + 8 * h < p.N) {
+                            float v8[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v8[j] = y[8 * h + j];
+                            store8<__nv_bfloat16>(o + 8 * h, v8);
+                        }
+                    }
+                } else if (p.out_dtype == SDNQ_F16) {
+                    __half* o = reinterpret_cast<__half*>(p.out) + int64_t(m) * p.N + n;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (n + 8 * h < p.N) {
+                            float v8[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v8[j] = y[8 * h + j];
+                            store8<__half>(o + 8 * h, v8);
+                        }
+                    }
+                } else {
+                    float* o = reinterpret_cast<float*>(p.out) + int64_t(m) * p.N + n;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (n + 8 * h < p.N) {
+                            float v8[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v8[j] = y[8 * h + j];
+                            store8<float>(o + 8 * h, v8);
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+        }
+    }
+    // ---- teardown
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+// [rows, K] row-major 1-byte matrix -> 2-D tensor map with box {128 B of K, box_rows}, 128 B swizzle, zero OOB fill
+int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    SDNQ_REQUIRE(enc != nullptr, SDNQ_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(K)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SDNQ_REQUIRE(r == CUDA_SUCCESS, SDNQ_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld K=%lld box_rows=%d)",
+                 static_cast<int>(r), (long long)rows, (long long)K, box_rows);
+    return SDNQ_OK;
+}
+
+template <int BN, bool kInt8>
+int launch_gemm(const void* a, const void* b, const GemmParams& p, cudaStream_t st) {
+    using C = Cfg<BN>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(gemm_w8a8_kernel<BN, kInt8>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    });
+    SDNQ_REQUIRE(attr_err == cudaSuccess, SDNQ_ECUDA, "cudaFuncSetAttribute(max dynamic smem %d) failed: %s", C::kSmemBytes,
+                 cudaGetErrorString(attr_err));
+    CUtensorMap ta, tb;
+    int rc = make_tmap(&ta, a, p.M, p.K, BM);
+    if (rc != SDNQ_OK) return rc;
+    rc = make_tmap(&tb, b, p.N, p.K, BN);
+    if (rc != SDNQ_OK) return rc;
+    const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    gemm_w8a8_kernel<BN, kInt8><<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, p);
+    return check_launch("gemm_w8a8_kernel");
+}
+
+// Tile-N choice: the widest tile that still gives every SM work; BN=256 halves the per-MMA shared-memory
+// operand traffic relative to BN=128, so it wins whenever the grid is full either way.
+int pick_bn(int M, int N) {
+    const int sms = num_sms();
+    const int num_m = (M + BM - 1) / BM;
+    auto waves_eff = [&](int bn) {
+        const int tiles = num_m * ((N + bn - 1) / bn);
+        const int waves = (tiles + sms - 1) / sms;
+        return static_cast<double>(tiles) / (static_cast<double>(waves) * sms);
+    };
+    const double e256 = waves_eff(256) * 1.00, e128 = waves_eff(128) * 0.90, e64 = waves_eff(64) * 0.70;
+    if (N <= 64) return 64;
+    if (e256 >= e128 && e256 >= e64) return 256;
+    if (e128 >= e64) return 128;
+    return 64;
+}
+
+}  // namespace
+
+int scaled_mm_impl(const void* a, const void* b, int ab_dtype, GemmParams p, cudaStream_t st) {
+    SDNQ_REQUIRE(a && b && p.out, SDNQ_EINVAL, "NULL pointer");
+    SDNQ_REQUIRE(ab_dtype == SDNQ_I8 || ab_dtype == SDNQ_F8E4M3, SDNQ_EINVAL, "operand dtype must be int8 or float8_e4m3fn (got %d)", ab_dtype);
+    SDNQ_REQUIRE(p.M >= 0 && p.N > 0 && p.K > 0, SDNQ_EINVAL, "bad shape M=%d N=%d K=%d", p.M, p.N, p.K);
+    SDNQ_REQUIRE(p.K % 16 == 0, SDNQ_EUNSUPPORTED, "K (=%d) must be a multiple of 16 (TMA row pitch)", p.K);
+    SDNQ_REQUIRE(p.N % 8 == 0, SDNQ_EUNSUPPORTED, "N (=%d) must be a multiple of 8 (16-byte output vectors)", p.N);
+    SDNQ_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(p.out) & 15) == 0, SDNQ_EINVAL, "a, b and out must be 16-byte aligned");
+    if (!p.raw) {
+        SDNQ_REQUIRE(p.sx && p.sw, SDNQ_EINVAL, "scale pointer is NULL");
+        SDNQ_REQUIRE(p.out_dtype == SDNQ_BF16 || p.out_dtype == SDNQ_F16 || p.out_dtype == SDNQ_F32, SDNQ_EINVAL, "bad out dtype %d", p.out_dtype);
+        if (p.bias) SDNQ_REQUIRE(p.bias_dtype == SDNQ_BF16 || p.bias_dtype == SDNQ_F16 || p.bias_dtype == SDNQ_F32, SDNQ_EINVAL, "bad bias dtype %d", p.bias_dtype);
+        SDNQ_REQUIRE(!p.zp || p.rowsum || p.colsum, SDNQ_EINVAL, "zp given without rowsum");
+        SDNQ_REQUIRE(!p.colsum || p.zx, SDNQ_EINVAL, "colsum given without zx");
+    }
+    if (p.M == 0) return SDNQ_OK;
+    const bool i8 = ab_dtype == SDNQ_I8;
+    switch (pick_bn(p.M, p.N)) {
+        case 256: return i8 ? launch_gemm<256, true>(a, b, p, st) : launch_gemm<256, false>(a, b, p, st);
+        case 128: return i8 ? launch_gemm<128, true>(a, b, p, st) : launch_gemm<128, false>(a, b, p, st);
+        default: return i8 ? launch_gemm<64, true>(a, b, p, st) : launch_gemm<64, false>(a, b, p, st);
+    }
+}
+
+}  // namespace sdnq
+
+using namespace sdnq;
+
+extern "C" int sdnq_b200_scaled_mm(const void* a, const void* b, int ab_dtype, const float* sx, const float* sw, const void* bias,
+                                   int bias_dtype, int64_t bias_ld, const int32_t* rowsum, const float* zp, const int32_t* colsum,
+                                   const float* zx, void* out, int out_dtype, int64_t M, int64_t N, int64_t K, void* stream) {
+    SDNQ_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), SDNQ_EUNSUPPORTED, "dimension too large");
+    GemmParams p{sx, sw, bias, bias_dtype, bias_ld, rowsum, zp, colsum, zx, out, out_dtype, (int)M, (int)N, (int)K, 0};
+    return scaled_mm_impl(a, b, ab_dtype, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sdnq_b200_mm(const void* a, const void* b, int ab_dtype, void* out, int64_t M, int64_t N, int64_t K, void* stream) {
+    SDNQ_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), SDNQ_EUNSUPPORTED, "dimension too large");
+    GemmParams p{nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, out, SDNQ_I32, (int)M, (int)N, (int)K, 1};
+    return scaled_mm_impl(a, b, ab_dtype, p, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,237 @@
+"""torch.Tensor-facing wrappers over the C ABI.  PyTorch is only the allocator / stream provider here: every
+function resolves raw device pointers and calls the hand-written sm_100a kernels; nothing computes in eager."""
+import torch
+
+from . import _lib
+from ._lib import (SDNQ_BF16, SDNQ_F16, SDNQ_F32, SDNQ_F8E4M3, SDNQ_I8, SDNQ_I32, SDNQ_U8, SDNQ_W_FP8_E4M3FN, SDNQ_W_FP8_E5M2,
+                   SDNQ_W_INT, SDNQ_W_MINIFLOAT, WeightFormat, check)
+from .common import dtype_dict
+
+_TORCH_TO_CODE = {torch.float32: SDNQ_F32, torch.bfloat16: SDNQ_BF16, torch.float16: SDNQ_F16, torch.int8: SDNQ_I8,
+                  torch.uint8: SDNQ_U8, torch.float8_e4m3fn: SDNQ_F8E4M3, torch.int32: SDNQ_I32}
+_MM_CODE = {"int8": SDNQ_I8, "uint8": SDNQ_U8, "float8_e4m3fn": SDNQ_F8E4M3, "fp8": SDNQ_F8E4M3}
+_MM_TORCH = {SDNQ_I8: torch.int8, SDNQ_U8: torch.int8, SDNQ_F8E4M3: torch.float8_e4m3fn}
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    try:
+        return _TORCH_TO_CODE[dtype]
+    except KeyError:
+        raise _lib.SDNQKernelError(f"dtype {dtype} is not supported by the sdnq_b200 kernels") from None
+
+
+def mm_code(matmul_dtype: str) -> int:
+    try:
+        return _MM_CODE[matmul_dtype]
+    except KeyError:
+        raise _lib.SDNQKernelError(f"quantized_matmul_dtype {matmul_dtype!r} has no sm_100a kernel (int8, uint8, float8_e4m3fn do)") from None
+
+
+def weight_format(weights_dtype: str, storage: torch.Tensor | None = None) -> WeightFormat:
+    """One row of `dtype_dict` -> the C ABI's sdnq_weight_format."""
+    e = dtype_dict[weights_dtype]
+    if e["num_bits"] > 8:
+        raise _lib.SDNQKernelError(f"weights_dtype {weights_dtype!r}: formats wider than 8 bits have no CUDA kernel yet")
+    word_bytes = 1
+    if e["num_bits"] == 1 and storage is not None:
+        word_bytes = storage.element_size()      # upstream stores uint1 as one int64 per packed byte
+    if e["is_integer"]:
+        return WeightFormat(SDNQ_W_INT, e["num_bits"], int(e["is_unsigned"]), 0, 0, word_bytes)
+    if e["torch_dtype"] == torch.float8_e4m3fn:
+        return WeightFormat(SDNQ_W_FP8_E4M3FN, 8, 0, 4, 3, 1)
+    if e["torch_dtype"] == torch.float8_e5m2:
+        return WeightFormat(SDNQ_W_FP8_E5M2, 8, 0, 5, 2, 1)
+    if not e["is_packed"]:
+        raise _lib.SDNQKernelError(f"weights_dtype {weights_dtype!r} is not a quantised storage format")
+    return WeightFormat(SDNQ_W_MINIFLOAT, e["num_bits"], int(e["is_unsigned"]), e["exponent"], e["mantissa"], word_bytes)
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.SDNQKernelError("sdnq_b200 kernels need CUDA tensors (there is no CPU path)")
+
+
+def physical_nk(t: torch.Tensor) -> torch.Tensor:
+    """A reference tensor that is logically [K,N] but K-major (stride (1,K)), or logically [N,K] contiguous, viewed as the
+    contiguous [N,K] array that is actually in memory.  Copies only if it is neither."""
+    if t.ndim != 2:
+        return t.contiguous()
+    if t.is_contiguous():
+        return t
+    if t.t().is_contiguous():
+        return t.t()
+    return t.contiguous()
+
+
+def unpack(packed: torch.Tensor, weights_dtype: str, shape, dtype: torch.dtype | None = None) -> torch.Tensor:
+    """packed_int.unpack_int / packed_float.unpack_float on device."""
+    _require_cuda(packed)
+    e = dtype_dict[weights_dtype]
+    if dtype is None:
+        dtype = (torch.uint8 if e["is_unsigned"] else torch.int8) if e["is_integer"] else torch.float32
+    packed = packed.contiguous()
+    out = torch.empty(tuple(shape), dtype=dtype, device=packed.device)
+    fmt = weight_format(weights_dtype, packed)
+    with torch.cuda.device(packed.device):
+        check(_lib.load().sdnq_b200_unpack(_ptr(packed), fmt, _ptr(out), dtype_code(dtype), out.numel(), _stream(packed)))
+    return out
+
+
+def _group_args(scale: torch.Tensor, N: int, K: int, group_size: int, use_codebook: bool, bits: int):
+    if group_size == -2:
+        return -2
+    per_row = scale.numel() // N // ((1 << bits) if use_codebook else 1)
+    return K // max(per_row, 1)
+
+
+def dequant(weight, weights_dtype, scale, zero_point, N, K, group_size, out_dtype, svd_up=None, svd_down=None,
+            svd_layout_matmul=False, hadamard_group=0, use_codebook=False) -> torch.Tensor:
+    """K3.  `weight` is the stored tensor (packed 1-D/2-D, or unpacked [N,K] / K-major [K,N]); returns W[N,K] of out_dtype.
+    svd factors are passed as stored: matmul layout has svd_up [r,N], svd_down [K,r]; plain layout svd_up [N,r], svd_down [r,K]."""
+    _require_cuda(weight, scale)
+    lib = _lib.load()
+    e = dtype_dict[weights_dtype]
+    w = weight if e["is_packed"] else physical_nk(weight)
+    w = w.contiguous() if e["is_packed"] else w
+    scale = scale.to(torch.float32).contiguous() if scale.dtype != torch.float32 or not scale.is_contiguous() else scale
+    if zero_point is not None and (zero_point.dtype != torch.float32 or not zero_point.is_contiguous()):
+        zero_point = zero_point.to(torch.float32).contiguous()
+    fmt = weight_format(weights_dtype, w)
+    gs = _group_args(scale, N, K, group_size, use_codebook, e["num_bits"])
+    out = torch.empty((N, K), dtype=out_dtype, device=w.device)
+    up_args = (None, 0, 0)
+    down_args = (None, 0, 0)
+    rank, svd_code = 0, SDNQ_BF16
+    if svd_up is not None:
+        if svd_layout_matmul:   # svd_up [r,N], svd_down [K,r]
+            rank = svd_up.shape[0]
+            up_args = (_ptr(svd_up), svd_up.stride(1), svd_up.stride(0))
+            down_args = (_ptr(svd_down), svd_down.stride(1), svd_down.stride(0))
+        else:                   # svd_up [N,r], svd_down [r,K]
+            rank = svd_up.shape[1]
+            up_args = (_ptr(svd_up), svd_up.stride(0), svd_up.stride(1))
+            down_args = (_ptr(svd_down), svd_down.stride(0), svd_down.stride(1))
+        svd_code = dtype_code(svd_up.dtype)
+    with torch.cuda.device(w.device):
+        check(lib.sdnq_b200_dequant(_ptr(w), fmt, _ptr(scale), _ptr(zero_point), int(use_codebook), N, K, gs,
+                                    *up_args, *down_args, rank, svd_code, int(hadamard_group), _ptr(out), dtype_code(out_dtype), _stream(w)))
+    return out
+
+
+def requant(weight, weights_dtype, scale, zero_point, N, K, group_size, matmul_dtype, use_codebook=False, want_colsum=False):
+    """K4.  Returns (wq [N,K] physical, sw [N], zw [N] | None, colsum [N] | None)."""
+    _require_cuda(weight, scale)
+    lib = _lib.load()
+    e = dtype_dict[weights_dtype]
+    w = weight.contiguous() if e["is_packed"] else physical_nk(weight)
+    scale = scale.to(torch.float32).contiguous()
+    if zero_point is not None:
+        zero_point = zero_point.to(torch.float32).contiguous()
+    code = mm_code(matmul_dtype)
+    fmt = weight_format(weights_dtype, w)
+    gs = _group_args(scale, N, K, group_size, use_codebook, e["num_bits"])
+    wq = torch.empty((N, K), dtype=_MM_TORCH[code], device=w.device)
+    sw = torch.empty((N,), dtype=torch.float32, device=w.device)
+    zw = torch.empty((N,), dtype=torch.float32, device=w.device) if code == SDNQ_U8 else None
+    colsum = torch.empty((N,), dtype=torch.int32, device=w.device) if (want_colsum or code == SDNQ_U8) else None
+    with torch.cuda.device(w.device):
+        check(lib.sdnq_b200_requant(_ptr(w), fmt, _ptr(scale), _ptr(zero_point), int(use_codebook), N, K, gs, code,
+                                    _ptr(wq), _ptr(sw), _ptr(zw), _ptr(colsum), _stream(w)))
+    return wq, sw, zw, colsum
+
+
+def act_quant(x: torch.Tensor, matmul_dtype: str, hadamard_group: int = 0, want_rowsum: bool = False, want_x_rot: bool = False):
+    """K2.  x [..., K] -> (xq [M,K], sx [M], zx [M] | None, rowsum [M] | None, x_rot [M,K] | None)."""
+    _require_cuda(x)
+    lib = _lib.load()
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1 or x2.stride(0) % 8 != 0 or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    code = mm_code(matmul_dtype)
+    dev = x2.device
+    xq = torch.empty((M, K), dtype=_MM_TORCH[code], device=dev)
+    sx = torch.empty((M,), dtype=torch.float32, device=dev)
+    zx = torch.empty((M,), dtype=torch.float32, device=dev) if code == SDNQ_U8 else None
+    rowsum = torch.empty((M,), dtype=torch.int32, device=dev) if want_rowsum else None
+    x_rot = torch.empty((M, K), dtype=x2.dtype, device=dev) if want_x_rot else None
+    with torch.cuda.device(dev):
+        check(lib.sdnq_b200_act_quant(_ptr(x2), dtype_code(x2.dtype), M, K, x2.stride(0), int(hadamard_group), code,
+                                      _ptr(xq), _ptr(sx), _ptr(zx), _ptr(rowsum), _ptr(x_rot), _stream(x2)))
+    return xq, sx, zx, rowsum, x_rot
+
+
+def scaled_mm(a: torch.Tensor, b_nk: torch.Tensor, sx: torch.Tensor, sw: torch.Tensor, bias: torch.Tensor | None = None,
+              out_dtype: torch.dtype = torch.bfloat16, rowsum=None, zp=None, colsum=None, zx=None) -> torch.Tensor:
+    """K1.  a [M,K] int8/fp8 contiguous, b_nk the physical [N,K] weight.  bias None | [N] | [M,N]."""
+    _require_cuda(a, b_nk)
+    lib = _lib.load()
+    M, K = a.shape
+    N = b_nk.shape[0]
+    assert b_nk.shape[1] == K and a.is_contiguous() and b_nk.is_contiguous()
+    out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    bias_ld, bias_code = 0, SDNQ_F32
+    if bias is not None:
+        bias = bias.contiguous()
+        bias_code = dtype_code(bias.dtype)
+        if bias.ndim == 2 and bias.shape[0] != 1:
+            bias_ld = bias.stride(0)
+    ab = SDNQ_F8E4M3 if a.dtype == torch.float8_e4m3fn else SDNQ_I8
+    with torch.cuda.device(a.device):
+        check(lib.sdnq_b200_scaled_mm(_ptr(a), _ptr(b_nk), ab, _ptr(sx), _ptr(sw), _ptr(bias), bias_code, bias_ld,
+                                      _ptr(rowsum), _ptr(zp), _ptr(colsum), _ptr(zx), _ptr(out), dtype_code(out_dtype), M, N, K, _stream(a)))
+    return out
+
+
+def mm(a: torch.Tensor, b_nk: torch.Tensor) -> torch.Tensor:
+    """plain int8 -> int32 / fp8 -> f32 matmul (int_mm_func / fp8_mm_func)."""
+    _require_cuda(a, b_nk)
+    M, K = a.shape
+    N = b_nk.shape[0]
+    fp8 = a.dtype == torch.float8_e4m3fn
+    out = torch.empty((M, N), dtype=torch.float32 if fp8 else torch.int32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(_lib.load().sdnq_b200_mm(_ptr(a), _ptr(b_nk), SDNQ_F8E4M3 if fp8 else SDNQ_I8, _ptr(out), M, N, K, _stream(a)))
+    return out
+
+
+_WORKSPACES: dict = {}
+
+
+def _workspace(dev, nbytes):
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def linear_w8a8(x, wq_nk, matmul_dtype, sw, bias=None, zp=None, colsum=None, hadamard_group=0, out_dtype=None) -> torch.Tensor:
+    """K2 + K1 in one C call (per-stream cached workspace)."""
+    _require_cuda(x, wq_nk)
+    lib = _lib.load()
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1 or x2.stride(0) % 8 != 0 or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    M, N = x2.shape[0], wq_nk.shape[0]
+    out_dtype = out_dtype or x.dtype
+    out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    nbytes = lib.sdnq_b200_linear_w8a8_workspace_bytes(M, K)
+    ws = _workspace(x.device, nbytes)
+    with torch.cuda.device(x.device):
+        check(lib.sdnq_b200_linear_w8a8(_ptr(x2), dtype_code(x2.dtype), x2.stride(0), _ptr(wq_nk), mm_code(matmul_dtype), _ptr(sw),
+                                        _ptr(zp), _ptr(colsum), _ptr(bias), dtype_code(bias.dtype) if bias is not None else SDNQ_F32,
+                                        int(hadamard_group), _ptr(out), dtype_code(out_dtype), M, N, K, _ptr(ws), ws.numel(), _stream(x)))
+    return out.view(*x.shape[:-1], N)

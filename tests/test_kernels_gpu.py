@@ -1,0 +1,251 @@
+"""Kernel-level parity: every C-ABI entry point against the numpy oracle and the reference-generated fixtures.
+All tests call through sdnq_b200.ops -> ctypes -> libsdnq_b200.so on a CUDA device."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sdnq_oracle as O
+from tests.util import GOLDEN, LAYER_FILES, LAYER_IDS, bf16_ulp_diff, fixture_tensors, np_to_torch, to_f32_np
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def ops():
+    from sdnq_b200 import ops as _ops
+    return _ops
+
+
+# ----------------------------------------------------------------------------------------------- unpack
+@pytest.mark.parametrize("bits", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("signed", [False, True])
+def test_unpack_int_bit_exact(bits, signed):
+    if bits == 1 and signed:
+        pytest.skip("int1 is an alias of uint1")
+    rng = np.random.default_rng(bits * 2 + signed)
+    n = 8 * 4099          # ragged: not a multiple of the block size
+    codes = rng.integers(0, 2 ** bits, size=n)
+    packed = O.pack_uint(codes, bits)
+    name = f"{'' if signed else 'u'}int{bits}"
+    expect = codes + (-(2 ** (bits - 1)) if signed else 0)
+    tp = torch.from_numpy(packed.astype(np.uint8)).to(DEV)
+    for dtype in ((torch.int8, torch.int32, torch.float32) if signed else (torch.uint8, torch.int32, torch.float32)):
+        got = ops().unpack(tp, name, (n,), dtype=dtype)
+        assert np.array_equal(got.cpu().numpy().astype(np.int64), expect)
+
+
+def test_unpack_uint1_int64_words():
+    rng = np.random.default_rng(5)
+    codes = rng.integers(0, 2, size=8 * 1000)
+    packed = O.pack_uint(codes, 1).astype(np.int64)      # upstream stores one int64 per packed byte
+    got = ops().unpack(torch.from_numpy(packed).to(DEV), "uint1", (codes.size,), dtype=torch.uint8)
+    assert np.array_equal(got.cpu().numpy(), codes)
+
+
+def test_unpack_golden_kat():
+    z = np.load(f"{GOLDEN}/pack_kat.npz")
+    for bits in range(1, 8):
+        codes, packed = z[f"uint{bits}_codes"], z[f"uint{bits}_packed"]
+        t = torch.from_numpy(packed.copy()).to(DEV)
+        got = ops().unpack(t, f"uint{bits}", codes.shape, dtype=torch.int32)
+        assert np.array_equal(got.cpu().numpy(), codes), bits
+
+
+def test_unpack_minifloat_all_codes():
+    z = np.load(f"{GOLDEN}/float_tables.npz")
+    for name in [str(n) for n in z["names"]]:
+        ref = z[f"{name}_decode"]
+        bits = O.dtype_info(name)["num_bits"]
+        codes = np.arange(ref.size)
+        pad = (-codes.size) % 8
+        codes_p = np.concatenate([codes, np.zeros(pad, dtype=codes.dtype)])
+        packed = codes_p.astype(np.uint8) if bits == 8 else O.pack_uint(codes_p, bits).astype(np.uint8)
+        got = ops().unpack(torch.from_numpy(packed).to(DEV), name, (codes_p.size,), dtype=torch.float32)
+        assert np.array_equal(got.cpu().numpy()[: ref.size].view(np.uint32), ref.view(np.uint32)), name
+
+
+# ----------------------------------------------------------------------------------------------- dequant / requant on fixtures
+def _dequant_fixture(t, meta, out_dtype=torch.bfloat16, **kw):
+    d = meta["dequantizer"]
+    N, K = d["original_shape"]
+    return ops().dequant(t["weight"], d["weights_dtype"], t["scale"], t["zero_point"], N, K, d["group_size"], out_dtype,
+                         svd_up=t["svd_up"], svd_down=t["svd_down"], svd_layout_matmul=d["use_quantized_matmul"],
+                         hadamard_group=d["hadamard_group_size"] if d["use_hadamard"] else 0, use_codebook=d["use_codebook"], **kw)
+
+
+@pytest.mark.parametrize("path", LAYER_FILES, ids=LAYER_IDS)
+def test_dequant_matches_reference(path):
+    t, z, meta = fixture_tensors(path, DEV)
+    d = meta["dequantizer"]
+    W = _dequant_fixture(t, meta)
+    Wref = np_to_torch(z["w_dequant"], "bfloat16", DEV)
+    assert W.shape == Wref.shape
+    du = bf16_ulp_diff(W, Wref)
+    if t["svd_up"] is None and not d["use_hadamard"]:
+        assert int(du.max()) == 0, f"{int((du > 0).sum())} elements differ, max {int(du.max())} ulp"
+    else:
+        err = (W.float() - Wref.float()).abs()
+        bound = 2.0 ** -8 * Wref.float().abs().amax(dim=-1, keepdim=True)
+        assert bool((err <= bound).all()) and float((du > 1).float().mean()) < 1e-3 and float((du > 0).float().mean()) < 0.02
+
+
+@pytest.mark.parametrize("path", [p for p in LAYER_FILES if "rq_weight__T" in np.load(p).files],
+                         ids=[i for p, i in zip(LAYER_FILES, LAYER_IDS) if "rq_weight__T" in np.load(p).files])
+def test_requant_matches_reference_bit_exact(path):
+    t, z, meta = fixture_tensors(path, DEV)
+    d = meta["dequantizer"]
+    N, K = d["original_shape"]
+    wq, sw, zw, colsum = ops().requant(t["weight"], d["weights_dtype"], t["scale"], t["zero_point"], N, K, d["group_size"],
+                                      d["quantized_matmul_dtype"], use_codebook=d["use_codebook"], want_colsum=True)
+    ref = z["rq_weight__T"]                                   # physical [N,K]
+    got = wq.view(torch.uint8).cpu().numpy() if wq.dtype == torch.float8_e4m3fn else wq.cpu().numpy()
+    assert np.array_equal(got.view(ref.dtype), ref)
+    assert np.array_equal(sw.cpu().numpy(), z["rq_scale"].reshape(-1))
+    if "rq_zero_point" in z.files:
+        assert np.array_equal(zw.cpu().numpy(), z["rq_zero_point"].reshape(-1))
+    if wq.dtype == torch.int8:
+        assert np.array_equal(colsum.cpu().numpy(), ref.astype(np.int64).sum(axis=1))
+
+
+# ----------------------------------------------------------------------------------------------- activation pre-pass
+@pytest.mark.parametrize("mode", ["int8", "uint8", "float8_e4m3fn"])
+@pytest.mark.parametrize("M,K", [(1, 64), (33, 640), (77, 2048), (130, 3072), (5, 15360), (64, 256), (19, 1000)])
+def test_act_quant_bit_exact(mode, M, K):
+    torch.manual_seed(M * 131 + K)
+    x = (torch.randn(M, K) * 3).to(torch.bfloat16)
+    if M > 4:
+        x[2] = 0                         # all-zero row: 0/0 -> code 0, scale 0
+        x[3, ::7] *= 50                  # outliers
+    xq, sx, zx, rowsum, _ = ops().act_quant(x.to(DEV), mode, want_rowsum=(mode != "float8_e4m3fn"))
+    xf = to_f32_np(x)
+    if mode == "int8":
+        q, s = O.quantize_int_mm(xf)
+    elif mode == "uint8":
+        q, s, zref = O.quantize_uint_mm(xf)
+        assert np.array_equal(zx.cpu().numpy(), zref.reshape(-1))
+    else:
+        q, s = O.quantize_fp_mm(xf)
+        q = O.e4m3fn_bits(q)
+    got = xq.view(torch.uint8).cpu().numpy() if mode == "float8_e4m3fn" else xq.cpu().numpy()
+    if mode == "float8_e4m3fn":
+        mism = got != q
+        # +0 / -0 and the zero row are value-equal
+        assert np.array_equal(O.from_e4m3fn_bits(got)[mism], O.from_e4m3fn_bits(q)[mism])
+    else:
+        assert np.array_equal(got, q)
+        assert np.array_equal(rowsum.cpu().numpy(), q.astype(np.int64).sum(axis=1))
+    assert np.array_equal(sx.cpu().numpy(), s.reshape(-1))
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_act_quant_other_activation_dtypes(dtype):
+    torch.manual_seed(3)
+    x = torch.randn(50, 1280).to(dtype)
+    xq, sx, _, _, _ = ops().act_quant(x.to(DEV), "int8")
+    q, s = O.quantize_int_mm(x.float().numpy())
+    assert np.array_equal(xq.cpu().numpy(), q) and np.array_equal(sx.cpu().numpy(), s.reshape(-1))
+
+
+@pytest.mark.parametrize("G", [4, 8, 16, 32, 64, 128, 256])
+def test_hadamard_rotation_matches_oracle(G):
+    torch.manual_seed(G)
+    M, K = 37, 5 * 256 if G == 256 else 640 if G <= 128 and 640 % G == 0 else 512
+    x = torch.randn(M, K).to(torch.bfloat16)
+    xq, sx, _, _, x_rot = ops().act_quant(x.to(DEV), "int8", hadamard_group=G, want_x_rot=True)
+    ref = O.rotate_hadamard(to_f32_np(x), G, "bfloat16")
+    du = bf16_ulp_diff(x_rot.cpu(), torch.from_numpy(ref).to(torch.bfloat16))
+    err = np.abs(to_f32_np(x_rot) - ref)
+    # f32 summation order differs from a GEMM: at most 1 bf16 ulp (or a hair of the row magnitude where sums cancel)
+    assert float((du > 1).float().mean()) < 2e-3 and err.max() <= 2.0 ** -7 * np.abs(ref).max()
+    assert float((du > 0).float().mean()) < 0.02
+    # quantisation of the kernel's own rotated values is exact
+    q, s = O.quantize_int_mm(to_f32_np(x_rot))
+    assert np.array_equal(xq.cpu().numpy(), q) and np.array_equal(sx.cpu().numpy(), s.reshape(-1))
+    # self-inverse: rotating twice returns the input up to bf16 rounding
+    _, _, _, _, x_back = ops().act_quant(x_rot, "int8", hadamard_group=G, want_x_rot=True)
+    assert float((x_back.float().cpu() - x.float()).abs().max()) <= 0.05 * float(x.float().abs().max())
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+SHAPES = [(128, 128, 128), (1, 64, 64), (77, 640, 2048), (130, 264, 400), (256, 512, 1024), (300, 1280, 640), (64, 5120, 640),
+          (1000, 640, 2560), (33, 48, 16), (513, 776, 208)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_int8_mm_exact(M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randint(-128, 128, (M, K), generator=g, dtype=torch.int8)
+    b = torch.randint(-128, 128, (N, K), generator=g, dtype=torch.int8)
+    got = ops().mm(a.to(DEV), b.to(DEV))
+    ref = O.int_mm(a.numpy(), b.numpy().T)
+    assert np.array_equal(got.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES[:7])
+def test_fp8_mm(M, N, K):
+    g = torch.Generator().manual_seed(M + N + K + 1)
+    a = (torch.randn(M, K, generator=g) * 2).to(torch.float8_e4m3fn)
+    b = (torch.randn(N, K, generator=g) * 2).to(torch.float8_e4m3fn)
+    got = ops().mm(a.to(DEV), b.to(DEV))
+    ref = O.fp8_mm(a.float().numpy(), b.float().numpy().T)
+    # products are exact; only the accumulation order / width of the tensor-core adder differs from f64
+    scale = np.abs(a.float().numpy()) @ np.abs(b.float().numpy().T)
+    assert np.all(np.abs(got.cpu().numpy() - ref) <= 2e-4 * scale + 1e-6)
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("bias_kind", ["none", "vec", "mat"])
+def test_int8_scaled_mm_epilogue(M, N, K, bias_kind):
+    g = torch.Generator().manual_seed(M * 3 + N + K)
+    a = torch.randint(-128, 128, (M, K), generator=g, dtype=torch.int8)
+    b = torch.randint(-128, 128, (N, K), generator=g, dtype=torch.int8)
+    sx = torch.rand(M, generator=g) * 0.05 + 1e-3
+    sw = torch.rand(N, generator=g) * 0.01 + 1e-4
+    bias = None
+    if bias_kind == "vec":
+        bias = torch.randn(N, generator=g).to(torch.bfloat16)
+    elif bias_kind == "mat":
+        bias = torch.randn(M, N, generator=g)
+    got = ops().scaled_mm(a.to(DEV), b.to(DEV), sx.to(DEV), sw.to(DEV), None if bias is None else bias.to(DEV), torch.bfloat16)
+    acc = O.int_mm(a.numpy(), b.numpy().T)
+    ref = O.scaled_mm(acc, sx.numpy()[:, None], sw.numpy()[None, :], None if bias is None else bias.float().numpy())
+    du = bf16_ulp_diff(got.cpu(), torch.from_numpy(ref).to(torch.bfloat16))
+    assert int(du.max()) <= 1 and float((du > 0).float().mean()) < 1e-3
+    out32 = ops().scaled_mm(a.to(DEV), b.to(DEV), sx.to(DEV), sw.to(DEV), None if bias is None else bias.to(DEV), torch.float32)
+    ref32 = O.scaled_mm(acc, sx.numpy()[:, None], sw.numpy()[None, :], None if bias is None else bias.float().numpy(), out_dtype="float32")
+    np.testing.assert_allclose(out32.cpu().numpy(), ref32, rtol=1e-6, atol=1e-6)
+
+
+def test_scaled_mm_many_tiles_persistent_loop():
+    """more tiles than SMs so every CTA walks several tiles and both TMEM accumulator stages are recycled."""
+    M, N, K = 2048, 4096, 384
+    g = torch.Generator().manual_seed(9)
+    a = torch.randint(-128, 128, (M, K), generator=g, dtype=torch.int8)
+    b = torch.randint(-128, 128, (N, K), generator=g, dtype=torch.int8)
+    got = ops().mm(a.to(DEV), b.to(DEV))
+    ref = torch._int_mm(a.to(DEV), b.to(DEV).t()) if hasattr(torch, "_int_mm") else None
+    expect = O.int_mm(a.numpy(), b.numpy().T)
+    assert np.array_equal(got.cpu().numpy(), expect)
+    if ref is not None:
+        assert torch.equal(got, ref)
+
+
+# ----------------------------------------------------------------------------------------------- K2 + K1 against the fixtures
+@pytest.mark.parametrize("path", [p for p in LAYER_FILES if "mm_xq" in np.load(p).files],
+                         ids=[i for p, i in zip(LAYER_FILES, LAYER_IDS) if "mm_xq" in np.load(p).files])
+def test_matmul_operands_and_output_match_reference(path):
+    t, z, meta = fixture_tensors(path, DEV)
+    d = meta["dequantizer"]
+    mmdt = d["quantized_matmul_dtype"]
+    hg = d["hadamard_group_size"] if d["use_hadamard"] else 0
+    xq, sx, zx, rowsum, _ = ops().act_quant(t["x"], mmdt, hadamard_group=hg, want_rowsum=True)
+    ref_xq = z["mm_xq"]
+    got_xq = xq.view(torch.uint8).cpu().numpy().view(ref_xq.dtype) if xq.dtype == torch.float8_e4m3fn else xq.cpu().numpy()
+    if hg:
+        assert float(np.mean(got_xq != ref_xq)) < 5e-3
+    else:
+        if xq.dtype == torch.float8_e4m3fn:
+            assert np.array_equal(O.from_e4m3fn_bits(got_xq), O.from_e4m3fn_bits(ref_xq))
+        else:
+            assert np.array_equal(got_xq, ref_xq)
+        assert np.array_equal(sx.cpu().numpy(), z["mm_sx"].reshape(-1))

@@ -1,0 +1,72 @@
+"""Shared helpers for the parity tests: fixture -> torch tensors, bf16 ulp distance, oracle bridges."""
+import glob
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import sdnq_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LAYER_FILES = sorted(glob.glob(os.path.join(GOLDEN, "layer_*.npz")))
+LAYER_IDS = [os.path.basename(p)[6:-4] for p in LAYER_FILES]
+
+_TORCH = {"bfloat16": torch.bfloat16, "float32": torch.float32, "float16": torch.float16, "int8": torch.int8, "uint8": torch.uint8,
+          "int64": torch.int64, "int16": torch.int16, "float8_e4m3fn": torch.float8_e4m3fn, "bool": torch.bool, "int32": torch.int32}
+
+
+def np_to_torch(a: np.ndarray, dtype_name: str, device="cpu") -> torch.Tensor:
+    """inverse of tests/golden/generate.py:to_np (bf16 / fp8 are stored as bit patterns)."""
+    if dtype_name == "bfloat16":
+        t = torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16)
+    elif dtype_name == "float8_e4m3fn":
+        t = torch.from_numpy(a.copy()).view(torch.float8_e4m3fn)
+    else:
+        t = torch.from_numpy(a.copy())
+        assert t.dtype == _TORCH[dtype_name], (t.dtype, dtype_name)
+    return t.to(device)
+
+
+def fixture_tensors(path, device="cpu"):
+    """-> (tensors dict with the reference's logical shapes/strides, raw arrays, meta)."""
+    z = np.load(path, allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    out = {}
+    for key in ("weight", "scale", "zero_point", "svd_up", "svd_down"):
+        info = meta["tensors"][key]
+        if info is None:
+            out[key] = None
+        elif key + "__T" in z.files:
+            out[key] = np_to_torch(z[key + "__T"], info["dtype"], device).t()
+        else:
+            out[key] = np_to_torch(z[key], info["dtype"], device)
+        if out[key] is not None:
+            assert list(out[key].shape) == info["shape"] and list(out[key].stride()) == info["stride"], (key, out[key].shape, out[key].stride(), info)
+    out["x"] = np_to_torch(z["x"], "bfloat16", device)
+    out["bias"] = np_to_torch(z["bias"], "bfloat16", device) if "bias" in z.files else None
+    out["w_orig"] = np_to_torch(z["w_orig"], "bfloat16", device)
+    return out, z, meta
+
+
+def bf16_ulp_diff(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """distance in bf16 ulps between two bf16 tensors (monotone integer mapping of the bit patterns)."""
+    def key(t):
+        i = t.contiguous().view(torch.int16).to(torch.int32) & 0xFFFF
+        return torch.where((i & 0x8000) != 0, -(i & 0x7FFF), i)
+    return (key(a) - key(b)).abs()
+
+
+def to_f32_np(t: torch.Tensor) -> np.ndarray:
+    return t.detach().float().cpu().numpy()
+
+
+def oracle_layer_from_torch(tensors, dequantizer_meta) -> O.Layer:
+    def conv(t):
+        if t is None:
+            return None
+        if t.dtype in (torch.bfloat16, torch.float16, torch.float32, torch.float8_e4m3fn):
+            return t.detach().float().cpu().numpy()
+        return t.detach().cpu().numpy()
+    return O.Layer(conv(tensors["weight"]), conv(tensors["scale"]), conv(tensors["zero_point"]), conv(tensors["svd_up"]),
+                   conv(tensors["svd_down"]), bias=conv(tensors.get("bias")), **dequantizer_meta)
