@@ -99,3 +99,44 @@ allowed_types = set.union(linear_types, embedding_types, conv_types, conv_transp
 
 accepted_weight_dtypes = set(dtype_dict.keys())
 accepted_matmul_dtypes = {"int8", "uint8", "fp8", "fp16", "float8_e4m3fn", "float16"}
+
+
+def _build_weights_dtype_order() -> list:
+    """Ascending "precision" order used by dynamic quantisation to pick the next dtype (reference common.py:302-334):
+    per bit-width: signed int, signed minifloats e1..e5, then unsigned int, unsigned minifloats e1..e5.  At 8 and 16
+    bits the native torch types come right after the integer."""
+    order = []
+    for bits in range(1, 17):
+        for unsigned in (False, True):
+            if bits == 1 and not unsigned:
+                continue
+            order.append(f"{'u' if unsigned else ''}int{bits}")
+            if not unsigned and bits == 8:
+                order += ["float8_e4m3fn", "float8_e5m2"]
+            if not unsigned and bits == 16:
+                order.append("float16")
+            for exponent in range(1, 6):
+                mantissa = bits - exponent - (0 if unsigned else 1)
+                if mantissa < 0:
+                    continue
+                name = f"float{bits}_e{exponent}m{mantissa}{'fnu' if unsigned else 'fn'}"
+                order.append("float8_e4m3fn_sdnq" if name == "float8_e4m3fn" else name)
+    return order
+
+
+weights_dtype_order = _build_weights_dtype_order()
+
+
+def _load_skip_keys():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "skip_keys.json")) as f:
+        raw = json.load(f)
+    table = {name: [e["modules_to_not_convert"], e["modules_dtype_dict"], e["modules_to_not_use_matmul"]] for name, e in raw["models"].items()}
+    for alias, target in raw["aliases"].items():
+        table[alias] = table[target]
+    return tuple(raw["common_skip_keys"]), table
+
+
+# per-architecture lists of modules that stay unquantised / keep bf16 matmul (policy data, see skip_keys.json)
+common_skip_keys, module_skip_keys_dict = _load_skip_keys()

@@ -13,7 +13,7 @@
 //                          [128 lanes x BN columns]; two accumulator stages so the epilogue of tile i overlaps
 //                          the main loop of tile i+1; tcgen05.commit releases smem slots / publishes the accumulator
 //   warps 2-5 epilogue   : tcgen05.ld (lane = output row), f32 epilogue in the reference's operation order,
-//                          16 B vector stores
+//                          swizzled shared-memory staging and TMA bulk stores (clip the M / N tails)
 // A = activations [M,K] (row-major, K contiguous); B = weight, the reference's K-major [K,N] operand, i.e.
 // physically [N,K] with K contiguous -- exactly the "TN" shape tcgen05 wants, so no transposes anywhere.
 #include <mutex>
@@ -28,7 +28,12 @@ constexpr int BK = 128;       // bytes (= elements) of K per stage row: one 128 
 constexpr int UMMA_K = 32;    // 8-bit operands: 32 elements per tcgen05.mma
 constexpr int kThreads = 192;
 constexpr int kEpiWarps = 4;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kStoreBufs = 2;                       // per-warp ring of 32-row x 128 B output blocks
+constexpr int kStoreBlkBytes = 32 * 128;
+constexpr int kStoreBytes = kEpiWarps * kStoreBufs * kStoreBlkBytes;   // 32 KB
+constexpr int kSmemLimit = 227 * 1024;
+
+enum OutKind { OUT_BF16 = 0, OUT_F16 = 1, OUT_F32 = 2, OUT_RAW32 = 3 };
 
 struct GemmParams {
     const float* sx;
@@ -51,28 +56,42 @@ struct Cfg {
     static constexpr int kStageA = BM * BK;
     static constexpr int kStageB = BN * BK;
     static constexpr int kStageBytes = kStageA + kStageB;
-    static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+    static constexpr int kVecBytes = 2 * BN * 4;                        // sw[BN] and bias[BN] of the current tile as f32
+    static constexpr int kFixed = kStoreBytes + kVecBytes + 256 /*barriers: 8*(2*stages+4)+4 <= 164 B*/;
+    static constexpr int kStagesRaw = (kSmemLimit - kFixed) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kFixed;
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
+    static_assert(kStages >= 3, "pipeline too shallow");
 };
 
-__device__ __forceinline__ float load_bias(const void* p, int64_t i, int dtype) {
-    if (dtype == SDNQ_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
-    if (dtype == SDNQ_F16) return __half2float(reinterpret_cast<const __half*>(p)[i]);
-    return reinterpret_cast<const float*>(p)[i];
+// 8 consecutive values of a f32 / bf16 / f16 vector as floats (16 B aligned for 2-byte types, 32 B for f32)
+__device__ __forceinline__ void load8_any(const void* p, int64_t i, int dtype, float (&v)[8]) {
+    if (dtype == SDNQ_BF16) load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(p) + i, v);
+    else if (dtype == SDNQ_F16) load8<__half>(reinterpret_cast<const __half*>(p) + i, v);
+    else load8<float>(reinterpret_cast<const float*>(p) + i, v);
 }
 
-template <int BN, bool kInt8>
+// kSimple: epilogue is exactly  out = fma(acc * sx[m], sw[n], bias[n])  (bias[n] = 0 when absent): no zero-point
+// terms and no [M,N] bias.  It is the case of every int8 / fp8 symmetric layer and is kept free of the generic
+// path's branches so the unrolled epilogue stays small (instruction cache) and at ~4 instructions per element.
+template <int BN, bool kInt8, int OUT, bool kSimple>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_o, const GemmParams p) {
     using C = Cfg<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr int kOutBytes = (OUT == OUT_BF16 || OUT == OUT_F16) ? 2 : 4;
+    constexpr int CPB = 128 / kOutBytes;              // output columns per 128 B store block: 64 or 32
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = ptx::smem_u32(smem_raw);
+    if ((smem_base & 1023u) != 0) __trap();          // the 128 B swizzle atoms need a 1024 B aligned base
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_base + C::kStages * C::kStageA;
-    const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
+    const uint32_t smem_o = smem_base + C::kStages * C::kStageBytes;
+    float* s_sw = reinterpret_cast<float*>(smem_raw + C::kStages * C::kStageBytes + kStoreBytes);
+    float* s_bias = s_sw + BN;
+    const uint32_t bar_base = smem_o + kStoreBytes + C::kVecBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + s); };
@@ -88,6 +107,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_b);
+        ptx::prefetch_tmap(&tmap_o);
         for (int s = 0; s < C::kStages; ++s) {
             ptx::mbar_init(full_bar(s), 1);
             ptx::mbar_init(empty_bar(s), 1);
@@ -155,103 +175,185 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else {
         // ======================================================== epilogue (warps 2..5)
+        // TMEM lane = output row.  Each warp turns its 32 rows x CPB columns into one 32 x 128 B block in shared
+        // memory (128 B swizzle, conflict-free 16 B stores) and hands it to a TMA store, which clips the M / N tails
+        // and writes full lines; a 2-deep ring per warp overlaps the store with the next block's math.
         const int q = warp & 3;                                   // TMEM lane quarter this warp may access
-        int it = 0;
+        const uint32_t my_o = smem_o + uint32_t(warp - 2) * (kStoreBufs * kStoreBlkBytes);
+        int it = 0, blk = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1u;
             const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
-            const int m = m0 + q * 32 + lane;
+            const int mrow0 = m0 + q * 32;
+            const int m = mrow0 + lane;
             const bool m_ok = m < p.M;
             float sxm = 0.f, zxm = 0.f, rsx = 0.f;
-            if (!p.raw && m_ok) {
+            if (OUT != OUT_RAW32 && m_ok) {
                 sxm = p.sx[m];
                 if (p.zx) zxm = p.zx[m];
                 if (p.rowsum) rsx = __fmul_rn(static_cast<float>(p.rowsum[m]), sxm);   // (rowsum -> f32) * sx
+            }
+            const bool vec_bias = p.bias != nullptr && p.bias_ld == 0;
+            if constexpr (OUT != OUT_RAW32) {
+                // per-column vectors of this tile -> shared memory once (f32), read back as broadcast LDS.128;
+                // issued before the accumulator wait so the global latency hides behind the main loop
+                asm volatile("bar.sync 1, 128;" ::: "memory");            // previous tile's readers are done
+                for (int c = threadIdx.x - 64; c < BN; c += 128) {
+                    const int nc = n0 + c;
+                    float sv = 0.f, bv = 0.f;
+                    if (nc < p.N) {
+                        sv = p.sw[nc];
+                        if (vec_bias)
+                            bv = p.bias_dtype == SDNQ_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[nc])
+                                 : p.bias_dtype == SDNQ_F16 ? __half2float(reinterpret_cast<const __half*>(p.bias)[nc])
+                                                            : reinterpret_cast<const float*>(p.bias)[nc];
+                    }
+                    s_sw[c] = sv;
+                    s_bias[c] = bv;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
             ptx::mbar_wait(tfull_bar(as), aphase);
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
-                uint32_t r[16];
-                ptx::tmem_ld16(t_row + c, r);
+            for (int cb = 0; cb < BN / CPB; ++cb) {
+                const int n = n0 + cb * CPB;
+                if (n >= p.N || mrow0 >= p.M) break;              // warp-uniform
+                uint32_t r[CPB];
+                {
+                    uint32_t (&r0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[0]);
+                    ptx::tmem_ld32(t_row + cb * CPB, r0);
+                    if constexpr (CPB == 64) {
+                        uint32_t (&r1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[32]);
+                        ptx::tmem_ld32(t_row + cb * CPB + 32, r1);
+                    }
+                }
+                const uint32_t buf = my_o + uint32_t(blk % kStoreBufs) * kStoreBlkBytes;
+                if (blk >= kStoreBufs) {                          // ring slot still being read by an older TMA store?
+                    if (lane == 0) ptx::tma_store_wait_read<kStoreBufs - 1>();
+                    __syncwarp();
+                }
                 ptx::tmem_ld_wait();
-                const int n = n0 + c;
-                if (!m_ok || n >= p.N) continue;
-                if (p.raw) {
-                    // plain mm: accumulator bits as they are (s32 or f32), 4 B each
-                    uint32_t* o = reinterpret_cast<uint32_t*>(p.out) + int64_t(m) * p.N + n;
+                const uint32_t row_addr = buf + uint32_t(lane) * 128u;
+                if constexpr (OUT == OUT_RAW32) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        if (n + j < p.N) *reinterpret_cast<uint4*>(o + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-                    continue;
-                }
-                float y[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int nj = (n + j < p.N) ? n + j : p.N - 1;
-                    const float acc = kInt8 ? static_cast<float>(static_cast<int>(r[j])) : __uint_as_float(r[j]);
-                    const float t = __fmul_rn(acc, sxm);
-                    const float swn = p.sw[nj];
-                    bool has_b = false;
-                    float b = 0.f;
-                    if (p.zp) {                     // zero_bias = (rowsum*sx)*zp            linear_int8.py:66
-                        b = __fmul_rn(rsx, p.zp[nj]);
-                        has_b = true;
-                    }
-                    if (p.colsum) {                 // (+)= (colsum*sw)*zx ; += K*(zx*zp)    linear_uint8.py:67-72
-                        const float wt = __fmul_rn(__fmul_rn(static_cast<float>(p.colsum[nj]), swn), zxm);
-                        b = has_b ? __fadd_rn(b, wt) : wt;
-                        if (p.zp) b = fmaf(static_cast<float>(p.K), __fmul_rn(zxm, p.zp[nj]), b);
-                        has_b = true;
-                    }
-                    if (p.bias) {
-                        const float bv = load_bias(p.bias, p.bias_ld ? int64_t(m) * p.bias_ld + nj : int64_t(nj), p.bias_dtype);
-                        b = has_b ? __fadd_rn(b, bv) : bv;
-                        has_b = true;
-                    }
-                    y[j] = has_b ? fmaf(t, swn, b) : __fmul_rn(t, swn);
-                }
-                if (p.out_dtype == SDNQ_BF16) {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + int64_t(m) * p.N + n;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (n + 8 * h < p.N) {
-                            float v8[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v8[j] = y[8 * h + j];
-                            store8<__nv_bfloat16>(o + 8 * h, v8);
-                        }
-                    }
-                } else if (p.out_dtype == SDNQ_F16) {
-                    __half* o = reinterpret_cast<__half*>(p.out) + int64_t(m) * p.N + n;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (n + 8 * h < p.N) {
-                            float v8[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v8[j] = y[8 * h + j];
-                            store8<__half>(o + 8 * h, v8);
-                        }
-                    }
+                    for (int c = 0; c < 8; ++c)
+                        ptx::st_shared_v4(row_addr + (uint32_t(c ^ (lane & 7)) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
                 } else {
-                    float* o = reinterpret_cast<float*>(p.out) + int64_t(m) * p.N + n;
+                    constexpr int kChunkCols = 16 / kOutBytes;    // 8 (2-byte out) or 4 (f32 out)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (n + 8 * h < p.N) {
-                            float v8[8];
+                    for (int c8 = 0; c8 < CPB / 8; ++c8) {        // groups of 8 columns
+                        const int nc = n + 8 * c8;
+                        float y[8];
+                        if (nc < p.N) {
+                            float swv[8];
+                            {
+                                const float4 s0 = *reinterpret_cast<const float4*>(s_sw + cb * CPB + 8 * c8);
+                                const float4 s1 = *reinterpret_cast<const float4*>(s_sw + cb * CPB + 8 * c8 + 4);
+                                swv[0] = s0.x; swv[1] = s0.y; swv[2] = s0.z; swv[3] = s0.w;
+                                swv[4] = s1.x; swv[5] = s1.y; swv[6] = s1.z; swv[7] = s1.w;
+                            }
+                            float b[8];
+                            if constexpr (kSimple) {
+                                const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cb * CPB + 8 * c8);
+                                const float4 b1 = *reinterpret_cast<const float4*>(s_bias + cb * CPB + 8 * c8 + 4);
+                                b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+                                b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v8[j] = y[8 * h + j];
-                            store8<float>(o + 8 * h, v8);
+                                for (int j = 0; j < 8; ++j) {
+                                    const uint32_t rv = r[8 * c8 + j];
+                                    const float acc = kInt8 ? static_cast<float>(static_cast<int>(rv)) : __uint_as_float(rv);
+                                    y[j] = fmaf(__fmul_rn(acc, sxm), swv[j], b[j]);      // fma(acc*sx, sw, bias)
+                                }
+                            } else {
+                                bool has_b = false;
+                                if (p.zp) {                           // zero_bias = (rowsum*sx)*zp            linear_int8.py:66
+                                    float zpv[8];
+                                    load8<float>(p.zp + nc, zpv);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) b[j] = __fmul_rn(rsx, zpv[j]);
+                                    has_b = true;
+                                    if (p.colsum) {                   // += (colsum*sw)*zx ; += K*(zx*zp)       linear_uint8.py:67-72
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) {
+                                            const float wt = __fmul_rn(__fmul_rn(static_cast<float>(p.colsum[nc + j]), swv[j]), zxm);
+                                            b[j] = __fadd_rn(b[j], wt);
+                                            b[j] = fmaf(static_cast<float>(p.K), __fmul_rn(zxm, zpv[j]), b[j]);
+                                        }
+                                    }
+                                } else if (p.colsum) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) b[j] = __fmul_rn(__fmul_rn(static_cast<float>(p.colsum[nc + j]), swv[j]), zxm);
+                                    has_b = true;
+                                }
+                                if (p.bias && (p.bias_ld == 0 || m_ok)) {
+                                    float bv[8];
+                                    if (vec_bias) {
+                                        const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cb * CPB + 8 * c8);
+                                        const float4 b1 = *reinterpret_cast<const float4*>(s_bias + cb * CPB + 8 * c8 + 4);
+                                        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+                                        bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+                                    } else {
+                                        load8_any(p.bias, int64_t(m) * p.bias_ld + nc, p.bias_dtype, bv);
+                                    }
+                                    if (has_b) {
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) b[j] = __fadd_rn(b[j], bv[j]);
+                                    } else {
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) b[j] = bv[j];
+                                        has_b = true;
+                                    }
+                                }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const uint32_t rv = r[8 * c8 + j];
+                                    const float acc = kInt8 ? static_cast<float>(static_cast<int>(rv)) : __uint_as_float(rv);
+                                    const float t = __fmul_rn(acc, sxm);          // acc * sx
+                                    y[j] = has_b ? fmaf(t, swv[j], b[j]) : __fmul_rn(t, swv[j]);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) y[j] = 0.f;
+                        }
+                        if constexpr (kChunkCols == 8) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if constexpr (OUT == OUT_BF16) {
+                                    __nv_bfloat162 h = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+                                    w[j] = *reinterpret_cast<uint32_t*>(&h);
+                                } else {
+                                    __half2 h = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+                                    w[j] = *reinterpret_cast<uint32_t*>(&h);
+                                }
+                            }
+                            ptx::st_shared_v4(row_addr + (uint32_t(c8 ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+                        } else {
+                            ptx::st_shared_v4(row_addr + (uint32_t((2 * c8) ^ (lane & 7)) << 4), __float_as_uint(y[0]), __float_as_uint(y[1]),
+                                              __float_as_uint(y[2]), __float_as_uint(y[3]));
+                            ptx::st_shared_v4(row_addr + (uint32_t((2 * c8 + 1) ^ (lane & 7)) << 4), __float_as_uint(y[4]), __float_as_uint(y[5]),
+                                              __float_as_uint(y[6]), __float_as_uint(y[7]));
                         }
                     }
                 }
+                ptx::fence_proxy_async_smem();                    // generic-proxy smem writes -> visible to the TMA engine
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_2d(&tmap_o, buf, n, mrow0);
+                    ptx::tma_store_commit();
+                }
+                ++blk;
             }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
         }
+        if (lane == 0) ptx::tma_store_wait_read<0>();             // smem must outlive the last bulk stores
+        __syncwarp();
     }
     // ---- teardown
     ptx::tc_fence_before();
@@ -281,41 +383,56 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// [rows, K] row-major 1-byte matrix -> 2-D tensor map with box {128 B of K, box_rows}, 128 B swizzle, zero OOB fill
-int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box_rows) {
+// [rows, cols] row-major matrix of `elem_bytes`-wide elements -> 2-D tensor map with a box of {128 B, box_rows},
+// 128 B swizzle; loads zero-fill out-of-bounds elements, stores clip them.
+int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int elem_bytes, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     SDNQ_REQUIRE(enc != nullptr, SDNQ_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
-    cuuint64_t strides[1] = {static_cast<cuuint64_t>(K)};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+    const CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                   : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * elem_bytes};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SDNQ_REQUIRE(r == CUDA_SUCCESS, SDNQ_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld K=%lld box_rows=%d)",
-                 static_cast<int>(r), (long long)rows, (long long)K, box_rows);
+    CUresult r = enc(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SDNQ_REQUIRE(r == CUDA_SUCCESS, SDNQ_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld elem=%d box_rows=%d)",
+                 static_cast<int>(r), (long long)rows, (long long)cols, elem_bytes, box_rows);
     return SDNQ_OK;
 }
 
-template <int BN, bool kInt8>
+template <int BN, bool kInt8, int OUT, bool kSimple>
 int launch_gemm(const void* a, const void* b, const GemmParams& p, cudaStream_t st) {
     using C = Cfg<BN>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_w8a8_kernel<BN, kInt8>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+        attr_err = cudaFuncSetAttribute(gemm_w8a8_kernel<BN, kInt8, OUT, kSimple>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     });
     SDNQ_REQUIRE(attr_err == cudaSuccess, SDNQ_ECUDA, "cudaFuncSetAttribute(max dynamic smem %d) failed: %s", C::kSmemBytes,
                  cudaGetErrorString(attr_err));
-    CUtensorMap ta, tb;
-    int rc = make_tmap(&ta, a, p.M, p.K, BM);
+    CUtensorMap ta, tb, to;
+    int rc = make_tmap(&ta, a, p.M, p.K, 1, BM);
     if (rc != SDNQ_OK) return rc;
-    rc = make_tmap(&tb, b, p.N, p.K, BN);
+    rc = make_tmap(&tb, b, p.N, p.K, 1, BN);
+    if (rc != SDNQ_OK) return rc;
+    rc = make_tmap(&to, p.out, p.M, p.N, (OUT == OUT_BF16 || OUT == OUT_F16) ? 2 : 4, 32);
     if (rc != SDNQ_OK) return rc;
     const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_w8a8_kernel<BN, kInt8><<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, p);
+    gemm_w8a8_kernel<BN, kInt8, OUT, kSimple><<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, to, p);
     return check_launch("gemm_w8a8_kernel");
+}
+
+template <int BN, bool kInt8>
+int launch_gemm_out(const void* a, const void* b, const GemmParams& p, cudaStream_t st) {
+    if (p.raw) return launch_gemm<BN, kInt8, OUT_RAW32, true>(a, b, p, st);
+    const bool simple = !p.zp && !p.colsum && (p.bias == nullptr || p.bias_ld == 0);
+    switch (p.out_dtype) {
+        case SDNQ_BF16: return simple ? launch_gemm<BN, kInt8, OUT_BF16, true>(a, b, p, st) : launch_gemm<BN, kInt8, OUT_BF16, false>(a, b, p, st);
+        case SDNQ_F16: return simple ? launch_gemm<BN, kInt8, OUT_F16, true>(a, b, p, st) : launch_gemm<BN, kInt8, OUT_F16, false>(a, b, p, st);
+        default: return simple ? launch_gemm<BN, kInt8, OUT_F32, true>(a, b, p, st) : launch_gemm<BN, kInt8, OUT_F32, false>(a, b, p, st);
+    }
 }
 
 // Tile-N choice: the widest tile that still gives every SM work; BN=256 halves the per-MMA shared-memory
@@ -355,9 +472,9 @@ int scaled_mm_impl(const void* a, const void* b, int ab_dtype, GemmParams p, cud
     if (p.M == 0) return SDNQ_OK;
     const bool i8 = ab_dtype == SDNQ_I8;
     switch (pick_bn(p.M, p.N)) {
-        case 256: return i8 ? launch_gemm<256, true>(a, b, p, st) : launch_gemm<256, false>(a, b, p, st);
-        case 128: return i8 ? launch_gemm<128, true>(a, b, p, st) : launch_gemm<128, false>(a, b, p, st);
-        default: return i8 ? launch_gemm<64, true>(a, b, p, st) : launch_gemm<64, false>(a, b, p, st);
+        case 256: return i8 ? launch_gemm_out<256, true>(a, b, p, st) : launch_gemm_out<256, false>(a, b, p, st);
+        case 128: return i8 ? launch_gemm_out<128, true>(a, b, p, st) : launch_gemm_out<128, false>(a, b, p, st);
+        default: return i8 ? launch_gemm_out<128, true>(a, b, p, st) : launch_gemm_out<128, false>(a, b, p, st);
     }
 }
 

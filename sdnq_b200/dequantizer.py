@@ -1,0 +1,89 @@
+"""SDNQDequantizer: per-layer metadata + the two weight-side entry points of the forward.
+
+  __call__            -> K3 kernel (unpack + scale [+zp | codebook] [+svd] [un-rotate] -> W[N,K])   reference dequantizer.py:389-429
+  re_quantize_matmul  -> K4 kernel (unpack + dequant f32 + row-wise re-quantise to int8 / fp8)     reference dequantizer.py:353-386
+
+Same dataclass fields as the reference (dequantizer.py:279-350) because `loader` / `apply_sdnq_options_to_model` and
+serialised checkpoints address them by name.  Difference by design: the reference recomputes the re-quantised operand on
+every forward; weights are frozen (requires_grad=False), so here it is computed once per layer and cached on the module
+(see forward._matmul_operand)."""
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+from .common import conv_transpose_types, conv_types, dtype_dict
+
+
+@dataclass
+class SDNQDequantizer:
+    result_dtype: torch.dtype
+    result_shape: torch.Size
+    original_shape: torch.Size
+    original_stride: list
+    quantized_weight_shape: torch.Size
+    weights_dtype: str
+    quantized_matmul_dtype: str
+    hadamard_group_size: int
+    group_size: int
+    svd_rank: int
+    svd_steps: int
+    codebook_steps: int
+    use_quantized_matmul: bool
+    re_quantize_for_matmul: bool
+    use_stochastic_rounding: bool
+    use_hadamard: bool
+    use_codebook: bool
+    layer_class_name: str
+
+    def __post_init__(self):
+        w, m = dtype_dict[self.weights_dtype], dtype_dict[self.quantized_matmul_dtype]
+        self.num_bits, self.is_packed, self.is_integer, self.is_unsigned = w["num_bits"], w["is_packed"], w["is_integer"], w["is_unsigned"]
+        self.num_bits_matmul, self.is_packed_matmul = m["num_bits"], m["is_packed"]
+        self.is_integer_matmul, self.is_unsigned_matmul = m["is_integer"], m["is_unsigned"]
+
+    # ---- geometry helpers --------------------------------------------------------------------
+    def _linear_nk(self):
+        if self.layer_class_name in conv_types or self.layer_class_name in conv_transpose_types:
+            raise NotImplementedError(f"sdnq_b200: {self.layer_class_name} layers are not on the CUDA path yet (Linear only)")
+        shape = tuple(self.original_shape)
+        if len(shape) != 2:
+            raise NotImplementedError(f"sdnq_b200: only 2-D Linear weights have a CUDA dequant kernel (got shape {shape})")
+        return shape
+
+    # ---- K3 ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def __call__(self, weight, scale, zero_point=None, svd_up=None, svd_down=None, hadamard=None, skip_quantized_matmul: bool = False,
+                 non_hadamard: bool = False, skip_compile: bool = False, dtype: torch.dtype | None = None) -> torch.Tensor:
+        """Dequantised weight [N,K] in `dtype` (default result_dtype).  `skip_quantized_matmul=True` means the tensors are stored in
+        matmul layout (K-major weight / transposed SVD factors); physically that is the same [N,K] weight, so only the SVD strides
+        differ.  `hadamard` (a matrix in the reference) is accepted for signature compatibility; the kernel un-rotates with its
+        own butterfly."""
+        N, K = self._linear_nk()
+        dtype = dtype or self.result_dtype
+        if not weight.is_cuda:
+            raise ops._lib.SDNQKernelError("SDNQDequantizer: the weight is not on a CUDA device; sdnq_b200 has no CPU dequant path")
+        un_rotate = self.hadamard_group_size if (self.use_hadamard and not non_hadamard) else 0
+        return ops.dequant(weight, self.weights_dtype, scale, zero_point, N, K, self.group_size, dtype, svd_up=svd_up, svd_down=svd_down,
+                           svd_layout_matmul=bool(skip_quantized_matmul), hadamard_group=un_rotate, use_codebook=self.use_codebook)
+
+    # ---- K4 ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def re_quantize_matmul(self, weight, scale, zero_point=None, svd_up=None, svd_down=None, hadamard=None, non_hadamard: bool = True,
+                           skip_compile: bool = False):
+        """-> (Wq [K,N] K-major view, sw [1,N][, zp [1,N]]) exactly as the reference returns them (dequantizer.py:166-239).
+        SVD / Hadamard are never applied here (the reference passes none on this path)."""
+        wq, sw, zw, _ = self.re_quantize_matmul_raw(weight, scale, zero_point)
+        if self.is_integer_matmul and self.is_unsigned_matmul:
+            return wq.t(), sw.unsqueeze(0), zw.unsqueeze(0)
+        return wq.t(), sw.unsqueeze(0)
+
+    @torch.no_grad()
+    def re_quantize_matmul_raw(self, weight, scale, zero_point=None, want_colsum: bool = False):
+        """physical form for the kernels: (wq [N,K], sw [N], zw [N] | None, colsum [N] | None)"""
+        N, K = self._linear_nk()
+        return ops.requant(weight, self.weights_dtype, scale, zero_point, N, K, self.group_size, self.quantized_matmul_dtype,
+                           use_codebook=self.use_codebook, want_colsum=want_colsum)
+
+
+torch.serialization.add_safe_globals([SDNQDequantizer])

@@ -1,0 +1,142 @@
+"""The hot path: forward functions plugged into SDNQLayer.forward_func.
+
+Same names / dispatch rule as the reference (forward.py:6-57, layers/linear/*.py) so `get_forward_func(...)` is a drop-in:
+
+    quantized_linear_forward                  K3 dequant kernel -> bf16 GEMM (library)          layers/linear/forward.py:24-26
+    quantized_linear_forward_int8_matmul      K2 act-quant + K1 tcgen05 int8 GEMM               layers/linear/linear_int8.py:100-125
+    quantized_linear_forward_uint8_matmul     K2 (asymmetric) + K1 with zero-point epilogue     layers/linear/linear_uint8.py:105-129
+    quantized_linear_forward_fp8_matmul       K2 (e4m3) + K1 tcgen05 fp8 GEMM                   layers/linear/linear_fp8.py:81-104
+
+Every function runs CUDA kernels from libsdnq_b200.so; there is no eager / CPU fallback (a CPU tensor raises)."""
+from collections.abc import Callable
+
+import torch
+
+from . import ops
+from .common import conv_transpose_types, conv_types, dtype_dict, embedding_types
+
+SMALL_M = 32     # rows below this use the dequant path, as upstream does (linear_int8.py:102-103)
+
+
+class _MatmulOperand:
+    """The weight as the GEMM reads it: wq [N,K] 1-byte codes (physical K-major [K,N]), sw [N], optional zp [N] / colsum [N]."""
+    __slots__ = ("wq", "sw", "zp", "colsum", "key")
+
+    def __init__(self, wq, sw, zp, colsum, key):
+        self.wq, self.sw, self.zp, self.colsum, self.key = wq, sw, zp, colsum, key
+
+
+def _flat_f32(t):
+    return None if t is None else t.reshape(-1).to(torch.float32).contiguous()
+
+
+@torch.no_grad()
+def matmul_operand(layer) -> _MatmulOperand:
+    """Build (once) and cache the matmul operand of a W8A8 layer.
+
+    reference: per call re_quantize_matmul (dequantizer.py:204-239) / unpack + transpose (linear_int8.py:38-44) / uint8 -> int8
+    re-centring (linear_int8.py:45-50).  Weights are frozen, so the result is cached per module and invalidated when the
+    stored tensors are replaced (apply_sdnq_options_to_model swaps .data, load_state_dict(assign=True) swaps the Parameter)."""
+    d = layer.sdnq_dequantizer
+    w, s, z = layer.weight, layer.scale, layer.zero_point
+    key = (w.data_ptr(), w._version, s.data_ptr(), None if z is None else z.data_ptr(), d.quantized_matmul_dtype, str(w.device))
+    cached = layer.__dict__.get("_sdnq_mm_cache")
+    if cached is not None and cached.key == key:
+        return cached
+    N, K = tuple(d.original_shape)
+    mm = d.quantized_matmul_dtype
+    uint8_mm = d.is_integer_matmul and d.is_unsigned_matmul
+    zp = colsum = None
+    if d.re_quantize_for_matmul:
+        wq, sw, zp, colsum = d.re_quantize_matmul_raw(w, s, z, want_colsum=uint8_mm)
+    elif d.is_packed:
+        if d.is_integer:
+            wq = ops.unpack(w, d.weights_dtype, (N, K), dtype=torch.int8)          # unsigned codes 0..2^b-1 fit int8 as-is
+            zp = _flat_f32(z)
+        else:
+            wq = ops.unpack(w, d.weights_dtype, (N, K), dtype=torch.float8_e4m3fn)
+        sw = _flat_f32(s)
+    else:
+        wq = ops.physical_nk(w)
+        sw = _flat_f32(s)
+        zp = _flat_f32(z)
+        if wq.dtype == torch.uint8:                                                 # uint8 codes -> int8 around 128
+            wq = wq.bitwise_xor(128).view(torch.int8)
+            zp = torch.add(zp, sw, alpha=128) if zp is not None else torch.mul(sw, 128)
+    if uint8_mm and colsum is None:
+        colsum = wq.to(torch.int32).sum(dim=1, dtype=torch.int32)
+    op = _MatmulOperand(wq.contiguous(), sw, zp, colsum, key)
+    layer.__dict__["_sdnq_mm_cache"] = op
+    return op
+
+
+def _dequant_linear(layer, input, skip_quantized_matmul):
+    d = layer.sdnq_dequantizer
+    W = d(layer.weight, layer.scale, zero_point=layer.zero_point, svd_up=layer.svd_up, svd_down=layer.svd_down,
+          skip_quantized_matmul=skip_quantized_matmul, dtype=input.dtype if input.dtype in (torch.float16, torch.bfloat16, torch.float32) else None)
+    return torch.nn.functional.linear(input, W, layer.bias)
+
+
+@torch.no_grad()
+def quantized_linear_forward(self, input: torch.Tensor) -> torch.Tensor:
+    return _dequant_linear(self, input, skip_quantized_matmul=False)
+
+
+def _w8a8_forward(self, input: torch.Tensor) -> torch.Tensor:
+    d = self.sdnq_dequantizer
+    if input.numel() // input.shape[-1] < SMALL_M:
+        return _dequant_linear(self, input, skip_quantized_matmul=True)
+    op = matmul_operand(self)
+    mm = d.quantized_matmul_dtype
+    hg = d.hadamard_group_size if d.use_hadamard else 0
+    if self.svd_up is None:
+        return ops.linear_w8a8(input, op.wq, mm, op.sw, bias=self.bias, zp=op.zp, colsum=op.colsum, hadamard_group=hg, out_dtype=input.dtype)
+    # SVD branch: bias2d = bias + (x_rot @ svd_down[K,r]) @ svd_up[r,N] in the SVD dtype on the rotated, un-quantised
+    # activations (linear_int8.py:57-62); two skinny library GEMMs, the rest stays in our kernels.
+    xq, sx, zx, rowsum, x_rot = ops.act_quant(input, mm, hadamard_group=hg, want_rowsum=op.zp is not None, want_x_rot=True)
+    down, up = self.svd_down, self.svd_up
+    low = torch.mm(x_rot.to(down.dtype), down)
+    bias2d = torch.mm(low, up) if self.bias is None else torch.addmm(self.bias.to(down.dtype), low, up)
+    out = ops.scaled_mm(xq, op.wq, sx, op.sw, bias2d, input.dtype, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx)
+    return out.view(*input.shape[:-1], out.shape[-1])
+
+
+@torch.no_grad()
+def quantized_linear_forward_int8_matmul(self, input: torch.Tensor) -> torch.Tensor:
+    return _w8a8_forward(self, input)
+
+
+@torch.no_grad()
+def quantized_linear_forward_uint8_matmul(self, input: torch.Tensor) -> torch.Tensor:
+    return _w8a8_forward(self, input)
+
+
+@torch.no_grad()
+def quantized_linear_forward_fp8_matmul(self, input: torch.Tensor) -> torch.Tensor:
+    return _w8a8_forward(self, input)
+
+
+def _unsupported(name: str, what: str) -> Callable:
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError(f"sdnq_b200: {what} has no sm_100a kernel yet; refusing to fall back to an eager path")
+    forward.__name__ = name
+    return forward
+
+
+quantized_linear_forward_fp16_matmul = _unsupported("quantized_linear_forward_fp16_matmul", "the float16 quantized matmul (quantized_matmul_dtype='float16')")
+quantized_conv_forward = _unsupported("quantized_conv_forward", "quantized convolution (quant_conv=True)")
+quantized_embedding_forward = _unsupported("quantized_embedding_forward", "quantized embedding (quant_embedding=True)")
+
+
+def get_forward_func(layer_class_name: str, quantized_matmul_dtype: str, use_quantized_matmul: bool) -> Callable:
+    """reference forward.py:6-57."""
+    if layer_class_name in embedding_types:
+        return quantized_embedding_forward
+    if layer_class_name in conv_types or layer_class_name in conv_transpose_types:
+        return quantized_conv_forward
+    if not use_quantized_matmul:
+        return quantized_linear_forward
+    mm = dtype_dict[quantized_matmul_dtype]
+    if mm["is_integer"]:
+        return quantized_linear_forward_uint8_matmul if mm["is_unsigned"] else quantized_linear_forward_int8_matmul
+    return quantized_linear_forward_fp8_matmul if mm["num_bits"] == 8 else quantized_linear_forward_fp16_matmul

@@ -294,12 +294,41 @@ def run_layer_case(name, K, N, M, bias, cfg):
     print(f"{name:34s} fwd={layer.forward_func.__name__:40s} w={tuple(layer.weight.shape)} gs={d.group_size} requant={d.re_quantize_for_matmul} nan={nan}")
 
 
-if __name__ == "__main__":
+def main():
     dump_dtype_table()
     dump_pack_kat()
     dump_float_tables()
     dump_hadamard()
+    dump_policy_tables()
     for name, (K, N, M, bias, cfg) in LAYER_CASES.items():
         run_layer_case(name, K, N, M, bias, cfg)
     total = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith((".npz", ".json")))
     print("fixtures bytes:", total)
+
+
+# --------------------------------------------------------------------------- policy tables (data, not code)
+def dump_policy_tables():
+    """weights_dtype_order and the per-architecture skip-key tables (reference common.py:302-334, 383-526).
+    Pure configuration data; sdnq_b200/skip_keys.json is this dump and tests/test_host_api.py checks they agree."""
+    from sdnq.common import common_skip_keys, module_skip_keys_dict, weights_dtype_order
+    seen = {}
+    models, aliases = {}, {}
+    for name, entry in module_skip_keys_dict.items():
+        if id(entry) in seen:
+            aliases[name] = seen[id(entry)]
+            continue
+        seen[id(entry)] = name
+        models[name] = {"modules_to_not_convert": list(entry[0]), "modules_dtype_dict": entry[1], "modules_to_not_use_matmul": entry[2]}
+    tables = {"weights_dtype_order": list(weights_dtype_order), "common_skip_keys": list(common_skip_keys), "models": models, "aliases": aliases}
+    with open(os.path.join(HERE, "policy_tables.json"), "w") as f:
+        json.dump(tables, f, indent=1, sort_keys=True)
+    pkg = os.path.join(os.path.dirname(os.path.dirname(HERE)), "sdnq_b200", "skip_keys.json")
+    with open(pkg, "w") as f:
+        json.dump({k: tables[k] for k in ("common_skip_keys", "models", "aliases")}, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    if os.environ.get("SDNQ_GOLDEN_POLICY_ONLY"):
+        dump_policy_tables()
+    else:
+        main()

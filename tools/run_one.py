@@ -1,0 +1,40 @@
+"""Run one kernel a few times (for ncu captures).  usage: python tools/run_one.py gemm M N K [int8|fp8] | actq M K | dequant N K wdtype gs"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from sdnq_b200 import ops
+
+kind = sys.argv[1]
+dev = "cuda"
+if kind == "gemm":
+    M, N, K = map(int, sys.argv[2:5])
+    fp8 = len(sys.argv) > 5 and sys.argv[5] == "fp8"
+    a = torch.randint(-128, 128, (M, K), dtype=torch.int8, device=dev)
+    b = torch.randint(-128, 128, (N, K), dtype=torch.int8, device=dev)
+    if fp8:
+        a = a.float().clamp(-8, 8).to(torch.float8_e4m3fn)
+        b = b.float().clamp(-8, 8).to(torch.float8_e4m3fn)
+    sx = torch.rand(M, device=dev) * 0.01
+    sw = torch.rand(N, device=dev) * 0.01
+    bias = torch.randn(N, device=dev, dtype=torch.bfloat16)
+    for _ in range(4):
+        ops.scaled_mm(a, b, sx, sw, bias, torch.bfloat16)
+elif kind == "actq":
+    M, K = map(int, sys.argv[2:4])
+    x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+    for _ in range(4):
+        ops.act_quant(x, "int8", hadamard_group=int(sys.argv[4]) if len(sys.argv) > 4 else 0)
+elif kind == "dequant":
+    N, K = map(int, sys.argv[2:4])
+    wd, gs = sys.argv[4], int(sys.argv[5])
+    from sdnq_b200.common import dtype_dict
+    bits = dtype_dict[wd]["num_bits"]
+    w = torch.randint(0, 256, (N * K * bits // 8,), dtype=torch.uint8, device=dev)
+    scale = torch.rand(N * (K // gs), device=dev) * 0.01
+    zp = torch.rand(N * (K // gs), device=dev) if dtype_dict[wd]["is_unsigned"] else None
+    for _ in range(4):
+        ops.dequant(w, wd, scale, zp, N, K, gs, torch.bfloat16)
+torch.cuda.synchronize()
