@@ -31,49 +31,175 @@ struct ActArgs {
     void* x_rot;
 };
 
-template <typename T, int WPR, int MAXC>
-__global__ void __launch_bounds__(kThreads) act_quant_kernel(const ActArgs a) {
+// A 256-chunk slice held between the statistics pass and the quantise pass: 8 values per lane, kept in the activation
+// dtype (they were rounded to it anyway) so a bf16 / f16 row costs 4 registers per chunk instead of 8.
+template <typename T> struct Held {
+    uint4 raw;
+    __device__ __forceinline__ void load(const T* p) { raw = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void zero() { raw = make_uint4(0u, 0u, 0u, 0u); }
+    __device__ __forceinline__ void put(const float (&v)[8]) {
+        uint32_t* w = reinterpret_cast<uint32_t*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if constexpr (sizeof(T) == 2 && ElemTraits<T>::kDtype == SDNQ_BF16) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                w[i] = *reinterpret_cast<uint32_t*>(&h);
+            } else {
+                __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+        }
+    }
+    __device__ __forceinline__ void get(float (&v)[8]) const {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if constexpr (ElemTraits<T>::kDtype == SDNQ_BF16) {
+                v[2 * i] = __uint_as_float(w[i] << 16);
+                v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+            } else {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                v[2 * i] = f.x;
+                v[2 * i + 1] = f.y;
+            }
+        }
+    }
+};
+template <> struct Held<float> {
+    float val[8];
+    __device__ __forceinline__ void load(const float* p) { load8<float>(p, val); }
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) val[i] = 0.f;
+    }
+    __device__ __forceinline__ void put(const float (&v)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) val[i] = v[i];
+    }
+    __device__ __forceinline__ void get(float (&v)[8]) const {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = val[i];
+    }
+};
+
+// Correctly rounded x / s with the reciprocal hoisted out of the element loop.  This is the fast path of nvcc's own
+// div.rn.f32 expansion (MUFU.RCP, one Newton step on the reciprocal, q0 = x*r, one residual correction), which is
+// correctly rounded whenever no intermediate under/overflows; rows whose scale is outside a generous normal range take
+// __fdiv_rn instead (kSafe = false instantiation of the quantise loop).  Codes are bit-identical to __fdiv_rn (tests).
+struct RowDivider {
+    float s, r;
+    __device__ __forceinline__ explicit RowDivider(float scale) : s(scale) {
+        float r0;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(scale));
+        const float e = fmaf(r0, -scale, 1.0f);
+        r = fmaf(r0, e, r0);
+    }
+    __device__ __forceinline__ bool safe() const { const float a = fabsf(s); return a > 1e-18f && a < 1e18f; }
+    template <bool kSafe>
+    __device__ __forceinline__ float div(float x) const {
+        if constexpr (kSafe) {
+            const float q0 = x * r;
+            const float rem = fmaf(q0, -s, x);
+            return fmaf(r, rem, q0);
+        } else {
+            return __fdiv_rn(x, s);
+        }
+    }
+};
+
+// 8 values -> 8 one-byte codes (packed in a uint2) for one lane
+template <int MODE, bool kSafe>
+__device__ __forceinline__ uint2 quantise8(const float (&v)[8], const RowDivider& d, float zero, bool want_sum, int& code_sum) {
+    uint2 r;
+    if constexpr (MODE == SDNQ_F8E4M3) {
+        uint16_t* h = reinterpret_cast<uint16_t*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float q0 = d.div<kSafe>(v[2 * i]), q1 = d.div<kSafe>(v[2 * i + 1]);
+            if constexpr (!kSafe) {                                   // nan_to_num (0/0 on an all-zero row)
+                if (q0 != q0) q0 = 0.f;
+                if (q1 != q1) q1 = 0.f;
+            }
+            // cvt.rn.satfinite.e4m3x2 saturates to +-448 = the reference's clamp_(-448, 448) before the cast
+            h[i] = static_cast<uint16_t>(__nv_cvt_float2_to_fp8x2(make_float2(q0, q1), __NV_SATFINITE, __NV_E4M3));
+        }
+    } else {
+        // round-to-nearest-even to s32 (NaN -> 0, as the reference's NaN -> int cast gives) then saturating pack to s8:
+        // == clamp(round(q), -128, 127).to(int8)                                                    (quant_utils.py:272)
+        int c[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float q = v[i];
+            if constexpr (MODE == SDNQ_U8) q = __fsub_rn(q, zero);
+            c[i] = __float2int_rn(d.div<kSafe>(q));
+        }
+        uint32_t lo, hi;
+        // cvt.pack.sat.s8.s32.b32 d, a, b, c :  d = (c << 16) | (sat8(a) << 8) | sat8(b)
+        asm("{\n\t.reg .b32 t;\n\tcvt.pack.sat.s8.s32.b32 t, %4, %3, 0;\n\tcvt.pack.sat.s8.s32.b32 %0, %2, %1, t;\n\t}"
+            : "=r"(lo) : "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
+        asm("{\n\t.reg .b32 t;\n\tcvt.pack.sat.s8.s32.b32 t, %4, %3, 0;\n\tcvt.pack.sat.s8.s32.b32 %0, %2, %1, t;\n\t}"
+            : "=r"(hi) : "r"(c[4]), "r"(c[5]), "r"(c[6]), "r"(c[7]));
+        r.x = lo;
+        r.y = hi;
+        if (want_sum) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) code_sum += max(-128, min(127, c[i]));
+        }
+    }
+    return r;
+}
+
+template <typename T, int WPR, int MAXC, int MODE>
+__global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? 6 : 3) act_quant_kernel(const ActArgs a) {
     constexpr int RPC = kWarps / WPR;                 // rows per CTA
     __shared__ float s_a[RPC][WPR];
     __shared__ float s_b[RPC][WPR];
     __shared__ int s_sum[RPC][WPR];
+    pdl_launch_dependents();      // the GEMM behind us may start its prologue / weight prefetch now
+    pdl_wait();                   // x (and the workspace we overwrite) belong to the stream predecessor
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r_in = warp / WPR, w_in = warp % WPR;
     const int64_t row = int64_t(blockIdx.x) * RPC + r_in;
     const bool row_ok = row < a.M;
     const T* xrow = reinterpret_cast<const T*>(a.x) + row * a.ldx;
+    const int K = static_cast<int>(a.K);
 
-    float v[MAXC][8];
+    Held<T> held[MAXC];
+    // all loads of the row first (memory-level parallelism), statistics afterwards
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int k = (c * WPR + w_in) * 256 + lane * 8;
+        if (row_ok && k < K) held[c].load(xrow + k);
+        else held[c].zero();
+    }
     float amax = 0.f, vmax = -INFINITY, vmin = INFINITY;
     const float hfac = a.hadamard ? hadamard_factor<T>(a.hadamard) : 1.f;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
-        const int64_t k0 = (int64_t(c) * WPR + w_in) * 256;          // chunk start (warp-uniform)
-        const int64_t k = k0 + lane * 8;
-        const bool ok = row_ok && k < a.K;
-        if (ok) {
-            load8<T>(xrow + k, v[c]);
-        } else {
+        const int k0 = (c * WPR + w_in) * 256;          // chunk start (warp-uniform)
+        const bool ok = row_ok && k0 + lane * 8 < K;
+        float v[8];
+        held[c].get(v);
+        if (a.hadamard && k0 < K) {
+            hadamard_warp_dyn(a.hadamard, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[c][i] = 0.f;
-        }
-        if (a.hadamard && k0 < a.K) {
-            hadamard_warp_dyn(a.hadamard, v[c]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[c][i] = ElemTraits<T>::round(v[c][i] * hfac);   // result of the matmul is in x.dtype
+            for (int i = 0; i < 8; ++i) v[i] = v[i] * hfac;   // put() rounds to x.dtype: the reference's matmul returns x.dtype
+            held[c].put(v);
+            held[c].get(v);
         }
         if (ok) {
+            if constexpr (MODE == SDNQ_U8) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                amax = fmaxf(amax, fabsf(v[c][i]));
-                vmax = fmaxf(vmax, v[c][i]);
-                vmin = fminf(vmin, v[c][i]);
+                for (int i = 0; i < 8; ++i) { vmax = fmaxf(vmax, v[i]); vmin = fminf(vmin, v[i]); }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[i]));
             }
         }
     }
     // ---- row statistics
     float scale, zero = 0.f;
-    if (a.mode == SDNQ_U8) {
+    if constexpr (MODE == SDNQ_U8) {
         vmax = warp_max(vmax);
         vmin = warp_min(vmin);
         if (WPR > 1) {
@@ -92,32 +218,21 @@ __global__ void __launch_bounds__(kThreads) act_quant_kernel(const ActArgs a) {
 #pragma unroll
             for (int i = 0; i < WPR; ++i) amax = fmaxf(amax, s_a[r_in][i]);
         }
-        scale = __fdiv_rn(amax, a.mode == SDNQ_F8E4M3 ? 448.f : 127.f);  // get_scale_symmetric
+        scale = __fdiv_rn(amax, MODE == SDNQ_F8E4M3 ? 448.f : 127.f);    // get_scale_symmetric
     }
+    const RowDivider divider(scale);
+    const bool safe = divider.safe();                                    // uniform across the row (and the warp)
     // ---- quantise from registers
     int local_sum = 0;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
-        const int64_t k = (int64_t(c) * WPR + w_in) * 256 + lane * 8;
-        if (!(row_ok && k < a.K)) continue;
-        if (a.x_rot != nullptr) store8<T>(reinterpret_cast<T*>(a.x_rot) + row * a.K + k, v[c]);
-        uint2 r;
-        uint8_t* b = reinterpret_cast<uint8_t*>(&r);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float q = v[c][i];
-            if (a.mode == SDNQ_U8) q = __fsub_rn(q, zero);
-            q = __fdiv_rn(q, scale);
-            if (a.mode == SDNQ_F8E4M3) {
-                if (q != q) q = 0.f;                                     // nan_to_num
-                b[i] = f32_to_e4m3(fminf(fmaxf(q, -448.f), 448.f));
-            } else {
-                q = rintf(q);
-                const int ci = (q != q) ? 0 : static_cast<int>(fminf(fmaxf(q, -128.f), 127.f));
-                b[i] = static_cast<uint8_t>(static_cast<int8_t>(ci));
-                local_sum += ci;
-            }
-        }
+        const int k = (c * WPR + w_in) * 256 + lane * 8;
+        if (!(row_ok && k < K)) continue;
+        float v[8];
+        held[c].get(v);
+        if (a.x_rot != nullptr) store8<T>(reinterpret_cast<T*>(a.x_rot) + row * a.K + k, v);
+        const bool want_sum = a.rowsum != nullptr;
+        const uint2 r = safe ? quantise8<MODE, true>(v, divider, zero, want_sum, local_sum) : quantise8<MODE, false>(v, divider, zero, want_sum, local_sum);
         *reinterpret_cast<uint2*>(a.xq + row * a.K + k) = r;
     }
     if (a.rowsum != nullptr) {
@@ -141,7 +256,11 @@ template <typename T, int WPR, int MAXC>
 int launch(const ActArgs& a, cudaStream_t st) {
     constexpr int RPC = kWarps / WPR;
     const unsigned blocks = static_cast<unsigned>((a.M + RPC - 1) / RPC);
-    act_quant_kernel<T, WPR, MAXC><<<blocks, kThreads, 0, st>>>(a);
+    cudaError_t e;
+    if (a.mode == SDNQ_I8) e = launch_pdl(act_quant_kernel<T, WPR, MAXC, SDNQ_I8>, dim3(blocks), dim3(kThreads), 0, st, a);
+    else if (a.mode == SDNQ_U8) e = launch_pdl(act_quant_kernel<T, WPR, MAXC, SDNQ_U8>, dim3(blocks), dim3(kThreads), 0, st, a);
+    else e = launch_pdl(act_quant_kernel<T, WPR, MAXC, SDNQ_F8E4M3>, dim3(blocks), dim3(kThreads), 0, st, a);
+    if (e != cudaSuccess) return set_error(SDNQ_ECUDA, "launch of act_quant_kernel failed: %s", cudaGetErrorString(e));
     return check_launch("act_quant_kernel");
 }
 

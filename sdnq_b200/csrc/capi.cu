@@ -1,5 +1,6 @@
 // Library-level pieces of the C ABI: error reporting, device checks, launch accounting and the fused
 // W8A8 Linear entry point (K2 + K1 on one stream with a caller-owned workspace).
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -20,6 +21,14 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches += n; }
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("SDNQ_B200_PDL");
+        return !(e && (e[0] == '0' || e[0] == 'n' || e[0] == 'N' || e[0] == 'f' || e[0] == 'F'));
+    }();
+    return on;
+}
 
 int num_sms() {
     static thread_local int cached_dev = -1;

@@ -33,6 +33,9 @@ struct DequantArgs {
     const void* down; int64_t down_sr, down_sk;
     int rank; int svd_dtype;
     int hadamard;
+    // 32-bit copies for the hot kernel (N*K < 2^31 elements is enforced on the host)
+    int K32, group32, group_shift;   // group_shift >= 0 when the group size is a power of two
+    int gpr32, row_stride32;
 };
 
 __device__ __forceinline__ float load_any(const void* p, int64_t i, int dtype) {
@@ -46,16 +49,16 @@ __device__ __forceinline__ float round_any(float v, int dtype) {
     return v;
 }
 
-// unpack + scale (+ zero point | codebook) of the octet starting at (row n, column k): f32 values, reference op order
-template <int BITS>
-__device__ __forceinline__ void dequant_octet(const DequantArgs& a, int64_t n, int64_t k, float (&w)[8]) {
-    uint32_t codes[8];
-    float q[8];
-    const int64_t oct = (n * a.K + k) >> 3;
-    octet_values<BITS>(a.weight, oct, a.f, q, codes);
-    if ((a.group & 7) == 0 || a.group >= a.K) {
-        const int64_t g = (a.groups_per_row > 0) ? (k / a.group) : 0;
-        const int64_t si = n * a.scale_row_stride + g;
+__device__ __forceinline__ int group_of(const DequantArgs& a, int k) {
+    if (a.gpr32 <= 1) return 0;
+    return a.group_shift >= 0 ? (k >> a.group_shift) : static_cast<int>(static_cast<uint32_t>(k) / static_cast<uint32_t>(a.group32));
+}
+
+// scale (+ zero point | codebook) of the octet starting at (row n, column k): f32 values, reference op order
+__device__ __forceinline__ void scale_octet(const DequantArgs& a, int n, int k, const float (&q)[8], const uint32_t (&codes)[8],
+                                            float (&w)[8]) {
+    if ((a.group32 & 7) == 0 || a.group32 >= a.K32) {
+        const int64_t si = int64_t(n) * a.row_stride32 + group_of(a, k);
         if (a.codebook) {
             const float* lv = a.scale + si * (int64_t(1) << a.f.bits);
 #pragma unroll
@@ -74,7 +77,7 @@ __device__ __forceinline__ void dequant_octet(const DequantArgs& a, int64_t n, i
     } else {   // group sizes that are not a multiple of 8: per-element scale lookup
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int64_t si = n * a.scale_row_stride + (k + i) / a.group;
+            const int64_t si = int64_t(n) * a.row_stride32 + group_of(a, k + i);
             if (a.codebook) w[i] = a.scale[si * (int64_t(1) << a.f.bits) + codes[i]];
             else if (a.zp != nullptr) w[i] = fmaf(q[i], a.scale[si], a.zp[si]);
             else w[i] = __fmul_rn(q[i], a.scale[si]);
@@ -82,53 +85,163 @@ __device__ __forceinline__ void dequant_octet(const DequantArgs& a, int64_t n, i
     }
 }
 
+// unpack + scale of one octet (used by the re-quantise kernel)
+template <int BITS>
+__device__ __forceinline__ void dequant_octet(const DequantArgs& a, int64_t n, int64_t k, float (&w)[8]) {
+    uint32_t codes[8];
+    float q[8];
+    octet_values<BITS>(a.weight, (n * a.K + k) >> 3, a.f, q, codes);
+    scale_octet(a, static_cast<int>(n), static_cast<int>(k), q, codes, w);
+}
+
 // ------------------------------------------------------------------------------------------------ K3
-// grid: (N, ceil(K / (256 * kWarps * ITERS))); each warp walks 256-element chunks of row blockIdx.x.
-template <int BITS, typename OutT, int ITERS>
-__global__ void __launch_bounds__(kThreads) dequant_kernel(const DequantArgs a, OutT* __restrict__ out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t n = blockIdx.x;
-    const int64_t k_cta = int64_t(blockIdx.y) * (256 * kWarps * ITERS);
-    extern __shared__ float s_up[];   // [rank] svd_up row n as f32
-    if (a.up != nullptr) {
-        for (int j = threadIdx.x; j < a.rank; j += kThreads) s_up[j] = load_any(a.up, n * a.up_sn + j * a.up_sr, a.svd_dtype);
-        __syncthreads();
-    }
+// Work unit = one warp x one 256-element chunk of one row (lane l owns the octet at column 256*c + 8*l).  A warp walks
+// chunks with a grid stride and keeps U chunks in flight: all U packed-byte loads are issued before any of them is used,
+// which is what the kernel needs to cover HBM latency (it has no reuse, so memory-level parallelism is the only lever:
+// ~2k threads/SM x U independent loads).  Reads: 32*bits contiguous bytes per warp per chunk; writes: 512 contiguous
+// bytes of bf16 per warp per chunk (one 16 B store per lane).
+template <int BITS, typename OutT, int U, bool kPlain>
+__global__ void __launch_bounds__(kThreads, kPlain ? 5 : 3) dequant_kernel(const DequantArgs a, OutT* __restrict__ out, int chunks_per_row, int total_chunks) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const int warps_total = gridDim.x * kWarps;
+    for (int t0 = warp_global; t0 < total_chunks; t0 += warps_total * U) {
+        int n[U], k[U];
+        bool live[U], valid[U];
+        uint32_t raw[U][OctetWords<BITS>::N];
 #pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-        const int64_t k = k_cta + (int64_t(it) * kWarps + warp) * 256 + lane * 8;
-        const bool valid = k < a.K;
-        if (!a.hadamard && !valid) continue;
-        if (a.hadamard && k - lane * 8 >= a.K) continue;   // whole chunk out of range (warp-uniform)
-        float w[8];
-        if (valid) {
-            dequant_octet<BITS>(a, n, k, w);
-            if (a.up != nullptr) {
-                // result.to(svd dtype).addmm_(svd_up, svd_down): f32 accumulate, one rounding (dequantizer.py:69-79)
-                float acc[8];
+        for (int u = 0; u < U; ++u) {
+            const int t = t0 + u * warps_total;
+            live[u] = t < total_chunks;                               // warp-uniform
+            n[u] = live[u] ? static_cast<int>(static_cast<uint32_t>(t) / static_cast<uint32_t>(chunks_per_row)) : 0;
+            k[u] = live[u] ? (t - n[u] * chunks_per_row) * 256 + lane * 8 : 0;
+            valid[u] = live[u] && k[u] < a.K32;
+            if (valid[u]) load_octet_bytes<BITS>(a.weight, (int64_t(n[u]) * a.K32 + k[u]) >> 3, a.f.word_bytes, raw[u]);
+        }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = round_any(w[i], a.svd_dtype);
-                for (int j = 0; j < a.rank; ++j) {
-                    const float u = s_up[j];
+        for (int u = 0; u < U; ++u) {
+            if (!live[u]) continue;
+            float w[8];
+            if (valid[u]) {
+                uint32_t codes[8];
+                float q[8];
+                decode_octet<BITS>(raw[u], codes);
+                codes_to_values<BITS>(codes, a.f, q);
+                scale_octet(a, n[u], k[u], q, codes, w);
+                if constexpr (!kPlain) {
+                    if (a.up != nullptr) {
+                        // result.to(svd dtype).addmm_(svd_up, svd_down): f32 accumulate, one rounding (dequantizer.py:69-79)
+                        float acc[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[i] = fmaf(u, load_any(a.down, j * a.down_sr + (k + i) * a.down_sk, a.svd_dtype), acc[i]);
+                        for (int i = 0; i < 8; ++i) acc[i] = round_any(w[i], a.svd_dtype);
+                        for (int j = 0; j < a.rank; ++j) {
+                            const float uj = load_any(a.up, int64_t(n[u]) * a.up_sn + j * a.up_sr, a.svd_dtype);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                acc[i] = fmaf(uj, load_any(a.down, j * a.down_sr + int64_t(k[u] + i) * a.down_sk, a.svd_dtype), acc[i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) w[i] = round_any(acc[i], a.svd_dtype);
+                    }
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) w[i] = round_any(acc[i], a.svd_dtype);
+                for (int i = 0; i < 8; ++i) w[i] = ElemTraits<OutT>::round(w[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = 0.f;
             }
+            if constexpr (!kPlain) {
+                if (a.hadamard) {   // un-rotate in the result dtype (dequantizer.py:82-83); whole warp participates
+                    hadamard_warp_dyn(a.hadamard, w);
+                    const float h = hadamard_factor<OutT>(a.hadamard);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = ElemTraits<OutT>::round(w[i]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = 0.f;
+                    for (int i = 0; i < 8; ++i) w[i] = w[i] * h;
+                }
+            }
+            if (valid[u]) store8<OutT>(out + int64_t(n[u]) * a.K32 + k[u], w);
         }
-        if (a.hadamard) {   // un-rotate in the result dtype (dequantizer.py:82-83)
-            hadamard_warp_dyn(a.hadamard, w);
-            const float h = hadamard_factor<OutT>(a.hadamard);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K3 fast path
+// Integer formats (int/uint 1..8 bit), one scale (and zero point) per octet, no codebook / SVD / Hadamard: everything that can
+// be decided at compile time is.  Each warp streams a contiguous run of 256-element chunks (row / column advance
+// incrementally: one integer division per warp, none per chunk) with U chunks in flight; int4 and int8 go from storage
+// word to float with one PRMT per element (byte -> 0x4B0000bb = 2^23 + b, then one FADD), so the kernel sits at ~7 SASS
+// instructions per element and 40 registers (6 CTAs / SM).
+template <int BITS>
+__device__ __forceinline__ void octet_to_floats(const uint32_t (&w)[OctetWords<BITS>::N], uint32_t flip, float bias, float (&q)[8]) {
+    if constexpr (BITS == 4) {
+        const uint32_t lo = w[0] & 0x0F0F0F0Fu, hi = (w[0] >> 4) & 0x0F0F0F0Fu;       // even / odd nibbles, one per byte
 #pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = w[i] * h;
+        for (int i = 0; i < 4; ++i) {
+            q[2 * i] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7440 | i)) - bias;
+            q[2 * i + 1] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7440 | i)) - bias;
         }
-        if (valid) store8<OutT>(out + n * a.K + k, w);
+    } else if constexpr (BITS == 8) {
+        const uint32_t a = w[0] ^ flip, b = w[1] ^ flip;                              // flip = 0x80808080 for two's complement bytes
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            q[i] = __uint_as_float(__byte_perm(a, 0x4B000000u, 0x7440 | i)) - bias;
+            q[4 + i] = __uint_as_float(__byte_perm(b, 0x4B000000u, 0x7440 | i)) - bias;
+        }
+    } else {
+        uint32_t codes[8];
+        decode_octet<BITS>(w, codes);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = __uint_as_float(0x4B000000u | codes[i]) - bias;
+    }
+}
+
+template <int BITS, bool kZP, bool kPow2, typename OutT, int U>
+__global__ void __launch_bounds__(kThreads, 6) dequant_int_kernel(const DequantArgs a, OutT* __restrict__ out, int cpr, int total_chunks) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const int warps_total = gridDim.x * kWarps;
+    const bool twos = (BITS == 8 && !a.f.is_unsigned);
+    const float bias = twos ? 8388736.0f : 8388608.0f - static_cast<float>(a.f.int_offset);
+    const uint32_t flip = twos ? 0x80808080u : 0u;
+    const int per_warp = (total_chunks + warps_total - 1) / warps_total;
+    int t = warp_global * per_warp;
+    const int t_end = min(t + per_warp, total_chunks);
+    if (t >= t_end) return;
+    int n = static_cast<int>(static_cast<uint32_t>(t) / static_cast<uint32_t>(cpr));
+    int c = t - n * cpr;
+    const int K = a.K32, wb = a.f.word_bytes;
+    for (; t < t_end; t += U) {
+        int nn[U], kk[U];
+        bool valid[U];
+        uint32_t raw[U][OctetWords<BITS>::N];
+        float sc[U], zp[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            nn[u] = n;
+            kk[u] = c * 256 + lane * 8;
+            valid[u] = (t + u < t_end) && kk[u] < K;
+            if (++c == cpr) { c = 0; ++n; }
+            sc[u] = zp[u] = 0.f;
+            if (valid[u]) {
+                const uint32_t e = static_cast<uint32_t>(nn[u]) * static_cast<uint32_t>(K) + static_cast<uint32_t>(kk[u]);   // < 2^31
+                load_octet_bytes<BITS>(a.weight, e >> 3, wb, raw[u]);
+                const int g = a.gpr32 <= 1 ? 0 : (kPow2 ? (kk[u] >> a.group_shift) : static_cast<int>(static_cast<uint32_t>(kk[u]) / static_cast<uint32_t>(a.group32)));
+                const uint32_t si = static_cast<uint32_t>(nn[u]) * static_cast<uint32_t>(a.row_stride32) + g;
+                sc[u] = a.scale[si];
+                if constexpr (kZP) zp[u] = a.zp[si];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!valid[u]) continue;
+            float q[8], w[8];
+            octet_to_floats<BITS>(raw[u], flip, bias, q);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = kZP ? fmaf(q[i], sc[u], zp[u]) : __fmul_rn(q[i], sc[u]);
+            store8<OutT>(out + (static_cast<uint32_t>(nn[u]) * static_cast<uint32_t>(K) + static_cast<uint32_t>(kk[u])), w);
+        }
     }
 }
 
@@ -136,6 +249,8 @@ __global__ void __launch_bounds__(kThreads) dequant_kernel(const DequantArgs a, 
 template <int BITS>
 __global__ void __launch_bounds__(kThreads) unpack_kernel(const uint8_t* __restrict__ packed, WFormat f, void* __restrict__ out,
                                                           int out_dtype, int64_t octets) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t oct = int64_t(blockIdx.x) * kThreads + threadIdx.x;
     if (oct >= octets) return;
     uint32_t codes[8];
@@ -198,6 +313,8 @@ __global__ void __launch_bounds__(kThreads) requant_kernel(const DequantArgs a, 
                                                            int32_t* __restrict__ colsum) {
     __shared__ float s_red[kWarps];
     __shared__ int s_sum[kWarps];
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t n = blockIdx.x;
     float w[kRequantMaxOct][8];
     float vmax = -INFINITY, vmin = INFINITY, amax = 0.f;
@@ -290,6 +407,16 @@ int fill_args(DequantArgs& a, const void* weight, const sdnq_weight_format* fmt,
         a.group = group_size; a.groups_per_row = K / group_size; a.scale_row_stride = K / group_size;
     }
     if (codebook) SDNQ_REQUIRE(a.f.kind == SDNQ_W_INT && a.f.is_unsigned, SDNQ_EINVAL, "codebook needs an unsigned integer format");
+    SDNQ_REQUIRE(N * K < (int64_t(1) << 31), SDNQ_EUNSUPPORTED, "weights with 2^31 or more elements are not supported (N=%lld K=%lld)", (long long)N, (long long)K);
+    a.K32 = static_cast<int>(K);
+    a.group32 = static_cast<int>(a.group);
+    a.group_shift = -1;
+    if ((a.group32 & (a.group32 - 1)) == 0) {
+        a.group_shift = 0;
+        while ((1 << a.group_shift) < a.group32) ++a.group_shift;
+    }
+    a.gpr32 = static_cast<int>(a.groups_per_row);
+    a.row_stride32 = static_cast<int>(a.scale_row_stride);
     a.up = a.down = nullptr;
     a.up_sn = a.up_sr = a.down_sr = a.down_sk = 0;
     a.rank = 0; a.svd_dtype = SDNQ_BF16; a.hadamard = 0;
@@ -302,10 +429,31 @@ bool hadamard_ok(int g) { return g == 0 || (g >= 4 && g <= 256 && (g & (g - 1)) 
 
 template <typename OutT>
 static int launch_dequant(const DequantArgs& a, void* out, cudaStream_t st) {
-    constexpr int ITERS = 2;
-    dim3 grid(static_cast<unsigned>(a.N), static_cast<unsigned>((a.K + 256 * kWarps * ITERS - 1) / (256 * kWarps * ITERS)));
-    const size_t smem = a.up ? sizeof(float) * a.rank : 0;
-    SDNQ_DISPATCH_BITS(a.f.bits, (dequant_kernel<BITS, OutT, ITERS><<<grid, kThreads, smem, st>>>(a, reinterpret_cast<OutT*>(out))));
+    constexpr int U = 4;
+    const int64_t cpr64 = (a.K + 255) / 256, total64 = a.N * cpr64;
+    SDNQ_REQUIRE(total64 < (int64_t(1) << 30), SDNQ_EUNSUPPORTED, "weight too large");
+    const int cpr = static_cast<int>(cpr64), total = static_cast<int>(total64);
+    const int64_t want = (total64 + int64_t(kWarps) * U - 1) / (int64_t(kWarps) * U);
+    const int64_t cap = int64_t(num_sms()) * 16;
+    const unsigned grid = static_cast<unsigned>(want < cap ? (want > 0 ? want : 1) : cap);
+    const bool plain = a.up == nullptr && a.hadamard == 0;
+    cudaError_t e = cudaSuccess;
+    const bool fast_int = plain && a.f.kind == SDNQ_W_INT && !a.codebook && ((a.group32 & 7) == 0 || a.group32 >= a.K32);
+    if (fast_int) {
+        const bool pow2 = a.group_shift >= 0;
+        if (a.zp != nullptr) {
+            if (pow2) { SDNQ_DISPATCH_BITS(a.f.bits, (e = launch_pdl(dequant_int_kernel<BITS, true, true, OutT, U>, dim3(grid), dim3(kThreads), 0, st, a, reinterpret_cast<OutT*>(out), cpr, total))); }
+            else { SDNQ_DISPATCH_BITS(a.f.bits, (e = launch_pdl(dequant_int_kernel<BITS, true, false, OutT, U>, dim3(grid), dim3(kThreads), 0, st, a, reinterpret_cast<OutT*>(out), cpr, total))); }
+        } else {
+            if (pow2) { SDNQ_DISPATCH_BITS(a.f.bits, (e = launch_pdl(dequant_int_kernel<BITS, false, true, OutT, U>, dim3(grid), dim3(kThreads), 0, st, a, reinterpret_cast<OutT*>(out), cpr, total))); }
+            else { SDNQ_DISPATCH_BITS(a.f.bits, (e = launch_pdl(dequant_int_kernel<BITS, false, false, OutT, U>, dim3(grid), dim3(kThreads), 0, st, a, reinterpret_cast<OutT*>(out), cpr, total))); }
+        }
+    } else if (plain) {
+        SDNQ_DISPATCH_BITS(a.f.bits, (e = launch_pdl(dequant_kernel<BITS, OutT, U, true>, dim3(grid), dim3(kThreads), 0, st, a, reinterpret_cast<OutT*>(out), cpr, total)));
+    } else {
+        SDNQ_DISPATCH_BITS(a.f.bits, (e = launch_pdl(dequant_kernel<BITS, OutT, U, false>, dim3(grid), dim3(kThreads), 0, st, a, reinterpret_cast<OutT*>(out), cpr, total)));
+    }
+    if (e != cudaSuccess) return set_error(SDNQ_ECUDA, "launch of dequant_kernel failed: %s", cudaGetErrorString(e));
     return check_launch("dequant_kernel");
 }
 

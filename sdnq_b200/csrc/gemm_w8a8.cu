@@ -126,15 +126,36 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_launch_dependents();     // our own dependents may begin their prologue
 
     if (warp == 0) {
         // ======================================================== TMA producer
         if (lane == 0) {
+            // The weight operand never depends on the stream predecessor (weights are frozen), the activations do: start
+            // the first ring-full of B tiles now, then wait for the predecessor (the activation quantiser) and add the A tiles.
+            const int tile0 = blockIdx.x;
+            const int npre = (tile0 < num_tiles) ? (num_kb < C::kStages ? num_kb : C::kStages) : 0;
+            if (npre > 0) {
+                const int n0 = (tile0 % num_n) * BN;
+                for (int s = 0; s < npre; ++s) {
+                    ptx::mbar_arrive_expect_tx(full_bar(s), C::kStageBytes);
+                    ptx::tma_load_2d(smem_b + s * C::kStageB, &tmap_b, full_bar(s), s * BK, n0);
+                }
+            }
+            pdl_wait();
+            if (npre > 0) {
+                const int m0 = (tile0 / num_n) * BM;
+                for (int s = 0; s < npre; ++s) ptx::tma_load_2d(smem_a + s * C::kStageA, &tmap_a, full_bar(s), s * BK, m0);
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
+                    if (tile == tile0 && kb < npre) {             // already in flight (prefetched above)
+                        if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
                     ptx::mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
                     ptx::tma_load_2d(smem_a + stage * C::kStageA, &tmap_a, full_bar(stage), kb * BK, m0);
@@ -146,6 +167,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else if (warp == 1) {
         // ======================================================== MMA issuer
         if (lane == 0) {
+            pdl_wait();
             constexpr uint32_t idesc = kInt8 ? ptx::make_idesc(2, 1, 1, BM, BN) : ptx::make_idesc(1, 0, 0, BM, BN);
             int stage = 0;
             uint32_t phase = 0;
@@ -178,6 +200,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // TMEM lane = output row.  Each warp turns its 32 rows x CPB columns into one 32 x 128 B block in shared
         // memory (128 B swizzle, conflict-free 16 B stores) and hands it to a TMA store, which clips the M / N tails
         // and writes full lines; a 2-deep ring per warp overlaps the store with the next block's math.
+        pdl_wait();                                               // sx / rowsum / bias may come from the predecessor
         const int q = warp & 3;                                   // TMEM lane quarter this warp may access
         const uint32_t my_o = smem_o + uint32_t(warp - 2) * (kStoreBufs * kStoreBlkBytes);
         int it = 0, blk = 0;
@@ -420,7 +443,8 @@ int launch_gemm(const void* a, const void* b, const GemmParams& p, cudaStream_t 
     if (rc != SDNQ_OK) return rc;
     const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_w8a8_kernel<BN, kInt8, OUT, kSimple><<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, to, p);
+    cudaError_t e = launch_pdl(gemm_w8a8_kernel<BN, kInt8, OUT, kSimple>, dim3(grid), dim3(kThreads), C::kSmemBytes, st, ta, tb, to, p);
+    if (e != cudaSuccess) return set_error(SDNQ_ECUDA, "launch of gemm_w8a8_kernel failed: %s", cudaGetErrorString(e));
     return check_launch("gemm_w8a8_kernel");
 }
 

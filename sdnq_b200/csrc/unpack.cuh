@@ -49,78 +49,83 @@ inline int make_wformat(const sdnq_weight_format* f, WFormat* out) {
     return SDNQ_OK;
 }
 
-// ---- read the `BITS` storage bytes of octet `oct` (octets are numbered along the flattened tensor)
+// ---- read the `BITS` storage bytes of octet `oct` (octets are numbered along the flattened tensor) as packed
+// little-endian 32-bit words (byte i of the octet = bits [8i, 8i+8) of the word array); widest aligned loads possible
+template <int BITS> struct OctetWords { static constexpr int N = (BITS + 3) / 4; };
+
 template <int BITS>
 __device__ __forceinline__ void load_octet_bytes(const uint8_t* __restrict__ base, int64_t oct, int word_bytes,
-                                                 uint32_t (&b)[BITS]) {
+                                                 uint32_t (&w)[OctetWords<BITS>::N]) {
     if constexpr (BITS == 8) {
         const uint2 r = *reinterpret_cast<const uint2*>(base + oct * 8);
-        b[0] = r.x & 0xFF; b[1] = (r.x >> 8) & 0xFF; b[2] = (r.x >> 16) & 0xFF; b[3] = r.x >> 24;
-        b[4] = r.y & 0xFF; b[5] = (r.y >> 8) & 0xFF; b[6] = (r.y >> 16) & 0xFF; b[7] = r.y >> 24;
+        w[0] = r.x; w[1] = r.y;
     } else if constexpr (BITS == 4) {
-        const uint32_t r = *reinterpret_cast<const uint32_t*>(base + oct * 4);
-        b[0] = r & 0xFF; b[1] = (r >> 8) & 0xFF; b[2] = (r >> 16) & 0xFF; b[3] = r >> 24;
+        w[0] = *reinterpret_cast<const uint32_t*>(base + oct * 4);
     } else if constexpr (BITS == 2) {
-        const uint16_t r = *reinterpret_cast<const uint16_t*>(base + oct * 2);
-        b[0] = r & 0xFF; b[1] = r >> 8;
+        w[0] = *reinterpret_cast<const uint16_t*>(base + oct * 2);
     } else if constexpr (BITS == 1) {
-        b[0] = base[oct * word_bytes];   // little-endian low byte of the int64 word when word_bytes == 8
-    } else {
+        w[0] = base[oct * word_bytes];   // little-endian low byte of the int64 word when word_bytes == 8
+    } else if constexpr (BITS == 6) {    // 6 bytes, 2-byte aligned
+        const uint16_t* p = reinterpret_cast<const uint16_t*>(base + oct * 6);
+        w[0] = uint32_t(p[0]) | (uint32_t(p[1]) << 16);
+        w[1] = p[2];
+    } else {                             // 3, 5, 7 bytes at an odd offset: byte loads
         const uint8_t* p = base + oct * BITS;
 #pragma unroll
-        for (int i = 0; i < BITS; ++i) b[i] = p[i];
+        for (int i = 0; i < OctetWords<BITS>::N; ++i) w[i] = 0;
+#pragma unroll
+        for (int i = 0; i < BITS; ++i) w[i >> 2] |= uint32_t(p[i]) << (8 * (i & 3));
     }
 }
 
+template <int NW>
+__device__ __forceinline__ uint32_t octet_byte(const uint32_t (&w)[NW], int i) { return (w[i >> 2] >> (8 * (i & 3))) & 0xFFu; }
+
 // ---- storage bytes of one octet -> 8 unsigned codes
 template <int BITS>
-__device__ __forceinline__ void decode_octet(const uint32_t (&b)[BITS], uint32_t (&v)[8]) {
+__device__ __forceinline__ void decode_octet(const uint32_t (&w)[OctetWords<BITS>::N], uint32_t (&v)[8]) {
     if constexpr (BITS == 8) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = b[i];
+        for (int i = 0; i < 8; ++i) v[i] = octet_byte(w, i);
     } else if constexpr (BITS == 7) {   // b_i = v_i | ((v7 << (i+1)) & 0x80)
         uint32_t top = 0;
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
-            v[i] = b[i] & 0x7F;
-            top |= (b[i] >> 7) << (6 - i);
+            const uint32_t b = octet_byte(w, i);
+            v[i] = b & 0x7F;
+            top |= (b >> 7) << (6 - i);
         }
         v[7] = top;
     } else if constexpr (BITS == 6) {   // two groups: 4 values <- 3 bytes, b_i = v_i | ((v3 << 2(i+1)) & 0xC0)
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-            const uint32_t b0 = b[3 * g], b1 = b[3 * g + 1], b2 = b[3 * g + 2];
+            const uint32_t b0 = octet_byte(w, 3 * g), b1 = octet_byte(w, 3 * g + 1), b2 = octet_byte(w, 3 * g + 2);
             v[4 * g] = b0 & 0x3F;
             v[4 * g + 1] = b1 & 0x3F;
             v[4 * g + 2] = b2 & 0x3F;
             v[4 * g + 3] = ((b0 >> 6) << 4) | ((b1 >> 6) << 2) | (b2 >> 6);
         }
     } else if constexpr (BITS == 5) {
+        const uint32_t b0 = octet_byte(w, 0), b1 = octet_byte(w, 1), b2 = octet_byte(w, 2), b3 = octet_byte(w, 3), b4 = octet_byte(w, 4);
+        v[0] = b0 & 0x1F; v[1] = b1 & 0x1F; v[2] = b2 & 0x1F; v[3] = b3 & 0x1F; v[4] = b4 & 0x1F;
+        v[5] = (b0 >> 5) | (((b3 >> 5) & 3) << 3);
+        v[6] = (b1 >> 5) | (((b4 >> 5) & 3) << 3);
+        v[7] = (b2 >> 5) | ((b4 >> 7) << 3) | ((b3 >> 7) << 4);
+    } else if constexpr (BITS == 4) {   // 4 bytes, two values each: b = v0 | v1 << 4  ==  nibble i of the word
 #pragma unroll
-        for (int i = 0; i < 5; ++i) v[i] = b[i] & 0x1F;
-        v[5] = (b[0] >> 5) | (((b[3] >> 5) & 3) << 3);
-        v[6] = (b[1] >> 5) | (((b[4] >> 5) & 3) << 3);
-        v[7] = (b[2] >> 5) | ((b[4] >> 7) << 3) | ((b[3] >> 7) << 4);
-    } else if constexpr (BITS == 4) {   // 4 bytes, two values each: b = v0 | v1 << 4
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            v[2 * i] = b[i] & 0xF;
-            v[2 * i + 1] = b[i] >> 4;
-        }
+        for (int i = 0; i < 8; ++i) v[i] = (w[0] >> (4 * i)) & 0xF;
     } else if constexpr (BITS == 3) {
-        v[0] = b[0] & 7; v[1] = b[1] & 7; v[2] = b[2] & 7;
-        v[3] = (b[0] >> 3) & 7; v[4] = (b[1] >> 3) & 7; v[5] = (b[2] >> 3) & 7;
-        v[6] = (b[0] >> 6) | (((b[2] >> 6) & 1) << 2);
-        v[7] = (b[1] >> 6) | ((b[2] >> 7) << 2);
-    } else if constexpr (BITS == 2) {   // 2 bytes, four values each
+        const uint32_t b0 = octet_byte(w, 0), b1 = octet_byte(w, 1), b2 = octet_byte(w, 2);
+        v[0] = b0 & 7; v[1] = b1 & 7; v[2] = b2 & 7;
+        v[3] = (b0 >> 3) & 7; v[4] = (b1 >> 3) & 7; v[5] = (b2 >> 3) & 7;
+        v[6] = (b0 >> 6) | (((b2 >> 6) & 1) << 2);
+        v[7] = (b1 >> 6) | ((b2 >> 7) << 2);
+    } else if constexpr (BITS == 2) {   // 2 bytes, four values each  ==  2-bit field i of the 16-bit word
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[4 * i + j] = (b[i] >> (2 * j)) & 3;
-        }
+        for (int i = 0; i < 8; ++i) v[i] = (w[0] >> (2 * i)) & 3;
     } else {                            // 1 bit: one byte, value i in bit i
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (b[0] >> j) & 1;
+        for (int j = 0; j < 8; ++j) v[j] = (w[0] >> j) & 1;
     }
 }
 
@@ -143,20 +148,18 @@ __device__ __forceinline__ float decode_minifloat(uint32_t c, int bits, int E, i
     return (sign && mag != 0u) ? -val : val;
 }
 
-// ---- one octet -> 8 real-valued codes (before scale): integer code (+ signed offset) or float value
+// ---- 8 codes -> 8 real values (before scale): integer code (+ signed offset) or minifloat / fp8 value
 template <int BITS>
-__device__ __forceinline__ void octet_values(const uint8_t* __restrict__ base, int64_t oct, const WFormat& f,
-                                             float (&q)[8], uint32_t (&codes)[8]) {
-    uint32_t b[BITS];
-    load_octet_bytes<BITS>(base, oct, f.word_bytes, b);
-    decode_octet<BITS>(b, codes);
+__device__ __forceinline__ void codes_to_values(const uint32_t (&codes)[8], const WFormat& f, float (&q)[8]) {
     if (f.kind == SDNQ_W_INT) {
+        // exact int -> float without the conversion pipe: 0x4B000000 | c is the float 2^23 + c for c < 2^23
         if (BITS == 8 && !f.is_unsigned) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) q[i] = static_cast<float>(static_cast<int8_t>(codes[i]));
+            for (int i = 0; i < 8; ++i) q[i] = __uint_as_float(0x4B000000u | (codes[i] ^ 0x80u)) - 8388736.0f;      // two's complement byte
         } else {
+            const float bias = 8388608.0f - static_cast<float>(f.int_offset);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) q[i] = static_cast<float>(static_cast<int>(codes[i]) + f.int_offset);
+            for (int i = 0; i < 8; ++i) q[i] = __uint_as_float(0x4B000000u | codes[i]) - bias;
         }
     } else if (f.kind == SDNQ_W_MINIFLOAT) {
 #pragma unroll
@@ -168,6 +171,16 @@ __device__ __forceinline__ void octet_values(const uint8_t* __restrict__ base, i
 #pragma unroll
         for (int i = 0; i < 8; ++i) q[i] = e5m2_to_f32(static_cast<uint8_t>(codes[i]));
     }
+}
+
+// ---- one octet of storage -> 8 real values
+template <int BITS>
+__device__ __forceinline__ void octet_values(const uint8_t* __restrict__ base, int64_t oct, const WFormat& f,
+                                             float (&q)[8], uint32_t (&codes)[8]) {
+    uint32_t w[OctetWords<BITS>::N];
+    load_octet_bytes<BITS>(base, oct, f.word_bytes, w);
+    decode_octet<BITS>(w, codes);
+    codes_to_values<BITS>(codes, f, q);
 }
 
 #define SDNQ_DISPATCH_BITS(bits, ...)                       \

@@ -1,0 +1,154 @@
+"""CPU tests of the host-side surface (config, policy helpers, packers, quantise-time layout rules) against
+reference-generated fixtures.  No kernels are launched here."""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import GOLDEN, LAYER_FILES, LAYER_IDS, fixture_tensors
+
+
+def test_dtype_table_equals_reference_dump():
+    from sdnq_b200.common import dtype_dict
+    table = json.load(open(os.path.join(GOLDEN, "dtype_table.json")))
+    assert set(table) == set(dtype_dict)
+    for name, row in table.items():
+        if "alias_of" in row:
+            assert dtype_dict[name] is dtype_dict[row["alias_of"]], name
+            continue
+        for key, ref in row.items():
+            mine = dtype_dict[name][key]
+            mine = str(mine).replace("torch.", "") if isinstance(mine, torch.dtype) else mine
+            assert mine == ref or (isinstance(ref, float) and abs(mine - ref) <= 1e-5 * abs(ref)), (name, key, mine, ref)
+
+
+def test_policy_tables_equal_reference_dump():
+    from sdnq_b200.common import common_skip_keys, module_skip_keys_dict, weights_dtype_order
+    ref = json.load(open(os.path.join(GOLDEN, "policy_tables.json")))
+    assert weights_dtype_order == ref["weights_dtype_order"]
+    assert list(common_skip_keys) == ref["common_skip_keys"]
+    for name, entry in ref["models"].items():
+        assert module_skip_keys_dict[name] == [entry["modules_to_not_convert"], entry["modules_dtype_dict"], entry["modules_to_not_use_matmul"]]
+    for alias, target in ref["aliases"].items():
+        assert module_skip_keys_dict[alias] is module_skip_keys_dict[target]
+
+
+def test_check_param_name_in_rules():
+    from sdnq_b200.utils import check_param_name_in
+    keys = [".proj_out", "norm_out", "time_text_embed", "transformer_blocks.0.norm*"]
+    assert check_param_name_in("proj_out.weight", keys) == ".proj_out"                       # leading dot = top-level prefix only
+    assert check_param_name_in("single_transformer_blocks.3.proj_out.weight", keys) is None
+    assert check_param_name_in("blocks.1.norm_out.linear.weight", keys) == "norm_out"        # whole dotted segment
+    assert check_param_name_in("blocks.1.norm_out2.weight", keys) is None
+    assert check_param_name_in("transformer_blocks.0.norm1.linear.weight", keys) == "transformer_blocks.0.norm*"
+    assert check_param_name_in("transformer_blocks.10.norm1.linear.weight", keys) is None
+
+
+def test_config_validation_and_json_roundtrip():
+    from sdnq_b200 import SDNQConfig
+    cfg = SDNQConfig(weights_dtype="uint4", use_quantized_matmul=True, modules_to_not_convert="lm_head", modules_dtype_dict={"int8": "proj"})
+    d = cfg.to_dict()
+    assert d["modules_to_not_convert"] == ["lm_head"] and d["modules_dtype_dict"] == {"int8": ["proj"]} and d["quant_method"] == "sdnq"
+    again = SDNQConfig(**{k: v for k, v in d.items() if k not in ("is_integer", "is_unsigned", "quant_method")})
+    assert again.to_dict() == d
+    with pytest.raises(ValueError):
+        SDNQConfig(weights_dtype="int17")
+    with pytest.raises(ValueError):
+        SDNQConfig(weights_dtype="int4", use_codebook=True)
+    with pytest.raises(ValueError):
+        SDNQConfig(quantized_matmul_dtype="int4")
+
+
+@pytest.mark.parametrize("bits", list(range(1, 8)) + list(range(9, 16)))
+def test_pack_int_matches_reference_vectors(bits):
+    from sdnq_b200.packing import pack_int, unpack_int
+    z = np.load(os.path.join(GOLDEN, "pack_kat.npz"))
+    codes, packed = z[f"uint{bits}_codes"], z[f"uint{bits}_packed"]
+    mine = pack_int(torch.from_numpy(codes), f"uint{bits}")
+    assert list(mine.shape) == list(z[f"uint{bits}_packed_shape"])
+    assert np.array_equal(mine.numpy().astype(np.int64) & 0xFFFF, packed.astype(np.int64) & 0xFFFF)
+    assert np.array_equal(unpack_int(mine, f"uint{bits}", codes.shape).numpy().astype(np.int64), codes)
+    if bits > 1:
+        signed = torch.from_numpy(codes) - 2 ** (bits - 1)
+        assert torch.equal(pack_int(signed, f"int{bits}"), mine)
+        assert torch.equal(unpack_int(mine, f"int{bits}", codes.shape).to(torch.int64), signed.to(torch.int64))
+
+
+def test_pack_float_roundtrip_matches_reference():
+    from sdnq_b200.common import dtype_dict
+    from sdnq_b200.packing import pack_float, unpack_float
+    z = np.load(os.path.join(GOLDEN, "float_tables.npz"))
+    sweep = torch.from_numpy(z["sweep"])
+    n = sweep.numel() // 8 * 8
+    for name in [str(s) for s in z["names"]]:
+        info = dtype_dict[name]
+        clamped = sweep.clamp(info["min"], info["max"])[:n]
+        mine = unpack_float(pack_float(clamped, name), name, (n,))
+        ref = z[f"{name}_encode_roundtrip"]
+        assert np.array_equal(mine.numpy().view(np.uint32), ref.view(np.uint32)), name
+
+
+@pytest.mark.parametrize("path", LAYER_FILES, ids=LAYER_IDS)
+def test_quantize_layer_reproduces_reference_tensors(path):
+    """same float weight + same config -> same stored tensors and metadata as the reference produced."""
+    from sdnq_b200 import SDNQConfig, sdnq_quantize_layer
+    t, z, meta = fixture_tensors(path)
+    cfg = meta["config"]
+    lin = torch.nn.Linear(meta["K"], meta["N"], bias=t["bias"] is not None).to(torch.bfloat16)
+    with torch.no_grad():
+        lin.weight.copy_(t["w_orig"])
+        if t["bias"] is not None:
+            lin.bias.copy_(t["bias"])
+    torch.manual_seed(0)
+    layer, _ = sdnq_quantize_layer(copy.deepcopy(lin), SDNQConfig(**cfg))
+    d, ref = layer.sdnq_dequantizer, meta["dequantizer"]
+    assert layer.forward_func.__name__ == meta["forward_func"]
+    for key in ("weights_dtype", "quantized_matmul_dtype", "group_size", "hadamard_group_size", "use_quantized_matmul", "re_quantize_for_matmul",
+                "use_hadamard", "use_codebook", "is_packed", "is_unsigned", "is_integer", "is_integer_matmul", "svd_rank", "layer_class_name"):
+        assert getattr(d, key) == ref[key], key
+    assert list(d.quantized_weight_shape) == ref["quantized_weight_shape"] and list(d.original_shape) == ref["original_shape"]
+    assert (None if d.result_shape is None else list(d.result_shape)) == ref["result_shape"]
+    exact = not cfg.get("use_svd", False)       # svd_lowrank is randomised: the residual (and so the codes) differ run to run
+    for key in ("weight", "scale", "zero_point", "svd_up", "svd_down"):
+        mine, theirs, info = getattr(layer, key), t[key], meta["tensors"][key]
+        assert (mine is None) == (theirs is None), key
+        if mine is None:
+            continue
+        assert list(mine.shape) == info["shape"] and str(mine.dtype).replace("torch.", "") == info["dtype"], (key, mine.shape, mine.dtype, info)
+        assert all(a == b or n == 1 for a, b, n in zip(mine.stride(), info["stride"], info["shape"])), (key, mine.stride(), info["stride"])
+        if exact and not cfg.get("use_codebook", False):
+            a = mine.detach().view(torch.uint8) if mine.dtype == torch.float8_e4m3fn else mine.detach()
+            b = theirs.view(torch.uint8) if theirs.dtype == torch.float8_e4m3fn else theirs
+            assert torch.equal(a.contiguous() if a.dtype != torch.bfloat16 else a.float(), b.contiguous() if b.dtype != torch.bfloat16 else b.float()), key
+
+
+def test_apply_sdnq_to_module_skips_and_swaps():
+    from sdnq_b200 import SDNQConfig, sdnq_post_load_quant
+    from sdnq_b200.layers import SDNQLinear
+
+    class Block(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.to_q = torch.nn.Linear(256, 256)
+            self.proj_out = torch.nn.Linear(256, 256)
+            self.tiny = torch.nn.Linear(16, 16)
+            self.norm = torch.nn.LayerNorm(256)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.proj_out = torch.nn.Linear(256, 64)          # top-level: hit by the ".proj_out" common skip key
+            self.blocks = torch.nn.ModuleList([Block(), Block()])
+
+    net = sdnq_post_load_quant(Net(), weights_dtype="int8", use_quantized_matmul=True)
+    assert not isinstance(net.proj_out, SDNQLinear)
+    assert isinstance(net.blocks[0].to_q, SDNQLinear) and isinstance(net.blocks[1].proj_out, SDNQLinear)
+    assert not isinstance(net.blocks[0].tiny, SDNQLinear)                     # below minimum_allowed_numel
+    assert "blocks.0.tiny.weight" in net.quantization_config.modules_to_not_convert
+    assert net.blocks[0].to_q.weight.dtype == torch.int8 and net.blocks[0].to_q.weight.stride() == (1, 256)
+    assert set(net.blocks[0].to_q.state_dict().keys()) >= {"weight", "scale", "bias"}
+    with pytest.raises(RuntimeError):
+        sdnq_post_load_quant(net, weights_dtype="int8")                        # already quantised

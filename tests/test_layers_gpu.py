@@ -1,0 +1,159 @@
+"""Layer-level parity on the GPU: SDNQLinear.forward through the public surface (SDNQConfig -> sdnq_quantize_layer ->
+forward_func -> C ABI kernels) against the reference outputs recorded in tests/golden/, plus size-independent properties at
+the BASELINE.json shapes."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sdnq_oracle as O
+from tests.util import LAYER_FILES, LAYER_IDS, bf16_ulp_diff, fixture_tensors, np_to_torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def build_layer(path):
+    """quantise w_orig with our host code, then pin the stored tensors to the reference's (bit-identical anyway unless SVD)."""
+    from sdnq_b200 import SDNQConfig, sdnq_quantize_layer
+    t, z, meta = fixture_tensors(path)
+    lin = torch.nn.Linear(meta["K"], meta["N"], bias=t["bias"] is not None).to(torch.bfloat16)
+    with torch.no_grad():
+        lin.weight.copy_(t["w_orig"])
+        if t["bias"] is not None:
+            lin.bias.copy_(t["bias"])
+    layer, _ = sdnq_quantize_layer(copy.deepcopy(lin), SDNQConfig(**meta["config"]))
+    for key in ("weight", "scale", "zero_point", "svd_up", "svd_down"):
+        if t[key] is not None:
+            setattr(layer, key, torch.nn.Parameter(t[key], requires_grad=False))
+    return layer.to(DEV), t, z, meta
+
+
+@pytest.mark.parametrize("path", LAYER_FILES, ids=LAYER_IDS)
+def test_forward_matches_reference_output(path):
+    layer, t, z, meta = build_layer(path)
+    d = meta["dequantizer"]
+    y = layer(t["x"].to(DEV))
+    yref = np_to_torch(z["y"], "bfloat16", DEV)
+    assert y.shape == yref.shape and y.dtype == torch.bfloat16
+    finite = torch.isfinite(yref)
+    assert torch.equal(finite, torch.isfinite(y))
+    is_mm = d["use_quantized_matmul"] and meta["M"] >= 32
+    scale = float(yref[finite].float().abs().max())
+    err = (y.float() - yref.float())[finite].abs()
+    if is_mm and not d["use_hadamard"] and t["svd_up"] is None:
+        # integer / fp8 contraction is exact, activation codes are bit-exact: only the f32 epilogue rounding can move 1 bf16 ulp
+        du = bf16_ulp_diff(y, yref)[finite]
+        assert int(du.max()) <= 1, f"max {int(du.max())} ulp"
+        assert float((du > 0).float().mean()) < 0.02
+    else:
+        # tolerance for paths with a bf16 GEMM / Hadamard / SVD in them: 2e-2 of the output range max, 3e-3 rms (bf16 has 8 bits)
+        assert float(err.max()) <= 2e-2 * scale and float(err.pow(2).mean().sqrt()) <= 3e-3 * scale
+
+
+@pytest.mark.parametrize("path", [p for p in LAYER_FILES if "c2_int8_w8a8." in p or "uint4_auto_dequant" in p or "int8_svd_w8a8" in p],
+                         ids=["int8_w8a8", "int8_svd_w8a8", "uint4_dequant"])
+def test_dequantize_restores_module(path):
+    layer, t, z, meta = build_layer(path)
+    x = t["x"].to(DEV)
+    y_q = layer(x)
+    dense = layer.dequantize()
+    assert type(dense) is torch.nn.Linear and not hasattr(dense, "sdnq_dequantizer")
+    wref = np_to_torch(z["w_dequant"], "bfloat16", DEV)
+    assert dense.weight.shape == wref.shape
+    assert float((dense.weight.float() - wref.float()).abs().max()) <= 2.0 ** -7 * float(wref.float().abs().max())
+    y_d = dense(x)
+    assert float((y_d.float() - y_q.float()).abs().max()) <= 0.05 * float(y_q.float().abs().max())
+
+
+def _model(K=256, N=128):
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Linear(K, N)
+            self.b = torch.nn.Linear(N, K)
+
+        def forward(self, x):
+            return self.b(torch.nn.functional.gelu(self.a(x)))
+    torch.manual_seed(4)
+    return Net().to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("cfg", [dict(weights_dtype="int8"), dict(weights_dtype="uint8"), dict(weights_dtype="float8_e4m3fn", use_hadamard=True),
+                                 dict(weights_dtype="int8", use_svd=True, svd_rank=8), dict(weights_dtype="int4", group_size=64)],
+                         ids=["int8", "uint8", "fp8_hadamard", "int8_svd", "int4_g64"])
+def test_apply_sdnq_options_flips_matmul_in_place(cfg):
+    """quantise with the matmul off, flip it on with apply_sdnq_options_to_model, and compare with a model quantised with the
+    matmul on from the start: same stored bytes, same outputs (reference loader.py:286-301)."""
+    from sdnq_b200 import apply_sdnq_options_to_model, sdnq_post_load_quant
+    base = _model()
+    torch.manual_seed(1)
+    off = sdnq_post_load_quant(copy.deepcopy(base), use_quantized_matmul=False, add_skip_keys=False, **cfg).to(DEV)
+    torch.manual_seed(1)
+    on = sdnq_post_load_quant(copy.deepcopy(base), use_quantized_matmul=True, add_skip_keys=False, **cfg).to(DEV)
+    x = torch.randn(64, 256, dtype=torch.bfloat16, device=DEV)
+    y_off = off(x)
+    flipped = apply_sdnq_options_to_model(off, use_quantized_matmul=True)
+    assert flipped.a.forward_func.__name__ == on.a.forward_func.__name__
+    assert flipped.a.sdnq_dequantizer.use_quantized_matmul is True
+    if not cfg.get("use_svd"):
+        for key in ("weight", "scale", "zero_point"):
+            u, v = getattr(flipped.a, key), getattr(on.a, key)
+            assert (u is None) == (v is None)
+            if u is not None:
+                assert u.shape == v.shape and u.stride() == v.stride()
+                assert torch.equal(u.view(torch.uint8) if u.dtype == torch.float8_e4m3fn else u, v.view(torch.uint8) if v.dtype == torch.float8_e4m3fn else v)
+        assert torch.equal(flipped(x), on(x))
+    y_on = flipped(x)
+    assert float((y_on.float() - y_off.float()).abs().max()) <= 0.08 * float(y_off.float().abs().max())
+    back = apply_sdnq_options_to_model(flipped, use_quantized_matmul=False)
+    assert back.a.forward_func.__name__ == "quantized_linear_forward"
+    assert torch.equal(back(x), y_off)
+
+
+def test_cpu_tensor_fails_loudly():
+    from sdnq_b200 import SDNQConfig, sdnq_quantize_layer
+    from sdnq_b200._lib import SDNQKernelError
+    layer, _ = sdnq_quantize_layer(torch.nn.Linear(64, 64).to(torch.bfloat16), SDNQConfig(weights_dtype="int8", use_quantized_matmul=True, minimum_allowed_numel=1))
+    with pytest.raises(SDNQKernelError):
+        layer(torch.randn(40, 64, dtype=torch.bfloat16))
+
+
+# --------------------------------------------------------------------------------------- BASELINE-size properties
+SDXL = [(4096, 640, 640), (4096, 5120, 640), (1024, 1280, 5120), (77, 1280, 2048)]
+FLUX = [(16384, 3072, 3072), (2048, 12288, 3072)]
+
+
+@pytest.mark.parametrize("M,N,K", SDXL + FLUX)
+@pytest.mark.parametrize("wd", ["int8", "float8_e4m3fn"])
+def test_full_size_properties(M, N, K, wd):
+    """at the real SD-XL / FLUX Linear shapes: (1) row independence -- permuting the rows of x permutes the rows of y bit-exactly;
+    (2) power-of-two linearity -- y(4x) - bias == 4 (y(x) - bias) up to the output rounding (codes identical, scales x4);
+    (3) agreement with the oracle on a random sample of rows (oracle evaluated on those rows only)."""
+    from sdnq_b200 import SDNQConfig, sdnq_quantize_layer
+    torch.manual_seed(M + N + K)
+    lin = torch.nn.Linear(K, N, bias=True).to(torch.bfloat16)
+    layer, _ = sdnq_quantize_layer(copy.deepcopy(lin), SDNQConfig(weights_dtype=wd, use_quantized_matmul=True, use_hadamard=(wd != "int8")))
+    layer = layer.to(DEV)
+    x = torch.randn(M, K, dtype=torch.bfloat16, device=DEV)
+    y = layer(x)
+    perm = torch.randperm(M, device=DEV)
+    assert torch.equal(layer(x[perm]), y[perm])
+    bias = layer.bias
+    layer.bias = None
+    y0, y4 = layer(x), layer(x * 4)
+    layer.bias = bias
+    assert torch.equal(y4, y0 * 4)
+    rows = torch.randperm(M)[:48].sort().values
+    meta = {k: (list(v) if isinstance(v, torch.Size) else v) for k, v in layer.sdnq_dequantizer.__dict__.items() if k != "result_dtype"}
+    ol = O.Layer(layer.weight.detach().float().cpu().numpy() if wd != "int8" else layer.weight.detach().cpu().numpy(),
+                 layer.scale.detach().cpu().numpy(), bias=layer.bias.detach().float().cpu().numpy(), **meta)
+    ref = O.linear_forward(ol, x[rows.to(DEV)].float().cpu().numpy())
+    got = y[rows.to(DEV)].float().cpu().numpy()
+    scale = np.abs(ref).max()
+    if wd == "int8":
+        du = bf16_ulp_diff(torch.from_numpy(got).to(torch.bfloat16), torch.from_numpy(ref).to(torch.bfloat16))
+        assert int(du.max()) <= 1
+    else:
+        assert np.abs(got - ref).max() <= 2e-2 * scale and np.sqrt(np.mean((got - ref) ** 2)) <= 3e-3 * scale
