@@ -73,6 +73,8 @@ def flux_linears(batch=4):
 WORKLOADS = {
     "sdxl_int8": dict(describe="SD-XL UNet int8 W8A8 (use_quantized_matmul=True), bs=1, 1024x1024: all quantised Linears of one denoise step",
                       layers=sdxl_linears, config=dict(weights_dtype="int8", use_quantized_matmul=True), dtype="int8"),
+    "sdxl_int4_svd_dequant": dict(describe="SD-XL UNet int4 group_size=128 + SVD rank 32, dequant-to-bf16-GEMM path (use_quantized_matmul=False), bs=1, 1024x1024",
+                                  layers=sdxl_linears, config=dict(weights_dtype="int4", group_size=128, use_svd=True, svd_rank=32), dtype="bf16"),
     "flux_fp8": dict(describe="FLUX.1-dev DiT float8_e4m3fn + Hadamard(256) W8A8, bs=4, 1024x1024: all quantised Linears of one denoise step",
                      layers=flux_linears, config=dict(weights_dtype="float8_e4m3fn", use_quantized_matmul=True, use_hadamard=True, hadamard_group_size=256),
                      dtype="f8e4m3"),
@@ -139,8 +141,21 @@ def cpu_oracle_sample(workload, budget_s=15.0, seed=0):
     fp8 = spec["config"]["weights_dtype"].startswith("float8")
     hg = spec["config"].get("hadamard_group_size", 256) if spec["config"].get("use_hadamard") else 0
     prepared = []
+    dequant_path = not spec["config"].get("use_quantized_matmul", False)
     for m, n, k in shapes:
         w = (rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32)
+        if dequant_path:       # int4 g128 + SVD rank 32: packed codes, group scales, low-rank factors; dequant then f32 GEMM
+            gs, r = spec["config"]["group_size"], spec["config"]["svd_rank"]
+            wg = w.reshape(n, k // gs, gs)
+            sc = (np.abs(wg).max(axis=-1, keepdims=True) / 7).astype(np.float32)
+            codes = np.clip(np.rint(wg / sc), -8, 7).astype(np.int64)
+            layer = O.Layer(O.pack_int(codes, "int4"), sc, None, O.bf16_round(rng.standard_normal((n, r)).astype(np.float32) * 0.05),
+                            O.bf16_round(rng.standard_normal((r, k)).astype(np.float32) * 0.05),
+                            bias=O.bf16_round(rng.standard_normal(n).astype(np.float32)), weights_dtype="int4", quantized_weight_shape=[n, k // gs, gs],
+                            result_shape=[n, k], group_size=gs, use_quantized_matmul=False)
+            x = O.bf16_round(rng.standard_normal((m, k)).astype(np.float32))
+            prepared.append((layer, x, 2.0 * m * n * k))
+            continue
         if fp8:
             wq, sw = O.quantize_fp_mm(w, axis=-1)
         else:
@@ -315,10 +330,12 @@ def run_gpu_arm(args):
     barrier()
     w0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()         # no-op unless run under `ncu --profile-from-start off` (profiles/ launch lists)
     e0.record()
     for _ in range(args.steps):
         run_step()
     e1.record()
+    torch.cuda.profiler.stop()
     barrier()
     w1 = time.time()
     ms = e0.elapsed_time(e1)
@@ -357,10 +374,24 @@ def run_gpu_arm(args):
         acts = derive_activations(dev_in, shapes)
         gemm_ms = gemm_flops = k2_ms = k2_bytes = 0.0
         n_gemm = 0
+        dq_ms = dq_bytes = 0.0
+        n_dq = 0
         for _, m, n, k, layer in stack:
+            d = layer.sdnq_dequantizer
+            if not d.use_quantized_matmul:
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda._sleep(400_000)
+                b0.record()
+                d(layer.weight, layer.scale, layer.zero_point, layer.svd_up, layer.svd_down)
+                b1.record()
+                b1.synchronize()
+                dq_ms += b0.elapsed_time(b1)
+                tensors = [layer.weight, layer.scale, layer.zero_point, layer.svd_up, layer.svd_down]
+                dq_bytes += sum(t.numel() * t.element_size() for t in tensors if t is not None) + 2.0 * n * k
+                n_dq += 1
+                continue
             if m < 32:
                 continue
-            d = layer.sdnq_dequantizer
             op = matmul_operand(layer)
             hg = d.hadamard_group_size if d.use_hadamard else 0
             a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -384,13 +415,20 @@ def run_gpu_arm(args):
         bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        achieved = gemm_flops / gemm_ms / 1e9
-        roofline = {"bound": "tensor", "kernel": "gemm_w8a8_kernel (tcgen05 kind::i8 / kind::f8f6f4)", "achieved": achieved, "peak": 2.0 * bf16_peak,
-                    "unit": "TFLOP/s", "frac": achieved / (2.0 * bf16_peak), "traffic": None,
-                    "peak_note": f"8-bit dense tensor peak taken as 2x the {src} bf16 cuBLAS burst figure ({bf16_peak} TF)",
-                    "launches": n_gemm, "avg_launch_us": 1e3 * gemm_ms / max(n_gemm, 1), "share_of_step": gemm_ms / (gemm_ms + k2_ms),
-                    "act_quant": {"bound": "hbm", "achieved": k2_bytes / k2_ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
-                                  "frac": k2_bytes / k2_ms / 1e6 / hbm_peak, "avg_launch_us": 1e3 * k2_ms / max(n_gemm, 1)}}
+        if n_dq:
+            ach = dq_bytes / dq_ms / 1e6
+            roofline = {"bound": "hbm", "kernel": "dequant_svd_kernel / dequant_kernel (K3)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": ach / hbm_peak, "traffic": None, "peak_note": f"HBM copy peak, {src}", "launches": n_dq,
+                        "avg_launch_us": 1e3 * dq_ms / n_dq,
+                        "algorithmic_bytes": "packed codes + scales (+zp) + svd factors read, bf16 weight written"}
+        achieved = gemm_flops / max(gemm_ms, 1e-9) / 1e9
+        if not n_dq:
+            roofline = {"bound": "tensor", "kernel": "gemm_w8a8_kernel (tcgen05 kind::i8 / kind::f8f6f4)", "achieved": achieved, "peak": 2.0 * bf16_peak,
+                        "unit": "TFLOP/s", "frac": achieved / (2.0 * bf16_peak), "traffic": None,
+                        "peak_note": f"8-bit dense tensor peak taken as 2x the {src} bf16 cuBLAS burst figure ({bf16_peak} TF)",
+                        "launches": n_gemm, "avg_launch_us": 1e3 * gemm_ms / max(n_gemm, 1), "share_of_step": gemm_ms / (gemm_ms + k2_ms),
+                        "act_quant": {"bound": "hbm", "achieved": k2_bytes / k2_ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": k2_bytes / k2_ms / 1e6 / hbm_peak, "avg_launch_us": 1e3 * k2_ms / max(n_gemm, 1)}}
         if world == 1 and not args.no_cpu_baseline:
             cpu_base = cpu_oracle_sample(args.workload, budget_s=12.0)
 

@@ -230,10 +230,18 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? 6 : 
         if (!(row_ok && k < K)) continue;
         float v[8];
         held[c].get(v);
-        if (a.x_rot != nullptr) store8<T>(reinterpret_cast<T*>(a.x_rot) + row * a.K + k, v);
         const bool want_sum = a.rowsum != nullptr;
         const uint2 r = safe ? quantise8<MODE, true>(v, divider, zero, want_sum, local_sum) : quantise8<MODE, false>(v, divider, zero, want_sum, local_sum);
-        *reinterpret_cast<uint2*>(a.xq + row * a.K + k) = r;
+        // after a power-of-4 Hadamard the lane's two 4-element halves belong elsewhere in the chunk (see hadamard_dest)
+        const int64_t chunk0 = row * a.K + (k - lane * 8);
+        const int d0 = hadamard_dest_dyn(a.hadamard, lane, 0), d1 = hadamard_dest_dyn(a.hadamard, lane, 1);
+        *reinterpret_cast<uint32_t*>(a.xq + chunk0 + d0) = r.x;
+        *reinterpret_cast<uint32_t*>(a.xq + chunk0 + d1) = r.y;
+        if (a.x_rot != nullptr) {
+            T* xr = reinterpret_cast<T*>(a.x_rot) + chunk0;
+            store4<T>(xr + d0, v[0], v[1], v[2], v[3]);
+            store4<T>(xr + d1, v[4], v[5], v[6], v[7]);
+        }
     }
     if (a.rowsum != nullptr) {
         local_sum = warp_sum(local_sum);

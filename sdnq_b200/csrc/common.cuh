@@ -148,6 +148,24 @@ __device__ __forceinline__ void store8<__half>(__half* p, const float (&v)[8]) {
     *reinterpret_cast<uint4*>(p) = r;
 }
 
+// 4 consecutive elements (half an octet)
+template <typename T>
+__device__ __forceinline__ void store4(T* p, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+template <>
+__device__ __forceinline__ void store4<__half>(__half* p, float a, float b, float c, float d) {
+    __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+
 // float -> e4m3fn byte, round-to-nearest-even, input already clamped to +-448 (matches torch's cast)
 __device__ __forceinline__ uint8_t f32_to_e4m3(float v) {
     return static_cast<uint8_t>(__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3));
@@ -178,87 +196,89 @@ __device__ __forceinline__ int warp_sum(int v) {
 }
 
 // ---------------------------------------------------------------- device: Hadamard over a warp
-// A warp holds a 256-element chunk of one row: lane l owns elements [8l, 8l+8).  The transform is
-// applied independently to each aligned sub-block of `G` elements (G = 4..256, power of two).
-//   G a power of 4 : kron^k(H4), H4 = [[1,1,1,-1],[1,1,-1,1],[1,-1,1,1],[-1,1,1,1]]; per base-4 digit
-//                    y_i = (x0+x1+x2+x3) - 2*x_{3-i}                      (reference quant_utils.py:155-165)
-//   otherwise      : Sylvester kron^k([[1,1],[1,-1]]); per bit y = (a+b, a-b)   (quant_utils.py:144-152)
-// The 1/sqrt(G) factor is applied by the caller (it is rounded to the activation dtype upstream).
-__device__ __forceinline__ void h4_inlane(float& a, float& b, float& c, float& d) {
-    const float s = (a + b) + (c + d);
-    const float a2 = s - 2.f * d, b2 = s - 2.f * c, c2 = s - 2.f * b, d2 = s - 2.f * a;
-    a = a2; b = b2; c = c2; d = d2;
+// A warp holds a 256-element chunk of one row: lane l owns elements [8l, 8l+8).  The transform is applied independently to
+// each aligned sub-block of G elements (G = 4..256, power of two); the 1/sqrt(G) factor is applied by the caller.
+//
+//   G not a power of 4 : Sylvester kron^k([[1,1],[1,-1]])                                  (reference quant_utils.py:144-152)
+//   G a power of 4     : kron^k(H4), H4 = [[1,1,1,-1],[1,1,-1,1],[1,-1,1,1],[-1,1,1,1]]    (reference quant_utils.py:155-165)
+//
+// Both run as radix-2 butterflies (3 in-register stages + one xor-shuffle stage per remaining bit).  For the H4 family we use
+//   H4 = P . D . (H2 (x) H2) . D,   D = diag(1,1,1,-1),  P = swap of the two middle outputs,
+// applied per base-4 digit: negate inputs whose digit is 3 (for every digit), run the Sylvester transform, negate outputs by
+// the same rule, and deliver output p at position swap_bit_pairs(p).  The in-register half of that permutation (bits 0<->1)
+// is done here by renaming registers; the cross-lane half is *not* moved through shuffles: callers store the two 4-element
+// halves of the lane at hadamard_dest<G>(lane, half) instead (a permutation of 8 B / 4 B pieces inside the same 256-chunk).
+template <int G> struct HadamardInfo {
+    static_assert(G >= 4 && G <= 256 && (G & (G - 1)) == 0, "hadamard group must be a power of two in [4,256]");
+    static constexpr int LOG = (G == 4) ? 2 : (G == 8) ? 3 : (G == 16) ? 4 : (G == 32) ? 5 : (G == 64) ? 6 : (G == 128) ? 7 : 8;
+    static constexpr bool kPow4 = (LOG & 1) == 0;
+};
+
+template <int G>
+__device__ __forceinline__ void hadamard_signs(float (&v)[8], int lane) {
+    constexpr int LOG = HadamardInfo<G>::LOG;
+    bool neg = false;                                   // digits held in the lane index
+    if (LOG >= 6) neg ^= ((lane >> 1) & 3) == 3;
+    if (LOG >= 8) neg ^= ((lane >> 3) & 3) == 3;
+    const uint32_t base = neg ? 0x80000000u : 0u;
+    const uint32_t odd = (LOG >= 4 && (lane & 1)) ? 0x80000000u : 0u;   // digit 1 = (lane bit 0, element bit 2)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint32_t m = base;
+        if ((j & 3) == 3) m ^= 0x80000000u;             // digit 0 = element bits 0-1
+        if (j >= 4) m ^= odd;
+        v[j] = __uint_as_float(__float_as_uint(v[j]) ^ m);
+    }
 }
 
 template <int G>
 __device__ __forceinline__ void hadamard_warp(float (&v)[8]) {
-    static_assert(G >= 4 && G <= 256 && (G & (G - 1)) == 0, "hadamard group must be a power of two in [4,256]");
-    constexpr int LOG = (G == 4) ? 2 : (G == 8) ? 3 : (G == 16) ? 4 : (G == 32) ? 5 : (G == 64) ? 6 : (G == 128) ? 7 : 8;
+    constexpr int LOG = HadamardInfo<G>::LOG;
+    constexpr bool kPow4 = HadamardInfo<G>::kPow4;
     const int lane = threadIdx.x & 31;
-    if constexpr ((LOG & 1) == 0) {
-        // ---- base-4 digits.  digit 0 = element bits 0-1 (in lane)
+    if constexpr (kPow4) hadamard_signs<G>(v, lane);
 #pragma unroll
-        for (int j = 0; j < 8; j += 4) h4_inlane(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        if constexpr (LOG >= 4) {
-            // digit 1 = element bit 2 (in lane) + element bit 3 (lane bit 0)
+    for (int b = 1; b < 8 && b < G; b <<= 1) {          // element bits 0..2: in registers
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float lo = v[j], hi = v[j + 4];
-                const float part = lo + hi;
-                const float s = part + __shfl_xor_sync(0xffffffffu, part, 1);
-                const float rev_lo = __shfl_xor_sync(0xffffffffu, hi, 1);  // complement of (bit3, bit2=0) is (!bit3, 1)
-                const float rev_hi = __shfl_xor_sync(0xffffffffu, lo, 1);
-                v[j] = s - 2.f * rev_lo;
-                v[j + 4] = s - 2.f * rev_hi;
-            }
-        }
-        if constexpr (LOG >= 6) {
-            // digit 2 = lane bits 1-2
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float t = v[j] + __shfl_xor_sync(0xffffffffu, v[j], 2);
-                const float s = t + __shfl_xor_sync(0xffffffffu, t, 4);
-                const float rev = __shfl_xor_sync(0xffffffffu, v[j], 6);
-                v[j] = s - 2.f * rev;
-            }
-        }
-        if constexpr (LOG >= 8) {
-            // digit 3 = lane bits 3-4
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float t = v[j] + __shfl_xor_sync(0xffffffffu, v[j], 8);
-                const float s = t + __shfl_xor_sync(0xffffffffu, t, 16);
-                const float rev = __shfl_xor_sync(0xffffffffu, v[j], 24);
-                v[j] = s - 2.f * rev;
-            }
-        }
-    } else {
-        // ---- Sylvester: element bits 0..2 in lane, bits 3.. across lanes
-#pragma unroll
-        for (int b = 1; b < 8; b <<= 1) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if ((j & b) == 0) {
-                    const float x = v[j], y = v[j | b];
-                    v[j] = x + y;
-                    v[j | b] = x - y;
-                }
-            }
-        }
-#pragma unroll
-        for (int b = 3; b < LOG; ++b) {
-            const int m = 1 << (b - 3);
-            const bool upper = (lane & m) != 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float o = __shfl_xor_sync(0xffffffffu, v[j], m);
-                v[j] = upper ? (o - v[j]) : (v[j] + o);
+        for (int j = 0; j < 8; ++j) {
+            if ((j & b) == 0) {
+                const float x = v[j], y = v[j | b];
+                v[j] = x + y;
+                v[j | b] = x - y;
             }
         }
     }
+#pragma unroll
+    for (int b = 3; b < LOG; ++b) {                     // element bits 3..: across lanes
+        const int m = 1 << (b - 3);
+        const float sgn = (lane & m) ? -1.0f : 1.0f;       // upper half of the pair computes (other - mine): one FFMA, exact
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float o = __shfl_xor_sync(0xffffffffu, v[j], m);
+            v[j] = fmaf(sgn, v[j], o);
+        }
+    }
+    if constexpr (kPow4) {
+        hadamard_signs<G>(v, lane);
+        float t;                                        // output bits 0 <-> 1: registers (1,2) and (5,6) trade places
+        t = v[1]; v[1] = v[2]; v[2] = t;
+        t = v[5]; v[5] = v[6]; v[6] = t;
+    }
 }
 
-// runtime dispatch; returns false if G is not supported
+// element offset inside the 256-chunk where registers [4*half, 4*half+4) of this lane belong after hadamard_warp<G>
+template <int G>
+__device__ __forceinline__ int hadamard_dest(int lane, int half) {
+    constexpr int LOG = HadamardInfo<G>::LOG;
+    int p = lane * 8 + half * 4;
+    if constexpr (HadamardInfo<G>::kPow4 && LOG >= 4) {
+        constexpr int mask = (1 << LOG) - 1;
+        const int even = p & 0x54 & mask, odd = p & 0xA8 & mask;    // bit pairs (2,3), (4,5), (6,7) below LOG
+        p = (p & ~(0xFC & mask)) | (even << 1) | (odd >> 1);
+    }
+    return p;
+}
+
 __device__ __forceinline__ void hadamard_warp_dyn(int G, float (&v)[8]) {
     switch (G) {
         case 4: hadamard_warp<4>(v); break;
@@ -269,6 +289,14 @@ __device__ __forceinline__ void hadamard_warp_dyn(int G, float (&v)[8]) {
         case 128: hadamard_warp<128>(v); break;
         case 256: hadamard_warp<256>(v); break;
         default: break;
+    }
+}
+__device__ __forceinline__ int hadamard_dest_dyn(int G, int lane, int half) {
+    switch (G) {
+        case 16: return hadamard_dest<16>(lane, half);
+        case 64: return hadamard_dest<64>(lane, half);
+        case 256: return hadamard_dest<256>(lane, half);
+        default: return lane * 8 + half * 4;            // no rotation, Sylvester groups and G = 4 keep their place
     }
 }
 

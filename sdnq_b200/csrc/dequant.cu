@@ -13,6 +13,10 @@
 
 namespace sdnq {
 
+int dequant_svd_tc(const void* weight, const WFormat& f, const float* scale, const float* zp, int64_t N, int64_t K, int group32, int group_shift,
+                   int gpr32, int row_stride32, const void* up, int64_t up_sn, int64_t up_sr, const void* down, int64_t down_sr, int64_t down_sk,
+                   int rank, int svd_dtype, void* out, int out_dtype, cudaStream_t st);
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -160,7 +164,15 @@ __global__ void __launch_bounds__(kThreads, kPlain ? 5 : 3) dequant_kernel(const
                     for (int i = 0; i < 8; ++i) w[i] = w[i] * h;
                 }
             }
-            if (valid[u]) store8<OutT>(out + int64_t(n[u]) * a.K32 + k[u], w);
+            if (valid[u]) {
+                if (kPlain || !a.hadamard) {
+                    store8<OutT>(out + int64_t(n[u]) * a.K32 + k[u], w);
+                } else {   // power-of-4 un-rotation leaves the two halves of the lane at permuted places of the chunk
+                    OutT* o = out + int64_t(n[u]) * a.K32 + (k[u] - lane * 8);
+                    store4<OutT>(o + hadamard_dest_dyn(a.hadamard, lane, 0), w[0], w[1], w[2], w[3]);
+                    store4<OutT>(o + hadamard_dest_dyn(a.hadamard, lane, 1), w[4], w[5], w[6], w[7]);
+                }
+            }
         }
     }
 }
@@ -171,30 +183,6 @@ __global__ void __launch_bounds__(kThreads, kPlain ? 5 : 3) dequant_kernel(const
 // incrementally: one integer division per warp, none per chunk) with U chunks in flight; int4 and int8 go from storage
 // word to float with one PRMT per element (byte -> 0x4B0000bb = 2^23 + b, then one FADD), so the kernel sits at ~7 SASS
 // instructions per element and 40 registers (6 CTAs / SM).
-template <int BITS>
-__device__ __forceinline__ void octet_to_floats(const uint32_t (&w)[OctetWords<BITS>::N], uint32_t flip, float bias, float (&q)[8]) {
-    if constexpr (BITS == 4) {
-        const uint32_t lo = w[0] & 0x0F0F0F0Fu, hi = (w[0] >> 4) & 0x0F0F0F0Fu;       // even / odd nibbles, one per byte
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            q[2 * i] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7440 | i)) - bias;
-            q[2 * i + 1] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7440 | i)) - bias;
-        }
-    } else if constexpr (BITS == 8) {
-        const uint32_t a = w[0] ^ flip, b = w[1] ^ flip;                              // flip = 0x80808080 for two's complement bytes
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            q[i] = __uint_as_float(__byte_perm(a, 0x4B000000u, 0x7440 | i)) - bias;
-            q[4 + i] = __uint_as_float(__byte_perm(b, 0x4B000000u, 0x7440 | i)) - bias;
-        }
-    } else {
-        uint32_t codes[8];
-        decode_octet<BITS>(w, codes);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) q[i] = __uint_as_float(0x4B000000u | codes[i]) - bias;
-    }
-}
-
 template <int BITS, bool kZP, bool kPow2, typename OutT, int U>
 __global__ void __launch_bounds__(kThreads, 6) dequant_int_kernel(const DequantArgs a, OutT* __restrict__ out, int cpr, int total_chunks) {
     pdl_launch_dependents();
@@ -502,6 +490,12 @@ extern "C" int sdnq_b200_dequant(const void* weight, const sdnq_weight_format* f
     }
     a.hadamard = hadamard_group;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (svd_up != nullptr && hadamard_group == 0 && !codebook) {
+        // rank-r correction on the tensor cores when the layout allows it (dequant_svd.cu); 1 = "not covered, use the generic kernel"
+        rc = dequant_svd_tc(weight, a.f, scale, zero_point, N, K, a.group32, a.group_shift, a.gpr32, a.row_stride32, svd_up, up_stride_n, up_stride_r,
+                            svd_down, down_stride_r, down_stride_k, svd_rank, svd_dtype, out, out_dtype, st);
+        if (rc != 1) return rc;
+    }
     switch (out_dtype) {
         case SDNQ_BF16: return launch_dequant<__nv_bfloat16>(a, out, st);
         case SDNQ_F16: return launch_dequant<__half>(a, out, st);

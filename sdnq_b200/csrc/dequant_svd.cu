@@ -1,0 +1,364 @@
+// K3s: dequant-only path WITH the SVD low-rank correction, rank-r term on the tensor cores.
+//
+//   W[n,k] = cast( cast(q[n,k] * scale[n,g] (+ zp)) + sum_j svd_up[n,j] * svd_down[j,k] )          reference dequantizer.py:52-84
+//
+// The rank-r update is a [N x r] . [r x K] GEMM with r = 16 / 32 / 64: 32 FMA per output element on CUDA cores make the
+// kernel compute-bound (~2.4x the HBM time), one tcgen05.mma (kind::f16, bf16 operands, f32 accumulate in TMEM) per
+// 128 x 256 output tile makes it free.  Structure = the W8A8 GEMM's (persistent CTA per SM, TMA producer warp, one MMA
+// thread, 4 epilogue warps, double-buffered TMEM accumulator, swizzled smem staging + TMA bulk stores) with a single
+// k-block per tile and a different epilogue: TMEM lane = weight row n, so each epilogue lane dequantises 64 consecutive k of
+// its own row per block (packed bytes for the whole 256-wide tile row are fetched up front: 128 B per lane for 4-bit codes,
+// 16 KB in flight per SM), adds the accumulator and rounds exactly where the reference's `result.to(svd dtype).addmm_()` does.
+//
+// Operands: A = svd_up [N, r] (r contiguous: K-major), B = svd_down as stored for the dequant path, logical [r, K] with stride
+// (1, r) = physical [K, r] (r contiguous: K-major).  One TMA box row is r*2 bytes = the swizzle span (32 / 64 / 128 B).
+#include <mutex>
+
+#include "ptx.cuh"
+#include "unpack.cuh"
+
+namespace sdnq {
+
+namespace {
+
+constexpr int TM = 128;         // weight rows per tile (TMEM lanes)
+constexpr int TN = 256;         // weight columns per tile (MMA N)
+constexpr int kThreads = 192;
+constexpr int kStages = 2;
+constexpr int kStoreBufs = 2;
+constexpr int kStoreBlkBytes = 32 * 128;
+constexpr int kStoreBytes = 4 * kStoreBufs * kStoreBlkBytes;
+constexpr int kMaxRank = 64;
+constexpr int kStageA = TM * kMaxRank * 2;     // 16 KB
+constexpr int kStageB = TN * kMaxRank * 2;     // 32 KB
+constexpr int kPkBytes = 8 * 32 * 16;           // one tile row of 4-bit codes per lane: 8 units x 32 lanes x 16 B
+constexpr int kPkTotal = 4 * 2 * kPkBytes;      // 4 epilogue warps x double buffer = 32 KB
+constexpr int kScTotal = 4 * 2 * 2 * 4 * 32 * 4; // 4 warps x 2 buffers x (scale, zp) x 4 blocks x 32 lanes x f32 = 8 KB
+constexpr int kSmemBytes = kStages * (kStageA + kStageB) + kStoreBytes + kPkTotal + kScTotal + 256;
+
+struct SvdArgs {
+    const uint8_t* weight;
+    const float* scale;
+    const float* zp;
+    int N, K;
+    int group32, group_shift, gpr32, row_stride32;
+    WFormat f;
+    int rank;
+    int out_dtype;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_kmajor(uint32_t smem_addr, int swizzle_bytes) {
+    // K-major operand, rows of `swizzle_bytes` (32 / 64 / 128), 8-row swizzle atoms: SBO = 8 * swizzle_bytes
+    const uint64_t layout = swizzle_bytes == 128 ? 2 : swizzle_bytes == 64 ? 4 : 6;
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>((8 * swizzle_bytes) >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= layout << 61;
+    return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int BITS, bool kBf16Out>
+__global__ void __launch_bounds__(kThreads, 1)
+dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_constant__ CUtensorMap tmap_down,
+                   const __grid_constant__ CUtensorMap tmap_out, const SvdArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = ptx::smem_u32(smem_raw);
+    if ((smem_base & 1023u) != 0) __trap();
+    const uint32_t smem_a = smem_base;
+    const uint32_t smem_b = smem_base + kStages * kStageA;
+    const uint32_t smem_o = smem_base + kStages * (kStageA + kStageB);
+    const uint32_t smem_pk = smem_o + kStoreBytes;
+    float* s_scales = reinterpret_cast<float*>(smem_raw + kStages * (kStageA + kStageB) + kStoreBytes + kPkTotal);
+    const uint32_t bar_base = smem_pk + kPkTotal + kScTotal;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = (a.N + TM - 1) / TM, num_n = (a.K + TN - 1) / TN;
+    const int num_tiles = num_m * num_n;
+    const int row_bytes = a.rank * 2;                               // = swizzle span
+    const uint32_t stage_tx = static_cast<uint32_t>((TM + TN) * row_bytes);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_up);
+        ptx::prefetch_tmap(&tmap_down);
+        ptx::prefetch_tmap(&tmap_out);
+        for (int s = 0; s < kStages; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(tfull_bar(s), 1);
+            ptx::mbar_init(tempty_bar(s), 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_launch_dependents();
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / num_n) * TM, n0 = (tile % num_n) * TN;
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                ptx::mbar_arrive_expect_tx(full_bar(stage), stage_tx);
+                ptx::tma_load_2d(smem_a + stage * kStageA, &tmap_up, full_bar(stage), 0, m0);
+                ptx::tma_load_2d(smem_b + stage * kStageB, &tmap_down, full_bar(stage), 0, n0);
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc(1 /*f32 acc*/, 1 /*bf16*/, 1 /*bf16*/, TM, TN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1u;
+                ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
+                ptx::mbar_wait(full_bar(stage), phase);
+                ptx::tc_fence_after();
+                const uint64_t a_desc = make_smem_desc_kmajor(smem_a + stage * kStageA, row_bytes);
+                const uint64_t b_desc = make_smem_desc_kmajor(smem_b + stage * kStageB, row_bytes);
+                for (int k = 0; k < a.rank / 16; ++k)                 // 16 bf16 = 32 B per MMA along the contraction
+                    umma_bf16(tmem_base + as * TN, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc, k != 0 ? 1u : 0u);
+                ptx::umma_commit(empty_bar(stage));
+                ptx::umma_commit(tfull_bar(as));
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ======================================================== epilogue: dequant + add + round + store
+        // Packed codes of a lane's tile row (256 four-bit codes = 128 B) and its per-64-column scales are prefetched one tile
+        // ahead into shared memory with cp.async (16 KB in flight per SM, lane-interleaved 16 B units: conflict-free both ways),
+        // and consumed by a *rolled* loop over 32-column slices -- the unrolled form of this epilogue overflowed the
+        // instruction cache (ncu: 56 % icc hit rate, no_inst stalls), the rolled one is ~400 SASS instructions.
+        const int q = warp & 3, ew = warp - 2;
+        const uint32_t my_o = smem_o + uint32_t(ew) * (kStoreBufs * kStoreBlkBytes);
+        const uint32_t pk_base = smem_pk + uint32_t(ew) * (2 * kPkBytes);              // [2 buffers][8 units][32 lanes][16 B]
+        float* sc_base = s_scales + ew * (2 * 2 * 4 * 32);                              // [2 buffers][scale|zp][4 blocks][32 lanes]
+        const float bias = 8388608.0f - static_cast<float>(a.f.int_offset);
+        const bool blk_scales = a.gpr32 <= 1 || (a.group32 & 63) == 0;
+
+        auto prefetch = [&](int tile, int buf) {
+            const int m0 = (tile / num_n) * TM, n0 = (tile % num_n) * TN;
+            const int n = m0 + q * 32 + lane;
+            const bool row_ok = n < a.N;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = n0 + 32 * u;
+                const bool ok = row_ok && k < a.K;
+                const uint8_t* src = a.weight + (ok ? ((static_cast<uint32_t>(n) * static_cast<uint32_t>(a.K) + k) >> 1) : 0u);
+                const uint32_t dst = pk_base + uint32_t(buf) * kPkBytes + uint32_t(u * 32 + lane) * 16u;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (blk_scales) {
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) {
+                    const int k = n0 + cb * 64;
+                    float sc = 0.f, z = 0.f;
+                    if (row_ok && k < a.K) {
+                        const int g = a.gpr32 <= 1 ? 0 : (a.group_shift >= 0 ? (k >> a.group_shift) : static_cast<int>(static_cast<uint32_t>(k) / static_cast<uint32_t>(a.group32)));
+                        const uint32_t si = static_cast<uint32_t>(n) * static_cast<uint32_t>(a.row_stride32) + g;
+                        sc = a.scale[si];
+                        if (a.zp) z = a.zp[si];
+                    }
+                    sc_base[(buf * 2 + 0) * 128 + cb * 32 + lane] = sc;
+                    sc_base[(buf * 2 + 1) * 128 + cb * 32 + lane] = z;
+                }
+            }
+        };
+
+        int it = 0, blk = 0;
+        if (blockIdx.x < num_tiles) prefetch(blockIdx.x, 0);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1, buf = it & 1;
+            const uint32_t aphase = (it >> 1) & 1u;
+            const int m0 = (tile / num_n) * TM, n0 = (tile % num_n) * TN;
+            const int mrow0 = m0 + q * 32;
+            const int n = mrow0 + lane;
+            const bool row_ok = n < a.N;
+            const int next = tile + gridDim.x;
+            if (next < num_tiles) {
+                prefetch(next, buf ^ 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");      // this tile's codes have landed (own lane's data only)
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            ptx::mbar_wait(tfull_bar(as), aphase);
+            ptx::tc_fence_after();
+            const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * TN;
+            const uint32_t pk = pk_base + uint32_t(buf) * kPkBytes + uint32_t(lane) * 16u;
+            const float* scs = sc_base + (buf * 2) * 128 + lane;
+#pragma unroll 1
+            for (int cb = 0; cb < TN / 64; ++cb) {
+                const int kb0 = n0 + cb * 64;
+                if (kb0 >= a.K || mrow0 >= a.N) break;                     // warp-uniform
+                const uint32_t sbuf = my_o + uint32_t(blk % kStoreBufs) * kStoreBlkBytes;
+                if (blk >= kStoreBufs) {
+                    if (lane == 0) ptx::tma_store_wait_read<kStoreBufs - 1>();
+                    __syncwarp();
+                }
+                const uint32_t row_addr = sbuf + uint32_t(lane) * 128u;
+                float sc = scs[cb * 32], z = scs[128 + cb * 32];
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {                              // two 32-column slices per store block
+                    const int u = cb * 2 + h;
+                    uint32_t r[32];
+                    ptx::tmem_ld32(t_row + u * 32, r);
+                    uint32_t w0, w1, w2, w3;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(pk + uint32_t(u) * 512u));
+                    const uint32_t words[4] = {w0, w1, w2, w3};
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {                          // octet o of the slice
+                        const int k = kb0 + h * 32 + o * 8;
+                        if (!blk_scales && row_ok && k < a.K) {
+                            const int g = a.group_shift >= 0 ? (k >> a.group_shift) : static_cast<int>(static_cast<uint32_t>(k) / static_cast<uint32_t>(a.group32));
+                            const uint32_t si = static_cast<uint32_t>(n) * static_cast<uint32_t>(a.row_stride32) + g;
+                            sc = a.scale[si];
+                            if (a.zp) z = a.zp[si];
+                        }
+                        const uint32_t lo = words[o] & 0x0F0F0F0Fu, hi = (words[o] >> 4) & 0x0F0F0F0Fu;
+                        float y[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t src = (j & 1) ? hi : lo;
+                            const float qv = __uint_as_float(__byte_perm(src, 0x4B000000u, 0x7440 | (j >> 1))) - bias;
+                            float w = a.zp ? fmaf(qv, sc, z) : __fmul_rn(qv, sc);
+                            // result.to(svd dtype): round to bf16 (mantissa RNE on the f32 bit pattern, no conversion pipe)
+                            uint32_t wb = __float_as_uint(w);
+                            wb = (wb + 0x7FFFu + ((wb >> 16) & 1u)) & 0xFFFF0000u;
+                            y[j] = __uint_as_float(wb) + __uint_as_float(r[8 * o + j]);     // addmm_: f32 accumulate, rounded once below
+                        }
+                        uint32_t w4[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __nv_bfloat162 hh = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+                            w4[j] = *reinterpret_cast<uint32_t*>(&hh);
+                        }
+                        const int c8 = h * 4 + o;
+                        ptx::st_shared_v4(row_addr + (uint32_t(c8 ^ (lane & 7)) << 4), w4[0], w4[1], w4[2], w4[3]);
+                    }
+                }
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_2d(&tmap_out, sbuf, kb0, mrow0);
+                    ptx::tma_store_commit();
+                }
+                ++blk;
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+        }
+        if (lane == 0) ptx::tma_store_wait_read<0>();
+        __syncwarp();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+// 2-byte element matrix [rows, cols] with row pitch `pitch_elems`, box {box_cols, box_rows}, swizzle = box_cols * 2 bytes
+int make_tmap16(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t pitch_elems, int box_cols, int box_rows, int swizzle_bytes) {
+    EncodeTiledFn enc = encode_fn();
+    SDNQ_REQUIRE(enc != nullptr, SDNQ_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch_elems) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SDNQ_REQUIRE(r == CUDA_SUCCESS, SDNQ_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld pitch=%lld box=%dx%d)", static_cast<int>(r),
+                 (long long)rows, (long long)cols, (long long)pitch_elems, box_cols, box_rows);
+    return SDNQ_OK;
+}
+
+template <int BITS, bool kBf16Out>
+int launch_svd(const SvdArgs& a, const void* up, int64_t up_pitch, const void* down, int64_t down_pitch, void* out, cudaStream_t st) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(dequant_svd_kernel<BITS, kBf16Out>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); });
+    SDNQ_REQUIRE(attr_err == cudaSuccess, SDNQ_ECUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+    CUtensorMap tu, td, to;
+    int rc = make_tmap16(&tu, up, a.N, a.rank, up_pitch, a.rank, TM, a.rank * 2);
+    if (rc != SDNQ_OK) return rc;
+    rc = make_tmap16(&td, down, a.K, a.rank, down_pitch, a.rank, TN, a.rank * 2);
+    if (rc != SDNQ_OK) return rc;
+    rc = make_tmap16(&to, out, a.N, a.K, a.K, 64, 32, 128);
+    if (rc != SDNQ_OK) return rc;
+    const int tiles = ((a.N + TM - 1) / TM) * ((a.K + TN - 1) / TN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    cudaError_t e = launch_pdl(dequant_svd_kernel<BITS, kBf16Out>, dim3(grid), dim3(kThreads), kSmemBytes, st, tu, td, to, a);
+    if (e != cudaSuccess) return set_error(SDNQ_ECUDA, "launch of dequant_svd_kernel failed: %s", cudaGetErrorString(e));
+    return check_launch("dequant_svd_kernel");
+}
+
+}  // namespace
+
+// Returns SDNQ_OK when it handled the request, 1 when the configuration is outside what the tensor-core kernel covers (the
+// caller then uses the generic kernel), negative on error.
+int dequant_svd_tc(const void* weight, const WFormat& f, const float* scale, const float* zp, int64_t N, int64_t K, int group32, int group_shift,
+                   int gpr32, int row_stride32, const void* up, int64_t up_sn, int64_t up_sr, const void* down, int64_t down_sr, int64_t down_sk,
+                   int rank, int svd_dtype, void* out, int out_dtype, cudaStream_t st) {
+    const bool rank_ok = rank == 16 || rank == 32 || rank == 64;
+    const bool layout_ok = up_sr == 1 && up_sn >= rank && up_sn % 8 == 0 && down_sr == 1 && down_sk >= rank && down_sk % 8 == 0;   // both K-major
+    const bool dtype_ok = svd_dtype == SDNQ_BF16 && out_dtype == SDNQ_BF16;        // bf16 model dtype (f16 operands would need kind::f16 f16 formats)
+    const bool group_ok = (group32 & 7) == 0 || group32 >= K;
+    const bool align_ok = (reinterpret_cast<uintptr_t>(up) & 15) == 0 && (reinterpret_cast<uintptr_t>(down) & 15) == 0 && K % 8 == 0;
+    const bool fmt_ok = f.kind == SDNQ_W_INT && f.bits == 4 && K % 32 == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0;   // 16 B cp.async units
+    if (!(rank_ok && layout_ok && dtype_ok && group_ok && align_ok && fmt_ok) || N * K >= (int64_t(1) << 31)) return 1;
+    SvdArgs a{reinterpret_cast<const uint8_t*>(weight), scale, zp, static_cast<int>(N), static_cast<int>(K), group32, group_shift, gpr32, row_stride32, f, rank, out_dtype};
+    return launch_svd<4, true>(a, up, up_sn, down, down_sk, out, st);
+}
+
+}  // namespace sdnq

@@ -183,6 +183,33 @@ __device__ __forceinline__ void octet_values(const uint8_t* __restrict__ base, i
     codes_to_values<BITS>(codes, f, q);
 }
 
+// ---- integer octet -> 8 floats (code + signed offset) through the magic-number trick: byte b -> 0x4B0000bb = 2^23 + b.
+// `bias` = 2^23 - offset (2^23 + 128 for two's-complement int8 with flip = 0x80808080); int4 / int8 use one PRMT per element.
+template <int BITS>
+__device__ __forceinline__ void octet_to_floats(const uint32_t (&w)[OctetWords<BITS>::N], uint32_t flip, float bias, float (&q)[8]) {
+    if constexpr (BITS == 4) {
+        const uint32_t lo = w[0] & 0x0F0F0F0Fu, hi = (w[0] >> 4) & 0x0F0F0F0Fu;       // even / odd nibbles, one per byte
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            q[2 * i] = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7440 | i)) - bias;
+            q[2 * i + 1] = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7440 | i)) - bias;
+        }
+    } else if constexpr (BITS == 8) {
+        const uint32_t a = w[0] ^ flip, b = w[1] ^ flip;                              // flip = 0x80808080 for two's complement bytes
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            q[i] = __uint_as_float(__byte_perm(a, 0x4B000000u, 0x7440 | i)) - bias;
+            q[4 + i] = __uint_as_float(__byte_perm(b, 0x4B000000u, 0x7440 | i)) - bias;
+        }
+    } else {
+        uint32_t codes[8];
+        decode_octet<BITS>(w, codes);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = __uint_as_float(0x4B000000u | codes[i]) - bias;
+    }
+}
+
+
 #define SDNQ_DISPATCH_BITS(bits, ...)                       \
     switch (bits) {                                         \
         case 1: { constexpr int BITS = 1; __VA_ARGS__; } break; \

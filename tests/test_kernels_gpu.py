@@ -249,3 +249,33 @@ def test_matmul_operands_and_output_match_reference(path):
         else:
             assert np.array_equal(got_xq, ref_xq)
         assert np.array_equal(sx.cpu().numpy(), z["mm_sx"].reshape(-1))
+
+
+# ----------------------------------------------------------------------------------------------- SVD dequant on tensor cores
+@pytest.mark.parametrize("wd,bits", [("int4", 4), ("uint4", 4), ("int3", 3), ("uint2", 2)])
+@pytest.mark.parametrize("N,K,rank,gs", [(128, 256, 32, 128), (300, 640, 32, 128), (520, 1288, 16, 8), (257, 2048, 64, 64), (1280, 1280, 32, 1280)])
+def test_dequant_svd_tensor_core_path(wd, bits, N, K, rank, gs):
+    """int<=4-bit + SVD (plain layout) goes through dequant_svd.cu (tcgen05 rank-r update); compare with the oracle."""
+    rng = np.random.default_rng(N + K + rank + bits)
+    codes = rng.integers(0, 2 ** bits, size=(N, K))
+    packed = torch.from_numpy(O.pack_uint(codes, bits).astype(np.uint8))
+    groups = K // gs
+    sshape = (N, groups, 1) if groups > 1 else (N, 1)
+    scale = torch.from_numpy((rng.random(sshape) * 0.02 + 0.001).astype(np.float32))
+    zp = torch.from_numpy(rng.standard_normal(sshape).astype(np.float32) * 0.05) if wd.startswith("u") else None
+    up = (torch.from_numpy(rng.standard_normal((N, rank)).astype(np.float32)) * 0.1).to(torch.bfloat16)
+    down_phys = (torch.from_numpy(rng.standard_normal((K, rank)).astype(np.float32)) * 0.1).to(torch.bfloat16)   # [K,r] = K-major [r,K]
+    down = down_phys.t()
+    before = ops()._lib.launch_count(reset=True)
+    W = ops().dequant(packed.to(DEV), wd, scale.to(DEV), None if zp is None else zp.to(DEV), N, K, gs if groups > 1 else -1, torch.bfloat16,
+                      svd_up=up.to(DEV), svd_down=down_phys.to(DEV).t(), svd_layout_matmul=False)
+    assert ops()._lib.launch_count() == 1
+    layer = O.Layer(packed.numpy(), scale.numpy(), None if zp is None else zp.numpy(), up.float().numpy(), down.float().numpy(),
+                    weights_dtype=wd, quantized_weight_shape=[N, groups, gs] if groups > 1 else [N, K], result_shape=[N, K] if groups > 1 else None,
+                    group_size=gs if groups > 1 else -1)
+    ref = O.dequantize(layer, dtype="bfloat16")
+    got = to_f32_np(W)
+    du = bf16_ulp_diff(W.cpu(), torch.from_numpy(ref).to(torch.bfloat16))
+    bound = 2.0 ** -8 * np.abs(ref).max(axis=-1, keepdims=True)
+    assert np.all(np.abs(got - ref) <= bound), float(np.abs(got - ref).max())
+    assert float((du > 1).float().mean()) < 1e-3 and float((du > 0).float().mean()) < 0.03

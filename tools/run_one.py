@@ -26,7 +26,7 @@ elif kind == "actq":
     M, K = map(int, sys.argv[2:4])
     x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
     for _ in range(4):
-        ops.act_quant(x, "int8", hadamard_group=int(sys.argv[4]) if len(sys.argv) > 4 else 0)
+        ops.act_quant(x, sys.argv[5] if len(sys.argv) > 5 else "int8", hadamard_group=int(sys.argv[4]) if len(sys.argv) > 4 else 0)
 elif kind == "dequant":
     N, K = map(int, sys.argv[2:4])
     wd, gs = sys.argv[4], int(sys.argv[5])
@@ -37,4 +37,12 @@ elif kind == "dequant":
     zp = torch.rand(N * (K // gs), device=dev) if dtype_dict[wd]["is_unsigned"] else None
     for _ in range(4):
         ops.dequant(w, wd, scale, zp, N, K, gs, torch.bfloat16)
+if kind == "dequant_svd":
+    N, K = map(int, sys.argv[2:4])
+    w = torch.randint(0, 256, (N * K // 2,), dtype=torch.uint8, device=dev)
+    scale = torch.rand(N * (K // 128), device=dev) * 0.01
+    up = torch.randn(N, 32, device=dev, dtype=torch.bfloat16) * 0.1
+    down = (torch.randn(K, 32, device=dev, dtype=torch.bfloat16) * 0.1).t()
+    for _ in range(4):
+        ops.dequant(w, "int4", scale, None, N, K, 128, torch.bfloat16, svd_up=up, svd_down=down)
 torch.cuda.synchronize()
