@@ -9,7 +9,8 @@ the real shapes, each layer with its own random weights quantised
   value  whole-job TFLOP/s (2*M*N*K over all Linears of the step), inputs resident in HBM, step replayed as a CUDA graph
   e2e    same metric through the same call with HOST inputs: pinned host -> device copy of the step inputs and a device ->
          host read of the step output inside the timed region
-  roofline      the dominant kernel (tcgen05 W8A8 GEMM): sum of algorithmic FLOPs / sum of per-launch CUDA-event durations
+  roofline      the dominant kernel (tcgen05 W8A8 GEMM): algorithmic FLOPs of all its launches in a step / their CUDA-event time
+                (the launches replayed back to back as a graph, activations L2-hot and weights cold exactly as in the step)
   cpu_baseline  the oracle port (numpy) on the host cores, bounded sample of the same workload
 
 N > 1 (torchrun): every rank runs the same stack on its own batch shard (weights replicated, no data-path collective), one
@@ -367,46 +368,66 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
 
-    # ---- roofline of the dominant kernel: per-launch CUDA events around every tcgen05 GEMM of one eager step (rank 0)
+    # ---- roofline of the dominant kernel (rank 0): every launch of that kernel in one step, replayed as a graph between CUDA events
     roofline = cpu_base = None
     if rank == 0:
         from sdnq_b200.forward import matmul_operand
         acts = derive_activations(dev_in, shapes)
-        gemm_ms = gemm_flops = k2_ms = k2_bytes = 0.0
-        n_gemm = 0
-        dq_ms = dq_bytes = 0.0
-        n_dq = 0
-        for _, m, n, k, layer in stack:
-            d = layer.sdnq_dequantizer
-            if not d.use_quantized_matmul:
-                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                torch.cuda._sleep(400_000)
-                b0.record()
-                d(layer.weight, layer.scale, layer.zero_point, layer.svd_up, layer.svd_down)
-                b1.record()
-                b1.synchronize()
-                dq_ms += b0.elapsed_time(b1)
+
+        def graph_time(fn, reps=5):
+            """capture fn() (a list of kernel launches) in a CUDA graph and time `reps` replays with CUDA events: per-launch
+            durations without any host launch overhead in between (what the kernels cost inside the real, graph-replayed step)"""
+            fn()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            g.replay()
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(reps):
+                g.replay()
+            t1.record()
+            t1.synchronize()
+            return t0.elapsed_time(t1) / reps
+
+        mm_layers = [(m, n, k, layer) for _, m, n, k, layer in stack if layer.sdnq_dequantizer.use_quantized_matmul and m >= 32]
+        dq_layers = [(m, n, k, layer) for _, m, n, k, layer in stack if not layer.sdnq_dequantizer.use_quantized_matmul]
+        gemm_ms = gemm_flops = k2_ms = k2_bytes = dq_ms = dq_bytes = 0.0
+        n_gemm, n_dq = len(mm_layers), len(dq_layers)
+        if mm_layers:
+            pre = {}
+            for m, n, k, layer in mm_layers:        # one pre-quantised activation per distinct (M, K, mode): L2-hot like in the step
+                d = layer.sdnq_dequantizer
+                key = (m, k, d.quantized_matmul_dtype, d.hadamard_group_size if d.use_hadamard else 0)
+                if key not in pre:
+                    pre[key] = ops.act_quant(acts[(m, k)], key[2], hadamard_group=key[3], want_rowsum=matmul_operand(layer).zp is not None)
+
+            def all_gemms():
+                for m, n, k, layer in mm_layers:
+                    d = layer.sdnq_dequantizer
+                    op = matmul_operand(layer)
+                    xq, sx, zx, rowsum, _ = pre[(m, k, d.quantized_matmul_dtype, d.hadamard_group_size if d.use_hadamard else 0)]
+                    ops.scaled_mm(xq, op.wq, sx, op.sw, layer.bias, torch.bfloat16, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx)
+
+            def all_act_quants():
+                for m, n, k, layer in mm_layers:
+                    d = layer.sdnq_dequantizer
+                    ops.act_quant(acts[(m, k)], d.quantized_matmul_dtype, hadamard_group=d.hadamard_group_size if d.use_hadamard else 0)
+
+            gemm_ms = graph_time(all_gemms)
+            k2_ms = graph_time(all_act_quants)
+            gemm_flops = sum(2.0 * m * n * k for m, n, k, _ in mm_layers)
+            k2_bytes = sum(3.0 * m * k for m, n, k, _ in mm_layers)
+        if dq_layers:
+            def all_dequants():
+                for m, n, k, layer in dq_layers:
+                    layer.sdnq_dequantizer(layer.weight, layer.scale, layer.zero_point, layer.svd_up, layer.svd_down)
+            dq_ms = graph_time(all_dequants)
+            for m, n, k, layer in dq_layers:
                 tensors = [layer.weight, layer.scale, layer.zero_point, layer.svd_up, layer.svd_down]
                 dq_bytes += sum(t.numel() * t.element_size() for t in tensors if t is not None) + 2.0 * n * k
-                n_dq += 1
-                continue
-            if m < 32:
-                continue
-            op = matmul_operand(layer)
-            hg = d.hadamard_group_size if d.use_hadamard else 0
-            a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            torch.cuda._sleep(400_000)        # keep the GPU busy while the launches below are enqueued: events then bracket pure kernel time
-            a0.record()
-            xq, sx, zx, rowsum, _ = ops.act_quant(acts[(m, k)], d.quantized_matmul_dtype, hadamard_group=hg, want_rowsum=op.zp is not None)
-            a1.record()
-            ops.scaled_mm(xq, op.wq, sx, op.sw, layer.bias, torch.bfloat16, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx)
-            a2.record()
-            a2.synchronize()
-            k2_ms += a0.elapsed_time(a1)
-            gemm_ms += a1.elapsed_time(a2)
-            gemm_flops += 2.0 * m * n * k
-            k2_bytes += 3.0 * m * k
-            n_gemm += 1
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -415,14 +436,14 @@ def run_gpu_arm(args):
         bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        if n_dq:
+        if n_dq and not n_gemm:
             ach = dq_bytes / dq_ms / 1e6
             roofline = {"bound": "hbm", "kernel": "dequant_svd_kernel / dequant_kernel (K3)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                         "frac": ach / hbm_peak, "traffic": None, "peak_note": f"HBM copy peak, {src}", "launches": n_dq,
                         "avg_launch_us": 1e3 * dq_ms / n_dq,
                         "algorithmic_bytes": "packed codes + scales (+zp) + svd factors read, bf16 weight written"}
         achieved = gemm_flops / max(gemm_ms, 1e-9) / 1e9
-        if not n_dq:
+        if n_gemm:
             roofline = {"bound": "tensor", "kernel": "gemm_w8a8_kernel (tcgen05 kind::i8 / kind::f8f6f4)", "achieved": achieved, "peak": 2.0 * bf16_peak,
                         "unit": "TFLOP/s", "frac": achieved / (2.0 * bf16_peak), "traffic": None,
                         "peak_note": f"8-bit dense tensor peak taken as 2x the {src} bf16 cuBLAS burst figure ({bf16_peak} TF)",

@@ -181,9 +181,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? 6 : 
         float v[8];
         held[c].get(v);
         if (a.hadamard && k0 < K) {
-            hadamard_warp_dyn(a.hadamard, v);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = v[i] * hfac;   // put() rounds to x.dtype: the reference's matmul returns x.dtype
+            hadamard_warp_dyn(a.hadamard, v, hfac);            // put() rounds to x.dtype: the reference's matmul returns x.dtype
             held[c].put(v);
             held[c].get(v);
         }

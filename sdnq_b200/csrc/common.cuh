@@ -214,55 +214,74 @@ template <int G> struct HadamardInfo {
     static constexpr bool kPow4 = (LOG & 1) == 0;
 };
 
+// sign mask (0 or 0x80000000) of register j of this lane: product over the base-4 digits below LOG of (digit == 3 ? -1 : +1)
 template <int G>
-__device__ __forceinline__ void hadamard_signs(float (&v)[8], int lane) {
+__device__ __forceinline__ uint32_t hadamard_sign_mask(int lane, int j) {
     constexpr int LOG = HadamardInfo<G>::LOG;
-    bool neg = false;                                   // digits held in the lane index
+    bool neg = (j & 3) == 3;                                            // digit 0 = element bits 0-1
+    if (LOG >= 4) neg ^= (j >= 4) && (lane & 1);                        // digit 1 = (lane bit 0, element bit 2)
     if (LOG >= 6) neg ^= ((lane >> 1) & 3) == 3;
     if (LOG >= 8) neg ^= ((lane >> 3) & 3) == 3;
-    const uint32_t base = neg ? 0x80000000u : 0u;
-    const uint32_t odd = (LOG >= 4 && (lane & 1)) ? 0x80000000u : 0u;   // digit 1 = (lane bit 0, element bit 2)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        uint32_t m = base;
-        if ((j & 3) == 3) m ^= 0x80000000u;             // digit 0 = element bits 0-1
-        if (j >= 4) m ^= odd;
-        v[j] = __uint_as_float(__float_as_uint(v[j]) ^ m);
-    }
+    return neg ? 0x80000000u : 0u;
 }
 
+// In:  v = the lane's 8 elements.  Out: v = transformed elements times `factor` (1/sqrt(G) in the activation dtype), for
+// power-of-4 groups with registers (1,2) and (5,6) exchanged and belonging at hadamard_dest<G>() (see above).
+// The butterflies use the packed f32x2 pipe of sm_100 (FADD2 / FFMA2 / FMUL2: two floats per instruction).
 template <int G>
-__device__ __forceinline__ void hadamard_warp(float (&v)[8]) {
+__device__ __forceinline__ void hadamard_warp(float (&v)[8], float factor) {
     constexpr int LOG = HadamardInfo<G>::LOG;
     constexpr bool kPow4 = HadamardInfo<G>::kPow4;
     const int lane = threadIdx.x & 31;
-    if constexpr (kPow4) hadamard_signs<G>(v, lane);
-#pragma unroll
-    for (int b = 1; b < 8 && b < G; b <<= 1) {          // element bits 0..2: in registers
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if ((j & b) == 0) {
-                const float x = v[j], y = v[j | b];
-                v[j] = x + y;
-                v[j | b] = x - y;
-            }
-        }
-    }
-#pragma unroll
-    for (int b = 3; b < LOG; ++b) {                     // element bits 3..: across lanes
-        const int m = 1 << (b - 3);
-        const float sgn = (lane & m) ? -1.0f : 1.0f;       // upper half of the pair computes (other - mine): one FFMA, exact
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float o = __shfl_xor_sync(0xffffffffu, v[j], m);
-            v[j] = fmaf(sgn, v[j], o);
-        }
-    }
     if constexpr (kPow4) {
-        hadamard_signs<G>(v, lane);
-        float t;                                        // output bits 0 <-> 1: registers (1,2) and (5,6) trade places
-        t = v[1]; v[1] = v[2]; v[2] = t;
-        t = v[5]; v[5] = v[6]; v[6] = t;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(__float_as_uint(v[j]) ^ hadamard_sign_mask<G>(lane, j));
+    }
+    float2 p[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = make_float2(v[2 * i] + v[2 * i + 1], v[2 * i] - v[2 * i + 1]);      // element bit 0
+    const float2 minus = make_float2(-1.f, -1.f);
+    if constexpr (G >= 4) {                                                                               // element bit 1
+#pragma unroll
+        for (int i = 0; i < 4; i += 2) {
+            const float2 a = p[i], b = p[i + 1];
+            p[i] = __fadd2_rn(a, b);
+            p[i + 1] = __ffma2_rn(b, minus, a);
+        }
+    }
+    if constexpr (G >= 8) {                                                                               // element bit 2
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float2 a = p[i], b = p[i + 2];
+            p[i] = __fadd2_rn(a, b);
+            p[i + 2] = __ffma2_rn(b, minus, a);
+        }
+    }
+#pragma unroll
+    for (int b = 3; b < LOG; ++b) {                                                                       // element bits 3..: across lanes
+        const int m = 1 << (b - 3);
+        const float sg = (lane & m) ? -1.0f : 1.0f;       // upper half of the pair computes (other - mine)
+        const float2 sgn = make_float2(sg, sg);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 o;
+            o.x = __shfl_xor_sync(0xffffffffu, p[i].x, m);
+            o.y = __shfl_xor_sync(0xffffffffu, p[i].y, m);
+            p[i] = __ffma2_rn(sgn, p[i], o);
+        }
+    }
+    // scale (and, for the H4 family, the output signs folded into the factor; then bits 0 <-> 1 of the output index)
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = kPow4 ? __uint_as_float(__float_as_uint(factor) ^ hadamard_sign_mask<G>(lane, j)) : factor;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = __fmul2_rn(p[i], make_float2(f[2 * i], f[2 * i + 1]));
+    if constexpr (kPow4) {
+        v[0] = p[0].x; v[1] = p[1].x; v[2] = p[0].y; v[3] = p[1].y;
+        v[4] = p[2].x; v[5] = p[3].x; v[6] = p[2].y; v[7] = p[3].y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = p[i].x; v[2 * i + 1] = p[i].y; }
     }
 }
 
@@ -279,15 +298,15 @@ __device__ __forceinline__ int hadamard_dest(int lane, int half) {
     return p;
 }
 
-__device__ __forceinline__ void hadamard_warp_dyn(int G, float (&v)[8]) {
+__device__ __forceinline__ void hadamard_warp_dyn(int G, float (&v)[8], float factor) {
     switch (G) {
-        case 4: hadamard_warp<4>(v); break;
-        case 8: hadamard_warp<8>(v); break;
-        case 16: hadamard_warp<16>(v); break;
-        case 32: hadamard_warp<32>(v); break;
-        case 64: hadamard_warp<64>(v); break;
-        case 128: hadamard_warp<128>(v); break;
-        case 256: hadamard_warp<256>(v); break;
+        case 4: hadamard_warp<4>(v, factor); break;
+        case 8: hadamard_warp<8>(v, factor); break;
+        case 16: hadamard_warp<16>(v, factor); break;
+        case 32: hadamard_warp<32>(v, factor); break;
+        case 64: hadamard_warp<64>(v, factor); break;
+        case 128: hadamard_warp<128>(v, factor); break;
+        case 256: hadamard_warp<256>(v, factor); break;
         default: break;
     }
 }

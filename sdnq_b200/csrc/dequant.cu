@@ -158,10 +158,7 @@ __global__ void __launch_bounds__(kThreads, kPlain ? 5 : 3) dequant_kernel(const
             }
             if constexpr (!kPlain) {
                 if (a.hadamard) {   // un-rotate in the result dtype (dequantizer.py:82-83); whole warp participates
-                    hadamard_warp_dyn(a.hadamard, w);
-                    const float h = hadamard_factor<OutT>(a.hadamard);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) w[i] = w[i] * h;
+                    hadamard_warp_dyn(a.hadamard, w, hadamard_factor<OutT>(a.hadamard));
                 }
             }
             if (valid[u]) {
