@@ -1,4 +1,2 @@
-mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 2>&1 | tee gpurun_out/bench_r01_sdxl_2gpu.json | tail -3 | cut -c1-600
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>&1 | tail -2 | cut -c1-400
+timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x -k "packed_int4" 2>&1 | tail -6
+timeout 600 python -m pytest tests/test_layers_gpu.py -q -m gpu -k "rowwise or forward_matches" 2>&1 | tail -4

@@ -142,6 +142,17 @@ SDNQ_API int sdnq_b200_scaled_mm(const void* a, const void* b, int ab_dtype, con
                         const int32_t* rowsum, const float* zp, const int32_t* colsum, const float* zx,
                         void* out, int out_dtype, int64_t M, int64_t N, int64_t K, void* stream);
 
+/* ---- K1 with the packed-weight unpack fused into the GEMM (north_star "unpack + scale in the GEMM prologue"):
+ *      linear_int8.py:38-44 (per-call unpack_int(...).t_() of a row-wise packed weight) + the scaled matmul above.
+ * b_packed  [N, K*bits/8] packed row-wise int4 / uint4 storage exactly as the reference keeps it (packed_int/pack.py:273-276);
+ *           TMA stages the packed tile in shared memory, four unpack warps expand it to int8 in the UMMA layout, the
+ *           row-wise scale sw[n] (and, for uint4, the zero-point term rowsum[m]*sx[m]*zp[n]) is applied in the epilogue.
+ * a, sx, bias, out as in sdnq_b200_scaled_mm (a is int8).  K % 32 == 0. */
+SDNQ_API int sdnq_b200_scaled_mm_packed(const void* a, const void* b_packed, const sdnq_weight_format* b_fmt, const float* sx,
+                                        const float* sw, const void* bias, int bias_dtype, int64_t bias_ld,
+                                        const int32_t* rowsum, const float* zp, void* out, int out_dtype,
+                                        int64_t M, int64_t N, int64_t K, void* stream);
+
 /* ---- plain matmul:  int_mm_func / fp8_mm_func (kernel_wrappers.py:160-181) -> sdnq_triton_mm
  *      (kernels/triton_mm.py:119-150).  out[M,N] = A @ B as int32 (I8) or f32 (F8E4M3). */
 SDNQ_API int sdnq_b200_mm(const void* a, const void* b, int ab_dtype, void* out, int64_t M, int64_t N, int64_t K, void* stream);

@@ -49,15 +49,21 @@ struct GemmParams {
     int out_dtype;
     int M, N, K;
     int raw;   // plain mm: store the accumulator (s32 / f32) untouched
+    uint32_t w_sub;   // packed 4-bit weights: per-byte offset removed while expanding (0x08080808 for int4, 0 for uint4)
 };
 
-template <int BN>
+// WB = storage bits of the B operand: 8 (int8 / fp8 tiles land in the ring directly by TMA) or 4 (packed int4 / uint4:
+// TMA stages the packed tile, four unpack warps expand it into the ring -- "unpack in the GEMM prologue").
+template <int BN, int WB = 8>
 struct Cfg {
     static constexpr int kStageA = BM * BK;
     static constexpr int kStageB = BN * BK;
     static constexpr int kStageBytes = kStageA + kStageB;
     static constexpr int kVecBytes = 2 * BN * 4;                        // sw[BN] and bias[BN] of the current tile as f32
-    static constexpr int kFixed = kStoreBytes + kVecBytes + 256 /*barriers: 8*(2*stages+4)+4 <= 164 B*/;
+    static constexpr int kPStages = WB < 8 ? 3 : 0;                     // packed staging ring
+    static constexpr int kStageP = WB < 8 ? BN * (BK * WB / 8) : 0;
+    static constexpr int kThreads = WB < 8 ? 320 : 192;
+    static constexpr int kFixed = kStoreBytes + kVecBytes + kPStages * kStageP + 256 /*barriers: 8*(2*stages+4+2*3)+4 <= 212 B*/;
     static constexpr int kStagesRaw = (kSmemLimit - kFixed) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -76,11 +82,12 @@ __device__ __forceinline__ void load8_any(const void* p, int64_t i, int dtype, f
 // kSimple: epilogue is exactly  out = fma(acc * sx[m], sw[n], bias[n])  (bias[n] = 0 when absent): no zero-point
 // terms and no [M,N] bias.  It is the case of every int8 / fp8 symmetric layer and is kept free of the generic
 // path's branches so the unrolled epilogue stays small (instruction cache) and at ~4 instructions per element.
-template <int BN, bool kInt8, int OUT, bool kSimple>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, bool kInt8, int OUT, bool kSimple, int WB>
+__global__ void __launch_bounds__((Cfg<BN, WB>::kThreads), 1)
 gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_o, const GemmParams p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, WB>;
+    constexpr bool kPacked = WB < 8;
     constexpr int kOutBytes = (OUT == OUT_BF16 || OUT == OUT_F16) ? 2 : 4;
     constexpr int CPB = 128 / kOutBytes;              // output columns per 128 B store block: 64 or 32
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -91,12 +98,15 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t smem_o = smem_base + C::kStages * C::kStageBytes;
     float* s_sw = reinterpret_cast<float*>(smem_raw + C::kStages * C::kStageBytes + kStoreBytes);
     float* s_bias = s_sw + BN;
-    const uint32_t bar_base = smem_o + kStoreBytes + C::kVecBytes;
+    const uint32_t smem_p = smem_o + kStoreBytes + C::kVecBytes;       // packed B staging ring (kPacked only)
+    const uint32_t bar_base = smem_p + C::kPStages * C::kStageP;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 2 + s); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
+    auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 4 + s); };
+    auto pempty_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 4 + C::kPStages + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4 + 2 * C::kPStages);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,12 +119,16 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ptx::prefetch_tmap(&tmap_b);
         ptx::prefetch_tmap(&tmap_o);
         for (int s = 0; s < C::kStages; ++s) {
-            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(full_bar(s), kPacked ? 1 + 4 : 1);     // TMA (A) [+ the four unpack warps (B)]
             ptx::mbar_init(empty_bar(s), 1);
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(tfull_bar(s), 1);
             ptx::mbar_init(tempty_bar(s), kEpiWarps);
+        }
+        for (int s = 0; s < C::kPStages; ++s) {
+            ptx::mbar_init(pfull_bar(s), 1);
+            ptx::mbar_init(pempty_bar(s), 4);
         }
         ptx::fence_barrier_init();
     }
@@ -130,7 +144,25 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
     if (warp == 0) {
         // ======================================================== TMA producer
-        if (lane == 0) {
+        if (lane == 0 && kPacked) {
+            // packed weights: A tiles go to the ring, packed B tiles to the staging ring (the unpack warps fill the ring's B half)
+            pdl_wait();
+            int stage = 0, ps = 0;
+            uint32_t phase = 0, pphase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), C::kStageA);
+                    ptx::tma_load_2d(smem_a + stage * C::kStageA, &tmap_a, full_bar(stage), kb * BK, m0);
+                    ptx::mbar_wait(pempty_bar(ps), pphase ^ 1u);
+                    ptx::mbar_arrive_expect_tx(pfull_bar(ps), C::kStageP);
+                    ptx::tma_load_2d(smem_p + ps * C::kStageP, &tmap_b, pfull_bar(ps), kb * (BK * WB / 8), n0);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                    if (++ps == C::kPStages) { ps = 0; pphase ^= 1u; }
+                }
+            }
+        } else if (lane == 0) {
             // The weight operand never depends on the stream predecessor (weights are frozen), the activations do: start
             // the first ring-full of B tiles now, then wait for the predecessor (the activation quantiser) and add the A tiles.
             const int tile0 = blockIdx.x;
@@ -193,6 +225,46 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
                 }
                 ptx::umma_commit(tfull_bar(as));                  // accumulator complete
+            }
+        }
+    } else if (kPacked && warp >= 6) {
+        // ======================================================== unpack warps (6..9): packed int4 / uint4 -> int8 tile
+        // One task = one 16 B chunk of the 128 B-swizzled B tile (16 values of one weight row) = 8 packed bytes: LDS.64,
+        // nibble split + byte interleave (PRMT), offset-binary -> two's complement without cross-byte borrows, STS.128.
+        // Both sides are bank-conflict free (a warp reads 256 contiguous bytes and writes 4 swizzled 128 B rows).
+        const int t = threadIdx.x - 192;
+        int stage = 0, ps = 0;
+        uint32_t phase = 0, pphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                ptx::mbar_wait(pfull_bar(ps), pphase);            // packed tile landed
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1u);     // the ring slot's previous MMAs retired
+                const uint32_t src = smem_p + ps * C::kStageP, dst = smem_b + stage * C::kStageB;
+#pragma unroll 4
+                for (int i = 0; i < BN * 8 / 128; ++i) {
+                    const int idx = i * 128 + t;
+                    const int row = idx >> 3, chunk = idx & 7;
+                    uint32_t x0, x1;
+                    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x0), "=r"(x1) : "r"(src + uint32_t(row * 64 + chunk * 8)));
+                    uint32_t o[4];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t x = h ? x1 : x0;
+                        const uint32_t lo = x & 0x0F0F0F0Fu, hi = (x >> 4) & 0x0F0F0F0Fu;     // even / odd nibbles
+                        const uint32_t a = __byte_perm(lo, hi, 0x5140), b = __byte_perm(lo, hi, 0x7362);   // values 0-3, 4-7
+                        o[2 * h] = ((a | 0x80808080u) - p.w_sub) ^ 0x80808080u;                // code - 8 per byte (int4) / code (uint4)
+                        o[2 * h + 1] = ((b | 0x80808080u) - p.w_sub) ^ 0x80808080u;
+                    }
+                    ptx::st_shared_v4(dst + uint32_t(row * 128) + (uint32_t(chunk ^ (row & 7)) << 4), o[0], o[1], o[2], o[3]);
+                }
+                ptx::fence_proxy_async_smem();                    // generic-proxy writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::mbar_arrive(full_bar(stage));
+                    ptx::mbar_arrive(pempty_bar(ps));
+                }
+                if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                if (++ps == C::kPStages) { ps = 0; pphase ^= 1u; }
             }
         }
     } else {
@@ -408,44 +480,56 @@ EncodeTiledFn get_encode_fn() {
 
 // [rows, cols] row-major matrix of `elem_bytes`-wide elements -> 2-D tensor map with a box of {128 B, box_rows},
 // 128 B swizzle; loads zero-fill out-of-bounds elements, stores clip them.
-int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int elem_bytes, int box_rows) {
+int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int elem_bytes, int box_rows, int box_bytes = 128) {
     EncodeTiledFn enc = get_encode_fn();
     SDNQ_REQUIRE(enc != nullptr, SDNQ_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     const CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
                                    : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * elem_bytes};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_bytes / elem_bytes), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
+    // 128 B boxes are swizzled (UMMA operands, conflict-free staging); narrower boxes (packed weights) stay linear
     CUresult r = enc(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     box_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SDNQ_REQUIRE(r == CUDA_SUCCESS, SDNQ_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld elem=%d box_rows=%d)",
                  static_cast<int>(r), (long long)rows, (long long)cols, elem_bytes, box_rows);
     return SDNQ_OK;
 }
 
-template <int BN, bool kInt8, int OUT, bool kSimple>
+template <int BN, bool kInt8, int OUT, bool kSimple, int WB = 8>
 int launch_gemm(const void* a, const void* b, const GemmParams& p, cudaStream_t st) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, WB>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_w8a8_kernel<BN, kInt8, OUT, kSimple>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+        attr_err = cudaFuncSetAttribute(gemm_w8a8_kernel<BN, kInt8, OUT, kSimple, WB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     });
     SDNQ_REQUIRE(attr_err == cudaSuccess, SDNQ_ECUDA, "cudaFuncSetAttribute(max dynamic smem %d) failed: %s", C::kSmemBytes,
                  cudaGetErrorString(attr_err));
     CUtensorMap ta, tb, to;
     int rc = make_tmap(&ta, a, p.M, p.K, 1, BM);
     if (rc != SDNQ_OK) return rc;
-    rc = make_tmap(&tb, b, p.N, p.K, 1, BN);
+    rc = WB < 8 ? make_tmap(&tb, b, p.N, int64_t(p.K) * WB / 8, 1, BN, BK * WB / 8) : make_tmap(&tb, b, p.N, p.K, 1, BN);
     if (rc != SDNQ_OK) return rc;
     rc = make_tmap(&to, p.out, p.M, p.N, (OUT == OUT_BF16 || OUT == OUT_F16) ? 2 : 4, 32);
     if (rc != SDNQ_OK) return rc;
     const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    cudaError_t e = launch_pdl(gemm_w8a8_kernel<BN, kInt8, OUT, kSimple>, dim3(grid), dim3(kThreads), C::kSmemBytes, st, ta, tb, to, p);
+    cudaError_t e = launch_pdl(gemm_w8a8_kernel<BN, kInt8, OUT, kSimple, WB>, dim3(grid), dim3(C::kThreads), C::kSmemBytes, st, ta, tb, to, p);
     if (e != cudaSuccess) return set_error(SDNQ_ECUDA, "launch of gemm_w8a8_kernel failed: %s", cudaGetErrorString(e));
     return check_launch("gemm_w8a8_kernel");
+}
+
+// packed int4 / uint4 B operand (unpack warps); int8 activations, 128-wide tiles
+int launch_gemm_packed4(const void* a, const void* b, const GemmParams& p, cudaStream_t st) {
+    const bool simple = !p.zp && !p.colsum && (p.bias == nullptr || p.bias_ld == 0);
+    switch (p.out_dtype) {
+        case SDNQ_BF16: return simple ? launch_gemm<128, true, OUT_BF16, true, 4>(a, b, p, st) : launch_gemm<128, true, OUT_BF16, false, 4>(a, b, p, st);
+        case SDNQ_F16: return simple ? launch_gemm<128, true, OUT_F16, true, 4>(a, b, p, st) : launch_gemm<128, true, OUT_F16, false, 4>(a, b, p, st);
+        default: return simple ? launch_gemm<128, true, OUT_F32, true, 4>(a, b, p, st) : launch_gemm<128, true, OUT_F32, false, 4>(a, b, p, st);
+    }
 }
 
 template <int BN, bool kInt8>
@@ -478,7 +562,7 @@ int pick_bn(int M, int N) {
 
 }  // namespace
 
-int scaled_mm_impl(const void* a, const void* b, int ab_dtype, GemmParams p, cudaStream_t st) {
+int scaled_mm_impl(const void* a, const void* b, int ab_dtype, GemmParams p, cudaStream_t st, int wbits = 8) {
     SDNQ_REQUIRE(a && b && p.out, SDNQ_EINVAL, "NULL pointer");
     SDNQ_REQUIRE(ab_dtype == SDNQ_I8 || ab_dtype == SDNQ_F8E4M3, SDNQ_EINVAL, "operand dtype must be int8 or float8_e4m3fn (got %d)", ab_dtype);
     SDNQ_REQUIRE(p.M >= 0 && p.N > 0 && p.K > 0, SDNQ_EINVAL, "bad shape M=%d N=%d K=%d", p.M, p.N, p.K);
@@ -495,6 +579,11 @@ int scaled_mm_impl(const void* a, const void* b, int ab_dtype, GemmParams p, cud
     }
     if (p.M == 0) return SDNQ_OK;
     const bool i8 = ab_dtype == SDNQ_I8;
+    if (wbits != 8) {
+        SDNQ_REQUIRE(wbits == 4 && i8 && !p.raw, SDNQ_EUNSUPPORTED, "in-kernel unpack covers 4-bit integer weights with int8 activations (got %d bits)", wbits);
+        SDNQ_REQUIRE(p.K % 32 == 0, SDNQ_EUNSUPPORTED, "packed 4-bit B needs K %% 32 == 0 (16-byte row pitch), K=%d", p.K);
+        return launch_gemm_packed4(a, b, p, st);
+    }
     switch (pick_bn(p.M, p.N)) {
         case 256: return i8 ? launch_gemm_out<256, true>(a, b, p, st) : launch_gemm_out<256, false>(a, b, p, st);
         case 128: return i8 ? launch_gemm_out<128, true>(a, b, p, st) : launch_gemm_out<128, false>(a, b, p, st);
@@ -510,12 +599,24 @@ extern "C" int sdnq_b200_scaled_mm(const void* a, const void* b, int ab_dtype, c
                                    int bias_dtype, int64_t bias_ld, const int32_t* rowsum, const float* zp, const int32_t* colsum,
                                    const float* zx, void* out, int out_dtype, int64_t M, int64_t N, int64_t K, void* stream) {
     SDNQ_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), SDNQ_EUNSUPPORTED, "dimension too large");
-    GemmParams p{sx, sw, bias, bias_dtype, bias_ld, rowsum, zp, colsum, zx, out, out_dtype, (int)M, (int)N, (int)K, 0};
+    GemmParams p{sx, sw, bias, bias_dtype, bias_ld, rowsum, zp, colsum, zx, out, out_dtype, (int)M, (int)N, (int)K, 0, 0u};
     return scaled_mm_impl(a, b, ab_dtype, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sdnq_b200_scaled_mm_packed(const void* a, const void* b_packed, const sdnq_weight_format* b_fmt, const float* sx, const float* sw,
+                                          const void* bias, int bias_dtype, int64_t bias_ld, const int32_t* rowsum, const float* zp, void* out,
+                                          int out_dtype, int64_t M, int64_t N, int64_t K, void* stream) {
+    SDNQ_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), SDNQ_EUNSUPPORTED, "dimension too large");
+    SDNQ_REQUIRE(b_fmt != nullptr && b_fmt->kind == SDNQ_W_INT && b_fmt->bits == 4, SDNQ_EUNSUPPORTED,
+                 "scaled_mm_packed: only int4 / uint4 weights are expanded in-kernel (other packed formats use sdnq_b200_unpack + scaled_mm)");
+    SDNQ_REQUIRE(b_fmt->is_unsigned == 0 || (zp != nullptr && rowsum != nullptr), SDNQ_EINVAL, "uint4 weights need zp and rowsum");
+    GemmParams p{sx, sw, bias, bias_dtype, bias_ld, rowsum, zp, nullptr, nullptr, out, out_dtype, (int)M, (int)N, (int)K, 0,
+                 b_fmt->is_unsigned ? 0u : 0x08080808u};
+    return scaled_mm_impl(a, b_packed, SDNQ_I8, p, reinterpret_cast<cudaStream_t>(stream), 4);
 }
 
 extern "C" int sdnq_b200_mm(const void* a, const void* b, int ab_dtype, void* out, int64_t M, int64_t N, int64_t K, void* stream) {
     SDNQ_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), SDNQ_EUNSUPPORTED, "dimension too large");
-    GemmParams p{nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, out, SDNQ_I32, (int)M, (int)N, (int)K, 1};
+    GemmParams p{nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, out, SDNQ_I32, (int)M, (int)N, (int)K, 1, 0u};
     return scaled_mm_impl(a, b, ab_dtype, p, reinterpret_cast<cudaStream_t>(stream));
 }

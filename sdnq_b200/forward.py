@@ -8,6 +8,7 @@ Same names / dispatch rule as the reference (forward.py:6-57, layers/linear/*.py
     quantized_linear_forward_fp8_matmul       K2 (e4m3) + K1 tcgen05 fp8 GEMM                   layers/linear/linear_fp8.py:81-104
 
 Every function runs CUDA kernels from libsdnq_b200.so; there is no eager / CPU fallback (a CPU tensor raises)."""
+import os
 from collections.abc import Callable
 
 import torch
@@ -19,11 +20,12 @@ SMALL_M = 32     # rows below this use the dequant path, as upstream does (linea
 
 
 class _MatmulOperand:
-    """The weight as the GEMM reads it: wq [N,K] 1-byte codes (physical K-major [K,N]), sw [N], optional zp [N] / colsum [N]."""
-    __slots__ = ("wq", "sw", "zp", "colsum", "key")
+    """The weight as the GEMM reads it: wq [N,K] 1-byte codes (physical K-major [K,N]), sw [N], optional zp [N] / colsum [N].
+    `packed` = weights_dtype when wq is still the stored packed tensor and the GEMM expands it in its prologue."""
+    __slots__ = ("wq", "sw", "zp", "colsum", "key", "packed")
 
-    def __init__(self, wq, sw, zp, colsum, key):
-        self.wq, self.sw, self.zp, self.colsum, self.key = wq, sw, zp, colsum, key
+    def __init__(self, wq, sw, zp, colsum, key, packed=None):
+        self.wq, self.sw, self.zp, self.colsum, self.key, self.packed = wq, sw, zp, colsum, key, packed
 
 
 def _flat_f32(t):
@@ -49,6 +51,12 @@ def matmul_operand(layer) -> _MatmulOperand:
     zp = colsum = None
     if d.re_quantize_for_matmul:
         wq, sw, zp, colsum = d.re_quantize_matmul_raw(w, s, z, want_colsum=uint8_mm)
+    elif (d.is_packed and d.is_integer and d.num_bits == 4 and mm == "int8" and K % 32 == 0
+          and os.environ.get("SDNQ_B200_CACHE_UNPACKED", "0").lower() in ("0", "false", "no", "")):
+        # row-wise int4 / uint4: keep the packed bytes, the GEMM unpacks them tile by tile in its prologue (no N*K-byte copy)
+        op = _MatmulOperand(w.contiguous(), _flat_f32(s), _flat_f32(z), None, key, packed=d.weights_dtype)
+        layer.__dict__["_sdnq_mm_cache"] = op
+        return op
     elif d.is_packed:
         if d.is_integer:
             wq = ops.unpack(w, d.weights_dtype, (N, K), dtype=torch.int8)          # unsigned codes 0..2^b-1 fit int8 as-is
@@ -89,6 +97,14 @@ def _w8a8_forward(self, input: torch.Tensor) -> torch.Tensor:
     op = matmul_operand(self)
     mm = d.quantized_matmul_dtype
     hg = d.hadamard_group_size if d.use_hadamard else 0
+    if op.packed is not None:
+        xq, sx, _, rowsum, x_rot = ops.act_quant(input, mm, hadamard_group=hg, want_rowsum=op.zp is not None, want_x_rot=self.svd_up is not None)
+        bias = self.bias
+        if self.svd_up is not None:
+            low = torch.mm(x_rot.to(self.svd_down.dtype), self.svd_down)
+            bias = torch.mm(low, self.svd_up) if self.bias is None else torch.addmm(self.bias.to(self.svd_down.dtype), low, self.svd_up)
+        out = ops.scaled_mm_packed(xq, op.wq, op.packed, d.original_shape[0], sx, op.sw, bias, input.dtype, rowsum=rowsum, zp=op.zp)
+        return out.view(*input.shape[:-1], out.shape[-1])
     if self.svd_up is None:
         return ops.linear_w8a8(input, op.wq, mm, op.sw, bias=self.bias, zp=op.zp, colsum=op.colsum, hadamard_group=hg, out_dtype=input.dtype)
     # SVD branch: bias2d = bias + (x_rot @ svd_down[K,r]) @ svd_up[r,N] in the SVD dtype on the rotated, un-quantised

@@ -193,6 +193,25 @@ def scaled_mm(a: torch.Tensor, b_nk: torch.Tensor, sx: torch.Tensor, sw: torch.T
     return out
 
 
+def scaled_mm_packed(a: torch.Tensor, b_packed: torch.Tensor, weights_dtype: str, N: int, sx, sw, bias=None,
+                     out_dtype: torch.dtype = torch.bfloat16, rowsum=None, zp=None) -> torch.Tensor:
+    """K1 with in-kernel unpack: a [M,K] int8, b_packed the stored row-wise packed int4 / uint4 weight ([N*K/2] bytes)."""
+    _require_cuda(a, b_packed)
+    M, K = a.shape
+    out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    bias_ld, bias_code = 0, SDNQ_F32
+    if bias is not None:
+        bias = bias.contiguous()
+        bias_code = dtype_code(bias.dtype)
+        if bias.ndim == 2 and bias.shape[0] != 1:
+            bias_ld = bias.stride(0)
+    fmt = weight_format(weights_dtype, b_packed)
+    with torch.cuda.device(a.device):
+        check(_lib.load().sdnq_b200_scaled_mm_packed(_ptr(a), _ptr(b_packed), fmt, _ptr(sx), _ptr(sw), _ptr(bias), bias_code, bias_ld,
+                                                     _ptr(rowsum), _ptr(zp), _ptr(out), dtype_code(out_dtype), M, N, K, _stream(a)))
+    return out
+
+
 def mm(a: torch.Tensor, b_nk: torch.Tensor) -> torch.Tensor:
     """plain int8 -> int32 / fp8 -> f32 matmul (int_mm_func / fp8_mm_func)."""
     _require_cuda(a, b_nk)

@@ -279,3 +279,31 @@ def test_dequant_svd_tensor_core_path(wd, bits, N, K, rank, gs):
     bound = 2.0 ** -8 * np.abs(ref).max(axis=-1, keepdims=True)
     assert np.all(np.abs(got - ref) <= bound), float(np.abs(got - ref).max())
     assert float((du > 1).float().mean()) < 1e-3 and float((du > 0).float().mean()) < 0.03
+
+
+# ----------------------------------------------------------------------------------------------- GEMM with in-kernel int4 unpack
+@pytest.mark.parametrize("signed", [True, False])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (77, 640, 2048), (300, 1288, 640), (1000, 5120, 640), (2048, 4096, 384), (64, 136, 32)])
+def test_scaled_mm_packed_int4(signed, M, N, K):
+    """packed int4 / uint4 weights expanded by the GEMM's unpack warps == exact integer matmul on the unpacked codes."""
+    rng = np.random.default_rng(M + N + K + signed)
+    codes = rng.integers(0, 16, size=(N, K))
+    packed = torch.from_numpy(O.pack_uint(codes, 4).astype(np.uint8)).to(DEV)
+    wvals = codes - 8 if signed else codes
+    a = torch.from_numpy(rng.integers(-128, 128, size=(M, K)).astype(np.int8))
+    sx = torch.from_numpy((rng.random(M) * 0.05 + 1e-3).astype(np.float32))
+    sw = torch.from_numpy((rng.random(N) * 0.01 + 1e-4).astype(np.float32))
+    bias = torch.from_numpy(rng.standard_normal(N).astype(np.float32)).to(torch.bfloat16)
+    acc = O.int_mm(a.numpy(), wvals.T.astype(np.int8))
+    if signed:
+        got = ops().scaled_mm_packed(a.to(DEV), packed, "int4", N, sx.to(DEV), sw.to(DEV), bias.to(DEV), torch.float32)
+        ref = O.scaled_mm(acc, sx.numpy()[:, None], sw.numpy()[None, :], bias.float().numpy(), out_dtype="float32")
+    else:
+        zp = torch.from_numpy(rng.standard_normal(N).astype(np.float32) * 0.1)
+        rowsum = torch.from_numpy(a.numpy().astype(np.int64).sum(axis=1).astype(np.int32))
+        got = ops().scaled_mm_packed(a.to(DEV), packed, "uint4", N, sx.to(DEV), sw.to(DEV), bias.to(DEV), torch.float32,
+                                     rowsum=rowsum.to(DEV), zp=zp.to(DEV))
+        zb = (rowsum.numpy().astype(np.float32)[:, None] * sx.numpy()[:, None]).astype(np.float32) * zp.numpy()[None, :]
+        zb = (zb.astype(np.float32) + bias.float().numpy()[None, :]).astype(np.float32)
+        ref = O.scaled_mm(acc, sx.numpy()[:, None], sw.numpy()[None, :], zb, out_dtype="float32")
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=2e-6, atol=1e-5)
