@@ -159,7 +159,11 @@ SDNQ_API int sdnq_b200_mm(const void* a, const void* b, int ab_dtype, void* out,
 
 /* ---- fused W8A8 Linear:  quantized_linear_forward_{int8,uint8,fp8}_matmul for layers whose stored
  *      weight is already the matmul operand (linear_int8.py:100-125 with re_quantize_for_matmul cached).
- * One call = K2 + K1 on `stream`; workspace holds xq / sx / zx / rowsum.
+ * One call = K2 + K1 on `stream` (programmatic dependent launch between them); with SDNQ_B200_FUSED=1 in the
+ * environment the single-launch kernel below is used wherever it applies.  The workspace holds the strip counters of
+ * the fused kernel, xq, sx, zx and rowsum.  Its first 4096 bytes must be zero when the workspace is used for the first
+ * time (zero-fill it once after allocating); every call leaves them zero again.  One workspace per stream: calls that
+ * may run concurrently need separate workspaces.
  *   mm_dtype SDNQ_I8 / SDNQ_U8 / SDNQ_F8E4M3; wq physical [N,K]; zp / colsum as in scaled_mm. */
 SDNQ_API size_t sdnq_b200_linear_w8a8_workspace_bytes(int64_t M, int64_t K);
 SDNQ_API int sdnq_b200_linear_w8a8(const void* x, int x_dtype, int64_t ldx, const void* wq, int mm_dtype,
@@ -167,6 +171,17 @@ SDNQ_API int sdnq_b200_linear_w8a8(const void* x, int x_dtype, int64_t ldx, cons
                           const void* bias, int bias_dtype, int hadamard_group,
                           void* out, int out_dtype, int64_t M, int64_t N, int64_t K,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same Linear as ONE kernel launch: the GEMM kernel row-quantises the activations itself (every CTA takes a share
+ * of the rows: bulk copy to shared memory, warp-reduction amax, quantise, codes + scales to the workspace) and its TMA
+ * producers pick the quantised strips up through release/acquire strip counters -- linear_int8.py:14-22 + 100-125 /
+ * linear_fp8.py:14-22 + 81-104 in one kernel.  Covers symmetric int8 / float8_e4m3fn without Hadamard or zero-points,
+ * x and out both bf16 or both f16, vector (or no) bias; anything else returns SDNQ_EUNSUPPORTED.  Bit-identical to
+ * act_quant + scaled_mm.  Workspace contract as for sdnq_b200_linear_w8a8. */
+SDNQ_API int sdnq_b200_linear_w8a8_fused(const void* x, int x_dtype, int64_t ldx, const void* wq, int mm_dtype,
+                                const float* sw, const void* bias, int bias_dtype,
+                                void* out, int out_dtype, int64_t M, int64_t N, int64_t K,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* number of kernels launched by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches) */

@@ -17,7 +17,9 @@
 // A = activations [M,K] (row-major, K contiguous); B = weight, the reference's K-major [K,N] operand, i.e.
 // physically [N,K] with K contiguous -- exactly the "TN" shape tcgen05 wants, so no transposes anywhere.
 #include <mutex>
+#include <type_traits>
 
+#include "act_quant.cuh"
 #include "ptx.cuh"
 
 namespace sdnq {
@@ -50,7 +52,14 @@ struct GemmParams {
     int M, N, K;
     int raw;   // plain mm: store the accumulator (s32 / f32) untouched
     uint32_t w_sub;   // packed 4-bit weights: per-byte offset removed while expanding (0x08080808 for int4, 0 for uint4)
+    // fused activation quantiser (XM != 0): un-quantised activations in, xq / sx written by this kernel
+    const void* fx;
+    int64_t fldx;
+    uint8_t* fxq;
+    float* fsx;
+    int* fsync;       // [kSyncStrips] rows quantised per 128-row strip | [kSyncStrips] tiles that consumed the strip
 };
+constexpr int kSyncStrips = 512;
 
 // WB = storage bits of the B operand: 8 (int8 / fp8 tiles land in the ring directly by TMA) or 4 (packed int4 / uint4:
 // TMA stages the packed tile, four unpack warps expand it into the ring -- "unpack in the GEMM prologue").
@@ -63,7 +72,7 @@ struct Cfg {
     static constexpr int kPStages = WB < 8 ? 3 : 0;                     // packed staging ring
     static constexpr int kStageP = WB < 8 ? BN * (BK * WB / 8) : 0;
     static constexpr int kThreads = WB < 8 ? 320 : 192;
-    static constexpr int kFixed = kStoreBytes + kVecBytes + kPStages * kStageP + 256 /*barriers: 8*(2*stages+4+2*3)+4 <= 212 B*/;
+    static constexpr int kFixed = kStoreBytes + kVecBytes + kPStages * kStageP + 256 /*barriers: 8*(2*stages+4+2*3)+4+16 <= 228 B*/;
     static constexpr int kStagesRaw = (kSmemLimit - kFixed) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -82,7 +91,15 @@ __device__ __forceinline__ void load8_any(const void* p, int64_t i, int dtype, f
 // kSimple: epilogue is exactly  out = fma(acc * sx[m], sw[n], bias[n])  (bias[n] = 0 when absent): no zero-point
 // terms and no [M,N] bias.  It is the case of every int8 / fp8 symmetric layer and is kept free of the generic
 // path's branches so the unrolled epilogue stays small (instruction cache) and at ~4 instructions per element.
-template <int BN, bool kInt8, int OUT, bool kSimple, int WB>
+//
+// XM != 0 (1: bf16 activations, 2: f16): the activation quantiser runs inside this kernel ("phase 1").  Every CTA
+// quantises an equal share of the rows of x (1-D bulk copies into the still idle A half of the ring, amax + quantise
+// from shared memory, codes and row scales to the workspace in L2), publishes per-128-row-strip progress counters with
+// release semantics, and the TMA producer of a tile acquires its strip's counter before it loads A.  One launch per
+// Linear instead of two: the dependent-launch gap (~2.5 us, as long as the GEMM itself at SD-XL sizes) disappears,
+// and the weight prefetch overlaps the quantisation.  All CTAs are co-resident (grid <= SMs, 1 CTA/SM), which the
+// cross-CTA wait relies on.
+template <int BN, bool kInt8, int OUT, bool kSimple, int WB, int XM>
 __global__ void __launch_bounds__((Cfg<BN, WB>::kThreads), 1)
 gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_o, const GemmParams p) {
@@ -107,6 +124,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 4 + s); };
     auto pempty_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 4 + C::kPStages + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4 + 2 * C::kPStages);
+    const uint32_t xstage_bar = tmem_slot + 8u;                        // fused quantiser: bulk copies of x landed
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -130,6 +148,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ptx::mbar_init(pfull_bar(s), 1);
             ptx::mbar_init(pempty_bar(s), 4);
         }
+        if constexpr (XM != 0) ptx::mbar_init(xstage_bar, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -141,6 +160,100 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     pdl_launch_dependents();     // our own dependents may begin their prologue
+
+    // weight prefetch bookkeeping shared by the producer branch below
+    const int tile0 = blockIdx.x;
+    const int npre = (!kPacked && tile0 < num_tiles) ? (num_kb < C::kStages ? num_kb : C::kStages) : 0;
+    if constexpr (XM != 0) {
+        // ======================================================== phase 1: quantise this CTA's share of the activation rows
+        if (warp == 0 && lane == 0 && npre > 0) {                 // weights first: they do not depend on anything
+            const int n0 = (tile0 % num_n) * BN;
+            for (int s = 0; s < npre; ++s) {
+                ptx::mbar_arrive_expect_tx(full_bar(s), C::kStageBytes);
+                ptx::tma_load_2d(smem_b + s * C::kStageB, &tmap_b, full_bar(s), s * BK, n0);
+            }
+        }
+        pdl_wait();                                               // x belongs to the stream predecessor
+        using XT = typename std::conditional<XM == 1, __nv_bfloat16, __half>::type;
+        constexpr int MODE = kInt8 ? SDNQ_I8 : SDNQ_F8E4M3;
+        constexpr int kWarpsAll = C::kThreads / 32;
+        const int K = p.K;
+        const int rpc = (p.M + int(gridDim.x) - 1) / int(gridDim.x);
+        const int r0 = min(p.M, int(blockIdx.x) * rpc), r1 = min(p.M, r0 + rpc);
+        const uint32_t row_bytes = uint32_t(K) * 2u;
+        const int rpb = int(uint32_t(C::kStages * C::kStageA) / row_bytes);      // rows per staging batch (host guarantees >= 1)
+        uint32_t xphase = 0;
+        for (int rb = r0; rb < r1; rb += rpb) {
+            const int re = min(r1, rb + rpb);
+            if (warp == 0) {
+                if (lane == 0) ptx::mbar_arrive_expect_tx(xstage_bar, uint32_t(re - rb) * row_bytes);
+                __syncwarp();
+                for (int r = rb + lane; r < re; r += 32)
+                    ptx::bulk_load_1d(smem_a + uint32_t(r - rb) * row_bytes,
+                                      reinterpret_cast<const uint8_t*>(p.fx) + int64_t(r) * p.fldx * 2, row_bytes, xstage_bar);
+            }
+            ptx::mbar_wait(xstage_bar, xphase);
+            xphase ^= 1u;
+            for (int r = rb + warp; r < re; r += kWarpsAll) {
+                const uint8_t* srow = smem_raw + size_t(r - rb) * row_bytes;
+                float amax = 0.f;
+#pragma unroll 4
+                for (int k = lane * 8; k < K; k += 256) {
+                    actq::Held<XT> h;
+                    h.raw = *reinterpret_cast<const uint4*>(srow + 2 * k);
+                    float v[8];
+                    h.get(v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[i]));
+                }
+                amax = warp_max(amax);
+                const float scale = __fdiv_rn(amax, kInt8 ? 127.f : 448.f);     // get_scale_symmetric (quant_utils.py:264-299)
+                const actq::RowDivider divider(scale);
+                const bool safe = divider.safe();
+                uint8_t* dst = p.fxq + int64_t(r) * K;
+                int unused = 0;
+#pragma unroll 2
+                for (int k = lane * 8; k < K; k += 256) {
+                    actq::Held<XT> h;
+                    h.raw = *reinterpret_cast<const uint4*>(srow + 2 * k);
+                    float v[8];
+                    h.get(v);
+                    const uint2 q = safe ? actq::quantise8<MODE, true>(v, divider, 0.f, false, unused)
+                                         : actq::quantise8<MODE, false>(v, divider, 0.f, false, unused);
+                    *reinterpret_cast<uint2*>(dst + k) = q;
+                }
+                if (lane == 0) p.fsx[r] = scale;
+                // publish the row: every lane orders its stores against the async proxy (the TMA engines of the other
+                // CTAs read them), the warp converges, one lane bumps the strip counter with release semantics
+                ptx::fence_proxy_async_all();
+                __syncwarp();
+                if (lane == 0) ptx::red_release_gpu_add(p.fsync + r / BM, 1);
+            }
+            if (rb + rpb < r1) __syncthreads();                   // the staging rows are overwritten by the next batch
+        }
+        __syncthreads();                                          // staging reads are done before A tiles land in the same memory
+    }
+    // producer side of the cross-CTA dependency: all rows of the tile's 128-row strip are quantised
+    auto acquire_strip = [&](int ms) {
+        if constexpr (XM != 0) {
+            const int target = min(BM, p.M - ms * BM);
+            int spins = 0;
+            while (ptx::ld_acquire_gpu(p.fsync + ms) < target) {
+                if (++spins > (1 << 27)) __trap();                // seconds: a CTA of this grid never ran (not co-resident?)
+            }
+            ptx::fence_proxy_async_all();
+        }
+    };
+    // ... and, off the critical path, once the tile's loads are on their way: the last of the strip's num_n consumers
+    // re-arms both counters for the next launch on this workspace
+    auto release_strip = [&](int ms) {
+        if constexpr (XM != 0) {
+            if (atomicAdd(p.fsync + kSyncStrips + ms, 1) == num_n - 1) {
+                p.fsync[kSyncStrips + ms] = 0;
+                p.fsync[ms] = 0;
+            }
+        }
+    };
 
     if (warp == 0) {
         // ======================================================== TMA producer
@@ -165,24 +278,26 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         } else if (lane == 0) {
             // The weight operand never depends on the stream predecessor (weights are frozen), the activations do: start
             // the first ring-full of B tiles now, then wait for the predecessor (the activation quantiser) and add the A tiles.
-            const int tile0 = blockIdx.x;
-            const int npre = (tile0 < num_tiles) ? (num_kb < C::kStages ? num_kb : C::kStages) : 0;
-            if (npre > 0) {
-                const int n0 = (tile0 % num_n) * BN;
-                for (int s = 0; s < npre; ++s) {
-                    ptx::mbar_arrive_expect_tx(full_bar(s), C::kStageBytes);
-                    ptx::tma_load_2d(smem_b + s * C::kStageB, &tmap_b, full_bar(s), s * BK, n0);
+            if constexpr (XM == 0) {
+                if (npre > 0) {
+                    const int n0 = (tile0 % num_n) * BN;
+                    for (int s = 0; s < npre; ++s) {
+                        ptx::mbar_arrive_expect_tx(full_bar(s), C::kStageBytes);
+                        ptx::tma_load_2d(smem_b + s * C::kStageB, &tmap_b, full_bar(s), s * BK, n0);
+                    }
                 }
+                pdl_wait();
             }
-            pdl_wait();
             if (npre > 0) {
                 const int m0 = (tile0 / num_n) * BM;
+                acquire_strip(tile0 / num_n);
                 for (int s = 0; s < npre; ++s) ptx::tma_load_2d(smem_a + s * C::kStageA, &tmap_a, full_bar(s), s * BK, m0);
             }
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+                if (tile != tile0) acquire_strip(tile / num_n);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     if (tile == tile0 && kb < npre) {             // already in flight (prefetched above)
                         if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
@@ -194,6 +309,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     ptx::tma_load_2d(smem_b + stage * C::kStageB, &tmap_b, full_bar(stage), kb * BK, n0);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
                 }
+                release_strip(tile / num_n);
             }
         }
     } else if (warp == 1) {
@@ -284,7 +400,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int m = mrow0 + lane;
             const bool m_ok = m < p.M;
             float sxm = 0.f, zxm = 0.f, rsx = 0.f;
-            if (OUT != OUT_RAW32 && m_ok) {
+            if (XM == 0 && OUT != OUT_RAW32 && m_ok) {
                 sxm = p.sx[m];
                 if (p.zx) zxm = p.zx[m];
                 if (p.rowsum) rsx = __fmul_rn(static_cast<float>(p.rowsum[m]), sxm);   // (rowsum -> f32) * sx
@@ -311,6 +427,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             ptx::mbar_wait(tfull_bar(as), aphase);
             ptx::tc_fence_after();
+            if (XM != 0 && m_ok) sxm = __ldcg(p.sx + m);          // written by phase 1 of some CTA of this grid: read it from L2, after the accumulator
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
 #pragma unroll 1
             for (int cb = 0; cb < BN / CPB; ++cb) {
@@ -498,13 +615,13 @@ int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int
     return SDNQ_OK;
 }
 
-template <int BN, bool kInt8, int OUT, bool kSimple, int WB = 8>
+template <int BN, bool kInt8, int OUT, bool kSimple, int WB = 8, int XM = 0>
 int launch_gemm(const void* a, const void* b, const GemmParams& p, cudaStream_t st) {
     using C = Cfg<BN, WB>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_w8a8_kernel<BN, kInt8, OUT, kSimple, WB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+        attr_err = cudaFuncSetAttribute(gemm_w8a8_kernel<BN, kInt8, OUT, kSimple, WB, XM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     });
     SDNQ_REQUIRE(attr_err == cudaSuccess, SDNQ_ECUDA, "cudaFuncSetAttribute(max dynamic smem %d) failed: %s", C::kSmemBytes,
                  cudaGetErrorString(attr_err));
@@ -516,8 +633,9 @@ int launch_gemm(const void* a, const void* b, const GemmParams& p, cudaStream_t 
     rc = make_tmap(&to, p.out, p.M, p.N, (OUT == OUT_BF16 || OUT == OUT_F16) ? 2 : 4, 32);
     if (rc != SDNQ_OK) return rc;
     const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    cudaError_t e = launch_pdl(gemm_w8a8_kernel<BN, kInt8, OUT, kSimple, WB>, dim3(grid), dim3(C::kThreads), C::kSmemBytes, st, ta, tb, to, p);
+    // fused quantiser: always one CTA per SM (CTAs without a tile still quantise their share of the rows)
+    const int grid = (XM != 0 || tiles >= num_sms()) ? num_sms() : tiles;
+    cudaError_t e = launch_pdl(gemm_w8a8_kernel<BN, kInt8, OUT, kSimple, WB, XM>, dim3(grid), dim3(C::kThreads), C::kSmemBytes, st, ta, tb, to, p);
     if (e != cudaSuccess) return set_error(SDNQ_ECUDA, "launch of gemm_w8a8_kernel failed: %s", cudaGetErrorString(e));
     return check_launch("gemm_w8a8_kernel");
 }
@@ -546,6 +664,8 @@ int launch_gemm_out(const void* a, const void* b, const GemmParams& p, cudaStrea
 // Tile-N choice: the widest tile that still gives every SM work; BN=256 halves the per-MMA shared-memory
 // operand traffic relative to BN=128, so it wins whenever the grid is full either way.
 int pick_bn(int M, int N) {
+    static const int forced = [] { const char* e = getenv("SDNQ_B200_BN"); return e ? atoi(e) : 0; }();   // tuning knob
+    if (forced == 128 || forced == 256) return forced;
     const int sms = num_sms();
     const int num_m = (M + BM - 1) / BM;
     auto waves_eff = [&](int bn) {
@@ -589,6 +709,33 @@ int scaled_mm_impl(const void* a, const void* b, int ab_dtype, GemmParams p, cud
         case 128: return i8 ? launch_gemm_out<128, true>(a, b, p, st) : launch_gemm_out<128, false>(a, b, p, st);
         default: return i8 ? launch_gemm_out<128, true>(a, b, p, st) : launch_gemm_out<128, false>(a, b, p, st);
     }
+}
+
+// Fused W8A8 Linear (one launch): quantise x [M,K] (bf16 / f16) per row into xq / sx and run the scaled GEMM on it.
+// Returns 1 when the problem is outside what the fused kernel covers (the caller then runs K2 + K1).
+//   covered: symmetric int8 / e4m3 activations without Hadamard, no zero-point terms, vector (or no) bias,
+//            out dtype == x dtype, one row of x fits the staging area, <= kSyncStrips row strips.
+int linear_fused_impl(const void* x, int x_dtype, int64_t ldx, const void* wq, int ab_dtype, const float* sw, const void* bias,
+                      int bias_dtype, void* out, int out_dtype, int64_t M, int64_t N, int64_t K, uint8_t* xq, float* sx, int* sync,
+                      cudaStream_t st) {
+    if (!(x_dtype == SDNQ_BF16 || x_dtype == SDNQ_F16) || out_dtype != x_dtype) return 1;
+    if (ab_dtype != SDNQ_I8 && ab_dtype != SDNQ_F8E4M3) return 1;
+    if (M <= 0 || M > int64_t(kSyncStrips) * BM || K % 16 != 0 || N % 8 != 0 || ldx % 8 != 0) return 1;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return 1;
+    // per-CTA share of x beyond a few staging batches: the quantiser is no longer latency-bound and the
+    // stand-alone pre-pass (more warps, registers instead of shared memory) is the better tool
+    if (M * K > (int64_t(16) << 20)) return 1;
+    const int bn = pick_bn(int(M), int(N));
+    const int64_t stage_bytes = bn == 256 ? int64_t(Cfg<256>::kStages) * Cfg<256>::kStageA : int64_t(Cfg<128>::kStages) * Cfg<128>::kStageA;
+    if (K * 2 > stage_bytes) return 1;
+    GemmParams p{sx, sw, bias, bias_dtype, 0, nullptr, nullptr, nullptr, nullptr, out, out_dtype, int(M), int(N), int(K), 0, 0u, x, ldx, xq, sx, sync};
+    const bool i8 = ab_dtype == SDNQ_I8;
+    const bool bf = x_dtype == SDNQ_BF16;
+#define SDNQ_FUSED(BN_)                                                                                                    \
+    (i8 ? (bf ? launch_gemm<BN_, true, OUT_BF16, true, 8, 1>(xq, wq, p, st) : launch_gemm<BN_, true, OUT_F16, true, 8, 2>(xq, wq, p, st))  \
+        : (bf ? launch_gemm<BN_, false, OUT_BF16, true, 8, 1>(xq, wq, p, st) : launch_gemm<BN_, false, OUT_F16, true, 8, 2>(xq, wq, p, st)))
+    return bn == 256 ? SDNQ_FUSED(256) : SDNQ_FUSED(128);
+#undef SDNQ_FUSED
 }
 
 }  // namespace sdnq

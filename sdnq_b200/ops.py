@@ -231,13 +231,16 @@ def _workspace(dev, nbytes):
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        # zero-filled: the first 4 KB hold the fused kernel's cross-CTA strip counters, which every launch leaves at zero
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
         _WORKSPACES[key] = ws
     return ws
 
 
-def linear_w8a8(x, wq_nk, matmul_dtype, sw, bias=None, zp=None, colsum=None, hadamard_group=0, out_dtype=None) -> torch.Tensor:
-    """K2 + K1 in one C call (per-stream cached workspace)."""
+def linear_w8a8(x, wq_nk, matmul_dtype, sw, bias=None, zp=None, colsum=None, hadamard_group=0, out_dtype=None, fused=None) -> torch.Tensor:
+    """The W8A8 Linear in one C call (per-stream cached workspace): K2 + K1 chained by programmatic dependent launch.
+    fused=True asks for the single-launch kernel (in-kernel activation quantiser; raises when the case is not covered),
+    fused=None leaves the choice to the library (SDNQ_B200_FUSED)."""
     _require_cuda(x, wq_nk)
     lib = _lib.load()
     K = x.shape[-1]
@@ -249,6 +252,14 @@ def linear_w8a8(x, wq_nk, matmul_dtype, sw, bias=None, zp=None, colsum=None, had
     out = torch.empty((M, N), dtype=out_dtype, device=x.device)
     nbytes = lib.sdnq_b200_linear_w8a8_workspace_bytes(M, K)
     ws = _workspace(x.device, nbytes)
+    if fused:
+        if zp is not None or colsum is not None or hadamard_group:
+            raise _lib.SDNQKernelError("fused Linear: no zero-point terms and no Hadamard rotation")
+        with torch.cuda.device(x.device):
+            check(lib.sdnq_b200_linear_w8a8_fused(_ptr(x2), dtype_code(x2.dtype), x2.stride(0), _ptr(wq_nk), mm_code(matmul_dtype), _ptr(sw),
+                                                  _ptr(bias), dtype_code(bias.dtype) if bias is not None else SDNQ_F32, _ptr(out),
+                                                  dtype_code(out_dtype), M, N, K, _ptr(ws), ws.numel(), _stream(x)))
+        return out.view(*x.shape[:-1], N)
     with torch.cuda.device(x.device):
         check(lib.sdnq_b200_linear_w8a8(_ptr(x2), dtype_code(x2.dtype), x2.stride(0), _ptr(wq_nk), mm_code(matmul_dtype), _ptr(sw),
                                         _ptr(zp), _ptr(colsum), _ptr(bias), dtype_code(bias.dtype) if bias is not None else SDNQ_F32,

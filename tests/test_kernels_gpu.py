@@ -307,3 +307,110 @@ def test_scaled_mm_packed_int4(signed, M, N, K):
         zb = (zb.astype(np.float32) + bias.float().numpy()[None, :]).astype(np.float32)
         ref = O.scaled_mm(acc, sx.numpy()[:, None], sw.numpy()[None, :], zb, out_dtype="float32")
     np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=2e-6, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------------------------- fused quantise + GEMM (one launch)
+FUSED_SHAPES = [(1024, 1280, 1280), (4096, 640, 640), (77, 1280, 2048), (333, 136, 272), (1, 64, 32), (32, 8, 16), (128 * 5 + 7, 648, 5120),
+                (2500, 256, 4096 + 16), (148 * 2 + 1, 384, 16384)]
+
+
+@pytest.mark.parametrize("mm", ["int8", "float8_e4m3fn"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", FUSED_SHAPES)
+def test_linear_w8a8_fused_matches_two_kernel_path(mm, dtype, M, N, K):
+    """linear_w8a8(fused=True) (single launch: in-kernel activation quantiser + cross-CTA strip flags) must be bit-identical to
+    act_quant followed by scaled_mm, launch after launch on the same workspace (the counters re-arm themselves)."""
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    x = (torch.randn(M, K, generator=g) * 3).to(dtype).to(DEV)
+    if M > 2:
+        x[1].zero_()                                     # all-zero row: scale 0, codes 0
+        x[2, 0] = 1e4                                    # outlier row
+    if mm == "int8":
+        w = torch.randint(-127, 128, (N, K), generator=g, dtype=torch.int8).to(DEV)
+    else:
+        w = (torch.randn(N, K, generator=g) * 2).to(torch.float8_e4m3fn).to(DEV)
+    sw = (torch.rand(N, generator=g) * 0.01 + 1e-4).to(DEV)
+    bias = torch.randn(N, generator=g).to(dtype).to(DEV)
+    o = ops()
+    o._lib.launch_count(reset=True)
+    got = o.linear_w8a8(x, w, mm, sw, bias=bias, out_dtype=dtype, fused=True)
+    assert o._lib.launch_count() == 1, "expected the single fused launch"
+    xq, sx, *_ = o.act_quant(x, mm)
+    ref = o.scaled_mm(xq, w, sx, sw, bias, dtype)
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+    for _ in range(3):                                   # same workspace again, and without bias
+        got2 = o.linear_w8a8(x, w, mm, sw, bias=None, out_dtype=dtype, fused=True)
+    ref2 = o.scaled_mm(xq, w, sx, sw, None, dtype)
+    assert torch.equal(got2.view(torch.int16), ref2.view(torch.int16))
+    torch.cuda.synchronize()
+    ws = next(iter(o._WORKSPACES.values()))
+    assert int(ws[:4096].view(torch.int32).abs().sum()) == 0, "strip counters must be left at zero"
+
+
+def test_linear_w8a8_fused_strided_rows_and_graph_replay():
+    """x with a row stride (ldx > K), interleaved shapes on one workspace, and CUDA-graph replay with changing inputs."""
+    o = ops()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    big = torch.randn(600, 1024, generator=g).to(torch.bfloat16).to(DEV)
+    x = big[:, 128:128 + 640]                            # ldx = 1024, K = 640, 16 B aligned
+    w = torch.randint(-127, 128, (328, 640), generator=g, dtype=torch.int8).to(DEV)
+    w2 = torch.randint(-127, 128, (640, 1024), generator=g, dtype=torch.int8).to(DEV)
+    sw = (torch.rand(328, generator=g) * 0.01 + 1e-4).to(DEV)
+    sw2 = (torch.rand(640, generator=g) * 0.01 + 1e-4).to(DEV)
+
+    def both():
+        return (o.linear_w8a8(x, w, "int8", sw, out_dtype=torch.bfloat16, fused=True),
+                o.linear_w8a8(big, w2, "int8", sw2, out_dtype=torch.bfloat16, fused=True))
+
+    def refs():
+        xq, sx, *_ = o.act_quant(x, "int8")
+        bq, bs, *_ = o.act_quant(big, "int8")
+        return o.scaled_mm(xq, w, sx, sw, None, torch.bfloat16), o.scaled_mm(bq, w2, bs, sw2, None, torch.bfloat16)
+
+    for a, b in zip(both(), refs()):
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        both()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ya, yb = both()
+    for seed in (1, 2, 3):
+        big.copy_(torch.randn(600, 1024, generator=torch.Generator().manual_seed(seed)).to(torch.bfloat16))
+        graph.replay()
+        torch.cuda.synchronize()
+        for a, b in zip((ya, yb), refs()):
+            assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+
+
+# ----------------------------------------------------------------------------------------------- flat dequant kernel (int4 / int8)
+@pytest.mark.parametrize("wd", ["int4", "uint4", "int8", "uint8"])
+@pytest.mark.parametrize("N,K,gs", [(64, 640, 128), (33, 1280, 32), (7, 24, -1), (100, 1296, 8), (5, 16, 16), (257, 2048, -1), (1280, 5120, 128), (3, 4104, -1)])
+@pytest.mark.parametrize("out_dtype", ["bfloat16", "float32"])
+def test_dequant_flat_path_bit_exact(wd, N, K, gs, out_dtype):
+    """int4 / int8 weights with in-row groups (or row-wise scales) take the flat, fully coalesced kernel; bit-exact vs the oracle."""
+    bits = 4 if wd.endswith("4") else 8
+    rng = np.random.default_rng(N * 3 + K + bits)
+    codes = rng.integers(0, 2 ** bits, size=(N, K))
+    if bits == 4:
+        stored = O.pack_uint(codes, 4).astype(np.uint8)
+    else:
+        stored = codes.astype(np.uint8) if wd == "uint8" else (codes - 128).astype(np.int8)
+    groups = K // gs if gs > 0 else 1
+    sshape = (N, groups, 1) if groups > 1 else (N, 1)
+    scale = (rng.random(sshape) * 0.02 + 0.001).astype(np.float32)
+    zp = (rng.standard_normal(sshape) * 0.05).astype(np.float32) if wd.startswith("u") else None
+    td = getattr(torch, out_dtype)
+    w_dev = torch.from_numpy(stored).to(DEV)
+    ops()._lib.launch_count(reset=True)
+    W = ops().dequant(w_dev, wd, torch.from_numpy(scale).to(DEV), None if zp is None else torch.from_numpy(zp).to(DEV), N, K,
+                      gs if groups > 1 else -1, td)
+    assert ops()._lib.launch_count() == 1
+    layer = O.Layer(stored if bits == 4 else (stored.reshape(N, groups, K // groups) if groups > 1 else stored), scale, zp, None, None, weights_dtype=wd,
+                    quantized_weight_shape=[N, groups, gs] if groups > 1 else [N, K], result_shape=[N, K] if groups > 1 else None,
+                    group_size=gs if groups > 1 else -1)
+    ref = O.dequantize(layer, dtype=out_dtype)
+    assert np.array_equal(to_f32_np(W).reshape(N, K), np.asarray(ref, dtype=np.float32).reshape(N, K))
