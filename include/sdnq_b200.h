@@ -1,5 +1,5 @@
 /*
- * sdnq_b200.h -- C ABI of the B200-native SDNQ quantized-Linear kernels.
+ * sdnq_b200.h -- C ABI of the B200-native SDNQ quantized-Linear / Conv kernels.
  *
  * Every entry point is what a binding of the reference's kernel layer for this
  * path would call; the reference interface each one replaces is cited as
@@ -103,6 +103,21 @@ SDNQ_API int sdnq_b200_dequant(const void* weight, const sdnq_weight_format* fmt
                       int svd_rank, int svd_dtype, int hadamard_group,
                       void* out, int out_dtype, void* stream);
 
+/* ---- K3 for convolution weights:  dequantize_symmetric / _asymmetric / _codebook as a broadcast over the quantised view
+ *      (dequantizer.py:15-131) for layers whose scale is not one value per contiguous K-group: Conv weights reduce over
+ *      the input-channel axis only (scale [N,1,kh,kw], grouped [N,C/g,1,kh,kw]; quantizer.py:95-110, 185-199), ConvTranspose
+ *      weights over axis 0.
+ *   weight         stored codes in flattened order of the quantised view (packed or not)
+ *   dims[ndim]     shape of the quantised view (ndim <= 6, product % 8 == 0)
+ *   scale_strides  element stride of scale / zero_point (and, times 2^bits, of the codebook levels) along each axis of the
+ *                  view, 0 on broadcast axes
+ *   addend         optional tensor of the same number of elements added in f32 before the cast: mm(svd_up, svd_down) of an
+ *                  SVD layer (dequantizer.py:36-37, 72-73); NULL if none
+ *   out            contiguous, dims-shaped, out_dtype SDNQ_BF16 / SDNQ_F16 / SDNQ_F32 */
+SDNQ_API int sdnq_b200_dequant_nd(const void* weight, const sdnq_weight_format* fmt, const float* scale, const float* zero_point,
+                         int codebook, int ndim, const int64_t* dims, const int64_t* scale_strides,
+                         const void* addend, int addend_dtype, void* out, int out_dtype, void* stream);
+
 /* ---- K4 re-quantise for matmul:  SDNQDequantizer.re_quantize_matmul (dequantizer.py:204-239, 353-386)
  * dequant to f32 (no SVD, no un-rotate) then row-wise re-quantise to the matmul dtype.
  *   mm_dtype  SDNQ_I8 (symmetric, quantize_int_mm), SDNQ_U8 (asymmetric int8 codes + zero point,
@@ -123,6 +138,20 @@ SDNQ_API int sdnq_b200_requant(const void* weight, const sdnq_weight_format* fmt
  *           rotated activations (operand of the SVD branch).  K % 8 == 0. */
 SDNQ_API int sdnq_b200_act_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx, int hadamard_group,
                         int mm_dtype, void* xq, float* sx, float* zx, int32_t* rowsum, void* x_rot, void* stream);
+
+/* ---- K2 for convolutions:  process_conv_input (layers/conv/forward.py:30-76: F.unfold(...).transpose(1, 2)) +
+ *      rotate_hadamard + quantize_{int,uint,fp}_mm_input of conv_{int8,uint8,fp8}_matmul (layers/conv/conv_int8.py:17-90).
+ * The im2col matrix [M, K] (M = batch * H_out * W_out rows in (b, oh, ow) order, K = channels * kernel_h * kernel_w columns in
+ * (c, i, j) order, zero padding) is never written: each row is gathered from the strided input, rotated, row-quantised and
+ * only the 1-byte codes xq [M, K] (+ sx / zx / rowsum / optional x_rot, as sdnq_b200_act_quant) are stored.  conv1d: height = 1.
+ * K % 8 == 0.  Strides are in elements and must be non-negative. */
+typedef struct sdnq_conv2d_geometry {
+    int64_t batch, channels, height, width;
+    int64_t x_stride_b, x_stride_c, x_stride_h, x_stride_w;
+    int32_t kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w;
+} sdnq_conv2d_geometry;
+SDNQ_API int sdnq_b200_conv_act_quant(const void* x, int x_dtype, const sdnq_conv2d_geometry* geometry, int hadamard_group,
+                             int mm_dtype, void* xq, float* sx, float* zx, int32_t* rowsum, void* x_rot, void* stream);
 
 /* ---- K1 scaled matmul:  int_scaled_mm_func / fp8_scaled_mm_func (kernel_wrappers.py:193-204) ->
  *      sdnq_scaled_mm (kernels/triton_scaled_mm.py:239-275)

@@ -290,6 +290,8 @@ def hadamard_matrix(n: int, dtype: str) -> np.ndarray:
     """H / sqrt(n) rounded to `dtype` the way the reference does: divide in dtype (quant_utils.py:150,161)."""
     H = build_hadamard(n).astype(F32)
     Hn = (H / F32(n ** 0.5)).astype(F32)   # div_ by a python scalar is done in f32 opmath
+    if dtype == "float16":
+        return Hn.astype(np.float16).astype(F32)
     return bf16_round(Hn) if dtype == "bfloat16" else Hn
 
 
@@ -298,6 +300,8 @@ def rotate_hadamard(x, group: int, dtype: str) -> np.ndarray:
     x = np.asarray(x, F32)
     H = hadamard_matrix(group, dtype)
     y = (x.reshape(-1, group) @ H).reshape(x.shape)
+    if dtype == "float16":
+        return y.astype(np.float16).astype(F32)
     return bf16_round(y) if dtype == "bfloat16" else y.astype(F32)
 
 
@@ -398,6 +402,9 @@ class Layer:
         self.hadamard_group_size = meta.get("hadamard_group_size", 256)
         self.use_codebook = bool(meta.get("use_codebook", False))
         self.info = dtype_info(self.weights_dtype)
+        self.layer_class_name = meta.get("layer_class_name", "Linear")
+        self.original_shape = None if meta.get("original_shape") is None else tuple(meta["original_shape"])
+        self.svd_dtype = meta.get("svd_dtype", "bfloat16")
 
 
 def _cast(x, dtype):
@@ -437,7 +444,10 @@ def dequantize(layer: Layer, dtype=None, skip_quantized_matmul=False, with_svd=T
         up, down = np.asarray(layer.svd_up, F32), np.asarray(layer.svd_down, F32)
         if skip_quantized_matmul:
             up, down = up.T, down.T
-        res = _cast(_cast(res, dtype) + (up @ down).astype(F32), dtype)   # bf16 addmm_: f32 accumulate, one rounding
+        if res.ndim > 2 and np.asarray(q).ndim > 2:                     # is_conv (dequantizer.py:30, 36-37): f32 weight + mm in the SVD dtype
+            res = (res + _cast((up @ down).astype(F32), layer.svd_dtype).reshape(res.shape)).astype(F32)
+        else:
+            res = _cast(_cast(res, dtype) + (up @ down).astype(F32), dtype)   # bf16 addmm_: f32 accumulate, one rounding
     res = _cast(res, dtype)
     if layer.use_hadamard and not non_hadamard:                         # dequantizer.py:46-47
         res = rotate_hadamard(res, layer.hadamard_group_size, dtype)
@@ -551,6 +561,61 @@ def linear_forward(layer: Layer, x, dtype="bfloat16"):
             acc = fp8_mm(p["xq"], p["wq"])
         y = scaled_mm(acc, p["sx"], p["sw"], p["bias"], out_dtype=dtype)
     return y.reshape(*lead, -1)
+
+
+# =============================================================================
+# convolution forwards   (reference: layers/conv/forward.py, conv_int8.py, conv_uint8.py, conv_fp8.py)
+# =============================================================================
+def conv_unfold(x, kernel, stride, padding, dilation):
+    """F.unfold(x, ...).transpose(1, 2) of process_conv_input (layers/conv/forward.py:30-76) for 2-D convolutions:
+    x [B,C,H,W] -> (cols [B, H_out*W_out, C*kh*kw] with columns in (c, i, j) order, (H_out, W_out)).  Zero padding."""
+    x = np.asarray(x, F32)
+    B, C, H, W = x.shape
+    (kh, kw), (sh, sw), (ph, pw), (dh, dw) = kernel, stride, padding, dilation
+    Ho = (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+    Wo = (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+    xp = np.zeros((B, C, H + 2 * ph, W + 2 * pw), F32)
+    xp[:, :, ph:ph + H, pw:pw + W] = x
+    cols = np.empty((B, Ho, Wo, C, kh, kw), F32)
+    for i in range(kh):
+        for j in range(kw):
+            cols[:, :, :, :, i, j] = xp[:, :, i * dh:i * dh + sh * (Ho - 1) + 1:sh, j * dw:j * dw + sw * (Wo - 1) + 1:sw].transpose(0, 2, 3, 1)
+    return cols.reshape(B, Ho * Wo, C * kh * kw), (Ho, Wo)
+
+
+def _tuple_n(v, n):
+    return (int(v),) * n if isinstance(v, (int, np.integer)) else tuple(int(i) for i in v)
+
+
+def conv_forward(layer: Layer, x, kernel_size, stride=1, padding=0, dilation=1, dtype="bfloat16"):
+    """SDNQConv1d/2d.forward for groups == 1, padding_mode == "zeros".  W8A8 layers: conv_{int8,uint8,fp8}_matmul
+    (conv_int8.py:17-125) = im2col + the Linear matmul path + permute back; others (and inputs with fewer than 32 rows,
+    conv_int8.py:95-96): dequantise + a float convolution (computed here as an f32 im2col GEMM, rounded once)."""
+    x = np.asarray(x, F32)
+    nd = x.ndim - 2
+    k, s, p, d = (_tuple_n(v, nd) for v in (kernel_size, stride, padding, dilation))
+    x4 = x
+    if nd == 1:                                                         # get_conv_args (layers/conv/forward.py:8-27)
+        x4 = x[:, :, None, :]
+        k, s, p, d = (1, k[0]), (1, s[0]), (0, p[0]), (1, d[0])
+    B = x4.shape[0]
+    cols, (Ho, Wo) = conv_unfold(x4, k, s, p, d)
+    cols2 = cols.reshape(B * Ho * Wo, -1)
+    small = x.size / x.shape[2] < 32
+    if not layer.use_quantized_matmul or small:
+        W = dequantize(layer, dtype=dtype, skip_quantized_matmul=layer.use_quantized_matmul)
+        y = cols2 @ W.reshape(W.shape[0], -1).T
+        if layer.bias is not None:
+            y = y + np.asarray(layer.bias, F32)
+        y = _cast(y, dtype)
+    else:
+        pm = matmul_inputs(layer, cols2, dtype)
+        acc = int_mm(pm["xq"], pm["wq"]) if dtype_info(layer.quantized_matmul_dtype)["is_integer"] else fp8_mm(pm["xq"], pm["wq"])
+        y = scaled_mm(acc, pm["sx"], pm["sw"], pm["bias"], out_dtype=dtype)
+    N = y.shape[-1]
+    if nd == 1:
+        return y.reshape(B, Wo, N).transpose(0, 2, 1)
+    return y.reshape(B, Ho, Wo, N).transpose(0, 3, 1, 2)
 
 
 # =============================================================================

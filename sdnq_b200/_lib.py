@@ -15,6 +15,11 @@ SDNQ_W_INT, SDNQ_W_MINIFLOAT, SDNQ_W_FP8_E4M3FN, SDNQ_W_FP8_E5M2 = range(4)
 ABI_VERSION = 1
 
 
+class Conv2dGeometry(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int64) for n in ("batch", "channels", "height", "width", "x_stride_b", "x_stride_c", "x_stride_h", "x_stride_w")] + \
+               [(n, ctypes.c_int32) for n in ("kernel_h", "kernel_w", "stride_h", "stride_w", "pad_h", "pad_w", "dilation_h", "dilation_w")]
+
+
 class WeightFormat(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("bits", ctypes.c_int32), ("is_unsigned", ctypes.c_int32),
                 ("exponent", ctypes.c_int32), ("mantissa", ctypes.c_int32), ("word_bytes", ctypes.c_int32)]
@@ -30,8 +35,10 @@ SIGNATURES = {
     "sdnq_b200_check_device": (_I, [_I]),
     "sdnq_b200_unpack": (_I, [_P, _WF, _P, _I, _L, _P]),
     "sdnq_b200_dequant": (_I, [_P, _WF, _P, _P, _I, _L, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _P, _I, _P]),
+    "sdnq_b200_dequant_nd": (_I, [_P, _WF, _P, _P, _I, _I, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), _P, _I, _P, _I, _P]),
     "sdnq_b200_requant": (_I, [_P, _WF, _P, _P, _I, _L, _L, _L, _I, _P, _P, _P, _P, _P]),
     "sdnq_b200_act_quant": (_I, [_P, _I, _L, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "sdnq_b200_conv_act_quant": (_I, [_P, _I, ctypes.POINTER(Conv2dGeometry), _I, _I, _P, _P, _P, _P, _P, _P]),
     "sdnq_b200_scaled_mm": (_I, [_P, _P, _I, _P, _P, _P, _I, _L, _P, _P, _P, _P, _P, _I, _L, _L, _L, _P]),
     "sdnq_b200_scaled_mm_packed": (_I, [_P, _P, _WF, _P, _P, _P, _I, _L, _P, _P, _P, _I, _L, _L, _L, _P]),
     "sdnq_b200_mm": (_I, [_P, _P, _I, _P, _L, _L, _L, _P]),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(PKG, "libsdnq_b200.so")
-SOURCES = ["capi.cu", "dequant.cu", "dequant_svd.cu", "act_quant.cu", "gemm_w8a8.cu"]
+SOURCES = ["capi.cu", "dequant.cu", "dequant_nd.cu", "dequant_svd.cu", "act_quant.cu", "act_quant_conv.cu", "gemm_w8a8.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
@@ -42,14 +42,22 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB
 
+    headers = [d for d in deps if not d.endswith(".cu")]
+
     def compile_one(src):
         obj = os.path.join(BUILD, src.replace(".cu", ".o"))
+        # per-object stamp: the source, every header and the flags
+        ostamp, odigest = obj + ".stamp", _digest([os.path.join(HERE, src), *headers])
+        if not force and os.path.exists(obj) and os.path.exists(ostamp) and open(ostamp).read() == odigest:
+            return obj
         cmd = [NVCC, *FLAGS, "-c", os.path.join(HERE, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:
             sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
+        with open(ostamp, "w") as f:
+            f.write(odigest)
         return obj
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:

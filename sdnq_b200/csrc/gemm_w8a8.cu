@@ -665,7 +665,7 @@ int launch_gemm_out(const void* a, const void* b, const GemmParams& p, cudaStrea
 // operand traffic relative to BN=128, so it wins whenever the grid is full either way.
 int pick_bn(int M, int N) {
     static const int forced = [] { const char* e = getenv("SDNQ_B200_BN"); return e ? atoi(e) : 0; }();   // tuning knob
-    if (forced == 128 || forced == 256) return forced;
+    if (forced == 128 || forced == 192 || forced == 256) return forced;
     const int sms = num_sms();
     const int num_m = (M + BM - 1) / BM;
     auto waves_eff = [&](int bn) {
@@ -673,9 +673,11 @@ int pick_bn(int M, int N) {
         const int waves = (tiles + sms - 1) / sms;
         return static_cast<double>(tiles) / (static_cast<double>(waves) * sms);
     };
-    const double e256 = waves_eff(256) * 1.00, e128 = waves_eff(128) * 0.90, e64 = waves_eff(64) * 0.70;
+    // relative per-tile efficiency of the narrower tiles (shared-memory operand traffic per MMA grows as BN shrinks)
+    const double e256 = waves_eff(256) * 1.00, e192 = waves_eff(192) * 0.94, e128 = waves_eff(128) * 0.90, e64 = waves_eff(64) * 0.70;
     if (N <= 64) return 64;
-    if (e256 >= e128 && e256 >= e64) return 256;
+    if (e256 >= e192 && e256 >= e128 && e256 >= e64) return 256;
+    if (e192 >= e128 && e192 >= e64) return 192;
     if (e128 >= e64) return 128;
     return 64;
 }
@@ -706,6 +708,7 @@ int scaled_mm_impl(const void* a, const void* b, int ab_dtype, GemmParams p, cud
     }
     switch (pick_bn(p.M, p.N)) {
         case 256: return i8 ? launch_gemm_out<256, true>(a, b, p, st) : launch_gemm_out<256, false>(a, b, p, st);
+        case 192: return i8 ? launch_gemm_out<192, true>(a, b, p, st) : launch_gemm_out<192, false>(a, b, p, st);
         case 128: return i8 ? launch_gemm_out<128, true>(a, b, p, st) : launch_gemm_out<128, false>(a, b, p, st);
         default: return i8 ? launch_gemm_out<128, true>(a, b, p, st) : launch_gemm_out<128, false>(a, b, p, st);
     }

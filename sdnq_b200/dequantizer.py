@@ -43,9 +43,26 @@ class SDNQDequantizer:
         self.is_integer_matmul, self.is_unsigned_matmul = m["is_integer"], m["is_unsigned"]
 
     # ---- geometry helpers --------------------------------------------------------------------
+    @property
+    def is_conv(self) -> bool:
+        return self.layer_class_name in conv_types or self.layer_class_name in conv_transpose_types
+
+    def matmul_nk(self):
+        """(N, K) of the GEMM a W8A8 layer runs: Linear [N,K]; Conv [N, C*kh*kw] (the im2col contraction)."""
+        shape = tuple(self.original_shape)
+        if self.layer_class_name in conv_types:
+            k = 1
+            for v in shape[1:]:
+                k *= int(v)
+            return int(shape[0]), k
+        return self._linear_nk()
+
     def _linear_nk(self):
-        if self.layer_class_name in conv_types or self.layer_class_name in conv_transpose_types:
-            raise NotImplementedError(f"sdnq_b200: {self.layer_class_name} layers are not on the CUDA path yet (Linear only)")
+        if self.is_conv:
+            if self.layer_class_name in conv_types and self.use_quantized_matmul and not self.re_quantize_for_matmul:
+                return self.matmul_nk()        # stored row-wise on the flattened [N, C*kh*kw] weight: same layout as a Linear
+            raise NotImplementedError(f"sdnq_b200: re-quantising {self.layer_class_name} weights for the quantized matmul has no CUDA kernel yet "
+                                      "(grouped / packed conv weights with use_quantized_matmul_conv)")
         shape = tuple(self.original_shape)
         if len(shape) != 2:
             raise NotImplementedError(f"sdnq_b200: only 2-D Linear weights have a CUDA dequant kernel (got shape {shape})")
@@ -59,13 +76,38 @@ class SDNQDequantizer:
         matmul layout (K-major weight / transposed SVD factors); physically that is the same [N,K] weight, so only the SVD strides
         differ.  `hadamard` (a matrix in the reference) is accepted for signature compatibility; the kernel un-rotates with its
         own butterfly."""
-        N, K = self._linear_nk()
         dtype = dtype or self.result_dtype
         if not weight.is_cuda:
             raise ops._lib.SDNQKernelError("SDNQDequantizer: the weight is not on a CUDA device; sdnq_b200 has no CPU dequant path")
+        if self.is_conv:
+            return self._conv_dequant(weight, scale, zero_point, svd_up, svd_down, skip_quantized_matmul, non_hadamard, dtype)
+        N, K = self._linear_nk()
         un_rotate = self.hadamard_group_size if (self.use_hadamard and not non_hadamard) else 0
         return ops.dequant(weight, self.weights_dtype, scale, zero_point, N, K, self.group_size, dtype, svd_up=svd_up, svd_down=svd_down,
                            svd_layout_matmul=bool(skip_quantized_matmul), hadamard_group=un_rotate, use_codebook=self.use_codebook)
+
+    def _conv_dequant(self, weight, scale, zero_point, svd_up, svd_down, skip_quantized_matmul, non_hadamard, dtype):
+        """Conv / ConvTranspose weights: broadcast dequant over the quantised view (reference dequantizer.py:15-84 with
+        `is_conv`): scale [N,1,kh,kw] / grouped [N,C/g,1,kh,kw] / ConvTranspose [1,N,kh,kw] ...; the SVD term is
+        mm(svd_up, svd_down) in the SVD dtype added in f32 (no intermediate rounding of the weight, unlike Linear)."""
+        if self.use_hadamard and not non_hadamard:
+            raise NotImplementedError("sdnq_b200: un-rotating Hadamard-rotated convolution weights has no CUDA kernel yet")
+        stored_t = bool(skip_quantized_matmul and not self.re_quantize_for_matmul and self.use_quantized_matmul)
+        if stored_t:      # matmul layout: weight [K,N] K-major (physically [N,K]), scale / zp [1,N]
+            N, K = self.matmul_nk()
+            weight = ops.physical_nk(weight)
+            view = (N, K)
+            scale = scale.reshape(N, 1)
+            zero_point = None if zero_point is None else zero_point.reshape(N, 1)
+        else:
+            view = tuple(self.quantized_weight_shape)
+        addend = None
+        if svd_up is not None:
+            if stored_t:
+                svd_up, svd_down = svd_up.t().contiguous(), svd_down.contiguous().t()
+            addend = torch.mm(svd_up, svd_down)
+        out = ops.dequant_nd(weight, self.weights_dtype, scale, zero_point, view, dtype, use_codebook=self.use_codebook, addend=addend)
+        return out.view(tuple(self.result_shape) if self.result_shape is not None else tuple(self.original_shape))
 
     # ---- K4 ------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -6,6 +6,8 @@ Same names / dispatch rule as the reference (forward.py:6-57, layers/linear/*.py
     quantized_linear_forward_int8_matmul      K2 act-quant + K1 tcgen05 int8 GEMM               layers/linear/linear_int8.py:100-125
     quantized_linear_forward_uint8_matmul     K2 (asymmetric) + K1 with zero-point epilogue     layers/linear/linear_uint8.py:105-129
     quantized_linear_forward_fp8_matmul       K2 (e4m3) + K1 tcgen05 fp8 GEMM                   layers/linear/linear_fp8.py:81-104
+    quantized_conv_forward (+ transpose 1/2/3d) K3 broadcast dequant -> library convolution       layers/conv/forward.py:79-99
+    quantized_conv_forward_{int8,uint8,fp8}_matmul  K2 over the im2col view (gathered, never materialised) + K1   layers/conv/conv_*.py
 
 Every function runs CUDA kernels from libsdnq_b200.so; there is no eager / CPU fallback (a CPU tensor raises)."""
 import os
@@ -45,10 +47,13 @@ def matmul_operand(layer) -> _MatmulOperand:
     cached = layer.__dict__.get("_sdnq_mm_cache")
     if cached is not None and cached.key == key:
         return cached
-    N, K = tuple(d.original_shape)
+    N, K = d.matmul_nk()
     mm = d.quantized_matmul_dtype
     uint8_mm = d.is_integer_matmul and d.is_unsigned_matmul
     zp = colsum = None
+    if d.is_conv and d.is_packed and not d.re_quantize_for_matmul:
+        # the reference's conv matmul prologue (conv_int8.py:38-44) transposes the unpacked 4-D weight and fails on this combination too
+        raise NotImplementedError("sdnq_b200: packed convolution weights without re-quantisation have no W8A8 kernel")
     if d.re_quantize_for_matmul:
         wq, sw, zp, colsum = d.re_quantize_matmul_raw(w, s, z, want_colsum=uint8_mm)
     elif (d.is_packed and d.is_integer and d.num_bits == 4 and mm == "int8" and K % 32 == 0
@@ -140,16 +145,113 @@ def _unsupported(name: str, what: str) -> Callable:
 
 
 quantized_linear_forward_fp16_matmul = _unsupported("quantized_linear_forward_fp16_matmul", "the float16 quantized matmul (quantized_matmul_dtype='float16')")
-quantized_conv_forward = _unsupported("quantized_conv_forward", "quantized convolution (quant_conv=True)")
+quantized_conv_forward_fp16_matmul = _unsupported("quantized_conv_forward_fp16_matmul", "the float16 quantized conv matmul (quantized_matmul_dtype='float16')")
 quantized_embedding_forward = _unsupported("quantized_embedding_forward", "quantized embedding (quant_embedding=True)")
+
+
+# ------------------------------------------------------------------------------------------------ convolutions
+def _conv_dense_weight(self, skip_quantized_matmul):
+    d = self.sdnq_dequantizer
+    return d(self.weight, self.scale, zero_point=self.zero_point, svd_up=self.svd_up, svd_down=self.svd_down,
+             skip_quantized_matmul=skip_quantized_matmul)
+
+
+@torch.no_grad()
+def quantized_conv_forward(self, input: torch.Tensor) -> torch.Tensor:
+    """K3 (broadcast dequant of the conv weight) -> the library convolution (reference layers/conv/forward.py:79-81)."""
+    return self._conv_forward(input, _conv_dense_weight(self, False), self.bias)
+
+
+def _conv_transpose_forward(nd, fn):
+    @torch.no_grad()
+    def forward(self, input: torch.Tensor, output_size=None) -> torch.Tensor:
+        output_padding = self._output_padding(input, output_size, self.stride, self.padding, self.kernel_size, nd, self.dilation)
+        return fn(input, _conv_dense_weight(self, False), self.bias, self.stride, self.padding, output_padding, self.groups, self.dilation)
+    forward.__name__ = f"quantized_conv_transpose_{nd}d_forward"
+    return forward
+
+
+# reference layers/conv/forward.py:84-99
+quantized_conv_transpose_1d_forward = _conv_transpose_forward(1, torch.nn.functional.conv_transpose1d)
+quantized_conv_transpose_2d_forward = _conv_transpose_forward(2, torch.nn.functional.conv_transpose2d)
+quantized_conv_transpose_3d_forward = _conv_transpose_forward(3, torch.nn.functional.conv_transpose3d)
+
+
+def _pair(v, n):
+    return (int(v),) * n if isinstance(v, int) else tuple(int(i) for i in v)
+
+
+def _w8a8_conv_forward(self, input: torch.Tensor) -> torch.Tensor:
+    """conv_{int8,uint8,fp8}_matmul (reference layers/conv/conv_int8.py:17-125, conv_uint8.py, conv_fp8.py): the convolution as
+    one W8A8 GEMM over the im2col view.  Here: K2 gathers each im2col row straight from the input (the [M, C*kh*kw] bf16
+    matrix of F.unfold is never written), rotates / row-quantises it; K1 contracts it with the row-wise weight; the
+    [B, H_out, W_out, N] result is returned in the reference's NCHW-contiguous form."""
+    d = self.sdnq_dequantizer
+    if input.numel() / input.shape[2] < SMALL_M:                                  # conv_int8.py:95-96
+        return self._conv_forward(input, _conv_dense_weight(self, True), self.bias)
+    if self.groups != 1:
+        raise NotImplementedError("sdnq_b200: grouped convolutions have no W8A8 kernel yet (set use_quantized_matmul_conv=False for them)")
+    if self.padding_mode != "zeros":
+        raise NotImplementedError(f"sdnq_b200: padding_mode={self.padding_mode!r} has no W8A8 conv kernel yet")
+    if input.ndim not in (3, 4):
+        raise NotImplementedError("sdnq_b200: Conv3d has no W8A8 kernel yet")
+    if isinstance(self.padding, str):
+        raise NotImplementedError("sdnq_b200: string padding ('same' / 'valid') has no W8A8 conv kernel yet")
+    nd = input.ndim - 2
+    ksz, stride, padding, dilation = (_pair(v, nd) for v in (self.kernel_size, self.stride, self.padding, self.dilation))
+    x4 = input
+    if nd == 1:                                                                   # get_conv_args: conv1d = conv2d with H = 1
+        x4 = input.unsqueeze(2)
+        ksz, stride, padding, dilation = (1, ksz[0]), (1, stride[0]), (0, padding[0]), (1, dilation[0])
+    op = matmul_operand(self)
+    mm = d.quantized_matmul_dtype
+    hg = d.hadamard_group_size if d.use_hadamard else 0
+    svd = self.svd_up is not None
+    xq, sx, zx, rowsum, x_rot, (B, Ho, Wo) = ops.conv_act_quant(x4, ksz, stride, padding, dilation, mm, hadamard_group=hg,
+                                                                want_rowsum=op.zp is not None, want_x_rot=svd)
+    bias = self.bias
+    if svd:                                                                       # conv_int8.py:56-61
+        low = torch.mm(x_rot.to(self.svd_down.dtype), self.svd_down)
+        bias = torch.mm(low, self.svd_up) if self.bias is None else torch.addmm(self.bias.to(self.svd_down.dtype), low, self.svd_up)
+    if op.packed is not None:
+        out = ops.scaled_mm_packed(xq, op.wq, op.packed, d.original_shape[0], sx, op.sw, bias, input.dtype, rowsum=rowsum, zp=op.zp)
+    else:
+        out = ops.scaled_mm(xq, op.wq, sx, op.sw, bias, input.dtype, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx)
+    N = out.shape[-1]
+    if nd == 1:
+        return out.view(B, Wo, N).transpose(1, 2).contiguous()
+    return out.view(B, Ho, Wo, N).permute(0, 3, 1, 2).contiguous()
+
+
+@torch.no_grad()
+def quantized_conv_forward_int8_matmul(self, input: torch.Tensor) -> torch.Tensor:
+    return _w8a8_conv_forward(self, input)
+
+
+@torch.no_grad()
+def quantized_conv_forward_uint8_matmul(self, input: torch.Tensor) -> torch.Tensor:
+    return _w8a8_conv_forward(self, input)
+
+
+@torch.no_grad()
+def quantized_conv_forward_fp8_matmul(self, input: torch.Tensor) -> torch.Tensor:
+    return _w8a8_conv_forward(self, input)
 
 
 def get_forward_func(layer_class_name: str, quantized_matmul_dtype: str, use_quantized_matmul: bool) -> Callable:
     """reference forward.py:6-57."""
     if layer_class_name in embedding_types:
         return quantized_embedding_forward
-    if layer_class_name in conv_types or layer_class_name in conv_transpose_types:
-        return quantized_conv_forward
+    if layer_class_name in conv_types:
+        if not use_quantized_matmul:
+            return quantized_conv_forward
+        mm = dtype_dict[quantized_matmul_dtype]
+        if mm["is_integer"]:
+            return quantized_conv_forward_uint8_matmul if mm["is_unsigned"] else quantized_conv_forward_int8_matmul
+        return quantized_conv_forward_fp8_matmul if mm["num_bits"] == 8 else quantized_conv_forward_fp16_matmul
+    if layer_class_name in conv_transpose_types:
+        return {"1": quantized_conv_transpose_1d_forward, "2": quantized_conv_transpose_2d_forward,
+                "3": quantized_conv_transpose_3d_forward}[layer_class_name[-2]]
     if not use_quantized_matmul:
         return quantized_linear_forward
     mm = dtype_dict[quantized_matmul_dtype]

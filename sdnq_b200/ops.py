@@ -127,6 +127,48 @@ def dequant(weight, weights_dtype, scale, zero_point, N, K, group_size, out_dtyp
     return out
 
 
+def dequant_nd(weight, weights_dtype, scale, zero_point, view_shape, out_dtype, use_codebook=False, addend=None) -> torch.Tensor:
+    """K3 for convolution layers: broadcast dequant over the quantised view (scale / zero_point broadcastable to view_shape;
+    codebook levels carry one extra trailing axis).  `addend` (same numel) is added in f32 before the cast."""
+    import ctypes
+    _require_cuda(weight, scale)
+    e = dtype_dict[weights_dtype]
+    w = weight.contiguous()
+    view_shape = tuple(int(v) for v in view_shape)
+    scale = scale.to(torch.float32) if scale.dtype != torch.float32 else scale
+    sshape = tuple(scale.shape[:-1]) if use_codebook else tuple(scale.shape)
+    if len(sshape) != len(view_shape):
+        raise _lib.SDNQKernelError(f"dequant_nd: scale shape {tuple(scale.shape)} does not line up with the quantised view {view_shape}")
+    scale = scale.contiguous()
+    strides, acc = [], 1
+    for dim, sdim in zip(reversed(view_shape), reversed(sshape)):
+        if sdim == 1:
+            strides.append(0)
+        elif sdim == dim:
+            strides.append(acc)
+            acc *= sdim
+        else:
+            raise _lib.SDNQKernelError(f"dequant_nd: scale shape {tuple(scale.shape)} is not broadcastable to {view_shape}")
+    strides.reverse()
+    if zero_point is not None:
+        zero_point = zero_point.to(torch.float32).contiguous()
+        if tuple(zero_point.shape) != tuple(scale.shape):
+            raise _lib.SDNQKernelError("dequant_nd: zero_point and scale shapes differ")
+    out = torch.empty(view_shape, dtype=out_dtype, device=w.device)
+    n = len(view_shape)
+    dims_c = (ctypes.c_int64 * n)(*view_shape)
+    str_c = (ctypes.c_int64 * n)(*strides)
+    if addend is not None:
+        addend = addend.contiguous()
+        if addend.numel() != out.numel():
+            raise _lib.SDNQKernelError("dequant_nd: addend size mismatch")
+    fmt = weight_format(weights_dtype, w)
+    with torch.cuda.device(w.device):
+        check(_lib.load().sdnq_b200_dequant_nd(_ptr(w), fmt, _ptr(scale), _ptr(zero_point), int(use_codebook), n, dims_c, str_c, _ptr(addend),
+                                               dtype_code(addend.dtype) if addend is not None else SDNQ_F32, _ptr(out), dtype_code(out_dtype), _stream(w)))
+    return out
+
+
 def requant(weight, weights_dtype, scale, zero_point, N, K, group_size, matmul_dtype, use_codebook=False, want_colsum=False):
     """K4.  Returns (wq [N,K] physical, sw [N], zw [N] | None, colsum [N] | None)."""
     _require_cuda(weight, scale)
@@ -169,6 +211,34 @@ def act_quant(x: torch.Tensor, matmul_dtype: str, hadamard_group: int = 0, want_
         check(lib.sdnq_b200_act_quant(_ptr(x2), dtype_code(x2.dtype), M, K, x2.stride(0), int(hadamard_group), code,
                                       _ptr(xq), _ptr(sx), _ptr(zx), _ptr(rowsum), _ptr(x_rot), _stream(x2)))
     return xq, sx, zx, rowsum, x_rot
+
+
+def conv_act_quant(x: torch.Tensor, kernel_size, stride, padding, dilation, matmul_dtype: str, hadamard_group: int = 0,
+                   want_rowsum: bool = False, want_x_rot: bool = False):
+    """K2 over the im2col view of a conv input (never materialised).  x [B,C,H,W] (any non-negative strides; conv1d callers pass
+    H = 1) -> (xq [M,K], sx [M], zx, rowsum, x_rot, (B, H_out, W_out)) with M = B*H_out*W_out, K = C*kh*kw in (c, i, j) order."""
+    _require_cuda(x)
+    if x.ndim != 4:
+        raise _lib.SDNQKernelError("conv_act_quant expects a 4-D input (conv1d: unsqueeze(2))")
+    if any(s < 0 for s in x.stride()):
+        x = x.contiguous()
+    B, C, H, W = x.shape
+    (kh, kw), (sh, sw), (ph, pw), (dh, dw) = kernel_size, stride, padding, dilation
+    Hout = (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+    Wout = (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+    M, K = B * Hout * Wout, C * kh * kw
+    code = mm_code(matmul_dtype)
+    dev = x.device
+    xq = torch.empty((M, K), dtype=_MM_TORCH[code], device=dev)
+    sx = torch.empty((M,), dtype=torch.float32, device=dev)
+    zx = torch.empty((M,), dtype=torch.float32, device=dev) if code == SDNQ_U8 else None
+    rowsum = torch.empty((M,), dtype=torch.int32, device=dev) if want_rowsum else None
+    x_rot = torch.empty((M, K), dtype=x.dtype, device=dev) if want_x_rot else None
+    geo = _lib.Conv2dGeometry(B, C, H, W, *x.stride(), kh, kw, sh, sw, ph, pw, dh, dw)
+    with torch.cuda.device(dev):
+        check(_lib.load().sdnq_b200_conv_act_quant(_ptr(x), dtype_code(x.dtype), geo, int(hadamard_group), code, _ptr(xq), _ptr(sx), _ptr(zx),
+                                                   _ptr(rowsum), _ptr(x_rot), _stream(x)))
+    return xq, sx, zx, rowsum, x_rot, (B, Hout, Wout)
 
 
 def scaled_mm(a: torch.Tensor, b_nk: torch.Tensor, sx: torch.Tensor, sw: torch.Tensor, bias: torch.Tensor | None = None,

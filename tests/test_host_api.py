@@ -152,3 +152,15 @@ def test_apply_sdnq_to_module_skips_and_swaps():
     assert set(net.blocks[0].to_q.state_dict().keys()) >= {"weight", "scale", "bias"}
     with pytest.raises(RuntimeError):
         sdnq_post_load_quant(net, weights_dtype="int8")                        # already quantised
+
+
+# ----------------------------------------------------------------------------------------------- convolution layers (host side)
+from tests.util import CONV_FILES, CONV_IDS, build_conv_layer  # noqa: E402
+
+
+@pytest.mark.parametrize("path", CONV_FILES, ids=CONV_IDS)
+def test_conv_quantisation_stores_what_the_reference_stores(path):
+    """sdnq_quantize_layer on Conv / ConvTranspose modules: same dequantizer metadata, forward_func and bit-identical stored
+    weight / scale / zero_point as the reference (tests/golden/generate_conv.py); the asserts live in build_conv_layer."""
+    layer, t, z, meta = build_conv_layer(path)
+    assert type(layer).__name__ == "SDNQ" + meta["module"]

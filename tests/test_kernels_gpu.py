@@ -166,6 +166,37 @@ def test_hadamard_rotation_matches_oracle(G):
     assert float((x_back.float().cpu() - x.float()).abs().max()) <= 0.05 * float(x.float().abs().max())
 
 
+@pytest.mark.parametrize("G", [8, 16, 32, 64, 128, 256])
+@pytest.mark.parametrize("mode", ["int8", "uint8", "float8_e4m3fn"])
+def test_hadamard_f16_and_partial_chunks(G, mode):
+    """float16 activations (MMA 1 in f16, three bf16 pieces for MMA 2), rows that end in half a chunk, every matmul dtype."""
+    torch.manual_seed(100 + G)
+    M, K = 45, 256 * 3 + (128 if G <= 128 else 256 * 2)
+    x = (torch.randn(M, K) * 3).to(torch.float16)
+    xq, sx, zx, rowsum, x_rot = ops().act_quant(x.to(DEV), mode, hadamard_group=G, want_x_rot=True, want_rowsum=True)
+    ref = O.rotate_hadamard(x.float().numpy(), G, "float16").astype(np.float16)
+    got = x_rot.cpu().numpy()
+    ulp = np.abs(got.view(np.int16).astype(np.int32) - ref.view(np.int16).astype(np.int32))
+    same_sign = np.signbit(got) == np.signbit(ref)
+    assert float(np.mean((ulp > 1) & same_sign)) < 2e-3 and float(np.mean(ulp > 0)) < 0.02
+    assert np.abs(got.astype(np.float32) - ref.astype(np.float32)).max() <= 2.0 ** -9 * np.abs(ref.astype(np.float32)).max()
+    # quantisation of the kernel's own rotated values is exact
+    xr = got.astype(np.float32)
+    if mode == "int8":
+        q, s = O.quantize_int_mm(xr)
+        assert np.array_equal(xq.cpu().numpy(), q) and np.array_equal(sx.cpu().numpy(), s.reshape(-1))
+        assert np.array_equal(rowsum.cpu().numpy(), q.astype(np.int32).sum(-1))
+    elif mode == "uint8":
+        q, s, z = O.quantize_uint_mm(xr)
+        assert np.array_equal(xq.cpu().numpy(), q) and np.array_equal(sx.cpu().numpy(), s.reshape(-1))
+        assert np.array_equal(zx.cpu().numpy(), z.reshape(-1))
+        assert np.array_equal(rowsum.cpu().numpy(), q.astype(np.int32).sum(-1))
+    else:
+        q, s = O.quantize_fp_mm(xr)
+        assert np.array_equal(O.from_e4m3fn_bits(xq.view(torch.uint8).cpu().numpy()), np.asarray(q, np.float32))
+        assert np.array_equal(sx.cpu().numpy(), s.reshape(-1))
+
+
 # ----------------------------------------------------------------------------------------------- GEMM
 SHAPES = [(128, 128, 128), (1, 64, 64), (77, 640, 2048), (130, 264, 400), (256, 512, 1024), (300, 1280, 640), (64, 5120, 640),
           (1000, 640, 2560), (33, 48, 16), (513, 776, 208)]

@@ -165,3 +165,61 @@ def test_layer_against_reference(path):
     else:
         assert err.max() <= 2e-2 * scale, (err.max(), scale)
         assert np.sqrt((err ** 2).mean()) <= 3e-3 * scale
+
+
+# ----------------------------------------------------------------------------------------------- convolutions
+from .util import CONV_FILES, CONV_IDS  # noqa: E402
+
+
+@pytest.mark.parametrize("path", CONV_FILES, ids=CONV_IDS)
+def test_conv_layer_against_reference(path):
+    """Oracle restatement of the conv forwards / conv dequant against fixtures generated by the reference
+    (tests/golden/generate_conv.py)."""
+    layer, arr, meta = O.load_fixture(path)
+    x = O.from_bf16_bits(arr["x"])
+    d = meta["dequantizer"]
+    kw = meta["module_kwargs"]
+    # ---- dequantised weight (the reference itself cannot dequantise SVD / Hadamard convs stored in matmul layout)
+    if "w_dequant" in arr:
+        Wref = O.from_bf16_bits(arr["w_dequant"])
+        W = O.dequantize(layer, skip_quantized_matmul=d["use_quantized_matmul"])
+        assert W.shape == Wref.shape
+        du = ulp_diff_bf16(W, Wref)
+        if layer.svd_up is None:
+            assert du.max() == 0, f"conv dequant differs: max {du.max()} ulp"
+        else:
+            assert du.max() <= 1 and (du > 0).mean() < 0.02
+    if meta["module"].startswith("ConvTranspose") or meta["module"] == "Conv3d":
+        return                       # forward = dequant + library convolution; covered by the weight check
+    # ---- im2col + activation quantisation
+    if "mm_xq" in arr:
+        nd = x.ndim - 2
+        x4 = x if nd == 2 else x[:, :, None, :]
+        t = lambda v: O._tuple_n(v, nd)  # noqa: E731
+        k, s_, p_, dl = t(kw["kernel_size"]), t(kw.get("stride", 1)), t(kw.get("padding", 0)), t(kw.get("dilation", 1))
+        if nd == 1:
+            k, s_, p_, dl = (1, k[0]), (1, s_[0]), (0, p_[0]), (1, dl[0])
+        cols, _ = O.conv_unfold(x4, k, s_, p_, dl)
+        cols = cols.reshape(-1, cols.shape[-1])
+        if not layer.use_hadamard:
+            assert np.array_equal(cols, O.from_bf16_bits(arr["cols"]))
+        pm = O.matmul_inputs(layer, cols)
+        fp8 = meta["forward_func"].endswith("fp8_matmul")
+        xq_ref = O.from_e4m3fn_bits(arr["mm_xq"]) if fp8 else arr["mm_xq"].astype(np.int32)
+        xq = pm["xq"].astype(np.float32 if fp8 else np.int32).reshape(xq_ref.shape)
+        if layer.use_hadamard:
+            assert (xq != xq_ref).mean() < 5e-3
+        else:
+            assert np.array_equal(xq, xq_ref)
+            assert np.array_equal(pm["sx"].reshape(-1), arr["mm_sx"].reshape(-1))
+    # ---- output
+    yref = O.from_bf16_bits(arr["y"])
+    y = O.conv_forward(layer, x, kw["kernel_size"], kw.get("stride", 1), kw.get("padding", 0), kw.get("dilation", 1))
+    assert y.shape == yref.shape
+    err = np.abs(y - yref)
+    scale = np.abs(yref).max()
+    is_mm = d["use_quantized_matmul"] and x.size / x.shape[2] >= 32
+    if is_mm and not layer.use_hadamard and layer.svd_up is None:
+        assert ulp_diff_bf16(y, yref).max() <= 1
+    else:
+        assert err.max() <= 2e-2 * scale and np.sqrt((err ** 2).mean()) <= 3e-3 * scale
