@@ -63,7 +63,7 @@ __device__ __forceinline__ uint32_t pack16(T a, T b) {
 // kTC: the rotation runs on the tensor cores (hadamard_tc.cuh; 16-bit activations).  The lane then owns elements
 // [4l, 4l+4) and [128+4l, 128+4l+4) of a chunk (two coalesced 8-byte accesses) instead of [8l, 8l+8).
 template <typename T, int WPR, int MAXC, int MODE, bool kTC, bool kConv>
-__global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC ? 4 : 6) : (kTC ? 2 : 3)) act_quant_kernel(const ActArgs a) {
+__global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC ? 4 : 5) : (kTC ? 2 : 3)) act_quant_kernel(const ActArgs a) {
     constexpr int RPC = kWarps / WPR;                 // rows per CTA
     __shared__ float s_a[RPC][WPR];
     __shared__ float s_b[RPC][WPR];
@@ -86,34 +86,42 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC
         xrow += int64_t(b) * a.conv.sB;
     }
 
+    // Per-thread bases; inside the unrolled loops every address is base + a compile-time offset and every validity test is
+    // one compare against a constant (hoisted by hand: under the register cap the compiler re-derived them per chunk).
+    constexpr int kStep = WPR * 256;                                  // column distance between this warp's consecutive chunks
+    const int kb = w_in * 256 + lane * (kTC ? 4 : 8);                 // this lane's first column
+    const int lim = row_ok ? K - kb : 0;                              // chunk c holds data for this lane iff c * kStep < lim
+    const int wlim = row_ok ? K - w_in * 256 : 0;                     // ... for this warp (uniform)
+    const T* xp = xrow + (kConv ? 0 : kb);
+    uint8_t* qp = a.xq + row * a.K + kb;
+    T* rp = a.x_rot != nullptr ? reinterpret_cast<T*>(a.x_rot) + row * a.K + kb : nullptr;
+
     Held<T> held[MAXC];
     // all loads of the row first (memory-level parallelism), statistics afterwards
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
         if constexpr (kTC) {
-            const int k = (c * WPR + w_in) * 256 + lane * 4;
             uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
             if constexpr (kConv) {
                 T g[4];
-                if (row_ok && k < K) { conv_gather<T, 4>(a.conv, xrow, ih0, iw0, k, K, g); lo = make_uint2(pack16(g[0], g[1]), pack16(g[2], g[3])); }
-                if (row_ok && k + 128 < K) { conv_gather<T, 4>(a.conv, xrow, ih0, iw0, k + 128, K, g); hi = make_uint2(pack16(g[0], g[1]), pack16(g[2], g[3])); }
+                if (c * kStep < lim) { conv_gather<T, 4>(a.conv, xrow, ih0, iw0, kb + c * kStep, K, g); lo = make_uint2(pack16(g[0], g[1]), pack16(g[2], g[3])); }
+                if (c * kStep + 128 < lim) { conv_gather<T, 4>(a.conv, xrow, ih0, iw0, kb + c * kStep + 128, K, g); hi = make_uint2(pack16(g[0], g[1]), pack16(g[2], g[3])); }
             } else {
-                if (row_ok && k < K) lo = *reinterpret_cast<const uint2*>(xrow + k);
-                if (row_ok && k + 128 < K) hi = *reinterpret_cast<const uint2*>(xrow + k + 128);
+                if (c * kStep < lim) lo = *reinterpret_cast<const uint2*>(xp + c * kStep);
+                if (c * kStep + 128 < lim) hi = *reinterpret_cast<const uint2*>(xp + c * kStep + 128);
             }
             held[c].raw = make_uint4(lo.x, lo.y, hi.x, hi.y);
         } else {
-            const int k = (c * WPR + w_in) * 256 + lane * 8;
-            if (!(row_ok && k < K)) held[c].zero();
+            if (!(c * kStep < lim)) held[c].zero();
             else if constexpr (kConv) {
                 T g[8];
-                conv_gather<T, 8>(a.conv, xrow, ih0, iw0, k, K, g);
+                conv_gather<T, 8>(a.conv, xrow, ih0, iw0, kb + c * kStep, K, g);
                 if constexpr (sizeof(T) == 2) held[c].raw = make_uint4(pack16(g[0], g[1]), pack16(g[2], g[3]), pack16(g[4], g[5]), pack16(g[6], g[7]));
                 else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) held[c].val[i] = g[i];
                 }
-            } else held[c].load(xrow + k);
+            } else held[c].load(xp + c * kStep);
         }
     }
     float amax = 0.f, vmax = -INFINITY, vmin = INFINITY;
@@ -122,12 +130,11 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC
     if constexpr (kTC) rot.init(a.hadamard, lane);
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
-        const int k0 = (c * WPR + w_in) * 256;          // chunk start (warp-uniform)
         float v[8];
         if constexpr (kTC) {
-            if (k0 < K) rot.apply(held[c].raw, hfac);          // rounds to x.dtype: the reference's matmul returns x.dtype
+            if (c * kStep < wlim) rot.apply(held[c].raw, hfac);       // warp-uniform; rounds to x.dtype: the reference's matmul returns x.dtype
             held[c].get(v);
-            const bool ok_lo = row_ok && k0 + lane * 4 < K, ok_hi = row_ok && k0 + 128 + lane * 4 < K;
+            const bool ok_lo = c * kStep < lim, ok_hi = c * kStep + 128 < lim;
             if constexpr (MODE == SDNQ_U8) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -139,9 +146,9 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC
             }
             continue;
         }
-        const bool ok = row_ok && k0 + lane * 8 < K;
+        const bool ok = c * kStep < lim;
         held[c].get(v);
-        if (a.hadamard && k0 < K) {
+        if (a.hadamard && c * kStep < wlim) {
             hadamard_warp_dyn(a.hadamard, v, hfac);            // put() rounds to x.dtype: the reference's matmul returns x.dtype
             held[c].put(v);
             held[c].get(v);
@@ -183,12 +190,13 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC
     const bool safe = divider.safe();                                    // uniform across the row (and the warp)
     // ---- quantise from registers
     int local_sum = 0;
+    [[maybe_unused]] const int d0 = kTC ? 0 : hadamard_dest_dyn(a.hadamard, lane, 0) - lane * 8;
+    [[maybe_unused]] const int d1 = kTC ? 4 : hadamard_dest_dyn(a.hadamard, lane, 1) - lane * 8;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
         if constexpr (kTC) {
-            const int k = (c * WPR + w_in) * 256 + lane * 4;
-            if (!(row_ok && k < K)) continue;
-            const bool ok_hi = k + 128 < K;
+            if (!(c * kStep < lim)) continue;
+            const bool ok_hi = c * kStep + 128 < lim;
             float v[8];
             held[c].get(v);
             int sum8 = 0;
@@ -201,31 +209,27 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC
                     local_sum += cb[0] + cb[1] + cb[2] + cb[3];
                 }
             }
-            const int64_t e0 = row * a.K + k;
-            *reinterpret_cast<uint32_t*>(a.xq + e0) = r.x;
-            if (ok_hi) *reinterpret_cast<uint32_t*>(a.xq + e0 + 128) = r.y;
-            if (a.x_rot != nullptr) {
-                T* xr = reinterpret_cast<T*>(a.x_rot) + e0;
-                *reinterpret_cast<uint2*>(xr) = make_uint2(held[c].raw.x, held[c].raw.y);
-                if (ok_hi) *reinterpret_cast<uint2*>(xr + 128) = make_uint2(held[c].raw.z, held[c].raw.w);
+            *reinterpret_cast<uint32_t*>(qp + c * kStep) = r.x;
+            if (ok_hi) *reinterpret_cast<uint32_t*>(qp + c * kStep + 128) = r.y;
+            if (rp != nullptr) {
+                *reinterpret_cast<uint2*>(rp + c * kStep) = make_uint2(held[c].raw.x, held[c].raw.y);
+                if (ok_hi) *reinterpret_cast<uint2*>(rp + c * kStep + 128) = make_uint2(held[c].raw.z, held[c].raw.w);
             }
             continue;
         }
-        const int k = (c * WPR + w_in) * 256 + lane * 8;
-        if (!(row_ok && k < K)) continue;
+        if (!(c * kStep < lim)) continue;
         float v[8];
         held[c].get(v);
         const bool want_sum = a.rowsum != nullptr;
         const uint2 r = safe ? quantise8<MODE, true>(v, divider, zero, want_sum, local_sum) : quantise8<MODE, false>(v, divider, zero, want_sum, local_sum);
         // after a power-of-4 Hadamard the lane's two 4-element halves belong elsewhere in the chunk (see hadamard_dest)
-        const int64_t chunk0 = row * a.K + (k - lane * 8);
-        const int d0 = hadamard_dest_dyn(a.hadamard, lane, 0), d1 = hadamard_dest_dyn(a.hadamard, lane, 1);
-        *reinterpret_cast<uint32_t*>(a.xq + chunk0 + d0) = r.x;
-        *reinterpret_cast<uint32_t*>(a.xq + chunk0 + d1) = r.y;
-        if (a.x_rot != nullptr) {
-            T* xr = reinterpret_cast<T*>(a.x_rot) + chunk0;
-            store4<T>(xr + d0, v[0], v[1], v[2], v[3]);
-            store4<T>(xr + d1, v[4], v[5], v[6], v[7]);
+        // d0 / d1: where the lane's two 4-element halves belong, relative to its own column (0 / 4 unless a power-of-4 Hadamard
+        // left them permuted inside the chunk, see hadamard_dest)
+        *reinterpret_cast<uint32_t*>(qp + c * kStep + d0) = r.x;
+        *reinterpret_cast<uint32_t*>(qp + c * kStep + d1) = r.y;
+        if (rp != nullptr) {
+            store4<T>(rp + c * kStep + d0, v[0], v[1], v[2], v[3]);
+            store4<T>(rp + c * kStep + d1, v[4], v[5], v[6], v[7]);
         }
     }
     if (a.rowsum != nullptr) {

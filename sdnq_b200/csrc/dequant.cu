@@ -10,6 +10,7 @@
 // reads 32*bits contiguous bytes and writes 256 contiguous outputs (512 B of bf16) per step -- every global
 // access is a full-sector, fully-coalesced transaction and there is no reuse to stage in shared memory.
 #include "unpack.cuh"
+#include "hadamard_tc.cuh"
 
 namespace sdnq {
 
@@ -170,6 +171,71 @@ __global__ void __launch_bounds__(kThreads, kPlain ? 5 : 3) dequant_kernel(const
                     store4<OutT>(o + hadamard_dest_dyn(a.hadamard, lane, 1), w[4], w[5], w[6], w[7]);
                 }
             }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K3 rotated 8-bit path
+// 8-bit formats (int8 / uint8 / fp8 / 8-bit minifloats) whose dequantised weight is un-rotated (use_hadamard layers on the
+// dequant path: FLUX AdaLN Linears with M = batch < 32, `.dequantize()`): scale -> round to the result dtype -> Hadamard on
+// the tensor cores (hadamard_tc.cuh) -> store.  Lane l owns elements [4l, 4l+4) and [128+4l, 128+4l+4) of a 256-chunk: two
+// 4-byte code loads, two 8-byte stores, all coalesced.  The generic kernel's shuffle butterflies made this path issue-bound
+// (1.7 TB/s on the 3072 -> 18432 AdaLN weight).
+template <typename OutT, int U>
+__global__ void __launch_bounds__(kThreads, 4) dequant_rot8_kernel(const DequantArgs a, OutT* __restrict__ out, int chunks_per_row, int total_chunks) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const int warps_total = gridDim.x * kWarps;
+    hadtc::Rotation<OutT> rot;
+    rot.init(a.hadamard, lane);
+    const float factor = hadamard_factor<OutT>(a.hadamard);
+    for (int t0 = warp_global; t0 < total_chunks; t0 += warps_total * U) {
+        int n[U], k[U];
+        bool live[U];
+        uint32_t lo[U], hi[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = t0 + u * warps_total;
+            live[u] = t < total_chunks;                               // warp-uniform
+            n[u] = live[u] ? static_cast<int>(static_cast<uint32_t>(t) / static_cast<uint32_t>(chunks_per_row)) : 0;
+            k[u] = live[u] ? (t - n[u] * chunks_per_row) * 256 + lane * 4 : 0;
+            lo[u] = hi[u] = 0u;
+            const uint8_t* row = a.weight + int64_t(n[u]) * a.K32;
+            if (live[u] && k[u] < a.K32) lo[u] = *reinterpret_cast<const uint32_t*>(row + k[u]);
+            if (live[u] && k[u] + 128 < a.K32) hi[u] = *reinterpret_cast<const uint32_t*>(row + k[u] + 128);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!live[u]) continue;
+            const bool ok_lo = k[u] < a.K32, ok_hi = k[u] + 128 < a.K32;
+            uint32_t codes[8];
+            float q[8], w[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { codes[i] = (lo[u] >> (8 * i)) & 0xFFu; codes[4 + i] = (hi[u] >> (8 * i)) & 0xFFu; }
+            codes_to_values<8>(codes, a.f, q);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const bool ok = h ? ok_hi : ok_lo;
+                const int64_t si = int64_t(n[u]) * a.row_stride32 + group_of(a, k[u] + 128 * h);
+                const float sc = ok ? a.scale[si] : 0.f;
+                const float z = (ok && a.zp != nullptr) ? a.zp[si] : 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float v = a.zp != nullptr ? fmaf(q[4 * h + i], sc, z) : __fmul_rn(q[4 * h + i], sc);
+                    w[4 * h + i] = ok ? v : 0.f;
+                }
+            }
+            uint4 raw;                                                // rounded to the result dtype before the rotation (dequantizer.py:80-83)
+            raw.x = hadtc::Half16<OutT>::pack(w[0], w[1]);
+            raw.y = hadtc::Half16<OutT>::pack(w[2], w[3]);
+            raw.z = hadtc::Half16<OutT>::pack(w[4], w[5]);
+            raw.w = hadtc::Half16<OutT>::pack(w[6], w[7]);
+            rot.apply(raw, factor);
+            OutT* o = out + int64_t(n[u]) * a.K32 + k[u];
+            if (ok_lo) *reinterpret_cast<uint2*>(o) = make_uint2(raw.x, raw.y);
+            if (ok_hi) *reinterpret_cast<uint2*>(o + 128) = make_uint2(raw.z, raw.w);
         }
     }
 }
@@ -486,7 +552,17 @@ static int launch_dequant(const DequantArgs& a, void* out, cudaStream_t st) {
     const bool rowwise = a.gpr32 == 1 && a.row_stride32 == 1 && a.group32 >= a.K32;
     const bool flat = fast_int && (a.f.bits == 4 || a.f.bits == 8) && a.f.word_bytes == 1 && a.K32 % 8 == 0 && total_oct < (int64_t(1) << 31) &&
                       (grouped || rowwise) && (reinterpret_cast<uintptr_t>(a.weight) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    if (flat) {
+    // rotated 8-bit weights without SVD: tensor-core un-rotate
+    bool rot8 = false;
+    if constexpr (sizeof(OutT) == 2) {
+        rot8 = a.hadamard != 0 && a.up == nullptr && !a.codebook && a.f.bits == 8 && a.f.word_bytes == 1 && a.K32 % 8 == 0 &&
+               ((a.group32 & 3) == 0 || a.group32 >= a.K32) && (reinterpret_cast<uintptr_t>(a.weight) & 3) == 0 &&
+               (reinterpret_cast<uintptr_t>(out) & 7) == 0 && getenv("SDNQ_B200_HADAMARD_BUTTERFLY") == nullptr;
+    }
+    if (rot8) {
+        if constexpr (sizeof(OutT) == 2)
+            e = launch_pdl(dequant_rot8_kernel<OutT, U>, dim3(grid), dim3(kThreads), 0, st, a, reinterpret_cast<OutT*>(out), cpr, total);
+    } else if (flat) {
         const bool twos = a.f.bits == 8 && !a.f.is_unsigned;
         const float bias = twos ? 8388736.0f : 8388608.0f - static_cast<float>(a.f.int_offset);
         const uint32_t flip = twos ? 0x80808080u : 0u;

@@ -16,6 +16,7 @@
 //                          swizzled shared-memory staging and TMA bulk stores (clip the M / N tails)
 // A = activations [M,K] (row-major, K contiguous); B = weight, the reference's K-major [K,N] operand, i.e.
 // physically [N,K] with K contiguous -- exactly the "TN" shape tcgen05 wants, so no transposes anywhere.
+#include <cmath>
 #include <mutex>
 #include <type_traits>
 
@@ -63,10 +64,12 @@ constexpr int kSyncStrips = 512;
 
 // WB = storage bits of the B operand: 8 (int8 / fp8 tiles land in the ring directly by TMA) or 4 (packed int4 / uint4:
 // TMA stages the packed tile, four unpack warps expand it into the ring -- "unpack in the GEMM prologue").
-template <int BN, int WB = 8>
+// CG = CTAs per MMA (tcgen05 cta_group): 1, or 2 = a CTA pair computes a 256 x BN tile, each CTA staging its own 128 rows of A
+// and only half of the B tile (BN/2 weight rows) -- per SM that is 16 + BN/2 * 128 B per k-block instead of 16 + BN * 128 B.
+template <int BN, int WB = 8, int CG = 1>
 struct Cfg {
     static constexpr int kStageA = BM * BK;
-    static constexpr int kStageB = BN * BK;
+    static constexpr int kStageB = BN / CG * BK;
     static constexpr int kStageBytes = kStageA + kStageB;
     static constexpr int kVecBytes = 2 * BN * 4;                        // sw[BN] and bias[BN] of the current tile as f32
     static constexpr int kPStages = WB < 8 ? 3 : 0;                     // packed staging ring
@@ -79,6 +82,7 @@ struct Cfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + kFixed;
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
     static_assert(kStages >= 3, "pipeline too shallow");
+    static_assert(CG == 1 || (CG == 2 && WB == 8 && BN % 32 == 0), "CTA pairs: unpacked operands, BN/2 a multiple of 16");
 };
 
 // 8 consecutive values of a f32 / bf16 / f16 vector as floats (16 B aligned for 2-byte types, 32 B for f32)
@@ -99,11 +103,16 @@ __device__ __forceinline__ void load8_any(const void* p, int64_t i, int dtype, f
 // Linear instead of two: the dependent-launch gap (~2.5 us, as long as the GEMM itself at SD-XL sizes) disappears,
 // and the weight prefetch overlaps the quantisation.  All CTAs are co-resident (grid <= SMs, 1 CTA/SM), which the
 // cross-CTA wait relies on.
-template <int BN, bool kInt8, int OUT, bool kSimple, int WB, int XM>
-__global__ void __launch_bounds__((Cfg<BN, WB>::kThreads), 1)
+template <int BN, bool kInt8, int OUT, bool kSimple, int WB, int XM, int CG>
+__global__ void __launch_bounds__((Cfg<BN, WB, CG>::kThreads), 1)
 gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_o, const GemmParams p) {
-    using C = Cfg<BN, WB>;
+    using C = Cfg<BN, WB, CG>;
+    static_assert(CG == 1 || XM == 0, "the fused quantiser runs with single-CTA MMAs");
+    constexpr bool kPair = CG == 2;
+    // CTA pair: rank 0 (the leader) issues the MMAs; tiles are numbered per pair (256 rows x BN columns)
+    const uint32_t cta_rank = kPair ? ptx::cluster_ctarank() : 0u;
+    const int tile_first = int(blockIdx.x) / CG, tile_step = int(gridDim.x) / CG;
     constexpr bool kPacked = WB < 8;
     constexpr int kOutBytes = (OUT == OUT_BF16 || OUT == OUT_F16) ? 2 : 4;
     constexpr int CPB = 128 / kOutBytes;              // output columns per 128 B store block: 64 or 32
@@ -128,9 +137,18 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_m = (p.M + BM - 1) / BM, num_n = (p.N + BN - 1) / BN;
+    const int num_m = (p.M + BM * CG - 1) / (BM * CG), num_n = (p.N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
     const int num_kb = (p.K + BK - 1) / BK;
+    auto tile_m0 = [&](int tile) { return (tile / num_n) * (BM * CG) + int(cta_rank) * BM; };      // this CTA's 128 output rows
+    auto tile_nb0 = [&](int tile) { return (tile % num_n) * BN + int(cta_rank) * (BN / CG); };      // this CTA's share of the B rows
+    // the barrier TMA completions are counted on: the leader's (it alone waits for the operands of both CTAs)
+    auto load_bar = [&](int s) { return kPair ? ptx::mapa(full_bar(s), 0) : full_bar(s); };
+    auto tma_load = [&](uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+        if constexpr (kPair) ptx::tma_load_2d_pair(dst, tmap, bar, c0, c1);
+        else ptx::tma_load_2d(dst, tmap, bar, c0, c1);
+    };
+    auto expect_stage = [&](int s) { if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(s), C::kStageBytes * CG); };
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
@@ -142,7 +160,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(tfull_bar(s), 1);
-            ptx::mbar_init(tempty_bar(s), kEpiWarps);
+            ptx::mbar_init(tempty_bar(s), kEpiWarps * CG);       // pair: the epilogue warps of both CTAs release the leader's MMA warp
         }
         for (int s = 0; s < C::kPStages; ++s) {
             ptx::mbar_init(pfull_bar(s), 1);
@@ -152,17 +170,18 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, C::kTmemCols);
-        ptx::tmem_relinquish();
+        if constexpr (kPair) { ptx::tmem_alloc_pair(tmem_slot, C::kTmemCols); ptx::tmem_relinquish_pair(); }
+        else { ptx::tmem_alloc(tmem_slot, C::kTmemCols); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) ptx::cluster_sync();     // the peer's barriers are initialised before anything signals them
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     pdl_launch_dependents();     // our own dependents may begin their prologue
 
     // weight prefetch bookkeeping shared by the producer branch below
-    const int tile0 = blockIdx.x;
+    const int tile0 = tile_first;
     const int npre = (!kPacked && tile0 < num_tiles) ? (num_kb < C::kStages ? num_kb : C::kStages) : 0;
     if constexpr (XM != 0) {
         // ======================================================== phase 1: quantise this CTA's share of the activation rows
@@ -262,7 +281,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             pdl_wait();
             int stage = 0, ps = 0;
             uint32_t phase = 0, pphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
                 const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -280,23 +299,23 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             // the first ring-full of B tiles now, then wait for the predecessor (the activation quantiser) and add the A tiles.
             if constexpr (XM == 0) {
                 if (npre > 0) {
-                    const int n0 = (tile0 % num_n) * BN;
+                    const int nb0 = tile_nb0(tile0);
                     for (int s = 0; s < npre; ++s) {
-                        ptx::mbar_arrive_expect_tx(full_bar(s), C::kStageBytes);
-                        ptx::tma_load_2d(smem_b + s * C::kStageB, &tmap_b, full_bar(s), s * BK, n0);
+                        expect_stage(s);
+                        tma_load(smem_b + s * C::kStageB, &tmap_b, load_bar(s), s * BK, nb0);
                     }
                 }
                 pdl_wait();
             }
             if (npre > 0) {
-                const int m0 = (tile0 / num_n) * BM;
+                const int m0 = tile_m0(tile0);
                 acquire_strip(tile0 / num_n);
-                for (int s = 0; s < npre; ++s) ptx::tma_load_2d(smem_a + s * C::kStageA, &tmap_a, full_bar(s), s * BK, m0);
+                for (int s = 0; s < npre; ++s) tma_load(smem_a + s * C::kStageA, &tmap_a, load_bar(s), s * BK, m0);
             }
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+                const int m0 = tile_m0(tile), nb0 = tile_nb0(tile);
                 if (tile != tile0) acquire_strip(tile / num_n);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     if (tile == tile0 && kb < npre) {             // already in flight (prefetched above)
@@ -304,9 +323,9 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         continue;
                     }
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-                    ptx::mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
-                    ptx::tma_load_2d(smem_a + stage * C::kStageA, &tmap_a, full_bar(stage), kb * BK, m0);
-                    ptx::tma_load_2d(smem_b + stage * C::kStageB, &tmap_b, full_bar(stage), kb * BK, n0);
+                    expect_stage(stage);
+                    tma_load(smem_a + stage * C::kStageA, &tmap_a, load_bar(stage), kb * BK, m0);
+                    tma_load(smem_b + stage * C::kStageB, &tmap_b, load_bar(stage), kb * BK, nb0);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
                 }
                 release_strip(tile / num_n);
@@ -314,13 +333,14 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else if (warp == 1) {
         // ======================================================== MMA issuer
-        if (lane == 0) {
+        if (lane == 0 && cta_rank == 0) {
             pdl_wait();
-            constexpr uint32_t idesc = kInt8 ? ptx::make_idesc(2, 1, 1, BM, BN) : ptx::make_idesc(1, 0, 0, BM, BN);
+            constexpr uint32_t idesc = kInt8 ? ptx::make_idesc(2, 1, 1, BM * CG, BN) : ptx::make_idesc(1, 0, 0, BM * CG, BN);
+            auto commit = [&](uint32_t bar) { if constexpr (kPair) ptx::umma_commit_pair(bar); else ptx::umma_commit(bar); };
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1u;
                 ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);     // epilogue has drained this accumulator stage
@@ -334,13 +354,17 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advancing K inside the 128 B swizzle span = advancing the start address (>>4 units)
-                        ptx::umma_ss<kInt8>(d_tmem, a_desc + uint64_t(k * UMMA_K >> 4), b_desc + uint64_t(k * UMMA_K >> 4), idesc,
-                                            (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (kPair)
+                            ptx::umma_ss_pair<kInt8>(d_tmem, a_desc + uint64_t(k * UMMA_K >> 4), b_desc + uint64_t(k * UMMA_K >> 4), idesc,
+                                                     (kb | k) != 0 ? 1u : 0u);
+                        else
+                            ptx::umma_ss<kInt8>(d_tmem, a_desc + uint64_t(k * UMMA_K >> 4), b_desc + uint64_t(k * UMMA_K >> 4), idesc,
+                                                (kb | k) != 0 ? 1u : 0u);
                     }
-                    ptx::umma_commit(empty_bar(stage));           // smem slot free once these MMAs retire
+                    commit(empty_bar(stage));                     // smem slot free (in both CTAs of a pair) once these MMAs retire
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
                 }
-                ptx::umma_commit(tfull_bar(as));                  // accumulator complete
+                commit(tfull_bar(as));                            // accumulator complete
             }
         }
     } else if (kPacked && warp >= 6) {
@@ -351,7 +375,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int t = threadIdx.x - 192;
         int stage = 0, ps = 0;
         uint32_t phase = 0, pphase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
             for (int kb = 0; kb < num_kb; ++kb) {
                 ptx::mbar_wait(pfull_bar(ps), pphase);            // packed tile landed
                 ptx::mbar_wait(empty_bar(stage), phase ^ 1u);     // the ring slot's previous MMAs retired
@@ -392,10 +416,10 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int q = warp & 3;                                   // TMEM lane quarter this warp may access
         const uint32_t my_o = smem_o + uint32_t(warp - 2) * (kStoreBufs * kStoreBlkBytes);
         int it = 0, blk = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1u;
-            const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+            const int m0 = tile_m0(tile), n0 = (tile % num_n) * BN;
             const int mrow0 = m0 + q * 32;
             const int m = mrow0 + lane;
             const bool m_ok = m < p.M;
@@ -562,18 +586,23 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+            if (lane == 0) {
+                if constexpr (kPair) ptx::mbar_arrive_cluster(ptx::mapa(tempty_bar(as), 0));
+                else ptx::mbar_arrive(tempty_bar(as));
+            }
         }
         if (lane == 0) ptx::tma_store_wait_read<0>();             // smem must outlive the last bulk stores
         __syncwarp();
     }
     // ---- teardown
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) ptx::cluster_sync();     // neither CTA's shared memory / barriers may go away while the peer can still touch them
+    else __syncthreads();
     if (warp == 1) {
         __syncwarp();
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+        if constexpr (kPair) ptx::tmem_dealloc_pair(tmem_base, C::kTmemCols);
+        else ptx::tmem_dealloc(tmem_base, C::kTmemCols);
     }
 }
 
@@ -615,27 +644,44 @@ int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int
     return SDNQ_OK;
 }
 
-template <int BN, bool kInt8, int OUT, bool kSimple, int WB = 8, int XM = 0>
+template <int BN, bool kInt8, int OUT, bool kSimple, int WB = 8, int XM = 0, int CG = 1>
 int launch_gemm(const void* a, const void* b, const GemmParams& p, cudaStream_t st) {
-    using C = Cfg<BN, WB>;
+    using C = Cfg<BN, WB, CG>;
+    auto kernel = gemm_w8a8_kernel<BN, kInt8, OUT, kSimple, WB, XM, CG>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_w8a8_kernel<BN, kInt8, OUT, kSimple, WB, XM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    });
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes); });
     SDNQ_REQUIRE(attr_err == cudaSuccess, SDNQ_ECUDA, "cudaFuncSetAttribute(max dynamic smem %d) failed: %s", C::kSmemBytes,
                  cudaGetErrorString(attr_err));
     CUtensorMap ta, tb, to;
     int rc = make_tmap(&ta, a, p.M, p.K, 1, BM);
     if (rc != SDNQ_OK) return rc;
-    rc = WB < 8 ? make_tmap(&tb, b, p.N, int64_t(p.K) * WB / 8, 1, BN, BK * WB / 8) : make_tmap(&tb, b, p.N, p.K, 1, BN);
+    rc = WB < 8 ? make_tmap(&tb, b, p.N, int64_t(p.K) * WB / 8, 1, BN, BK * WB / 8) : make_tmap(&tb, b, p.N, p.K, 1, BN / CG);
     if (rc != SDNQ_OK) return rc;
     rc = make_tmap(&to, p.out, p.M, p.N, (OUT == OUT_BF16 || OUT == OUT_F16) ? 2 : 4, 32);
     if (rc != SDNQ_OK) return rc;
-    const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+    const int tiles = ((p.M + BM * CG - 1) / (BM * CG)) * ((p.N + BN - 1) / BN);      // CG == 2: 256-row tiles, one per CTA pair
     // fused quantiser: always one CTA per SM (CTAs without a tile still quantise their share of the rows)
-    const int grid = (XM != 0 || tiles >= num_sms()) ? num_sms() : tiles;
-    cudaError_t e = launch_pdl(gemm_w8a8_kernel<BN, kInt8, OUT, kSimple, WB, XM>, dim3(grid), dim3(C::kThreads), C::kSmemBytes, st, ta, tb, to, p);
+    const int slots = num_sms() / CG;
+    const int grid = CG * ((XM != 0 || tiles >= slots) ? slots : tiles);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(C::kThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (CG == 2) {                        // the two CTAs of a pair are co-scheduled on one TPC
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 2;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ta, tb, to, p);
     if (e != cudaSuccess) return set_error(SDNQ_ECUDA, "launch of gemm_w8a8_kernel failed: %s", cudaGetErrorString(e));
     return check_launch("gemm_w8a8_kernel");
 }
@@ -648,6 +694,15 @@ int launch_gemm_packed4(const void* a, const void* b, const GemmParams& p, cudaS
         case SDNQ_F16: return simple ? launch_gemm<128, true, OUT_F16, true, 4>(a, b, p, st) : launch_gemm<128, true, OUT_F16, false, 4>(a, b, p, st);
         default: return simple ? launch_gemm<128, true, OUT_F32, true, 4>(a, b, p, st) : launch_gemm<128, true, OUT_F32, false, 4>(a, b, p, st);
     }
+}
+
+// CTA-pair kernels exist for the 2-byte output types (what a bf16 / f16 model produces); everything else runs single-CTA MMAs
+template <int BN, bool kInt8>
+int launch_gemm_pair(const void* a, const void* b, const GemmParams& p, cudaStream_t st) {
+    const bool simple = !p.zp && !p.colsum && (p.bias == nullptr || p.bias_ld == 0);
+    if (p.out_dtype == SDNQ_BF16)
+        return simple ? launch_gemm<BN, kInt8, OUT_BF16, true, 8, 0, 2>(a, b, p, st) : launch_gemm<BN, kInt8, OUT_BF16, false, 8, 0, 2>(a, b, p, st);
+    return simple ? launch_gemm<BN, kInt8, OUT_F16, true, 8, 0, 2>(a, b, p, st) : launch_gemm<BN, kInt8, OUT_F16, false, 8, 0, 2>(a, b, p, st);
 }
 
 template <int BN, bool kInt8>
@@ -664,7 +719,8 @@ int launch_gemm_out(const void* a, const void* b, const GemmParams& p, cudaStrea
 // Tile-N choice: the widest tile that still gives every SM work; BN=256 halves the per-MMA shared-memory
 // operand traffic relative to BN=128, so it wins whenever the grid is full either way.
 int pick_bn(int M, int N) {
-    static const int forced = [] { const char* e = getenv("SDNQ_B200_BN"); return e ? atoi(e) : 0; }();   // tuning knob
+    const char* bn_env = getenv("SDNQ_B200_BN");      // tuning knob, read per call
+    const int forced = bn_env ? atoi(bn_env) : 0;
     if (forced == 128 || forced == 192 || forced == 256) return forced;
     const int sms = num_sms();
     const int num_m = (M + BM - 1) / BM;
@@ -680,6 +736,39 @@ int pick_bn(int M, int N) {
     if (e192 >= e128 && e192 >= e64) return 192;
     if (e128 >= e64) return 128;
     return 64;
+}
+
+// CTA pairs (tcgen05 cta_group::2): 0 = use single-CTA MMAs, else the tile width.  SDNQ_B200_CG=1 / 2 forces the choice.
+int pick_pair(const GemmParams& p) {
+    const char* cg_env = getenv("SDNQ_B200_CG");      // read per call: tests and A/B tools flip it inside one process
+    const int forced = cg_env ? atoi(cg_env) : 0;
+    if (forced == 1 || p.raw || (p.out_dtype != SDNQ_BF16 && p.out_dtype != SDNQ_F16) || p.M <= BM) return 0;
+    const char* bn_env = getenv("SDNQ_B200_BN");
+    const int forced_bn = bn_env ? atoi(bn_env) : 0;
+    const int pairs = num_sms() / 2;
+    const int num_m2 = (p.M + 2 * BM - 1) / (2 * BM);
+    auto eff = [&](int bn) {
+        const int tiles = num_m2 * ((p.N + bn - 1) / bn);
+        const int waves = (tiles + pairs - 1) / pairs;
+        return static_cast<double>(tiles) / (static_cast<double>(waves) * pairs);
+    };
+    if (forced == 2) return forced_bn == 128 || forced_bn == 256 ? forced_bn : (eff(256) >= 0.92 * eff(128) ? 256 : 128);
+    // Auto: a small cost model calibrated on B200 (profiles/r01_gemm_pair_vs_single.md; microseconds, k-block = 128 bytes of K):
+    //   time = waves * (k-blocks * per-k-block cost + exposed epilogue) + launch / prologue / drain
+    // single-CTA tiles stream 16 KB + BN * 128 B of operands per k-block and SM, a pair 16 KB + 128 * 128 B for a 256-wide tile,
+    // which is what makes the pair faster once a launch has several waves of deep tiles and slower for the small SD-XL GEMMs
+    // (cluster launch + two cluster barriers, half as many schedulable units).
+    const int kb = (p.K + BK - 1) / BK;
+    const int sms = num_sms();
+    const int num_m = (p.M + BM - 1) / BM;
+    auto single_time = [&](int bn, double per_kb) {
+        const int tiles = num_m * ((p.N + bn - 1) / bn);
+        return ((tiles + sms - 1) / sms) * (kb * per_kb + 0.3) + 4.5;
+    };
+    const double t_single = fmin(single_time(256, 0.40), fmin(single_time(192, 0.32), single_time(128, 0.25)));
+    const int ptiles = num_m2 * ((p.N + 255) / 256);
+    const double t_pair = ((ptiles + pairs - 1) / pairs) * (kb * 0.36 + 0.3) + 6.0;
+    return t_pair < 0.97 * t_single ? 256 : 0;
 }
 
 }  // namespace
@@ -705,6 +794,10 @@ int scaled_mm_impl(const void* a, const void* b, int ab_dtype, GemmParams p, cud
         SDNQ_REQUIRE(wbits == 4 && i8 && !p.raw, SDNQ_EUNSUPPORTED, "in-kernel unpack covers 4-bit integer weights with int8 activations (got %d bits)", wbits);
         SDNQ_REQUIRE(p.K % 32 == 0, SDNQ_EUNSUPPORTED, "packed 4-bit B needs K %% 32 == 0 (16-byte row pitch), K=%d", p.K);
         return launch_gemm_packed4(a, b, p, st);
+    }
+    if (const int pair_bn = pick_pair(p); pair_bn != 0) {
+        if (pair_bn == 256) return i8 ? launch_gemm_pair<256, true>(a, b, p, st) : launch_gemm_pair<256, false>(a, b, p, st);
+        return i8 ? launch_gemm_pair<128, true>(a, b, p, st) : launch_gemm_pair<128, false>(a, b, p, st);
     }
     switch (pick_bn(p.M, p.N)) {
         case 256: return i8 ? launch_gemm_out<256, true>(a, b, p, st) : launch_gemm_out<256, false>(a, b, p, st);

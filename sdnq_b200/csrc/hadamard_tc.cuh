@@ -46,9 +46,14 @@ constexpr int left_entry(int lg, int r, int r2) {       // lg > 4: L = I (x) H_(
 constexpr int slot_col(int s) { return 4 * ((s & 7) >> 1) + (s & 1) + 2 * (s >> 3); }
 
 // Per-lane constant fragments for every group size (lg = 2..8) and both 16-bit formats of MMA 1 (MMA 2 is always bf16):
-// words 0-3 = B fragments of MMA 1 ([n-block][reg]), words 4-7 = A fragment of MMA 2.
+// words 0-3 = B fragments of MMA 1 ([n-block][reg]), words 4-7 = A fragment of MMA 2.  For the H4 family (lg even) the
+// normalisation 1/sqrt(G) = 2^-(lg/2) is exact in every format, so it is folded into the constants of the last product
+// (exact: a power-of-two scale commutes with every rounding here) and the rotation needs no multiply afterwards.
 struct FragTable { uint32_t w[7][2][32][8]; };
-constexpr uint32_t half_bits(int sign, bool f16) { return sign == 0 ? 0u : f16 ? (sign > 0 ? 0x3C00u : 0xBC00u) : (sign > 0 ? 0x3F80u : 0xBF80u); }
+// +-2^-shift as f16 / bf16 bits (0 for sign == 0)
+constexpr uint32_t half_bits(int sign, bool f16, int shift = 0) {
+    return sign == 0 ? 0u : (sign < 0 ? 0x8000u : 0u) | (f16 ? uint32_t(15 - shift) << 10 : uint32_t(127 - shift) << 7);
+}
 constexpr FragTable make_frag_table() {
     FragTable t{};
     for (int lg = 2; lg <= 8; ++lg)
@@ -56,16 +61,18 @@ constexpr FragTable make_frag_table() {
             for (int lane = 0; lane < 32; ++lane) {
                 const int g = lane >> 2, q = lane & 3;
                 uint32_t* w = t.w[lg - 2][f][lane];
+                const int fold = (lg & 1) == 0 ? lg / 2 : 0;          // folded into MMA 1 when it is the only product, else MMA 2
+                const int s1 = lg > 4 ? 0 : fold, s2 = lg > 4 ? fold : 0;
                 for (int j = 0; j < 2; ++j) {
                     const int n = slot_col(8 * j + g);
-                    w[2 * j] = half_bits(right_entry(lg, slot_col(2 * q), n), f) | (half_bits(right_entry(lg, slot_col(2 * q + 1), n), f) << 16);
-                    w[2 * j + 1] = half_bits(right_entry(lg, slot_col(2 * q + 8), n), f) | (half_bits(right_entry(lg, slot_col(2 * q + 9), n), f) << 16);
+                    w[2 * j] = half_bits(right_entry(lg, slot_col(2 * q), n), f, s1) | (half_bits(right_entry(lg, slot_col(2 * q + 1), n), f, s1) << 16);
+                    w[2 * j + 1] = half_bits(right_entry(lg, slot_col(2 * q + 8), n), f, s1) | (half_bits(right_entry(lg, slot_col(2 * q + 9), n), f, s1) << 16);
                 }
                 if (lg > 4) {   // A2[r'][r] = L[r][r']:  a0 = (row g, k 2q..), a1 = (row g+8, k 2q..), a2 = (row g, k 2q+8..), a3 = (row g+8, k 2q+8..)
-                    w[4] = half_bits(left_entry(lg, 2 * q, g), false) | (half_bits(left_entry(lg, 2 * q + 1, g), false) << 16);
-                    w[5] = half_bits(left_entry(lg, 2 * q, g + 8), false) | (half_bits(left_entry(lg, 2 * q + 1, g + 8), false) << 16);
-                    w[6] = half_bits(left_entry(lg, 2 * q + 8, g), false) | (half_bits(left_entry(lg, 2 * q + 9, g), false) << 16);
-                    w[7] = half_bits(left_entry(lg, 2 * q + 8, g + 8), false) | (half_bits(left_entry(lg, 2 * q + 9, g + 8), false) << 16);
+                    w[4] = half_bits(left_entry(lg, 2 * q, g), false, s2) | (half_bits(left_entry(lg, 2 * q + 1, g), false, s2) << 16);
+                    w[5] = half_bits(left_entry(lg, 2 * q, g + 8), false, s2) | (half_bits(left_entry(lg, 2 * q + 1, g + 8), false, s2) << 16);
+                    w[6] = half_bits(left_entry(lg, 2 * q + 8, g), false, s2) | (half_bits(left_entry(lg, 2 * q + 9, g), false, s2) << 16);
+                    w[7] = half_bits(left_entry(lg, 2 * q + 8, g + 8), false, s2) | (half_bits(left_entry(lg, 2 * q + 9, g + 8), false, s2) << 16);
                 }
             }
     return t;
@@ -114,10 +121,12 @@ struct Rotation {
     uint32_t b1[4];      // MMA 1 B fragments: [n-block j][reg]
     uint32_t a2[4];      // MMA 2 A fragment
     bool two_sided;
+    bool folded;         // 1/sqrt(G) is already in the constants (H4 family)
 
     __device__ __forceinline__ void init(int G, int lane) {
         const int lg = 31 - __clz(G);
         two_sided = G > 16;
+        folded = (lg & 1) == 0;
         constexpr int f = ElemTraits<T>::kDtype == SDNQ_F16 ? 1 : 0;
         const uint4* w = reinterpret_cast<const uint4*>(g_frag_table.w[lg - 2][f][lane]);
         const uint4 lo = w[0], hi = w[1];
@@ -138,10 +147,14 @@ struct Rotation {
 #pragma unroll
             for (int i = 0; i < 4; ++i) { t0[i] = y0[i]; t1[i] = y1[i]; }
         }
-        raw.x = Half16<T>::pack(t0[0] * factor, t0[1] * factor);
-        raw.y = Half16<T>::pack(t1[0] * factor, t1[1] * factor);
-        raw.z = Half16<T>::pack(t0[2] * factor, t0[3] * factor);
-        raw.w = Half16<T>::pack(t1[2] * factor, t1[3] * factor);
+        if (!folded) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { t0[i] *= factor; t1[i] *= factor; }
+        }
+        raw.x = Half16<T>::pack(t0[0], t0[1]);
+        raw.y = Half16<T>::pack(t1[0], t1[1]);
+        raw.z = Half16<T>::pack(t0[2], t0[3]);
+        raw.w = Half16<T>::pack(t1[2], t1[3]);
     }
 
     // y += L^T . t for one n-block: t = C fragment (rows g / g+8) -> bf16 pieces (hi, lo[, lo2]: 8 bits each) ->

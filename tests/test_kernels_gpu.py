@@ -261,6 +261,42 @@ def test_scaled_mm_many_tiles_persistent_loop():
         assert torch.equal(got, ref)
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (300, 520, 400), (1024, 1280, 1280), (513, 776, 208), (4096, 640, 640), (2048, 3072, 3072),
+                                   (129, 264, 64), (777, 10240, 1280)])
+@pytest.mark.parametrize("kind", ["int8", "fp8", "int8_zp"])
+def test_cta_pair_gemm_matches_single_cta(M, N, K, kind, monkeypatch):
+    """tcgen05 cta_group::2 kernels (a CTA pair per 256-row tile) against the single-CTA kernels and the exact oracle."""
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = torch.randint(-128, 128, (M, K), generator=g, dtype=torch.int8)
+    b = torch.randint(-128, 128, (N, K), generator=g, dtype=torch.int8)
+    sx = (torch.rand(M, generator=g) * 0.01 + 1e-3).to(DEV)
+    sw = (torch.rand(N, generator=g) * 0.01 + 1e-3).to(DEV)
+    bias = torch.randn(N, generator=g).to(torch.bfloat16).to(DEV)
+    kw = {}
+    if kind == "fp8":
+        a = (a.float() / 16).to(torch.float8_e4m3fn)
+        b = (b.float() / 16).to(torch.float8_e4m3fn)
+    if kind == "int8_zp":
+        kw = dict(rowsum=a.to(torch.int32).sum(-1).to(torch.int32).to(DEV), zp=torch.randn(N, generator=g).to(DEV))
+    a, b = a.to(DEV), b.to(DEV)
+    monkeypatch.setenv("SDNQ_B200_CG", "1")
+    single = ops().scaled_mm(a, b, sx, sw, bias, torch.bfloat16, **kw)
+    for bn in ("128", "256"):
+        monkeypatch.setenv("SDNQ_B200_CG", "2")
+        monkeypatch.setenv("SDNQ_B200_BN", bn)
+        pair = ops().scaled_mm(a, b, sx, sw, bias, torch.bfloat16, **kw)
+        monkeypatch.delenv("SDNQ_B200_BN")
+        torch.cuda.synchronize()
+        if kind == "fp8":
+            assert int(bf16_ulp_diff(pair, single).max()) <= 1
+        else:
+            assert torch.equal(pair, single), f"BN={bn}: max diff {float((pair.float() - single.float()).abs().max())}"
+    if kind == "int8":
+        acc = O.int_mm(a.cpu().numpy(), b.cpu().numpy().T)
+        ref = O.scaled_mm(acc, sx.cpu().numpy().reshape(-1, 1), sw.cpu().numpy().reshape(1, -1), bias.float().cpu().numpy(), out_dtype="bfloat16")
+        assert int(bf16_ulp_diff(single.cpu(), torch.from_numpy(ref).to(torch.bfloat16)).max()) <= 1
+
+
 # ----------------------------------------------------------------------------------------------- K2 + K1 against the fixtures
 @pytest.mark.parametrize("path", [p for p in LAYER_FILES if "mm_xq" in np.load(p).files],
                          ids=[i for p, i in zip(LAYER_FILES, LAYER_IDS) if "mm_xq" in np.load(p).files])
@@ -280,6 +316,42 @@ def test_matmul_operands_and_output_match_reference(path):
         else:
             assert np.array_equal(got_xq, ref_xq)
         assert np.array_equal(sx.cpu().numpy(), z["mm_sx"].reshape(-1))
+
+
+# ----------------------------------------------------------------------------------------------- rotated 8-bit dequant (tensor-core un-rotate)
+@pytest.mark.parametrize("wd", ["int8", "uint8", "float8_e4m3fn"])
+@pytest.mark.parametrize("N,K,gs,G", [(96, 1024, -1, 256), (130, 896, 128, 128), (64, 640, 32, 64), (48, 512, -1, 16), (33, 3072, -1, 256)])
+def test_dequant_rotated_8bit(wd, N, K, gs, G):
+    """use_hadamard layers on the dequant path (dequant_rot8_kernel): scale -> round -> un-rotate, against the oracle."""
+    rng = np.random.default_rng(N + K + G)
+    groups = K // gs if gs > 0 else 1
+    sshape = (N, groups, 1) if groups > 1 else (N, 1)
+    scale = (rng.random(sshape) * 0.02 + 0.001).astype(np.float32)
+    zp = None
+    if wd == "int8":
+        w_np = rng.integers(-128, 128, size=(N, K)).astype(np.int8)
+        w_t = torch.from_numpy(w_np)
+    elif wd == "uint8":
+        w_np = rng.integers(0, 256, size=(N, K)).astype(np.uint8)
+        w_t = torch.from_numpy(w_np)
+        zp = (rng.standard_normal(sshape) * 0.05).astype(np.float32)
+    else:
+        w_t = torch.from_numpy(np.clip(rng.standard_normal((N, K)).astype(np.float32) * 100, -448, 448)).to(torch.float8_e4m3fn)
+        w_np = w_t.float().numpy()
+    qshape = [N, groups, gs] if groups > 1 else [N, K]
+    layer = O.Layer(w_np.reshape(qshape), scale, zp, weights_dtype=wd, quantized_weight_shape=qshape, result_shape=[N, K] if groups > 1 else None,
+                    group_size=gs, use_hadamard=True, hadamard_group_size=G)
+    ref = O.dequantize(layer, dtype="bfloat16")
+    before = ops()._lib.launch_count(reset=True)
+    W = ops().dequant(w_t.to(DEV), wd, torch.from_numpy(scale).to(DEV), None if zp is None else torch.from_numpy(zp).to(DEV), N, K, gs,
+                      torch.bfloat16, hadamard_group=G)
+    assert ops()._lib.launch_count() == 1
+    du = bf16_ulp_diff(W.cpu(), torch.from_numpy(ref).to(torch.bfloat16)).numpy()
+    err = np.abs(to_f32_np(W) - ref)
+    # f32 summation order differs from a GEMM: one bf16 ulp, except where a group's terms cancel (tiny sums: bound those absolutely)
+    solid = np.abs(ref) > 0.05 * np.abs(ref).max(axis=-1, keepdims=True)
+    assert float(((du > 1) & solid).mean()) < 1e-3 and float((du > 0).mean()) < 0.03
+    assert err.max() <= 2.0 ** -7 * np.abs(ref).max()
 
 
 # ----------------------------------------------------------------------------------------------- SVD dequant on tensor cores

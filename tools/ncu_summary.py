@@ -2,6 +2,8 @@
 
     python tools/ncu_summary.py launches <launches.csv> <out.md>       # per-kernel share of a launch list
     python tools/ncu_summary.py full <report.ncu-rep> <out.md> [title]   # key metrics of one --set full capture
+    python tools/ncu_summary.py traffic <dram.csv> <workload> <regex>    # per-launch DRAM bytes of the kernels matching <regex>
+                                                                         # -> merged into profiles/traffic.json (bench.py reads it)
 """
 import collections
 import csv
@@ -69,8 +71,37 @@ def full(rep, out, title=""):
     print(open(out).read())
 
 
+def traffic(path, workload, pattern):
+    """csv of `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --csv` over one step of bench.py"""
+    import json
+    import os
+    text = open(path, errors="replace").read()
+    rows = list(csv.reader(io.StringIO(text[text.find('"ID"'):])))
+    hdr = rows[0]
+    ci = {h: i for i, h in enumerate(hdr)}
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per_id = collections.defaultdict(float)
+    names = {}
+    for r in rows[1:]:
+        if len(r) < len(hdr) or not r[ci["Metric Name"]].startswith("dram__bytes"):
+            continue
+        per_id[r[ci["ID"]]] += float(r[ci["Metric Value"]].replace(",", "")) * mult.get(r[ci["Metric Unit"]], 1.0)
+        names[r[ci["ID"]]] = r[ci["Kernel Name"]]
+    sel = [v for k, v in per_id.items() if re.search(pattern, names[k])]
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    data = json.load(open(out)) if os.path.exists(out) else {}
+    data[workload] = {"dominant_kernel_dram_bytes_per_launch": sum(sel) / max(len(sel), 1), "launches": len(sel), "kernel_regex": pattern,
+                      "all_kernels_dram_bytes_per_step": sum(per_id.values()),
+                      "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over one graph-replayed step of bench.py --workload {workload} "
+                                f"({os.path.basename(path)}); mean over the {len(sel)} launches matching /{pattern}/"}
+    json.dump(data, open(out, "w"), indent=1, sort_keys=True)
+    print(json.dumps(data[workload], indent=1))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
     else:
         full(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
