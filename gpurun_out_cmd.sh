@@ -1,9 +1,10 @@
 set -x
 mkdir -p gpurun_out
-( timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_layers_gpu.py tests/test_conv_gpu.py -q -m gpu ) > gpurun_out/c9_pytest.log 2>&1
-tail -6 gpurun_out/c9_pytest.log
-timeout 300 python tools/actq_ab.py > gpurun_out/c9_actq.log 2>&1
-grep -E "hadamard=(0|256)" gpurun_out/c9_actq.log | head -20
-timeout 300 python tools/shape_breakdown.py sdxl > gpurun_out/c9_bd_sdxl.log 2>&1
-tail -10 gpurun_out/c9_bd_sdxl.log
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:act_quant -c 1 -s 2 -f -o gpurun_out/c9_actq_had_tc python tools/run_one.py actq 16384 3072 256 fp8 > gpurun_out/c9_ncu.log 2>&1
+( timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "rotated" ) > gpurun_out/c10_pytest.log 2>&1
+tail -3 gpurun_out/c10_pytest.log
+timeout 300 python tools/dequant_bw.py --rot > gpurun_out/c10_dequant_rot.log 2>&1
+cat gpurun_out/c10_dequant_rot.log
+SDNQ_B200_HADAMARD_BUTTERFLY=1 timeout 300 python tools/dequant_bw.py --rot > gpurun_out/c10_dequant_rot_bf.log 2>&1
+cat gpurun_out/c10_dequant_rot_bf.log
+timeout 300 python tools/conv_bench.py > gpurun_out/c10_conv_bench.log 2>&1
+cat gpurun_out/c10_conv_bench.log

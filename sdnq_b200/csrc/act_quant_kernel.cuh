@@ -249,6 +249,128 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC
     }
 }
 
+// Rows longer than the register-resident kernel holds (K > 16384): one CTA per row, two passes over the row (statistics, then
+// quantise; the second read comes from L2).  Same arithmetic, same layout (lane l owns elements [8l, 8l+8) of a 256-chunk, warp w
+// takes chunks w, w+8, ...); the butterfly rotation is applied in both passes when asked for.
+template <typename T, int MODE, bool kConv>
+__global__ void __launch_bounds__(kThreads) act_quant_long_kernel(const ActArgs a) {
+    __shared__ float s_a[kWarps];
+    __shared__ float s_b[kWarps];
+    __shared__ int s_sum[kWarps];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = blockIdx.x;
+    const int K = static_cast<int>(a.K);
+    const T* xrow = reinterpret_cast<const T*>(a.x) + (kConv ? 0 : row * a.ldx);
+    int ih0 = 0, iw0 = 0;
+    if constexpr (kConv) {
+        const int b = static_cast<int>(row / a.conv.HWout);
+        const int rem = static_cast<int>(row - int64_t(b) * a.conv.HWout);
+        const int oh = rem / a.conv.Wout, ow = rem - oh * a.conv.Wout;
+        ih0 = oh * a.conv.sh - a.conv.ph;
+        iw0 = ow * a.conv.sw - a.conv.pw;
+        xrow += int64_t(b) * a.conv.sB;
+    }
+    const int chunks = (K + 255) / 256;
+    auto fetch = [&](int c, float (&v)[8]) {          // the lane's 8 values of chunk c (rotated if asked), zeros past the end
+        const int k = c * 256 + lane * 8;
+        Held<T> h;
+        if (k >= K) h.zero();
+        else if constexpr (kConv) {
+            T g[8];
+            conv_gather<T, 8>(a.conv, xrow, ih0, iw0, k, K, g);
+            if constexpr (sizeof(T) == 2) h.raw = make_uint4(pack16(g[0], g[1]), pack16(g[2], g[3]), pack16(g[4], g[5]), pack16(g[6], g[7]));
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) h.val[i] = g[i];
+            }
+        } else h.load(xrow + k);
+        h.get(v);
+        if (a.hadamard) {
+            hadamard_warp_dyn(a.hadamard, v, a.hfac);
+            h.put(v);                                   // rounds to x.dtype
+            h.get(v);
+        }
+    };
+    float amax = 0.f, vmax = -INFINITY, vmin = INFINITY;
+    for (int c = warp; c < chunks; c += kWarps) {
+        float v[8];
+        fetch(c, v);
+        if (c * 256 + lane * 8 < K) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if constexpr (MODE == SDNQ_U8) { vmax = fmaxf(vmax, v[i]); vmin = fminf(vmin, v[i]); }
+                else amax = fmaxf(amax, fabsf(v[i]));
+            }
+        }
+    }
+    float scale, zero = 0.f;
+    if constexpr (MODE == SDNQ_U8) {
+        vmax = warp_max(vmax);
+        vmin = warp_min(vmin);
+        if (lane == 0) { s_a[warp] = vmax; s_b[warp] = vmin; }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kWarps; ++i) { vmax = fmaxf(vmax, s_a[i]); vmin = fminf(vmin, s_b[i]); }
+        scale = __fdiv_rn(__fsub_rn(vmax, vmin), 255.f);
+        zero = __fsub_rn(vmin, __fmul_rn(scale, -128.f));
+    } else {
+        amax = warp_max(amax);
+        if (lane == 0) s_a[warp] = amax;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kWarps; ++i) amax = fmaxf(amax, s_a[i]);
+        scale = __fdiv_rn(amax, MODE == SDNQ_F8E4M3 ? 448.f : 127.f);
+    }
+    const RowDivider divider(scale);
+    const bool safe = divider.safe();
+    const int d0 = hadamard_dest_dyn(a.hadamard, lane, 0), d1 = hadamard_dest_dyn(a.hadamard, lane, 1);
+    int local_sum = 0;
+    for (int c = warp; c < chunks; c += kWarps) {
+        float v[8];
+        fetch(c, v);
+        if (c * 256 + lane * 8 >= K) continue;
+        const bool want_sum = a.rowsum != nullptr;
+        const uint2 r = safe ? quantise8<MODE, true>(v, divider, zero, want_sum, local_sum) : quantise8<MODE, false>(v, divider, zero, want_sum, local_sum);
+        const int64_t chunk0 = row * a.K + c * 256;
+        *reinterpret_cast<uint32_t*>(a.xq + chunk0 + d0) = r.x;
+        *reinterpret_cast<uint32_t*>(a.xq + chunk0 + d1) = r.y;
+        if (a.x_rot != nullptr) {
+            T* xr = reinterpret_cast<T*>(a.x_rot) + chunk0;
+            store4<T>(xr + d0, v[0], v[1], v[2], v[3]);
+            store4<T>(xr + d1, v[4], v[5], v[6], v[7]);
+        }
+    }
+    if (a.rowsum != nullptr) {
+        local_sum = warp_sum(local_sum);
+        if (lane == 0) s_sum[warp] = local_sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+#pragma unroll
+            for (int i = 0; i < kWarps; ++i) t += s_sum[i];
+            a.rowsum[row] = t;
+        }
+    }
+    if (threadIdx.x == 0) {
+        a.sx[row] = scale;
+        if (a.zx != nullptr) a.zx[row] = zero;
+    }
+}
+
+template <typename T, bool kConv>
+int launch_long(const ActArgs& a, cudaStream_t st) {
+    SDNQ_REQUIRE(a.M < (int64_t(1) << 31), SDNQ_EUNSUPPORTED, "act_quant: too many rows");
+    const unsigned blocks = static_cast<unsigned>(a.M);
+    cudaError_t e;
+    if (a.mode == SDNQ_I8) e = launch_pdl(act_quant_long_kernel<T, SDNQ_I8, kConv>, dim3(blocks), dim3(kThreads), 0, st, a);
+    else if (a.mode == SDNQ_U8) e = launch_pdl(act_quant_long_kernel<T, SDNQ_U8, kConv>, dim3(blocks), dim3(kThreads), 0, st, a);
+    else e = launch_pdl(act_quant_long_kernel<T, SDNQ_F8E4M3, kConv>, dim3(blocks), dim3(kThreads), 0, st, a);
+    if (e != cudaSuccess) return set_error(SDNQ_ECUDA, "launch of act_quant_long_kernel failed: %s", cudaGetErrorString(e));
+    return check_launch("act_quant_long_kernel");
+}
+
 template <typename T, int WPR, int MAXC, bool kTC, bool kConv>
 int launch_mode(const ActArgs& a, cudaStream_t st) {
     constexpr int RPC = kWarps / WPR;
@@ -288,7 +410,7 @@ int dispatch(const ActArgs& a, cudaStream_t st) {
     if (chunks <= 16) return launch<T, 4, 4, kConv>(a, st);
     if (chunks <= 32) return launch<T, 8, 4, kConv>(a, st);
     if (chunks <= 64) return launch<T, 8, 8, kConv>(a, st);
-    return set_error(SDNQ_EUNSUPPORTED, "act_quant: K=%lld exceeds 16384", (long long)a.K);
+    return launch_long<T, kConv>(a, st);          // K > 16384: two-pass kernel
 }
 
 template <bool kConv>

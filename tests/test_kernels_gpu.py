@@ -146,6 +146,32 @@ def test_act_quant_other_activation_dtypes(dtype):
     assert np.array_equal(xq.cpu().numpy(), q) and np.array_equal(sx.cpu().numpy(), s.reshape(-1))
 
 
+@pytest.mark.parametrize("mode,hg", [("int8", 0), ("uint8", 0), ("float8_e4m3fn", 0), ("int8", 256), ("float8_e4m3fn", 128)])
+def test_act_quant_long_rows(mode, hg):
+    """K > 16384 (LLM-sized MLPs, wide conv im2col rows): the two-pass kernel; bit-exact codes / scales / row sums."""
+    torch.manual_seed(11)
+    M, K = 19, 16384 + 2048 + 128
+    x = (torch.randn(M, K) * 2).to(torch.bfloat16)
+    xq, sx, zx, rowsum, x_rot = ops().act_quant(x.to(DEV), mode, hadamard_group=hg, want_rowsum=True, want_x_rot=True)
+    xr = to_f32_np(x_rot)
+    if hg:
+        ref = O.rotate_hadamard(to_f32_np(x), hg, "bfloat16")
+        assert float((bf16_ulp_diff(x_rot.cpu(), torch.from_numpy(ref).to(torch.bfloat16)) > 1).float().mean()) < 2e-3
+    else:
+        assert torch.equal(x_rot.cpu(), x)
+    if mode == "int8":
+        q, s = O.quantize_int_mm(xr)
+        assert np.array_equal(xq.cpu().numpy(), q) and np.array_equal(sx.cpu().numpy(), s.reshape(-1))
+        assert np.array_equal(rowsum.cpu().numpy(), q.astype(np.int32).sum(-1))
+    elif mode == "uint8":
+        q, s, z = O.quantize_uint_mm(xr)
+        assert np.array_equal(xq.cpu().numpy(), q) and np.array_equal(sx.cpu().numpy(), s.reshape(-1)) and np.array_equal(zx.cpu().numpy(), z.reshape(-1))
+    else:
+        q, s = O.quantize_fp_mm(xr)
+        assert np.array_equal(O.from_e4m3fn_bits(xq.view(torch.uint8).cpu().numpy()), np.asarray(q, np.float32))
+        assert np.array_equal(sx.cpu().numpy(), s.reshape(-1))
+
+
 @pytest.mark.parametrize("G", [4, 8, 16, 32, 64, 128, 256])
 def test_hadamard_rotation_matches_oracle(G):
     torch.manual_seed(G)

@@ -15,9 +15,13 @@ DEV = "cuda"
 
 
 def main():
-    cases = [("int4", 128), ("uint4", 128), ("int8", -1), ("int4", 32), ("uint3", 64), ("int5", 128), ("float8_e4m3fn", -1), ("float6_e3m2fn", -1)]
-    for (N, K) in [(10240, 1280), (12288, 3072), (3072, 12288), (1280, 5120)]:
-        for wd, gs in cases:
+    # (weights_dtype, group_size, hadamard group for the un-rotate: 0 = none)
+    cases = [("int4", 128, 0), ("uint4", 128, 0), ("int8", -1, 0), ("int4", 32, 0), ("uint3", 64, 0), ("int5", 128, 0), ("float8_e4m3fn", -1, 0),
+             ("float6_e3m2fn", -1, 0), ("float8_e4m3fn", -1, 256), ("int8", -1, 128)]
+    if "--rot" in sys.argv:
+        cases = [c for c in cases if c[2]]
+    for (N, K) in [(10240, 1280), (12288, 3072), (18432, 3072), (3072, 12288), (1280, 5120)]:
+        for wd, gs, hg in cases:
             bits = 8 if "8" in wd else int("".join(ch for ch in wd.split("_")[0] if ch.isdigit()))
             count = max(4, int(600e6 // (N * K * 2)))
             nbytes = N * K * bits // 8
@@ -34,11 +38,11 @@ def main():
             def run():
                 outs.clear()
                 for w in ws:
-                    outs.append(ops.dequant(w, wd, scale, zp, N, K, gs, torch.bfloat16))
+                    outs.append(ops.dequant(w, wd, scale, zp, N, K, gs, torch.bfloat16, hadamard_group=hg))
 
             ms = graph_time(run) / count
             by = nbytes + scale.numel() * 4 * (2 if zp is not None else 1) + 2 * N * K
-            print(f"dequant {wd:14s} g{gs:4d} {N:6d}x{K:6d}: {ms * 1e3:8.2f} us  {by / ms / 1e6:7.0f} GB/s", flush=True)
+            print(f"dequant {wd:14s} g{gs:4d} had{hg:3d} {N:6d}x{K:6d}: {ms * 1e3:8.2f} us  {by / ms / 1e6:7.0f} GB/s", flush=True)
             del ws, outs
             torch.cuda.empty_cache()
 
