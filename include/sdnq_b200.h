@@ -201,6 +201,18 @@ SDNQ_API int sdnq_b200_linear_w8a8(const void* x, int x_dtype, int64_t ldx, cons
                           void* out, int out_dtype, int64_t M, int64_t N, int64_t K,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- K5 small-M Linear on 8-bit weights ("W8A16 GEMV"):  the rows < 32 branch of every quantized-matmul forward
+ *      (linear_int8.py:102-103, linear_uint8.py:107-108, linear_fp8.py:83-84: dequantise the weight, then F.linear) without
+ *      materialising the dequantised weight:
+ *          out[m,n] = sw[n] * sum_k x[m,k] * q[n,k]  (+ zp[n] * sum_k x[m,k])  + bias[n]
+ *   x     [M,K] bf16 / f16, row stride ldx (for use_hadamard layers: already rotated, e.g. the x_rot output of act_quant)
+ *   wq    physical [N,K] 1-byte codes, w_dtype SDNQ_I8 or SDNQ_F8E4M3 (row-wise scales sw[N], optional zero points zp[N])
+ *   out   [M,N] row-major in x_dtype.   1 <= M <= 32, K % 16 == 0.
+ * The codes are read once (N*K bytes instead of the 3*N*K of dequantise-then-GEMM); accumulation is f32 on the tensor cores. */
+SDNQ_API int sdnq_b200_linear_small_m(const void* x, int x_dtype, int64_t ldx, const void* wq, int w_dtype, const float* sw,
+                             const float* zp, const void* bias, int bias_dtype, void* out,
+                             int64_t M, int64_t N, int64_t K, void* stream);
+
 /* The same Linear as ONE kernel launch: the GEMM kernel row-quantises the activations itself (every CTA takes a share
  * of the rows: bulk copy to shared memory, warp-reduction amax, quantise, codes + scales to the workspace) and its TMA
  * producers pick the quantised strips up through release/acquire strip counters -- linear_int8.py:14-22 + 100-125 /

@@ -95,9 +95,25 @@ def quantized_linear_forward(self, input: torch.Tensor) -> torch.Tensor:
     return _dequant_linear(self, input, skip_quantized_matmul=False)
 
 
+def _small_m_gemv_ok(self, input) -> bool:
+    """K5 applies when the stored weight is itself the row-wise 8-bit matmul operand (int8 / uint8 / float8_e4m3fn, no re-quantise,
+    no packing, no SVD) and the activations are 16-bit.  SDNQ_B200_SMALL_M_GEMV=0 keeps the reference's dequantise + GEMM."""
+    d = self.sdnq_dequantizer
+    return (not d.re_quantize_for_matmul and not d.is_packed and self.svd_up is None and input.dtype in (torch.bfloat16, torch.float16)
+            and input.shape[-1] % 16 == 0 and input.numel() > 0 and os.environ.get("SDNQ_B200_SMALL_M_GEMV", "1") not in ("0", "false", "no"))
+
+
 def _w8a8_forward(self, input: torch.Tensor) -> torch.Tensor:
     d = self.sdnq_dequantizer
     if input.numel() // input.shape[-1] < SMALL_M:
+        if _small_m_gemv_ok(self, input):
+            # rows < 32 (linear_int8.py:102-103): the reference dequantises the whole weight and runs F.linear; K5 reads the codes
+            # once instead.  Rotated layers: x @ (W_rot H)^T = (x H) @ W_rot^T, so rotate the (tiny) activation, not the weight.
+            op = matmul_operand(self)
+            x = input
+            if d.use_hadamard:
+                x = ops.act_quant(input, d.quantized_matmul_dtype, hadamard_group=d.hadamard_group_size, want_x_rot=True)[4].view(input.shape)
+            return ops.linear_small_m(x, op.wq, op.sw, zp=op.zp, bias=self.bias)
         return _dequant_linear(self, input, skip_quantized_matmul=True)
     op = matmul_operand(self)
     mm = d.quantized_matmul_dtype

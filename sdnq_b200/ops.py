@@ -294,6 +294,22 @@ def mm(a: torch.Tensor, b_nk: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def linear_small_m(x: torch.Tensor, wq_nk: torch.Tensor, sw, zp=None, bias=None) -> torch.Tensor:
+    """K5: x [..., K] with fewer than 33 rows times the 1-byte weight codes wq_nk [N,K] (int8 / float8_e4m3fn, row-wise scales)."""
+    _require_cuda(x, wq_nk)
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1 or x2.stride(0) % 8 != 0 or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    M, N = x2.shape[0], wq_nk.shape[0]
+    out = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    wcode = SDNQ_F8E4M3 if wq_nk.dtype == torch.float8_e4m3fn else SDNQ_I8
+    with torch.cuda.device(x.device):
+        check(_lib.load().sdnq_b200_linear_small_m(_ptr(x2), dtype_code(x2.dtype), x2.stride(0), _ptr(wq_nk), wcode, _ptr(sw), _ptr(zp), _ptr(bias),
+                                                   dtype_code(bias.dtype) if bias is not None else SDNQ_F32, _ptr(out), M, N, K, _stream(x)))
+    return out.view(*x.shape[:-1], N)
+
+
 _WORKSPACES: dict = {}
 
 

@@ -150,7 +150,7 @@ def test_act_quant_other_activation_dtypes(dtype):
 def test_act_quant_long_rows(mode, hg):
     """K > 16384 (LLM-sized MLPs, wide conv im2col rows): the two-pass kernel; bit-exact codes / scales / row sums."""
     torch.manual_seed(11)
-    M, K = 19, 16384 + 2048 + 128
+    M, K = 19, 16384 + 2048 + 256
     x = (torch.randn(M, K) * 2).to(torch.bfloat16)
     xq, sx, zx, rowsum, x_rot = ops().act_quant(x.to(DEV), mode, hadamard_group=hg, want_rowsum=True, want_x_rot=True)
     xr = to_f32_np(x_rot)
@@ -321,6 +321,57 @@ def test_cta_pair_gemm_matches_single_cta(M, N, K, kind, monkeypatch):
         acc = O.int_mm(a.cpu().numpy(), b.cpu().numpy().T)
         ref = O.scaled_mm(acc, sx.cpu().numpy().reshape(-1, 1), sw.cpu().numpy().reshape(1, -1), bias.float().cpu().numpy(), out_dtype="bfloat16")
         assert int(bf16_ulp_diff(single.cpu(), torch.from_numpy(ref).to(torch.bfloat16)).max()) <= 1
+
+
+# ----------------------------------------------------------------------------------------------- K5 small-M Linear (W8A16 GEMV)
+@pytest.mark.parametrize("M", [1, 4, 7, 8, 13, 16, 31, 32])
+@pytest.mark.parametrize("N,K", [(64, 64), (130, 208), (1280, 1280), (1000, 2816), (18432, 3072)])
+@pytest.mark.parametrize("kind", ["int8", "fp8", "int8_zp"])
+def test_small_m_linear(M, N, K, kind):
+    """y = s[n] * sum_k x q (+ zp[n] * sum_k x) + bias against the same expression in float64, rounded once to bf16: the codes are
+    exact in bf16, products exact in f32, accumulation f32 -- so at most a bf16 ulp (or a hair of the row magnitude when sums cancel)."""
+    if N * K > 4e6 and M not in (4, 32):
+        pytest.skip("large weight: two row counts are enough")
+    g = torch.Generator().manual_seed(M * 131 + N + K)
+    x = (torch.randn(M, K, generator=g) * 1.5).to(torch.bfloat16)
+    q = torch.randint(-128, 128, (N, K), generator=g, dtype=torch.int8)
+    if kind == "fp8":
+        q = (torch.randn(N, K, generator=g) * 60).clamp(-448, 448).to(torch.float8_e4m3fn)
+    sw = torch.rand(N, generator=g) * 0.01 + 1e-3
+    zp = torch.randn(N, generator=g) * 0.02 if kind == "int8_zp" else None
+    bias = torch.randn(N, generator=g).to(torch.bfloat16)
+    y = ops().linear_small_m(x.to(DEV), q.to(DEV), sw.to(DEV), zp=None if zp is None else zp.to(DEV), bias=bias.to(DEV))
+    assert y.shape == (M, N) and y.dtype == torch.bfloat16
+    xd, qd = x.double(), q.double() if kind != "fp8" else q.float().double()
+    ref = (xd @ qd.T) * sw.double() + bias.double()
+    mag = (xd.abs() @ qd.abs().T) * sw.double() + bias.double().abs()
+    if zp is not None:
+        ref = ref + xd.sum(-1, keepdim=True) * zp.double()
+        mag = mag + xd.abs().sum(-1, keepdim=True) * zp.double().abs()
+    err = (y.cpu().double() - ref).abs()
+    # one rounding to bf16 (2^-9 relative) + f32 accumulation error (~K * 2^-24 of the magnitude sum)
+    bound = ref.abs() * 2.0 ** -8 + mag * (K * 2.0 ** -23 + 2.0 ** -16)
+    assert bool((err <= bound).all()), f"max excess {(err - bound).max()}"
+    # f16 activations share the kernel template
+    if M == 4 and N <= 1280:
+        yh = ops().linear_small_m(x.to(torch.float16).to(DEV), q.to(DEV), sw.to(DEV), zp=None if zp is None else zp.to(DEV), bias=bias.to(torch.float16).to(DEV))
+        refh = (x.to(torch.float16).double() @ qd.T) * sw.double() + bias.to(torch.float16).double()
+        if zp is not None:
+            refh = refh + x.to(torch.float16).double().sum(-1, keepdim=True) * zp.double()
+        assert bool(((yh.cpu().double() - refh).abs() <= refh.abs() * 2.0 ** -10 + mag * (K * 2.0 ** -23 + 2.0 ** -16)).all())
+
+
+def test_small_m_linear_strided_and_errors():
+    x = torch.randn(4, 3, 512, device=DEV, dtype=torch.bfloat16)[:, 1]           # rows 1536 elements apart
+    q = torch.randint(-128, 128, (96, 512), dtype=torch.int8, device=DEV)
+    sw = torch.rand(96, device=DEV) * 0.01
+    y = ops().linear_small_m(x, q, sw)
+    y2 = ops().linear_small_m(x.contiguous(), q, sw)
+    assert torch.equal(y, y2)
+    with pytest.raises(ops()._lib.SDNQKernelError):
+        ops().linear_small_m(torch.randn(40, 512, device=DEV, dtype=torch.bfloat16), q, sw)      # M > 32
+    with pytest.raises(ops()._lib.SDNQKernelError):
+        ops().linear_small_m(torch.randn(4, 512, device=DEV), q, sw)                              # f32 activations
 
 
 # ----------------------------------------------------------------------------------------------- K2 + K1 against the fixtures

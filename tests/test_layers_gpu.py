@@ -157,3 +157,35 @@ def test_full_size_properties(M, N, K, wd):
         assert int(du.max()) <= 1
     else:
         assert np.abs(got - ref).max() <= 2e-2 * scale and np.sqrt(np.mean((got - ref) ** 2)) <= 3e-3 * scale
+
+
+@pytest.mark.parametrize("cfg", [dict(weights_dtype="int8"), dict(weights_dtype="uint8"), dict(weights_dtype="float8_e4m3fn"),
+                                 dict(weights_dtype="float8_e4m3fn", use_hadamard=True, hadamard_group_size=256),
+                                 dict(weights_dtype="int8", use_hadamard=True, hadamard_group_size=128)],
+                         ids=["int8", "uint8", "fp8", "fp8_hadamard256", "int8_hadamard128"])
+@pytest.mark.parametrize("M", [1, 4, 31])
+def test_small_m_forward_gemv_vs_dequant_path(cfg, M, monkeypatch):
+    """rows < 32 of a W8A8 layer: the K5 GEMV (default) against the reference-shaped dequantise + bf16 GEMM path
+    (SDNQ_B200_SMALL_M_GEMV=0), which is itself pinned to the reference by the `small_m` fixture.  Tolerance = the one stated for
+    every path with a 16-bit GEMM in it (the dequant path rounds each weight to bf16, the GEMV does not)."""
+    from sdnq_b200 import SDNQConfig, sdnq_quantize_layer
+    torch.manual_seed(7 + M)
+    lin = torch.nn.Linear(768, 1536, bias=True).to(torch.bfloat16)
+    layer, _ = sdnq_quantize_layer(copy.deepcopy(lin), SDNQConfig(use_quantized_matmul=True, **cfg))
+    layer = layer.to(DEV)
+    x = torch.randn(M, 768, dtype=torch.bfloat16, device=DEV)
+    from sdnq_b200 import _lib
+    _lib.launch_count(reset=True)
+    y = layer(x)
+    n_gemv = _lib.launch_count()
+    monkeypatch.setenv("SDNQ_B200_SMALL_M_GEMV", "0")
+    y_ref = layer(x)
+    monkeypatch.delenv("SDNQ_B200_SMALL_M_GEMV")
+    assert n_gemv == (2 if cfg.get("use_hadamard") else 1)
+    dense = lin.to(DEV)(x)
+    scale = float(y_ref.float().abs().max())
+    err = (y.float() - y_ref.float()).abs()
+    assert float(err.max()) <= 2e-2 * scale and float(err.pow(2).mean().sqrt()) <= 3e-3 * scale
+    # and both are the same distance from the unquantised layer (quantisation error dominates)
+    e1, e2 = (y.float() - dense.float()).pow(2).mean().sqrt(), (y_ref.float() - dense.float()).pow(2).mean().sqrt()
+    assert float(e1) <= 1.1 * float(e2) + 1e-3 * scale
