@@ -260,6 +260,8 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line (the version banner goes to stdout)
         dist.init_process_group("nccl", device_id=device)
     _lib.check(_lib.load().sdnq_b200_check_device(local_rank))
     spec = WORKLOADS[args.workload]
