@@ -649,7 +649,8 @@ extern "C" int sdnq_b200_dequant(const void* weight, const sdnq_weight_format* f
     }
     a.hadamard = hadamard_group;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (svd_up != nullptr && hadamard_group == 0 && !codebook) {
+    const char* svd_env = getenv("SDNQ_B200_SVD_TC");          // "0": keep the CUDA-core SVD update (A/B measurements), read per call
+    if (svd_up != nullptr && hadamard_group == 0 && !codebook && !(svd_env != nullptr && svd_env[0] == '0')) {
         // rank-r correction on the tensor cores when the layout allows it (dequant_svd.cu); 1 = "not covered, use the generic kernel"
         rc = dequant_svd_tc(weight, a.f, scale, zero_point, N, K, a.group32, a.group_shift, a.gpr32, a.row_stride32, svd_up, up_stride_n, up_stride_r,
                             svd_down, down_stride_r, down_stride_k, svd_rank, svd_dtype, out, out_dtype, st);
