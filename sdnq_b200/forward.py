@@ -83,10 +83,52 @@ def matmul_operand(layer) -> _MatmulOperand:
     return op
 
 
-def _dequant_linear(layer, input, skip_quantized_matmul):
+# ---- dequant path: K3 on a side stream -------------------------------------------------------------------------------------
+# The dequantised weight depends on nothing but the (frozen) stored tensors, so K3 of layer i can run while the GEMM of layer i-1
+# is still executing: it is launched on a per-device side stream and the GEMM waits for it with an event.  At SD-XL bs=1 sizes
+# both kernels are latency-bound (~7 us each), so this hides most of K3.  Works eagerly and under CUDA-graph capture (the side
+# stream is forked into the capture once and joined at every GEMM).  Safety: if a layer's stored tensors changed identity or
+# version since its last call (weights just loaded / converted on the main stream), the side stream first waits for the main
+# stream.  SDNQ_B200_DEQUANT_STREAM=0 runs K3 on the caller's stream.
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device):
+    st = _SIDE_STREAMS.get(device.index)
+    if st is None:
+        st = _SIDE_STREAMS[device.index] = torch.cuda.Stream(device=device)
+    return st
+
+
+def _weights_key(layer):
+    ts = (layer.weight, layer.scale, layer.zero_point, layer.svd_up, layer.svd_down)
+    return tuple((t.data_ptr(), t._version) if t is not None else None for t in ts)
+
+
+def _dequant_weight(layer, dtype, skip_quantized_matmul):
     d = layer.sdnq_dequantizer
-    W = d(layer.weight, layer.scale, zero_point=layer.zero_point, svd_up=layer.svd_up, svd_down=layer.svd_down,
-          skip_quantized_matmul=skip_quantized_matmul, dtype=input.dtype if input.dtype in (torch.float16, torch.bfloat16, torch.float32) else None)
+    return d(layer.weight, layer.scale, zero_point=layer.zero_point, svd_up=layer.svd_up, svd_down=layer.svd_down,
+             skip_quantized_matmul=skip_quantized_matmul, dtype=dtype)
+
+
+def _dequant_linear(layer, input, skip_quantized_matmul):
+    dtype = input.dtype if input.dtype in (torch.float16, torch.bfloat16, torch.float32) else None
+    if not input.is_cuda or os.environ.get("SDNQ_B200_DEQUANT_STREAM", "1") in ("0", "false", "no"):
+        return torch.nn.functional.linear(input, _dequant_weight(layer, dtype, skip_quantized_matmul), layer.bias)
+    main = torch.cuda.current_stream(input.device)
+    side = _side_stream(input.device)
+    key = _weights_key(layer)
+    fresh = layer.__dict__.get("_sdnq_dq_key") != key
+    layer.__dict__["_sdnq_dq_key"] = key
+    capturing = torch.cuda.is_current_stream_capturing()
+    with torch.cuda.stream(side):
+        side_capturing = torch.cuda.is_current_stream_capturing()
+    if fresh or (capturing and not side_capturing):
+        side.wait_stream(main)              # weights may have just been written on the main stream / fork the side stream into the capture
+    with torch.cuda.stream(side):
+        W = _dequant_weight(layer, dtype, skip_quantized_matmul)
+    main.wait_stream(side)
+    W.record_stream(main)                   # allocated on the side stream, consumed (and released) on the main one
     return torch.nn.functional.linear(input, W, layer.bias)
 
 
