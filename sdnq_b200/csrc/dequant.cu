@@ -307,7 +307,7 @@ template <int BITS, bool kZP, bool kRow, typename OutT, int U>
 __global__ void __launch_bounds__(kThreads) dequant_flat_kernel(const uint8_t* __restrict__ weight, const float* __restrict__ scale,
                                                                 const float* __restrict__ zp, OutT* __restrict__ out,
                                                                 uint32_t total_octets, int shift, uint32_t opr, uint32_t opr_magic,
-                                                                uint32_t flip, float bias) {
+                                                                uint32_t flip, float bias, int streaming) {
     static_assert(BITS == 4 || BITS == 8, "flat path: one or two storage words per octet");
     pdl_launch_dependents();
     pdl_wait();
@@ -347,6 +347,23 @@ __global__ void __launch_bounds__(kThreads) dequant_flat_kernel(const uint8_t* _
             octet_to_floats<BITS>(raw[u], flip, bias, q);
 #pragma unroll
             for (int i = 0; i < 8; ++i) w[i] = kZP ? fmaf(q[i], sc[u], z[u]) : __fmul_rn(q[i], sc[u]);
+            if constexpr (sizeof(OutT) == 2) {
+                if (streaming) {            // the dequantised weight is consumed once by the GEMM behind us: evict-first stores
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if constexpr (ElemTraits<OutT>::kDtype == SDNQ_BF16) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(w[2 * i], w[2 * i + 1]);
+                            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                        } else {
+                            __half2 h = __floats2half2_rn(w[2 * i], w[2 * i + 1]);
+                            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                    }
+                    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(out + size_t(o) * 8), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                    continue;
+                }
+            }
             store8<OutT>(out + size_t(o) * 8, w);
         }
     }
@@ -570,13 +587,18 @@ static int launch_dequant(const DequantArgs& a, void* out, cudaStream_t st) {
         const uint32_t magic = static_cast<uint32_t>((uint64_t(1) << 32) / opr);          // floor(2^32 / opr): quotient estimate is exact or one low
         const int shift = grouped ? a.group_shift - 3 : 0;
         const int64_t blocks64 = (total_oct + int64_t(kThreads) * U - 1) / (int64_t(kThreads) * U);
-        const int64_t capf = int64_t(num_sms()) * 8;
+        const char* gm = getenv("SDNQ_B200_FLAT_GRID");            // tuning knobs (read per call): CTAs per SM, streaming stores
+        const char* se = getenv("SDNQ_B200_FLAT_STREAMING");
+        // measured on B200 (tools/flat_tune.py, profiles/r01_dequant_flat_tuning.md): 32 CTAs per SM of grid (short grid-stride
+        // loops) reach 5.9-6.2 TB/s where 8 gave 5.1-5.3; evict-first stores add 1-2 % for 4-bit sources and cost 1 % for 8-bit ones
+        const int streaming = se != nullptr ? atoi(se) : (a.f.bits == 4 ? 1 : 0);
+        const int64_t capf = int64_t(num_sms()) * (gm != nullptr && atoi(gm) > 0 ? atoi(gm) : 32);
         const unsigned gridf = static_cast<unsigned>(blocks64 < capf ? blocks64 : capf);
         OutT* o = reinterpret_cast<OutT*>(out);
         const uint32_t tot = static_cast<uint32_t>(total_oct);
 #define SDNQ_FLAT(BITS_, ZP_, ROW_)                                                                                              \
     e = launch_pdl(dequant_flat_kernel<BITS_, ZP_, ROW_, OutT, U>, dim3(gridf), dim3(kThreads), 0, st, a.weight, a.scale, a.zp, o, tot, \
-                   shift, opr, magic, flip, bias)
+                   shift, opr, magic, flip, bias, streaming)
         const bool z = a.zp != nullptr;
         if (a.f.bits == 4) {
             if (rowwise) { if (z) SDNQ_FLAT(4, true, true); else SDNQ_FLAT(4, false, true); }
