@@ -303,7 +303,8 @@ __global__ void __launch_bounds__(kThreads, 6) dequant_int_kernel(const DequantA
 // (16 B per lane, 512 B per warp) is a fully coalesced warp access.  Per octet: 1-2 LDG, 8 x (PRMT, FADD, FMUL | FFMA),
 // 4 pack, 1 STG.128 -- ~4.5 SASS instructions per element, a third of the row-walking kernel, which leaves the
 // kernel bound by HBM alone.  kRow: row-wise scale (group == K): the row of an octet by multiply-high division.
-template <int BITS, bool kZP, bool kRow, typename OutT, int U>
+// kFp8: the bytes are float8_e4m3fn values (cvt.f16x2.e4m3x2, exact) instead of integer codes.
+template <int BITS, bool kZP, bool kRow, typename OutT, int U, bool kFp8 = false>
 __global__ void __launch_bounds__(kThreads) dequant_flat_kernel(const uint8_t* __restrict__ weight, const float* __restrict__ scale,
                                                                 const float* __restrict__ zp, OutT* __restrict__ out,
                                                                 uint32_t total_octets, int shift, uint32_t opr, uint32_t opr_magic,
@@ -344,7 +345,18 @@ __global__ void __launch_bounds__(kThreads) dequant_flat_kernel(const uint8_t* _
             const uint32_t o = base + uint32_t(u * kThreads);
             if (o >= total_octets) continue;
             float q[8], w[8];
-            octet_to_floats<BITS>(raw[u], flip, bias, q);
+            if constexpr (kFp8) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t h;
+                    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h) : "h"(static_cast<unsigned short>((raw[u][i >> 1] >> (16 * (i & 1))) & 0xFFFFu)));
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+                    q[2 * i] = f.x;
+                    q[2 * i + 1] = f.y;
+                }
+            } else {
+                octet_to_floats<BITS>(raw[u], flip, bias, q);
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) w[i] = kZP ? fmaf(q[i], sc[u], z[u]) : __fmul_rn(q[i], sc[u]);
             if constexpr (sizeof(OutT) == 2) {
@@ -558,7 +570,8 @@ static int launch_dequant(const DequantArgs& a, void* out, cudaStream_t st) {
     SDNQ_REQUIRE(total64 < (int64_t(1) << 30), SDNQ_EUNSUPPORTED, "weight too large");
     const int cpr = static_cast<int>(cpr64), total = static_cast<int>(total64);
     const int64_t want = (total64 + int64_t(kWarps) * U - 1) / (int64_t(kWarps) * U);
-    const int64_t cap = int64_t(num_sms()) * 16;
+    const char* dq_grid = getenv("SDNQ_B200_DQ_GRID");             // tuning knob (read per call): CTAs per SM of grid
+    const int64_t cap = int64_t(num_sms()) * (dq_grid != nullptr && atoi(dq_grid) > 0 ? atoi(dq_grid) : 16);
     const unsigned grid = static_cast<unsigned>(want < cap ? (want > 0 ? want : 1) : cap);
     const bool plain = a.up == nullptr && a.hadamard == 0;
     cudaError_t e = cudaSuccess;
@@ -567,7 +580,8 @@ static int launch_dequant(const DequantArgs& a, void* out, cudaStream_t st) {
     const int64_t total_oct = a.N * a.K / 8;
     const bool grouped = a.gpr32 > 1 && a.group_shift >= 3 && a.K32 % a.group32 == 0 && a.row_stride32 == a.gpr32;
     const bool rowwise = a.gpr32 == 1 && a.row_stride32 == 1 && a.group32 >= a.K32;
-    const bool flat = fast_int && (a.f.bits == 4 || a.f.bits == 8) && a.f.word_bytes == 1 && a.K32 % 8 == 0 && total_oct < (int64_t(1) << 31) &&
+    const bool fp8_plain = plain && a.f.kind == SDNQ_W_FP8_E4M3FN && !a.codebook && a.zp == nullptr && ((a.group32 & 7) == 0 || a.group32 >= a.K32);
+    const bool flat = (fast_int || fp8_plain) && (a.f.bits == 4 || a.f.bits == 8) && a.f.word_bytes == 1 && a.K32 % 8 == 0 && total_oct < (int64_t(1) << 31) &&
                       (grouped || rowwise) && (reinterpret_cast<uintptr_t>(a.weight) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     // rotated 8-bit weights without SVD: tensor-core un-rotate
     bool rot8 = false;
@@ -600,7 +614,12 @@ static int launch_dequant(const DequantArgs& a, void* out, cudaStream_t st) {
     e = launch_pdl(dequant_flat_kernel<BITS_, ZP_, ROW_, OutT, U>, dim3(gridf), dim3(kThreads), 0, st, a.weight, a.scale, a.zp, o, tot, \
                    shift, opr, magic, flip, bias, streaming)
         const bool z = a.zp != nullptr;
-        if (a.f.bits == 4) {
+        if (fp8_plain) {
+            if (rowwise) e = launch_pdl(dequant_flat_kernel<8, false, true, OutT, U, true>, dim3(gridf), dim3(kThreads), 0, st, a.weight, a.scale, a.zp, o, tot,
+                                        shift, opr, magic, flip, bias, streaming);
+            else e = launch_pdl(dequant_flat_kernel<8, false, false, OutT, U, true>, dim3(gridf), dim3(kThreads), 0, st, a.weight, a.scale, a.zp, o, tot,
+                                shift, opr, magic, flip, bias, streaming);
+        } else if (a.f.bits == 4) {
             if (rowwise) { if (z) SDNQ_FLAT(4, true, true); else SDNQ_FLAT(4, false, true); }
             else { if (z) SDNQ_FLAT(4, true, false); else SDNQ_FLAT(4, false, false); }
         } else {
