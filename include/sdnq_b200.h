@@ -9,6 +9,12 @@
  * entry point allocates, frees, or synchronises; all of them are asynchronous on
  * `stream` (a `cudaStream_t` passed as `void*`) and CUDA-graph capturable.
  *
+ * Stream ordering: kernels are launched with programmatic dependent launch; every kernel waits (griddepcontrol.wait) before it
+ * reads anything its stream predecessors may have produced -- with one exception: the GEMM entry points prefetch *weight*
+ * tiles (b / wq) before that wait.  Weights are frozen in this path; the library orders its own operand producers
+ * (sdnq_b200_unpack, sdnq_b200_requant) with a trailing fence kernel, and a caller that rewrites a weight buffer must let that
+ * write complete (any ordinary kernel or copy in between suffices) before the next GEMM call on the stream.
+ *
  * Return value: 0 on success, negative `sdnq_status` otherwise; the message of
  * the last failure on the calling thread is returned by `sdnq_b200_last_error()`.
  * There is no CPU fallback anywhere behind this ABI.

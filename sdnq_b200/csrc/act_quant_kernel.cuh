@@ -132,17 +132,18 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC
     for (int c = 0; c < MAXC; ++c) {
         float v[8];
         if constexpr (kTC) {
-            if (c * kStep < wlim) rot.apply(held[c].raw, hfac);       // warp-uniform; rounds to x.dtype: the reference's matmul returns x.dtype
-            held[c].get(v);
-            const bool ok_lo = c * kStep < lim, ok_hi = c * kStep + 128 < lim;
+            float m = 0.f;
+            if (c * kStep < wlim) m = rot.apply(held[c].raw, hfac);    // warp-uniform; rounds to x.dtype: the reference's matmul returns x.dtype
             if constexpr (MODE == SDNQ_U8) {
+                held[c].get(v);
+                const bool ok_lo = c * kStep < lim, ok_hi = c * kStep + 128 < lim;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     if (i < 4 ? ok_lo : ok_hi) { vmax = fmaxf(vmax, v[i]); vmin = fminf(vmin, v[i]); }
                 }
-            } else {     // halves past the end of the row hold zeros: no effect on an absolute maximum
-#pragma unroll
-                for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[i]));
+            } else {     // halves past the end of the row hold zeros (groups never straddle the end): no effect on an absolute maximum;
+                         // the maximum of the unrounded values is rounded once below (monotone rounding commutes with max)
+                amax = fmaxf(amax, m);
             }
             continue;
         }
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC
 #pragma unroll
             for (int i = 0; i < WPR; ++i) amax = fmaxf(amax, s_a[r_in][i]);
         }
+        if constexpr (kTC) amax = ElemTraits<T>::round(amax);            // the rotated values are stored rounded to x.dtype
         scale = __fdiv_rn(amax, MODE == SDNQ_F8E4M3 ? 448.f : 127.f);    // get_scale_symmetric
     }
     const RowDivider divider(scale);

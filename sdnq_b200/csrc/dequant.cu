@@ -385,7 +385,8 @@ __global__ void __launch_bounds__(kThreads) dequant_flat_kernel(const uint8_t* _
 template <int BITS>
 __global__ void __launch_bounds__(kThreads) unpack_kernel(const uint8_t* __restrict__ packed, WFormat f, void* __restrict__ out,
                                                           int out_dtype, int64_t octets) {
-    pdl_launch_dependents();
+    // no early trigger: the codes written here may be the B operand of the GEMM, which prefetches its weights *before* its own
+    // griddepcontrol.wait (weights are assumed complete when a dependent starts); dependents start when this grid has finished
     pdl_wait();
     const int64_t oct = int64_t(blockIdx.x) * kThreads + threadIdx.x;
     if (oct >= octets) return;
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(kThreads) requant_kernel(const DequantArgs a, 
                                                            int32_t* __restrict__ colsum) {
     __shared__ float s_red[kWarps];
     __shared__ int s_sum[kWarps];
-    pdl_launch_dependents();
+    // no early trigger (see unpack_kernel): wq / sw written here are the GEMM's weight operand
     pdl_wait();
     const int64_t n = blockIdx.x;
     float w[kRequantMaxOct][8];
@@ -558,6 +559,13 @@ int fill_args(DequantArgs& a, const void* weight, const sdnq_weight_format* fmt,
     a.rank = 0; a.svd_dtype = SDNQ_BF16; a.hadamard = 0;
     return SDNQ_OK;
 }
+
+// Ordering barrier behind the kernels that *produce a GEMM weight operand* (unpack, re-quantise).  The GEMM prefetches its
+// weight tiles before its griddepcontrol.wait (weights are assumed complete and visible when a programmatic dependent
+// starts), and only a wait / a normally launched kernel gives that guarantee: this empty kernel is launched without the
+// programmatic attribute, so it starts after the producer has completed and flushed, and it never triggers early, so whatever
+// follows starts after it.  Runs once per layer (the operands are cached).
+__global__ void operand_fence_kernel() {}
 
 bool hadamard_ok(int g) { return g == 0 || (g >= 4 && g <= 256 && (g & (g - 1)) == 0); }
 
@@ -668,6 +676,7 @@ extern "C" int sdnq_b200_unpack(const void* packed, const sdnq_weight_format* fm
     const unsigned blocks = static_cast<unsigned>((octets + kThreads - 1) / kThreads);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     SDNQ_DISPATCH_BITS(f.bits, (unpack_kernel<BITS><<<blocks, kThreads, 0, st>>>(reinterpret_cast<const uint8_t*>(packed), f, out, out_dtype, octets)));
+    operand_fence_kernel<<<1, 32, 0, st>>>();
     return check_launch("unpack_kernel");
 }
 
@@ -719,5 +728,6 @@ extern "C" int sdnq_b200_requant(const void* weight, const sdnq_weight_format* f
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     SDNQ_DISPATCH_BITS(a.f.bits, (requant_kernel<BITS><<<static_cast<unsigned>(N), kThreads, 0, st>>>(
                                      a, mm_dtype, reinterpret_cast<uint8_t*>(wq), sw, mm_dtype == SDNQ_U8 ? zw : nullptr, colsum)));
+    operand_fence_kernel<<<1, 32, 0, st>>>();
     return check_launch("requant_kernel");
 }

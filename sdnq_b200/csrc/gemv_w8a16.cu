@@ -13,7 +13,7 @@
 // Rotated layers (use_hadamard): y = x @ (W_rot H)^T = (x H) @ W_rot^T, so the caller passes x already rotated (K2's x_rot).
 //
 // Mapping: the contraction runs on the tensor cores as mma.sync.m16n8k16 with the *weight rows* as the M dimension (16 rows per
-// warp tile) and the activation rows as N (8 per block, up to 4 blocks = 32 rows).  Lane (g, t) streams 16 consecutive codes of
+// CTA tile, K split over the CTA's 8 warps and reduced through shared memory) and the activation rows as N (8 per block, up to 4 blocks = 32 rows).  Lane (g, t) streams 16 consecutive codes of
 // rows g and g+8 per 64-column step (two 16-byte loads, 4 steps in flight), converts them to the activation dtype in registers
 // (exact) and feeds 4 MMAs; the k-slots of the fragments are permuted so that these 16 codes are exactly what the lane needs, and
 // the matching 16 activations of row m = g come from one 32-byte read of x (L1-resident: x is M*K*2 bytes).  HBM-bound on the
@@ -98,6 +98,7 @@ __device__ __forceinline__ void codes4(uint32_t w, uint32_t& p01, uint32_t& p23)
 template <typename T, bool kFp8, int MB>
 __global__ void __launch_bounds__(kThreads) gemv_w8a16_kernel(const GemvArgs a) {
     __shared__ float s_xsum[32];
+    __shared__ float s_red[kWarps - 1][MB * 4][32];          // partial accumulators of warps 1..7 (the K split of a tile)
     pdl_launch_dependents();
     pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -116,7 +117,9 @@ __global__ void __launch_bounds__(kThreads) gemv_w8a16_kernel(const GemvArgs a) 
     const int tiles = (a.N + 15) / 16;
     const int steps = a.K / 64;                              // whole 64-column steps; the tail (K % 64, a multiple of 16) is handled below
     const int tail16 = (a.K - steps * 64) / 16;
-    for (int tile = blockIdx.x * kWarps + warp; tile < tiles; tile += gridDim.x * kWarps) {
+    // One CTA per 16-row tile; its 8 warps split K (warp w takes the 64-column steps w, w+8, ...) and warp 0 adds the partial
+    // accumulators up: every SM holds several CTAs, so >= 100 KB of codes are in flight per SM even when N is small.
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int n_lo = tile * 16 + g, n_hi = n_lo + 8;
         const bool lo_ok = n_lo < a.N, hi_ok = n_hi < a.N;
         const uint8_t* w_lo = a.wq + int64_t(lo_ok ? n_lo : 0) * a.K + 16 * t;
@@ -153,20 +156,20 @@ __global__ void __launch_bounds__(kThreads) gemv_w8a16_kernel(const GemvArgs a) 
                 Act<T>::mma(acc[b], af[3], x1.z, x1.w);
             }
         };
-        constexpr int U = 4;                                 // steps in flight
-        int s = 0;
-        for (; s + U <= steps; s += U) {
+        constexpr int U = 4;                                 // steps in flight per warp
+        int s = warp;
+        for (; s + (U - 1) * kWarps < steps; s += U * kWarps) {
             uint4 cl[U], ch[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                cl[u] = *reinterpret_cast<const uint4*>(w_lo + (s + u) * 64);
-                ch[u] = *reinterpret_cast<const uint4*>(w_hi + (s + u) * 64);
+                cl[u] = *reinterpret_cast<const uint4*>(w_lo + (s + u * kWarps) * 64);
+                ch[u] = *reinterpret_cast<const uint4*>(w_hi + (s + u * kWarps) * 64);
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) step(cl[u], ch[u], (s + u) * 64);
+            for (int u = 0; u < U; ++u) step(cl[u], ch[u], (s + u * kWarps) * 64);
         }
-        for (; s < steps; ++s) step(*reinterpret_cast<const uint4*>(w_lo + s * 64), *reinterpret_cast<const uint4*>(w_hi + s * 64), s * 64);
-        if (tail16 > 0) {                                    // K % 64 in {16, 32, 48}: lanes with t < tail16 hold real columns
+        for (; s < steps; s += kWarps) step(*reinterpret_cast<const uint4*>(w_lo + s * 64), *reinterpret_cast<const uint4*>(w_hi + s * 64), s * 64);
+        if (tail16 > 0 && warp == kWarps - 1) {                                    // K % 64 in {16, 32, 48}: lanes with t < tail16 hold real columns
             uint4 cl = make_uint4(0u, 0u, 0u, 0u), ch = cl;
             const bool live = t < tail16;
             if (live) {
@@ -193,6 +196,24 @@ __global__ void __launch_bounds__(kThreads) gemv_w8a16_kernel(const GemvArgs a) 
                 Act<T>::mma(acc[b], af[3], x1.z, x1.w);
             }
         }
+        // ---- add the K-split partials up in warp 0
+        if (warp > 0) {
+#pragma unroll
+            for (int b = 0; b < MB; ++b)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s_red[warp - 1][b * 4 + i][lane] = acc[b][i];
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int w = 0; w < kWarps - 1; ++w)
+#pragma unroll
+                for (int b = 0; b < MB; ++b)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[b][i] += s_red[w][b * 4 + i][lane];
+        }
+        __syncthreads();                                     // s_red is reused by the next tile
+        if (warp != 0) continue;
         // ---- epilogue: C fragment = (weight row g | g+8) x (activation rows 2t, 2t+1 of block b)
         const float s_lo = lo_ok ? a.sw[n_lo] : 0.f, s_hi = hi_ok ? a.sw[n_hi] : 0.f;
         const float z_lo = (a.zp != nullptr && lo_ok) ? a.zp[n_lo] : 0.f, z_hi = (a.zp != nullptr && hi_ok) ? a.zp[n_hi] : 0.f;
@@ -220,9 +241,8 @@ __global__ void __launch_bounds__(kThreads) gemv_w8a16_kernel(const GemvArgs a) 
 template <typename T, bool kFp8>
 int launch_mb(const GemvArgs& a, cudaStream_t st) {
     const int tiles = (a.N + 15) / 16;
-    const int want = (tiles + kWarps - 1) / kWarps;
-    const int cap = num_sms() * 4;
-    const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
+    const int cap = num_sms() * 8;
+    const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
     cudaError_t e;
     const int mb = (a.M + 7) / 8;
     if (mb <= 1) e = launch_pdl(gemv_w8a16_kernel<T, kFp8, 1>, dim3(grid), dim3(kThreads), 0, st, a);

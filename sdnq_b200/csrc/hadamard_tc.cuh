@@ -136,7 +136,9 @@ struct Rotation {
 
     // raw: x = elements (4l, 4l+1), y = (4l+2, 4l+3), z = (128+4l, +1), w = (128+4l+2, +3) of the chunk, as 16-bit pairs.
     // On return the same places hold the rotated chunk times `factor`, rounded to T.  All 32 lanes must call this.
-    __device__ __forceinline__ void apply(uint4& raw, float factor) const {
+    // Returns max |rotated value| over the lane's 8 outputs *before* the rounding to T: rounding is monotone and symmetric, so
+    // round(max |y|) == max |round(y)| and the caller can round the row maximum once instead of re-reading the packed values.
+    __device__ __forceinline__ float apply(uint4& raw, float factor) const {
         float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
         Half16<T>::mma(t0, raw.x, raw.z, raw.y, raw.w, b1[0], b1[1]);      // columns 4t', 4t'+1     of rows g, g+8
         Half16<T>::mma(t1, raw.x, raw.z, raw.y, raw.w, b1[2], b1[3]);      // columns 4t'+2, 4t'+3
@@ -155,6 +157,8 @@ struct Rotation {
         raw.y = Half16<T>::pack(t1[0], t1[1]);
         raw.z = Half16<T>::pack(t0[2], t0[3]);
         raw.w = Half16<T>::pack(t1[2], t1[3]);
+        return fmaxf(fmaxf(fmaxf(fabsf(t0[0]), fabsf(t0[1])), fmaxf(fabsf(t0[2]), fabsf(t0[3]))),
+                     fmaxf(fmaxf(fabsf(t1[0]), fabsf(t1[1])), fmaxf(fabsf(t1[2]), fabsf(t1[3]))));
     }
 
     // y += L^T . t for one n-block: t = C fragment (rows g / g+8) -> bf16 pieces (hi, lo[, lo2]: 8 bits each) ->
