@@ -159,6 +159,20 @@ typedef struct sdnq_conv2d_geometry {
 SDNQ_API int sdnq_b200_conv_act_quant(const void* x, int x_dtype, const sdnq_conv2d_geometry* geometry, int hadamard_group,
                              int mm_dtype, void* xq, float* sx, float* zx, int32_t* rowsum, void* x_rot, void* stream);
 
+/* The same, with a caller-owned workspace: 1x1 and 3x3 kernels without rotation / x_rot then take the tiled path (a coalesced
+ * per-pixel statistics pass into the workspace + a shared-memory tiled quantiser: bit-identical results, ~10x the throughput of
+ * the gather kernel); every other case falls through to sdnq_b200_conv_act_quant.  workspace: at least
+ * sdnq_b200_conv_act_quant_workspace_bytes() bytes, 8-byte aligned; contents are scratch. */
+SDNQ_API size_t sdnq_b200_conv_act_quant_workspace_bytes(const sdnq_conv2d_geometry* geometry, int mm_dtype);
+SDNQ_API int sdnq_b200_conv_act_quant_ws(const void* x, int x_dtype, const sdnq_conv2d_geometry* geometry, int hadamard_group,
+                                int mm_dtype, void* xq, float* sx, float* zx, int32_t* rowsum, void* x_rot,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- conv output layout:  `.view(B, H_out, W_out, N).permute(0, 3, 1, 2).contiguous()` of conv_int8_matmul
+ *      (layers/conv/conv_int8.py:83-89).  in [batch*hw, channels] row-major (the GEMM output) -> out [batch, channels, hw];
+ *      elem_bytes 2 (bf16 / f16) or 4 (f32). */
+SDNQ_API int sdnq_b200_rows_to_nchw(const void* in, void* out, int elem_bytes, int64_t batch, int64_t hw, int64_t channels, void* stream);
+
 /* ---- K1 scaled matmul:  int_scaled_mm_func / fp8_scaled_mm_func (kernel_wrappers.py:193-204) ->
  *      sdnq_scaled_mm (kernels/triton_scaled_mm.py:239-275)
  * out[M,N] = cast( fma( f32(A @ B) * sx[m], sw[n], bias ) )        (no bias: (acc*sx)*sw)

@@ -276,9 +276,8 @@ def _w8a8_conv_forward(self, input: torch.Tensor) -> torch.Tensor:
     else:
         out = ops.scaled_mm(xq, op.wq, sx, op.sw, bias, input.dtype, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx)
     N = out.shape[-1]
-    if nd == 1:
-        return out.view(B, Wo, N).transpose(1, 2).contiguous()
-    return out.view(B, Ho, Wo, N).permute(0, 3, 1, 2).contiguous()
+    y = ops.rows_to_nchw(out, B, Ho * Wo)                                         # [B*L, N] -> [B, N, L] (conv_int8.py:83-89)
+    return y.view(B, N, Wo) if nd == 1 else y.view(B, N, Ho, Wo)
 
 
 @torch.no_grad()

@@ -235,10 +235,27 @@ def conv_act_quant(x: torch.Tensor, kernel_size, stride, padding, dilation, matm
     rowsum = torch.empty((M,), dtype=torch.int32, device=dev) if want_rowsum else None
     x_rot = torch.empty((M, K), dtype=x.dtype, device=dev) if want_x_rot else None
     geo = _lib.Conv2dGeometry(B, C, H, W, *x.stride(), kh, kw, sh, sw, ph, pw, dh, dw)
+    lib = _lib.load()
+    # scratch for the tiled path (per-input-pixel channel statistics); the library falls back to the gather kernel where the
+    # tiled one does not apply (other kernel sizes, rotation, x_rot)
+    ws = torch.empty(max(int(lib.sdnq_b200_conv_act_quant_workspace_bytes(geo, code)), 8), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        check(_lib.load().sdnq_b200_conv_act_quant(_ptr(x), dtype_code(x.dtype), geo, int(hadamard_group), code, _ptr(xq), _ptr(sx), _ptr(zx),
-                                                   _ptr(rowsum), _ptr(x_rot), _stream(x)))
+        check(lib.sdnq_b200_conv_act_quant_ws(_ptr(x), dtype_code(x.dtype), geo, int(hadamard_group), code, _ptr(xq), _ptr(sx), _ptr(zx),
+                                              _ptr(rowsum), _ptr(x_rot), _ptr(ws), ws.numel(), _stream(x)))
     return xq, sx, zx, rowsum, x_rot, (B, Hout, Wout)
+
+
+def rows_to_nchw(y: torch.Tensor, batch: int, hw: int) -> torch.Tensor:
+    """[batch*hw, N] GEMM output -> contiguous [batch, N, hw] (the permute(0, 3, 1, 2).contiguous() of the conv forwards)."""
+    _require_cuda(y)
+    y = y.contiguous()
+    N = y.shape[-1]
+    out = torch.empty((batch, N, hw), dtype=y.dtype, device=y.device)
+    if y.element_size() not in (2, 4):
+        raise _lib.SDNQKernelError(f"rows_to_nchw: unsupported dtype {y.dtype}")
+    with torch.cuda.device(y.device):
+        check(_lib.load().sdnq_b200_rows_to_nchw(_ptr(y), _ptr(out), y.element_size(), batch, hw, N, _stream(y)))
+    return out
 
 
 def scaled_mm(a: torch.Tensor, b_nk: torch.Tensor, sx: torch.Tensor, sw: torch.Tensor, bias: torch.Tensor | None = None,

@@ -31,7 +31,7 @@ def graph_time(fn, reps=10):
 
 
 for (B, C, H, W, N, k, s, p) in [(1, 320, 128, 128, 320, 3, 1, 1), (1, 640, 64, 64, 640, 3, 1, 1), (1, 1280, 32, 32, 1280, 3, 1, 1),
-                                 (1, 320, 128, 128, 320, 3, 2, 1), (1, 1920, 32, 32, 1280, 3, 1, 1), (1, 960, 64, 64, 640, 1, 1, 0)]:
+                                 (1, 320, 128, 128, 320, 3, 2, 1), (1, 1920, 32, 32, 1280, 3, 1, 1), (1, 960, 64, 64, 640, 1, 1, 0), (2, 640, 64, 64, 640, 3, 1, 1)]:
     torch.manual_seed(0)
     conv = torch.nn.Conv2d(C, N, k, stride=s, padding=p).to(DEV, torch.bfloat16)
     x = torch.randn(B, C, H, W, device=DEV, dtype=torch.bfloat16)
@@ -43,7 +43,7 @@ for (B, C, H, W, N, k, s, p) in [(1, 320, 128, 128, 320, 3, 1, 1), (1, 640, 64, 
     M, K = xq.shape
     t_k2 = graph_time(lambda: ops.conv_act_quant(x, (k, k), (s, s), (p, p), (1, 1), "int8"))
     t_k1 = graph_time(lambda: ops.scaled_mm(xq, op.wq, sx, op.sw, layer.bias, torch.bfloat16))
-    t_perm = graph_time(lambda: out.view(b_, ho, wo, N).permute(0, 3, 1, 2).contiguous())
+    t_perm = graph_time(lambda: ops.rows_to_nchw(out, b_, ho * wo))
     t_all = graph_time(lambda: layer(x))
     t_lib = graph_time(lambda: conv(x))
     t_unf = graph_time(lambda: ops.act_quant(torch.nn.functional.unfold(x, kernel_size=k, padding=p, stride=s).transpose(1, 2).reshape(M, K).contiguous(), "int8"))
