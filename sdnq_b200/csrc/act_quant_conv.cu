@@ -98,10 +98,10 @@ __global__ void __launch_bounds__(256) conv_pixel_stats_kernel(const ConvTileArg
 }
 
 template <typename T, int MODE, int KH, int KW>
-__global__ void __launch_bounds__(256) conv_quant_tile_kernel(const ConvTileArgs a) {
+__global__ void __launch_bounds__(256, 3) conv_quant_tile_kernel(const ConvTileArgs a) {
     constexpr int TAPS = KH * KW;
     constexpr int kPitch = kChunkCh * TAPS / 4 + 1;                  // words per tile row (odd)
-    __shared__ uint32_t s_tile[kTilePixels * kPitch];
+    __shared__ uint32_t s_tiles[2][kTilePixels * kPitch];            // double-buffered: one barrier per chunk
     __shared__ int s_sum[8][kTilePixels];
     pdl_launch_dependents();
     pdl_wait();
@@ -171,7 +171,9 @@ __global__ void __launch_bounds__(256) conv_quant_tile_kernel(const ConvTileArgs
     const bool want_sum = a.rowsum != nullptr;
     uint8_t* const out_row0 = a.xq + int64_t(blockIdx.x) * kTilePixels * a.K;
     // blockIdx.y splits the channel chunks of a tile over several CTAs when there are too few tiles to fill the machine
-    for (int c0 = int(blockIdx.y) * kChunkCh; c0 < cv.C; c0 += int(gridDim.y) * kChunkCh) {
+    int buf = 0;
+    for (int c0 = int(blockIdx.y) * kChunkCh; c0 < cv.C; c0 += int(gridDim.y) * kChunkCh, buf ^= 1) {
+        uint32_t* const s_tile = s_tiles[buf];
         const int cw = c0 + 4 * warp;                                  // this warp's four channels
         if (cw < cv.C) {                                               // C % 4 == 0 (host-checked)
             uint8_t codes[4 * TAPS];
@@ -211,7 +213,8 @@ __global__ void __launch_bounds__(256) conv_quant_tile_kernel(const ConvTileArgs
             const int p = e / row_words, col = e - p * row_words;
             *reinterpret_cast<uint32_t*>(out_row0 + int64_t(p) * a.K + c0 * TAPS + 4 * col) = s_tile[p * kPitch + col];
         }
-        __syncthreads();
+        // no second barrier: the next chunk fills the other buffer, and this one is refilled only after the next chunk's barrier,
+        // which every thread reaches after finishing the stores above
     }
     if (want_sum) {
         s_sum[warp][lane] = local_sum;
@@ -234,7 +237,8 @@ int launch_tiled(const ConvTileArgs& a, int mode, int64_t in_pixels, cudaStream_
     unsigned ss = 1, ts = 1;
     if (mode != SDNQ_U8 && int(gs) < target) ss = static_cast<unsigned>(std::min<int>(std::max(1, a.cv.C / 32), (target + int(gs) - 1) / int(gs)));
     const int chunks = (a.cv.C + kChunkCh - 1) / kChunkCh;
-    if (int(gt) < target) ts = static_cast<unsigned>(std::min<int>(chunks, (target + int(gt) - 1) / int(gt)));
+    // ... and about four CTAs per resident slot, so that the last wave of tiles does not leave most of the machine idle
+    if (int(gt) < 4 * target) ts = static_cast<unsigned>(std::min<int>(chunks, (4 * target + int(gt) - 1) / int(gt)));
     if (ss > 1) SDNQ_CUDA_OK(cudaMemsetAsync(a.stats, 0, sizeof(float) * in_pixels, st));
     if (ts > 1 && a.rowsum != nullptr) SDNQ_CUDA_OK(cudaMemsetAsync(a.rowsum, 0, sizeof(int32_t) * a.M, st));
     cudaError_t e = mode == SDNQ_U8 ? launch_pdl(conv_pixel_stats_kernel<T, true>, dim3(gs, 1), dim3(256), 0, st, a, in_pixels)
