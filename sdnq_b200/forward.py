@@ -111,10 +111,11 @@ def _dequant_weight(layer, dtype, skip_quantized_matmul):
              skip_quantized_matmul=skip_quantized_matmul, dtype=dtype)
 
 
-def _dequant_linear(layer, input, skip_quantized_matmul):
+def _dequant_weight_overlapped(layer, input, skip_quantized_matmul):
+    """The dequantised weight of `layer`, produced on the side stream and made visible to the caller's stream."""
     dtype = input.dtype if input.dtype in (torch.float16, torch.bfloat16, torch.float32) else None
     if not input.is_cuda or os.environ.get("SDNQ_B200_DEQUANT_STREAM", "1") in ("0", "false", "no"):
-        return torch.nn.functional.linear(input, _dequant_weight(layer, dtype, skip_quantized_matmul), layer.bias)
+        return _dequant_weight(layer, dtype, skip_quantized_matmul)
     main = torch.cuda.current_stream(input.device)
     side = _side_stream(input.device)
     key = _weights_key(layer)
@@ -129,7 +130,11 @@ def _dequant_linear(layer, input, skip_quantized_matmul):
         W = _dequant_weight(layer, dtype, skip_quantized_matmul)
     main.wait_stream(side)
     W.record_stream(main)                   # allocated on the side stream, consumed (and released) on the main one
-    return torch.nn.functional.linear(input, W, layer.bias)
+    return W
+
+
+def _dequant_linear(layer, input, skip_quantized_matmul):
+    return torch.nn.functional.linear(input, _dequant_weight_overlapped(layer, input, skip_quantized_matmul), layer.bias)
 
 
 @torch.no_grad()
@@ -208,7 +213,9 @@ quantized_embedding_forward = _unsupported("quantized_embedding_forward", "quant
 
 
 # ------------------------------------------------------------------------------------------------ convolutions
-def _conv_dense_weight(self, skip_quantized_matmul):
+def _conv_dense_weight(self, skip_quantized_matmul, input=None):
+    if input is not None and input.dtype == self.sdnq_dequantizer.result_dtype:
+        return _dequant_weight_overlapped(self, input, skip_quantized_matmul)      # K3c on the side stream, like the Linear dequant path
     d = self.sdnq_dequantizer
     return d(self.weight, self.scale, zero_point=self.zero_point, svd_up=self.svd_up, svd_down=self.svd_down,
              skip_quantized_matmul=skip_quantized_matmul)
@@ -217,14 +224,14 @@ def _conv_dense_weight(self, skip_quantized_matmul):
 @torch.no_grad()
 def quantized_conv_forward(self, input: torch.Tensor) -> torch.Tensor:
     """K3 (broadcast dequant of the conv weight) -> the library convolution (reference layers/conv/forward.py:79-81)."""
-    return self._conv_forward(input, _conv_dense_weight(self, False), self.bias)
+    return self._conv_forward(input, _conv_dense_weight(self, False, input), self.bias)
 
 
 def _conv_transpose_forward(nd, fn):
     @torch.no_grad()
     def forward(self, input: torch.Tensor, output_size=None) -> torch.Tensor:
         output_padding = self._output_padding(input, output_size, self.stride, self.padding, self.kernel_size, nd, self.dilation)
-        return fn(input, _conv_dense_weight(self, False), self.bias, self.stride, self.padding, output_padding, self.groups, self.dilation)
+        return fn(input, _conv_dense_weight(self, False, input), self.bias, self.stride, self.padding, output_padding, self.groups, self.dilation)
     forward.__name__ = f"quantized_conv_transpose_{nd}d_forward"
     return forward
 
@@ -246,7 +253,7 @@ def _w8a8_conv_forward(self, input: torch.Tensor) -> torch.Tensor:
     [B, H_out, W_out, N] result is returned in the reference's NCHW-contiguous form."""
     d = self.sdnq_dequantizer
     if input.numel() / input.shape[2] < SMALL_M:                                  # conv_int8.py:95-96
-        return self._conv_forward(input, _conv_dense_weight(self, True), self.bias)
+        return self._conv_forward(input, _conv_dense_weight(self, True, input), self.bias)
     if self.groups != 1:
         raise NotImplementedError("sdnq_b200: grouped convolutions have no W8A8 kernel yet (set use_quantized_matmul_conv=False for them)")
     if self.padding_mode != "zeros":
