@@ -97,6 +97,54 @@ __global__ void __launch_bounds__(256) conv_pixel_stats_kernel(const ConvTileArg
     else atomicMax(reinterpret_cast<unsigned int*>(a.stats) + p, __float_as_uint(amax));
 }
 
+// Four consecutive channels x TAPS window elements of one output pixel -> TAPS packed words (column order (c, i, j)) in the
+// shared-memory tile; returns the sum of the integer codes.
+template <typename T, int MODE, int TAPS, bool kSafe>
+__device__ __forceinline__ int quantise_channels(const T* __restrict__ xc, int64_t sC, const int (&toff)[TAPS], uint32_t tmask,
+                                                 const actq::RowDivider& divider, float zero, bool want_sum, uint32_t* __restrict__ dst) {
+    float v[4 * TAPS];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int tp = 0; tp < TAPS; ++tp) v[q * TAPS + tp] = (tmask >> tp) & 1u ? ElemTraits<T>::load(xc[q * sC + toff[tp]]) : 0.f;
+    }
+    int sum = 0;
+#pragma unroll
+    for (int wd = 0; wd < TAPS; ++wd) {                       // word wd = columns 4wd .. 4wd+3 of the four-channel run
+        float qv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float x0 = v[4 * wd + i];
+            if constexpr (MODE == SDNQ_U8) x0 = __fsub_rn(x0, zero);
+            qv[i] = divider.template div<kSafe>(x0);
+        }
+        if constexpr (MODE == SDNQ_F8E4M3) {
+            if constexpr (!kSafe) {                           // nan_to_num (0/0 on an all-zero row)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (qv[i] != qv[i]) qv[i] = 0.f;
+            }
+            // cvt.rn.satfinite.e4m3x2 saturates to +-448 = the reference's clamp before the cast
+            const uint32_t lo = static_cast<uint16_t>(__nv_cvt_float2_to_fp8x2(make_float2(qv[0], qv[1]), __NV_SATFINITE, __NV_E4M3));
+            const uint32_t hi = static_cast<uint16_t>(__nv_cvt_float2_to_fp8x2(make_float2(qv[2], qv[3]), __NV_SATFINITE, __NV_E4M3));
+            dst[wd] = lo | (hi << 16);
+        } else {
+            int c[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[i] = __float2int_rn(qv[i]);      // round-half-even; NaN -> 0
+            uint32_t w;
+            // cvt.pack.sat.s8.s32.b32 d, a, b, c :  d = (c << 16) | (sat8(a) << 8) | sat8(b)
+            asm("{\n\t.reg .b32 t;\n\tcvt.pack.sat.s8.s32.b32 t, %4, %3, 0;\n\tcvt.pack.sat.s8.s32.b32 %0, %2, %1, t;\n\t}"
+                : "=r"(w) : "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
+            dst[wd] = w;
+            if (want_sum) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sum += max(-128, min(127, c[i]));
+            }
+        }
+    }
+    return sum;
+}
+
 template <typename T, int MODE, int KH, int KW>
 __global__ void __launch_bounds__(256, 3) conv_quant_tile_kernel(const ConvTileArgs a) {
     constexpr int TAPS = KH * KW;
@@ -176,32 +224,11 @@ __global__ void __launch_bounds__(256, 3) conv_quant_tile_kernel(const ConvTileA
         uint32_t* const s_tile = s_tiles[buf];
         const int cw = c0 + 4 * warp;                                  // this warp's four channels
         if (cw < cv.C) {                                               // C % 4 == 0 (host-checked)
-            uint8_t codes[4 * TAPS];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const T* xc = xim + int64_t(cw + q) * cv.sC;
-                float v[TAPS];
-#pragma unroll
-                for (int tp = 0; tp < TAPS; ++tp) v[tp] = (tmask >> tp) & 1u ? ElemTraits<T>::load(xc[toff[tp]]) : 0.f;
-#pragma unroll
-                for (int tp = 0; tp < TAPS; ++tp) {
-                    float x0 = v[tp];
-                    if constexpr (MODE == SDNQ_U8) x0 = __fsub_rn(x0, zero);
-                    const float qv = safe ? divider.template div<true>(x0) : divider.template div<false>(x0);
-                    if constexpr (MODE == SDNQ_F8E4M3) {
-                        const float qq = (qv != qv) ? 0.f : qv;                                   // nan_to_num (0/0 on an all-zero row)
-                        codes[q * TAPS + tp] = f32_to_e4m3(fminf(fmaxf(qq, -448.f), 448.f));
-                    } else {
-                        const int ci = max(-128, min(127, __float2int_rn(qv)));
-                        codes[q * TAPS + tp] = static_cast<uint8_t>(static_cast<int8_t>(ci));
-                        if (want_sum) local_sum += ci;
-                    }
-                }
-            }
             uint32_t* dst = s_tile + lane * kPitch + warp * TAPS;
-#pragma unroll
-            for (int wd = 0; wd < TAPS; ++wd)
-                dst[wd] = uint32_t(codes[4 * wd]) | (uint32_t(codes[4 * wd + 1]) << 8) | (uint32_t(codes[4 * wd + 2]) << 16) | (uint32_t(codes[4 * wd + 3]) << 24);
+            const T* xc = xim + int64_t(cw) * cv.sC;
+            // one uniform branch per chunk (not per element) on the division path, as in quantise8
+            if (safe) local_sum += quantise_channels<T, MODE, TAPS, true>(xc, cv.sC, toff, tmask, divider, zero, want_sum, dst);
+            else local_sum += quantise_channels<T, MODE, TAPS, false>(xc, cv.sC, toff, tmask, divider, zero, want_sum, dst);
         }
         __syncthreads();
         // ---- write the tile out: row p holds (chunk channels) * TAPS bytes, contiguous in xq at column c0 * TAPS
@@ -209,9 +236,9 @@ __global__ void __launch_bounds__(256, 3) conv_quant_tile_kernel(const ConvTileA
         const int row_words = chunk_ch * TAPS / 4;
         const int64_t rows_left = a.M - int64_t(blockIdx.x) * kTilePixels;
         const int rows = rows_left < kTilePixels ? static_cast<int>(rows_left) : kTilePixels;
-        for (int e = threadIdx.x; e < rows * row_words; e += 256) {
-            const int p = e / row_words, col = e - p * row_words;
-            *reinterpret_cast<uint32_t*>(out_row0 + int64_t(p) * a.K + c0 * TAPS + 4 * col) = s_tile[p * kPitch + col];
+        for (int p = warp; p < rows; p += 8) {                         // a warp writes whole row segments: no index division
+            uint8_t* orow = out_row0 + int64_t(p) * a.K + c0 * TAPS;
+            for (int col = lane; col < row_words; col += 32) *reinterpret_cast<uint32_t*>(orow + 4 * col) = s_tile[p * kPitch + col];
         }
         // no second barrier: the next chunk fills the other buffer, and this one is refilled only after the next chunk's barrier,
         // which every thread reaches after finishing the stores above

@@ -55,7 +55,8 @@ def launches(path, out):
 
 
 def full(rep, out, title=""):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .csv argument is the output of `ncu -i X.ncu-rep --page raw --csv` made on the GPU box (reports can exceed the transfer limit)
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     with open(out, "w") as f:

@@ -1,4 +1,5 @@
-"""Run one kernel a few times (for ncu captures).  usage: python tools/run_one.py gemm M N K [int8|fp8] | actq M K | dequant N K wdtype gs"""
+"""Run one kernel a few times (for ncu captures).  usage: python tools/run_one.py gemm M N K [int8|fp8] | actq M K [G mode] | dequant N K wdtype gs |
+   dequant_svd N K | gemv M N K [fp8] | conv C H W N k"""
 import os
 import sys
 
@@ -45,4 +46,18 @@ if kind == "dequant_svd":
     down = (torch.randn(K, 32, device=dev, dtype=torch.bfloat16) * 0.1).t()
     for _ in range(4):
         ops.dequant(w, "int4", scale, None, N, K, 128, torch.bfloat16, svd_up=up, svd_down=down)
+if kind == "gemv":
+    M, N, K = map(int, sys.argv[2:5])
+    q = torch.randint(-128, 128, (N, K), dtype=torch.int8, device=dev)
+    if len(sys.argv) > 5 and sys.argv[5] == "fp8":
+        q = (q.float() / 4).to(torch.float8_e4m3fn)
+    x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+    sw = torch.rand(N, device=dev) * 0.01
+    for _ in range(4):
+        ops.linear_small_m(x, q, sw)
+if kind == "conv":
+    C, H, W, N, k = map(int, sys.argv[2:7])
+    x = torch.randn(1, C, H, W, device=dev, dtype=torch.bfloat16)
+    for _ in range(4):
+        ops.conv_act_quant(x, (k, k), (1, 1), (k // 2, k // 2), (1, 1), "int8")
 torch.cuda.synchronize()
