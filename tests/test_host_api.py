@@ -164,3 +164,14 @@ def test_conv_quantisation_stores_what_the_reference_stores(path):
     weight / scale / zero_point as the reference (tests/golden/generate_conv.py); the asserts live in build_conv_layer."""
     layer, t, z, meta = build_conv_layer(path)
     assert type(layer).__name__ == "SDNQ" + meta["module"]
+
+
+def test_forward_dispatch_table_matches_reference():
+    """get_forward_func(layer class, matmul dtype, use_quantized_matmul) returns a function of the same name as the reference's for
+    every combination (tests/golden/forward_dispatch.json was written by calling the reference's get_forward_func, forward.py:6-57)."""
+    from sdnq_b200.forward import get_forward_func
+    table = json.load(open(os.path.join(GOLDEN, "forward_dispatch.json")))
+    assert len(table) >= 80
+    for key, ref_name in table.items():
+        cls, mm, use = key.split("|")
+        assert get_forward_func(cls, mm, bool(int(use))).__name__ == ref_name, key
