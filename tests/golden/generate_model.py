@@ -1,0 +1,59 @@
+"""Model-level parity fixture: run the reference's sdnq_post_load_quant on tests/golden/toy_model.py for a few configs and record,
+for every module / state-dict entry, what came out (class names, forward function names, dequantizer metadata, tensor shapes /
+dtypes / strides and a hash of the bytes) plus the resulting quantization_config lists.
+
+    SDNQ_USE_CONTIGUOUS_MM=0 SDNQ_ALLOW_FP8_MM=1 SDNQ_USE_TORCH_COMPILE=0 python tests/golden/generate_model.py
+"""
+import hashlib
+import json
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from _ref_loader import load_reference  # noqa: E402
+
+assert os.environ.get("SDNQ_USE_CONTIGUOUS_MM") == "0" and os.environ.get("SDNQ_ALLOW_FP8_MM") == "1", __doc__
+load_reference()
+from sdnq import sdnq_post_load_quant  # noqa: E402
+import toy_model  # noqa: E402
+
+
+def describe(model):
+    mods = {}
+    for name, m in model.named_modules():
+        if name == "":
+            continue
+        e = {"class": type(m).__name__}
+        d = getattr(m, "sdnq_dequantizer", None)
+        if d is not None:
+            e["forward_func"] = m.forward_func.__name__
+            e["dequantizer"] = {k: (str(v).replace("torch.", "") if isinstance(v, torch.dtype) else (list(v) if isinstance(v, (torch.Size, tuple)) else v))
+                                for k, v in d.__dict__.items()}
+        mods[name] = e
+    tensors = {}
+    for key, t in model.state_dict().items():
+        tt = t.detach()
+        phys = tt.t() if (tt.ndim == 2 and not tt.is_contiguous() and tt.t().is_contiguous()) else tt.contiguous()
+        raw = phys.view(torch.uint8) if phys.dtype in (torch.float8_e4m3fn, torch.float8_e5m2) else phys
+        data = raw.view(torch.uint8).numpy().tobytes() if raw.dtype != torch.bfloat16 else raw.view(torch.int16).numpy().tobytes()
+        tensors[key] = {"dtype": str(tt.dtype).replace("torch.", ""), "shape": list(tt.shape), "stride": list(tt.stride()),
+                        "sha1": hashlib.sha1(data).hexdigest()}
+    return mods, tensors
+
+
+out = {}
+for name, cfg in toy_model.CONFIGS.items():
+    model = toy_model.build()
+    model = sdnq_post_load_quant(model, **cfg)
+    mods, tensors = describe(model)
+    qc = model.quantization_config
+    out[name] = {"config": cfg, "modules": mods, "tensors": tensors,
+                 "modules_to_not_convert": sorted(qc.modules_to_not_convert), "modules_dtype_dict": {k: sorted(v) for k, v in qc.modules_dtype_dict.items()},
+                 "modules_to_not_use_matmul": sorted(qc.modules_to_not_use_matmul)}
+    nq = sum(1 for e in mods.values() if "forward_func" in e)
+    print(f"{name:24s} quantised modules: {nq:2d}  state-dict entries: {len(tensors)}")
+json.dump(out, open(os.path.join(HERE, "model_parity.json"), "w"), indent=0, sort_keys=True)
+print("bytes:", os.path.getsize(os.path.join(HERE, "model_parity.json")))

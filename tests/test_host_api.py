@@ -175,3 +175,66 @@ def test_forward_dispatch_table_matches_reference():
     for key, ref_name in table.items():
         cls, mm, use = key.split("|")
         assert get_forward_func(cls, mm, bool(int(use))).__name__ == ref_name, key
+
+
+# ----------------------------------------------------------------------------------------------- model-level drop-in parity
+import hashlib  # noqa: E402
+import sys  # noqa: E402
+
+sys.path.insert(0, GOLDEN)
+import toy_model  # noqa: E402
+
+_MODEL_PARITY = json.load(open(os.path.join(GOLDEN, "model_parity.json")))
+
+
+def _describe(model):
+    mods = {}
+    for name, m in model.named_modules():
+        if name == "":
+            continue
+        e = {"class": type(m).__name__}
+        d = getattr(m, "sdnq_dequantizer", None)
+        if d is not None:
+            e["forward_func"] = m.forward_func.__name__
+            e["dequantizer"] = {k: (str(v).replace("torch.", "") if isinstance(v, torch.dtype) else (list(v) if isinstance(v, (torch.Size, tuple)) else v))
+                                for k, v in d.__dict__.items()}
+        mods[name] = e
+    tensors = {}
+    for key, t in model.state_dict().items():
+        tt = t.detach()
+        phys = tt.t() if (tt.ndim == 2 and not tt.is_contiguous() and tt.t().is_contiguous()) else tt.contiguous()
+        raw = phys.view(torch.uint8) if phys.dtype in (torch.float8_e4m3fn, torch.float8_e5m2) else phys
+        data = raw.view(torch.uint8).numpy().tobytes() if raw.dtype != torch.bfloat16 else raw.view(torch.int16).numpy().tobytes()
+        tensors[key] = {"dtype": str(tt.dtype).replace("torch.", ""), "shape": list(tt.shape), "stride": list(tt.stride()),
+                        "sha1": hashlib.sha1(data).hexdigest()}
+    return mods, tensors
+
+
+@pytest.mark.parametrize("name", sorted(_MODEL_PARITY))
+def test_post_load_quant_matches_reference_on_a_model(name):
+    """sdnq_post_load_quant on a UNet-shaped toy model (tests/golden/toy_model.py): which modules are swapped (skip keys, size
+    thresholds, quant_conv / quant_embedding, per-module dtype overrides), the wrapper class and forward function of each, the
+    dequantizer metadata, every state-dict key with its dtype / shape / stride and the bytes themselves, and the bookkeeping lists of
+    the quantization config -- all equal to what the reference produced (tests/golden/generate_model.py)."""
+    from sdnq_b200 import sdnq_post_load_quant
+    ref = _MODEL_PARITY[name]
+    model = sdnq_post_load_quant(toy_model.build(), **ref["config"])
+    mods, tensors = _describe(model)
+    assert sorted(mods) == sorted(ref["modules"])
+    for mname, e in ref["modules"].items():
+        got = mods[mname]
+        assert got["class"] == e["class"], mname
+        assert got.get("forward_func") == e.get("forward_func"), mname
+        if "dequantizer" in e:
+            for k, v in e["dequantizer"].items():
+                assert got["dequantizer"].get(k) == v, (mname, k, got["dequantizer"].get(k), v)
+    assert sorted(tensors) == sorted(ref["tensors"])
+    for key, e in ref["tensors"].items():
+        got = tensors[key]
+        assert got["dtype"] == e["dtype"] and got["shape"] == e["shape"], key
+        assert all(a == b or n == 1 for a, b, n in zip(got["stride"], e["stride"], e["shape"])), (key, got["stride"], e["stride"])
+        assert got["sha1"] == e["sha1"], f"{key}: stored bytes differ from the reference's"
+    qc = model.quantization_config
+    assert sorted(qc.modules_to_not_convert) == ref["modules_to_not_convert"]
+    assert {k: sorted(v) for k, v in qc.modules_dtype_dict.items()} == ref["modules_dtype_dict"]
+    assert sorted(qc.modules_to_not_use_matmul) == ref["modules_to_not_use_matmul"]
