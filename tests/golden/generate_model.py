@@ -57,3 +57,25 @@ for name, cfg in toy_model.CONFIGS.items():
     print(f"{name:24s} quantised modules: {nq:2d}  state-dict entries: {len(tensors)}")
 json.dump(out, open(os.path.join(HERE, "model_parity.json"), "w"), indent=0, sort_keys=True)
 print("bytes:", os.path.getsize(os.path.join(HERE, "model_parity.json")))
+
+# ---- apply_sdnq_options_to_model: in-place layout / option flips on an already quantised model (loader.py:221-346)
+from sdnq.loader import apply_sdnq_options_to_model  # noqa: E402
+
+FLIPS = {
+    "int8_off_to_on": (dict(weights_dtype="int8"), dict(use_quantized_matmul=True)),
+    "int8_on_to_off": (dict(weights_dtype="int8", use_quantized_matmul=True), dict(use_quantized_matmul=False)),
+    "fp8_hadamard_off_to_on": (dict(weights_dtype="float8_e4m3fn", use_hadamard=True), dict(use_quantized_matmul=True)),
+    "uint4_off_to_on": (dict(weights_dtype="uint4"), dict(use_quantized_matmul=True)),
+    "int8_svd_on_to_off": (dict(weights_dtype="int8", use_quantized_matmul=True, use_svd=True, svd_rank=8), dict(use_quantized_matmul=False)),
+    "int8_conv_off_to_on": (dict(weights_dtype="int8", quant_conv=True), dict(use_quantized_matmul=True)),
+}
+flips = {}
+for name, (cfg, opts) in FLIPS.items():
+    torch.manual_seed(1)
+    model = sdnq_post_load_quant(toy_model.build(), **cfg)
+    before_mods, before = describe(model)
+    model = apply_sdnq_options_to_model(model, **opts)
+    mods, tensors = describe(model)
+    flips[name] = {"config": cfg, "options": opts, "modules": mods, "tensors": tensors, "tensors_before": before}
+    print(f"flip {name:24s} changed entries: {sum(1 for k in tensors if tensors[k] != before.get(k))}")
+json.dump(flips, open(os.path.join(HERE, "model_flips.json"), "w"), indent=0, sort_keys=True)

@@ -238,3 +238,35 @@ def test_post_load_quant_matches_reference_on_a_model(name):
     assert sorted(qc.modules_to_not_convert) == ref["modules_to_not_convert"]
     assert {k: sorted(v) for k, v in qc.modules_dtype_dict.items()} == ref["modules_dtype_dict"]
     assert sorted(qc.modules_to_not_use_matmul) == ref["modules_to_not_use_matmul"]
+
+
+_MODEL_FLIPS = json.load(open(os.path.join(GOLDEN, "model_flips.json")))
+
+
+@pytest.mark.parametrize("name", sorted(_MODEL_FLIPS))
+def test_apply_sdnq_options_matches_reference_on_a_model(name):
+    """apply_sdnq_options_to_model (in-place matmul on / off flips of the stored layouts, loader.py:221-346) on the toy model: every
+    state-dict entry (dtype, shape, stride, bytes), wrapper class, forward function and dequantizer field afterwards equals what the
+    reference's own function left behind (tests/golden/generate_model.py)."""
+    from sdnq_b200 import apply_sdnq_options_to_model, sdnq_post_load_quant
+    ref = _MODEL_FLIPS[name]
+    torch.manual_seed(1)
+    model = sdnq_post_load_quant(toy_model.build(), **ref["config"])
+    _, before = _describe(model)
+    if "svd" not in name:       # svd_lowrank draws random test matrices: the factors are reproducible only with the same RNG stream
+        assert {k: v["sha1"] for k, v in before.items()} == {k: v["sha1"] for k, v in ref["tensors_before"].items()}
+    model = apply_sdnq_options_to_model(model, **ref["options"])
+    mods, tensors = _describe(model)
+    for mname, e in ref["modules"].items():
+        got = mods[mname]
+        assert got["class"] == e["class"] and got.get("forward_func") == e.get("forward_func"), mname
+        if "dequantizer" in e:
+            for k, v in e["dequantizer"].items():
+                assert got["dequantizer"].get(k) == v, (mname, k, got["dequantizer"].get(k), v)
+    assert sorted(tensors) == sorted(ref["tensors"])
+    for key, e in ref["tensors"].items():
+        got = tensors[key]
+        assert got["dtype"] == e["dtype"] and got["shape"] == e["shape"], key
+        assert all(a == b or n == 1 for a, b, n in zip(got["stride"], e["stride"], e["shape"])), (key, got["stride"], e["stride"])
+        if "svd" not in name:
+            assert got["sha1"] == e["sha1"], f"{key}: bytes differ from the reference's after the flip"
