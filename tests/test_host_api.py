@@ -270,3 +270,17 @@ def test_apply_sdnq_options_matches_reference_on_a_model(name):
         assert all(a == b or n == 1 for a, b, n in zip(got["stride"], e["stride"], e["shape"])), (key, got["stride"], e["stride"])
         if "svd" not in name:
             assert got["sha1"] == e["sha1"], f"{key}: bytes differ from the reference's after the flip"
+
+
+def test_config_to_dict_matches_reference():
+    """SDNQConfig(**kwargs).to_dict() -- what `quantization_config.json` of a pre-quantized repo carries (quantizer.py:1075-1079) -- equals
+    the reference's for 12 configurations (tests/golden/config_dicts.json, written by the reference's own SDNQConfig).  The skip list
+    goes through list(set(...)) on both sides, so its order is compared as a set."""
+    from sdnq_b200 import SDNQConfig
+    ref = json.load(open(os.path.join(GOLDEN, "config_dicts.json")))
+    assert len(ref) >= 12
+    for name, e in ref.items():
+        d = json.loads(json.dumps(SDNQConfig(**e["kwargs"]).to_dict(), default=str))
+        want = dict(e["to_dict"])
+        assert sorted(d.pop("modules_to_not_convert")) == sorted(want.pop("modules_to_not_convert")), name
+        assert d == want, (name, {k: (d.get(k), want.get(k)) for k in set(d) | set(want) if d.get(k) != want.get(k)})
