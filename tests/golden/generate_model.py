@@ -79,3 +79,20 @@ for name, (cfg, opts) in FLIPS.items():
     flips[name] = {"config": cfg, "options": opts, "modules": mods, "tensors": tensors, "tensors_before": before}
     print(f"flip {name:24s} changed entries: {sum(1 for k in tensors if tensors[k] != before.get(k))}")
 json.dump(flips, open(os.path.join(HERE, "model_flips.json"), "w"), indent=0, sort_keys=True)
+
+# ---- dynamic quantisation (quantizer.py:280-419): the per-layer dtype search of sdnq_quantize_layer_weight_dynamic
+DYNAMIC = {
+    "uint4_dynamic": dict(weights_dtype="uint4", use_dynamic_quantization=True),
+    "int3_dynamic_tight": dict(weights_dtype="int3", use_dynamic_quantization=True, dynamic_loss_threshold=3e-3),
+    "uint4_dynamic_w8a8": dict(weights_dtype="uint4", use_dynamic_quantization=True, use_quantized_matmul=True, dynamic_loss_threshold=2e-3),
+}
+dyn = {}
+for name, cfg in DYNAMIC.items():
+    model = sdnq_post_load_quant(toy_model.build(), **cfg)
+    mods, tensors = describe(model)
+    qc = model.quantization_config
+    dyn[name] = {"config": cfg, "modules": mods, "tensors": tensors, "modules_to_not_convert": sorted(qc.modules_to_not_convert),
+                 "modules_dtype_dict": {k: sorted(v) for k, v in qc.modules_dtype_dict.items()},
+                 "modules_to_not_use_matmul": sorted(qc.modules_to_not_use_matmul)}
+    print(f"dynamic {name:22s} ->", {k: len(v) for k, v in qc.modules_dtype_dict.items()})
+json.dump(dyn, open(os.path.join(HERE, "model_dynamic.json"), "w"), indent=0, sort_keys=True)

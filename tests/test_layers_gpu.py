@@ -189,3 +189,41 @@ def test_small_m_forward_gemv_vs_dequant_path(cfg, M, monkeypatch):
     # and both are the same distance from the unquantised layer (quantisation error dominates)
     e1, e2 = (y.float() - dense.float()).pow(2).mean().sqrt(), (y_ref.float() - dense.float()).pow(2).mean().sqrt()
     assert float(e1) <= 1.1 * float(e2) + 1e-3 * scale
+
+
+@pytest.mark.parametrize("name", ["uint4_dynamic", "int3_dynamic_tight", "uint4_dynamic_w8a8"])
+def test_dynamic_quantization_picks_the_reference_dtypes(name):
+    """use_dynamic_quantization (quantizer.py:280-419): walk weights_dtype_order until the normalised MSE of quantise -> dequantise
+    (through the K3 kernel here) drops below the threshold.  The dtype chosen for every layer, the wrapper classes, forward
+    functions, dequantizer metadata and stored shapes equal the reference's run on the same toy model
+    (tests/golden/model_dynamic.json), and the quantised model still tracks the dense one."""
+    import json
+    import os
+    import sys
+    from tests.util import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    import toy_model
+    from sdnq_b200 import sdnq_post_load_quant
+    ref = json.load(open(os.path.join(GOLDEN, "model_dynamic.json")))[name]
+    dense = toy_model.build().to(DEV)
+    model = sdnq_post_load_quant(toy_model.build().to(DEV), **ref["config"])
+    qc = model.quantization_config
+    assert {k: sorted(v) for k, v in qc.modules_dtype_dict.items()} == ref["modules_dtype_dict"]
+    assert sorted(qc.modules_to_not_convert) == ref["modules_to_not_convert"]
+    assert sorted(qc.modules_to_not_use_matmul) == ref["modules_to_not_use_matmul"]
+    mods = dict(model.named_modules())
+    for mname, e in ref["modules"].items():
+        m = mods[mname]
+        assert type(m).__name__ == e["class"], mname
+        if "forward_func" in e:
+            assert m.forward_func.__name__ == e["forward_func"], mname
+            for k in ("weights_dtype", "group_size", "quantized_matmul_dtype", "use_quantized_matmul", "re_quantize_for_matmul", "quantized_weight_shape"):
+                got = getattr(m.sdnq_dequantizer, k)
+                got = list(got) if isinstance(got, (torch.Size, tuple)) else got
+                assert got == e["dequantizer"][k], (mname, k, got, e["dequantizer"][k])
+    sd = model.state_dict()
+    for key, e in ref["tensors"].items():
+        assert key in sd and list(sd[key].shape) == e["shape"] and str(sd[key].dtype).replace("torch.", "") == e["dtype"], key
+    x = torch.randn(40, 128, dtype=torch.bfloat16, device=DEV)
+    y, yd = model.mid[0].ff(x), dense.mid[0].ff(x)
+    assert float((y.float() - yd.float()).pow(2).mean().sqrt()) <= 0.1 * float(yd.float().pow(2).mean().sqrt())
