@@ -284,3 +284,32 @@ def test_config_to_dict_matches_reference():
         want = dict(e["to_dict"])
         assert sorted(d.pop("modules_to_not_convert")) == sorted(want.pop("modules_to_not_convert")), name
         assert d == want, (name, {k: (d.get(k), want.get(k)) for k in set(d) | set(want) if d.get(k) != want.get(k)})
+
+
+@pytest.mark.parametrize("name", ["uint4_conv_embedding", "int8_w8a8_conv"])
+def test_load_reference_written_checkpoint(name, tmp_path):
+    """Checkpoint interchange (SURVEY.md 8 f4 / 8b "config compatibility"): tests/golden/ckpt_<name>/ was written from a model the
+    *reference* quantised (state_dict -> safetensors as save_pretrained does, quantization_config.to_dict() -> JSON).  Our loader
+    (config -> SDNQ modules with pre_quantized=True -> load_state_dict(assign=True) -> post_process_model) must end up with exactly
+    the reference's in-memory model: classes, forward functions, dequantizer metadata, dtypes, shapes, K-major strides, bytes.
+    Then our own save -> load round trip must reproduce it again."""
+    from sdnq_b200 import load_sdnq_state_dict, save_sdnq_model
+    ref = _MODEL_PARITY[name]
+
+    def check(model):
+        mods, tensors = _describe(model)
+        for mname, e in ref["modules"].items():
+            assert mods[mname]["class"] == e["class"] and mods[mname].get("forward_func") == e.get("forward_func"), mname
+            for k, v in e.get("dequantizer", {}).items():
+                assert mods[mname]["dequantizer"].get(k) == v, (mname, k)
+        assert sorted(tensors) == sorted(ref["tensors"])
+        for key, e in ref["tensors"].items():
+            got = tensors[key]
+            assert got["dtype"] == e["dtype"] and got["shape"] == e["shape"] and got["sha1"] == e["sha1"], key
+            assert all(a == b or n == 1 for a, b, n in zip(got["stride"], e["stride"], e["shape"])), (key, got["stride"], e["stride"])
+
+    model = load_sdnq_state_dict(toy_model.build(seed=123), os.path.join(GOLDEN, "ckpt_" + name))
+    check(model)
+    save_sdnq_model(model, str(tmp_path))
+    assert sorted(os.listdir(tmp_path)) == ["model.safetensors", "quantization_config.json"]
+    check(load_sdnq_state_dict(toy_model.build(seed=7), str(tmp_path)))
