@@ -96,3 +96,41 @@ for name, cfg in DYNAMIC.items():
                  "modules_to_not_use_matmul": sorted(qc.modules_to_not_use_matmul)}
     print(f"dynamic {name:22s} ->", {k: len(v) for k, v in qc.modules_dtype_dict.items()})
 json.dump(dyn, open(os.path.join(HERE, "model_dynamic.json"), "w"), indent=0, sort_keys=True)
+
+# ---- get_forward_func dispatch table (forward.py:6-57)
+from sdnq.forward import get_forward_func  # noqa: E402
+
+table = {}
+for c in ["Linear", "SDNQLinear", "Conv1d", "Conv2d", "Conv3d", "SDNQConv2d", "ConvTranspose1d", "ConvTranspose2d", "ConvTranspose3d", "Embedding"]:
+    for m in ["int8", "uint8", "float8_e4m3fn", "float16"]:
+        for use in (False, True):
+            table[f"{c}|{m}|{int(use)}"] = get_forward_func(c, m, use).__name__
+json.dump(table, open(os.path.join(HERE, "forward_dispatch.json"), "w"), indent=0, sort_keys=True)
+
+# ---- SDNQConfig.to_dict() (what quantization_config.json carries, quantizer.py:1075-1079)
+from sdnq import SDNQConfig  # noqa: E402
+
+cases = dict(toy_model.CONFIGS)
+cases.update({
+    "defaults": {},
+    "int4_svd": dict(weights_dtype="int4", group_size=128, use_svd=True, svd_rank=32),
+    "dynamic": dict(weights_dtype="uint4", use_dynamic_quantization=True, dynamic_loss_threshold=0.01),
+    "fp8_tensorwise": dict(weights_dtype="float8_e4m3fn", group_size=-2, dequantize_fp32=False),
+    "matmul_dtype": dict(weights_dtype="int6", quantized_matmul_dtype="float8_e4m3fn", use_quantized_matmul=True),
+    "codebook": dict(weights_dtype="uint4", use_codebook=True, codebook_steps=12),
+})
+json.dump({n: {"kwargs": c, "to_dict": json.loads(json.dumps(SDNQConfig(**c).to_dict(), default=str))} for n, c in cases.items()},
+          open(os.path.join(HERE, "config_dicts.json"), "w"), indent=0, sort_keys=True)
+
+# ---- checkpoints of reference-quantised toy models: what save_pretrained writes (every tensor .contiguous() into safetensors) plus
+#      the config's to_dict() as quantization_config.json (QuantizationConfigMixin.to_json_file)
+from safetensors.torch import save_file  # noqa: E402
+
+for name in ("uint4_conv_embedding", "int8_w8a8_conv"):
+    model = sdnq_post_load_quant(toy_model.build(), **toy_model.CONFIGS[name])
+    ckpt = os.path.join(HERE, "ckpt_" + name)
+    os.makedirs(ckpt, exist_ok=True)
+    save_file({k: v.contiguous() for k, v in model.state_dict().items()}, os.path.join(ckpt, "model.safetensors"))
+    with open(os.path.join(ckpt, "quantization_config.json"), "w") as f:
+        json.dump(json.loads(json.dumps(model.quantization_config.to_dict(), default=str)), f, indent=2, sort_keys=True)
+print("dispatch / config / checkpoint fixtures written")
