@@ -56,6 +56,33 @@ def test_argument_errors_are_reported_not_thrown(lib):
     assert rc == -1
 
 
+def test_argument_errors_of_the_conv_and_small_m_entries(lib):
+    """the entry points added for the conv path and the small-M Linear validate before touching CUDA"""
+    from sdnq_b200._lib import Conv2dGeometry, WeightFormat
+    P = ctypes.c_void_p
+    rc = lib.sdnq_b200_linear_small_m(P(16), 1, 64, P(16), 3, P(16), None, None, 0, P(16), 40, 64, 64, None)          # M > 32
+    assert rc == -1 and b"M <= 32" in lib.sdnq_b200_last_error()
+    rc = lib.sdnq_b200_linear_small_m(P(16), 0, 64, P(16), 3, P(16), None, None, 0, P(16), 4, 64, 64, None)           # f32 activations
+    assert rc == -2 and b"bf16 / f16" in lib.sdnq_b200_last_error()
+    rc = lib.sdnq_b200_linear_small_m(P(16), 1, 72, P(16), 3, P(16), None, None, 0, P(16), 4, 64, 72, None)           # K % 16
+    assert rc == -2
+    rc = lib.sdnq_b200_rows_to_nchw(P(16), P(16), 3, 1, 64, 64, None)                                                  # 3-byte elements
+    assert rc == -1 and b"2 or 4 bytes" in lib.sdnq_b200_last_error()
+    geo = Conv2dGeometry(1, 64, 8, 8, 4096, 64, 8, 1, 3, 3, 0, 1, 1, 1, 1, 1)                                           # stride_h = 0
+    rc = lib.sdnq_b200_conv_act_quant(P(16), 1, ctypes.byref(geo), 0, 3, P(16), P(16), None, None, None, None)
+    assert rc == -1 and b"geometry" in lib.sdnq_b200_last_error()
+    geo = Conv2dGeometry(2, 64, 8, 8, 4096, 64, 8, 1, 3, 3, 1, 1, 1, 1, 1, 1)
+    assert lib.sdnq_b200_conv_act_quant_workspace_bytes(ctypes.byref(geo), 3) == 2 * 8 * 8 * 4
+    assert lib.sdnq_b200_conv_act_quant_workspace_bytes(ctypes.byref(geo), 4) == 2 * 8 * 8 * 4 * 2                        # uint8: min and max
+    rc = lib.sdnq_b200_conv_act_quant_ws(P(16), 1, ctypes.byref(geo), 0, 3, P(16), P(16), None, None, None, P(16), 8, None)    # workspace too small
+    assert rc == -1 and b"workspace" in lib.sdnq_b200_last_error()
+    fmt = WeightFormat(0, 8, 0, 0, 0, 1)
+    dims = (ctypes.c_int64 * 2)(3, 5)                                                                                    # 15 weights: not a multiple of 8
+    strides = (ctypes.c_int64 * 2)(1, 0)
+    rc = lib.sdnq_b200_dequant_nd(P(16), ctypes.byref(fmt), P(16), None, 0, 2, dims, strides, None, 0, P(16), 1, None)
+    assert rc == -2 and b"multiple of 8" in lib.sdnq_b200_last_error()
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from sdnq_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
