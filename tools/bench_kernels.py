@@ -88,8 +88,6 @@ def main():
         print(f"{M}x{N}x{K}", json.dumps({k: (round(v, 3) if isinstance(v, float) else v) for k, v in line.items()}), flush=True)
         del a8, b8, af, bf, xb
     # dequant kernel (K3) and requant (K4) on SD-XL / FLUX weight shapes
-    from oracle import sdnq_oracle as O  # noqa: F401  (only for packing test data on the host)
-    import numpy as np
     for (N, K) in [(10240, 1280), (1280, 5120), (12288, 3072), (4096, 4096)]:
         for wd, bits, gs in [("int4", 4, 128), ("int8", 8, K), ("uint3", 3, 64), ("float6_e3m2fn", 6, K)]:
             nbytes = N * K * bits // 8
