@@ -89,3 +89,108 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.SDNQKernelError, match="no CPU or eager fallback"):
         _lib.load()
+
+
+# ---- the header is the contract: the ctypes binding (and the stub INTEGRATION.md shows to reference maintainers) must agree with it
+def header_prototypes():
+    """{name: (return type, [parameter types])} parsed from include/sdnq_b200.h (comments stripped)."""
+    text = open(os.path.join(ROOT, "include", "sdnq_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    protos = {}
+    for ret, name, params in re.findall(r"SDNQ_API\s+([\w\s\*]+?)\b(sdnq_b200_\w+)\s*\(([^)]*)\)\s*;", text):
+        plist = []
+        for p in params.split(","):
+            p = " ".join(p.split())
+            if p in ("void", ""):
+                continue
+            m = re.match(r"(.*?)(\w+)$", p)                    # drop the parameter name
+            plist.append(m.group(1).replace(" ", ""))
+        protos[name] = (ret.replace(" ", ""), plist)
+    return protos, text
+
+
+def _ctype_of(c_type):
+    from sdnq_b200._lib import Conv2dGeometry, WeightFormat
+    table = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t, "constchar*": ctypes.c_char_p,
+             "constsdnq_weight_format*": ctypes.POINTER(WeightFormat), "constsdnq_conv2d_geometry*": ctypes.POINTER(Conv2dGeometry),
+             "constint64_t*": ctypes.POINTER(ctypes.c_int64)}
+    if c_type in table:
+        return table[c_type]
+    assert c_type.endswith("*"), f"unmapped C type {c_type!r}"
+    return ctypes.c_void_p                                     # every other pointer (void / float / int32_t, const or not) is a device pointer
+
+
+def test_ctypes_signatures_match_the_header_types():
+    from sdnq_b200 import _lib
+    protos, _ = header_prototypes()
+    assert sorted(protos) == sorted(_lib.SIGNATURES)
+    for name, (ret, params) in protos.items():
+        res, args = _lib.SIGNATURES[name]
+        assert res is _ctype_of(ret), f"{name}: return type {ret} bound as {res}"
+        assert len(args) == len(params), f"{name}: {len(params)} parameters in the header, {len(args)} in the binding"
+        for i, (c, a) in enumerate(zip(params, args)):
+            assert a is _ctype_of(c), f"{name}: parameter {i} is {c} in the header, {a} in the binding"
+
+
+def test_struct_layouts_match_the_header():
+    from sdnq_b200._lib import Conv2dGeometry, WeightFormat
+    _, text = header_prototypes()
+    ctype = {"int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "int": ctypes.c_int}
+    for struct, cls in (("sdnq_weight_format", WeightFormat), ("sdnq_conv2d_geometry", Conv2dGeometry)):
+        body = re.search(r"typedef\s+struct\s+" + struct + r"\s*\{(.*?)\}\s*" + struct + r"\s*;", text, flags=re.S).group(1)
+        fields = []
+        for decl in body.split(";"):
+            decl = " ".join(decl.split())
+            if decl:
+                typ, names = decl.split(" ", 1)
+                fields += [(n.strip(), ctype[typ]) for n in names.split(",")]
+        assert [(n, t) for n, t in cls._fields_] == fields, f"{struct}: ctypes fields differ from the header"
+
+
+def test_integration_stub_binds_against_the_built_library(lib):
+    """The ctypes stub INTEGRATION.md proposes for the reference (sdnq/kernels/b200.py) loads our library, and the argument
+    lists it declares have the header's length and types."""
+    from sdnq_b200 import _lib
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", md, flags=re.S)
+    stub = next(b for b in blocks if "sdnq/kernels/b200.py" in b)
+    assert '"libsdnq_b200.so"' in stub
+    ns = {}
+    exec(compile(stub.replace('"libsdnq_b200.so"', repr(_lib.LIB_PATH)), "INTEGRATION.md:b200.py", "exec"), ns)
+    protos, _ = header_prototypes()
+    bound = 0
+    for name, (_, params) in protos.items():
+        fn = getattr(ns["_lib"], name)
+        if fn.argtypes is None:
+            continue
+        bound += 1
+        assert len(fn.argtypes) == len(params), f"INTEGRATION.md stub: {name} declares {len(fn.argtypes)} arguments, header has {len(params)}"
+        for i, (c, a) in enumerate(zip(params, fn.argtypes)):
+            want = _ctype_of(c)
+            want = ctypes.c_void_p if isinstance(want, type) and issubclass(want, ctypes._Pointer) else want
+            assert a is want, f"INTEGRATION.md stub: {name} parameter {i}: {c} bound as {a}"
+    assert bound >= 2
+    for fn in ("sdnq_scaled_mm", "quantize_int_mm_input"):
+        assert callable(ns[fn])
+    assert [ns[k] for k in ("F32", "BF16", "F16", "I8", "U8", "F8E4M3", "I32")] == \
+        [_lib.SDNQ_F32, _lib.SDNQ_BF16, _lib.SDNQ_F16, _lib.SDNQ_I8, _lib.SDNQ_U8, _lib.SDNQ_F8E4M3, _lib.SDNQ_I32]
+
+
+def test_enum_values_match_the_header():
+    from sdnq_b200 import _lib
+    _, text = header_prototypes()
+    values = {}
+    for body in re.findall(r"enum\s*\w*\s*\{(.*?)\}", text, flags=re.S):
+        nxt = 0
+        for item in body.split(","):
+            item = item.strip()
+            if not item:
+                continue
+            name, _, val = (s.strip() for s in item.partition("="))
+            nxt = int(val, 0) if val else nxt
+            values[name] = nxt
+            nxt += 1
+    for name in ("SDNQ_F32", "SDNQ_BF16", "SDNQ_F16", "SDNQ_I8", "SDNQ_U8", "SDNQ_F8E4M3", "SDNQ_I32",
+                 "SDNQ_W_INT", "SDNQ_W_MINIFLOAT", "SDNQ_W_FP8_E4M3FN", "SDNQ_W_FP8_E5M2"):
+        assert values[name] == getattr(_lib, name), name
