@@ -1,0 +1,82 @@
+// g++ build of the per-lane device arithmetic of the sdnq_b200 kernels (see prelude.h).  Exposes a tiny C ABI for the test.
+#include "prelude.h"
+#include "../../sdnq_b200/csrc/unpack.cuh"
+
+using namespace sdnq;
+
+namespace sdnq {
+int set_error(int code, const char*, ...) { return code; }
+void count_launch(int) {}
+}  // namespace sdnq
+
+extern "C" {
+
+// storage bytes -> unsigned codes, octet by octet, through load_octet_bytes + decode_octet exactly as the kernels do
+int emu_decode(int bits, int word_bytes, const uint8_t* packed, int64_t octets, uint32_t* codes) {
+    if (bits < 1 || bits > 8) return -1;
+    for (int64_t o = 0; o < octets; ++o) {
+        SDNQ_DISPATCH_BITS(bits, {
+            uint32_t w[OctetWords<BITS>::N];
+            load_octet_bytes<BITS>(packed, o, word_bytes, w);
+            uint32_t v[8];
+            decode_octet<BITS>(w, v);
+            for (int i = 0; i < 8; ++i) codes[8 * o + i] = v[i];
+        });
+    }
+    return 0;
+}
+
+// storage bytes -> real values before the scale (codes_to_values: integer offset / minifloat / fp8 decode)
+int emu_values(const sdnq_weight_format* fmt, const uint8_t* packed, int64_t octets, float* out) {
+    WFormat f;
+    int rc = make_wformat(fmt, &f);
+    if (rc != SDNQ_OK) return rc;
+    for (int64_t o = 0; o < octets; ++o) {
+        SDNQ_DISPATCH_BITS(f.bits, {
+            float q[8];
+            uint32_t c[8];
+            octet_values<BITS>(packed, o, f, q, c);
+            for (int i = 0; i < 8; ++i) out[8 * o + i] = q[i];
+        });
+    }
+    return 0;
+}
+
+// the byte-permute fast path of the flat dequant kernel / GEMV for integer formats
+int emu_octet_to_floats(const sdnq_weight_format* fmt, const uint8_t* packed, int64_t octets, float* out) {
+    WFormat f;
+    int rc = make_wformat(fmt, &f);
+    if (rc != SDNQ_OK || f.kind != SDNQ_W_INT) return -1;
+    const bool twos = f.bits == 8 && !f.is_unsigned;
+    const uint32_t flip = twos ? 0x80808080u : 0u;
+    const float bias = twos ? 8388608.0f + 128.0f : 8388608.0f - static_cast<float>(f.int_offset);
+    for (int64_t o = 0; o < octets; ++o) {
+        SDNQ_DISPATCH_BITS(f.bits, {
+            uint32_t w[OctetWords<BITS>::N];
+            load_octet_bytes<BITS>(packed, o, f.word_bytes, w);
+            float q[8];
+            octet_to_floats<BITS>(w, flip, bias, q);
+            for (int i = 0; i < 8; ++i) out[8 * o + i] = q[i];
+        });
+    }
+    return 0;
+}
+
+void emu_f32_to_e4m3(const float* in, int64_t n, uint8_t* out) { for (int64_t i = 0; i < n; ++i) out[i] = f32_to_e4m3(in[i]); }
+void emu_e4m3_to_f32(const uint8_t* in, int64_t n, float* out) { for (int64_t i = 0; i < n; ++i) out[i] = e4m3_to_f32(in[i]); }
+void emu_e5m2_to_f32(const uint8_t* in, int64_t n, float* out) { for (int64_t i = 0; i < n; ++i) out[i] = e5m2_to_f32(in[i]); }
+void emu_round_bf16(const float* in, int64_t n, float* out) { for (int64_t i = 0; i < n; ++i) out[i] = ElemTraits<__nv_bfloat16>::round(in[i]); }
+void emu_round_f16(const float* in, int64_t n, float* out) { for (int64_t i = 0; i < n; ++i) out[i] = ElemTraits<__half>::round(in[i]); }
+
+// where the two 4-element halves of lane `lane` land after the in-warp H4-family transform, and the per-register sign rule
+int emu_hadamard_dest(int G, int lane, int half) { return hadamard_dest_dyn(G, lane, half); }
+uint32_t emu_hadamard_sign(int G, int lane, int j) {
+    switch (G) {
+        case 4: return hadamard_sign_mask<4>(lane, j);
+        case 16: return hadamard_sign_mask<16>(lane, j);
+        case 64: return hadamard_sign_mask<64>(lane, j);
+        case 256: return hadamard_sign_mask<256>(lane, j);
+        default: return 0;
+    }
+}
+}

@@ -1,0 +1,33 @@
+// Host stand-ins for the CUDA device intrinsics used by the per-lane arithmetic in sdnq_b200/csrc/{common,unpack}.cuh, so that
+// g++ can compile those headers unchanged and tests/test_device_arithmetic_on_host.py can check the decode / convert
+// functions bit-for-bit against the oracle without a GPU.  Test infrastructure only; warp-collective code (shuffles) is
+// declared but never executed here.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#include <vector_types.h>
+#include <vector_functions.h>
+
+static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+// PRMT in its default mode: result byte i = byte (selector nibble i & 7) of the 8-byte pool {y:x}; nibble bit 3 replicates the sign
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+    const uint64_t pool = (uint64_t(y) << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t sel = (s >> (4 * i)) & 0xF;
+        uint32_t b = uint32_t(pool >> (8 * (sel & 7))) & 0xFF;
+        if (sel & 8) b = (b & 0x80) ? 0xFF : 0x00;
+        r |= b << (8 * i);
+    }
+    return r;
+}
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+static inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(std::fma(a.x, b.x, c.x), std::fma(a.y, b.y, c.y)); }
+// never executed on the host (single "lane"): identity
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
+static const uint3 threadIdx = {0, 0, 0};

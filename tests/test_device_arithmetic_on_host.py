@@ -1,0 +1,218 @@
+"""The per-lane arithmetic of the CUDA kernels, compiled for the host and checked against the oracle WITHOUT a GPU.
+
+`tests/host_emu/emu.cpp` includes `sdnq_b200/csrc/unpack.cuh` (and through it `common.cuh`) unchanged and is built with g++;
+`tests/host_emu/prelude.h` supplies host stand-ins for the few device intrinsics those headers use (`__byte_perm`,
+`__uint_as_float`, ...).  So the storage decoders (`load_octet_bytes` + `decode_octet`), the value decoders
+(`codes_to_values`: signed offset, every minifloat format, fp8) and the byte-permute fast path (`octet_to_floats`) that the
+dequant / re-quantise / GEMV kernels run are the same source lines the GPU executes; the bar is bit-exact against the numpy oracle,
+which is itself pinned to reference-generated fixtures (tests/test_oracle_golden.py).  The GPU tests stay the parity tests
+proper; this is the CPU-only regression gate for the integer / bit-manipulation part of the kernels."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import sdnq_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "host_emu")
+P = ctypes.c_void_p
+
+
+class WeightFormat(ctypes.Structure):            # include/sdnq_b200.h: sdnq_weight_format
+    _fields_ = [(n, ctypes.c_int32) for n in ("kind", "bits", "is_unsigned", "exponent", "mantissa", "word_bytes")]
+
+
+W_INT, W_MINIFLOAT, W_E4M3, W_E5M2 = range(4)
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("host_emu") / "libsdnq_emu.so")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-w", "-include", os.path.join(EMU_DIR, "prelude.h"), "-I", cuda_inc,
+           os.path.join(EMU_DIR, "emu.cpp"), "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, "host build of the device headers failed:\n" + r.stderr[-3000:]
+    lib = ctypes.CDLL(out)
+    lib.emu_decode.argtypes = [ctypes.c_int, ctypes.c_int, P, ctypes.c_int64, P]
+    lib.emu_values.argtypes = [ctypes.POINTER(WeightFormat), P, ctypes.c_int64, P]
+    lib.emu_octet_to_floats.argtypes = [ctypes.POINTER(WeightFormat), P, ctypes.c_int64, P]
+    for name in ("emu_f32_to_e4m3", "emu_e4m3_to_f32", "emu_e5m2_to_f32", "emu_round_bf16", "emu_round_f16"):
+        getattr(lib, name).argtypes = [P, ctypes.c_int64, P]
+        getattr(lib, name).restype = None
+    lib.emu_hadamard_sign.restype = ctypes.c_uint32
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(P)
+
+
+def _storage_bytes(packed, bits):
+    """the oracle's packed words as the byte stream the kernels read (uint1: upstream keeps one int64 per packed byte)"""
+    a = np.ascontiguousarray(packed)
+    assert a.dtype == np.uint8, a.dtype
+    return a.reshape(-1)
+
+
+INT_NAMES = [f"{u}int{b}" for u in ("", "u") for b in range(2, 9)] + ["uint1"]
+_FLOATS = [f"float{1 + e + m}_e{e}m{m}fn" for e in range(1, 6) for m in range(0, 7) if 2 <= 1 + e + m <= 8] + \
+          [f"float{e + m}_e{e}m{m}fnu" for e in range(1, 6) for m in range(0, 8) if 1 <= e + m <= 8]
+
+
+def _known_minifloats():
+    names = []
+    for n in _FLOATS + ["float8_e4m3fn_sdnq"]:
+        try:
+            info = O.dtype_info(n)
+        except (ValueError, AssertionError):
+            continue
+        if info["is_packed"] or n.endswith("_sdnq"):
+            names.append(n)
+    return names
+
+
+MINIFLOATS = _known_minifloats()
+
+
+def test_the_format_lists_cover_the_dtype_table():
+    from sdnq_b200.common import dtype_dict
+    canonical = {k for k, v in dtype_dict.items()
+                 if k.startswith("float") and not v["is_integer"] and v["is_packed"] and v["num_bits"] <= 8}
+    assert canonical <= set(MINIFLOATS), sorted(canonical - set(MINIFLOATS))
+    assert len(MINIFLOATS) >= 55
+
+
+@pytest.mark.parametrize("name", INT_NAMES)
+def test_integer_storage_decoders_bit_exact(emu, name):
+    info = O.dtype_info(name)
+    bits = info["num_bits"]
+    rng = np.random.default_rng(bits * 7 + info["is_unsigned"])
+    n = 8 * 1031                                                   # octets at every byte alignment for the odd widths
+    values = rng.integers(info["min"], info["max"] + 1, size=n)
+    values[:2 ** min(bits, 8)] = np.arange(info["min"], info["min"] + 2 ** min(bits, 8))[:n]       # every code at least once
+    packed = O.pack_int(values, name) if bits < 8 else (values.astype(np.int8).view(np.uint8) if not info["is_unsigned"] else values.astype(np.uint8))
+    raw = _storage_bytes(packed, bits)
+    assert raw.size == n * bits // 8
+    # unsigned codes
+    codes = np.empty(n, dtype=np.uint32)
+    assert emu.emu_decode(bits, 1, _ptr(raw), n // 8, _ptr(codes)) == 0
+    want_codes = values - info["min"] if (bits < 8 and not info["is_unsigned"]) else (values & 0xFF)
+    np.testing.assert_array_equal(codes.astype(np.int64), want_codes)
+    # real values through both value paths
+    fmt = WeightFormat(W_INT, bits, int(info["is_unsigned"]), 0, 0, 1)
+    for fn in (emu.emu_values, emu.emu_octet_to_floats):
+        out = np.empty(n, dtype=np.float32)
+        assert fn(ctypes.byref(fmt), _ptr(raw), n // 8, _ptr(out)) == 0
+        np.testing.assert_array_equal(out, values.astype(np.float32))
+    if bits < 8:
+        np.testing.assert_array_equal(O.unpack_int(packed, name, (n,)), values)       # and the oracle agrees with itself
+
+
+def test_uint1_int64_words(emu):
+    """upstream stores uint1 as one int64 per packed byte; the kernels read the low byte of each word"""
+    rng = np.random.default_rng(1)
+    bits_in = rng.integers(0, 2, size=8 * 257)
+    packed = O.pack_int(bits_in, "uint1").astype(np.int64)
+    raw = packed.view(np.uint8)
+    codes = np.empty(bits_in.size, dtype=np.uint32)
+    assert emu.emu_decode(1, 8, _ptr(raw), bits_in.size // 8, _ptr(codes)) == 0
+    np.testing.assert_array_equal(codes, bits_in)
+
+
+@pytest.mark.parametrize("name", MINIFLOATS)
+def test_minifloat_decoders_bit_exact(emu, name):
+    info = O.dtype_info(name)
+    bits = info["num_bits"]
+    rng = np.random.default_rng(bits)
+    n = 8 * 257
+    codes = rng.integers(0, 2 ** bits, size=n)
+    codes[:2 ** bits] = np.arange(2 ** bits)[:n]                   # the whole code table
+    packed = O.pack_uint(codes, bits) if bits < 8 else codes.astype(np.uint8)
+    raw = _storage_bytes(packed, bits)
+    fmt = WeightFormat(W_MINIFLOAT, bits, int(info["is_unsigned"]), info["exponent"], info["mantissa"], 1)
+    out = np.empty(n, dtype=np.float32)
+    assert emu.emu_values(ctypes.byref(fmt), _ptr(raw), n // 8, _ptr(out)) == 0
+    want = O.unpack_float(packed, name, (n,))
+    np.testing.assert_array_equal(out.view(np.uint32), want.view(np.uint32))         # bit patterns: "-0" must decode to +0
+
+
+def test_native_fp8_tables(emu):
+    allb = np.arange(256, dtype=np.uint8)
+    out = np.empty(256, dtype=np.float32)
+    emu.emu_e4m3_to_f32(_ptr(allb), 256, _ptr(out))
+    want = O.from_e4m3fn_bits(allb)
+    finite = ~np.isnan(want)
+    np.testing.assert_array_equal(out[finite], want[finite])
+    assert np.isnan(out[~finite]).all() and set(allb[~finite]) == {0x7F, 0xFF}
+    # e5m2 is the top byte of an IEEE half
+    emu.emu_e5m2_to_f32(_ptr(allb), 256, _ptr(out))
+    want5 = (allb.astype(np.uint16) << 8).view(np.float16).astype(np.float32)
+    ok = np.isfinite(want5)
+    np.testing.assert_array_equal(out[ok], want5[ok])
+    # through the weight-format path as well
+    for kind, table in ((W_E4M3, want), (W_E5M2, want5)):
+        fmt = WeightFormat(kind, 8, 0, 4 if kind == W_E4M3 else 5, 3 if kind == W_E4M3 else 2, 1)
+        assert emu.emu_values(ctypes.byref(fmt), _ptr(allb), 32, _ptr(out)) == 0
+        good = np.isfinite(table)
+        np.testing.assert_array_equal(out[good], table[good])
+
+
+def test_activation_cast_to_e4m3_is_round_to_nearest_even(emu):
+    """K2's fp8 quantiser: clamp to +-448 then cast (quant_utils.py:289-299); the cast must equal torch's / the oracle's RNE"""
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.standard_normal(20000).astype(np.float32) * s for s in (1e-3, 0.05, 1.0, 30.0, 200.0)])
+    table = O.from_e4m3fn_bits(np.arange(0x7F, dtype=np.uint8))                        # positive finite values, ascending
+    mids = (table[:-1] + table[1:]) / 2                                                  # exact ties between neighbours
+    x = np.clip(np.concatenate([x, mids, -mids, table, -table, np.float32([0.0, -0.0, 448.0, -448.0, 2 ** -10, 2 ** -11])]), -448, 448).astype(np.float32)
+    got = np.empty(x.size, dtype=np.uint8)
+    emu.emu_f32_to_e4m3(_ptr(x), x.size, _ptr(got))
+    np.testing.assert_array_equal(got, O.e4m3fn_bits(x))
+
+
+def test_rounding_to_the_activation_dtype(emu):
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(50000) * np.exp2(rng.integers(-20, 20, size=50000))).astype(np.float32)
+    out = np.empty_like(x)
+    emu.emu_round_bf16(_ptr(x), x.size, _ptr(out))
+    np.testing.assert_array_equal(out, O.bf16_round(x))
+    emu.emu_round_f16(_ptr(x), x.size, _ptr(out))
+    with np.errstate(over="ignore"):
+        np.testing.assert_array_equal(out, x.astype(np.float16).astype(np.float32))
+
+
+@pytest.mark.parametrize("G", [4, 16, 64, 256])
+def test_h4_family_sign_and_placement_rules(emu, G):
+    """common.cuh factors the reference's power-of-4 Hadamard (quant_utils.py:155-165, kron^k(H4)) as
+    P . D . Sylvester . D: D negates positions with a base-4 digit equal to 3 (product over digits), P swaps the two bits of
+    every base-4 digit of the output index.  Check the sign rule and the placement map the kernels use against the matrix."""
+    H = O.build_hadamard(G).astype(np.float64)                        # unnormalised +-1 entries
+    H = np.sign(H)
+    logg = G.bit_length() - 1
+    S = np.array([[1.0]])
+    for _ in range(logg):
+        S = np.kron(S, np.array([[1.0, 1.0], [1.0, -1.0]]))
+    pos = np.arange(G)
+    sign = np.array([-1.0 if (emu.emu_hadamard_sign(G, int(p) // 8, int(p) % 8) >> 31) else 1.0 for p in pos])
+    digits3 = np.ones(G)
+    for d in range(logg // 2):
+        digits3 *= np.where(((pos >> (2 * d)) & 3) == 3, -1.0, 1.0)
+    np.testing.assert_array_equal(sign, digits3)
+    # output p of D.S.D lands at swap_bit_pairs(p): bits (0,1) are exchanged in registers by hadamard_warp, the rest by hadamard_dest
+    swap = np.zeros(G, dtype=np.int64)
+    for p in pos:
+        q = 0
+        for d in range(logg // 2):
+            dig = (p >> (2 * d)) & 3
+            q |= (((dig & 1) << 1) | (dig >> 1)) << (2 * d)
+        swap[p] = q
+    M = np.zeros((G, G))
+    M[swap, :] = (sign[:, None] * S * sign[None, :])
+    np.testing.assert_array_equal(M, H)
+    for p in range(0, G, 4):
+        lane, half = p // 8, (p % 8) // 4
+        dest = emu.emu_hadamard_dest(G, lane, half)
+        assert dest == (swap[p] & ~3) and dest % 4 == 0, (p, dest, swap[p])
