@@ -328,12 +328,18 @@ def linear_small_m(x: torch.Tensor, wq_nk: torch.Tensor, sw, zp=None, bias=None)
 
 
 _WORKSPACES: dict = {}
+_RETIRED_WORKSPACES: list = []
 
 
 def _workspace(dev, nbytes):
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            # a captured CUDA graph may still hold the old pointer: outgrown workspaces are kept alive, never freed
+            # (sizes grow geometrically below, so this is a handful of buffers per stream at most)
+            _RETIRED_WORKSPACES.append(ws)
+            nbytes = max(nbytes, 2 * ws.numel())
         # zero-filled: the first 4 KB hold the fused kernel's cross-CTA strip counters, which every launch leaves at zero
         ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
         _WORKSPACES[key] = ws
