@@ -194,3 +194,19 @@ def test_enum_values_match_the_header():
     for name in ("SDNQ_F32", "SDNQ_BF16", "SDNQ_F16", "SDNQ_I8", "SDNQ_U8", "SDNQ_F8E4M3", "SDNQ_I32",
                  "SDNQ_W_INT", "SDNQ_W_MINIFLOAT", "SDNQ_W_FP8_E4M3FN", "SDNQ_W_FP8_E5M2"):
         assert values[name] == getattr(_lib, name), name
+
+
+def test_plain_c_client_links_and_runs(lib, tmp_path):
+    """include/sdnq_b200.h is valid C99 (-pedantic -Werror), and a program with no torch / CUDA headers links against the
+    library and gets status codes + messages back (tests/c_abi/c_client.c; every call returns before touching CUDA)."""
+    import subprocess
+
+    from sdnq_b200 import _lib
+    exe = str(tmp_path / "c_client")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c_abi", "c_client.c"), "-o", exe, "-L", libdir, "-lsdnq_b200", f"-Wl,-rpath,{libdir}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "0 failure(s)" in r.stdout, r.stdout + r.stderr
