@@ -210,3 +210,35 @@ def test_plain_c_client_links_and_runs(lib, tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "0 failure(s)" in r.stdout, r.stdout + r.stderr
+
+
+def test_last_error_is_per_thread(lib):
+    """exported functions must be callable from several Python threads; the error string is thread-local,
+    so concurrent failing calls never see each other's message."""
+    import threading
+
+    from sdnq_b200._lib import WeightFormat
+    wide = WeightFormat(0, 12, 0, 0, 0, 1)
+    start = threading.Barrier(4)
+    bad = []
+
+    def worker(kind):
+        start.wait()
+        for _ in range(2000):
+            if kind % 2:
+                rc = lib.sdnq_b200_unpack(ctypes.c_void_p(16), ctypes.byref(wide), ctypes.c_void_p(16), 3, 8, None)
+                want = b"8 bits"
+            else:
+                rc = lib.sdnq_b200_rows_to_nchw(ctypes.c_void_p(16), ctypes.c_void_p(16), 3, 1, 64, 64, None)
+                want = b"2 or 4 bytes"
+            msg = lib.sdnq_b200_last_error()
+            if rc >= 0 or want not in msg:
+                bad.append((kind, rc, msg))
+                return
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not bad, bad[:3]
