@@ -20,6 +20,9 @@
 #pragma once
 #include "common.cuh"
 
+// SDNQ_HOST_EMU (tests/host_emu only): the three warp primitives below (cvt pack, mma.sync, movmatrix) are replaced by host
+// models running 32 lock-stepped threads, so tests/test_device_arithmetic_on_host.py can execute Rotation<T>::apply on a CPU.
+
 namespace sdnq {
 namespace hadtc {
 
@@ -83,36 +86,56 @@ template <typename T> struct Half16;
 template <> struct Half16<__nv_bfloat16> {
     static constexpr uint32_t kOne = 0x3F80u, kMinusOne = 0xBF80u;
     __device__ static __forceinline__ uint32_t pack(float lo, float hi) {
+#ifdef SDNQ_HOST_EMU
+        return ::sdnq_emu::pack16x2(false, lo, hi);
+#else
         uint32_t r;
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
         return r;
+#endif
     }
     __device__ static __forceinline__ float lo(uint32_t w) { return __uint_as_float(w << 16); }
     __device__ static __forceinline__ float hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
     __device__ static __forceinline__ void mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+#ifdef SDNQ_HOST_EMU
+        ::sdnq_emu::mma_m16n8k16(false, d, a0, a1, a2, a3, b0, b1);
+#else
         asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+#endif
     }
 };
 template <> struct Half16<__half> {
     static constexpr uint32_t kOne = 0x3C00u, kMinusOne = 0xBC00u;
     __device__ static __forceinline__ uint32_t pack(float lo, float hi) {
+#ifdef SDNQ_HOST_EMU
+        return ::sdnq_emu::pack16x2(true, lo, hi);
+#else
         uint32_t r;
         asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
         return r;
+#endif
     }
     __device__ static __forceinline__ float lo(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w & 0xFFFFu))); }
     __device__ static __forceinline__ float hi(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w >> 16))); }
     __device__ static __forceinline__ void mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+#ifdef SDNQ_HOST_EMU
+        ::sdnq_emu::mma_m16n8k16(true, d, a0, a1, a2, a3, b0, b1);
+#else
         asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+#endif
     }
 };
 
 __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+#ifdef SDNQ_HOST_EMU
+    return ::sdnq_emu::movmatrix_trans(a);
+#else
     uint32_t d;
     asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
     return d;
+#endif
 }
 
 // Per-lane constant fragments: two 16-byte loads per thread from the table.

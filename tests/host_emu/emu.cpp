@@ -80,3 +80,57 @@ uint32_t emu_hadamard_sign(int G, int lane, int j) {
     }
 }
 }
+
+// ---------------------------------------------------------------- warp-level code on 32 lock-stepped host threads
+#include "../../sdnq_b200/csrc/hadamard_tc.cuh"
+
+namespace {
+template <typename T>
+void rotate_tc(int G, const uint16_t* in, uint16_t* out, float* lane_max, int64_t chunks) {
+    sdnq_emu::run_warp([&](int lane) {
+        hadtc::Rotation<T> rot;
+        rot.init(G, lane);
+        const float factor = hadamard_factor<T>(G);
+        for (int64_t c = 0; c < chunks; ++c) {
+            // the kernels' two coalesced 8-byte accesses: elements [4l, 4l+4) and [128+4l, 128+4l+4) of the 256-chunk
+            const uint16_t* p = in + 256 * c;
+            uint4 raw;
+            std::memcpy(&raw.x, p + 4 * lane, 8);
+            std::memcpy(&raw.z, p + 128 + 4 * lane, 8);
+            const float m = rot.apply(raw, factor);
+            std::memcpy(out + 256 * c + 4 * lane, &raw.x, 8);
+            std::memcpy(out + 256 * c + 128 + 4 * lane, &raw.z, 8);
+            lane_max[32 * c + lane] = m;
+        }
+    });
+}
+
+template <typename T>
+void rotate_butterfly(int G, const float* in, float* out, int64_t chunks) {
+    sdnq_emu::run_warp([&](int lane) {
+        const float factor = hadamard_factor<T>(G);
+        for (int64_t c = 0; c < chunks; ++c) {
+            float v[8];
+            for (int i = 0; i < 8; ++i) v[i] = in[256 * c + 8 * lane + i];
+            hadamard_warp_dyn(G, v, factor);
+            for (int half = 0; half < 2; ++half) {
+                const int dst = hadamard_dest_dyn(G, lane, half);
+                for (int i = 0; i < 4; ++i) out[256 * c + dst + i] = v[4 * half + i];
+            }
+        }
+    });
+}
+}  // namespace
+
+extern "C" {
+// Rotation<T>::apply (tensor-core path of K2 / rotated K3) over `chunks` 256-element chunks of 16-bit values
+void emu_rotate_tc(int f16, int G, const uint16_t* in, uint16_t* out, float* lane_max, int64_t chunks) {
+    if (f16) rotate_tc<__half>(G, in, out, lane_max, chunks);
+    else rotate_tc<__nv_bfloat16>(G, in, out, lane_max, chunks);
+}
+// hadamard_warp<G> + hadamard_dest<G> (shuffle-butterfly path), values scaled by the factor in T, not yet rounded to T
+void emu_rotate_butterfly(int f16, int G, const float* in, float* out, int64_t chunks) {
+    if (f16) rotate_butterfly<__half>(G, in, out, chunks);
+    else rotate_butterfly<__nv_bfloat16>(G, in, out, chunks);
+}
+}

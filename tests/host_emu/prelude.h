@@ -10,6 +10,9 @@
 #include <vector_types.h>
 #include <vector_functions.h>
 
+#define SDNQ_HOST_EMU 1
+#include "warp.h"
+
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 // PRMT in its default mode: result byte i = byte (selector nibble i & 7) of the 8-byte pool {y:x}; nibble bit 3 replicates the sign
@@ -28,6 +31,18 @@ static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 static inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(std::fma(a.x, b.x, c.x), std::fma(a.y, b.y, c.y)); }
-// never executed on the host (single "lane"): identity
-template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
-static const uint3 threadIdx = {0, 0, 0};
+static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz(static_cast<unsigned>(v)); }
+// xor-shuffle across the 32 lock-stepped host lanes (warp.h); outside run_warp() nothing calls it
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m) {
+    static_assert(sizeof(T) == 4, "32-bit shuffles only");
+    const int lane = sdnq_emu::t_lane;
+    std::memcpy(&sdnq_emu::g_xchg[lane][0], &v, 4);
+    sdnq_emu::warp_sync();
+    T r;
+    std::memcpy(&r, &sdnq_emu::g_xchg[lane ^ m][0], 4);
+    sdnq_emu::warp_sync();
+    return r;
+}
+// threadIdx.x & 31 is the lane in the device code: hand it the lane of the calling host thread
+struct EmuThreadIdx { struct X { operator int() const { return sdnq_emu::t_lane; } } x; };
+static const EmuThreadIdx threadIdx = {};

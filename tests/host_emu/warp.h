@@ -1,0 +1,97 @@
+// A 32-lane lock-step warp on the host: each lane is a pthread, collectives meet at a barrier.  Host models of the three
+// PTX warp primitives hadamard_tc.cuh uses, following the PTX ISA fragment layouts (g = lane >> 2, q = lane & 3):
+//   mma.sync.m16n8k16 row.col   A 16x16: a0 = (row g,   k 2q,2q+1)  a1 = (row g+8, k 2q,2q+1)  a2 = (row g, k 2q+8,2q+9)  a3 = (row g+8, k 2q+8,2q+9)
+//                               B 16x8 : b0 = (k 2q,2q+1,   col g)  b1 = (k 2q+8,2q+9, col g)
+//                               C/D 16x8: d0,d1 = (row g, col 2q,2q+1)   d2,d3 = (row g+8, col 2q,2q+1)
+//   movmatrix.m8n8.trans.b16    lane holds (row g, cols 2q,2q+1) of an 8x8 matrix of 16-bit elements; result = its transpose, same layout
+//   cvt.rn.{bf16x2,f16x2}.f32   two floats -> packed pair, round to nearest even (low half = first operand `lo`)
+// Products of 16-bit values are exact in double; the sum is formed in double and rounded once to f32, which equals the tensor
+// core's f32 accumulation whenever the exact sum is representable (the tests use such inputs for their bit-exact checks).
+#pragma once
+#include <pthread.h>
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace sdnq_emu {
+
+inline thread_local int t_lane = 0;
+inline pthread_barrier_t g_barrier;
+inline uint32_t g_xchg[32][6];
+
+inline void warp_sync() { pthread_barrier_wait(&g_barrier); }
+
+inline float half16_to_float(bool f16, uint32_t bits16) {
+    if (f16) {
+        __half_raw r; r.x = static_cast<unsigned short>(bits16);
+        return __half2float(__half(r));
+    }
+    uint32_t u = bits16 << 16; float f; std::memcpy(&f, &u, 4); return f;
+}
+
+inline uint32_t pack16x2(bool f16, float lo, float hi) {
+    if (f16) {
+        const __half a = __float2half_rn(lo), b = __float2half_rn(hi);
+        return uint32_t(__half_raw(a).x) | (uint32_t(__half_raw(b).x) << 16);
+    }
+    const __nv_bfloat16 a = __float2bfloat16_rn(lo), b = __float2bfloat16_rn(hi);
+    return uint32_t(__nv_bfloat16_raw(a).x) | (uint32_t(__nv_bfloat16_raw(b).x) << 16);
+}
+
+inline void mma_m16n8k16(bool f16, float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    const int lane = t_lane, g = lane >> 2, q = lane & 3;
+    uint32_t* mine = g_xchg[lane];
+    mine[0] = a0; mine[1] = a1; mine[2] = a2; mine[3] = a3; mine[4] = b0; mine[5] = b1;
+    warp_sync();
+    auto A = [&](int row, int k) {                       // element (row, k) of the 16x16 A operand
+        const int src = (row & 7) * 4 + ((k & 7) >> 1);
+        const int reg = (row >> 3) + 2 * (k >> 3);
+        return half16_to_float(f16, (g_xchg[src][reg] >> (16 * (k & 1))) & 0xFFFFu);
+    };
+    auto B = [&](int k, int col) {                       // element (k, col) of the 16x8 B operand
+        const int src = col * 4 + ((k & 7) >> 1);
+        return half16_to_float(f16, (g_xchg[src][4 + (k >> 3)] >> (16 * (k & 1))) & 0xFFFFu);
+    };
+    for (int i = 0; i < 4; ++i) {
+        const int row = g + 8 * (i >> 1), col = 2 * q + (i & 1);
+        double acc = d[i];
+        for (int k = 0; k < 16; ++k) acc += double(A(row, k)) * double(B(k, col));
+        d[i] = static_cast<float>(acc);
+    }
+    warp_sync();                                         // everyone has read before the exchange area is reused
+}
+
+inline uint32_t movmatrix_trans(uint32_t a) {
+    const int lane = t_lane, g = lane >> 2, q = lane & 3;
+    g_xchg[lane][0] = a;
+    warp_sync();
+    uint32_t r = 0;
+    for (int e = 0; e < 2; ++e) {                        // output element (row g, col 2q+e) = input element (row 2q+e, col g)
+        const int row = 2 * q + e, col = g;
+        const uint32_t w = g_xchg[row * 4 + (col >> 1)][0];
+        r |= ((w >> (16 * (col & 1))) & 0xFFFFu) << (16 * e);
+    }
+    warp_sync();
+    return r;
+}
+
+// run fn(lane) on 32 lock-stepped lanes
+template <typename F>
+void run_warp(F&& fn) {
+    pthread_barrier_init(&g_barrier, nullptr, 32);
+    struct Arg { F* fn; int lane; } args[32];
+    pthread_t th[32];
+    for (int l = 0; l < 32; ++l) {
+        args[l] = {&fn, l};
+        pthread_create(&th[l], nullptr, [](void* p) -> void* {
+            Arg* a = static_cast<Arg*>(p);
+            t_lane = a->lane;
+            (*a->fn)(a->lane);
+            return nullptr;
+        }, &args[l]);
+    }
+    for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
+    pthread_barrier_destroy(&g_barrier);
+}
+
+}  // namespace sdnq_emu

@@ -32,7 +32,7 @@ W_INT, W_MINIFLOAT, W_E4M3, W_E5M2 = range(4)
 def emu(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("host_emu") / "libsdnq_emu.so")
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-w", "-include", os.path.join(EMU_DIR, "prelude.h"), "-I", cuda_inc,
+    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-w", "-pthread", "-include", os.path.join(EMU_DIR, "prelude.h"), "-I", cuda_inc,
            os.path.join(EMU_DIR, "emu.cpp"), "-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, "host build of the device headers failed:\n" + r.stderr[-3000:]
@@ -216,3 +216,73 @@ def test_h4_family_sign_and_placement_rules(emu, G):
         lane, half = p // 8, (p % 8) // 4
         dest = emu.emu_hadamard_dest(G, lane, half)
         assert dest == (swap[p] & ~3) and dest % 4 == 0, (p, dest, swap[p])
+
+
+# ---- warp-level code on 32 lock-stepped host threads (tests/host_emu/warp.h: host models of mma.sync m16n8k16, movmatrix, cvt pack,
+# shfl.xor following the PTX fragment layouts).  Inputs are small integers times a power of two, so every partial sum is exact in
+# f32 and the tensor-core / butterfly / reference orders of summation must agree bit for bit.
+def _exact_chunks(rng, chunks):
+    x = rng.integers(-64, 65, size=(chunks, 256)).astype(np.float32) * np.exp2(rng.integers(-3, 4, size=(chunks, 1))).astype(np.float32)
+    x[0, :] = 0.0
+    x[0, 5] = 1.0                                                    # a unit impulse: one column of the matrix
+    return x
+
+
+def _bind_rotations(emu):
+    emu.emu_rotate_tc.argtypes = [ctypes.c_int, ctypes.c_int, P, P, P, ctypes.c_int64]
+    emu.emu_rotate_tc.restype = None
+    emu.emu_rotate_butterfly.argtypes = [ctypes.c_int, ctypes.c_int, P, P, ctypes.c_int64]
+    emu.emu_rotate_butterfly.restype = None
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
+@pytest.mark.parametrize("G", [4, 8, 16, 32, 64, 128, 256])
+def test_tensor_core_rotation_on_a_host_warp(emu, G, dtype):
+    """hadtc::Rotation<T>::apply -- the default rotation of K2 (FLUX: fp8 + Hadamard-256) and of the rotated K3 -- executed from
+    the kernel source with its compile-time fragment tables, against the reference rotation (quant_utils.py:193-209)."""
+    _bind_rotations(emu)
+    f16 = dtype == "float16"
+    rng = np.random.default_rng(G + f16)
+    chunks = 6
+    x = _exact_chunks(rng, chunks)
+    bits = (x.astype(np.float16).view(np.uint16) if f16 else O.bf16_bits(x).astype(np.uint16)).reshape(-1)
+    out = np.empty_like(bits)
+    lane_max = np.empty(32 * chunks, dtype=np.float32)
+    emu.emu_rotate_tc(int(f16), G, _ptr(bits), _ptr(out), _ptr(lane_max), chunks)
+    got = (out.view(np.float16).astype(np.float32) if f16 else O.from_bf16_bits(out)).reshape(chunks, 256)
+    want = O.rotate_hadamard(x, G, dtype)
+    np.testing.assert_array_equal(got, want)
+    # the value each lane returns: max |rotated| over its eight outputs before the rounding to T
+    exact = (x.reshape(-1, G).astype(np.float64) @ O.hadamard_matrix(G, dtype).astype(np.float64)).reshape(chunks, 256)
+    own = np.concatenate([exact[:, :128].reshape(chunks, 32, 4), exact[:, 128:].reshape(chunks, 32, 4)], axis=2)
+    np.testing.assert_array_equal(lane_max.reshape(chunks, 32), np.abs(own).max(axis=2).astype(np.float32))
+
+
+@pytest.mark.parametrize("G", [4, 8, 16, 32, 64, 128, 256])
+def test_butterfly_rotation_on_a_host_warp(emu, G):
+    """hadamard_warp<G> + hadamard_dest<G>: the shuffle-butterfly rotation (f32 activations, the gather conv quantiser, A/B knob)"""
+    _bind_rotations(emu)
+    rng = np.random.default_rng(100 + G)
+    chunks = 4
+    x = _exact_chunks(rng, chunks)
+    out = np.empty_like(x)
+    emu.emu_rotate_butterfly(0, G, _ptr(np.ascontiguousarray(x)), _ptr(out), chunks)
+    np.testing.assert_array_equal(O.bf16_round(out), O.rotate_hadamard(x, G, "bfloat16"))
+
+
+def test_tensor_core_rotation_on_random_activations(emu):
+    """random bf16 activations: sums are no longer exact, so allow the one-ulp ties the GPU test allows (tests/test_kernels_gpu.py)"""
+    _bind_rotations(emu)
+    rng = np.random.default_rng(7)
+    chunks = 16
+    x = O.bf16_round(rng.standard_normal((chunks, 256)).astype(np.float32))
+    bits = O.bf16_bits(x).astype(np.uint16).reshape(-1)
+    out = np.empty_like(bits)
+    lane_max = np.empty(32 * chunks, dtype=np.float32)
+    emu.emu_rotate_tc(0, 256, _ptr(bits), _ptr(out), _ptr(lane_max), chunks)
+    got = O.from_bf16_bits(out).reshape(chunks, 256)
+    want = O.rotate_hadamard(x, 256, "bfloat16")
+    ulp = np.exp2(np.floor(np.log2(np.maximum(np.abs(want), 1e-30))) - 7)
+    # one bf16 ulp of the result, or -- where the 256 terms cancel to almost nothing -- the f32 accumulation noise of sums of size ~16
+    assert (np.abs(got - want) <= np.maximum(ulp, 4e-6)).all()
+    assert (got != want).mean() < 0.01
