@@ -233,6 +233,21 @@ SDNQ_API int sdnq_b200_linear_small_m(const void* x, int x_dtype, int64_t ldx, c
                              const float* zp, const void* bias, int bias_dtype, void* out,
                              int64_t M, int64_t N, int64_t K, void* stream);
 
+/* ---- K5p small-M Linear straight from the STORED weight (packed sub-byte integers, minifloats, fp8 / int8; row-wise or
+ *      group-wise scales; optional zero points): the rows < 32 branch (layers/linear/forward.py:24-26 with
+ *      use_quantized_matmul=False, linear_int8.py:102-103 otherwise: SDNQDequantizer.__call__ then F.linear) without writing the
+ *      dequantised weight:   out[m,n] = sum_k x[m,k] * cast_T(q[n,k] * s[n,k/g] (+ zp[n,k/g]))  + bias
+ *   weight      the stored tensor as the reference keeps it: packed along the flattened [N,K] weight (packed_int/pack.py), or
+ *               plain 1-byte codes [N,K];  fmt as for sdnq_b200_unpack (1..8 bits, word_bytes 1)
+ *   scale / zero_point   f32 [N, K/group_size] (zero_point NULL for symmetric formats); group_size <= 0 or >= K: row-wise;
+ *               otherwise a multiple of 8 dividing K.  Every weight is rounded to the activation dtype before the product,
+ *               exactly the value the reference's dequantised weight holds (dequantizer.py:15-84).
+ *   bias        NULL, [N] (bias_ld = 0) or [M,N] (bias_ld = row stride; e.g. the SVD term (x @ svd_down^T) @ svd_up^T + bias)
+ *   x, out      [M,K] / [M,N] bf16 or f16 (x_dtype), 1 <= M <= 32, K % 16 == 0, ldx % 8 == 0.  Accumulation f32 on the tensor cores. */
+SDNQ_API int sdnq_b200_linear_small_m_packed(const void* x, int x_dtype, int64_t ldx, const void* weight, const sdnq_weight_format* fmt,
+                                             const float* scale, const float* zero_point, int64_t group_size, const void* bias,
+                                             int bias_dtype, int64_t bias_ld, void* out, int64_t M, int64_t N, int64_t K, void* stream);
+
 /* The same Linear as ONE kernel launch: the GEMM kernel row-quantises the activations itself (every CTA takes a share
  * of the rows: bulk copy to shared memory, warp-reduction amax, quantise, codes + scales to the workspace) and its TMA
  * producers pick the quantised strips up through release/acquire strip counters -- linear_int8.py:14-22 + 100-125 /

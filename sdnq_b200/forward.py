@@ -137,8 +137,35 @@ def _dequant_linear(layer, input, skip_quantized_matmul):
     return torch.nn.functional.linear(input, _dequant_weight_overlapped(layer, input, skip_quantized_matmul), layer.bias)
 
 
+def _small_m_packed_ok(self, input) -> bool:
+    """K5p applies to rows < 32 of a Linear whose weight is stored packed and / or with group-wise scales (no SVD, no codebook,
+    no tensor-wise scale, 2..8 bits, scale groups that are multiples of 8 columns) and 16-bit activations: the stored bytes are read
+    once instead of dequantise + GEMM.  Opt-in this round (SDNQ_B200_SMALL_M_PACKED=1): the kernel is validated against the oracle
+    on the host emulator (tests/test_device_arithmetic_on_host.py); it becomes the default after its first run on hardware."""
+    if os.environ.get("SDNQ_B200_SMALL_M_PACKED", "0") in ("0", "false", "no", ""):
+        return False
+    d = self.sdnq_dequantizer
+    if (d.use_codebook or d.group_size == -2 or self.svd_up is not None or self.weight.ndim > 3 or d.is_conv
+            or input.dtype not in (torch.bfloat16, torch.float16) or input.numel() == 0):
+        return False
+    info = dtype_dict[d.weights_dtype]
+    N, K = d.matmul_nk()
+    if not 2 <= info["num_bits"] <= 8 or K % 16 != 0 or input.shape[-1] != K:
+        return False
+    per_row = self.scale.numel() // N
+    return per_row >= 1 and self.scale.numel() == N * per_row and K % per_row == 0 and (K // per_row) % 8 == 0
+
+
+def _small_m_packed_linear(self, x):
+    d = self.sdnq_dequantizer
+    N, K = d.matmul_nk()
+    return ops.linear_small_m_packed(x, self.weight, d.weights_dtype, self.scale, self.zero_point, N, K, bias=self.bias)
+
+
 @torch.no_grad()
 def quantized_linear_forward(self, input: torch.Tensor) -> torch.Tensor:
+    if (input.numel() // max(input.shape[-1], 1) < SMALL_M and not self.sdnq_dequantizer.use_hadamard and _small_m_packed_ok(self, input)):
+        return _small_m_packed_linear(self, input)
     return _dequant_linear(self, input, skip_quantized_matmul=False)
 
 
@@ -161,6 +188,12 @@ def _w8a8_forward(self, input: torch.Tensor) -> torch.Tensor:
             if d.use_hadamard:
                 x = ops.act_quant(input, d.quantized_matmul_dtype, hadamard_group=d.hadamard_group_size, want_x_rot=True)[4].view(input.shape)
             return ops.linear_small_m(x, op.wq, op.sw, zp=op.zp, bias=self.bias)
+        if (d.re_quantize_for_matmul or d.is_packed) and _small_m_packed_ok(self, input):
+            # packed / group-wise weights: K5p reads the stored bytes once (rotated layers: rotate the activation, as above)
+            x = input
+            if d.use_hadamard:
+                x = ops.act_quant(input, d.quantized_matmul_dtype, hadamard_group=d.hadamard_group_size, want_x_rot=True)[4].view(input.shape)
+            return _small_m_packed_linear(self, x)
         return _dequant_linear(self, input, skip_quantized_matmul=True)
     op = matmul_operand(self)
     mm = d.quantized_matmul_dtype

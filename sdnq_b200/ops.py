@@ -327,6 +327,37 @@ def linear_small_m(x: torch.Tensor, wq_nk: torch.Tensor, sw, zp=None, bias=None)
     return out.view(*x.shape[:-1], N)
 
 
+def linear_small_m_packed(x: torch.Tensor, weight: torch.Tensor, weights_dtype: str, scale: torch.Tensor, zero_point, N: int, K: int,
+                          bias: torch.Tensor | None = None) -> torch.Tensor:
+    """K5p: x [..., K] with fewer than 33 rows times the *stored* weight (packed sub-byte / minifloat / 8-bit codes of the flattened
+    [N,K] tensor, scale / zero_point [N, K/g] in any shape with that many elements).  bias None | [N] | [M,N]."""
+    _require_cuda(x, weight, scale)
+    e = dtype_dict[weights_dtype]
+    w = weight.contiguous() if e["is_packed"] else physical_nk(weight)
+    scale = scale.to(torch.float32).contiguous()
+    if zero_point is not None:
+        zero_point = zero_point.to(torch.float32).contiguous()
+    per_row = scale.numel() // N
+    if per_row < 1 or scale.numel() != N * per_row or K % per_row != 0:
+        raise _lib.SDNQKernelError(f"linear_small_m_packed: {scale.numel()} scales do not tile a [{N},{K}] weight")
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1 or x2.stride(0) % 8 != 0 or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    out = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    bias_ld, bias_code = 0, SDNQ_F32
+    if bias is not None:
+        bias = bias.contiguous()
+        bias_code = dtype_code(bias.dtype)
+        if bias.ndim == 2 and bias.shape[0] != 1:
+            bias_ld = bias.stride(0)
+    fmt = weight_format(weights_dtype, w)
+    with torch.cuda.device(x.device):
+        check(_lib.load().sdnq_b200_linear_small_m_packed(_ptr(x2), dtype_code(x2.dtype), x2.stride(0), _ptr(w), fmt, _ptr(scale), _ptr(zero_point),
+                                                          K // per_row, _ptr(bias), bias_code, bias_ld, _ptr(out), M, N, K, _stream(x)))
+    return out.view(*x.shape[:-1], N)
+
+
 _WORKSPACES: dict = {}
 _RETIRED_WORKSPACES: list = []
 

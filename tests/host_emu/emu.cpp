@@ -134,3 +134,34 @@ void emu_rotate_butterfly(int f16, int G, const float* in, float* out, int64_t c
     else rotate_butterfly<__nv_bfloat16>(G, in, out, chunks);
 }
 }
+
+// ---------------------------------------------------------------- a whole kernel: K5p (gemv_packed_kernel.cuh) on emulated CTAs
+#include "../../sdnq_b200/csrc/gemv_packed_kernel.cuh"
+
+namespace {
+template <typename T, int BITS>
+void run_gemv_packed(const gemvp::Args& a, int grid) {
+    const int mb = (a.M + 7) / 8;
+    static float s_red[(gemvp::kWarps - 1) * 4 * 4 * 32];        // the kernel's __shared__ array (CTAs run one at a time)
+    sdnq_emu::run_grid(grid, gemvp::kThreads, [&] {
+        if (mb <= 1) gemvp::body<T, BITS, 1>(a, s_red);
+        else if (mb == 2) gemvp::body<T, BITS, 2>(a, s_red);
+        else gemvp::body<T, BITS, 4>(a, s_red);
+    });
+}
+}  // namespace
+
+extern "C" int emu_gemv_packed(const void* x, int x_dtype, int64_t ldx, const void* weight, const sdnq_weight_format* fmt,
+                               const float* scale, const float* zero_point, int64_t group_size, const void* bias, int bias_dtype,
+                               int64_t bias_ld, void* out, int64_t M, int64_t N, int64_t K, int grid) {
+    WFormat f;
+    int rc = make_wformat(fmt, &f);
+    if (rc != SDNQ_OK) return rc;
+    const int64_t group = (group_size <= 0 || group_size >= K) ? K : group_size;
+    if (group % 8 != 0 || K % group != 0 || K % 16 != 0 || M < 1 || M > 32) return -1;
+    gemvp::Args a{x, ldx, reinterpret_cast<const uint8_t*>(weight), scale, zero_point, bias, bias_dtype, bias_ld, out,
+                  int(M), int(N), int(K), int(group), int(K / group), f};
+    if (x_dtype == SDNQ_BF16) { SDNQ_DISPATCH_BITS(f.bits, run_gemv_packed<__nv_bfloat16, BITS>(a, grid)); }
+    else { SDNQ_DISPATCH_BITS(f.bits, run_gemv_packed<__half, BITS>(a, grid)); }
+    return 0;
+}

@@ -35,14 +35,19 @@ static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz(static_cast<
 // xor-shuffle across the 32 lock-stepped host lanes (warp.h); outside run_warp() nothing calls it
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m) {
     static_assert(sizeof(T) == 4, "32-bit shuffles only");
-    const int lane = sdnq_emu::t_lane;
-    std::memcpy(&sdnq_emu::g_xchg[lane][0], &v, 4);
+    const int lane = sdnq_emu::lane_id();
+    std::memcpy(&sdnq_emu::xchg()[lane][0], &v, 4);
     sdnq_emu::warp_sync();
     T r;
-    std::memcpy(&r, &sdnq_emu::g_xchg[lane ^ m][0], 4);
+    std::memcpy(&r, &sdnq_emu::xchg()[lane ^ m][0], 4);
     sdnq_emu::warp_sync();
     return r;
 }
-// threadIdx.x & 31 is the lane in the device code: hand it the lane of the calling host thread
-struct EmuThreadIdx { struct X { operator int() const { return sdnq_emu::t_lane; } } x; };
+// threadIdx.x / blockIdx.x / gridDim.x of the calling host thread (warp.h: run_grid)
+struct EmuThreadIdx { struct X { operator int() const { return sdnq_emu::t_tid; } } x; };
+struct EmuBlockIdx { struct X { operator int() const { return sdnq_emu::g_block; } } x; };
+struct EmuGridDim { struct X { operator int() const { return sdnq_emu::g_grid; } } x; };
 static const EmuThreadIdx threadIdx = {};
+static const EmuBlockIdx blockIdx = {};
+static const EmuGridDim gridDim = {};
+static inline void __syncthreads() { sdnq_emu::cta_sync(); }

@@ -1,4 +1,4 @@
-// A 32-lane lock-step warp on the host: each lane is a pthread, collectives meet at a barrier.  Host models of the three
+// Lock-step warps / CTAs on the host: every CUDA thread is a pthread, warp collectives and __syncthreads meet at barriers.  Host models of the three
 // PTX warp primitives hadamard_tc.cuh uses, following the PTX ISA fragment layouts (g = lane >> 2, q = lane & 3):
 //   mma.sync.m16n8k16 row.col   A 16x16: a0 = (row g,   k 2q,2q+1)  a1 = (row g+8, k 2q,2q+1)  a2 = (row g, k 2q+8,2q+9)  a3 = (row g+8, k 2q+8,2q+9)
 //                               B 16x8 : b0 = (k 2q,2q+1,   col g)  b1 = (k 2q+8,2q+9, col g)
@@ -15,11 +15,16 @@
 
 namespace sdnq_emu {
 
-inline thread_local int t_lane = 0;
-inline pthread_barrier_t g_barrier;
-inline uint32_t g_xchg[32][6];
+constexpr int kMaxWarps = 8;
+inline thread_local int t_tid = 0;                    // threadIdx.x of the calling host thread
+inline int g_block = 0, g_grid = 1;                   // blockIdx.x / gridDim.x (CTAs run one after another)
+inline pthread_barrier_t g_warp_barrier[kMaxWarps], g_cta_barrier;
+inline uint32_t g_xchg_all[kMaxWarps][32][6];
 
-inline void warp_sync() { pthread_barrier_wait(&g_barrier); }
+inline int lane_id() { return t_tid & 31; }
+inline uint32_t (*xchg())[6] { return g_xchg_all[t_tid >> 5]; }
+inline void warp_sync() { pthread_barrier_wait(&g_warp_barrier[t_tid >> 5]); }
+inline void cta_sync() { pthread_barrier_wait(&g_cta_barrier); }
 
 inline float half16_to_float(bool f16, uint32_t bits16) {
     if (f16) {
@@ -39,7 +44,8 @@ inline uint32_t pack16x2(bool f16, float lo, float hi) {
 }
 
 inline void mma_m16n8k16(bool f16, float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    const int lane = t_lane, g = lane >> 2, q = lane & 3;
+    const int lane = lane_id(), g = lane >> 2, q = lane & 3;
+    uint32_t (*g_xchg)[6] = xchg();
     uint32_t* mine = g_xchg[lane];
     mine[0] = a0; mine[1] = a1; mine[2] = a2; mine[3] = a3; mine[4] = b0; mine[5] = b1;
     warp_sync();
@@ -62,7 +68,8 @@ inline void mma_m16n8k16(bool f16, float (&d)[4], uint32_t a0, uint32_t a1, uint
 }
 
 inline uint32_t movmatrix_trans(uint32_t a) {
-    const int lane = t_lane, g = lane >> 2, q = lane & 3;
+    const int lane = lane_id(), g = lane >> 2, q = lane & 3;
+    uint32_t (*g_xchg)[6] = xchg();
     g_xchg[lane][0] = a;
     warp_sync();
     uint32_t r = 0;
@@ -75,23 +82,37 @@ inline uint32_t movmatrix_trans(uint32_t a) {
     return r;
 }
 
-// run fn(lane) on 32 lock-stepped lanes
+// run fn() as a grid of `grid` CTAs of `threads` lock-stepped host threads each (CTAs one after another); the device code reads
+// threadIdx.x / blockIdx.x / gridDim.x through the stand-ins in prelude.h
+template <typename F>
+void run_grid(int grid, int threads, F&& fn) {
+    const int warps = (threads + 31) / 32;
+    g_grid = grid;
+    for (int blk = 0; blk < grid; ++blk) {
+        g_block = blk;
+        pthread_barrier_init(&g_cta_barrier, nullptr, threads);
+        for (int w = 0; w < warps; ++w) pthread_barrier_init(&g_warp_barrier[w], nullptr, 32);
+        struct Arg { F* fn; int tid; } args[kMaxWarps * 32];
+        pthread_t th[kMaxWarps * 32];
+        for (int t = 0; t < threads; ++t) {
+            args[t] = {&fn, t};
+            pthread_create(&th[t], nullptr, [](void* p) -> void* {
+                Arg* a = static_cast<Arg*>(p);
+                t_tid = a->tid;
+                (*a->fn)();
+                return nullptr;
+            }, &args[t]);
+        }
+        for (int t = 0; t < threads; ++t) pthread_join(th[t], nullptr);
+        pthread_barrier_destroy(&g_cta_barrier);
+        for (int w = 0; w < warps; ++w) pthread_barrier_destroy(&g_warp_barrier[w]);
+    }
+}
+
+// one warp: fn(lane)
 template <typename F>
 void run_warp(F&& fn) {
-    pthread_barrier_init(&g_barrier, nullptr, 32);
-    struct Arg { F* fn; int lane; } args[32];
-    pthread_t th[32];
-    for (int l = 0; l < 32; ++l) {
-        args[l] = {&fn, l};
-        pthread_create(&th[l], nullptr, [](void* p) -> void* {
-            Arg* a = static_cast<Arg*>(p);
-            t_lane = a->lane;
-            (*a->fn)(a->lane);
-            return nullptr;
-        }, &args[l]);
-    }
-    for (int l = 0; l < 32; ++l) pthread_join(th[l], nullptr);
-    pthread_barrier_destroy(&g_barrier);
+    run_grid(1, 32, [&] { fn(lane_id()); });
 }
 
 }  // namespace sdnq_emu

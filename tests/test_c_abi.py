@@ -66,6 +66,16 @@ def test_argument_errors_of_the_conv_and_small_m_entries(lib):
     assert rc == -2 and b"bf16 / f16" in lib.sdnq_b200_last_error()
     rc = lib.sdnq_b200_linear_small_m(P(16), 1, 72, P(16), 3, P(16), None, None, 0, P(16), 4, 64, 72, None)           # K % 16
     assert rc == -2
+    fmt4 = WeightFormat(0, 4, 0, 0, 0, 1)
+    args = lambda M, K, group, fmt=fmt4, ld=0: (P(16), 1, K, P(16), ctypes.byref(fmt), P(16), None, group, None, 0, ld, P(16), M, 64, K, None)  # noqa: E731
+    rc = lib.sdnq_b200_linear_small_m_packed(*args(40, 64, 0))                                                         # M > 32
+    assert rc == -1 and b"M <= 32" in lib.sdnq_b200_last_error()
+    rc = lib.sdnq_b200_linear_small_m_packed(*args(4, 64, 12))                                                         # group not a multiple of 8
+    assert rc == -2 and b"multiple of 8" in lib.sdnq_b200_last_error()
+    rc = lib.sdnq_b200_linear_small_m_packed(*args(4, 64, 0, fmt=WeightFormat(0, 1, 1, 0, 0, 8)))                      # uint1 in int64 words
+    assert rc == -2 and b"int64" in lib.sdnq_b200_last_error()
+    rc = lib.sdnq_b200_linear_small_m_packed(*args(4, 64, 0, ld=8))                                                    # matrix bias narrower than N
+    assert rc == -1 and b"bias_ld" in lib.sdnq_b200_last_error()
     rc = lib.sdnq_b200_rows_to_nchw(P(16), P(16), 3, 1, 64, 64, None)                                                  # 3-byte elements
     assert rc == -1 and b"2 or 4 bytes" in lib.sdnq_b200_last_error()
     geo = Conv2dGeometry(1, 64, 8, 8, 4096, 64, 8, 1, 3, 3, 0, 1, 1, 1, 1, 1)                                           # stride_h = 0

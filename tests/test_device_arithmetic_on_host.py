@@ -10,6 +10,7 @@ proper; this is the CPU-only regression gate for the integer / bit-manipulation 
 import ctypes
 import os
 import subprocess
+import zlib
 
 import numpy as np
 import pytest
@@ -286,3 +287,175 @@ def test_tensor_core_rotation_on_random_activations(emu):
     # one bf16 ulp of the result, or -- where the 256 terms cancel to almost nothing -- the f32 accumulation noise of sums of size ~16
     assert (np.abs(got - want) <= np.maximum(ulp, 4e-6)).all()
     assert (got != want).mean() < 0.01
+
+
+# ---- a whole kernel on emulated CTAs: K5p, the small-M Linear from the stored (packed / grouped) weight (gemv_packed_kernel.cuh).
+# 256 lock-stepped host threads per CTA run the kernel body unchanged; loads, fragment mapping, K-split reduction through
+# "shared memory", tails in N / K / M and the epilogue are all the device source.
+GEMV_CASES = [
+    # weights_dtype, group (0 = row-wise), M, N, K, bias kind, activation dtype
+    ("int4", 0, 4, 40, 208, "vector", "bfloat16"),
+    ("int4", 128, 1, 16, 256, "none", "bfloat16"),
+    ("uint4", 64, 9, 24, 192, "matrix", "bfloat16"),
+    ("int2", 16, 32, 33, 64, "vector", "bfloat16"),
+    ("uint3", 32, 5, 17, 96, "vector", "float16"),
+    ("int5", 0, 2, 8, 80, "none", "bfloat16"),
+    ("uint6", 16, 17, 16, 48, "vector", "bfloat16"),
+    ("int7", 8, 3, 19, 16, "vector", "bfloat16"),
+    ("int8", 0, 4, 48, 1040, "vector", "bfloat16"),
+    ("uint8", 0, 6, 20, 128, "matrix", "float16"),
+    ("float6_e3m2fn", 32, 4, 16, 128, "vector", "bfloat16"),
+    ("float4_e2m1fn", 0, 8, 31, 64, "none", "float16"),
+    ("float8_e4m3fn", 0, 4, 32, 576, "vector", "bfloat16"),
+]
+
+
+def _stored_weight(rng, name, N, K, exact):
+    """random codes of the format -> (storage bytes as the reference keeps them, real values q[N,K] before the scale, WeightFormat)"""
+    info = O.dtype_info(name)
+    bits = info["num_bits"]
+    if info["is_integer"]:
+        vals = rng.integers(info["min"], info["max"] + 1, size=(N, K))
+        if bits == 8:
+            raw = vals.astype(np.uint8) if info["is_unsigned"] else vals.astype(np.int8).view(np.uint8)
+        else:
+            raw = O.pack_int(vals, name)
+        return np.ascontiguousarray(raw).reshape(-1), vals.astype(np.float32), WeightFormat(W_INT, bits, int(info["is_unsigned"]), 0, 0, 1)
+    if name == "float8_e4m3fn":
+        codes = rng.integers(0, 256, size=(N, K)).astype(np.uint8)
+        codes[(codes & 0x7F) == 0x7F] = 0x3C                                      # no NaN codes
+        return codes.reshape(-1), O.from_e4m3fn_bits(codes), WeightFormat(W_E4M3, 8, 0, 4, 3, 1)
+    codes = rng.integers(0, 2 ** bits, size=(N, K))
+    raw = O.pack_uint(codes, bits) if bits < 8 else codes.astype(np.uint8)
+    fmt = WeightFormat(W_MINIFLOAT, bits, int(info["is_unsigned"]), info["exponent"], info["mantissa"], 1)
+    return np.ascontiguousarray(raw).reshape(-1), O.decode_minifloat(codes, name), fmt
+
+
+def _round_to(x, dtype):
+    return O.bf16_round(x) if dtype == "bfloat16" else np.asarray(x, np.float32).astype(np.float16).astype(np.float32)
+
+
+def _bits_of(x, dtype):
+    return O.bf16_bits(x).astype(np.uint16) if dtype == "bfloat16" else np.asarray(x, np.float32).astype(np.float16).view(np.uint16)
+
+
+def _from_bits(b, dtype):
+    return O.from_bf16_bits(b) if dtype == "bfloat16" else b.view(np.float16).astype(np.float32)
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact_sums", "random"])
+@pytest.mark.parametrize("case", GEMV_CASES, ids=[f"{c[0]}-g{c[1]}-M{c[2]}" for c in GEMV_CASES])
+def test_small_m_packed_linear_kernel_on_emulated_ctas(emu, case, exact):
+    name, group, M, N, K, bias_kind, dtype = case
+    emu.emu_gemv_packed.argtypes = [P, ctypes.c_int, ctypes.c_int64, P, ctypes.POINTER(WeightFormat), P, P, ctypes.c_int64, P, ctypes.c_int,
+                                    ctypes.c_int64, P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
+    info = O.dtype_info(name)
+    rng = np.random.default_rng(zlib.crc32(repr((name, group, M, exact)).encode()))
+    raw, q, fmt = _stored_weight(rng, name, N, K, exact)
+    raw = np.concatenate([raw, np.zeros(16, np.uint8)])                            # the kernel never reads past the weight; slack only for alignment of the copy
+    g = group or K
+    if exact:       # power-of-two scales and small integer activations: every product and partial sum is exact in f32
+        scale = np.exp2(rng.integers(-4, 2, size=(N, K // g))).astype(np.float32)
+        zp = np.exp2(rng.integers(-3, 1, size=(N, K // g))).astype(np.float32) * rng.integers(-4, 5, size=(N, K // g)) if info["is_unsigned"] else None
+        x = rng.integers(-8, 9, size=(M, K)).astype(np.float32)
+        bias_vals = rng.integers(-16, 17, size=(M, N)).astype(np.float32)
+    else:
+        scale = (rng.random((N, K // g)).astype(np.float32) + 0.5) * np.float32(0.02)
+        zp = (rng.standard_normal((N, K // g)).astype(np.float32) * np.float32(0.1)) if info["is_unsigned"] else None
+        x = _round_to(rng.standard_normal((M, K)).astype(np.float32), dtype)
+        bias_vals = _round_to(rng.standard_normal((M, N)).astype(np.float32), dtype)
+    if zp is not None:
+        zp = np.ascontiguousarray(zp, dtype=np.float32)
+    # the reference's dequantised weight: f32 math in its order, rounded to the activation dtype
+    s_full, z_full = np.repeat(scale, g, axis=1), None if zp is None else np.repeat(zp, g, axis=1)
+    W = _round_to(O.fma32(q, s_full, z_full) if zp is not None else (q * s_full).astype(np.float32), dtype)
+    ldx = K + 8
+    xbuf = np.zeros((M, ldx), dtype=np.uint16)
+    xbuf[:, :K] = _bits_of(x, dtype)
+    if bias_kind == "none":
+        bias, bias_ld, bias_arr = None, 0, None
+    elif bias_kind == "vector":
+        bias = bias_vals[0].copy()
+        bias_ld, bias_arr = 0, np.ascontiguousarray(_bits_of(bias, dtype))
+        bias = np.broadcast_to(bias, (M, N))
+    else:
+        bias, bias_ld, bias_arr = bias_vals, N, np.ascontiguousarray(bias_vals, dtype=np.float32)
+    out = np.full((M, N), 0x7FC0 if dtype == "bfloat16" else 0x7E00, dtype=np.uint16)          # NaN-filled: every output must be written
+    code = 1 if dtype == "bfloat16" else 2
+    bias_code = 0 if bias_kind == "matrix" else code
+    for grid in (1, 3):                                                               # one CTA walking all tiles, and a strided grid
+        out[:] = 0x7FC0 if dtype == "bfloat16" else 0x7E00
+        rc = emu.emu_gemv_packed(_ptr(xbuf), code, ldx, _ptr(raw), ctypes.byref(fmt), _ptr(scale), None if zp is None else _ptr(zp), group,
+                                 None if bias_arr is None else _ptr(bias_arr), bias_code, bias_ld, _ptr(out), M, N, K, grid)
+        assert rc == 0
+        got = _from_bits(out, dtype)
+        acc = x.astype(np.float64) @ W.astype(np.float64).T
+        if exact:
+            want = _round_to((acc.astype(np.float32) + (0 if bias is None else bias.astype(np.float32))).astype(np.float32), dtype)
+            np.testing.assert_array_equal(got, want)
+        else:
+            want = acc + (0 if bias is None else bias)
+            # f32 accumulation in the tensor-core model's order + one rounding to T
+            bound = np.abs(want) * 2.0 ** (-8 if dtype == "bfloat16" else -11) + (np.abs(x).astype(np.float64) @ np.abs(W).astype(np.float64).T) * 2.0 ** -20 + 1e-6
+            assert (np.abs(got - want) <= bound).all(), float(np.abs(got - want).max())
+
+
+# ---- the Python glue of K5p (forward hook -> ops.linear_small_m_packed -> C ABI arguments), with the C entry point replaced by the
+# emulated kernel: layers quantised through the public surface on the CPU, checked against the oracle's dequantise + linear.
+SMALL_M_LAYER_CONFIGS = [
+    dict(weights_dtype="int4", group_size=128), dict(weights_dtype="uint4"), dict(weights_dtype="int2", group_size=16),
+    dict(weights_dtype="float6_e3m2fn", group_size=32), dict(weights_dtype="int5", group_size=-1), dict(weights_dtype="uint7", group_size=8),
+    dict(weights_dtype="int4", group_size=-1, use_quantized_matmul=True), dict(weights_dtype="int8", group_size=64, use_quantized_matmul=True),
+    dict(weights_dtype="float8_e4m3fn", group_size=32),
+]
+
+
+@pytest.mark.parametrize("cfg", SMALL_M_LAYER_CONFIGS, ids=["-".join(f"{k[:5]}={v}" for k, v in c.items()) for c in SMALL_M_LAYER_CONFIGS])
+def test_small_m_packed_forward_glue_on_the_emulator(emu, cfg, monkeypatch):
+    import contextlib
+    import copy
+
+    import torch
+
+    from sdnq_b200 import SDNQConfig, forward, ops, sdnq_quantize_layer
+    emu.emu_gemv_packed.argtypes = [P, ctypes.c_int, ctypes.c_int64, P, ctypes.c_void_p, P, P, ctypes.c_int64, P, ctypes.c_int,
+                                    ctypes.c_int64, P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
+    calls = []
+
+    class FakeLib:
+        @staticmethod
+        def sdnq_b200_linear_small_m_packed(x, x_dtype, ldx, w, fmt, scale, zp, group, bias, bias_dtype, bias_ld, out, M, N, K, stream):
+            calls.append((M, N, K, group))
+            return emu.emu_gemv_packed(x, x_dtype, ldx, w, ctypes.cast(ctypes.byref(fmt), ctypes.c_void_p), scale, zp, group, bias, bias_dtype,
+                                       bias_ld, out, M, N, K, 2)
+
+    monkeypatch.setattr(ops._lib, "load", lambda: FakeLib)
+    monkeypatch.setattr(ops, "_require_cuda", lambda *t: None)
+    monkeypatch.setattr(ops, "_stream", lambda t: 0)
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    monkeypatch.setenv("SDNQ_B200_SMALL_M_PACKED", "1")
+    torch.manual_seed(5)
+    K, N, M = 256, 72, 5
+    lin = torch.nn.Linear(K, N, bias=True).to(torch.bfloat16)
+    layer, _ = sdnq_quantize_layer(copy.deepcopy(lin), SDNQConfig(**cfg))
+    x = torch.randn(M, K).to(torch.bfloat16)
+    assert forward._small_m_packed_ok(layer, x)
+    y = forward._small_m_packed_linear(layer, x)
+    assert calls and calls[0][:3] == (M, N, K)
+    d = layer.sdnq_dequantizer
+
+    def conv(t):
+        if t is None:
+            return None
+        t = t.detach()
+        return t.float().numpy() if t.is_floating_point() else t.numpy()
+    meta = {k: (list(v) if isinstance(v, (torch.Size, tuple)) else v) for k, v in d.__dict__.items() if k != "result_dtype"}
+    ol = O.Layer(conv(layer.weight), conv(layer.scale), conv(layer.zero_point), None, None, bias=conv(layer.bias), **meta)
+    want = O.linear_dequant(ol, x.float().numpy(), skip_quantized_matmul=bool(d.use_quantized_matmul))
+    got = y.float().numpy()
+    assert got.shape == want.shape
+    ulp = np.exp2(np.floor(np.log2(np.maximum(np.abs(want), 1e-30))) - 7)
+    assert (np.abs(got - want) <= 2 * ulp + 1e-5).all(), float(np.abs(got - want).max())
+    # opt-outs: SVD layers, the knob itself
+    monkeypatch.setenv("SDNQ_B200_SMALL_M_PACKED", "0")
+    assert not forward._small_m_packed_ok(layer, x)
