@@ -1,0 +1,49 @@
+"""K5p on the GPU: the small-M Linear straight from the stored (packed / group-wise) weight, opt-in with SDNQ_B200_SMALL_M_PACKED=1.
+
+Status: the kernel body (gemv_packed_kernel.cuh) and its Python glue are validated bit-for-bit against the oracle on the host CTA
+emulator (tests/test_device_arithmetic_on_host.py, CPU).  Round 1's GPU budget ran out before this file could run on a B200, so the
+test is marked xfail(strict=False): an XPASS in the round-end GPU run is its first hardware validation (then the marker goes and the
+knob's default flips), a failure stays contained here.  The file sorts last so that nothing else depends on it."""
+import copy
+
+import pytest
+import torch
+
+from tests.util import bf16_ulp_diff
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="K5p: validated on the host emulator only; first hardware run pending (round-1 GPU budget spent)")]
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("cfg", [dict(weights_dtype="int4", group_size=128), dict(weights_dtype="uint4"), dict(weights_dtype="int2", group_size=16),
+                                 dict(weights_dtype="float6_e3m2fn", group_size=32), dict(weights_dtype="int5", group_size=-1),
+                                 dict(weights_dtype="int4", group_size=-1, use_quantized_matmul=True),
+                                 dict(weights_dtype="int8", group_size=128, use_quantized_matmul=True),
+                                 dict(weights_dtype="uint4", use_quantized_matmul=True, use_hadamard=True, hadamard_group_size=256)],
+                         ids=["int4_g128", "uint4_auto", "int2_g16", "float6_g32", "int5_rowwise", "int4_rowwise_w8a8", "int8_g128_w8a8",
+                              "uint4_hadamard_w8a8"])
+@pytest.mark.parametrize("M", [1, 4, 31])
+def test_small_m_packed_forward_vs_dequant_path(cfg, M, monkeypatch):
+    """rows < 32 of a layer stored packed / group-wise: K5p (SDNQ_B200_SMALL_M_PACKED=1, reads the stored bytes once) against the
+    reference-shaped dequantise + bf16 GEMM path.  K5p multiplies by exactly the bf16 weights the dequant kernel would write, so
+    only the f32 accumulation order differs from the library GEMM."""
+    from sdnq_b200 import SDNQConfig, _lib, sdnq_quantize_layer
+    torch.manual_seed(11 + M)
+    lin = torch.nn.Linear(768, 1544, bias=True).to(torch.bfloat16)                 # N not a multiple of 16: a ragged last tile
+    layer, _ = sdnq_quantize_layer(copy.deepcopy(lin), SDNQConfig(**cfg))
+    layer = layer.to(DEV)
+    x = torch.randn(M, 768, dtype=torch.bfloat16, device=DEV)
+    monkeypatch.setenv("SDNQ_B200_SMALL_M_PACKED", "1")
+    _lib.launch_count(reset=True)
+    y = layer(x)
+    n_launch = _lib.launch_count()
+    monkeypatch.setenv("SDNQ_B200_SMALL_M_PACKED", "0")
+    y_ref = layer(x)
+    assert n_launch == (2 if cfg.get("use_hadamard") else 1), n_launch
+    assert y.shape == y_ref.shape and y.dtype == y_ref.dtype and bool(torch.isfinite(y).all())
+    scale = float(y_ref.float().abs().max())
+    err = (y.float() - y_ref.float()).abs()
+    assert float(err.max()) <= 2e-2 * scale and float(err.pow(2).mean().sqrt()) <= 3e-3 * scale
+    if not cfg.get("use_hadamard"):      # same bf16 weights, f32 accumulation: at most the last bf16 bit of an output moves
+        assert int(bf16_ulp_diff(y, y_ref).max()) <= 2 or float(err.max()) <= 2.0 ** -7 * scale
