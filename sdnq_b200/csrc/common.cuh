@@ -32,6 +32,13 @@ void count_launch(int n = 1);
             return ::sdnq::set_error(SDNQ_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));   \
     } while (0)
 
+#ifdef SDNQ_HOST_EMU
+// tests/host_emu: the launch runs the kernel function on emulated CTAs (lock-stepped host threads), synchronously
+inline int check_launch(const char*) {
+    count_launch();
+    return SDNQ_OK;
+}
+#else
 inline int check_launch(const char* what) {
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) {
@@ -41,6 +48,7 @@ inline int check_launch(const char* what) {
     count_launch();
     return SDNQ_OK;
 }
+#endif
 
 int num_sms();
 bool pdl_enabled();
@@ -48,6 +56,13 @@ bool pdl_enabled();
 // Launch with the programmatic-dependent-launch attribute: the kernel may start (prologue, weight prefetch) while its
 // stream predecessor is still draining; every kernel of this library calls pdl_wait() before touching data a predecessor
 // may have produced (and before exiting, which keeps the dependency chain transitive).
+#ifdef SDNQ_HOST_EMU
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t, cudaStream_t, Args&&... args) {
+    ::sdnq_emu::run_grid(static_cast<int>(grid.x), static_cast<int>(block.x), [&] { kernel(args...); });
+    return cudaSuccess;
+}
+#else
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg{};
@@ -62,10 +77,16 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
+#endif
 
 // ---------------------------------------------------------------- device: programmatic dependent launch
+#ifdef SDNQ_HOST_EMU
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_launch_dependents() {}
+#else
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // ---------------------------------------------------------------- device: small numerics
 __device__ __forceinline__ float bf16_to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }

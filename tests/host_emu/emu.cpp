@@ -2,11 +2,18 @@
 #include "prelude.h"
 #include "../../sdnq_b200/csrc/unpack.cuh"
 
+// kernels declare their shared memory as function-local `__shared__` arrays: on the host that is one static array per kernel
+// instantiation, shared by the lock-stepped threads of the (single) running CTA
+#undef __shared__
+#define __shared__ static
+
 using namespace sdnq;
 
 namespace sdnq {
 int set_error(int code, const char*, ...) { return code; }
 void count_launch(int) {}
+int num_sms() { return 148; }
+bool pdl_enabled() { return true; }
 }  // namespace sdnq
 
 extern "C" {
@@ -164,4 +171,15 @@ extern "C" int emu_gemv_packed(const void* x, int x_dtype, int64_t ldx, const vo
     if (x_dtype == SDNQ_BF16) { SDNQ_DISPATCH_BITS(f.bits, run_gemv_packed<__nv_bfloat16, BITS>(a, grid)); }
     else { SDNQ_DISPATCH_BITS(f.bits, run_gemv_packed<__half, BITS>(a, grid)); }
     return 0;
+}
+
+
+// ---------------------------------------------------------------- K2 whole: argument checks, dispatch over (K -> warps per row, chunks
+// per lane, tensor-core or butterfly rotation, two-pass kernel for long rows) and the kernels, all from act_quant_kernel.cuh
+#include "../../sdnq_b200/csrc/act_quant_kernel.cuh"
+
+extern "C" int emu_act_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx, int hadamard_group, int mm_dtype, void* xq,
+                             float* sx, float* zx, int32_t* rowsum, void* x_rot) {
+    ConvView none{};
+    return act_quant_run<false>(x, x_dtype, M, K, ldx, hadamard_group, mm_dtype, xq, sx, zx, rowsum, x_rot, none, nullptr);
 }

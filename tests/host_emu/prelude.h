@@ -11,6 +11,8 @@
 #include <vector_functions.h>
 
 #define SDNQ_HOST_EMU 1
+#define __noinline__ __attribute__((noinline))
+#define __launch_bounds__(...)
 #include "warp.h"
 
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
@@ -28,6 +30,17 @@ static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
     return r;
 }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }          // built with -ffp-contract=off: no fusion on the host either
+static inline float __fmul_rn(float a, float b) { return a * b; }
+// cvt.rni.s32.f32: round to nearest even, NaN -> 0, saturating
+static inline int __float2int_rn(float v) {
+    if (v != v) return 0;
+    if (v >= 2147483648.0f) return 2147483647;
+    if (v <= -2147483648.0f) return -2147483647 - 1;
+    return static_cast<int>(std::nearbyint(v));
+}
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline int min(int a, int b) { return a < b ? a : b; }
 static inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 static inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(std::fma(a.x, b.x, c.x), std::fma(a.y, b.y, c.y)); }

@@ -10,6 +10,8 @@
 #pragma once
 #include <pthread.h>
 
+#include <cmath>
+
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -81,6 +83,18 @@ inline uint32_t movmatrix_trans(uint32_t a) {
     warp_sync();
     return r;
 }
+
+// rcp.approx.ftz.f32: the hardware result is within 1 ulp of 1/x; the host model returns the correctly rounded reciprocal
+// (subnormal inputs / outputs flushed to zero).  RowDivider refines it to a correctly rounded quotient either way.
+inline float rcp_approx_ftz(float x) {
+    if (std::fabs(x) < 1.17549435e-38f) x = std::copysign(0.0f, x);
+    float r = 1.0f / x;
+    if (std::fabs(r) < 1.17549435e-38f) r = std::copysign(0.0f, r);
+    return r;
+}
+inline uint32_t sat8(int v) { return static_cast<uint32_t>(static_cast<uint8_t>(static_cast<int8_t>(v < -128 ? -128 : (v > 127 ? 127 : v)))); }
+// two cvt.pack.sat.s8.s32.b32: bytes (low -> high) = sat8(c0), sat8(c1), sat8(c2), sat8(c3)
+inline uint32_t pack_sat_s8x4(int c0, int c1, int c2, int c3) { return sat8(c0) | (sat8(c1) << 8) | (sat8(c2) << 16) | (sat8(c3) << 24); }
 
 // run fn() as a grid of `grid` CTAs of `threads` lock-stepped host threads each (CTAs one after another); the device code reads
 // threadIdx.x / blockIdx.x / gridDim.x through the stand-ins in prelude.h

@@ -33,7 +33,7 @@ W_INT, W_MINIFLOAT, W_E4M3, W_E5M2 = range(4)
 def emu(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("host_emu") / "libsdnq_emu.so")
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-w", "-pthread", "-include", os.path.join(EMU_DIR, "prelude.h"), "-I", cuda_inc,
+    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-w", "-pthread", "-ffp-contract=off", "-include", os.path.join(EMU_DIR, "prelude.h"), "-I", cuda_inc,
            os.path.join(EMU_DIR, "emu.cpp"), "-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, "host build of the device headers failed:\n" + r.stderr[-3000:]
@@ -459,3 +459,86 @@ def test_small_m_packed_forward_glue_on_the_emulator(emu, cfg, monkeypatch):
     # opt-outs: SVD layers, the knob itself
     monkeypatch.setenv("SDNQ_B200_SMALL_M_PACKED", "0")
     assert not forward._small_m_packed_ok(layer, x)
+
+
+# ---- K2 whole (act_quant_kernel.cuh: argument checks, the K -> (warps per row, chunks per lane) dispatch, tensor-core / butterfly
+# rotation, register-resident and two-pass kernels) on emulated CTAs.  launch_pdl is the emulator's grid runner under
+# SDNQ_HOST_EMU, so the host dispatch code runs unchanged too.  rcp.approx is modelled by the correctly rounded reciprocal
+# (RowDivider refines either to the correctly rounded quotient); everything else is the device source.
+def _act_quant_emu(emu, x, dtype, mode, hadamard=0, ldx=None, want_rowsum=False, want_x_rot=False):
+    emu.emu_act_quant.argtypes = [P, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, P, P, P, P, P]
+    M, K = x.shape
+    ldx = ldx or K
+    code = {"float32": 0, "bfloat16": 1, "float16": 2}[dtype]
+    if dtype == "float32":
+        buf = np.zeros((M, ldx), dtype=np.float32)
+        buf[:, :K] = x
+    else:
+        buf = np.zeros((M, ldx), dtype=np.uint16)
+        buf[:, :K] = _bits_of(x, dtype)
+    mm = {"int8": 3, "uint8": 4, "fp8": 5}[mode]
+    xq = np.full((M, K), 0x55, dtype=np.uint8)
+    sx = np.full(M, np.nan, dtype=np.float32)
+    zx = np.full(M, np.nan, dtype=np.float32)
+    rowsum = np.full(M, -12345, dtype=np.int32)
+    x_rot = np.zeros((M, K), dtype=buf.dtype)
+    rc = emu.emu_act_quant(_ptr(buf), code, M, K, ldx, hadamard, mm, _ptr(xq), _ptr(sx), _ptr(zx) if mode == "uint8" else None,
+                           _ptr(rowsum) if want_rowsum else None, _ptr(x_rot) if want_x_rot else None)
+    assert rc == 0, rc
+    return xq, sx, zx, rowsum, x_rot
+
+
+def _check_codes(mode, xq, sx, zx, rowsum, x_ref, want_rowsum):
+    """x_ref: the (rotated, dtype-rounded) activations the quantiser sees; bit-exact codes / scales / zero points / row sums"""
+    if mode == "int8":
+        q, s = O.quantize_int_mm(x_ref)
+        np.testing.assert_array_equal(xq.view(np.int8), q)
+    elif mode == "uint8":
+        q, s, z = O.quantize_uint_mm(x_ref)
+        np.testing.assert_array_equal(xq.view(np.int8), q)
+        np.testing.assert_array_equal(zx, z.reshape(-1))
+    else:
+        q, s = O.quantize_fp_mm(x_ref)
+        np.testing.assert_array_equal(xq, O.e4m3fn_bits(q))
+    np.testing.assert_array_equal(sx, s.reshape(-1))
+    if want_rowsum:
+        np.testing.assert_array_equal(rowsum, xq.view(np.int8).astype(np.int64).sum(axis=1))
+
+
+@pytest.mark.parametrize("mode", ["int8", "uint8", "fp8"])
+@pytest.mark.parametrize("K", [64, 200, 512, 640, 1280, 2560, 5120, 12288, 16640])
+def test_act_quant_kernels_on_emulated_ctas(emu, K, mode):
+    """every dispatch bucket of K2 (1 / 2 / 4 chunks per lane, 2 / 4 / 8 warps per row, 8 chunks, and the two-pass kernel for
+    K > 16384), ragged rows (K % 256 != 0), a padded row stride, an all-zero row: codes, scales, zero points and row sums are
+    bit-identical to the reference arithmetic (quant_utils.py:264-299)"""
+    rng = np.random.default_rng(K + len(mode))
+    M = 3 if K > 4096 else 9                                              # 9 rows: a ragged last CTA for every rows-per-CTA value
+    x = O.bf16_round((rng.standard_normal((M, K)) * np.exp2(rng.integers(-6, 6, size=(M, 1)))).astype(np.float32))
+    x[1, :] = 0.0                                                         # all-zero row: scale 0, codes 0 (0/0 -> NaN -> 0)
+    x[2, rng.integers(0, K)] = 300.0                                      # an outlier channel
+    xq, sx, zx, rowsum, _ = _act_quant_emu(emu, x, "bfloat16", mode, ldx=K + 8, want_rowsum=mode != "fp8")
+    _check_codes(mode, xq, sx, zx, rowsum, x, want_rowsum=mode != "fp8")
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float16"])
+def test_act_quant_other_activation_dtypes_on_the_emulator(emu, dtype):
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((5, 1000)).astype(np.float32)
+    x = x if dtype == "float32" else x.astype(np.float16).astype(np.float32)
+    xq, sx, zx, rowsum, _ = _act_quant_emu(emu, x, dtype, "int8", want_rowsum=True)
+    _check_codes("int8", xq, sx, zx, rowsum, x, want_rowsum=True)
+
+
+@pytest.mark.parametrize("mode", ["int8", "uint8", "fp8"])
+@pytest.mark.parametrize("G,K", [(256, 3072), (256, 768), (128, 640), (64, 1344), (16, 528), (32, 17408)])
+def test_act_quant_with_rotation_on_emulated_ctas(emu, G, K, mode):
+    """K2 with the Hadamard rotation in front (FLUX: fp8 + Hadamard-256; SD-XL C = 640: group 128).  Inputs with exact sums, so the
+    rotated activations -- checked through the x_rot output -- and with them codes / scales / row sums must equal the reference's
+    rotate_hadamard + quantise bit for bit.  K = 17408 takes the two-pass kernel with the butterfly rotation."""
+    rng = np.random.default_rng(G + K)
+    M = 2 if K > 4096 else 5
+    x = rng.integers(-64, 65, size=(M, K)).astype(np.float32) * np.exp2(rng.integers(-3, 4, size=(M, 1))).astype(np.float32)
+    xq, sx, zx, rowsum, x_rot = _act_quant_emu(emu, x, "bfloat16", mode, hadamard=G, want_rowsum=mode != "fp8", want_x_rot=True)
+    x_ref = O.rotate_hadamard(x, G, "bfloat16")
+    np.testing.assert_array_equal(O.from_bf16_bits(x_rot), x_ref)
+    _check_codes(mode, xq, sx, zx, rowsum, x_ref, want_rowsum=mode != "fp8")
