@@ -132,9 +132,13 @@ __device__ __forceinline__ int quantise_channels(const T* __restrict__ xc, int64
 #pragma unroll
             for (int i = 0; i < 4; ++i) c[i] = __float2int_rn(qv[i]);      // round-half-even; NaN -> 0
             uint32_t w;
+#ifdef SDNQ_HOST_EMU
+            w = ::sdnq_emu::pack_sat_s8x4(c[0], c[1], c[2], c[3]);
+#else
             // cvt.pack.sat.s8.s32.b32 d, a, b, c :  d = (c << 16) | (sat8(a) << 8) | sat8(b)
             asm("{\n\t.reg .b32 t;\n\tcvt.pack.sat.s8.s32.b32 t, %4, %3, 0;\n\tcvt.pack.sat.s8.s32.b32 %0, %2, %1, t;\n\t}"
                 : "=r"(w) : "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
+#endif
             dst[wd] = w;
             if (want_sum) {
 #pragma unroll

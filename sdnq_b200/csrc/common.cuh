@@ -59,10 +59,19 @@ bool pdl_enabled();
 #ifdef SDNQ_HOST_EMU
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t, cudaStream_t, Args&&... args) {
-    ::sdnq_emu::run_grid(static_cast<int>(grid.x), static_cast<int>(block.x), [&] { kernel(args...); });
+    ::sdnq_emu::run_grid(grid, static_cast<int>(block.x), [&] { kernel(args...); });
     return cudaSuccess;
 }
+// an ordinary launch (kernel<<<grid, block, smem, stream>>>(args...)) without the programmatic-dependent-launch attribute
+template <typename... KArgs, typename... Args>
+void launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t, cudaStream_t, Args&&... args) {
+    ::sdnq_emu::run_grid(grid, static_cast<int>(block.x), [&] { kernel(args...); });
+}
 #else
+template <typename... KArgs, typename... Args>
+void launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    kernel<<<grid, block, smem, st>>>(std::forward<Args>(args)...);
+}
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg{};

@@ -349,7 +349,11 @@ __global__ void __launch_bounds__(kThreads) dequant_flat_kernel(const uint8_t* _
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     uint32_t h;
+#ifdef SDNQ_HOST_EMU
+                    h = ::sdnq_emu::e4m3x2_to_f16x2(static_cast<unsigned short>((raw[u][i >> 1] >> (16 * (i & 1))) & 0xFFFFu));
+#else
                     asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h) : "h"(static_cast<unsigned short>((raw[u][i >> 1] >> (16 * (i & 1))) & 0xFFFFu)));
+#endif
                     const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
                     q[2 * i] = f.x;
                     q[2 * i + 1] = f.y;
@@ -372,7 +376,11 @@ __global__ void __launch_bounds__(kThreads) dequant_flat_kernel(const uint8_t* _
                             pk[i] = *reinterpret_cast<uint32_t*>(&h);
                         }
                     }
+#ifdef SDNQ_HOST_EMU
+                    *reinterpret_cast<uint4*>(out + size_t(o) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+#else
                     asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(out + size_t(o) * 8), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+#endif
                     continue;
                 }
             }
@@ -675,8 +683,8 @@ extern "C" int sdnq_b200_unpack(const void* packed, const sdnq_weight_format* fm
     const int64_t octets = numel / 8;
     const unsigned blocks = static_cast<unsigned>((octets + kThreads - 1) / kThreads);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    SDNQ_DISPATCH_BITS(f.bits, (unpack_kernel<BITS><<<blocks, kThreads, 0, st>>>(reinterpret_cast<const uint8_t*>(packed), f, out, out_dtype, octets)));
-    operand_fence_kernel<<<1, 32, 0, st>>>();
+    SDNQ_DISPATCH_BITS(f.bits, launch_plain(unpack_kernel<BITS>, dim3(blocks), dim3(kThreads), 0, st, reinterpret_cast<const uint8_t*>(packed), f, out, out_dtype, octets));
+    launch_plain(operand_fence_kernel, dim3(1), dim3(32), 0, st);
     return check_launch("unpack_kernel");
 }
 
@@ -726,8 +734,8 @@ extern "C" int sdnq_b200_requant(const void* weight, const sdnq_weight_format* f
     SDNQ_REQUIRE(K <= int64_t(kRequantMaxOct) * 8 * kThreads, SDNQ_EUNSUPPORTED, "requant: K=%lld exceeds %d", (long long)K,
                  kRequantMaxOct * 8 * kThreads);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    SDNQ_DISPATCH_BITS(a.f.bits, (requant_kernel<BITS><<<static_cast<unsigned>(N), kThreads, 0, st>>>(
-                                     a, mm_dtype, reinterpret_cast<uint8_t*>(wq), sw, mm_dtype == SDNQ_U8 ? zw : nullptr, colsum)));
-    operand_fence_kernel<<<1, 32, 0, st>>>();
+    SDNQ_DISPATCH_BITS(a.f.bits, launch_plain(requant_kernel<BITS>, dim3(static_cast<unsigned>(N)), dim3(kThreads), 0, st,
+                                              a, mm_dtype, reinterpret_cast<uint8_t*>(wq), sw, mm_dtype == SDNQ_U8 ? zw : nullptr, colsum));
+    launch_plain(operand_fence_kernel, dim3(1), dim3(32), 0, st);
     return check_launch("requant_kernel");
 }

@@ -41,13 +41,21 @@ struct GemvArgs {
 template <typename T> struct Act;
 template <> struct Act<__nv_bfloat16> {
     __device__ static __forceinline__ uint32_t pack(float lo, float hi) {
+#ifdef SDNQ_HOST_EMU
+        return ::sdnq_emu::pack16x2(false, lo, hi);
+#else
         uint32_t r;
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
         return r;
+#endif
     }
     __device__ static __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+#ifdef SDNQ_HOST_EMU
+        ::sdnq_emu::mma_m16n8k16(false, d, a[0], a[1], a[2], a[3], b0, b1);
+#else
         asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+#endif
     }
     __device__ static __forceinline__ float lo(uint32_t w) { return __uint_as_float(w << 16); }
     __device__ static __forceinline__ float hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
@@ -55,13 +63,21 @@ template <> struct Act<__nv_bfloat16> {
 };
 template <> struct Act<__half> {
     __device__ static __forceinline__ uint32_t pack(float lo, float hi) {
+#ifdef SDNQ_HOST_EMU
+        return ::sdnq_emu::pack16x2(true, lo, hi);
+#else
         uint32_t r;
         asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
         return r;
+#endif
     }
     __device__ static __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+#ifdef SDNQ_HOST_EMU
+        ::sdnq_emu::mma_m16n8k16(true, d, a[0], a[1], a[2], a[3], b0, b1);
+#else
         asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+#endif
     }
     __device__ static __forceinline__ float lo(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w & 0xFFFFu))); }
     __device__ static __forceinline__ float hi(uint32_t w) { return __half2float(__ushort_as_half(static_cast<unsigned short>(w >> 16))); }
@@ -74,8 +90,13 @@ __device__ __forceinline__ void codes4(uint32_t w, uint32_t& p01, uint32_t& p23)
     if constexpr (kFp8) {
         // e4m3 pair -> f16 pair (exact, one instruction); f16 needs nothing more, bf16 goes through f32 (exact: 4 significant bits)
         uint32_t h01, h23;
+#ifdef SDNQ_HOST_EMU
+        h01 = ::sdnq_emu::e4m3x2_to_f16x2(static_cast<unsigned short>(w & 0xFFFFu));
+        h23 = ::sdnq_emu::e4m3x2_to_f16x2(static_cast<unsigned short>(w >> 16));
+#else
         asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h01) : "h"(static_cast<unsigned short>(w & 0xFFFFu)));
         asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h23) : "h"(static_cast<unsigned short>(w >> 16)));
+#endif
         if constexpr (ElemTraits<T>::kDtype == SDNQ_F16) {
             p01 = h01;
             p23 = h23;

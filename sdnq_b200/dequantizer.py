@@ -77,8 +77,7 @@ class SDNQDequantizer:
         differ.  `hadamard` (a matrix in the reference) is accepted for signature compatibility; the kernel un-rotates with its
         own butterfly."""
         dtype = dtype or self.result_dtype
-        if not weight.is_cuda:
-            raise ops._lib.SDNQKernelError("SDNQDequantizer: the weight is not on a CUDA device; sdnq_b200 has no CPU dequant path")
+        ops._require_cuda(weight)          # raises: sdnq_b200 has no CPU dequant path
         if self.is_conv:
             return self._conv_dequant(weight, scale, zero_point, svd_up, svd_down, skip_quantized_matmul, non_hadamard, dtype)
         N, K = self._linear_nk()

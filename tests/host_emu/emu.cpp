@@ -2,19 +2,45 @@
 #include "prelude.h"
 #include "../../sdnq_b200/csrc/unpack.cuh"
 
-// kernels declare their shared memory as function-local `__shared__` arrays: on the host that is one static array per kernel
-// instantiation, shared by the lock-stepped threads of the (single) running CTA
-#undef __shared__
-#define __shared__ static
+#include <cstdarg>
+#include <cstdio>
 
 using namespace sdnq;
 
+// ---- what capi.cu provides in the real library (no CUDA runtime here)
 namespace sdnq {
-int set_error(int code, const char*, ...) { return code; }
-void count_launch(int) {}
-int num_sms() { return 148; }
+namespace {
+thread_local char g_error[512] = "";
+int64_t g_launches = 0;
+}  // namespace
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+void count_launch(int n) { g_launches += n; }
+int num_sms() { return 2; }                     // grids are sized from this: keep the emulated grids small
 bool pdl_enabled() { return true; }
+// dequant_svd.cu (tcgen05) is outside the emulator: "not covered" sends SVD layers to the CUDA-core update of dequant.cu
+int dequant_svd_tc(const void*, const WFormat&, const float*, const float*, int64_t, int64_t, int, int, int, int, const void*, int64_t, int64_t,
+                   const void*, int64_t, int64_t, int, int, void*, int, cudaStream_t) { return 1; }
 }  // namespace sdnq
+
+extern "C" {
+int sdnq_b200_abi_version(void) { return SDNQ_B200_ABI_VERSION; }
+const char* sdnq_b200_last_error(void) { return sdnq::g_error; }
+int sdnq_b200_check_device(int) { return SDNQ_OK; }
+int64_t sdnq_b200_launch_count(int reset) {
+    const int64_t v = sdnq::g_launches;
+    if (reset) sdnq::g_launches = 0;
+    return v;
+}
+// the two CUDA runtime calls the launch code makes besides the launch itself
+const char* cudaGetErrorString(cudaError_t) { return "cuda runtime is not available in the host emulator"; }
+cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }
+}
 
 extern "C" {
 
@@ -171,15 +197,4 @@ extern "C" int emu_gemv_packed(const void* x, int x_dtype, int64_t ldx, const vo
     if (x_dtype == SDNQ_BF16) { SDNQ_DISPATCH_BITS(f.bits, run_gemv_packed<__nv_bfloat16, BITS>(a, grid)); }
     else { SDNQ_DISPATCH_BITS(f.bits, run_gemv_packed<__half, BITS>(a, grid)); }
     return 0;
-}
-
-
-// ---------------------------------------------------------------- K2 whole: argument checks, dispatch over (K -> warps per row, chunks
-// per lane, tensor-core or butterfly rotation, two-pass kernel for long rows) and the kernels, all from act_quant_kernel.cuh
-#include "../../sdnq_b200/csrc/act_quant_kernel.cuh"
-
-extern "C" int emu_act_quant(const void* x, int x_dtype, int64_t M, int64_t K, int64_t ldx, int hadamard_group, int mm_dtype, void* xq,
-                             float* sx, float* zx, int32_t* rowsum, void* x_rot) {
-    ConvView none{};
-    return act_quant_run<false>(x, x_dtype, M, K, ldx, hadamard_group, mm_dtype, xq, sx, zx, rowsum, x_rot, none, nullptr);
 }

@@ -7,8 +7,18 @@
 #include <cstdint>
 #include <cstring>
 
+// every CUDA header the kernels include, up front, so that __shared__ can be redefined once after them: kernels declare shared
+// memory as function-local __shared__ arrays; on the host that is one static array per kernel instantiation, shared by the
+// lock-stepped threads of the (single) running CTA
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
 #include <vector_types.h>
 #include <vector_functions.h>
+#undef __shared__
+#define __shared__ static
 
 #define SDNQ_HOST_EMU 1
 #define __noinline__ __attribute__((noinline))
@@ -39,6 +49,15 @@ static inline int __float2int_rn(float v) {
     if (v <= -2147483648.0f) return -2147483647 - 1;
     return static_cast<int>(std::nearbyint(v));
 }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline unsigned int __umulhi(unsigned int a, unsigned int b) { return static_cast<unsigned int>((static_cast<unsigned long long>(a) * b) >> 32); }
+// the lock-stepped lanes are real threads: atomics must be atomic
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned int atomicMax(unsigned int* p, unsigned int v) {
+    unsigned int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -58,8 +77,16 @@ template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m) {
 }
 // threadIdx.x / blockIdx.x / gridDim.x of the calling host thread (warp.h: run_grid)
 struct EmuThreadIdx { struct X { operator int() const { return sdnq_emu::t_tid; } } x; };
-struct EmuBlockIdx { struct X { operator int() const { return sdnq_emu::g_block; } } x; };
-struct EmuGridDim { struct X { operator int() const { return sdnq_emu::g_grid; } } x; };
+struct EmuBlockIdx {
+    struct X { operator int() const { return sdnq_emu::g_block.x; } } x;
+    struct Y { operator int() const { return sdnq_emu::g_block.y; } } y;
+    struct Z { operator int() const { return sdnq_emu::g_block.z; } } z;
+};
+struct EmuGridDim {
+    struct X { operator int() const { return sdnq_emu::g_grid.x; } } x;
+    struct Y { operator int() const { return sdnq_emu::g_grid.y; } } y;
+    struct Z { operator int() const { return sdnq_emu::g_grid.z; } } z;
+};
 static const EmuThreadIdx threadIdx = {};
 static const EmuBlockIdx blockIdx = {};
 static const EmuGridDim gridDim = {};

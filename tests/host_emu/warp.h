@@ -14,12 +14,13 @@
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 namespace sdnq_emu {
 
 constexpr int kMaxWarps = 8;
 inline thread_local int t_tid = 0;                    // threadIdx.x of the calling host thread
-inline int g_block = 0, g_grid = 1;                   // blockIdx.x / gridDim.x (CTAs run one after another)
+inline dim3 g_block(0, 0, 0), g_grid(1, 1, 1);        // blockIdx / gridDim (CTAs run one after another)
 inline pthread_barrier_t g_warp_barrier[kMaxWarps], g_cta_barrier;
 inline uint32_t g_xchg_all[kMaxWarps][32][6];
 
@@ -92,20 +93,28 @@ inline float rcp_approx_ftz(float x) {
     if (std::fabs(r) < 1.17549435e-38f) r = std::copysign(0.0f, r);
     return r;
 }
+// cvt.rn.f16x2.e4m3x2: two e4m3 bytes -> two f16 (exact), low byte -> low half
+inline uint32_t e4m3x2_to_f16x2(unsigned short pair) {
+    const __half_raw lo = __nv_cvt_fp8_to_halfraw(static_cast<__nv_fp8_storage_t>(pair & 0xFF), __NV_E4M3);
+    const __half_raw hi = __nv_cvt_fp8_to_halfraw(static_cast<__nv_fp8_storage_t>(pair >> 8), __NV_E4M3);
+    return uint32_t(lo.x) | (uint32_t(hi.x) << 16);
+}
 inline uint32_t sat8(int v) { return static_cast<uint32_t>(static_cast<uint8_t>(static_cast<int8_t>(v < -128 ? -128 : (v > 127 ? 127 : v)))); }
 // two cvt.pack.sat.s8.s32.b32: bytes (low -> high) = sat8(c0), sat8(c1), sat8(c2), sat8(c3)
 inline uint32_t pack_sat_s8x4(int c0, int c1, int c2, int c3) { return sat8(c0) | (sat8(c1) << 8) | (sat8(c2) << 16) | (sat8(c3) << 24); }
 
-// run fn() as a grid of `grid` CTAs of `threads` lock-stepped host threads each (CTAs one after another); the device code reads
-// threadIdx.x / blockIdx.x / gridDim.x through the stand-ins in prelude.h
+// run fn() as a grid of CTAs of `threads` lock-stepped host threads each (CTAs one after another); the device code reads
+// threadIdx.x / blockIdx / gridDim through the stand-ins in prelude.h
 template <typename F>
-void run_grid(int grid, int threads, F&& fn) {
+void run_grid(dim3 grid, int threads, F&& fn) {
     const int warps = (threads + 31) / 32;
     g_grid = grid;
-    for (int blk = 0; blk < grid; ++blk) {
-        g_block = blk;
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+    for (unsigned bx = 0; bx < grid.x; ++bx) {
+        g_block = dim3(bx, by, bz);
         pthread_barrier_init(&g_cta_barrier, nullptr, threads);
-        for (int w = 0; w < warps; ++w) pthread_barrier_init(&g_warp_barrier[w], nullptr, 32);
+        for (int w = 0; w < warps; ++w) pthread_barrier_init(&g_warp_barrier[w], nullptr, threads - 32 * w < 32 ? threads - 32 * w : 32);
         struct Arg { F* fn; int tid; } args[kMaxWarps * 32];
         pthread_t th[kMaxWarps * 32];
         for (int t = 0; t < threads; ++t) {
@@ -122,6 +131,8 @@ void run_grid(int grid, int threads, F&& fn) {
         for (int w = 0; w < warps; ++w) pthread_barrier_destroy(&g_warp_barrier[w]);
     }
 }
+template <typename F>
+void run_grid(int grid, int threads, F&& fn) { run_grid(dim3(grid), threads, static_cast<F&&>(fn)); }
 
 // one warp: fn(lane)
 template <typename F>

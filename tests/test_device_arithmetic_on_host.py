@@ -1,6 +1,7 @@
 """The per-lane arithmetic of the CUDA kernels, compiled for the host and checked against the oracle WITHOUT a GPU.
 
-`tests/host_emu/emu.cpp` includes `sdnq_b200/csrc/unpack.cuh` (and through it `common.cuh`) unchanged and is built with g++;
+`tests/host_emu/emu.cpp` includes `sdnq_b200/csrc/unpack.cuh` (and through it `common.cuh`) unchanged and is built with g++
+(together with the kernels' `.cu` files, see `tests/host_emu/build_emu.py` and `tests/test_emulated_gpu_suite.py`);
 `tests/host_emu/prelude.h` supplies host stand-ins for the few device intrinsics those headers use (`__byte_perm`,
 `__uint_as_float`, ...).  So the storage decoders (`load_octet_bytes` + `decode_octet`), the value decoders
 (`codes_to_values`: signed offset, every minifloat format, fp8) and the byte-permute fast path (`octet_to_floats`) that the
@@ -9,7 +10,6 @@ which is itself pinned to reference-generated fixtures (tests/test_oracle_golden
 proper; this is the CPU-only regression gate for the integer / bit-manipulation part of the kernels."""
 import ctypes
 import os
-import subprocess
 import zlib
 
 import numpy as np
@@ -30,13 +30,9 @@ W_INT, W_MINIFLOAT, W_E4M3, W_E5M2 = range(4)
 
 
 @pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    out = str(tmp_path_factory.mktemp("host_emu") / "libsdnq_emu.so")
-    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-w", "-pthread", "-ffp-contract=off", "-include", os.path.join(EMU_DIR, "prelude.h"), "-I", cuda_inc,
-           os.path.join(EMU_DIR, "emu.cpp"), "-o", out]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    assert r.returncode == 0, "host build of the device headers failed:\n" + r.stderr[-3000:]
+def emu():
+    from tests.host_emu import build_emu
+    out = build_emu.build()              # g++ build of the kernels' CUDA sources + tests/host_emu/emu.cpp (cached by content hash)
     lib = ctypes.CDLL(out)
     lib.emu_decode.argtypes = [ctypes.c_int, ctypes.c_int, P, ctypes.c_int64, P]
     lib.emu_values.argtypes = [ctypes.POINTER(WeightFormat), P, ctypes.c_int64, P]
@@ -466,7 +462,7 @@ def test_small_m_packed_forward_glue_on_the_emulator(emu, cfg, monkeypatch):
 # SDNQ_HOST_EMU, so the host dispatch code runs unchanged too.  rcp.approx is modelled by the correctly rounded reciprocal
 # (RowDivider refines either to the correctly rounded quotient); everything else is the device source.
 def _act_quant_emu(emu, x, dtype, mode, hadamard=0, ldx=None, want_rowsum=False, want_x_rot=False):
-    emu.emu_act_quant.argtypes = [P, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, P, P, P, P, P]
+    emu.sdnq_b200_act_quant.argtypes = [P, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, P, P, P, P, P, P]
     M, K = x.shape
     ldx = ldx or K
     code = {"float32": 0, "bfloat16": 1, "float16": 2}[dtype]
@@ -482,8 +478,8 @@ def _act_quant_emu(emu, x, dtype, mode, hadamard=0, ldx=None, want_rowsum=False,
     zx = np.full(M, np.nan, dtype=np.float32)
     rowsum = np.full(M, -12345, dtype=np.int32)
     x_rot = np.zeros((M, K), dtype=buf.dtype)
-    rc = emu.emu_act_quant(_ptr(buf), code, M, K, ldx, hadamard, mm, _ptr(xq), _ptr(sx), _ptr(zx) if mode == "uint8" else None,
-                           _ptr(rowsum) if want_rowsum else None, _ptr(x_rot) if want_x_rot else None)
+    rc = emu.sdnq_b200_act_quant(_ptr(buf), code, M, K, ldx, hadamard, mm, _ptr(xq), _ptr(sx), _ptr(zx) if mode == "uint8" else None,
+                                 _ptr(rowsum) if want_rowsum else None, _ptr(x_rot) if want_x_rot else None, None)
     assert rc == 0, rc
     return xq, sx, zx, rowsum, x_rot
 
