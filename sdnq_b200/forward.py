@@ -159,12 +159,14 @@ def _small_m_packed_ok(self, input) -> bool:
 def _small_m_packed_linear(self, x):
     d = self.sdnq_dequantizer
     N, K = d.matmul_nk()
+    if d.use_hadamard:      # x @ (W_rot H)^T = (x H) @ W_rot^T: rotate the (tiny) activation with K2 instead of un-rotating the weight
+        x = ops.act_quant(x, "int8", hadamard_group=d.hadamard_group_size, want_x_rot=True)[4].view(x.shape)
     return ops.linear_small_m_packed(x, self.weight, d.weights_dtype, self.scale, self.zero_point, N, K, bias=self.bias)
 
 
 @torch.no_grad()
 def quantized_linear_forward(self, input: torch.Tensor) -> torch.Tensor:
-    if (input.numel() // max(input.shape[-1], 1) < SMALL_M and not self.sdnq_dequantizer.use_hadamard and _small_m_packed_ok(self, input)):
+    if input.numel() // max(input.shape[-1], 1) < SMALL_M and _small_m_packed_ok(self, input):
         return _small_m_packed_linear(self, input)
     return _dequant_linear(self, input, skip_quantized_matmul=False)
 
@@ -189,11 +191,8 @@ def _w8a8_forward(self, input: torch.Tensor) -> torch.Tensor:
                 x = ops.act_quant(input, d.quantized_matmul_dtype, hadamard_group=d.hadamard_group_size, want_x_rot=True)[4].view(input.shape)
             return ops.linear_small_m(x, op.wq, op.sw, zp=op.zp, bias=self.bias)
         if (d.re_quantize_for_matmul or d.is_packed) and _small_m_packed_ok(self, input):
-            # packed / group-wise weights: K5p reads the stored bytes once (rotated layers: rotate the activation, as above)
-            x = input
-            if d.use_hadamard:
-                x = ops.act_quant(input, d.quantized_matmul_dtype, hadamard_group=d.hadamard_group_size, want_x_rot=True)[4].view(input.shape)
-            return _small_m_packed_linear(self, x)
+            # packed / group-wise weights: K5p reads the stored bytes once
+            return _small_m_packed_linear(self, input)
         return _dequant_linear(self, input, skip_quantized_matmul=True)
     op = matmul_operand(self)
     mm = d.quantized_matmul_dtype

@@ -50,7 +50,7 @@ def cases(func, keep=None):
         if mark.name != "parametrize":
             continue
         names = [n.strip() for n in mark.args[0].split(",")]
-        values = [v.values if hasattr(v, "values") else v for v in mark.args[1]]
+        values = [v.values if hasattr(v, "marks") else v for v in mark.args[1]]      # pytest.param(...) -> its values
         axes.append([dict(zip(names, v if len(names) > 1 else (v,))) for v in values])
     out = []
     for combo in itertools.product(*axes):
@@ -64,7 +64,13 @@ def cases(func, keep=None):
 
 def ident(kw):
     import os
-    return "-".join(os.path.basename(v)[6:-4] if isinstance(v, str) and v.endswith(".npz") else str(v).replace("torch.", "") for v in kw.values())
+    def one(v):
+        if isinstance(v, str) and v.endswith(".npz"):
+            return os.path.basename(v)[6:-4]
+        if isinstance(v, dict):
+            return "_".join(str(x) for x in v.values())
+        return str(v).replace("torch.", "")
+    return "-".join(one(v) for v in kw.values())
 
 
 def emulated(func, keep=None):
@@ -159,3 +165,43 @@ def test_conv_weight_dequant(kw):
 @emulated(C.test_conv_act_quant_matches_reference)
 def test_conv_act_quant(kw):
     C.test_conv_act_quant_matches_reference(**kw)
+
+
+# ---- layer level (SDNQConfig -> sdnq_quantize_layer -> forward_func -> ops -> C ABI) for every forward that does not need the tcgen05
+# GEMM: the dequant path (K3 + the library matmul, here torch's CPU matmul), the rows < 32 branches (K5, K5p, dequantise + matmul)
+from tests import test_layers_gpu as L  # noqa: E402
+from tests import test_zz_small_m_packed_gpu as Z  # noqa: E402
+from tests.util import fixture_tensors  # noqa: E402
+
+
+@pytest.fixture(scope="module", autouse=True)
+def layer_modules_on_cpu(emulated_library):
+    mp = pytest.MonkeyPatch()
+    mp.setattr(L, "DEV", "cpu")
+    mp.setattr(Z, "DEV", "cpu")
+    yield
+    mp.undo()
+
+
+@emulated(L.test_forward_matches_reference_output)
+def test_layer_forward_fixtures(kw):
+    _, _, meta = fixture_tensors(kw["path"])
+    if meta["dequantizer"]["use_quantized_matmul"] and meta["M"] >= 32:
+        pytest.skip("W8A8 with 32 or more rows runs the tcgen05 GEMM: GPU only")
+    L.test_forward_matches_reference_output(**kw)
+
+
+def _thin_small_m(kw):
+    """rotated layers run the rotated K3 over the whole weight as their reference path (seconds on the emulator): one M for those"""
+    return kw["M"] == 4 if kw["cfg"].get("use_hadamard") else kw["M"] in (1, 31)
+
+
+@emulated(L.test_small_m_forward_gemv_vs_dequant_path, keep=_thin_small_m)
+def test_small_m_forward_gemv(kw, monkeypatch):
+    L.test_small_m_forward_gemv_vs_dequant_path(monkeypatch=monkeypatch, **kw)
+
+
+@emulated(Z.test_small_m_packed_forward_vs_dequant_path, keep=_thin_small_m)
+def test_small_m_packed_forward(kw, monkeypatch):
+    """K5p at layer level: the very test that is its hardware gate (tests/test_zz_small_m_packed_gpu.py), on the emulator"""
+    Z.test_small_m_packed_forward_vs_dequant_path(monkeypatch=monkeypatch, **kw)

@@ -20,9 +20,10 @@ DEV = "cuda"
                                  dict(weights_dtype="float6_e3m2fn", group_size=32), dict(weights_dtype="int5", group_size=-1),
                                  dict(weights_dtype="int4", group_size=-1, use_quantized_matmul=True),
                                  dict(weights_dtype="int8", group_size=128, use_quantized_matmul=True),
-                                 dict(weights_dtype="uint4", use_quantized_matmul=True, use_hadamard=True, hadamard_group_size=256)],
+                                 dict(weights_dtype="uint4", use_quantized_matmul=True, use_hadamard=True, hadamard_group_size=256),
+                                 dict(weights_dtype="int4", group_size=64, use_hadamard=True, hadamard_group_size=128)],
                          ids=["int4_g128", "uint4_auto", "int2_g16", "float6_g32", "int5_rowwise", "int4_rowwise_w8a8", "int8_g128_w8a8",
-                              "uint4_hadamard_w8a8"])
+                              "uint4_hadamard_w8a8", "int4_g64_hadamard128"])
 @pytest.mark.parametrize("M", [1, 4, 31])
 def test_small_m_packed_forward_vs_dequant_path(cfg, M, monkeypatch):
     """rows < 32 of a layer stored packed / group-wise: K5p (SDNQ_B200_SMALL_M_PACKED=1, reads the stored bytes once) against the
@@ -30,8 +31,11 @@ def test_small_m_packed_forward_vs_dequant_path(cfg, M, monkeypatch):
     only the f32 accumulation order differs from the library GEMM."""
     from sdnq_b200 import SDNQConfig, _lib, sdnq_quantize_layer
     torch.manual_seed(11 + M)
-    lin = torch.nn.Linear(768, 1544, bias=True).to(torch.bfloat16)                 # N not a multiple of 16: a ragged last tile
+    # W8A8 needs N % 16 == 0 (utils.py:93-98), otherwise the layer silently takes the dequant forward; the others get a ragged last tile
+    w8a8 = bool(cfg.get("use_quantized_matmul"))
+    lin = torch.nn.Linear(768, 1552 if w8a8 else 1544, bias=True).to(torch.bfloat16)
     layer, _ = sdnq_quantize_layer(copy.deepcopy(lin), SDNQConfig(**cfg))
+    assert layer.forward_func.__name__.endswith("_matmul") == w8a8, layer.forward_func.__name__
     layer = layer.to(DEV)
     x = torch.randn(M, 768, dtype=torch.bfloat16, device=DEV)
     monkeypatch.setenv("SDNQ_B200_SMALL_M_PACKED", "1")
