@@ -34,7 +34,9 @@ def build() -> str:
         return lib
     os.makedirs(out_dir, exist_ok=True)
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    flags = ["-O1", "-std=c++17", "-fPIC", "-w", "-pthread", "-ffp-contract=off", "-include", os.path.join(HERE, "prelude.h"), "-I", cuda_inc, "-I", HERE]
+    # -fsanitize=alignment: x86 tolerates the misaligned vector loads / stores a GPU faults on; UBSan aborts on them instead
+    # (uint4 / float4 / uint2 carry their CUDA alignment on the host too), so the emulated runs also check every access's alignment
+    flags = ["-O1", "-std=c++17", "-fPIC", "-w", "-pthread", "-ffp-contract=off", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-include", os.path.join(HERE, "prelude.h"), "-I", cuda_inc, "-I", HERE]
 
     def compile_one(src):
         obj = os.path.join(out_dir, os.path.basename(src) + ".o")
@@ -47,7 +49,7 @@ def build() -> str:
     with ThreadPoolExecutor(max_workers=len(sources)) as ex:
         objs = list(ex.map(compile_one, sources))
     tmp = lib + f".{os.getpid()}.tmp"
-    r = subprocess.run(["g++", "-shared", "-pthread", "-o", tmp, *objs], capture_output=True, text=True)
+    r = subprocess.run(["g++", "-shared", "-pthread", "-fsanitize=alignment", "-o", tmp, *objs], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link of the host emulation failed:\n" + r.stderr[-4000:])
     os.replace(tmp, lib)

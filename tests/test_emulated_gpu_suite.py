@@ -205,3 +205,37 @@ def test_small_m_forward_gemv(kw, monkeypatch):
 def test_small_m_packed_forward(kw, monkeypatch):
     """K5p at layer level: the very test that is its hardware gate (tests/test_zz_small_m_packed_gpu.py), on the emulator"""
     Z.test_small_m_packed_forward_vs_dequant_path(monkeypatch=monkeypatch, **kw)
+
+
+def test_emulator_traps_misaligned_vector_access():
+    """x86 would silently execute the misaligned 16-byte loads a GPU faults on; the emulator is built with -fsanitize=alignment, so a
+    kernel that issues one aborts the process.  Shown here by handing K5p's body (which skips the entry point's own alignment check)
+    an activation pointer that is 2 bytes off."""
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent('''
+        import ctypes, sys
+        import numpy as np
+        sys.path.insert(0, ".")
+        from tests.host_emu import build_emu
+        lib = ctypes.CDLL(build_emu.build())
+        P = ctypes.c_void_p
+        class WF(ctypes.Structure):
+            _fields_ = [(n, ctypes.c_int32) for n in ("kind", "bits", "is_unsigned", "exponent", "mantissa", "word_bytes")]
+        M, N, K = 2, 16, 64
+        x = np.zeros(M * K + 8, dtype=np.uint16); w = np.zeros(N * K // 2 + 16, dtype=np.uint8)
+        s = np.ones(N, dtype=np.float32); out = np.zeros(M * N, dtype=np.uint16)
+        lib.emu_gemv_packed.argtypes = [P, ctypes.c_int, ctypes.c_int64, P, P, P, P, ctypes.c_int64, P, ctypes.c_int, ctypes.c_int64, P,
+                                        ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
+        fmt = WF(0, 4, 0, 0, 0, 1)
+        rc = lib.emu_gemv_packed(x.ctypes.data + int(sys.argv[1]), 1, K, w.ctypes.data, ctypes.addressof(fmt), s.ctypes.data, None, 0, None, 0, 0,
+                                 out.ctypes.data, M, N, K, 1)
+        print("rc", rc)
+    ''')
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ok = subprocess.run([sys.executable, "-c", code, "0"], capture_output=True, text=True, cwd=root, timeout=300)
+    assert ok.returncode == 0 and "rc 0" in ok.stdout, ok.stderr[-500:]
+    bad = subprocess.run([sys.executable, "-c", code, "2"], capture_output=True, text=True, cwd=root, timeout=300)
+    assert bad.returncode != 0 and "misaligned" in bad.stderr, (bad.returncode, bad.stderr[-500:])
