@@ -138,14 +138,14 @@ def _dequant_linear(layer, input, skip_quantized_matmul):
 
 
 def _small_m_packed_ok(self, input) -> bool:
-    """K5p applies to rows < 32 of a Linear whose weight is stored packed and / or with group-wise scales (no SVD, no codebook,
+    """K5p applies to rows < 32 of a Linear whose weight is stored packed and / or with group-wise scales (no codebook,
     no tensor-wise scale, 2..8 bits, scale groups that are multiples of 8 columns) and 16-bit activations: the stored bytes are read
     once instead of dequantise + GEMM.  Opt-in this round (SDNQ_B200_SMALL_M_PACKED=1): the kernel is validated against the oracle
     on the host emulator (tests/test_device_arithmetic_on_host.py); it becomes the default after its first run on hardware."""
     if os.environ.get("SDNQ_B200_SMALL_M_PACKED", "0") in ("0", "false", "no", ""):
         return False
     d = self.sdnq_dequantizer
-    if (d.use_codebook or d.group_size == -2 or self.svd_up is not None or self.weight.ndim > 3 or d.is_conv
+    if (d.use_codebook or d.group_size == -2 or self.weight.ndim > 3 or d.is_conv
             or input.dtype not in (torch.bfloat16, torch.float16) or input.numel() == 0):
         return False
     info = dtype_dict[d.weights_dtype]
@@ -161,7 +161,18 @@ def _small_m_packed_linear(self, x):
     N, K = d.matmul_nk()
     if d.use_hadamard:      # x @ (W_rot H)^T = (x H) @ W_rot^T: rotate the (tiny) activation with K2 instead of un-rotating the weight
         x = ops.act_quant(x, "int8", hadamard_group=d.hadamard_group_size, want_x_rot=True)[4].view(x.shape)
-    return ops.linear_small_m_packed(x, self.weight, d.weights_dtype, self.scale, self.zero_point, N, K, bias=self.bias)
+    bias = self.bias
+    if self.svd_up is not None:
+        # W = dequant + svd_up @ svd_down (dequantizer.py:69-79)  =>  y = x @ dequant^T + (x @ svd_down^T) @ svd_up^T: the rank-r term
+        # of these few rows is two skinny library GEMMs handed to the kernel as an [M,N] bias.  Factors are stored [N,r] / [r,K], or
+        # transposed ([r,N] / [K,r]) when the layer is in matmul layout (quantizer.py:164-167).
+        up, down = self.svd_up, self.svd_down
+        if not d.use_quantized_matmul:
+            up, down = up.t(), down.t()                     # -> [r,N], [K,r]
+        x2 = x.reshape(-1, K).to(down.dtype)
+        low = torch.mm(x2, down)
+        bias = torch.mm(low, up) if bias is None else torch.addmm(bias.to(down.dtype), low, up)
+    return ops.linear_small_m_packed(x, self.weight, d.weights_dtype, self.scale, self.zero_point, N, K, bias=bias)
 
 
 @torch.no_grad()

@@ -193,7 +193,7 @@ def test_layer_forward_fixtures(kw):
 
 def _thin_small_m(kw):
     """rotated layers run the rotated K3 over the whole weight as their reference path (seconds on the emulator): one M for those"""
-    return kw["M"] == 4 if kw["cfg"].get("use_hadamard") else kw["M"] in (1, 31)
+    return kw["M"] == 4 if (kw["cfg"].get("use_hadamard") or kw["cfg"].get("use_svd")) else kw["M"] in (1, 31)
 
 
 @emulated(L.test_small_m_forward_gemv_vs_dequant_path, keep=_thin_small_m)

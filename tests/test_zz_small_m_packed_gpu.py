@@ -21,9 +21,12 @@ DEV = "cuda"
                                  dict(weights_dtype="int4", group_size=-1, use_quantized_matmul=True),
                                  dict(weights_dtype="int8", group_size=128, use_quantized_matmul=True),
                                  dict(weights_dtype="uint4", use_quantized_matmul=True, use_hadamard=True, hadamard_group_size=256),
-                                 dict(weights_dtype="int4", group_size=64, use_hadamard=True, hadamard_group_size=128)],
+                                 dict(weights_dtype="int4", group_size=64, use_hadamard=True, hadamard_group_size=128),
+                                 dict(weights_dtype="int4", group_size=128, use_svd=True, svd_rank=32),
+                                 dict(weights_dtype="uint4", use_svd=True, svd_rank=16, use_quantized_matmul=True),
+                                 dict(weights_dtype="int4", group_size=128, use_svd=True, svd_rank=32, use_hadamard=True, hadamard_group_size=256)],
                          ids=["int4_g128", "uint4_auto", "int2_g16", "float6_g32", "int5_rowwise", "int4_rowwise_w8a8", "int8_g128_w8a8",
-                              "uint4_hadamard_w8a8", "int4_g64_hadamard128"])
+                              "uint4_hadamard_w8a8", "int4_g64_hadamard128", "int4_g128_svd32", "uint4_svd16_w8a8", "int4_g128_svd32_hadamard256"])
 @pytest.mark.parametrize("M", [1, 4, 31])
 def test_small_m_packed_forward_vs_dequant_path(cfg, M, monkeypatch):
     """rows < 32 of a layer stored packed / group-wise: K5p (SDNQ_B200_SMALL_M_PACKED=1, reads the stored bytes once) against the
@@ -44,10 +47,10 @@ def test_small_m_packed_forward_vs_dequant_path(cfg, M, monkeypatch):
     n_launch = _lib.launch_count()
     monkeypatch.setenv("SDNQ_B200_SMALL_M_PACKED", "0")
     y_ref = layer(x)
-    assert n_launch == (2 if cfg.get("use_hadamard") else 1), n_launch
+    assert n_launch == (2 if cfg.get("use_hadamard") else 1), n_launch              # (the SVD term's two skinny GEMMs are library calls)
     assert y.shape == y_ref.shape and y.dtype == y_ref.dtype and bool(torch.isfinite(y).all())
     scale = float(y_ref.float().abs().max())
     err = (y.float() - y_ref.float()).abs()
     assert float(err.max()) <= 2e-2 * scale and float(err.pow(2).mean().sqrt()) <= 3e-3 * scale
-    if not cfg.get("use_hadamard"):      # same bf16 weights, f32 accumulation: at most the last bf16 bit of an output moves
+    if not cfg.get("use_hadamard") and not cfg.get("use_svd"):      # same bf16 weights, f32 accumulation: at most the last bf16 bit of an output moves
         assert int(bf16_ulp_diff(y, y_ref).max()) <= 2 or float(err.max()) <= 2.0 ** -7 * scale
