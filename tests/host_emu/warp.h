@@ -108,28 +108,32 @@ inline uint32_t pack_sat_s8x4(int c0, int c1, int c2, int c3) { return sat8(c0) 
 template <typename F>
 void run_grid(dim3 grid, int threads, F&& fn) {
     const int warps = (threads + 31) / 32;
+    const unsigned total = grid.x * grid.y * grid.z;
     g_grid = grid;
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-    for (unsigned bx = 0; bx < grid.x; ++bx) {
-        g_block = dim3(bx, by, bz);
-        pthread_barrier_init(&g_cta_barrier, nullptr, threads);
-        for (int w = 0; w < warps; ++w) pthread_barrier_init(&g_warp_barrier[w], nullptr, threads - 32 * w < 32 ? threads - 32 * w : 32);
-        struct Arg { F* fn; int tid; } args[kMaxWarps * 32];
-        pthread_t th[kMaxWarps * 32];
-        for (int t = 0; t < threads; ++t) {
-            args[t] = {&fn, t};
-            pthread_create(&th[t], nullptr, [](void* p) -> void* {
-                Arg* a = static_cast<Arg*>(p);
-                t_tid = a->tid;
+    pthread_barrier_t between;                            // separates consecutive CTAs (distinct from the kernel's own __syncthreads barrier)
+    pthread_barrier_init(&between, nullptr, threads);
+    pthread_barrier_init(&g_cta_barrier, nullptr, threads);
+    for (int w = 0; w < warps; ++w) pthread_barrier_init(&g_warp_barrier[w], nullptr, threads - 32 * w < 32 ? threads - 32 * w : 32);
+    struct Arg { F* fn; int tid; unsigned total; dim3 grid; pthread_barrier_t* between; } args[kMaxWarps * 32];
+    pthread_t th[kMaxWarps * 32];
+    for (int t = 0; t < threads; ++t) {
+        args[t] = {&fn, t, total, grid, &between};
+        pthread_create(&th[t], nullptr, [](void* p) -> void* {        // one host thread per CUDA thread, reused for every CTA of the grid
+            Arg* a = static_cast<Arg*>(p);
+            t_tid = a->tid;
+            for (unsigned b = 0; b < a->total; ++b) {
+                if (a->tid == 0) g_block = dim3(b % a->grid.x, (b / a->grid.x) % a->grid.y, b / (a->grid.x * a->grid.y));
+                pthread_barrier_wait(a->between);
                 (*a->fn)();
-                return nullptr;
-            }, &args[t]);
-        }
-        for (int t = 0; t < threads; ++t) pthread_join(th[t], nullptr);
-        pthread_barrier_destroy(&g_cta_barrier);
-        for (int w = 0; w < warps; ++w) pthread_barrier_destroy(&g_warp_barrier[w]);
+                pthread_barrier_wait(a->between);
+            }
+            return nullptr;
+        }, &args[t]);
     }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], nullptr);
+    pthread_barrier_destroy(&between);
+    pthread_barrier_destroy(&g_cta_barrier);
+    for (int w = 0; w < warps; ++w) pthread_barrier_destroy(&g_warp_barrier[w]);
 }
 template <typename F>
 void run_grid(int grid, int threads, F&& fn) { run_grid(dim3(grid), threads, static_cast<F&&>(fn)); }
