@@ -538,3 +538,55 @@ def test_act_quant_with_rotation_on_emulated_ctas(emu, G, K, mode):
     x_ref = O.rotate_hadamard(x, G, "bfloat16")
     np.testing.assert_array_equal(O.from_bf16_bits(x_rot), x_ref)
     _check_codes(mode, xq, sx, zx, rowsum, x_ref, want_rowsum=mode != "fp8")
+
+
+def test_small_m_packed_kernel_never_reads_or_writes_past_its_buffers():
+    """memcheck on the CPU: every buffer K5p touches ends right before an inaccessible page (tests/host_emu/guarded.py), so an
+    overrun of the stored weight, the scales, the activations, the bias or the output kills the (sub)process."""
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent('''
+        import ctypes, sys
+        import numpy as np
+        sys.path.insert(0, ".")
+        from oracle import sdnq_oracle as O
+        from tests.host_emu import build_emu
+        from tests.host_emu.guarded import guarded
+        from tests.test_device_arithmetic_on_host import GEMV_CASES, WeightFormat, _stored_weight, _bits_of, _from_bits, _round_to
+        lib = ctypes.CDLL(build_emu.build())
+        P = ctypes.c_void_p
+        lib.sdnq_b200_linear_small_m_packed.argtypes = [P, ctypes.c_int, ctypes.c_int64, P, ctypes.POINTER(WeightFormat), P, P, ctypes.c_int64, P,
+                                                        ctypes.c_int, ctypes.c_int64, P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, P]
+        ran = 0
+        for name, group, M, N, K, bias_kind, dtype in GEMV_CASES:
+            if (N * K * O.dtype_info(name)["num_bits"] // 8) % 16 or (M * K * 2) % 16:
+                continue                                   # the guarded copy must both end at the page boundary and start 16-byte aligned
+            rng = np.random.default_rng(ran)
+            raw, q, fmt = _stored_weight(rng, name, N, K, False)
+            g = group or K
+            scale = (rng.random((N, K // g)).astype(np.float32) + 0.5) * np.float32(0.02)
+            zp = (rng.standard_normal((N, K // g)).astype(np.float32) * np.float32(0.1)) if O.dtype_info(name)["is_unsigned"] else None
+            x = _round_to(rng.standard_normal((M, K)).astype(np.float32), dtype)
+            gx, gw, gs = guarded(_bits_of(x, dtype)), guarded(raw), guarded(scale, 4)
+            gz = None if zp is None else guarded(zp, 4)
+            bias = _round_to(rng.standard_normal(N).astype(np.float32), dtype)
+            gb = guarded(_bits_of(bias, dtype), 2) if bias_kind != "none" else None
+            gout = guarded(np.zeros((M, N), dtype=np.uint16), 2)
+            code = 1 if dtype == "bfloat16" else 2
+            rc = lib.sdnq_b200_linear_small_m_packed(gx.ctypes.data, code, K, gw.ctypes.data, ctypes.byref(fmt), gs.ctypes.data,
+                                                     None if gz is None else gz.ctypes.data, group, None if gb is None else gb.ctypes.data, code, 0,
+                                                     gout.ctypes.data, M, N, K, None)
+            assert rc == 0, (name, rc)
+            s_full = np.repeat(scale, g, axis=1)
+            W = _round_to(O.fma32(q, s_full, np.repeat(zp, g, axis=1)) if zp is not None else (q * s_full).astype(np.float32), dtype)
+            want = x.astype(np.float64) @ W.astype(np.float64).T + (0 if gb is None else bias)
+            got = _from_bits(np.array(gout), dtype)
+            assert np.abs(got - want).max() <= 2e-2 * np.abs(want).max(), name
+            ran += 1
+        print("guarded cases", ran)
+        assert ran >= 8
+    ''')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=600)
+    assert r.returncode == 0 and "guarded cases" in r.stdout, (r.returncode, r.stdout[-300:], r.stderr[-1500:])
