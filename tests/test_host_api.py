@@ -313,3 +313,21 @@ def test_load_reference_written_checkpoint(name, tmp_path):
     save_sdnq_model(model, str(tmp_path))
     assert sorted(os.listdir(tmp_path)) == ["model.safetensors", "quantization_config.json"]
     check(load_sdnq_state_dict(toy_model.build(seed=7), str(tmp_path)))
+
+
+@pytest.mark.parametrize("cfg", [dict(weights_dtype="int8", use_quantized_matmul=True), dict(weights_dtype="int4", group_size=32),
+                                 dict(weights_dtype="float8_e4m3fn", use_quantized_matmul=True, use_hadamard=True, hadamard_group_size=64)],
+                         ids=["w8a8", "dequant_path", "fp8_hadamard"])
+@pytest.mark.parametrize("rows", [4, 40])
+def test_no_cpu_fallback_anywhere_on_the_forward(cfg, rows):
+    """north_star: no CPU / eager fallback.  A CPU tensor raises from every forward (W8A8, dequant path, the rows < 32 branches)
+    instead of being computed some other way."""
+    import torch
+
+    from sdnq_b200 import SDNQConfig, sdnq_quantize_layer
+    from sdnq_b200._lib import SDNQKernelError
+    layer, _ = sdnq_quantize_layer(torch.nn.Linear(64, 64).to(torch.bfloat16), SDNQConfig(minimum_allowed_numel=1, **cfg))
+    with pytest.raises(SDNQKernelError, match="CUDA"):
+        layer(torch.randn(rows, 64, dtype=torch.bfloat16))
+    with pytest.raises(SDNQKernelError, match="CUDA"):
+        layer.dequantize()
