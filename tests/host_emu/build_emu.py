@@ -48,8 +48,9 @@ def build() -> str:
     sources = [os.path.join(HERE, "emu.cpp")] + [os.path.join(CSRC, s) for s in KERNEL_SOURCES]
     with ThreadPoolExecutor(max_workers=len(sources)) as ex:
         objs = list(ex.map(compile_one, sources))
+    # -Bsymbolic: the two CUDA runtime stubs of emu.cpp must win over a libcudart that torch has already loaded globally
     tmp = lib + f".{os.getpid()}.tmp"
-    r = subprocess.run(["g++", "-shared", "-pthread", "-fsanitize=alignment", "-o", tmp, *objs], capture_output=True, text=True)
+    r = subprocess.run(["g++", "-shared", "-pthread", "-fsanitize=alignment", "-Wl,-Bsymbolic", "-o", tmp, *objs], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link of the host emulation failed:\n" + r.stderr[-4000:])
     os.replace(tmp, lib)

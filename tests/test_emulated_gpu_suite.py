@@ -239,3 +239,15 @@ def test_emulator_traps_misaligned_vector_access():
     assert ok.returncode == 0 and "rc 0" in ok.stdout, ok.stderr[-500:]
     bad = subprocess.run([sys.executable, "-c", code, "2"], capture_output=True, text=True, cwd=root, timeout=300)
     assert bad.returncode != 0 and "misaligned" in bad.stderr, (bad.returncode, bad.stderr[-500:])
+
+
+@emulated(C.test_conv_forward_matches_reference_output)
+def test_conv_forward_fixtures(kw):
+    """quantized conv forwards at layer level: the dequant path (K3c + the library convolution, here torch's CPU convolution) and
+    the rows < 32 branch; W8A8 convolutions reach the tcgen05 GEMM, which the emulated library does not export"""
+    try:
+        C.test_conv_forward_matches_reference_output(**kw)
+    except AttributeError as e:
+        if "scaled_mm" not in str(e):
+            raise
+        pytest.skip("W8A8 convolution: runs the tcgen05 GEMM, GPU only")
