@@ -251,3 +251,25 @@ def test_conv_forward_fixtures(kw):
         if "scaled_mm" not in str(e):
             raise
         pytest.skip("W8A8 convolution: runs the tcgen05 GEMM, GPU only")
+
+
+@emulated(L.test_dequantize_restores_module)
+def test_dequantize_restores_module(kw):
+    try:
+        L.test_dequantize_restores_module(**kw)
+    except AttributeError as e:
+        if "scaled_mm" not in str(e) and "linear_w8a8" not in str(e):
+            raise
+        pytest.skip("the quantised forward of this fixture runs the tcgen05 GEMM: GPU only")
+
+
+@emulated(L.test_dynamic_quantization_picks_the_reference_dtypes)
+def test_dynamic_quantization(kw):
+    """use_dynamic_quantization: the per-layer dtype search dequantises every trial through K3 -- the dtypes it picks equal the
+    reference's run (tests/golden/model_dynamic.json) on the emulator as on the GPU"""
+    try:
+        L.test_dynamic_quantization_picks_the_reference_dtypes(**kw)
+    except AttributeError as e:
+        if "scaled_mm" not in str(e) and "linear_w8a8" not in str(e):
+            raise
+        pytest.skip("the model forward at the end of this case runs the tcgen05 GEMM: GPU only")
