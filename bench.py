@@ -1,21 +1,30 @@
-"""Benchmark of the quantized-Linear hot path (contract: see the repo brief).
+"""Benchmark of the quantized-Linear hot path (contract: see the repo brief; DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sdxl_int8|flux_fp8] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
 
 One "step" = one pass over every SDNQ-quantised Linear of one denoise step of the named model on synthetic activations of
 the real shapes, each layer with its own random weights quantised through the public API
-(`sdnq_quantize_layer(nn.Linear, SDNQConfig)`), run through `SDNQLinear.forward` -> C ABI -> sm_100a kernels.
+(`sdnq_quantize_layer(nn.Linear, SDNQConfig)`), run through `SDNQLinear.forward` -> C ABI -> sm_100a kernels.  Layers that share
+an input in the real model (to_q / to_k / to_v of one attention block, the cross-attention to_k / to_v of every block, FLUX
+single-block proj_mlp) are fed the same tensor; every other layer gets its own buffer.
 
-  value  whole-job TFLOP/s (2*M*N*K over all Linears of the step), inputs resident in HBM, step replayed as a CUDA graph
-  e2e    same metric through the same call with HOST inputs: pinned host -> device copy of the step inputs and a device ->
-         host read of the step output inside the timed region
-  roofline      the dominant kernel (tcgen05 W8A8 GEMM): algorithmic FLOPs of all its launches in a step / their CUDA-event time
-                (the launches replayed back to back as a graph, activations L2-hot and weights cold exactly as in the step)
-  cpu_baseline  the oracle port (numpy) on the host cores, bounded sample of the same workload
+Headline (default) workload: `flux_fp8` = BASELINE.json configs[2] (FLUX.1-dev fp8 + Hadamard(256), 4 images per GPU; with
+--gpus N it is configs[4]: batch 4N sharded over N GPUs).  Without --workload the same run also measures `sdxl_int8`
+(configs[1]) and `sdxl_int4_svd_dequant` (configs[3]) and nests their lines under "workloads".
+
+  value         whole-job TFLOP/s (2*M*N*K over all Linears of the step), inputs resident in HBM, step replayed as a CUDA graph
+  e2e           same metric through the same call with HOST inputs: pinned host -> device copy of the step inputs and a device ->
+                host read of the step output inside the timed region
+  peaks         8-bit dense tensor peak measured in this run (cuBLASLt int8 / fp8 8192^3, burst and sustained)
+  roofline      the dominant kernel: algorithmic FLOPs (bytes) of all its launches in a step / their CUDA-event time
+                (the launches replayed back to back as a graph), against the measured peak
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, a scripted copy of its package) on the host cores: CPU-eager path,
+                all cores, bounded sample of the same workload
+  gpu_reference the reference's own GPU paths on this B200 (Triton scaled-mm kernel; CUDA eager = cuBLASLt), same layer shapes
 
 N > 1 (torchrun): every rank runs the same stack on its own batch shard (weights replicated, no data-path collective), one
 NCCL all_gather of the step output per step; time = max over ranks; scaling = weak.
-`--impl reference`: the reference's CPU algorithm (oracle port) on the host cores, rank 0 only.
+`--impl reference`: the reference's CPU-eager path on the host cores (rank 0 only), same metric / config.
 """
 import argparse
 import json
@@ -32,58 +41,83 @@ if ROOT not in sys.path:
 
 
 # ------------------------------------------------------------------------------------------------ workloads
-def sdxl_linears():
-    """SD-XL UNet, bs = 1, 1024x1024 (latents 128^2): 4096 tokens at C = 640 (10 transformer layers in 5 Transformer2DModels),
-    1024 tokens at C = 1280 (60 layers in 6 models), 77 text tokens of width 2048; plus the M = batch Linears the reference also
-    quantises (ResNet time_emb_proj, add_embedding) which take the small-M dequant path.  -> list of (name, M, N, K)."""
+# a layer is (name, M, N, K, src): src names the tensor that feeds it -- layers with the same src share one input buffer
+def sdxl_linears(batch=1):
+    """SD-XL UNet, 1024x1024 (latents 128^2), `batch` images: 4096 tokens per image at C = 640 (10 transformer layers in 5
+    Transformer2DModels), 1024 at C = 1280 (60 layers in 6 models), 77 text tokens of width 2048 (one encoder_hidden_states
+    tensor feeds the cross-attention to_k / to_v of every block); plus the M = batch Linears the reference also quantises
+    (ResNet time_emb_proj, add_embedding), which take the small-M path."""
     layers = []
-    for C, M, models, per_model in ((640, 4096, 5, 2), (1280, 1024, 6, 10)):
+    for C, tokens, models, per_model in ((640, 4096, 5, 2), (1280, 1024, 6, 10)):
+        M = tokens * batch
         for t in range(models):
-            layers.append((f"c{C}.t{t}.proj_in", M, C, C))
+            layers.append((f"c{C}.t{t}.proj_in", M, C, C, f"c{C}.t{t}.in"))
             for blk in range(per_model):
                 p = f"c{C}.t{t}.b{blk}"
-                layers += [(f"{p}.attn1.to_q", M, C, C), (f"{p}.attn1.to_k", M, C, C), (f"{p}.attn1.to_v", M, C, C), (f"{p}.attn1.to_out", M, C, C),
-                           (f"{p}.attn2.to_q", M, C, C), (f"{p}.attn2.to_k", 77, C, 2048), (f"{p}.attn2.to_v", 77, C, 2048),
-                           (f"{p}.attn2.to_out", M, C, C), (f"{p}.ff.proj", M, 8 * C, C), (f"{p}.ff.out", M, C, 4 * C)]
-            layers.append((f"c{C}.t{t}.proj_out", M, C, C))
+                layers += [(f"{p}.attn1.to_q", M, C, C, f"{p}.norm1"), (f"{p}.attn1.to_k", M, C, C, f"{p}.norm1"), (f"{p}.attn1.to_v", M, C, C, f"{p}.norm1"),
+                           (f"{p}.attn1.to_out", M, C, C, f"{p}.attn1.o"), (f"{p}.attn2.to_q", M, C, C, f"{p}.norm2"),
+                           (f"{p}.attn2.to_k", 77 * batch, C, 2048, "context"), (f"{p}.attn2.to_v", 77 * batch, C, 2048, "context"),
+                           (f"{p}.attn2.to_out", M, C, C, f"{p}.attn2.o"), (f"{p}.ff.proj", M, 8 * C, C, f"{p}.norm3"), (f"{p}.ff.out", M, C, 4 * C, f"{p}.ff.h")]
+            layers.append((f"c{C}.t{t}.proj_out", M, C, C, f"c{C}.t{t}.out"))
     for i, c_out in enumerate([320] * 2 + [640] * 2 + [1280] * 2 + [1280] * 2 + [1280] * 3 + [640] * 3 + [320] * 3):
-        layers.append((f"resnet{i}.time_emb_proj", 1, c_out, 1280))
-    layers += [("add_embedding.linear_1", 1, 1280, 2816), ("add_embedding.linear_2", 1, 1280, 1280)]
+        layers.append((f"resnet{i}.time_emb_proj", batch, c_out, 1280, f"resnet{i}.temb"))
+    layers += [("add_embedding.linear_1", batch, 1280, 2816, "add_emb.in"), ("add_embedding.linear_2", batch, 1280, 1280, "add_emb.h")]
     return layers
 
 
 def flux_linears(batch=4):
-    """FLUX.1-dev DiT, 1024x1024, bs = `batch`: 4096 image tokens + 512 text tokens per image, D = 3072; 19 double blocks
-    (separate image / text streams), 38 single blocks; AdaLN Linears have M = batch (small-M path)."""
+    """FLUX.1-dev DiT, 1024x1024, `batch` images: 4096 image tokens + 512 text tokens per image, D = 3072; 19 double blocks
+    (separate image / text streams; q / k / v of a stream share the normed hidden states), 38 single blocks (q / k / v / proj_mlp
+    share them); AdaLN Linears have M = batch (small-M path)."""
     D, layers = 3072, []
     mi, mt = 4096 * batch, 512 * batch
     for b in range(19):
         for stream, M in (("img", mi), ("txt", mt)):
             p = f"double{b}.{stream}"
-            layers += [(f"{p}.norm1.linear", batch, 6 * D, D), (f"{p}.to_q", M, D, D), (f"{p}.to_k", M, D, D), (f"{p}.to_v", M, D, D),
-                       (f"{p}.to_out", M, D, D), (f"{p}.ff.proj", M, 4 * D, D), (f"{p}.ff.out", M, D, 4 * D)]
+            layers += [(f"{p}.norm1.linear", batch, 6 * D, D, f"double{b}.temb"), (f"{p}.to_q", M, D, D, f"{p}.norm1"), (f"{p}.to_k", M, D, D, f"{p}.norm1"),
+                       (f"{p}.to_v", M, D, D, f"{p}.norm1"), (f"{p}.to_out", M, D, D, f"{p}.attn.o"), (f"{p}.ff.proj", M, 4 * D, D, f"{p}.norm2"),
+                       (f"{p}.ff.out", M, D, 4 * D, f"{p}.ff.h")]
     for b in range(38):
         p, M = f"single{b}", mi + mt
         if b > 0:
-            layers.append((f"{p}.norm.linear", batch, 3 * D, D))
-        layers += [(f"{p}.to_q", M, D, D), (f"{p}.to_k", M, D, D), (f"{p}.to_v", M, D, D), (f"{p}.proj_mlp", M, 4 * D, D),
-                   (f"{p}.proj_out", M, D, 5 * D)]
+            layers.append((f"{p}.norm.linear", batch, 3 * D, D, f"{p}.temb"))
+        layers += [(f"{p}.to_q", M, D, D, f"{p}.norm"), (f"{p}.to_k", M, D, D, f"{p}.norm"), (f"{p}.to_v", M, D, D, f"{p}.norm"),
+                   (f"{p}.proj_mlp", M, 4 * D, D, f"{p}.norm"), (f"{p}.proj_out", M, D, 5 * D, f"{p}.cat")]
     return layers
 
 
 WORKLOADS = {
-    "sdxl_int8": dict(describe="SD-XL UNet int8 W8A8 (use_quantized_matmul=True), bs=1, 1024x1024: all quantised Linears of one denoise step",
-                      layers=sdxl_linears, config=dict(weights_dtype="int8", use_quantized_matmul=True), dtype="int8"),
-    "sdxl_int4_svd_dequant": dict(describe="SD-XL UNet int4 group_size=128 + SVD rank 32, dequant-to-bf16-GEMM path (use_quantized_matmul=False), bs=1, 1024x1024",
-                                  layers=sdxl_linears, config=dict(weights_dtype="int4", group_size=128, use_svd=True, svd_rank=32), dtype="bf16"),
-    "flux_fp8": dict(describe="FLUX.1-dev DiT float8_e4m3fn + Hadamard(256) W8A8, bs=4, 1024x1024: all quantised Linears of one denoise step",
-                     layers=flux_linears, config=dict(weights_dtype="float8_e4m3fn", use_quantized_matmul=True, use_hadamard=True, hadamard_group_size=256),
-                     dtype="f8e4m3"),
+    "flux_fp8": dict(describe="FLUX.1-dev DiT float8_e4m3fn + Hadamard(256) W8A8, 4 images per GPU, 1024x1024: all quantised Linears of one denoise step "
+                              "(BASELINE configs[2]; with N GPUs configs[4]: batch 4N sharded)",
+                     layers=flux_linears, batch_per_gpu=4, dtype="f8e4m3", model="FLUX.1-dev",
+                     config=dict(weights_dtype="float8_e4m3fn", use_quantized_matmul=True, use_hadamard=True, hadamard_group_size=256)),
+    "sdxl_int8": dict(describe="SD-XL UNet int8 W8A8 (use_quantized_matmul=True), 1 image per GPU, 1024x1024: all quantised Linears of one denoise step "
+                               "(BASELINE configs[1])",
+                      layers=sdxl_linears, batch_per_gpu=1, dtype="int8", model="SD-XL UNet",
+                      config=dict(weights_dtype="int8", use_quantized_matmul=True)),
+    "sdxl_int4_svd_dequant": dict(describe="SD-XL UNet int4 group_size=128 + SVD rank 32, dequant path (use_quantized_matmul=False), 1 image per GPU, 1024x1024 "
+                                           "(BASELINE configs[3])",
+                                  layers=sdxl_linears, batch_per_gpu=1, dtype="bf16", model="SD-XL UNet",
+                                  config=dict(weights_dtype="int4", group_size=128, use_svd=True, svd_rank=32)),
 }
+HEADLINE = "flux_fp8"
+NESTED = ("sdxl_int8", "sdxl_int4_svd_dequant")
 
 
 def total_flops(layers):
-    return sum(2.0 * m * n * k for _, m, n, k in layers)
+    return sum(2.0 * m * n * k for _, m, n, k, _ in layers)
+
+
+def workload_config(name, world):
+    """The workload definition, identical for every arm (ours / reference): nothing device- or implementation-specific in it."""
+    spec = WORKLOADS[name]
+    layers = spec["layers"](spec["batch_per_gpu"])
+    weight_gb = sum(n * k for _, _, n, k, _ in layers) * (0.5 if "int4" in name else 1.0) / 1e9
+    return {"workload": name, "describe": spec["describe"], "model_shapes": spec["model"], "sdnq_config": spec["config"],
+            "linears_per_step": len(layers), "gflop_per_step_per_gpu": total_flops(layers) / 1e9,
+            "batch_per_gpu": spec["batch_per_gpu"], "global_batch": spec["batch_per_gpu"] * world, "parallelism": f"dp{world}",
+            "l2": f"each Linear has its own weights ({weight_gb:.1f} GB per step >> 126 MB L2) and non-sibling layers their own activation buffers: "
+                  "weights stream from HBM every step, no flush needed"}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -125,82 +159,203 @@ class ClockSampler:
                 "power_w_max": max(num(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
 
 
-# ------------------------------------------------------------------------------------------------ CPU oracle arm
-def cpu_oracle_sample(workload, budget_s=15.0, seed=0):
-    """Time the numpy oracle (reference algorithm restated) on a bounded sample: one layer of each distinct (N, K) with M capped
-    at 256 rows; throughput is FLOPs of what was actually computed / wall time."""
-    import numpy as np
+# ------------------------------------------------------------------------------------------------ the reference itself
+CPU_M_CAP = 4096
 
-    from oracle import sdnq_oracle as O
+
+def reference_sample_shapes(workload, m_cap=None):
+    """One layer per distinct (M, N, K) of the workload's W8A8 / dequant-path GEMMs (M >= 32), with its multiplicity."""
     spec = WORKLOADS[workload]
-    rng = np.random.default_rng(seed)
-    shapes, seen = [], set()
-    for _, m, n, k in spec["layers"]():
-        if (n, k) not in seen and m >= 32:
-            seen.add((n, k))
-            shapes.append((min(m, 256), n, k))
-    fp8 = spec["config"]["weights_dtype"].startswith("float8")
-    hg = spec["config"].get("hadamard_group_size", 256) if spec["config"].get("use_hadamard") else 0
-    prepared = []
-    dequant_path = not spec["config"].get("use_quantized_matmul", False)
-    for m, n, k in shapes:
-        w = (rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32)
-        if dequant_path:       # int4 g128 + SVD rank 32: packed codes, group scales, low-rank factors; dequant then f32 GEMM
-            gs, r = spec["config"]["group_size"], spec["config"]["svd_rank"]
-            wg = w.reshape(n, k // gs, gs)
-            sc = (np.abs(wg).max(axis=-1, keepdims=True) / 7).astype(np.float32)
-            codes = np.clip(np.rint(wg / sc), -8, 7).astype(np.int64)
-            layer = O.Layer(O.pack_int(codes, "int4"), sc, None, O.bf16_round(rng.standard_normal((n, r)).astype(np.float32) * 0.05),
-                            O.bf16_round(rng.standard_normal((r, k)).astype(np.float32) * 0.05),
-                            bias=O.bf16_round(rng.standard_normal(n).astype(np.float32)), weights_dtype="int4", quantized_weight_shape=[n, k // gs, gs],
-                            result_shape=[n, k], group_size=gs, use_quantized_matmul=False)
-            x = O.bf16_round(rng.standard_normal((m, k)).astype(np.float32))
-            prepared.append((layer, x, 2.0 * m * n * k))
-            continue
-        if fp8:
-            wq, sw = O.quantize_fp_mm(w, axis=-1)
-        else:
-            wq, sw = O.quantize_int_mm(w, axis=-1)
-        meta = dict(weights_dtype=spec["config"]["weights_dtype"], quantized_matmul_dtype="float8_e4m3fn" if fp8 else "int8",
-                    quantized_weight_shape=[k, n], group_size=-1, use_quantized_matmul=True, use_hadamard=bool(hg),
-                    hadamard_group_size=hg if hg and k % hg == 0 else 128)
-        layer = O.Layer(np.ascontiguousarray(wq.T), np.ascontiguousarray(sw.T), bias=O.bf16_round(rng.standard_normal(n).astype(np.float32)), **meta)
-        x = O.bf16_round(rng.standard_normal((m, k)).astype(np.float32))
-        prepared.append((layer, x, 2.0 * m * n * k))
-    flops, t0, reps = 0.0, time.perf_counter(), 0
-    while True:
-        for layer, x, fl in prepared:
-            O.linear_forward(layer, x)
-            flops += fl
-        reps += 1
-        if time.perf_counter() - t0 >= budget_s:
-            break
+    count = {}
+    for _, m, n, k, _ in spec["layers"](spec["batch_per_gpu"]):
+        if m >= 32:
+            key = (min(m, m_cap) if m_cap else m, n, k)
+            count[key] = count.get(key, 0) + 1
+    return sorted(count.items())
+
+
+def _reference_layers(workload, device, dtype, m_cap):
+    """Quantise one nn.Linear per sample shape with the REFERENCE's own sdnq_quantize_layer and SDNQConfig."""
+    import torch
+
+    from oracle.ref_loader import load_reference
+    sdnq = load_reference()
+    from sdnq.quantizer import sdnq_quantize_layer as ref_quantize_layer
+    spec = WORKLOADS[workload]
+    torch.manual_seed(1234)
+    out = []
+    for (m, n, k), mult in reference_sample_shapes(workload, m_cap):
+        lin = torch.nn.Linear(k, n, bias=True, device=device, dtype=dtype)
+        layer = ref_quantize_layer(lin, sdnq.SDNQConfig(**spec["config"]))[0]
+        x = torch.randn(m, k, device=device, dtype=dtype)
+        out.append((m, n, k, mult, layer, x))
+    return out
+
+
+def cpu_reference_run(workload, steps, warmup, budget_s=None):
+    """The unmodified reference on the host cores: CPU-eager path (SDNQ_DEVICE=cpu, SDNQ_USE_TORCH_COMPILE=0; model dtype fp32
+    as sdnext.py:44 picks for CPU), every host thread, one step = one forward of one layer per distinct shape of the workload with
+    M capped at CPU_M_CAP rows.  -> (TFLOP/s, seconds per step, cpu_baseline dict)."""
+    os.environ["SDNQ_DEVICE"] = "cpu"
+    os.environ["SDNQ_USE_TORCH_COMPILE"] = "0"
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)                    # torchrun exports OMP_NUM_THREADS=1: override it for the host arm
+    layers = _reference_layers(workload, torch.device("cpu"), torch.float32, CPU_M_CAP)
+    flops = sum(2.0 * m * n * k for m, n, k, _, _, _ in layers)
+
+    def one_step():
+        with torch.no_grad():
+            for _, _, _, _, layer, x in layers:
+                layer(x)
+    t_w0 = time.perf_counter()
+    for _ in range(max(warmup, 1)):
+        one_step()
+    per_step = (time.perf_counter() - t_w0) / max(warmup, 1)
+    if budget_s is not None:
+        steps = max(1, min(steps, int(budget_s / max(per_step, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
     dt = time.perf_counter() - t0
-    return {"value": flops / dt / 1e12, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{len(prepared)} layers (one per distinct NxK of the workload, M capped at 256 rows) x {reps} passes, numpy oracle port of the reference CPU-eager path, {dt:.1f} s"}
+    value = flops * steps / dt / 1e12
+    from oracle.ref_loader import reference_root
+    info = {"value": value, "unit": "TFLOP/s", "cores": cores, "threads": torch.get_num_threads(), "kind": "reference",
+            "sample": f"{len(layers)} layers (one per distinct MxNxK of {workload}, M capped at {CPU_M_CAP} rows) x {steps} timed passes after "
+                      f"{max(warmup, 1)} warm-up, unmodified reference ({os.path.relpath(reference_root() or '?', ROOT)}) CPU-eager path, fp32 activations, "
+                      f"{dt:.1f} s; FLOPs counted = those computed"}
+    return value, dt / steps, info
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    spec = WORKLOADS[args.workload]
-    t0 = time.perf_counter()
-    per_step = max(2.0, min(20.0, 90.0 / max(args.steps + args.warmup, 1)))
-    vals = []
-    for i in range(args.warmup + args.steps):
-        r = cpu_oracle_sample(args.workload, budget_s=per_step, seed=i)
-        if i >= args.warmup:
-            vals.append(r)
-    value = statistics.mean(v["value"] for v in vals)
-    wall = time.perf_counter() - t0
-    line = {"impl": "reference", "metric": "quantized_linear_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps + args.warmup, 1), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": spec["dtype"], "data": "synthetic",
-            "config": {"workload": args.workload, "describe": spec["describe"], "device": "host CPU"},
-            "cpu_baseline": dict(vals[-1], value=value),
-            "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    name = args.workload or HEADLINE
+    spec = WORKLOADS[name]
+    value, s_per_step, info = cpu_reference_run(name, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "quantized_linear_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * s_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": spec["dtype"], "data": "synthetic", "config": workload_config(name, world),
+            "cpu_baseline": info, "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def run_gpu_reference_arm(args):
+    """Child process of the GPU arm: the reference's own GPU path on cuda:0 (flags come from the environment the parent set),
+    one layer per distinct shape, CUDA events around 10 back-to-back forwards after 3 warm-ups; the step time is extrapolated with
+    the shape multiplicities.  Prints one JSON object per workload."""
+    import torch
+
+    from oracle.ref_loader import load_reference
+    load_reference()
+    dev = torch.device("cuda", 0)
+    out = {}
+    for name in args.workload.split(","):
+        layers = _reference_layers(name, dev, torch.bfloat16, None)
+        rows, step_ms, flops = [], 0.0, 0.0
+        with torch.no_grad():
+            for m, n, k, mult, layer, x in layers:
+                for _ in range(3):
+                    layer(x)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    layer(x)
+                e1.record()
+                e1.synchronize()
+                ms = e0.elapsed_time(e1) / 10
+                rows.append({"M": m, "N": n, "K": k, "count": mult, "ms": ms, "tflops": 2.0 * m * n * k / ms / 1e9})
+                step_ms += mult * ms
+                flops += mult * 2.0 * m * n * k
+        out[name] = {"value": flops / step_ms / 1e9, "unit": "TFLOP/s", "step_ms_extrapolated": step_ms, "per_shape": rows,
+                     "forward_func": layers[0][4].forward_func.__name__}
+    print("GPU_REFERENCE " + json.dumps(out), flush=True)
+
+
+GPU_REFERENCE_VARIANTS = {
+    # the reference's defaults on a B200 with torch.compile off: Triton scaled-mm kernel (kernels/triton_scaled_mm.py:239-275)
+    "triton": {"SDNQ_USE_TORCH_COMPILE": "0"},
+    # CUDA eager: torch._int_mm / torch._scaled_mm (cuBLASLt) + elementwise epilogue (kernel_wrappers.py:132-150)
+    "cuda_eager": {"SDNQ_USE_TORCH_COMPILE": "0", "SDNQ_USE_TRITON_MM": "0"},
+}
+
+
+def gpu_reference(workloads, timeout_s=420):
+    """Run the reference's GPU paths in child processes (its flags are resolved at import time) and collect their numbers."""
+    from oracle.ref_loader import reference_root
+    if reference_root() is None:
+        return {"unavailable": "oracle/_ref is missing (python oracle/build_ref.py in the authoring container)"}
+    res = {"how": "unmodified reference on cuda:0, bf16, one layer per distinct MxNxK, CUDA events around 10 forwards after 3 warm-ups (eager launches, "
+                  "no CUDA graph: the reference has none), step time extrapolated with the shape multiplicities"}
+    for variant, env in GPU_REFERENCE_VARIANTS.items():
+        e = dict(os.environ, SDNQ_DEVICE="cuda", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0], **env)
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            e.pop(k, None)
+        t0 = time.time()
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "gpu_reference", "--workload", ",".join(workloads)],
+                               capture_output=True, text=True, timeout=timeout_s, env=e, cwd=ROOT)
+            got = [ln for ln in p.stdout.splitlines() if ln.startswith("GPU_REFERENCE ")]
+            if got:
+                res[variant] = json.loads(got[-1][len("GPU_REFERENCE "):])
+                res[variant]["seconds"] = round(time.time() - t0, 1)
+            else:
+                res[variant] = {"unavailable": (p.stderr or p.stdout).strip().splitlines()[-1][:300] if (p.stderr or p.stdout).strip() else f"exit {p.returncode}"}
+        except subprocess.TimeoutExpired:
+            res[variant] = {"unavailable": f"timed out after {timeout_s} s"}
+        except Exception as ex:      # noqa: BLE001
+            res[variant] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+    return res
+
+
+# ------------------------------------------------------------------------------------------------ measured tensor peaks
+def measure_peaks(device):
+    """Dense 8-bit tensor-core peak of this GPU, measured the way MEASURED_PEAKS.json measures bf16: the library GEMM at 8192^3
+    (torch._int_mm = cuBLASLt int8 -> int32; torch._scaled_mm = cuBLASLt e4m3 x e4m3 -> bf16), best of 10 single launches
+    (burst) and back to back for ~1.5 s (sustained)."""
+    import torch
+    n = 8192
+    flops = 2.0 * n ** 3
+    out = {"how": "torch._int_mm (int8 -> int32) and torch._scaled_mm (e4m3 -> bf16, tensor-wise unit scales) at 8192^3 on this GPU in this run: "
+                  "best of 10 launches (burst), back to back for 1.5 s (sustained)"}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(1500.0 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return flops / best / 1e9, flops * reps / e0.elapsed_time(e1) / 1e9
+    try:
+        a = torch.randint(-128, 127, (n, n), dtype=torch.int8, device=device)
+        b = torch.randint(-128, 127, (n, n), dtype=torch.int8, device=device).t()
+        out["int8_tflops"], out["int8_tflops_sustained"] = timed(lambda: torch._int_mm(a, b))
+    except Exception as ex:      # noqa: BLE001
+        out["int8_error"] = f"{type(ex).__name__}: {ex}"[:200]
+    try:
+        a8 = torch.randn(n, n, device=device).to(torch.float8_e4m3fn)
+        b8 = torch.randn(n, n, device=device).to(torch.float8_e4m3fn).t()
+        one = torch.ones((), device=device, dtype=torch.float32)
+        out["fp8_tflops"], out["fp8_tflops_sustained"] = timed(lambda: torch._scaled_mm(a8, b8, scale_a=one, scale_b=one, out_dtype=torch.bfloat16))
+    except Exception as ex:      # noqa: BLE001
+        out["fp8_error"] = f"{type(ex).__name__}: {ex}"[:200]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -212,80 +367,67 @@ def build_stack(workload, device):
     cfg = spec["config"]
     stack = []
     torch.manual_seed(1234)
-    for name, m, n, k in spec["layers"]():
+    for name, m, n, k, src in spec["layers"](spec["batch_per_gpu"]):
         lin = torch.nn.Linear(k, n, bias=True, device=device, dtype=torch.bfloat16)
         layer, _ = sdnq_quantize_layer(lin, SDNQConfig(**cfg), param_name=name + ".weight")
-        stack.append((name, m, n, k, layer))
+        stack.append((name, m, n, k, src, layer))
     return stack
 
 
-def make_inputs(stack, device, host_inputs):
-    """activation buffers of the step, all derived on device from the step inputs (`host_inputs`: name -> pinned host tensor)."""
-    import torch
-    dev_in = {k: torch.empty_like(v, device=device) for k, v in host_inputs.items()}
-    return dev_in
+POOL = 3      # distinct buffers per activation shape, handed out round-robin to the distinct producers
 
 
-def derive_activations(dev_in, shapes):
-    """(M,K) activations for every distinct input shape of the stack, cut out of the step inputs without extra HBM-resident
-    copies where possible (views) -- stand-ins for the attention / norm outputs that feed the Linears in the real model."""
+def make_activations(stack, dev_in, device):
+    """src -> activation tensor.  The step inputs (`dev_in`: "hidden" = the input of the first token-level Linear, "context" = the
+    text-encoder states of SD-XL) feed their consumers directly; every other producer (attention output, norm output, MLP hidden
+    state ...) is a stand-in buffer of the right shape, distinct from the buffers of the producers around it, so that only layers
+    that really share an input in the model present the same tensor to the library."""
     import torch
-    base = dev_in["hidden"]
-    flat = base.reshape(-1)
-    acts = {}
-    for (m, k) in shapes:
-        need = m * k
-        if need <= flat.numel():
-            acts[(m, k)] = flat[:need].view(m, k)
+    acts, pools, nxt = {}, {}, {}
+    first = next(src for _, m, _, _, src, _ in stack if m >= 32)
+    for _, m, _, k, src, _ in stack:
+        if src in acts:
+            continue
+        if src == first:
+            acts[src] = dev_in["hidden"]
+        elif src == "context" and "context" in dev_in:
+            acts[src] = dev_in["context"]
         else:
-            reps = (need + flat.numel() - 1) // flat.numel()
-            acts[(m, k)] = flat.repeat(reps)[:need].view(m, k)
-    if "context" in dev_in:
-        ctx = dev_in["context"]
-        for (m, k) in shapes:
-            if (m, k) == tuple(ctx.shape):
-                acts[(m, k)] = ctx
+            pool = pools.setdefault((m, k), [])
+            i = nxt.get((m, k), 0)
+            if len(pool) < POOL:
+                pool.append(torch.randn(m, k, device=device, dtype=torch.bfloat16))
+            acts[src] = pool[i % POOL]
+            nxt[(m, k)] = i + 1
     return acts
 
 
-def run_gpu_arm(args):
+def run_workload(name, args, world, rank, device, peaks, with_roofline=True):
+    """Build, warm up, capture and time one workload.  Returns the result dict (rank 0) or None."""
     import torch
     import torch.distributed as dist
 
     from sdnq_b200 import _lib, ops
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line (the version banner goes to stdout)
-        dist.init_process_group("nccl", device_id=device)
-    _lib.check(_lib.load().sdnq_b200_check_device(local_rank))
-    spec = WORKLOADS[args.workload]
-    stack = build_stack(args.workload, device)
-    layers_meta = [(n, m, nn_, k) for n, m, nn_, k, _ in stack]
+    spec = WORKLOADS[name]
+    local_rank = device.index
+    stack = build_stack(name, device)
+    layers_meta = [(n, m, nn_, k, s) for n, m, nn_, k, s, _ in stack]
     flops_step = total_flops(layers_meta)
 
     # ---- step inputs live on the host (pinned); everything else is derived on device
     torch.manual_seed(100 + rank)
-    hidden_shape = next((m, k) for _, m, _, k in layers_meta if m >= 32)      # the first Linear's input: the step's "latents"
+    hidden_shape = next((m, k) for _, m, _, k, _ in layers_meta if m >= 32)      # the first Linear's input: the step's "latents"
     host_inputs = {"hidden": torch.randn(hidden_shape, dtype=torch.bfloat16).pin_memory()}
-    ctx_shapes = [(m, k) for _, m, _, k in layers_meta if m == 77]
-    if ctx_shapes:
-        host_inputs["context"] = torch.randn(ctx_shapes[0], dtype=torch.bfloat16).pin_memory()
+    ctx = [(m, k) for _, m, _, k, s in layers_meta if s == "context"]
+    if ctx:
+        host_inputs["context"] = torch.randn(ctx[0], dtype=torch.bfloat16).pin_memory()
     dev_in = {k: v.to(device, non_blocking=True) for k, v in host_inputs.items()}
-    shapes = sorted({(m, k) for _, m, _, k in layers_meta})
-
+    acts = make_activations(stack, dev_in, device)
     out_holder = {}
 
     def step():
-        acts = derive_activations(dev_in, shapes)
-        y = None
-        for _, m, _, k, layer in stack:
-            y = layer(acts[(m, k)])
+        for _, m, _, _, src, layer in stack:
+            y = layer(acts[src])
             if m >= 32:
                 out_holder["y"] = y
         return out_holder["y"]
@@ -299,7 +441,7 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count()
 
-    # ---- capture the whole step in one CUDA graph (launch-bound inner loop: ~1.5k launches of a few microseconds each)
+    # ---- capture the whole step in one CUDA graph (launch-bound inner loop)
     graph = torch.cuda.CUDAGraph()
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
@@ -365,16 +507,14 @@ def run_gpu_arm(args):
     h2d = sum(v.numel() * v.element_size() for v in host_inputs.values())
     d2h = host_out.numel() * host_out.element_size()
 
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+    if world > 1:      # a multi-GPU step takes as long as its slowest rank
+        from sdnq_b200.parallel import max_over_ranks
+        ms, ms_e2e = max_over_ranks(ms, device=device), max_over_ranks(ms_e2e, device=device)
 
     # ---- roofline of the dominant kernel (rank 0): every launch of that kernel in one step, replayed as a graph between CUDA events
-    roofline = cpu_base = None
-    if rank == 0:
+    roofline = None
+    if rank == 0 and with_roofline:
         from sdnq_b200.forward import matmul_operand
-        acts = derive_activations(dev_in, shapes)
 
         def graph_time(fn, reps=5):
             """capture fn() (a list of kernel launches) in a CUDA graph and time `reps` replays with CUDA events: per-launch
@@ -394,101 +534,174 @@ def run_gpu_arm(args):
             t1.synchronize()
             return t0.elapsed_time(t1) / reps
 
-        mm_layers = [(m, n, k, layer) for _, m, n, k, layer in stack if layer.sdnq_dequantizer.use_quantized_matmul and m >= 32]
-        dq_layers = [(m, n, k, layer) for _, m, n, k, layer in stack if not layer.sdnq_dequantizer.use_quantized_matmul]
+        mm_layers = [(m, n, k, src, layer) for _, m, n, k, src, layer in stack if layer.sdnq_dequantizer.use_quantized_matmul and m >= 32]
+        dq_layers = [(m, n, k, src, layer) for _, m, n, k, src, layer in stack if not layer.sdnq_dequantizer.use_quantized_matmul and m >= 32]
         gemm_ms = gemm_flops = k2_ms = k2_bytes = dq_ms = dq_bytes = 0.0
-        n_gemm, n_dq = len(mm_layers), len(dq_layers)
+        n_gemm, n_dq, n_k2 = len(mm_layers), len(dq_layers), 0
+        peaks_file = {}
+        try:
+            peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:      # noqa: BLE001
+            pass
+        hbm_peak = float(peaks_file.get("hbm_gbs", 6650.0))
+        src_note = "measured (MEASURED_PEAKS.json)" if peaks_file else "fallback (B200_PROFILING.md)"
+        traffic = traffic_note = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
+            if tr:
+                traffic, traffic_note = tr.get("dominant_kernel_dram_bytes_per_launch"), tr.get("source")
+        except Exception:      # noqa: BLE001
+            pass
         if mm_layers:
-            pre = {}
-            for m, n, k, layer in mm_layers:        # one pre-quantised activation per distinct (M, K, mode): L2-hot like in the step
+            pre, k2_srcs, last = {}, [], None
+            for m, n, k, src, layer in mm_layers:        # one pre-quantised activation per distinct source tensor
                 d = layer.sdnq_dequantizer
-                key = (m, k, d.quantized_matmul_dtype, d.hadamard_group_size if d.use_hadamard else 0)
+                key = (src, d.quantized_matmul_dtype, d.hadamard_group_size if d.use_hadamard else 0)
                 if key not in pre:
-                    pre[key] = ops.act_quant(acts[(m, k)], key[2], hadamard_group=key[3], want_rowsum=matmul_operand(layer).zp is not None)
+                    pre[key] = ops.act_quant(acts[src], key[1], hadamard_group=key[2], want_rowsum=matmul_operand(layer).zp is not None)
+                if key != last:                          # the K2 launches the step really makes: one per run of siblings
+                    k2_srcs.append((m, k, key))
+                    last = key
 
             def all_gemms():
-                for m, n, k, layer in mm_layers:
+                for m, n, k, src, layer in mm_layers:
                     d = layer.sdnq_dequantizer
                     op = matmul_operand(layer)
-                    xq, sx, zx, rowsum, _ = pre[(m, k, d.quantized_matmul_dtype, d.hadamard_group_size if d.use_hadamard else 0)]
+                    xq, sx, zx, rowsum, _ = pre[(src, d.quantized_matmul_dtype, d.hadamard_group_size if d.use_hadamard else 0)]
                     ops.scaled_mm(xq, op.wq, sx, op.sw, layer.bias, torch.bfloat16, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx)
 
             def all_act_quants():
-                for m, n, k, layer in mm_layers:
-                    d = layer.sdnq_dequantizer
-                    ops.act_quant(acts[(m, k)], d.quantized_matmul_dtype, hadamard_group=d.hadamard_group_size if d.use_hadamard else 0)
+                for m, k, (src, mmd, hg) in k2_srcs:
+                    ops.act_quant(acts[src], mmd, hadamard_group=hg)
 
             gemm_ms = graph_time(all_gemms)
             k2_ms = graph_time(all_act_quants)
-            gemm_flops = sum(2.0 * m * n * k for m, n, k, _ in mm_layers)
-            k2_bytes = sum(3.0 * m * k for m, n, k, _ in mm_layers)
-        if dq_layers:
-            def all_dequants():
-                for m, n, k, layer in dq_layers:
-                    layer.sdnq_dequantizer(layer.weight, layer.scale, layer.zero_point, layer.svd_up, layer.svd_down)
-            dq_ms = graph_time(all_dequants)
-            for m, n, k, layer in dq_layers:
-                tensors = [layer.weight, layer.scale, layer.zero_point, layer.svd_up, layer.svd_down]
-                dq_bytes += sum(t.numel() * t.element_size() for t in tensors if t is not None) + 2.0 * n * k
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
-        bf16_sustained = float(peaks.get("bf16_tflops_sustained", bf16_peak))
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        # a kernel timed inside a long, power-limited region is held against the sustained figure, a short burst against the burst one
-        long_region = 5 * gemm_ms >= 200.0 or (clocks is not None and "sw_power_cap" in (clocks.get("reasons") or []))
-        tensor_peak = 2.0 * (bf16_sustained if long_region else bf16_peak)
-        # DRAM traffic per launch of the dominant kernel: from the committed ncu capture of this workload (profiles/traffic.json,
-        # written by tools/ncu_summary.py traffic from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over one step)
-        traffic = traffic_note = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-            if tr:
-                traffic, traffic_note = tr.get("dominant_kernel_dram_bytes_per_launch"), tr.get("source")
-        except Exception:
-            pass
-        if n_dq and not n_gemm:
-            ach = dq_bytes / dq_ms / 1e6
-            roofline = {"bound": "hbm", "kernel": "dequant_svd_kernel / dequant_kernel (K3)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": traffic, "traffic_note": traffic_note, "peak_note": f"HBM copy peak, {src}", "launches": n_dq,
-                        "algorithmic_bytes_per_launch": dq_bytes / n_dq,
-                        "avg_launch_us": 1e3 * dq_ms / n_dq,
-                        "algorithmic_bytes": "packed codes + scales (+zp) + svd factors read, bf16 weight written"}
-        achieved = gemm_flops / max(gemm_ms, 1e-9) / 1e9
-        if n_gemm:
+            n_k2 = len(k2_srcs)
+            gemm_flops = sum(2.0 * m * n * k for m, n, k, _, _ in mm_layers)
+            k2_bytes = sum(3.0 * m * k for m, k, _ in k2_srcs)
+            fp8 = spec["config"]["weights_dtype"].startswith("float")
+            kind = "fp8" if fp8 else "int8"
+            burst, sustained = peaks.get(f"{kind}_tflops"), peaks.get(f"{kind}_tflops_sustained")
+            if burst is None:       # library peak not measurable: 2 x the bf16 figures
+                burst = 2.0 * float(peaks_file.get("bf16_tflops", 1590.0))
+                sustained = 2.0 * float(peaks_file.get("bf16_tflops_sustained", burst / 2.0))
+                peak_src = f"2x the bf16 cuBLAS figure, {src_note}"
+            else:
+                peak_src = f"cuBLASLt {kind} 8192^3 measured in this run"
+            # a kernel timed inside a long, power-limited region is held against the sustained figure, a short burst against the burst one
+            long_region = 5 * gemm_ms >= 200.0 or (clocks is not None and "sw_power_cap" in (clocks.get("reasons") or []))
+            tensor_peak = sustained if long_region else burst
+            achieved = gemm_flops / max(gemm_ms, 1e-9) / 1e9
             roofline = {"bound": "tensor", "kernel": "gemm_w8a8_kernel (tcgen05 kind::i8 / kind::f8f6f4, single CTA or cta_group::2 pairs)",
-                        "achieved": achieved, "peak": tensor_peak,
-                        "unit": "TFLOP/s", "frac": achieved / tensor_peak, "traffic": traffic, "traffic_note": traffic_note,
-                        "peak_note": f"8-bit dense tensor peak taken as 2x the {src} bf16 cuBLAS figure: "
-                                     f"{'sustained' if long_region else 'burst'} ({bf16_sustained if long_region else bf16_peak} TF) because the timed region is "
-                                     f"{'long / power-capped' if long_region else 'short'}; burst {2 * bf16_peak:.0f} / sustained {2 * bf16_sustained:.0f} TF",
+                        "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                        "traffic": traffic, "traffic_note": traffic_note,
+                        "peak_note": f"{peak_src}: {'sustained' if long_region else 'burst'} figure because the timed region is "
+                                     f"{'long / power-capped' if long_region else 'short'} (burst {burst:.0f} / sustained {sustained:.0f} TF)",
                         "algorithmic_flops_per_launch": gemm_flops / max(n_gemm, 1),
-                        "algorithmic_bytes_per_launch": sum(float(n * k + m * k + 2 * m * n) for m, n, k, _ in mm_layers) / max(n_gemm, 1),
+                        "algorithmic_bytes_per_launch": sum(float(n * k + m * k + 2 * m * n) for m, n, k, _, _ in mm_layers) / max(n_gemm, 1),
                         "launches": n_gemm, "avg_launch_us": 1e3 * gemm_ms / max(n_gemm, 1), "share_of_step": gemm_ms / (gemm_ms + k2_ms),
-                        "act_quant": {"bound": "hbm", "achieved": k2_bytes / k2_ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
-                                      "frac": k2_bytes / k2_ms / 1e6 / hbm_peak, "avg_launch_us": 1e3 * k2_ms / max(n_gemm, 1)}}
-        if world == 1 and not args.no_cpu_baseline:
-            cpu_base = cpu_oracle_sample(args.workload, budget_s=12.0)
+                        "act_quant": {"bound": "hbm", "kernel": "act_quant_kernel (K2)", "achieved": k2_bytes / k2_ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": k2_bytes / k2_ms / 1e6 / hbm_peak, "launches": n_k2, "avg_launch_us": 1e3 * k2_ms / max(n_k2, 1),
+                                      "launches_without_sibling_reuse": n_gemm}}
+        elif dq_layers:
+            roofline = dequant_path_roofline(dq_layers, acts, graph_time, hbm_peak, src_note, peaks_file, traffic, traffic_note)
 
+    if rank != 0:
+        return None
+    tfl = flops_step * args.steps * world / (ms * 1e-3) / 1e12
+    tfl_e2e = flops_step * args.steps * world / (ms_e2e * 1e-3) / 1e12
+    res = {"metric": "quantized_linear_tflops", "value": tfl, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms / args.steps, "steps_per_s": 1e3 * args.steps / ms * world, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": spec["dtype"], "data": "synthetic", "config": workload_config(name, world),
+           "execution": "whole step captured in one CUDA graph, replayed per step; sibling projections share one activation-quantise launch",
+           "e2e": {"value": tfl_e2e, "unit": "TFLOP/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "gpu_launches": int(launches_per_step) * args.steps, "launches_per_step": int(launches_per_step),
+           "clocks": clocks, "roofline": roofline}
+    del graph, stack, acts
+    torch.cuda.empty_cache()
+    return res
+
+
+def dequant_path_roofline(dq_layers, acts, graph_time, hbm_peak, src_note, peaks_file, traffic, traffic_note):
+    """Dequant-path workload: the dominant kernel is whatever the forward launches per layer.  With the fused W4A16 kernel the
+    weight never reaches HBM as bf16, so the kernel is a GEMM (tensor bound, bf16 rate); with dequantise + library GEMM it is the
+    dequant kernel (HBM bound).  Both are timed; the one the forward uses is the headline of this line."""
+    import torch
+    n_dq = len(dq_layers)
+
+    def all_forwards():
+        for m, n, k, src, layer in dq_layers:
+            layer(acts[src])
+
+    def all_dequants():
+        for m, n, k, src, layer in dq_layers:
+            layer.sdnq_dequantizer(layer.weight, layer.scale, layer.zero_point, layer.svd_up, layer.svd_down)
+    fwd_ms = graph_time(all_forwards)
+    dq_ms = graph_time(all_dequants)
+    dq_bytes = 0.0
+    for m, n, k, src, layer in dq_layers:
+        tensors = [layer.weight, layer.scale, layer.zero_point, layer.svd_up, layer.svd_down]
+        dq_bytes += sum(t.numel() * t.element_size() for t in tensors if t is not None) + 2.0 * n * k
+    flops = sum(2.0 * m * n * k for m, n, k, _, _ in dq_layers)
+    bf16_peak = float(peaks_file.get("bf16_tflops", 1590.0))
+    ach_dq = dq_bytes / dq_ms / 1e6
+    k3 = {"bound": "hbm", "kernel": "dequant_svd_kernel / dequant_kernel (K3: the stand-alone dequantiser, used by dequantize() and as the fallback)",
+          "achieved": ach_dq, "peak": hbm_peak, "unit": "GB/s", "frac": ach_dq / hbm_peak, "launches": n_dq,
+          "algorithmic_bytes_per_launch": dq_bytes / n_dq, "avg_launch_us": 1e3 * dq_ms / n_dq, "peak_note": f"HBM copy peak, {src_note}",
+          "algorithmic_bytes": "packed codes + scales (+zp) + svd factors read, bf16 weight written"}
+    from sdnq_b200 import forward as F
+    fused = bool(getattr(F, "w4a16_enabled", lambda: False)())
+    if not fused:
+        return dict(k3, traffic=traffic, traffic_note=traffic_note, forward_ms_all_layers=fwd_ms)
+    ach = flops / fwd_ms / 1e9
+    return {"bound": "tensor", "kernel": "gemm_w4a16_kernel (tcgen05 kind::f16, packed int4 dequantised in the GEMM prologue, SVD rank-r second accumulate)",
+            "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak, "traffic": traffic, "traffic_note": traffic_note,
+            "peak_note": f"bf16 cuBLAS burst figure, {src_note} (the activations are bf16: the contraction runs at the 16-bit tensor rate)",
+            "algorithmic_flops_per_launch": flops / n_dq, "launches": n_dq, "avg_launch_us": 1e3 * fwd_ms / n_dq,
+            "algorithmic_bytes_per_launch": sum(float(sum(t.numel() * t.element_size() for t in (L.weight, L.scale, L.svd_up, L.svd_down) if t is not None)
+                                                      + 2 * m * k + 2 * m * n) for m, n, k, _, L in dq_layers) / n_dq,
+            "dequant_kernel": k3}
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from sdnq_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line (the version banner goes to stdout)
+        dist.init_process_group("nccl", device_id=device)
+    _lib.check(_lib.load().sdnq_b200_check_device(local_rank))
+    t_start = time.time()
+    peaks = measure_peaks(device) if rank == 0 else {}
+    headline = args.workload or HEADLINE
+    nested = [] if (args.workload or args.no_nested) else list(NESTED)
+    line = run_workload(headline, args, world, rank, device, peaks)
+    sub = {}
+    for name in nested:
+        r = run_workload(name, args, world, rank, device, peaks)
+        if r is not None:
+            sub[name] = r
     if rank == 0:
-        tfl = flops_step * args.steps * world / (ms * 1e-3) / 1e12
-        tfl_e2e = flops_step * args.steps * world / (ms_e2e * 1e-3) / 1e12
-        line = {"metric": "quantized_linear_tflops", "value": tfl, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "steps_per_s": 1e3 * args.steps / ms * world, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": spec["dtype"], "data": "synthetic",
-                "config": {"workload": args.workload, "describe": spec["describe"], "linears_per_step": len(stack),
-                           "gflop_per_step": flops_step / 1e9, "batch_per_gpu": 1 if args.workload == "sdxl_int8" else 4, "parallelism": f"dp{world}",
-                           "l2": "each Linear has its own weights (2.2 GB int8 for sdxl_int8, 12 GB fp8 for flux_fp8) >> 126 MB L2: weights stream from HBM every step, no flush needed",
-                           "execution": "whole step captured in one CUDA graph, replayed per step"},
-                "e2e": {"value": tfl_e2e, "unit": "TFLOP/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": int(launches_per_step) * args.steps, "launches_per_step": int(launches_per_step),
-                "clocks": clocks, "roofline": roofline}
-        if cpu_base is not None:
-            line["cpu_baseline"] = cpu_base
+        line["peaks"] = peaks
+        if sub:
+            line["workloads"] = sub
+        if world == 1 and not args.no_cpu_baseline:
+            budget = 20.0
+            _, _, info = cpu_reference_run(headline, steps=1000, warmup=1, budget_s=budget)
+            line["cpu_baseline"] = info
+            for name in sub:
+                _, _, sub[name]["cpu_baseline"] = cpu_reference_run(name, steps=1000, warmup=1, budget_s=6.0)
+        if world == 1 and not args.no_gpu_reference:
+            line["gpu_reference"] = gpu_reference([headline] + list(sub))
+        line["bench_seconds"] = round(time.time() - t_start, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -499,10 +712,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="sdxl_int8", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, help=f"one of {sorted(WORKLOADS)}; default: {HEADLINE} with {list(NESTED)} nested under 'workloads'")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "gpu_reference"])
+    ap.add_argument("--no-nested", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     args = ap.parse_args()
+    if args.impl == "gpu_reference":
+        return run_gpu_reference_arm(args)
+    if args.workload is not None and args.workload not in WORKLOADS:
+        ap.error(f"unknown workload {args.workload!r}")
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)

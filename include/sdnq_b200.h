@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SDNQ_B200_ABI_VERSION 1
+#define SDNQ_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SDNQ_API __attribute__((visibility("default")))
@@ -53,7 +53,10 @@ typedef enum sdnq_dtype {
     SDNQ_I8 = 3,
     SDNQ_U8 = 4,
     SDNQ_F8E4M3 = 5,
-    SDNQ_I32 = 6
+    SDNQ_I32 = 6,
+    SDNQ_F8E5M2 = 7 /* weight-side only: as the operand dtype of a matmul entry point it names the mixed pair
+                       a = float8_e4m3fn activations x b = float8_e5m2 weights (what the reference hands to
+                       torch._scaled_mm for weights_dtype="float8_e5m2", linear_fp8.py:25-54) */
 } sdnq_dtype;
 
 /* storage format of a quantised weight: one row of reference common.py:16-267 (`dtype_dict`) */
@@ -178,6 +181,7 @@ SDNQ_API int sdnq_b200_rows_to_nchw(const void* in, void* out, int elem_bytes, i
  * out[M,N] = cast( fma( f32(A @ B) * sx[m], sw[n], bias ) )        (no bias: (acc*sx)*sw)
  *   a   [M,K] row-major 1-byte codes (SDNQ_I8 or SDNQ_F8E4M3), row stride K
  *   b   the [K,N] operand stored K-major, i.e. physically [N,K] row-major, same dtype as a
+ *       (ab_dtype = SDNQ_F8E5M2: a is float8_e4m3fn, b is float8_e5m2)
  *   sx  f32 [M], sw f32 [N]
  *   bias        NULL, or [N] (bias_ld = 0), or [M,N] (bias_ld = row stride in elements); bias_dtype f32/bf16/f16
  *   zero-point rank-1 terms, all optional (NULL = absent), added to bias in f32 before the fma in the
@@ -213,7 +217,8 @@ SDNQ_API int sdnq_b200_mm(const void* a, const void* b, int ab_dtype, void* out,
  * the fused kernel, xq, sx, zx and rowsum.  Its first 4096 bytes must be zero when the workspace is used for the first
  * time (zero-fill it once after allocating); every call leaves them zero again.  One workspace per stream: calls that
  * may run concurrently need separate workspaces.
- *   mm_dtype SDNQ_I8 / SDNQ_U8 / SDNQ_F8E4M3; wq physical [N,K]; zp / colsum as in scaled_mm. */
+ *   mm_dtype SDNQ_I8 / SDNQ_U8 / SDNQ_F8E4M3 / SDNQ_F8E5M2 (e4m3 activation codes x stored float8_e5m2 weight);
+ *   wq physical [N,K]; zp / colsum as in scaled_mm. */
 SDNQ_API size_t sdnq_b200_linear_w8a8_workspace_bytes(int64_t M, int64_t K);
 SDNQ_API int sdnq_b200_linear_w8a8(const void* x, int x_dtype, int64_t ldx, const void* wq, int mm_dtype,
                           const float* sw, const float* zp, const int32_t* colsum,
@@ -226,7 +231,7 @@ SDNQ_API int sdnq_b200_linear_w8a8(const void* x, int x_dtype, int64_t ldx, cons
  *      materialising the dequantised weight:
  *          out[m,n] = sw[n] * sum_k x[m,k] * q[n,k]  (+ zp[n] * sum_k x[m,k])  + bias[n]
  *   x     [M,K] bf16 / f16, row stride ldx (for use_hadamard layers: already rotated, e.g. the x_rot output of act_quant)
- *   wq    physical [N,K] 1-byte codes, w_dtype SDNQ_I8 or SDNQ_F8E4M3 (row-wise scales sw[N], optional zero points zp[N])
+ *   wq    physical [N,K] 1-byte codes, w_dtype SDNQ_I8, SDNQ_F8E4M3 or SDNQ_F8E5M2 (row-wise scales sw[N], optional zero points zp[N])
  *   out   [M,N] row-major in x_dtype.   1 <= M <= 32, K % 16 == 0.
  * The codes are read once (N*K bytes instead of the 3*N*K of dequantise-then-GEMM); accumulation is f32 on the tensor cores. */
 SDNQ_API int sdnq_b200_linear_small_m(const void* x, int x_dtype, int64_t ldx, const void* wq, int w_dtype, const float* sw,
@@ -258,6 +263,11 @@ SDNQ_API int sdnq_b200_linear_w8a8_fused(const void* x, int x_dtype, int64_t ldx
                                 const float* sw, const void* bias, int bias_dtype,
                                 void* out, int out_dtype, int64_t M, int64_t N, int64_t K,
                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* 0 if `stream` is not being captured into a CUDA graph, else the (non-zero) id of the capture; -1 on error.  The host layer
+ * keys everything it caches across calls (quantised activations shared by sibling projections) on it, so that nothing computed
+ * eagerly is baked into a graph and nothing captured in one graph is taken for valid in another. */
+SDNQ_API int64_t sdnq_b200_stream_capture_id(void* stream);
 
 /* number of kernels launched by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches) */

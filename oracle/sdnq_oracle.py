@@ -125,6 +125,11 @@ def e4m3fn_round(x) -> np.ndarray:
     return from_e4m3fn_bits(e4m3fn_bits(x))
 
 
+def from_e5m2_bits(b) -> np.ndarray:
+    """float8_e5m2 bit pattern -> float32 value: an e5m2 code is the upper byte of an IEEE binary16."""
+    return (np.asarray(b, dtype=np.uint8).astype(np.uint16) << 8).view(np.float16).astype(F32)
+
+
 def fma32(a, b, c) -> np.ndarray:
     """float32 fused multiply-add emulated through float64 (a*b is exact in f64)."""
     return (np.asarray(a, F32).astype(np.float64) * np.asarray(b, F32).astype(np.float64)
@@ -450,7 +455,10 @@ def dequantize(layer: Layer, dtype=None, skip_quantized_matmul=False, with_svd=T
             res = _cast(_cast(res, dtype) + (up @ down).astype(F32), dtype)   # bf16 addmm_: f32 accumulate, one rounding
     res = _cast(res, dtype)
     if layer.use_hadamard and not non_hadamard:                         # dequantizer.py:46-47
-        res = rotate_hadamard(res, layer.hadamard_group_size, dtype)
+        if res.ndim > 2 and np.asarray(q).ndim > 2:                     # is_conv: groups run along the flattened [N, C*kh*kw] weight
+            res = rotate_hadamard(res.reshape(res.shape[0], -1), layer.hadamard_group_size, dtype).reshape(res.shape)   # quant_utils.py:199-208
+        else:
+            res = rotate_hadamard(res, layer.hadamard_group_size, dtype)
     return res
 
 
@@ -458,6 +466,8 @@ def re_quantize_matmul(layer: Layer):
     """dequantizer.py:204-239 + 166-200: dequant to f32 [N,K] (no SVD, no un-rotate) then row-wise
     re-quantise to the matmul dtype.  Returns logical (Wq[K,N], sw[1,N][, zp[1,N]])."""
     w = dequantize(layer, dtype="float32", with_svd=False, non_hadamard=True)
+    if w.ndim > 2:                                                      # convs: flatten(1,-1) (dequantizer.py:167-168, 179-180, 191-192)
+        w = w.reshape(w.shape[0], -1)
     mm = dtype_info(layer.quantized_matmul_dtype)
     if mm["is_integer"]:
         if mm["is_unsigned"]:
@@ -587,13 +597,19 @@ def _tuple_n(v, n):
     return (int(v),) * n if isinstance(v, (int, np.integer)) else tuple(int(i) for i in v)
 
 
-def conv_forward(layer: Layer, x, kernel_size, stride=1, padding=0, dilation=1, dtype="bfloat16"):
-    """SDNQConv1d/2d.forward for groups == 1, padding_mode == "zeros".  W8A8 layers: conv_{int8,uint8,fp8}_matmul
+_NP_PAD_MODE = {"reflect": "reflect", "replicate": "edge", "circular": "wrap"}
+
+
+def conv_forward(layer: Layer, x, kernel_size, stride=1, padding=0, dilation=1, dtype="bfloat16", padding_mode="zeros"):
+    """SDNQConv1d/2d.forward for groups == 1 (padding_mode != "zeros": F.pad first, then no padding, layers/conv/forward.py:53-55).  W8A8 layers: conv_{int8,uint8,fp8}_matmul
     (conv_int8.py:17-125) = im2col + the Linear matmul path + permute back; others (and inputs with fewer than 32 rows,
     conv_int8.py:95-96): dequantise + a float convolution (computed here as an f32 im2col GEMM, rounded once)."""
     x = np.asarray(x, F32)
     nd = x.ndim - 2
     k, s, p, d = (_tuple_n(v, nd) for v in (kernel_size, stride, padding, dilation))
+    if padding_mode != "zeros":
+        x = np.pad(x, [(0, 0), (0, 0)] + [(pi, pi) for pi in p], mode=_NP_PAD_MODE[padding_mode])
+        p = (0,) * nd
     x4 = x
     if nd == 1:                                                         # get_conv_args (layers/conv/forward.py:8-27)
         x4 = x[:, :, None, :]
@@ -647,6 +663,8 @@ def load_fixture(path):
             return from_bf16_bits(a)
         if dt == "float8_e4m3fn":
             return from_e4m3fn_bits(a)
+        if dt == "float8_e5m2":
+            return from_e5m2_bits(a)
         return a
 
     d = meta["dequantizer"]

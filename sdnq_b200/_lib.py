@@ -10,9 +10,9 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsdnq_b200.so")
 
-SDNQ_F32, SDNQ_BF16, SDNQ_F16, SDNQ_I8, SDNQ_U8, SDNQ_F8E4M3, SDNQ_I32 = range(7)
+SDNQ_F32, SDNQ_BF16, SDNQ_F16, SDNQ_I8, SDNQ_U8, SDNQ_F8E4M3, SDNQ_I32, SDNQ_F8E5M2 = range(8)
 SDNQ_W_INT, SDNQ_W_MINIFLOAT, SDNQ_W_FP8_E4M3FN, SDNQ_W_FP8_E5M2 = range(4)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class Conv2dGeometry(ctypes.Structure):
@@ -50,6 +50,7 @@ SIGNATURES = {
     "sdnq_b200_linear_w8a8_workspace_bytes": (_Z, [_L, _L]),
     "sdnq_b200_linear_w8a8": (_I, [_P, _I, _L, _P, _I, _P, _P, _P, _P, _I, _I, _P, _I, _L, _L, _L, _P, _Z, _P]),
     "sdnq_b200_linear_w8a8_fused": (_I, [_P, _I, _L, _P, _I, _P, _P, _I, _P, _I, _L, _L, _L, _P, _Z, _P]),
+    "sdnq_b200_stream_capture_id": (_L, [_P]),
     "sdnq_b200_launch_count": (_L, [_I]),
 }
 

@@ -66,6 +66,16 @@ extern "C" int sdnq_b200_check_device(int device) {
     return SDNQ_OK;
 }
 
+extern "C" int64_t sdnq_b200_stream_capture_id(void* stream) {
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    unsigned long long id = 0;
+    if (cudaStreamGetCaptureInfo(reinterpret_cast<cudaStream_t>(stream), &status, &id) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return status == cudaStreamCaptureStatusActive ? static_cast<int64_t>(id) : 0;
+}
+
 extern "C" int64_t sdnq_b200_launch_count(int reset) {
     const int64_t v = g_launches;
     if (reset) g_launches = 0;
@@ -134,22 +144,23 @@ extern "C" int sdnq_b200_linear_w8a8(const void* x, int x_dtype, int64_t ldx, co
                                      const float* zp, const int32_t* colsum, const void* bias, int bias_dtype, int hadamard_group,
                                      void* out, int out_dtype, int64_t M, int64_t N, int64_t K, void* workspace,
                                      size_t workspace_bytes, void* stream) {
-    SDNQ_REQUIRE(mm_dtype == SDNQ_I8 || mm_dtype == SDNQ_U8 || mm_dtype == SDNQ_F8E4M3, SDNQ_EINVAL, "bad matmul dtype %d", mm_dtype);
+    SDNQ_REQUIRE(mm_dtype == SDNQ_I8 || mm_dtype == SDNQ_U8 || mm_dtype == SDNQ_F8E4M3 || mm_dtype == SDNQ_F8E5M2, SDNQ_EINVAL, "bad matmul dtype %d", mm_dtype);
+    const int act_dtype = mm_dtype == SDNQ_F8E5M2 ? SDNQ_F8E4M3 : mm_dtype;      // e5m2 names the weight; activations are always e4m3
     SDNQ_REQUIRE(mm_dtype != SDNQ_U8 || colsum != nullptr, SDNQ_EINVAL, "uint8 matmul needs the weight column sums");
     if (M == 0) return SDNQ_OK;
     Workspace w;
     int rc = carve_workspace(workspace, workspace_bytes, M, K, &w);
     if (rc != SDNQ_OK) return rc;
     const bool need_rowsum = zp != nullptr;
-    if (fused_by_default() && hadamard_group == 0 && !need_rowsum && mm_dtype != SDNQ_U8) {
+    if (fused_by_default() && hadamard_group == 0 && !need_rowsum && mm_dtype != SDNQ_U8 && mm_dtype != SDNQ_F8E5M2) {
         rc = linear_fused_impl(x, x_dtype, ldx, wq, mm_dtype, sw, bias, bias_dtype, out, out_dtype, M, N, K, w.xq, w.sx, w.sync,
                                reinterpret_cast<cudaStream_t>(stream));
         if (rc <= 0) return rc;
     }
-    rc = sdnq_b200_act_quant(x, x_dtype, M, K, ldx, hadamard_group, mm_dtype, w.xq, w.sx, mm_dtype == SDNQ_U8 ? w.zx : nullptr,
+    rc = sdnq_b200_act_quant(x, x_dtype, M, K, ldx, hadamard_group, act_dtype, w.xq, w.sx, mm_dtype == SDNQ_U8 ? w.zx : nullptr,
                              need_rowsum ? w.rowsum : nullptr, nullptr, stream);
     if (rc != SDNQ_OK) return rc;
-    return sdnq_b200_scaled_mm(w.xq, wq, mm_dtype == SDNQ_F8E4M3 ? SDNQ_F8E4M3 : SDNQ_I8, w.sx, sw, bias, bias_dtype, 0,
+    return sdnq_b200_scaled_mm(w.xq, wq, (mm_dtype == SDNQ_F8E4M3 || mm_dtype == SDNQ_F8E5M2) ? mm_dtype : SDNQ_I8, w.sx, sw, bias, bias_dtype, 0,
                                need_rowsum ? w.rowsum : nullptr, zp, mm_dtype == SDNQ_U8 ? colsum : nullptr,
                                mm_dtype == SDNQ_U8 ? w.zx : nullptr, out, out_dtype, M, N, K, stream);
 }

@@ -53,6 +53,7 @@ struct GemmParams {
     int M, N, K;
     int raw;   // plain mm: store the accumulator (s32 / f32) untouched
     uint32_t w_sub;   // packed 4-bit weights: per-byte offset removed while expanding (0x08080808 for int4, 0 for uint4)
+    uint32_t b_fmt;   // fp8 GEMM: format of the B operand in the instruction descriptor (0 = e4m3, 1 = e5m2); A is always e4m3
     // fused activation quantiser (XM != 0): un-quantised activations in, xq / sx written by this kernel
     const void* fx;
     int64_t fldx;
@@ -335,7 +336,8 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // ======================================================== MMA issuer
         if (lane == 0 && cta_rank == 0) {
             pdl_wait();
-            constexpr uint32_t idesc = kInt8 ? ptx::make_idesc(2, 1, 1, BM * CG, BN) : ptx::make_idesc(1, 0, 0, BM * CG, BN);
+            // fp8: A = e4m3 activations, B = e4m3 or e5m2 weights (the mixed pair torch._scaled_mm takes for float8_e5m2 weights)
+            const uint32_t idesc = kInt8 ? ptx::make_idesc(2, 1, 1, BM * CG, BN) : ptx::make_idesc(1, 0, p.b_fmt, BM * CG, BN);
             auto commit = [&](uint32_t bar) { if constexpr (kPair) ptx::umma_commit_pair(bar); else ptx::umma_commit(bar); };
             int stage = 0;
             uint32_t phase = 0;
@@ -775,7 +777,8 @@ int pick_pair(const GemmParams& p) {
 
 int scaled_mm_impl(const void* a, const void* b, int ab_dtype, GemmParams p, cudaStream_t st, int wbits = 8) {
     SDNQ_REQUIRE(a && b && p.out, SDNQ_EINVAL, "NULL pointer");
-    SDNQ_REQUIRE(ab_dtype == SDNQ_I8 || ab_dtype == SDNQ_F8E4M3, SDNQ_EINVAL, "operand dtype must be int8 or float8_e4m3fn (got %d)", ab_dtype);
+    SDNQ_REQUIRE(ab_dtype == SDNQ_I8 || ab_dtype == SDNQ_F8E4M3 || ab_dtype == SDNQ_F8E5M2, SDNQ_EINVAL,
+                 "operand dtype must be int8, float8_e4m3fn or float8_e5m2 (= e4m3 activations x e5m2 weights) (got %d)", ab_dtype);
     SDNQ_REQUIRE(p.M >= 0 && p.N > 0 && p.K > 0, SDNQ_EINVAL, "bad shape M=%d N=%d K=%d", p.M, p.N, p.K);
     SDNQ_REQUIRE(p.K % 16 == 0, SDNQ_EUNSUPPORTED, "K (=%d) must be a multiple of 16 (TMA row pitch)", p.K);
     SDNQ_REQUIRE(p.N % 8 == 0, SDNQ_EUNSUPPORTED, "N (=%d) must be a multiple of 8 (16-byte output vectors)", p.N);
@@ -815,7 +818,7 @@ int linear_fused_impl(const void* x, int x_dtype, int64_t ldx, const void* wq, i
                       int bias_dtype, void* out, int out_dtype, int64_t M, int64_t N, int64_t K, uint8_t* xq, float* sx, int* sync,
                       cudaStream_t st) {
     if (!(x_dtype == SDNQ_BF16 || x_dtype == SDNQ_F16) || out_dtype != x_dtype) return 1;
-    if (ab_dtype != SDNQ_I8 && ab_dtype != SDNQ_F8E4M3) return 1;
+    if (ab_dtype != SDNQ_I8 && ab_dtype != SDNQ_F8E4M3 && ab_dtype != SDNQ_F8E5M2) return 1;
     if (M <= 0 || M > int64_t(kSyncStrips) * BM || K % 16 != 0 || N % 8 != 0 || ldx % 8 != 0) return 1;
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return 1;
     // per-CTA share of x beyond a few staging batches: the quantiser is no longer latency-bound and the
@@ -824,7 +827,7 @@ int linear_fused_impl(const void* x, int x_dtype, int64_t ldx, const void* wq, i
     const int bn = pick_bn(int(M), int(N));
     const int64_t stage_bytes = bn == 256 ? int64_t(Cfg<256>::kStages) * Cfg<256>::kStageA : int64_t(Cfg<128>::kStages) * Cfg<128>::kStageA;
     if (K * 2 > stage_bytes) return 1;
-    GemmParams p{sx, sw, bias, bias_dtype, 0, nullptr, nullptr, nullptr, nullptr, out, out_dtype, int(M), int(N), int(K), 0, 0u, x, ldx, xq, sx, sync};
+    GemmParams p{sx, sw, bias, bias_dtype, 0, nullptr, nullptr, nullptr, nullptr, out, out_dtype, int(M), int(N), int(K), 0, 0u, ab_dtype == SDNQ_F8E5M2 ? 1u : 0u, x, ldx, xq, sx, sync};
     const bool i8 = ab_dtype == SDNQ_I8;
     const bool bf = x_dtype == SDNQ_BF16;
 #define SDNQ_FUSED(BN_)                                                                                                    \
@@ -842,7 +845,7 @@ extern "C" int sdnq_b200_scaled_mm(const void* a, const void* b, int ab_dtype, c
                                    int bias_dtype, int64_t bias_ld, const int32_t* rowsum, const float* zp, const int32_t* colsum,
                                    const float* zx, void* out, int out_dtype, int64_t M, int64_t N, int64_t K, void* stream) {
     SDNQ_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), SDNQ_EUNSUPPORTED, "dimension too large");
-    GemmParams p{sx, sw, bias, bias_dtype, bias_ld, rowsum, zp, colsum, zx, out, out_dtype, (int)M, (int)N, (int)K, 0, 0u};
+    GemmParams p{sx, sw, bias, bias_dtype, bias_ld, rowsum, zp, colsum, zx, out, out_dtype, (int)M, (int)N, (int)K, 0, 0u, ab_dtype == SDNQ_F8E5M2 ? 1u : 0u};
     return scaled_mm_impl(a, b, ab_dtype, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -854,12 +857,12 @@ extern "C" int sdnq_b200_scaled_mm_packed(const void* a, const void* b_packed, c
                  "scaled_mm_packed: only int4 / uint4 weights are expanded in-kernel (other packed formats use sdnq_b200_unpack + scaled_mm)");
     SDNQ_REQUIRE(b_fmt->is_unsigned == 0 || (zp != nullptr && rowsum != nullptr), SDNQ_EINVAL, "uint4 weights need zp and rowsum");
     GemmParams p{sx, sw, bias, bias_dtype, bias_ld, rowsum, zp, nullptr, nullptr, out, out_dtype, (int)M, (int)N, (int)K, 0,
-                 b_fmt->is_unsigned ? 0u : 0x08080808u};
+                 b_fmt->is_unsigned ? 0u : 0x08080808u, 0u};
     return scaled_mm_impl(a, b_packed, SDNQ_I8, p, reinterpret_cast<cudaStream_t>(stream), 4);
 }
 
 extern "C" int sdnq_b200_mm(const void* a, const void* b, int ab_dtype, void* out, int64_t M, int64_t N, int64_t K, void* stream) {
     SDNQ_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), SDNQ_EUNSUPPORTED, "dimension too large");
-    GemmParams p{nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, out, SDNQ_I32, (int)M, (int)N, (int)K, 1, 0u};
+    GemmParams p{nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, out, SDNQ_I32, (int)M, (int)N, (int)K, 1, 0u, ab_dtype == SDNQ_F8E5M2 ? 1u : 0u};
     return scaled_mm_impl(a, b, ab_dtype, p, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -85,11 +85,16 @@ template <> struct Act<__half> {
 };
 
 // four consecutive codes (one 32-bit word) -> two packed pairs of T, exact
-template <typename T, bool kFp8>
+template <typename T, int kFp8>      // 0: int8 codes, 1: float8_e4m3fn, 2: float8_e5m2
 __device__ __forceinline__ void codes4(uint32_t w, uint32_t& p01, uint32_t& p23) {
-    if constexpr (kFp8) {
-        // e4m3 pair -> f16 pair (exact, one instruction); f16 needs nothing more, bf16 goes through f32 (exact: 4 significant bits)
+    if constexpr (kFp8 != 0) {
+        // e4m3 pair -> f16 pair (exact, one instruction); f16 needs nothing more, bf16 goes through f32 (exact: 4 significant bits).
+        // e5m2 is the upper byte of an f16: a byte permute.
         uint32_t h01, h23;
+        if constexpr (kFp8 == 2) {
+            h01 = __byte_perm(w, 0u, 0x1404);
+            h23 = __byte_perm(w, 0u, 0x3424);
+        } else {
 #ifdef SDNQ_HOST_EMU
         h01 = ::sdnq_emu::e4m3x2_to_f16x2(static_cast<unsigned short>(w & 0xFFFFu));
         h23 = ::sdnq_emu::e4m3x2_to_f16x2(static_cast<unsigned short>(w >> 16));
@@ -97,6 +102,7 @@ __device__ __forceinline__ void codes4(uint32_t w, uint32_t& p01, uint32_t& p23)
         asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h01) : "h"(static_cast<unsigned short>(w & 0xFFFFu)));
         asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h23) : "h"(static_cast<unsigned short>(w >> 16)));
 #endif
+        }
         if constexpr (ElemTraits<T>::kDtype == SDNQ_F16) {
             p01 = h01;
             p23 = h23;
@@ -116,7 +122,7 @@ __device__ __forceinline__ void codes4(uint32_t w, uint32_t& p01, uint32_t& p23)
 }
 
 // MB = number of 8-row activation blocks (M <= 8 * MB)
-template <typename T, bool kFp8, int MB>
+template <typename T, int kFp8, int MB>
 __global__ void __launch_bounds__(kThreads) gemv_w8a16_kernel(const GemvArgs a) {
     __shared__ float s_xsum[32];
     __shared__ float s_red[kWarps - 1][MB * 4][32];          // partial accumulators of warps 1..7 (the K split of a tile)
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(kThreads) gemv_w8a16_kernel(const GemvArgs a) 
     }
 }
 
-template <typename T, bool kFp8>
+template <typename T, int kFp8>
 int launch_mb(const GemvArgs& a, cudaStream_t st) {
     const int tiles = (a.N + 15) / 16;
     const int cap = num_sms() * 8;
@@ -283,7 +289,8 @@ extern "C" int sdnq_b200_linear_small_m(const void* x, int x_dtype, int64_t ldx,
     SDNQ_REQUIRE(x && wq && sw && out, SDNQ_EINVAL, "NULL pointer");
     SDNQ_REQUIRE(M >= 0 && M <= 32 && N > 0 && K > 0, SDNQ_EINVAL, "small-M Linear: 0 <= M <= 32 (got M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K);
     SDNQ_REQUIRE(K % 16 == 0 && ldx % 8 == 0 && ldx >= K, SDNQ_EUNSUPPORTED, "small-M Linear: K %% 16 == 0 and ldx %% 8 == 0 (K=%lld ldx=%lld)", (long long)K, (long long)ldx);
-    SDNQ_REQUIRE(w_dtype == SDNQ_I8 || w_dtype == SDNQ_F8E4M3, SDNQ_EINVAL, "weight codes must be int8 or float8_e4m3fn (got %d)", w_dtype);
+    SDNQ_REQUIRE(w_dtype == SDNQ_I8 || w_dtype == SDNQ_F8E4M3 || w_dtype == SDNQ_F8E5M2, SDNQ_EINVAL,
+                 "weight codes must be int8, float8_e4m3fn or float8_e5m2 (got %d)", w_dtype);
     SDNQ_REQUIRE(x_dtype == SDNQ_BF16 || x_dtype == SDNQ_F16, SDNQ_EUNSUPPORTED, "small-M Linear: bf16 / f16 activations (got %d)", x_dtype);
     SDNQ_REQUIRE(bias == nullptr || bias_dtype == SDNQ_BF16 || bias_dtype == SDNQ_F16 || bias_dtype == SDNQ_F32, SDNQ_EINVAL, "bad bias dtype %d", bias_dtype);
     SDNQ_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(wq) & 15) == 0, SDNQ_EINVAL, "x and wq must be 16-byte aligned");
@@ -291,7 +298,7 @@ extern "C" int sdnq_b200_linear_small_m(const void* x, int x_dtype, int64_t ldx,
     if (M == 0) return SDNQ_OK;
     GemvArgs a{x, ldx, reinterpret_cast<const uint8_t*>(wq), sw, zp, bias, bias_dtype, out, int(M), int(N), int(K)};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const bool fp8 = w_dtype == SDNQ_F8E4M3;
-    if (x_dtype == SDNQ_BF16) return fp8 ? launch_mb<__nv_bfloat16, true>(a, st) : launch_mb<__nv_bfloat16, false>(a, st);
-    return fp8 ? launch_mb<__half, true>(a, st) : launch_mb<__half, false>(a, st);
+    if (x_dtype == SDNQ_BF16)
+        return w_dtype == SDNQ_F8E4M3 ? launch_mb<__nv_bfloat16, 1>(a, st) : w_dtype == SDNQ_F8E5M2 ? launch_mb<__nv_bfloat16, 2>(a, st) : launch_mb<__nv_bfloat16, 0>(a, st);
+    return w_dtype == SDNQ_F8E4M3 ? launch_mb<__half, 1>(a, st) : w_dtype == SDNQ_F8E5M2 ? launch_mb<__half, 2>(a, st) : launch_mb<__half, 0>(a, st);
 }

@@ -59,10 +59,10 @@ class SDNQDequantizer:
 
     def _linear_nk(self):
         if self.is_conv:
-            if self.layer_class_name in conv_types and self.use_quantized_matmul and not self.re_quantize_for_matmul:
-                return self.matmul_nk()        # stored row-wise on the flattened [N, C*kh*kw] weight: same layout as a Linear
-            raise NotImplementedError(f"sdnq_b200: re-quantising {self.layer_class_name} weights for the quantized matmul has no CUDA kernel yet "
-                                      "(grouped / packed conv weights with use_quantized_matmul_conv)")
+            if self.layer_class_name in conv_types and self.use_quantized_matmul:
+                return self.matmul_nk()        # the flattened [N, C*kh*kw] weight: same GEMM geometry as a Linear
+            raise NotImplementedError(f"sdnq_b200: {self.layer_class_name} weights have no quantized-matmul operand (the reference "
+                                      "runs ConvTranspose layers on the dequant path only)")
         shape = tuple(self.original_shape)
         if len(shape) != 2:
             raise NotImplementedError(f"sdnq_b200: only 2-D Linear weights have a CUDA dequant kernel (got shape {shape})")
@@ -89,9 +89,13 @@ class SDNQDequantizer:
         """Conv / ConvTranspose weights: broadcast dequant over the quantised view (reference dequantizer.py:15-84 with
         `is_conv`): scale [N,1,kh,kw] / grouped [N,C/g,1,kh,kw] / ConvTranspose [1,N,kh,kw] ...; the SVD term is
         mm(svd_up, svd_down) in the SVD dtype added in f32 (no intermediate rounding of the weight, unlike Linear)."""
-        if self.use_hadamard and not non_hadamard:
-            raise NotImplementedError("sdnq_b200: un-rotating Hadamard-rotated convolution weights has no CUDA kernel yet")
         stored_t = bool(skip_quantized_matmul and not self.re_quantize_for_matmul and self.use_quantized_matmul)
+        un_rotate = self.use_hadamard and not non_hadamard
+        if un_rotate and stored_t:
+            # dequantize_symmetric (dequantizer.py:66, 82-83) decides `is_conv` from the *stored* tensor's rank: a weight kept in
+            # matmul layout is 2-D, so the reference rotates the 4-D result along its last (kernel-width) axis and fails in unflatten
+            raise NotImplementedError("sdnq_b200: a Hadamard-rotated convolution weight stored in matmul layout cannot be dequantised "
+                                      "(the reference raises on this combination too: rotate_hadamard over the kernel-width axis)")
         if stored_t:      # matmul layout: weight [K,N] K-major (physically [N,K]), scale / zp [1,N]
             N, K = self.matmul_nk()
             weight = ops.physical_nk(weight)
@@ -102,11 +106,17 @@ class SDNQDequantizer:
             view = tuple(self.quantized_weight_shape)
         addend = None
         if svd_up is not None:
-            if stored_t:
-                svd_up, svd_down = svd_up.t().contiguous(), svd_down.contiguous().t()
+            if skip_quantized_matmul:      # the factors are transposed whenever the layer is in matmul mode, re-quantised or not
+                svd_up, svd_down = svd_up.t().contiguous(), svd_down.contiguous().t()      # (quantizer.py:164-167, dequantizer.py:30-36)
             addend = torch.mm(svd_up, svd_down)
         out = ops.dequant_nd(weight, self.weights_dtype, scale, zero_point, view, dtype, use_codebook=self.use_codebook, addend=addend)
-        return out.view(tuple(self.result_shape) if self.result_shape is not None else tuple(self.original_shape))
+        shape = tuple(self.result_shape) if self.result_shape is not None else tuple(self.original_shape)
+        if un_rotate:
+            # rotate_hadamard(result, is_conv=True) (quant_utils.py:193-209): groups of hadamard_group_size along the flattened
+            # [N, C*kh*kw] weight, product rounded to the result dtype -- the rotation stage of K2 on the dense matrix
+            flat = out.view(shape[0], -1)
+            out = ops.act_quant(flat, "int8", hadamard_group=self.hadamard_group_size, want_x_rot=True)[4]
+        return out.view(shape)
 
     # ---- K4 ------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -123,6 +133,15 @@ class SDNQDequantizer:
     def re_quantize_matmul_raw(self, weight, scale, zero_point=None, want_colsum: bool = False):
         """physical form for the kernels: (wq [N,K], sw [N], zw [N] | None, colsum [N] | None)"""
         N, K = self._linear_nk()
+        if self.is_conv:
+            # re_quantize_*_mm on a convolution (dequantizer.py:166-200): dequantise over the quantised view in f32 (K3c), flatten to
+            # [N, C*kh*kw], row-wise quantise -- the row quantiser is K2 run on the dense f32 matrix (same arithmetic, bit-exact).
+            # Run once per layer; forward.matmul_operand caches the result.
+            dense = ops.dequant_nd(weight, self.weights_dtype, scale, zero_point, tuple(self.quantized_weight_shape), torch.float32,
+                                   use_codebook=self.use_codebook).view(N, K)
+            uint8_mm = self.is_integer_matmul and self.is_unsigned_matmul
+            wq, sw, zw, colsum, _ = ops.act_quant(dense, self.quantized_matmul_dtype, want_rowsum=want_colsum or uint8_mm)
+            return wq, sw, zw, colsum
         return ops.requant(weight, self.weights_dtype, scale, zero_point, N, K, self.group_size, self.quantized_matmul_dtype,
                            use_codebook=self.use_codebook, want_colsum=want_colsum)
 

@@ -11,6 +11,8 @@ Same names / dispatch rule as the reference (forward.py:6-57, layers/linear/*.py
 
 Every function runs CUDA kernels from libsdnq_b200.so; there is no eager / CPU fallback (a CPU tensor raises)."""
 import os
+import warnings
+import weakref
 from collections.abc import Callable
 
 import torch
@@ -34,6 +36,44 @@ def _flat_f32(t):
     return None if t is None else t.reshape(-1).to(torch.float32).contiguous()
 
 
+_UNTRACKED = 0
+
+
+def _version(t) -> int:
+    """In-place version of a tensor; tensors created under torch.inference_mode() do not track one: every look at such a tensor
+    returns a new value, so nothing derived from it is ever taken for current."""
+    global _UNTRACKED
+    try:
+        return t._version
+    except RuntimeError:
+        _UNTRACKED -= 1
+        return _UNTRACKED
+
+
+class _StoredState:
+    """Identity of a layer's stored tensors at the time something was derived from them: a weak reference to each tensor object
+    plus its data pointer and in-place version, and the module's generation counter (bumped by SDNQLayer._apply and
+    _load_from_state_dict).  data_ptr / _version alone are not enough: CPU-offload re-uploads weights into blocks the caching
+    allocator has just recycled (same pointer, version 0) -- those arrive as *new* tensor objects, which the weak references see."""
+    __slots__ = ("refs", "marks", "gen")
+
+    def __init__(self, layer, tensors):
+        self.refs = tuple(None if t is None else weakref.ref(t) for t in tensors)
+        self.marks = tuple(None if t is None else (t.data_ptr(), _version(t)) for t in tensors)
+        self.gen = layer.__dict__.get("_sdnq_generation", 0)
+
+    def matches(self, layer, tensors) -> bool:
+        if self.gen != layer.__dict__.get("_sdnq_generation", 0) or len(tensors) != len(self.refs):
+            return False
+        for t, r, m in zip(tensors, self.refs, self.marks):
+            if t is None:
+                if r is not None:
+                    return False
+            elif r is None or r() is not t or m != (t.data_ptr(), _version(t)):
+                return False
+        return True
+
+
 @torch.no_grad()
 def matmul_operand(layer) -> _MatmulOperand:
     """Build (once) and cache the matmul operand of a W8A8 layer.
@@ -43,10 +83,10 @@ def matmul_operand(layer) -> _MatmulOperand:
     stored tensors are replaced (apply_sdnq_options_to_model swaps .data, load_state_dict(assign=True) swaps the Parameter)."""
     d = layer.sdnq_dequantizer
     w, s, z = layer.weight, layer.scale, layer.zero_point
-    key = (w.data_ptr(), w._version, s.data_ptr(), None if z is None else z.data_ptr(), d.quantized_matmul_dtype, str(w.device))
     cached = layer.__dict__.get("_sdnq_mm_cache")
-    if cached is not None and cached.key == key:
+    if cached is not None and cached.key[1] == d.quantized_matmul_dtype and cached.key[0].matches(layer, (w, s, z)):
         return cached
+    key = (_StoredState(layer, (w, s, z)), d.quantized_matmul_dtype)
     N, K = d.matmul_nk()
     mm = d.quantized_matmul_dtype
     uint8_mm = d.is_integer_matmul and d.is_unsigned_matmul
@@ -70,7 +110,9 @@ def matmul_operand(layer) -> _MatmulOperand:
             wq = ops.unpack(w, d.weights_dtype, (N, K), dtype=torch.float8_e4m3fn)
         sw = _flat_f32(s)
     else:
-        wq = ops.physical_nk(w)
+        if w.dtype not in (torch.int8, torch.uint8, torch.float8_e4m3fn, torch.float8_e5m2):
+            raise NotImplementedError(f"sdnq_b200: a {w.dtype} weight cannot be the operand of a {mm} tensor-core matmul")
+        wq = ops.physical_nk(w)       # float8_e5m2 codes stay as stored: the GEMM reads them as e5m2 (mixed e4m3 x e5m2 operands)
         sw = _flat_f32(s)
         zp = _flat_f32(z)
         if wq.dtype == torch.uint8:                                                 # uint8 codes -> int8 around 128
@@ -100,9 +142,8 @@ def _side_stream(device):
     return st
 
 
-def _weights_key(layer):
-    ts = (layer.weight, layer.scale, layer.zero_point, layer.svd_up, layer.svd_down)
-    return tuple((t.data_ptr(), t._version) if t is not None else None for t in ts)
+def _stored_tensors(layer):
+    return (layer.weight, layer.scale, layer.zero_point, layer.svd_up, layer.svd_down)
 
 
 def _dequant_weight(layer, dtype, skip_quantized_matmul):
@@ -118,9 +159,15 @@ def _dequant_weight_overlapped(layer, input, skip_quantized_matmul):
         return _dequant_weight(layer, dtype, skip_quantized_matmul)
     main = torch.cuda.current_stream(input.device)
     side = _side_stream(input.device)
-    key = _weights_key(layer)
-    fresh = layer.__dict__.get("_sdnq_dq_key") != key
-    layer.__dict__["_sdnq_dq_key"] = key
+    # The side stream may run ahead of the main stream only while the stored tensors are provably the ones it has already been
+    # ordered after: same tensor objects (weak references), same data pointers and versions, same module generation.  Anything
+    # else -- a fresh load, .to(device) of an offloaded module (new Parameter objects in recycled memory), an in-place edit --
+    # makes the side stream wait for the main stream first.
+    tensors = _stored_tensors(layer)
+    seen = layer.__dict__.get("_sdnq_dq_key")
+    fresh = seen is None or not seen.matches(layer, tensors)
+    if fresh:
+        layer.__dict__["_sdnq_dq_key"] = _StoredState(layer, tensors)
     capturing = torch.cuda.is_current_stream_capturing()
     with torch.cuda.stream(side):
         side_capturing = torch.cuda.is_current_stream_capturing()
@@ -140,9 +187,8 @@ def _dequant_linear(layer, input, skip_quantized_matmul):
 def _small_m_packed_ok(self, input) -> bool:
     """K5p applies to rows < 32 of a Linear whose weight is stored packed and / or with group-wise scales (no codebook,
     no tensor-wise scale, 2..8 bits, scale groups that are multiples of 8 columns) and 16-bit activations: the stored bytes are read
-    once instead of dequantise + GEMM.  Opt-in this round (SDNQ_B200_SMALL_M_PACKED=1): the kernel is validated against the oracle
-    on the host emulator (tests/test_device_arithmetic_on_host.py); it becomes the default after its first run on hardware."""
-    if os.environ.get("SDNQ_B200_SMALL_M_PACKED", "0") in ("0", "false", "no", ""):
+    once instead of dequantise + GEMM.  Default; SDNQ_B200_SMALL_M_PACKED=0 restores the reference-shaped dequantise + GEMM."""
+    if os.environ.get("SDNQ_B200_SMALL_M_PACKED", "1") in ("0", "false", "no"):
         return False
     d = self.sdnq_dequantizer
     if (d.use_codebook or d.group_size == -2 or self.weight.ndim > 3 or d.is_conv
@@ -187,7 +233,42 @@ def _small_m_gemv_ok(self, input) -> bool:
     no packing, no SVD) and the activations are 16-bit.  SDNQ_B200_SMALL_M_GEMV=0 keeps the reference's dequantise + GEMM."""
     d = self.sdnq_dequantizer
     return (not d.re_quantize_for_matmul and not d.is_packed and self.svd_up is None and input.dtype in (torch.bfloat16, torch.float16)
+            and self.weight.dtype in (torch.int8, torch.uint8, torch.float8_e4m3fn, torch.float8_e5m2)
             and input.shape[-1] % 16 == 0 and input.numel() > 0 and os.environ.get("SDNQ_B200_SMALL_M_GEMV", "1") not in ("0", "false", "no"))
+
+
+# ---- K2 reuse: sibling projections quantise the same activations once ------------------------------------------------------
+# to_q / to_k / to_v of an attention block (FLUX single blocks: proj_mlp as well) and the cross-attention to_k / to_v of *every*
+# block (all fed the same encoder_hidden_states) call their forward with the very same input tensor, and the reference rotates
+# and row-quantises it again for each of them (linear_int8.py:55-63).  Here the result of K2 is kept -- one entry per device
+# and stream -- and reused while the next W8A8 forward on that stream presents the same tensor: same storage pointer, shape,
+# strides, dtype and in-place version, with a strong reference to the cached input held so that its memory cannot be recycled
+# under a new tensor.  The key carries the stream's CUDA-graph capture id: nothing computed eagerly is baked into a graph and
+# nothing from one capture is used in another.  SDNQ_B200_ACT_CACHE=0 turns it off.
+_ACT_CACHE: dict = {}
+
+
+def _act_cache_on() -> bool:
+    return os.environ.get("SDNQ_B200_ACT_CACHE", "1") not in ("0", "false", "no")
+
+
+def quantized_activations(x2: torch.Tensor, mm: str, hg: int, want_rowsum: bool, want_x_rot: bool):
+    """K2 on x2 [M,K] -> (xq, sx, zx, rowsum, x_rot), shared between consecutive forwards that present the same tensor."""
+    if not _act_cache_on() or not x2.is_cuda:       # (a CPU tensor raises inside ops: there is no CPU path)
+        return ops.act_quant(x2, mm, hadamard_group=hg, want_rowsum=want_rowsum, want_x_rot=want_x_rot)
+    stream = torch.cuda.current_stream(x2.device).cuda_stream
+    slot = (x2.device.index, stream)
+    key = (x2.data_ptr(), _version(x2), tuple(x2.shape), tuple(x2.stride()), x2.dtype, mm, int(hg), ops.capture_id(stream))
+    hit = _ACT_CACHE.get(slot)
+    if hit is not None and hit[0] == key and (not want_rowsum or hit[2][3] is not None) and (not want_x_rot or hit[2][4] is not None):
+        return hit[2]
+    out = ops.act_quant(x2, mm, hadamard_group=hg, want_rowsum=want_rowsum, want_x_rot=want_x_rot)
+    _ACT_CACHE[slot] = (key, x2, out)          # x2 is kept alive until the next miss on this stream replaces the entry
+    return out
+
+
+def _rows(input: torch.Tensor) -> torch.Tensor:
+    return input.reshape(-1, input.shape[-1])
 
 
 def _w8a8_forward(self, input: torch.Tensor) -> torch.Tensor:
@@ -209,7 +290,7 @@ def _w8a8_forward(self, input: torch.Tensor) -> torch.Tensor:
     mm = d.quantized_matmul_dtype
     hg = d.hadamard_group_size if d.use_hadamard else 0
     if op.packed is not None:
-        xq, sx, _, rowsum, x_rot = ops.act_quant(input, mm, hadamard_group=hg, want_rowsum=op.zp is not None, want_x_rot=self.svd_up is not None)
+        xq, sx, _, rowsum, x_rot = quantized_activations(_rows(input), mm, hg, op.zp is not None, self.svd_up is not None)
         bias = self.bias
         if self.svd_up is not None:
             low = torch.mm(x_rot.to(self.svd_down.dtype), self.svd_down)
@@ -217,10 +298,14 @@ def _w8a8_forward(self, input: torch.Tensor) -> torch.Tensor:
         out = ops.scaled_mm_packed(xq, op.wq, op.packed, d.original_shape[0], sx, op.sw, bias, input.dtype, rowsum=rowsum, zp=op.zp)
         return out.view(*input.shape[:-1], out.shape[-1])
     if self.svd_up is None:
-        return ops.linear_w8a8(input, op.wq, mm, op.sw, bias=self.bias, zp=op.zp, colsum=op.colsum, hadamard_group=hg, out_dtype=input.dtype)
+        if not _act_cache_on():       # one C call: K2 into the per-stream workspace + K1
+            return ops.linear_w8a8(input, op.wq, mm, op.sw, bias=self.bias, zp=op.zp, colsum=op.colsum, hadamard_group=hg, out_dtype=input.dtype)
+        xq, sx, zx, rowsum, _ = quantized_activations(_rows(input), mm, hg, op.zp is not None, False)
+        out = ops.scaled_mm(xq, op.wq, sx, op.sw, self.bias, input.dtype, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx)
+        return out.view(*input.shape[:-1], out.shape[-1])
     # SVD branch: bias2d = bias + (x_rot @ svd_down[K,r]) @ svd_up[r,N] in the SVD dtype on the rotated, un-quantised
     # activations (linear_int8.py:57-62); two skinny library GEMMs, the rest stays in our kernels.
-    xq, sx, zx, rowsum, x_rot = ops.act_quant(input, mm, hadamard_group=hg, want_rowsum=op.zp is not None, want_x_rot=True)
+    xq, sx, zx, rowsum, x_rot = quantized_activations(_rows(input), mm, hg, op.zp is not None, True)
     down, up = self.svd_down, self.svd_up
     low = torch.mm(x_rot.to(down.dtype), down)
     bias2d = torch.mm(low, up) if self.bias is None else torch.addmm(self.bias.to(down.dtype), low, up)
@@ -289,6 +374,17 @@ def _pair(v, n):
     return (int(v),) * n if isinstance(v, int) else tuple(int(i) for i in v)
 
 
+def conv_matmul_unsupported(module) -> str | None:
+    """Why the quantized conv matmul of this convolution has no sm_100a kernel (None = it has one)."""
+    if getattr(module, "groups", 1) != 1:
+        return "a grouped convolution"
+    if len(tuple(getattr(module, "kernel_size", (1, 1)))) > 2:
+        return "Conv3d"
+    if isinstance(getattr(module, "padding", 0), str):
+        return "string padding ('same' / 'valid')"
+    return None
+
+
 def _w8a8_conv_forward(self, input: torch.Tensor) -> torch.Tensor:
     """conv_{int8,uint8,fp8}_matmul (reference layers/conv/conv_int8.py:17-125, conv_uint8.py, conv_fp8.py): the convolution as
     one W8A8 GEMM over the im2col view.  Here: K2 gathers each im2col row straight from the input (the [M, C*kh*kw] bf16
@@ -297,19 +393,20 @@ def _w8a8_conv_forward(self, input: torch.Tensor) -> torch.Tensor:
     d = self.sdnq_dequantizer
     if input.numel() / input.shape[2] < SMALL_M:                                  # conv_int8.py:95-96
         return self._conv_forward(input, _conv_dense_weight(self, True, input), self.bias)
-    if self.groups != 1:
-        raise NotImplementedError("sdnq_b200: grouped convolutions have no W8A8 kernel yet (set use_quantized_matmul_conv=False for them)")
-    if self.padding_mode != "zeros":
-        raise NotImplementedError(f"sdnq_b200: padding_mode={self.padding_mode!r} has no W8A8 conv kernel yet")
-    if input.ndim not in (3, 4):
-        raise NotImplementedError("sdnq_b200: Conv3d has no W8A8 kernel yet")
-    if isinstance(self.padding, str):
-        raise NotImplementedError("sdnq_b200: string padding ('same' / 'valid') has no W8A8 conv kernel yet")
+    why = conv_matmul_unsupported(self)
+    if why is not None:
+        # sdnq_quantize_layer keeps such layers on the dequant path when it quantises them (with a warning); this is reached only by
+        # a checkpoint that was written with the quantized conv matmul on for them
+        raise NotImplementedError(f"sdnq_b200: {why} has no W8A8 conv kernel; call apply_sdnq_options_to_model(model, "
+                                  "use_quantized_matmul=False) or list the layer in modules_to_not_use_matmul")
     nd = input.ndim - 2
     ksz, stride, padding, dilation = (_pair(v, nd) for v in (self.kernel_size, self.stride, self.padding, self.dilation))
     x4 = input
+    if self.padding_mode != "zeros":                                              # process_conv_input (layers/conv/forward.py:53-55)
+        x4 = torch.nn.functional.pad(input, self._reversed_padding_repeated_twice, mode=self.padding_mode)
+        padding = (0,) * nd
     if nd == 1:                                                                   # get_conv_args: conv1d = conv2d with H = 1
-        x4 = input.unsqueeze(2)
+        x4 = x4.unsqueeze(2)
         ksz, stride, padding, dilation = (1, ksz[0]), (1, stride[0]), (0, padding[0]), (1, dilation[0])
     op = matmul_operand(self)
     mm = d.quantized_matmul_dtype

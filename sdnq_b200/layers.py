@@ -40,6 +40,23 @@ class SDNQLayer(torch.nn.Module):
     def forward(self, *args, **kwargs) -> torch.Tensor:
         return self.forward_func(self, *args, **kwargs)
 
+    # Everything the forwards derive from the stored tensors (the cached matmul operand, the side stream's licence to run ahead
+    # of the caller's stream) is tied to a generation counter that any wholesale replacement of the tensors bumps.
+    def _sdnq_touch(self):
+        self.__dict__["_sdnq_generation"] = self.__dict__.get("_sdnq_generation", 0) + 1
+
+    def _apply(self, fn, *args, **kwargs):
+        self._sdnq_touch()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._sdnq_touch()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def __getstate__(self):
+        # derived per-process state (cached operands, stream bookkeeping: weak references, device buffers) is not part of the module
+        return {k: v for k, v in self.__dict__.items() if not k.startswith("_sdnq_")}
+
     def __repr__(self) -> str:
         return (f"{self.__class__.__name__}(original_class={self.original_class} forward_func={self.forward_func} "
                 f"sdnq_dequantizer={getattr(self, 'sdnq_dequantizer', None)})")

@@ -3,12 +3,12 @@ function resolves raw device pointers and calls the hand-written sm_100a kernels
 import torch
 
 from . import _lib
-from ._lib import (SDNQ_BF16, SDNQ_F16, SDNQ_F32, SDNQ_F8E4M3, SDNQ_I8, SDNQ_I32, SDNQ_U8, SDNQ_W_FP8_E4M3FN, SDNQ_W_FP8_E5M2,
+from ._lib import (SDNQ_BF16, SDNQ_F16, SDNQ_F32, SDNQ_F8E4M3, SDNQ_F8E5M2, SDNQ_I8, SDNQ_I32, SDNQ_U8, SDNQ_W_FP8_E4M3FN, SDNQ_W_FP8_E5M2,
                    SDNQ_W_INT, SDNQ_W_MINIFLOAT, WeightFormat, check)
 from .common import dtype_dict
 
 _TORCH_TO_CODE = {torch.float32: SDNQ_F32, torch.bfloat16: SDNQ_BF16, torch.float16: SDNQ_F16, torch.int8: SDNQ_I8,
-                  torch.uint8: SDNQ_U8, torch.float8_e4m3fn: SDNQ_F8E4M3, torch.int32: SDNQ_I32}
+                  torch.uint8: SDNQ_U8, torch.float8_e4m3fn: SDNQ_F8E4M3, torch.int32: SDNQ_I32, torch.float8_e5m2: SDNQ_F8E5M2}
 _MM_CODE = {"int8": SDNQ_I8, "uint8": SDNQ_U8, "float8_e4m3fn": SDNQ_F8E4M3, "fp8": SDNQ_F8E4M3}
 _MM_TORCH = {SDNQ_I8: torch.int8, SDNQ_U8: torch.int8, SDNQ_F8E4M3: torch.float8_e4m3fn}
 
@@ -46,12 +46,31 @@ def weight_format(weights_dtype: str, storage: torch.Tensor | None = None) -> We
     return WeightFormat(SDNQ_W_MINIFLOAT, e["num_bits"], int(e["is_unsigned"]), e["exponent"], e["mantissa"], word_bytes)
 
 
+def _operand_code(a_dtype: torch.dtype, b: torch.Tensor) -> int:
+    """The C ABI's operand code of a GEMM over activation codes of `a_dtype` and the 1-byte weight `b`.  The weight's own dtype
+    decides how its bytes are decoded (a float8_e5m2 weight under a float8_e4m3fn matmul is the mixed pair of torch._scaled_mm);
+    anything the tensor cores cannot take raises instead of being reinterpreted."""
+    if a_dtype == torch.float8_e4m3fn:
+        if b.dtype == torch.float8_e4m3fn:
+            return SDNQ_F8E4M3
+        if b.dtype == torch.float8_e5m2:
+            return SDNQ_F8E5M2
+    elif a_dtype == torch.int8 and b.dtype == torch.int8:
+        return SDNQ_I8
+    raise _lib.SDNQKernelError(f"no sm_100a GEMM for {a_dtype} activation codes x {b.dtype} weight codes")
+
+
 def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
 def _ptr(t):
     return None if t is None else t.data_ptr()
+
+
+def capture_id(stream: int) -> int:
+    """0 when `stream` (a raw cudaStream_t) is not being captured into a CUDA graph, else the id of the capture."""
+    return int(_lib.load().sdnq_b200_stream_capture_id(stream))
 
 
 def _require_cuda(*tensors):
@@ -273,7 +292,7 @@ def scaled_mm(a: torch.Tensor, b_nk: torch.Tensor, sx: torch.Tensor, sw: torch.T
         bias_code = dtype_code(bias.dtype)
         if bias.ndim == 2 and bias.shape[0] != 1:
             bias_ld = bias.stride(0)
-    ab = SDNQ_F8E4M3 if a.dtype == torch.float8_e4m3fn else SDNQ_I8
+    ab = _operand_code(a.dtype, b_nk)
     with torch.cuda.device(a.device):
         check(lib.sdnq_b200_scaled_mm(_ptr(a), _ptr(b_nk), ab, _ptr(sx), _ptr(sw), _ptr(bias), bias_code, bias_ld,
                                       _ptr(rowsum), _ptr(zp), _ptr(colsum), _ptr(zx), _ptr(out), dtype_code(out_dtype), M, N, K, _stream(a)))
@@ -307,7 +326,7 @@ def mm(a: torch.Tensor, b_nk: torch.Tensor) -> torch.Tensor:
     fp8 = a.dtype == torch.float8_e4m3fn
     out = torch.empty((M, N), dtype=torch.float32 if fp8 else torch.int32, device=a.device)
     with torch.cuda.device(a.device):
-        check(_lib.load().sdnq_b200_mm(_ptr(a), _ptr(b_nk), SDNQ_F8E4M3 if fp8 else SDNQ_I8, _ptr(out), M, N, K, _stream(a)))
+        check(_lib.load().sdnq_b200_mm(_ptr(a), _ptr(b_nk), _operand_code(a.dtype, b_nk), _ptr(out), M, N, K, _stream(a)))
     return out
 
 
@@ -320,7 +339,9 @@ def linear_small_m(x: torch.Tensor, wq_nk: torch.Tensor, sw, zp=None, bias=None)
         x2 = x2.contiguous()
     M, N = x2.shape[0], wq_nk.shape[0]
     out = torch.empty((M, N), dtype=x.dtype, device=x.device)
-    wcode = SDNQ_F8E4M3 if wq_nk.dtype == torch.float8_e4m3fn else SDNQ_I8
+    if wq_nk.dtype not in (torch.int8, torch.float8_e4m3fn, torch.float8_e5m2):
+        raise _lib.SDNQKernelError(f"linear_small_m: weight codes must be int8 / float8_e4m3fn / float8_e5m2 (got {wq_nk.dtype})")
+    wcode = dtype_code(wq_nk.dtype)
     with torch.cuda.device(x.device):
         check(_lib.load().sdnq_b200_linear_small_m(_ptr(x2), dtype_code(x2.dtype), x2.stride(0), _ptr(wq_nk), wcode, _ptr(sw), _ptr(zp), _ptr(bias),
                                                    dtype_code(bias.dtype) if bias is not None else SDNQ_F32, _ptr(out), M, N, K, _stream(x)))
@@ -392,16 +413,22 @@ def linear_w8a8(x, wq_nk, matmul_dtype, sw, bias=None, zp=None, colsum=None, had
     out = torch.empty((M, N), dtype=out_dtype, device=x.device)
     nbytes = lib.sdnq_b200_linear_w8a8_workspace_bytes(M, K)
     ws = _workspace(x.device, nbytes)
+    code = mm_code(matmul_dtype)
+    expect = torch.int8 if code in (SDNQ_I8, SDNQ_U8) else torch.float8_e4m3fn
+    if wq_nk.dtype == torch.float8_e5m2 and code == SDNQ_F8E4M3:
+        code = SDNQ_F8E5M2                    # e4m3 activation codes x the stored e5m2 weight
+    elif wq_nk.dtype != expect:
+        raise _lib.SDNQKernelError(f"linear_w8a8: a {matmul_dtype} matmul cannot read {wq_nk.dtype} weight codes")
     if fused:
         if zp is not None or colsum is not None or hadamard_group:
             raise _lib.SDNQKernelError("fused Linear: no zero-point terms and no Hadamard rotation")
         with torch.cuda.device(x.device):
-            check(lib.sdnq_b200_linear_w8a8_fused(_ptr(x2), dtype_code(x2.dtype), x2.stride(0), _ptr(wq_nk), mm_code(matmul_dtype), _ptr(sw),
+            check(lib.sdnq_b200_linear_w8a8_fused(_ptr(x2), dtype_code(x2.dtype), x2.stride(0), _ptr(wq_nk), code, _ptr(sw),
                                                   _ptr(bias), dtype_code(bias.dtype) if bias is not None else SDNQ_F32, _ptr(out),
                                                   dtype_code(out_dtype), M, N, K, _ptr(ws), ws.numel(), _stream(x)))
         return out.view(*x.shape[:-1], N)
     with torch.cuda.device(x.device):
-        check(lib.sdnq_b200_linear_w8a8(_ptr(x2), dtype_code(x2.dtype), x2.stride(0), _ptr(wq_nk), mm_code(matmul_dtype), _ptr(sw),
+        check(lib.sdnq_b200_linear_w8a8(_ptr(x2), dtype_code(x2.dtype), x2.stride(0), _ptr(wq_nk), code, _ptr(sw),
                                         _ptr(zp), _ptr(colsum), _ptr(bias), dtype_code(bias.dtype) if bias is not None else SDNQ_F32,
                                         int(hadamard_group), _ptr(out), dtype_code(out_dtype), M, N, K, _ptr(ws), ws.numel(), _stream(x)))
     return out.view(*x.shape[:-1], N)

@@ -8,12 +8,14 @@ tensors and metadata as the reference did (fixtures in tests/golden/).
 Platform constants folded in (the reference resolves them at import time from the device, kernel_wrappers.py:9-103;
 SURVEY.md 5a gives their values on a B200): K-major B operands (use_contiguous_*_mm = False), fp8 matmul supported,
 use_tensorwise_fp8_matmul = True."""
+import warnings
+
 import torch
 
 from .common import conv_transpose_types, conv_types, dtype_dict, embedding_types, linear_types, weights_dtype_order
 from .config import QuantizationMethod, SDNQConfig
 from .dequantizer import SDNQDequantizer
-from .forward import get_forward_func
+from .forward import conv_matmul_unsupported, get_forward_func
 from .layers import get_sdnq_wrapper_class
 from .packing import pack_float, pack_int
 from .quant_math import (apply_hadamard, apply_svdquant, prepare_svd_for_matmul, prepare_weight_for_matmul, quantize_weight,
@@ -265,12 +267,21 @@ def sdnq_quantize_layer_weight_dynamic(weight, layer_class_name=None, weights_dt
 
 @torch.no_grad()
 def sdnq_quantize_layer(layer: torch.nn.Module, quantization_config: SDNQConfig, torch_dtype: torch.dtype | None = None,
-                        param_name: str = "", quant_kwargs: dict | None = None):
+                        param_name: str = "", quant_kwargs: dict | None = None, pre_quantized: bool = False):
     """Quantise one module in place and return (SDNQ wrapper, config)   (reference quantizer.py:422-473)."""
     torch_dtype = torch_dtype or layer.weight.dtype
     if quant_kwargs is None:
         quant_kwargs = get_quant_kwargs(layer, quantization_config, torch_dtype=torch_dtype, param_name=param_name)
     layer_class_name = layer.__class__.__name__
+    wanted_matmul = bool(quant_kwargs["use_quantized_matmul"])
+    if wanted_matmul and layer_class_name in conv_types and not pre_quantized:
+        # convolutions whose quantized matmul has no kernel here (groups, Conv3d, string padding) stay on the dequant path -- decided
+        # now, so that a model never quantises / loads fine and then fails in its first forward
+        why = conv_matmul_unsupported(layer)
+        if why is not None:
+            warnings.warn(f"sdnq_b200: {param_name or layer_class_name}: {why} has no W8A8 conv kernel; keeping the layer on the "
+                          "dequant path (use_quantized_matmul=False for it)", stacklevel=2)
+            quant_kwargs["use_quantized_matmul"] = False
     is_conv = layer_class_name in conv_types or layer_class_name in conv_transpose_types
     if (layer_class_name in embedding_types and not quantization_config.quant_embedding) or (is_conv and not quantization_config.quant_conv):
         quantization_config.modules_to_not_convert.append(param_name)
@@ -305,7 +316,7 @@ def sdnq_quantize_layer(layer: torch.nn.Module, quantization_config: SDNQConfig,
             setattr(layer, key, param)
         else:
             setattr(layer, key, value)
-    if (quant_kwargs["use_quantized_matmul"] and not deq.use_quantized_matmul
+    if (wanted_matmul and not deq.use_quantized_matmul
             and check_param_name_in(param_name, quantization_config.modules_to_not_use_matmul) is None):
         quantization_config.modules_to_not_use_matmul.append(param_name)
     return layer, quantization_config
@@ -321,7 +332,8 @@ def apply_sdnq_to_module(model: torch.nn.Module, quantization_config: SDNQConfig
             name = name + ".weight"
             if check_param_name_in(name, quantization_config.modules_to_not_convert) is None:
                 if check_quant_is_allowed(child.__class__.__name__, child.weight, quantization_config, pre_quantized=pre_quantized):
-                    child, quantization_config = sdnq_quantize_layer(child, quantization_config, torch_dtype=torch_dtype, param_name=name)
+                    child, quantization_config = sdnq_quantize_layer(child, quantization_config, torch_dtype=torch_dtype, param_name=name,
+                                                                     pre_quantized=pre_quantized)
                     setattr(model, child_name, child)
                 else:
                     quantization_config.modules_to_not_convert.append(name)

@@ -210,6 +210,17 @@ LAYER_CASES = {
     "int8_w8a8_small_m":            (256, 128, 8,  True,  dict(weights_dtype="int8", use_quantized_matmul=True)),
     "int8_tensorwise_dequant":      (256, 128, 40, True,  dict(weights_dtype="int8", group_size=-2)),
     "int8_w8a8_outliers":           (512, 256, 64, True,  dict(weights_dtype="int8", use_quantized_matmul=True)),
+    # round 2: float8_e5m2 weights under the e4m3 matmul (mixed e4m3 x e5m2 operands), its small-M branch and its dequant path
+    "fp8_e5m2_w8a8":                (256, 128, 48, True,  dict(weights_dtype="float8_e5m2", use_quantized_matmul=True)),
+    "fp8_e5m2_w8a8_small_m":        (256, 128, 8,  True,  dict(weights_dtype="float8_e5m2", use_quantized_matmul=True)),
+    "fp8_e5m2_dequant":             (256, 128, 40, True,  dict(weights_dtype="float8_e5m2")),
+    # round 2: rows < 32 of packed / group-wise layers (the K5p kernel) against the reference's dequantise + F.linear
+    "c4_int4_g128_svd_dequant_small_m": (256, 128, 8, True, dict(weights_dtype="int4", group_size=128, use_svd=True, svd_rank=32)),
+    "uint4_auto_w8a8_small_m":      (256, 128, 8,  True,  dict(weights_dtype="uint4", use_quantized_matmul=True)),
+    "float6_e3m2_w8a8_small_m":     (256, 128, 5,  True,  dict(weights_dtype="float6_e3m2fn", use_quantized_matmul=True)),
+    "int5_dequant_small_m":         (256, 128, 4,  True,  dict(weights_dtype="int5", group_size=32)),
+    "uint2_hadamard_dequant_small_m": (256, 128, 31, True, dict(weights_dtype="uint2", use_hadamard=True)),
+    "int4_g128_svd_w8a8_small_m":   (256, 128, 16, True,  dict(weights_dtype="int4", group_size=128, use_svd=True, svd_rank=32, use_quantized_matmul=True)),
 }
 
 
@@ -295,12 +306,16 @@ def run_layer_case(name, K, N, M, bias, cfg):
 
 
 def main():
-    dump_dtype_table()
-    dump_pack_kat()
-    dump_float_tables()
-    dump_hadamard()
-    dump_policy_tables()
+    only = [n for n in os.environ.get("SDNQ_GOLDEN_ONLY", "").split(",") if n]      # regenerate just the named layer cases
+    if not only:
+        dump_dtype_table()
+        dump_pack_kat()
+        dump_float_tables()
+        dump_hadamard()
+        dump_policy_tables()
     for name, (K, N, M, bias, cfg) in LAYER_CASES.items():
+        if only and name not in only:
+            continue
         run_layer_case(name, K, N, M, bias, cfg)
     total = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith((".npz", ".json")))
     print("fixtures bytes:", total)

@@ -52,6 +52,15 @@ CASES = {
     "uint4_convT_g16_dequant": ("ConvTranspose2d", dict(in_channels=32, out_channels=32, kernel_size=3, stride=1, padding=1), (2, 32, 6, 6), dict(weights_dtype="uint4", group_size=16, **DQ)),
     "int8_conv1dT_dequant":   ("ConvTranspose1d", dict(in_channels=32, out_channels=64, kernel_size=4, stride=2, padding=1), (2, 32, 20), dict(weights_dtype="int8", **DQ)),
     "int8_conv3d_dequant":    ("Conv3d", dict(in_channels=32, out_channels=32, kernel_size=3, padding=1), (1, 32, 4, 6, 6), dict(weights_dtype="int8", **DQ)),
+    # round 2: re-quantised (grouped / packed) conv weights on the quantized matmul, SVD factors of a re-quantised layer, padding modes,
+    # Hadamard-rotated conv weights on the dequant path
+    "uint4_3x3_g16_w8a8":     ("Conv2d", dict(in_channels=32, out_channels=64, kernel_size=3, padding=1), (1, 32, 8, 8), dict(weights_dtype="uint4", group_size=16, **W8)),
+    "uint4_3x3_g16_svd_w8a8": ("Conv2d", dict(in_channels=32, out_channels=64, kernel_size=3, padding=1), (1, 32, 8, 8), dict(weights_dtype="uint4", group_size=16, use_svd=True, svd_rank=8, **W8)),
+    "uint4_3x3_g16_svd_w8a8_small_m": ("Conv2d", dict(in_channels=32, out_channels=64, kernel_size=3, padding=1), (1, 32, 4, 4), dict(weights_dtype="uint4", group_size=16, use_svd=True, svd_rank=8, **W8)),
+    "int5_3x3_g16_w8a8":      ("Conv2d", dict(in_channels=32, out_channels=48, kernel_size=3, padding=1), (2, 32, 8, 6), dict(weights_dtype="int5", group_size=16, **W8)),
+    "float6_3x3_g16_fp8mm":   ("Conv2d", dict(in_channels=32, out_channels=48, kernel_size=3, padding=1), (2, 32, 8, 6), dict(weights_dtype="float6_e3m2fn", group_size=16, **W8)),
+    "int8_3x3_reflect_w8a8":  ("Conv2d", dict(in_channels=32, out_channels=64, kernel_size=3, padding=1, padding_mode="reflect"), (2, 32, 9, 8), dict(weights_dtype="int8", **W8)),
+    "int8_3x3_hadamard_dequant": ("Conv2d", dict(in_channels=32, out_channels=64, kernel_size=3, padding=1), (2, 32, 8, 8), dict(weights_dtype="int8", use_hadamard=True, **DQ)),
 }
 
 
@@ -113,6 +122,12 @@ def run(name, cls, kw, xshape, cfg):
 
 
 if __name__ == "__main__":
+    only = [n for n in os.environ.get("SDNQ_GOLDEN_ONLY", "").split(",") if n]      # regenerate just the named cases
     for name, (cls, kw, xshape, cfg) in CASES.items():
-        run(name, cls, kw, xshape, cfg)
+        if only and name not in only:
+            continue
+        try:
+            run(name, cls, kw, xshape, cfg)
+        except Exception as ex:      # combinations the reference itself cannot run produce no fixture
+            print(f"{name:30s} REFERENCE FAILS: {type(ex).__name__}: {str(ex)[:120]}")
     print("bytes:", sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.startswith("conv_")))

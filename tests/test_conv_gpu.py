@@ -71,6 +71,9 @@ def test_conv_act_quant_matches_reference(path):
     x4 = x
     if nd == 1:
         x4, k, s, p, dl = x.unsqueeze(2), (1, k[0]), (1, s[0]), (0, p[0]), (1, dl[0])
+    if kw.get("padding_mode", "zeros") != "zeros":       # process_conv_input pads first, then unfolds without padding
+        x4 = torch.nn.functional.pad(x4, [v for pi in reversed(p) for v in (pi, pi)], mode=kw["padding_mode"])
+        p = (0, 0)
     hg = d["hadamard_group_size"] if d["use_hadamard"] else 0
     mm = d["quantized_matmul_dtype"]
     xq, sx, zx, rowsum, x_rot, _ = ops().conv_act_quant(x4, k, s, p, dl, mm, hadamard_group=hg, want_rowsum=True, want_x_rot=True)

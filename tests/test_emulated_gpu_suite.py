@@ -170,7 +170,7 @@ def test_conv_act_quant(kw):
 # ---- layer level (SDNQConfig -> sdnq_quantize_layer -> forward_func -> ops -> C ABI) for every forward that does not need the tcgen05
 # GEMM: the dequant path (K3 + the library matmul, here torch's CPU matmul), the rows < 32 branches (K5, K5p, dequantise + matmul)
 from tests import test_layers_gpu as L  # noqa: E402
-from tests import test_zz_small_m_packed_gpu as Z  # noqa: E402
+from tests import test_small_m_packed_gpu as Z  # noqa: E402
 from tests.util import fixture_tensors  # noqa: E402
 
 
@@ -203,8 +203,13 @@ def test_small_m_forward_gemv(kw, monkeypatch):
 
 @emulated(Z.test_small_m_packed_forward_vs_dequant_path, keep=_thin_small_m)
 def test_small_m_packed_forward(kw, monkeypatch):
-    """K5p at layer level: the very test that is its hardware gate (tests/test_zz_small_m_packed_gpu.py), on the emulator"""
+    """K5p at layer level: the very test that is its hardware gate (tests/test_small_m_packed_gpu.py), on the emulator"""
     Z.test_small_m_packed_forward_vs_dequant_path(monkeypatch=monkeypatch, **kw)
+
+
+@emulated(Z.test_small_m_packed_forward_vs_oracle)
+def test_small_m_packed_forward_vs_oracle(kw):
+    Z.test_small_m_packed_forward_vs_oracle(**kw)
 
 
 def test_emulator_traps_misaligned_vector_access():

@@ -142,7 +142,10 @@ def test_layer_against_reference(path):
         else:
             assert np.array_equal(xq, xq_ref)
             assert np.array_equal(p["sx"].reshape(-1), arr["mm_sx"].reshape(-1))
-        wq_ref = O.from_e4m3fn_bits(arr["mm_wq"]) if fp8 else arr["mm_wq"]
+        if fp8 and layer.weights_dtype == "float8_e5m2" and not layer.re_quantize_for_matmul:
+            wq_ref = O.from_e5m2_bits(arr["mm_wq"])          # the stored e5m2 codes go to the matmul as they are (mixed e4m3 x e5m2)
+        else:
+            wq_ref = O.from_e4m3fn_bits(arr["mm_wq"]) if fp8 else arr["mm_wq"]
         assert np.array_equal(np.asarray(p["wq"]).astype(np.float32), np.asarray(wq_ref).astype(np.float32))
         assert np.array_equal(np.asarray(p["sw"], np.float32).reshape(-1), arr["mm_sw"].reshape(-1))
         if "mm_bias" in arr:
@@ -199,6 +202,9 @@ def test_conv_layer_against_reference(path):
         k, s_, p_, dl = t(kw["kernel_size"]), t(kw.get("stride", 1)), t(kw.get("padding", 0)), t(kw.get("dilation", 1))
         if nd == 1:
             k, s_, p_, dl = (1, k[0]), (1, s_[0]), (0, p_[0]), (1, dl[0])
+        if kw.get("padding_mode", "zeros") != "zeros":
+            x4 = np.pad(x4, [(0, 0), (0, 0)] + [(pi, pi) for pi in p_], mode=O._NP_PAD_MODE[kw["padding_mode"]])
+            p_ = (0, 0)
         cols, _ = O.conv_unfold(x4, k, s_, p_, dl)
         cols = cols.reshape(-1, cols.shape[-1])
         if not layer.use_hadamard:
@@ -214,7 +220,8 @@ def test_conv_layer_against_reference(path):
             assert np.array_equal(pm["sx"].reshape(-1), arr["mm_sx"].reshape(-1))
     # ---- output
     yref = O.from_bf16_bits(arr["y"])
-    y = O.conv_forward(layer, x, kw["kernel_size"], kw.get("stride", 1), kw.get("padding", 0), kw.get("dilation", 1))
+    y = O.conv_forward(layer, x, kw["kernel_size"], kw.get("stride", 1), kw.get("padding", 0), kw.get("dilation", 1),
+                       padding_mode=kw.get("padding_mode", "zeros"))
     assert y.shape == yref.shape
     err = np.abs(y - yref)
     scale = np.abs(yref).max()

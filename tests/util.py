@@ -16,15 +16,16 @@ CONV_FILES = sorted(glob.glob(os.path.join(GOLDEN, "conv_*.npz")))
 CONV_IDS = [os.path.basename(p)[5:-4] for p in CONV_FILES]
 
 _TORCH = {"bfloat16": torch.bfloat16, "float32": torch.float32, "float16": torch.float16, "int8": torch.int8, "uint8": torch.uint8,
-          "int64": torch.int64, "int16": torch.int16, "float8_e4m3fn": torch.float8_e4m3fn, "bool": torch.bool, "int32": torch.int32}
+          "int64": torch.int64, "int16": torch.int16, "float8_e4m3fn": torch.float8_e4m3fn, "float8_e5m2": torch.float8_e5m2, "bool": torch.bool,
+          "int32": torch.int32}
 
 
 def np_to_torch(a: np.ndarray, dtype_name: str, device="cpu") -> torch.Tensor:
     """inverse of tests/golden/generate.py:to_np (bf16 / fp8 are stored as bit patterns)."""
     if dtype_name == "bfloat16":
         t = torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16)
-    elif dtype_name == "float8_e4m3fn":
-        t = torch.from_numpy(a.copy()).view(torch.float8_e4m3fn)
+    elif dtype_name in ("float8_e4m3fn", "float8_e5m2"):
+        t = torch.from_numpy(a.copy()).view(_TORCH[dtype_name])
     else:
         t = torch.from_numpy(a.copy())
         assert t.dtype == _TORCH[dtype_name], (t.dtype, dtype_name)
@@ -69,7 +70,7 @@ def oracle_layer_from_torch(tensors, dequantizer_meta) -> O.Layer:
     def conv(t):
         if t is None:
             return None
-        if t.dtype in (torch.bfloat16, torch.float16, torch.float32, torch.float8_e4m3fn):
+        if t.dtype in (torch.bfloat16, torch.float16, torch.float32, torch.float8_e4m3fn, torch.float8_e5m2):
             return t.detach().float().cpu().numpy()
         return t.detach().cpu().numpy()
     return O.Layer(conv(tensors["weight"]), conv(tensors["scale"]), conv(tensors["zero_point"]), conv(tensors["svd_up"]),
@@ -100,7 +101,7 @@ def build_conv_layer(path):
         if t[key] is not None:
             assert mine.shape == t[key].shape, (key, mine.shape, t[key].shape)
             if key in ("weight", "scale", "zero_point") and t["svd_up"] is None:
-                a, b = (v.view(torch.uint8) if v.dtype == torch.float8_e4m3fn else v for v in (mine, t[key]))
+                a, b = (v.view(torch.uint8) if v.dtype in (torch.float8_e4m3fn, torch.float8_e5m2) else v for v in (mine, t[key]))
                 assert torch.equal(a, b), f"stored {key} differs from the reference's"
             setattr(layer, key, torch.nn.Parameter(t[key], requires_grad=False))
     return layer, t, z, meta
