@@ -253,6 +253,24 @@ SDNQ_API int sdnq_b200_linear_small_m_packed(const void* x, int x_dtype, int64_t
                                              const float* scale, const float* zero_point, int64_t group_size, const void* bias,
                                              int bias_dtype, int64_t bias_ld, void* out, int64_t M, int64_t N, int64_t K, void* stream);
 
+/* ---- K6 dequant-path Linear in one launch ("W4A16"):  quantized_linear_forward (layers/linear/forward.py:24-26) =
+ *      SDNQDequantizer.__call__ (dequantizer.py:389-429) + F.linear, for use_quantized_matmul=False layers with 4-bit weights:
+ *          out[m,n] = sum_k x[m,k] * cast_T(q[n,k] * s[n,k/g] (+ zp[n,k/g]))  +  sum_j cast_T(sum_k x[m,k] down[j,k]) * up[n,j]  + bias[n]
+ *      The packed codes are staged by TMA and dequantised (unpack, group scale, zero point, rounding to the activation dtype T --
+ *      exactly the values dequantize_symmetric / _asymmetric produce before the SVD add, dequantizer.py:15-84) into the UMMA
+ *      operand ring by the GEMM's prologue warps; the contraction runs on tcgen05 kind::f16 with f32 accumulation; the SVD
+ *      correction W += svd_up @ svd_down (dequantizer.py:69-79) is applied as a rank-r second accumulate on the activations,
+ *      (x down^T) up^T, so the [N,K] weight is never written in 16 bits.
+ *   x          [M,K] bf16 / f16 (x_dtype), row stride ldx (use_hadamard layers: pass the rotated activations, x_rot of act_quant)
+ *   weight     int4 / uint4 codes of the [N,K] weight packed as packed_int/pack.py:273-276 lays them out ([N*K/2] bytes)
+ *   scale / zero_point   f32 [N, K/group_size]; group_size <= 0 or >= K: row-wise, else a multiple of 32 dividing K
+ *   svd_down_rk [svd_rank, K] row-major and svd_up_nr [N, svd_rank] row-major, both of x_dtype (svd_rank 0: no SVD term; else 16 / 32 / 64)
+ *   bias       NULL or [N];   out [M,N] row-major of x_dtype.   K % 64 == 0, N % 8 == 0, ldx % 8 == 0. */
+SDNQ_API int sdnq_b200_linear_w4a16(const void* x, int x_dtype, int64_t ldx, const void* weight, const sdnq_weight_format* fmt,
+                                    const float* scale, const float* zero_point, int64_t group_size,
+                                    const void* svd_down_rk, const void* svd_up_nr, int svd_rank,
+                                    const void* bias, int bias_dtype, void* out, int64_t M, int64_t N, int64_t K, void* stream);
+
 /* The same Linear as ONE kernel launch: the GEMM kernel row-quantises the activations itself (every CTA takes a share
  * of the rows: bulk copy to shared memory, warp-reduction amax, quantise, codes + scales to the workspace) and its TMA
  * producers pick the quantised strips up through release/acquire strip counters -- linear_int8.py:14-22 + 100-125 /

@@ -12,6 +12,7 @@
 //
 // Operands: A = svd_up [N, r] (r contiguous: K-major), B = svd_down as stored for the dequant path, logical [r, K] with stride
 // (1, r) = physical [K, r] (r contiguous: K-major).  One TMA box row is r*2 bytes = the swizzle span (32 / 64 / 128 B).
+#include <cstdlib>
 #include <mutex>
 
 #include "ptx.cuh"
@@ -22,7 +23,9 @@ namespace sdnq {
 namespace {
 
 constexpr int TM = 128;         // weight rows per tile (TMEM lanes)
-constexpr int TN = 256;         // weight columns per tile (MMA N)
+// TN = weight columns per tile (MMA N): 256, 128 or 64.  The epilogue (dequantise + add + round + store, 4 warps) is the long pole
+// of a tile; the SD-XL weights are small (0.4 - 13 M elements), so the tile is narrowed until every SM has one: 128 x 256 tiles
+// left a 1280 x 1280 weight on 50 SMs (7.7 us, the side stream could not hide it behind the 6 us GEMM of the previous layer).
 constexpr int kThreads = 192;
 constexpr int kStages = 2;
 constexpr int kStoreBufs = 2;
@@ -30,11 +33,16 @@ constexpr int kStoreBlkBytes = 32 * 128;
 constexpr int kStoreBytes = 4 * kStoreBufs * kStoreBlkBytes;
 constexpr int kMaxRank = 64;
 constexpr int kStageA = TM * kMaxRank * 2;     // 16 KB
-constexpr int kStageB = TN * kMaxRank * 2;     // 32 KB
-constexpr int kPkBytes = 8 * 32 * 16;           // one tile row of 4-bit codes per lane: 8 units x 32 lanes x 16 B
-constexpr int kPkTotal = 4 * 2 * kPkBytes;      // 4 epilogue warps x double buffer = 32 KB
-constexpr int kScTotal = 4 * 2 * 2 * 4 * 32 * 4; // 4 warps x 2 buffers x (scale, zp) x 4 blocks x 32 lanes x f32 = 8 KB
-constexpr int kSmemBytes = kStages * (kStageA + kStageB) + kStoreBytes + kPkTotal + kScTotal + 256;
+template <int TN> struct SvdCfg {
+    static constexpr int kStageB = TN * kMaxRank * 2;                // 32 KB at TN = 256
+    static constexpr int kUnits = TN / 32;                            // 16 B units of 4-bit codes per tile row
+    static constexpr int kPkBytes = kUnits * 32 * 16;                 // one tile row of codes per lane: units x 32 lanes x 16 B
+    static constexpr int kPkTotal = 4 * 2 * kPkBytes;                 // 4 epilogue warps x double buffer
+    static constexpr int kBlocks = TN / 64;                           // 64-column store blocks per tile
+    static constexpr int kScFloats = 2 * kBlocks * 32;                // (scale, zp) x blocks x 32 lanes, per warp and buffer
+    static constexpr int kScTotal = 4 * 2 * kScFloats * 4;
+    static constexpr int kSmemBytes = kStages * (kStageA + kStageB) + kStoreBytes + kPkTotal + kScTotal + 256;
+};
 
 struct SvdArgs {
     const uint8_t* weight;
@@ -47,30 +55,12 @@ struct SvdArgs {
     int out_dtype;
 };
 
-__device__ __forceinline__ uint64_t make_smem_desc_kmajor(uint32_t smem_addr, int swizzle_bytes) {
-    // K-major operand, rows of `swizzle_bytes` (32 / 64 / 128), 8-row swizzle atoms: SBO = 8 * swizzle_bytes
-    const uint64_t layout = swizzle_bytes == 128 ? 2 : swizzle_bytes == 64 ? 4 : 6;
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-    d |= static_cast<uint64_t>(1) << 16;
-    d |= static_cast<uint64_t>((8 * swizzle_bytes) >> 4) << 32;
-    d |= static_cast<uint64_t>(1) << 46;
-    d |= layout << 61;
-    return d;
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-template <int BITS, bool kBf16Out>
+template <int BITS, bool kBf16Out, int TN>
 __global__ void __launch_bounds__(kThreads, 1)
 dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_constant__ CUtensorMap tmap_down,
                    const __grid_constant__ CUtensorMap tmap_out, const SvdArgs a) {
+    using SC = SvdCfg<TN>;
+    constexpr int kStageB = SC::kStageB, kPkBytes = SC::kPkBytes, kPkTotal = SC::kPkTotal, kScTotal = SC::kScTotal;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = ptx::smem_u32(smem_raw);
     if ((smem_base & 1023u) != 0) __trap();
@@ -143,10 +133,10 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
                 ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
                 ptx::mbar_wait(full_bar(stage), phase);
                 ptx::tc_fence_after();
-                const uint64_t a_desc = make_smem_desc_kmajor(smem_a + stage * kStageA, row_bytes);
-                const uint64_t b_desc = make_smem_desc_kmajor(smem_b + stage * kStageB, row_bytes);
+                const uint64_t a_desc = ptx::make_smem_desc_kmajor(smem_a + stage * kStageA, row_bytes);
+                const uint64_t b_desc = ptx::make_smem_desc_kmajor(smem_b + stage * kStageB, row_bytes);
                 for (int k = 0; k < a.rank / 16; ++k)                 // 16 bf16 = 32 B per MMA along the contraction
-                    umma_bf16(tmem_base + as * TN, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc, k != 0 ? 1u : 0u);
+                    ptx::umma_f16(tmem_base + as * TN, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc, k != 0 ? 1u : 0u);
                 ptx::umma_commit(empty_bar(stage));
                 ptx::umma_commit(tfull_bar(as));
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -161,7 +151,7 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
         const int q = warp & 3, ew = warp - 2;
         const uint32_t my_o = smem_o + uint32_t(ew) * (kStoreBufs * kStoreBlkBytes);
         const uint32_t pk_base = smem_pk + uint32_t(ew) * (2 * kPkBytes);              // [2 buffers][8 units][32 lanes][16 B]
-        float* sc_base = s_scales + ew * (2 * 2 * 4 * 32);                              // [2 buffers][scale|zp][4 blocks][32 lanes]
+        float* sc_base = s_scales + ew * (2 * SC::kScFloats);                           // [2 buffers][scale|zp][blocks][32 lanes]
         const float bias = 8388608.0f - static_cast<float>(a.f.int_offset);
         const bool blk_scales = a.gpr32 <= 1 || (a.group32 & 63) == 0;
 
@@ -170,7 +160,7 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
             const int n = m0 + q * 32 + lane;
             const bool row_ok = n < a.N;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < SC::kUnits; ++u) {
                 const int k = n0 + 32 * u;
                 const bool ok = row_ok && k < a.K;
                 const uint8_t* src = a.weight + (ok ? ((static_cast<uint32_t>(n) * static_cast<uint32_t>(a.K) + k) >> 1) : 0u);
@@ -180,7 +170,7 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
             asm volatile("cp.async.commit_group;" ::: "memory");
             if (blk_scales) {
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb) {
+                for (int cb = 0; cb < SC::kBlocks; ++cb) {
                     const int k = n0 + cb * 64;
                     float sc = 0.f, z = 0.f;
                     if (row_ok && k < a.K) {
@@ -189,8 +179,8 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
                         sc = a.scale[si];
                         if (a.zp) z = a.zp[si];
                     }
-                    sc_base[(buf * 2 + 0) * 128 + cb * 32 + lane] = sc;
-                    sc_base[(buf * 2 + 1) * 128 + cb * 32 + lane] = z;
+                    sc_base[(buf * 2 + 0) * (SC::kBlocks * 32) + cb * 32 + lane] = sc;
+                    sc_base[(buf * 2 + 1) * (SC::kBlocks * 32) + cb * 32 + lane] = z;
                 }
             }
         };
@@ -215,7 +205,7 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
             ptx::tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * TN;
             const uint32_t pk = pk_base + uint32_t(buf) * kPkBytes + uint32_t(lane) * 16u;
-            const float* scs = sc_base + (buf * 2) * 128 + lane;
+            const float* scs = sc_base + (buf * 2) * (SC::kBlocks * 32) + lane;
 #pragma unroll 1
             for (int cb = 0; cb < TN / 64; ++cb) {
                 const int kb0 = n0 + cb * 64;
@@ -226,7 +216,7 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
                     __syncwarp();
                 }
                 const uint32_t row_addr = sbuf + uint32_t(lane) * 128u;
-                float sc = scs[cb * 32], z = scs[128 + cb * 32];
+                float sc = scs[cb * 32], z = scs[SC::kBlocks * 32 + cb * 32];
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {                              // two 32-column slices per store block
                     const int u = cb * 2 + h;
@@ -323,11 +313,12 @@ int make_tmap16(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, i
     return SDNQ_OK;
 }
 
-template <int BITS, bool kBf16Out>
+template <int BITS, bool kBf16Out, int TN>
 int launch_svd(const SvdArgs& a, const void* up, int64_t up_pitch, const void* down, int64_t down_pitch, void* out, cudaStream_t st) {
+    constexpr int kSmemBytes = SvdCfg<TN>::kSmemBytes;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(dequant_svd_kernel<BITS, kBf16Out>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); });
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(dequant_svd_kernel<BITS, kBf16Out, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); });
     SDNQ_REQUIRE(attr_err == cudaSuccess, SDNQ_ECUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
     CUtensorMap tu, td, to;
     int rc = make_tmap16(&tu, up, a.N, a.rank, up_pitch, a.rank, TM, a.rank * 2);
@@ -338,7 +329,7 @@ int launch_svd(const SvdArgs& a, const void* up, int64_t up_pitch, const void* d
     if (rc != SDNQ_OK) return rc;
     const int tiles = ((a.N + TM - 1) / TM) * ((a.K + TN - 1) / TN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    cudaError_t e = launch_pdl(dequant_svd_kernel<BITS, kBf16Out>, dim3(grid), dim3(kThreads), kSmemBytes, st, tu, td, to, a);
+    cudaError_t e = launch_pdl(dequant_svd_kernel<BITS, kBf16Out, TN>, dim3(grid), dim3(kThreads), kSmemBytes, st, tu, td, to, a);
     if (e != cudaSuccess) return set_error(SDNQ_ECUDA, "launch of dequant_svd_kernel failed: %s", cudaGetErrorString(e));
     return check_launch("dequant_svd_kernel");
 }
@@ -358,7 +349,17 @@ int dequant_svd_tc(const void* weight, const WFormat& f, const float* scale, con
     const bool fmt_ok = f.kind == SDNQ_W_INT && f.bits == 4 && K % 32 == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0;   // 16 B cp.async units
     if (!(rank_ok && layout_ok && dtype_ok && group_ok && align_ok && fmt_ok) || N * K >= (int64_t(1) << 31)) return 1;
     SvdArgs a{reinterpret_cast<const uint8_t*>(weight), scale, zp, static_cast<int>(N), static_cast<int>(K), group32, group_shift, gpr32, row_stride32, f, rank, out_dtype};
-    return launch_svd<4, true>(a, up, up_sn, down, down_sk, out, st);
+    // the widest tile that still gives every SM one (SDNQ_B200_SVD_TN forces 64 / 128 / 256)
+    const int64_t row_tiles = (N + TM - 1) / TM;
+    int tn = 256;
+    while (tn > 64 && row_tiles * ((K + tn - 1) / tn) < num_sms()) tn >>= 1;
+    if (const char* e = getenv("SDNQ_B200_SVD_TN")) {
+        const int v = atoi(e);
+        if (v == 64 || v == 128 || v == 256) tn = v;
+    }
+    if (tn == 256) return launch_svd<4, true, 256>(a, up, up_sn, down, down_sk, out, st);
+    if (tn == 128) return launch_svd<4, true, 128>(a, up, up_sn, down, down_sk, out, st);
+    return launch_svd<4, true, 64>(a, up, up_sn, down, down_sk, out, st);
 }
 
 }  // namespace sdnq

@@ -209,10 +209,32 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// K-major operand tile whose rows are `row_bytes` = 32 / 64 / 128 bytes wide with the swizzle of that span (what TMA writes with
+// CU_TENSOR_MAP_SWIZZLE_32B / _64B / _128B for a box that wide): 8-row atoms, SBO = 8 * row_bytes; layout 6 / 4 / 2.
+__device__ __forceinline__ uint64_t make_smem_desc_kmajor(uint32_t smem_addr, int row_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2 : row_bytes == 64 ? 4 : 6;
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>((8 * row_bytes) >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= layout << 61;
+    return d;
+}
+
+// D[tmem] (+)= A[smem] * B[smem] with 16-bit operands (bf16 or f16, chosen by the instruction descriptor), f32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // Instruction descriptor (dense, no negate, both operands K-major):
 //   [4,6) D format (0 f16, 1 f32, 2 s32)   [7,10) A format   [10,13) B format
 //   [15] A major (0 = K)  [16] B major (0 = K)  [17,23) N >> 3  [24,29) M >> 4
-// kind::i8: format 0 = u8, 1 = s8.   kind::f8f6f4: 0 = e4m3, 1 = e5m2.
+// kind::i8: format 0 = u8, 1 = s8.   kind::f8f6f4: 0 = e4m3, 1 = e5m2.   kind::f16: 0 = f16, 1 = bf16.
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t d_fmt, uint32_t a_fmt, uint32_t b_fmt, uint32_t M, uint32_t N) {
     return (d_fmt << 4) | (a_fmt << 7) | (b_fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }

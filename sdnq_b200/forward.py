@@ -221,10 +221,71 @@ def _small_m_packed_linear(self, x):
     return ops.linear_small_m_packed(x, self.weight, d.weights_dtype, self.scale, self.zero_point, N, K, bias=bias)
 
 
+# ---- K6: the dequant path in one launch ("W4A16") ----------------------------------------------------------------------------
+def w4a16_enabled() -> bool:
+    """SDNQ_B200_W4A16=1 routes 4-bit dequant-path layers through the one-launch W4A16 kernel (K6) instead of dequantise (K3 on
+    the side stream) + library GEMM.  Off by default: measured on B200 (profiles/r02_w4a16.md) the fused kernel re-dequantises
+    the weight tile for every 128-row strip of activations and is bound by the L2 -> SM operand traffic of its 128 x 128 tiles;
+    at the SD-XL / FLUX shapes of BASELINE.json (M >= 77 rows) dequantise-once + GEMM is 1.4 - 2x faster."""
+    return os.environ.get("SDNQ_B200_W4A16", "0") not in ("0", "false", "no", "")
+
+
+def _w4a16_ok(self, input) -> bool:
+    """K6 applies to 32 or more rows of a dequant-path Linear stored as packed int4 / uint4 with row-wise scales or scale groups
+    that are multiples of 32 columns (no codebook, no tensor-wise scale), 16-bit activations, K % 64 == 0, N % 8 == 0 and, if
+    the layer has SVD factors, rank 16 / 32 / 64 in the activation dtype."""
+    d = self.sdnq_dequantizer
+    if (not w4a16_enabled() or d.is_conv or d.use_codebook or d.group_size == -2 or not d.is_integer or d.num_bits != 4
+            or input.dtype not in (torch.bfloat16, torch.float16) or self.weight.ndim > 3 or not input.is_cuda):
+        return False
+    N, K = d.matmul_nk()
+    if K % 64 != 0 or N % 8 != 0 or input.shape[-1] != K:
+        return False
+    per_row = self.scale.numel() // N
+    if per_row < 1 or self.scale.numel() != N * per_row or K % per_row != 0 or (per_row > 1 and (K // per_row) % 32 != 0):
+        return False
+    if self.svd_up is not None:
+        r = min(self.svd_up.shape)
+        if r not in (16, 32, 64) or self.svd_up.dtype != input.dtype or self.svd_down.dtype != input.dtype:
+            return False
+    return True
+
+
+def _svd_operands(self):
+    """The SVD factors as K6 reads them -- svd_down [r,K] and svd_up [N,r], both row-major -- built once per layer from the stored
+    tensors (matmul-off layout: svd_up [N,r], svd_down [r,K] kept K-major, i.e. physically [K,r]; matmul-on layout: both
+    transposed, quantizer.py:164-167) and rebuilt when those are replaced."""
+    up, down = self.svd_up, self.svd_down
+    if up is None:
+        return None, None
+    cached = self.__dict__.get("_sdnq_svd_cache")
+    if cached is not None and cached[0].matches(self, (up, down)):
+        return cached[1], cached[2]
+    if self.sdnq_dequantizer.use_quantized_matmul:
+        up, down = up.t(), down.t()                              # -> [N,r], [r,K]
+    down_rk, up_nr = down.contiguous(), up.contiguous()
+    self.__dict__["_sdnq_svd_cache"] = (_StoredState(self, (self.svd_up, self.svd_down)), down_rk, up_nr)
+    return down_rk, up_nr
+
+
+def _w4a16_linear(self, x):
+    d = self.sdnq_dequantizer
+    N, K = d.matmul_nk()
+    if d.use_hadamard:      # x @ ((Wq + up down) H)^T = (x H) @ (Wq + up down)^T: rotate the activations with K2, not the weight
+        x = ops.act_quant(x, "int8", hadamard_group=d.hadamard_group_size, want_x_rot=True)[4].view(x.shape)
+    down_rk, up_nr = _svd_operands(self)
+    return ops.linear_w4a16(x, self.weight, d.weights_dtype, self.scale, self.zero_point, N, K, bias=self.bias,
+                            svd_down_rk=down_rk, svd_up_nr=up_nr)
+
+
 @torch.no_grad()
 def quantized_linear_forward(self, input: torch.Tensor) -> torch.Tensor:
-    if input.numel() // max(input.shape[-1], 1) < SMALL_M and _small_m_packed_ok(self, input):
-        return _small_m_packed_linear(self, input)
+    rows = input.numel() // max(input.shape[-1], 1)
+    if rows < SMALL_M:
+        if _small_m_packed_ok(self, input):
+            return _small_m_packed_linear(self, input)
+    elif _w4a16_ok(self, input):
+        return _w4a16_linear(self, input)
     return _dequant_linear(self, input, skip_quantized_matmul=False)
 
 
@@ -240,12 +301,15 @@ def _small_m_gemv_ok(self, input) -> bool:
 # ---- K2 reuse: sibling projections quantise the same activations once ------------------------------------------------------
 # to_q / to_k / to_v of an attention block (FLUX single blocks: proj_mlp as well) and the cross-attention to_k / to_v of *every*
 # block (all fed the same encoder_hidden_states) call their forward with the very same input tensor, and the reference rotates
-# and row-quantises it again for each of them (linear_int8.py:55-63).  Here the result of K2 is kept -- one entry per device
-# and stream -- and reused while the next W8A8 forward on that stream presents the same tensor: same storage pointer, shape,
+# and row-quantises it again for each of them (linear_int8.py:55-63).  Here the result of K2 is kept -- per device and stream,
+# the newest entry plus a few small older ones -- and reused when a W8A8 forward on that stream presents the same tensor: same storage pointer, shape,
 # strides, dtype and in-place version, with a strong reference to the cached input held so that its memory cannot be recycled
 # under a new tensor.  The key carries the stream's CUDA-graph capture id: nothing computed eagerly is baked into a graph and
 # nothing from one capture is used in another.  SDNQ_B200_ACT_CACHE=0 turns it off.
 _ACT_CACHE: dict = {}
+_ACT_CACHE_ENTRIES = 4                   # per (device, stream): the newest entry plus a few small ones
+_ACT_CACHE_SMALL_BYTES = 8 << 20         # older entries are kept only while they pin less than this in total (e.g. the text
+                                         # encoder states every cross-attention block projects: 77 x 2048 for SD-XL)
 
 
 def _act_cache_on() -> bool:
@@ -253,17 +317,28 @@ def _act_cache_on() -> bool:
 
 
 def quantized_activations(x2: torch.Tensor, mm: str, hg: int, want_rowsum: bool, want_x_rot: bool):
-    """K2 on x2 [M,K] -> (xq, sx, zx, rowsum, x_rot), shared between consecutive forwards that present the same tensor."""
+    """K2 on x2 [M,K] -> (xq, sx, zx, rowsum, x_rot), shared between forwards that present the same tensor."""
     if not _act_cache_on() or not x2.is_cuda:       # (a CPU tensor raises inside ops: there is no CPU path)
         return ops.act_quant(x2, mm, hadamard_group=hg, want_rowsum=want_rowsum, want_x_rot=want_x_rot)
     stream = torch.cuda.current_stream(x2.device).cuda_stream
     slot = (x2.device.index, stream)
     key = (x2.data_ptr(), _version(x2), tuple(x2.shape), tuple(x2.stride()), x2.dtype, mm, int(hg), ops.capture_id(stream))
-    hit = _ACT_CACHE.get(slot)
-    if hit is not None and hit[0] == key and (not want_rowsum or hit[2][3] is not None) and (not want_x_rot or hit[2][4] is not None):
-        return hit[2]
+    entries = _ACT_CACHE.setdefault(slot, [])
+    for i, (k, _, out) in enumerate(entries):
+        if k == key and (not want_rowsum or out[3] is not None) and (not want_x_rot or out[4] is not None):
+            if i:
+                entries.insert(0, entries.pop(i))
+            return out
     out = ops.act_quant(x2, mm, hadamard_group=hg, want_rowsum=want_rowsum, want_x_rot=want_x_rot)
-    _ACT_CACHE[slot] = (key, x2, out)          # x2 is kept alive until the next miss on this stream replaces the entry
+    # the newest entry always stays; older ones only while they are small (x2 is kept alive while its entry is, so that its memory
+    # cannot be recycled under a new tensor) and belong to the same graph capture (or to none)
+    kept, held = [(key, x2, out)], 0
+    for e in entries:
+        nbytes = 2 * e[1].numel() * e[1].element_size()
+        if len(kept) < _ACT_CACHE_ENTRIES and e[0][-1] == key[-1] and held + nbytes <= _ACT_CACHE_SMALL_BYTES:
+            kept.append(e)
+            held += nbytes
+    entries[:] = kept
     return out
 
 

@@ -379,6 +379,39 @@ def linear_small_m_packed(x: torch.Tensor, weight: torch.Tensor, weights_dtype: 
     return out.view(*x.shape[:-1], N)
 
 
+def linear_w4a16(x: torch.Tensor, weight: torch.Tensor, weights_dtype: str, scale: torch.Tensor, zero_point, N: int, K: int,
+                 bias: torch.Tensor | None = None, svd_down_rk: torch.Tensor | None = None, svd_up_nr: torch.Tensor | None = None) -> torch.Tensor:
+    """K6: the dequant-path Linear in one launch.  x [..., K] bf16 / f16; `weight` the stored packed int4 / uint4 tensor of the
+    [N,K] weight; scale / zero_point with N * (K / group) elements; svd factors already as [r,K] / [N,r] contiguous in x.dtype."""
+    _require_cuda(x, weight, scale)
+    w = weight.contiguous()
+    scale = scale.to(torch.float32).contiguous()
+    if zero_point is not None:
+        zero_point = zero_point.to(torch.float32).contiguous()
+    per_row = scale.numel() // N
+    if per_row < 1 or scale.numel() != N * per_row or K % per_row != 0:
+        raise _lib.SDNQKernelError(f"linear_w4a16: {scale.numel()} scales do not tile a [{N},{K}] weight")
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1 or x2.stride(0) % 8 != 0 or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    out = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    rank = 0
+    if svd_up_nr is not None:
+        rank = svd_up_nr.shape[1]
+        if (svd_up_nr.dtype != x.dtype or svd_down_rk.dtype != x.dtype or not svd_up_nr.is_contiguous() or not svd_down_rk.is_contiguous()
+                or tuple(svd_up_nr.shape) != (N, rank) or tuple(svd_down_rk.shape) != (rank, K)):
+            raise _lib.SDNQKernelError("linear_w4a16: svd factors must be contiguous [N,r] / [r,K] tensors of the activation dtype")
+    if bias is not None:
+        bias = bias.contiguous()
+    fmt = weight_format(weights_dtype, w)
+    with torch.cuda.device(x.device):
+        check(_lib.load().sdnq_b200_linear_w4a16(_ptr(x2), dtype_code(x2.dtype), x2.stride(0), _ptr(w), fmt, _ptr(scale), _ptr(zero_point), K // per_row,
+                                                 _ptr(svd_down_rk), _ptr(svd_up_nr), rank, _ptr(bias), dtype_code(bias.dtype) if bias is not None else SDNQ_F32,
+                                                 _ptr(out), M, N, K, _stream(x)))
+    return out.view(*x.shape[:-1], N)
+
+
 _WORKSPACES: dict = {}
 _RETIRED_WORKSPACES: list = []
 
