@@ -271,6 +271,27 @@ SDNQ_API int sdnq_b200_linear_w4a16(const void* x, int x_dtype, int64_t ldx, con
                                     const void* svd_down_rk, const void* svd_up_nr, int svd_rank,
                                     const void* bias, int bias_dtype, void* out, int64_t M, int64_t N, int64_t K, void* stream);
 
+/* ---- K7 + K1: the SVD branch of the W8A8 forwards (get_int8_matmul_inputs / get_uint8_matmul_inputs / get_fp8_matmul_inputs with
+ *      svd_up / svd_down, layers/linear/linear_int8.py:57-62, linear_uint8.py:58-63, linear_fp8.py:47-52, conv_int8.py:56-61):
+ *          bias2d = bias + torch.mm(torch.mm(x_rot, svd_down), svd_up)          (reference: two library GEMMs + a dense [M,N] bias)
+ *      Here:  low = sdnq_b200_svd_low(x_rot, svd_down)  [M, r], rounded to the activation dtype exactly where torch.mm rounds it, then
+ *      sdnq_b200_scaled_mm_svd accumulates low @ svd_up as a rank-r tcgen05.mma (kind::f16, f32 accumulator in its own TMEM region)
+ *      per output tile and its epilogue adds it to the bias in f32 -- no [M,N] bias tensor, no library GEMM.
+ *   x            [M,K] bf16 / f16 (the rotated, un-quantised activations: x_rot of act_quant, or x itself without Hadamard), row stride ldx
+ *   svd_down_rk  [svd_rank, K] row-major of x_dtype (the stored [K, r] factor transposed once);  svd_rank % 8 == 0, <= 64;  K % 16 == 0
+ *   low          [M, svd_rank] row-major of x_dtype (written) */
+SDNQ_API int sdnq_b200_svd_low(const void* x, int x_dtype, int64_t ldx, const void* svd_down_rk, int svd_rank, void* low,
+                               int64_t M, int64_t K, void* stream);
+
+/*   a, b, sx, sw, bias, rowsum, zp, colsum, zx, out, M, N, K   as for sdnq_b200_scaled_mm (bias_ld != 0: an [M,N] bias on top)
+ *   b_fmt        NULL: b is the physical [N,K] 1-byte operand;  else int4 / uint4: b is the stored packed weight (as sdnq_b200_scaled_mm_packed)
+ *   svd_low      [M, svd_rank] from sdnq_b200_svd_low;  svd_up_nr [N, svd_rank] row-major;  both svd_dtype (SDNQ_BF16 / SDNQ_F16)
+ *   svd_rank     16, 32 or 64 (pad the factors with zero columns for other ranks);  out_dtype SDNQ_BF16 / SDNQ_F16 */
+SDNQ_API int sdnq_b200_scaled_mm_svd(const void* a, const void* b, int ab_dtype, const sdnq_weight_format* b_fmt, const float* sx, const float* sw,
+                                     const void* bias, int bias_dtype, int64_t bias_ld, const int32_t* rowsum, const float* zp,
+                                     const int32_t* colsum, const float* zx, const void* svd_low, const void* svd_up_nr, int svd_rank,
+                                     int svd_dtype, void* out, int out_dtype, int64_t M, int64_t N, int64_t K, void* stream);
+
 /* The same Linear as ONE kernel launch: the GEMM kernel row-quantises the activations itself (every CTA takes a share
  * of the rows: bulk copy to shared memory, warp-reduction amax, quantise, codes + scales to the workspace) and its TMA
  * producers pick the quantised strips up through release/acquire strip counters -- linear_int8.py:14-22 + 100-125 /

@@ -32,16 +32,26 @@ constexpr int kStoreBufs = 2;
 constexpr int kStoreBlkBytes = 32 * 128;
 constexpr int kStoreBytes = 4 * kStoreBufs * kStoreBlkBytes;
 constexpr int kMaxRank = 64;
-constexpr int kStageA = TM * kMaxRank * 2;     // 16 KB
+// operand stages are sized by the layer's rank at launch: A = svd_up tile [128 x r], B = svd_down tile [TN x r] (r * 2 bytes per row)
+__host__ __device__ constexpr int stage_a_bytes(int rank) { return TM * rank * 2; }
 template <int TN> struct SvdCfg {
-    static constexpr int kStageB = TN * kMaxRank * 2;                // 32 KB at TN = 256
+    __host__ __device__ static constexpr int stage_b_bytes(int rank) { return TN * rank * 2; }
     static constexpr int kUnits = TN / 32;                            // 16 B units of 4-bit codes per tile row
     static constexpr int kPkBytes = kUnits * 32 * 16;                 // one tile row of codes per lane: units x 32 lanes x 16 B
     static constexpr int kPkTotal = 4 * 2 * kPkBytes;                 // 4 epilogue warps x double buffer
     static constexpr int kBlocks = TN / 64;                           // 64-column store blocks per tile
     static constexpr int kScFloats = 2 * kBlocks * 32;                // (scale, zp) x blocks x 32 lanes, per warp and buffer
     static constexpr int kScTotal = 4 * 2 * kScFloats * 4;
-    static constexpr int kSmemBytes = kStages * (kStageA + kStageB) + kStoreBytes + kPkTotal + kScTotal + 256;
+    static constexpr int kFixedBytes = kStoreBytes + kPkTotal + kScTotal + 256;
+    __host__ __device__ static constexpr int smem_bytes(int rank) { return kStages * (stage_a_bytes(rank) + stage_b_bytes(rank)) + kFixedBytes; }
+    // Two accumulator stages of TN columns: allocating exactly that (not all 512 columns) and keeping the CTA small lets several
+    // CTAs share an SM, which is what hides the per-tile latency chain (TMA -> MMA -> TMEM -> epilogue)
+    static constexpr int kTmemCols = 2 * TN;
+    static constexpr int kCtasPerSm = 512 / kTmemCols < 3 ? 512 / kTmemCols : 3;      // (launch bound: registers for up to 3 CTAs)
+    static int ctas_per_sm(int rank) {
+        const int by_smem = (227 * 1024) / (smem_bytes(rank) + 1024);
+        return by_smem < 1 ? 1 : by_smem < kCtasPerSm ? by_smem : kCtasPerSm;
+    }
 };
 
 struct SvdArgs {
@@ -56,11 +66,12 @@ struct SvdArgs {
 };
 
 template <int BITS, bool kBf16Out, int TN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, SvdCfg<TN>::kCtasPerSm)
 dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_constant__ CUtensorMap tmap_down,
                    const __grid_constant__ CUtensorMap tmap_out, const SvdArgs a) {
     using SC = SvdCfg<TN>;
-    constexpr int kStageB = SC::kStageB, kPkBytes = SC::kPkBytes, kPkTotal = SC::kPkTotal, kScTotal = SC::kScTotal;
+    constexpr int kPkBytes = SC::kPkBytes, kPkTotal = SC::kPkTotal, kScTotal = SC::kScTotal;
+    const int kStageA = stage_a_bytes(a.rank), kStageB = SC::stage_b_bytes(a.rank);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = ptx::smem_u32(smem_raw);
     if ((smem_base & 1023u) != 0) __trap();
@@ -98,7 +109,7 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_alloc(tmem_slot, SC::kTmemCols);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
@@ -277,7 +288,7 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
     if (warp == 1) {
         __syncwarp();
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, 512);
+        ptx::tmem_dealloc(tmem_base, SC::kTmemCols);
     }
 }
 
@@ -315,10 +326,11 @@ int make_tmap16(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, i
 
 template <int BITS, bool kBf16Out, int TN>
 int launch_svd(const SvdArgs& a, const void* up, int64_t up_pitch, const void* down, int64_t down_pitch, void* out, cudaStream_t st) {
-    constexpr int kSmemBytes = SvdCfg<TN>::kSmemBytes;
+    constexpr int kSmemMax = SvdCfg<TN>::smem_bytes(kMaxRank);
+    const int kSmemBytes = SvdCfg<TN>::smem_bytes(a.rank);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(dequant_svd_kernel<BITS, kBf16Out, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); });
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(dequant_svd_kernel<BITS, kBf16Out, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax); });
     SDNQ_REQUIRE(attr_err == cudaSuccess, SDNQ_ECUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
     CUtensorMap tu, td, to;
     int rc = make_tmap16(&tu, up, a.N, a.rank, up_pitch, a.rank, TM, a.rank * 2);
@@ -328,7 +340,8 @@ int launch_svd(const SvdArgs& a, const void* up, int64_t up_pitch, const void* d
     rc = make_tmap16(&to, out, a.N, a.K, a.K, 64, 32, 128);
     if (rc != SDNQ_OK) return rc;
     const int tiles = ((a.N + TM - 1) / TM) * ((a.K + TN - 1) / TN);
-    const int grid = tiles < num_sms() ? tiles : num_sms();
+    const int slots = num_sms() * SvdCfg<TN>::ctas_per_sm(a.rank);
+    const int grid = tiles < slots ? tiles : slots;
     cudaError_t e = launch_pdl(dequant_svd_kernel<BITS, kBf16Out, TN>, dim3(grid), dim3(kThreads), kSmemBytes, st, tu, td, to, a);
     if (e != cudaSuccess) return set_error(SDNQ_ECUDA, "launch of dequant_svd_kernel failed: %s", cudaGetErrorString(e));
     return check_launch("dequant_svd_kernel");
@@ -349,10 +362,9 @@ int dequant_svd_tc(const void* weight, const WFormat& f, const float* scale, con
     const bool fmt_ok = f.kind == SDNQ_W_INT && f.bits == 4 && K % 32 == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0;   // 16 B cp.async units
     if (!(rank_ok && layout_ok && dtype_ok && group_ok && align_ok && fmt_ok) || N * K >= (int64_t(1) << 31)) return 1;
     SvdArgs a{reinterpret_cast<const uint8_t*>(weight), scale, zp, static_cast<int>(N), static_cast<int>(K), group32, group_shift, gpr32, row_stride32, f, rank, out_dtype};
-    // the widest tile that still gives every SM one (SDNQ_B200_SVD_TN forces 64 / 128 / 256)
-    const int64_t row_tiles = (N + TM - 1) / TM;
-    int tn = 256;
-    while (tn > 64 && row_tiles * ((K + tn - 1) / tn) < num_sms()) tn >>= 1;
+    // Narrow tiles (several CTAs per SM) for the small weights of a UNet, wider ones as the weight grows: measured on B200 over
+    // the SD-XL int4 + SVD step: TN = 64 9.62 ms, 128 9.86 ms, 256 10.7 ms (SDNQ_B200_SVD_TN forces 64 / 128 / 256)
+    int tn = N * K <= (int64_t(32) << 20) ? 64 : N * K <= (int64_t(128) << 20) ? 128 : 256;
     if (const char* e = getenv("SDNQ_B200_SVD_TN")) {
         const int v = atoi(e);
         if (v == 64 || v == 128 || v == 256) tn = v;

@@ -54,6 +54,11 @@ struct GemmParams {
     int raw;   // plain mm: store the accumulator (s32 / f32) untouched
     uint32_t w_sub;   // packed 4-bit weights: per-byte offset removed while expanding (0x08080808 for int4, 0 for uint4)
     uint32_t b_fmt;   // fp8 GEMM: format of the B operand in the instruction descriptor (0 = e4m3, 1 = e5m2); A is always e4m3
+    // SVD branch (kSvd): low [M, svd_rank] = cast(x_rot @ svd_down) from svd_low.cu and svd_up as [N, svd_rank], both row-major 16-bit
+    const void* svd_low;
+    const void* svd_up;
+    int svd_rank;     // 16, 32 or 64
+    uint32_t svd_fmt; // kind::f16 operand format: 1 = bf16, 0 = f16
     // fused activation quantiser (XM != 0): un-quantised activations in, xq / sx written by this kernel
     const void* fx;
     int64_t fldx;
@@ -67,7 +72,9 @@ constexpr int kSyncStrips = 512;
 // TMA stages the packed tile, four unpack warps expand it into the ring -- "unpack in the GEMM prologue").
 // CG = CTAs per MMA (tcgen05 cta_group): 1, or 2 = a CTA pair computes a 256 x BN tile, each CTA staging its own 128 rows of A
 // and only half of the B tile (BN/2 weight rows) -- per SM that is 16 + BN/2 * 128 B per k-block instead of 16 + BN * 128 B.
-template <int BN, int WB = 8, int CG = 1>
+constexpr int kSvdTileBytes = 128 * 64 * 2;          // one [128 x rank <= 64] 16-bit operand tile
+
+template <int BN, int WB = 8, int CG = 1, bool kSvd = false>
 struct Cfg {
     static constexpr int kStageA = BM * BK;
     static constexpr int kStageB = BN / CG * BK;
@@ -76,14 +83,17 @@ struct Cfg {
     static constexpr int kPStages = WB < 8 ? 3 : 0;                     // packed staging ring
     static constexpr int kStageP = WB < 8 ? BN * (BK * WB / 8) : 0;
     static constexpr int kThreads = WB < 8 ? 320 : 192;
-    static constexpr int kFixed = kStoreBytes + kVecBytes + kPStages * kStageP + 256 /*barriers: 8*(2*stages+4+2*3)+4+16 <= 228 B*/;
+    static constexpr int kSvdBytes = kSvd ? 2 * kSvdTileBytes : 0;      // low tile [128 x r] + svd_up tile [BN x r], BN = 128
+    static constexpr int kFixed = kStoreBytes + kVecBytes + kPStages * kStageP + kSvdBytes + 256 /*barriers: 8*(2*stages+4+2*3+2)+4+16 <= 244 B*/;
     static constexpr int kStagesRaw = (kSmemLimit - kFixed) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-    static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int kAccCols = (kSvd ? 4 : 2) * BN;               // two accumulator stages (+ two f32 stages of the rank-r SVD product)
+    static constexpr int kTmemCols = (kAccCols <= 32) ? 32 : (kAccCols <= 64) ? 64 : (kAccCols <= 128) ? 128 : (kAccCols <= 256) ? 256 : 512;
     static constexpr int kSmemBytes = kStages * kStageBytes + kFixed;
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
     static_assert(kStages >= 3, "pipeline too shallow");
     static_assert(CG == 1 || (CG == 2 && WB == 8 && BN % 32 == 0), "CTA pairs: unpacked operands, BN/2 a multiple of 16");
+    static_assert(!kSvd || (BN == 128 && CG == 1), "the SVD accumulate runs with 128-wide single-CTA tiles (4 x 128 TMEM columns)");
 };
 
 // 8 consecutive values of a f32 / bf16 / f16 vector as floats (16 B aligned for 2-byte types, 32 B for f32)
@@ -104,11 +114,16 @@ __device__ __forceinline__ void load8_any(const void* p, int64_t i, int dtype, f
 // Linear instead of two: the dependent-launch gap (~2.5 us, as long as the GEMM itself at SD-XL sizes) disappears,
 // and the weight prefetch overlaps the quantisation.  All CTAs are co-resident (grid <= SMs, 1 CTA/SM), which the
 // cross-CTA wait relies on.
-template <int BN, bool kInt8, int OUT, bool kSimple, int WB, int XM, int CG>
-__global__ void __launch_bounds__((Cfg<BN, WB, CG>::kThreads), 1)
+// kSvd: the SVD branch of the W8A8 forwards (linear_int8.py:57-62).  The reference adds bias2d = bias + (x @ svd_down) @ svd_up as
+// a dense [M,N] bias; here the rank-r product low[128 x r] . svd_up[BN x r]^T of the tile is one more tcgen05.mma (kind::f16) after
+// the k-loop into its own f32 TMEM region, and the epilogue adds it to the bias in f32 before the fma.
+template <int BN, bool kInt8, int OUT, bool kSimple, int WB, int XM, int CG, bool kSvd = false>
+__global__ void __launch_bounds__((Cfg<BN, WB, CG, kSvd>::kThreads), 1)
 gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_o, const GemmParams p) {
-    using C = Cfg<BN, WB, CG>;
+                 const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_l,
+                 const __grid_constant__ CUtensorMap tmap_u, const GemmParams p) {
+    using C = Cfg<BN, WB, CG, kSvd>;
+    static_assert(!kSvd || (XM == 0 && !kSimple), "SVD tiles use the generic epilogue and the stand-alone activation quantiser");
     static_assert(CG == 1 || XM == 0, "the fused quantiser runs with single-CTA MMAs");
     constexpr bool kPair = CG == 2;
     // CTA pair: rank 0 (the leader) issues the MMAs; tiles are numbered per pair (256 rows x BN columns)
@@ -126,7 +141,9 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     float* s_sw = reinterpret_cast<float*>(smem_raw + C::kStages * C::kStageBytes + kStoreBytes);
     float* s_bias = s_sw + BN;
     const uint32_t smem_p = smem_o + kStoreBytes + C::kVecBytes;       // packed B staging ring (kPacked only)
-    const uint32_t bar_base = smem_p + C::kPStages * C::kStageP;
+    const uint32_t smem_l = smem_p + C::kPStages * C::kStageP;         // kSvd: low tile, then the svd_up tile (1 KB aligned: kVecBytes = 1 KB at BN = 128)
+    const uint32_t smem_u = smem_l + kSvdTileBytes;
+    const uint32_t bar_base = smem_l + C::kSvdBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + s); };
@@ -135,6 +152,8 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     auto pempty_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 4 + C::kPStages + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4 + 2 * C::kPStages);
     const uint32_t xstage_bar = tmem_slot + 8u;                        // fused quantiser: bulk copies of x landed
+    const uint32_t svdfull_bar = tmem_slot + 16u;                      // kSvd: low / svd_up tiles landed
+    const uint32_t svdfree_bar = tmem_slot + 24u;                      // kSvd: the tile's rank-r MMAs retired
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -168,6 +187,12 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ptx::mbar_init(pempty_bar(s), 4);
         }
         if constexpr (XM != 0) ptx::mbar_init(xstage_bar, 1);
+        if constexpr (kSvd) {
+            ptx::prefetch_tmap(&tmap_l);
+            ptx::prefetch_tmap(&tmap_u);
+            ptx::mbar_init(svdfull_bar, 1);
+            ptx::mbar_init(svdfree_bar, 1);
+        }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -275,15 +300,26 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     };
 
+    // kSvd: the producer fetches the tile's low / svd_up operand tiles once the previous tile's rank-r MMAs have read the old ones
+    auto load_svd_tiles = [&](int it, int m0, int n0) {
+        if constexpr (kSvd) {
+            if (it > 0) ptx::mbar_wait(svdfree_bar, (it - 1) & 1u);
+            ptx::mbar_arrive_expect_tx(svdfull_bar, uint32_t(BM + BN) * uint32_t(p.svd_rank) * 2u);
+            ptx::tma_load_2d(smem_l, &tmap_l, svdfull_bar, 0, m0);
+            ptx::tma_load_2d(smem_u, &tmap_u, svdfull_bar, 0, n0);
+        }
+    };
+
     if (warp == 0) {
         // ======================================================== TMA producer
         if (lane == 0 && kPacked) {
             // packed weights: A tiles go to the ring, packed B tiles to the staging ring (the unpack warps fill the ring's B half)
             pdl_wait();
-            int stage = 0, ps = 0;
+            int stage = 0, ps = 0, pit = 0;
             uint32_t phase = 0, pphase = 0;
-            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++pit) {
                 const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+                load_svd_tiles(pit, m0, n0);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
                     ptx::mbar_arrive_expect_tx(full_bar(stage), C::kStageA);
@@ -313,11 +349,12 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 acquire_strip(tile0 / num_n);
                 for (int s = 0; s < npre; ++s) tma_load(smem_a + s * C::kStageA, &tmap_a, load_bar(s), s * BK, m0);
             }
-            int stage = 0;
+            int stage = 0, pit = 0;
             uint32_t phase = 0;
-            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++pit) {
                 const int m0 = tile_m0(tile), nb0 = tile_nb0(tile);
                 if (tile != tile0) acquire_strip(tile / num_n);
+                load_svd_tiles(pit, m0, (tile % num_n) * BN);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     if (tile == tile0 && kb < npre) {             // already in flight (prefetched above)
                         if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
@@ -365,6 +402,16 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                     commit(empty_bar(stage));                     // smem slot free (in both CTAs of a pair) once these MMAs retire
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                }
+                if constexpr (kSvd) {
+                    ptx::mbar_wait(svdfull_bar, it & 1u);
+                    ptx::tc_fence_after();
+                    const uint32_t idesc_svd = ptx::make_idesc(1, p.svd_fmt, p.svd_fmt, BM, BN);
+                    const uint64_t l_desc = ptx::make_smem_desc_kmajor(smem_l, p.svd_rank * 2);
+                    const uint64_t u_desc = ptx::make_smem_desc_kmajor(smem_u, p.svd_rank * 2);
+                    for (int k = 0; k < p.svd_rank / 16; ++k)
+                        ptx::umma_f16(tmem_base + 2 * BN + as * BN, l_desc + uint64_t(2 * k), u_desc + uint64_t(2 * k), idesc_svd, k != 0 ? 1u : 0u);
+                    commit(svdfree_bar);
                 }
                 commit(tfull_bar(as));                            // accumulator complete
             }
@@ -526,6 +573,19 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                     for (int j = 0; j < 8; ++j) b[j] = __fmul_rn(__fmul_rn(static_cast<float>(p.colsum[nc + j]), swv[j]), zxm);
                                     has_b = true;
                                 }
+                                if constexpr (kSvd) {                 // + (low @ svd_up^T)[m, n]: the rank-r MMA's f32 accumulator
+                                    uint32_t sv[8];
+                                    ptx::tmem_ld8(t_row + 2 * BN + cb * CPB + 8 * c8, sv);
+                                    ptx::tmem_ld_wait();
+                                    if (has_b) {
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) b[j] = __fadd_rn(b[j], __uint_as_float(sv[j]));
+                                    } else {
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) b[j] = __uint_as_float(sv[j]);
+                                        has_b = true;
+                                    }
+                                }
                                 if (p.bias && (p.bias_ld == 0 || m_ok)) {
                                     float bv[8];
                                     if (vec_bias) {
@@ -646,10 +706,25 @@ int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int
     return SDNQ_OK;
 }
 
-template <int BN, bool kInt8, int OUT, bool kSimple, int WB = 8, int XM = 0, int CG = 1>
+// [rows, rank] 16-bit matrix (row pitch = rank) -> tensor map with a box of {rank, box_rows} and the swizzle of a rank*2-byte row
+int make_tmap_svd(CUtensorMap* map, const void* ptr, int64_t rows, int rank, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    SDNQ_REQUIRE(enc != nullptr, SDNQ_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(rank), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(rank) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(rank), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = rank == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : rank == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SDNQ_REQUIRE(r == CUDA_SUCCESS, SDNQ_ECUDA, "cuTensorMapEncodeTiled (svd operand) failed with CUresult %d (rows=%lld rank=%d)", static_cast<int>(r), (long long)rows, rank);
+    return SDNQ_OK;
+}
+
+template <int BN, bool kInt8, int OUT, bool kSimple, int WB = 8, int XM = 0, int CG = 1, bool kSvd = false>
 int launch_gemm(const void* a, const void* b, const GemmParams& p, cudaStream_t st) {
-    using C = Cfg<BN, WB, CG>;
-    auto kernel = gemm_w8a8_kernel<BN, kInt8, OUT, kSimple, WB, XM, CG>;
+    using C = Cfg<BN, WB, CG, kSvd>;
+    auto kernel = gemm_w8a8_kernel<BN, kInt8, OUT, kSimple, WB, XM, CG, kSvd>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes); });
@@ -662,6 +737,13 @@ int launch_gemm(const void* a, const void* b, const GemmParams& p, cudaStream_t 
     if (rc != SDNQ_OK) return rc;
     rc = make_tmap(&to, p.out, p.M, p.N, (OUT == OUT_BF16 || OUT == OUT_F16) ? 2 : 4, 32);
     if (rc != SDNQ_OK) return rc;
+    CUtensorMap tl = ta, tu = ta;
+    if (kSvd) {
+        rc = make_tmap_svd(&tl, p.svd_low, p.M, p.svd_rank, BM);
+        if (rc != SDNQ_OK) return rc;
+        rc = make_tmap_svd(&tu, p.svd_up, p.N, p.svd_rank, BN);
+        if (rc != SDNQ_OK) return rc;
+    }
     const int tiles = ((p.M + BM * CG - 1) / (BM * CG)) * ((p.N + BN - 1) / BN);      // CG == 2: 256-row tiles, one per CTA pair
     // fused quantiser: always one CTA per SM (CTAs without a tile still quantise their share of the rows)
     const int slots = num_sms() / CG;
@@ -683,13 +765,21 @@ int launch_gemm(const void* a, const void* b, const GemmParams& p, cudaStream_t 
         attr[1].val.clusterDim.z = 1;
         cfg.numAttrs = 2;
     }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ta, tb, to, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ta, tb, to, tl, tu, p);
     if (e != cudaSuccess) return set_error(SDNQ_ECUDA, "launch of gemm_w8a8_kernel failed: %s", cudaGetErrorString(e));
     return check_launch("gemm_w8a8_kernel");
 }
 
+// SVD layers: 128-wide single-CTA tiles, generic epilogue, 16-bit outputs (the model dtype of the SVD factors)
+template <bool kInt8, int WB>
+int launch_gemm_svd(const void* a, const void* b, const GemmParams& p, cudaStream_t st) {
+    if (p.out_dtype == SDNQ_BF16) return launch_gemm<128, kInt8, OUT_BF16, false, WB, 0, 1, true>(a, b, p, st);
+    return launch_gemm<128, kInt8, OUT_F16, false, WB, 0, 1, true>(a, b, p, st);
+}
+
 // packed int4 / uint4 B operand (unpack warps); int8 activations, 128-wide tiles
 int launch_gemm_packed4(const void* a, const void* b, const GemmParams& p, cudaStream_t st) {
+    if (p.svd_rank != 0) return launch_gemm_svd<true, 4>(a, b, p, st);
     const bool simple = !p.zp && !p.colsum && (p.bias == nullptr || p.bias_ld == 0);
     switch (p.out_dtype) {
         case SDNQ_BF16: return simple ? launch_gemm<128, true, OUT_BF16, true, 4>(a, b, p, st) : launch_gemm<128, true, OUT_BF16, false, 4>(a, b, p, st);
@@ -791,6 +881,12 @@ int scaled_mm_impl(const void* a, const void* b, int ab_dtype, GemmParams p, cud
         SDNQ_REQUIRE(!p.zp || p.rowsum || p.colsum, SDNQ_EINVAL, "zp given without rowsum");
         SDNQ_REQUIRE(!p.colsum || p.zx, SDNQ_EINVAL, "colsum given without zx");
     }
+    if (p.svd_rank != 0) {
+        SDNQ_REQUIRE(!p.raw && (p.out_dtype == SDNQ_BF16 || p.out_dtype == SDNQ_F16), SDNQ_EUNSUPPORTED, "the SVD accumulate needs a bf16 / f16 output");
+        SDNQ_REQUIRE(p.svd_rank == 16 || p.svd_rank == 32 || p.svd_rank == 64, SDNQ_EUNSUPPORTED, "svd rank must be 16, 32 or 64 (got %d)", p.svd_rank);
+        SDNQ_REQUIRE(p.svd_low && p.svd_up && ((reinterpret_cast<uintptr_t>(p.svd_low) | reinterpret_cast<uintptr_t>(p.svd_up)) & 15) == 0, SDNQ_EINVAL,
+                     "svd operands must be non-NULL and 16-byte aligned");
+    }
     if (p.M == 0) return SDNQ_OK;
     const bool i8 = ab_dtype == SDNQ_I8;
     if (wbits != 8) {
@@ -798,6 +894,7 @@ int scaled_mm_impl(const void* a, const void* b, int ab_dtype, GemmParams p, cud
         SDNQ_REQUIRE(p.K % 32 == 0, SDNQ_EUNSUPPORTED, "packed 4-bit B needs K %% 32 == 0 (16-byte row pitch), K=%d", p.K);
         return launch_gemm_packed4(a, b, p, st);
     }
+    if (p.svd_rank != 0) return i8 ? launch_gemm_svd<true, 8>(a, b, p, st) : launch_gemm_svd<false, 8>(a, b, p, st);
     if (const int pair_bn = pick_pair(p); pair_bn != 0) {
         if (pair_bn == 256) return i8 ? launch_gemm_pair<256, true>(a, b, p, st) : launch_gemm_pair<256, false>(a, b, p, st);
         return i8 ? launch_gemm_pair<128, true>(a, b, p, st) : launch_gemm_pair<128, false>(a, b, p, st);
@@ -827,7 +924,7 @@ int linear_fused_impl(const void* x, int x_dtype, int64_t ldx, const void* wq, i
     const int bn = pick_bn(int(M), int(N));
     const int64_t stage_bytes = bn == 256 ? int64_t(Cfg<256>::kStages) * Cfg<256>::kStageA : int64_t(Cfg<128>::kStages) * Cfg<128>::kStageA;
     if (K * 2 > stage_bytes) return 1;
-    GemmParams p{sx, sw, bias, bias_dtype, 0, nullptr, nullptr, nullptr, nullptr, out, out_dtype, int(M), int(N), int(K), 0, 0u, ab_dtype == SDNQ_F8E5M2 ? 1u : 0u, x, ldx, xq, sx, sync};
+    GemmParams p{sx, sw, bias, bias_dtype, 0, nullptr, nullptr, nullptr, nullptr, out, out_dtype, int(M), int(N), int(K), 0, 0u, ab_dtype == SDNQ_F8E5M2 ? 1u : 0u, nullptr, nullptr, 0, 0u, x, ldx, xq, sx, sync};
     const bool i8 = ab_dtype == SDNQ_I8;
     const bool bf = x_dtype == SDNQ_BF16;
 #define SDNQ_FUSED(BN_)                                                                                                    \
@@ -865,4 +962,25 @@ extern "C" int sdnq_b200_mm(const void* a, const void* b, int ab_dtype, void* ou
     SDNQ_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), SDNQ_EUNSUPPORTED, "dimension too large");
     GemmParams p{nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, out, SDNQ_I32, (int)M, (int)N, (int)K, 1, 0u, ab_dtype == SDNQ_F8E5M2 ? 1u : 0u};
     return scaled_mm_impl(a, b, ab_dtype, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- scaled matmul with the SVD rank-r term accumulated on the tensor cores (the SVD branch of get_*_matmul_inputs)
+extern "C" int sdnq_b200_scaled_mm_svd(const void* a, const void* b, int ab_dtype, const sdnq_weight_format* b_fmt, const float* sx, const float* sw,
+                                       const void* bias, int bias_dtype, int64_t bias_ld, const int32_t* rowsum, const float* zp,
+                                       const int32_t* colsum, const float* zx, const void* svd_low, const void* svd_up_nr, int svd_rank,
+                                       int svd_dtype, void* out, int out_dtype, int64_t M, int64_t N, int64_t K, void* stream) {
+    SDNQ_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), SDNQ_EUNSUPPORTED, "dimension too large");
+    SDNQ_REQUIRE(svd_dtype == SDNQ_BF16 || svd_dtype == SDNQ_F16, SDNQ_EUNSUPPORTED, "svd factors must be bf16 / f16 (got %d)", svd_dtype);
+    SDNQ_REQUIRE(svd_rank != 0, SDNQ_EINVAL, "svd_rank is 0: use sdnq_b200_scaled_mm");
+    uint32_t w_sub = 0u;
+    int wbits = 8;
+    if (b_fmt != nullptr) {
+        SDNQ_REQUIRE(b_fmt->kind == SDNQ_W_INT && b_fmt->bits == 4, SDNQ_EUNSUPPORTED, "scaled_mm_svd: packed weights must be int4 / uint4");
+        SDNQ_REQUIRE(b_fmt->is_unsigned == 0 || (zp != nullptr && rowsum != nullptr), SDNQ_EINVAL, "uint4 weights need zp and rowsum");
+        w_sub = b_fmt->is_unsigned ? 0u : 0x08080808u;
+        wbits = 4;
+    }
+    GemmParams p{sx, sw, bias, bias_dtype, bias_ld, rowsum, zp, colsum, zx, out, out_dtype, (int)M, (int)N, (int)K, 0, w_sub,
+                 ab_dtype == SDNQ_F8E5M2 ? 1u : 0u, svd_low, svd_up_nr, svd_rank, svd_dtype == SDNQ_BF16 ? 1u : 0u};
+    return scaled_mm_impl(a, b, wbits == 4 ? SDNQ_I8 : ab_dtype, p, reinterpret_cast<cudaStream_t>(stream), wbits);
 }

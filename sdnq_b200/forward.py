@@ -268,6 +268,35 @@ def _svd_operands(self):
     return down_rk, up_nr
 
 
+def _svd_mm_operands(self, x_dtype):
+    """The SVD factors as K7 / K1 read them on the W8A8 path: svd_down [r',K] and svd_up [N,r'] row-major in the activation dtype, the
+    rank padded with zero rows / columns to r' = 16, 32 or 64 (the tcgen05 kind::f16 k-step and the TMA swizzle spans).  None when the
+    kernels do not apply (rank > 64, factors not stored in the 16-bit activation dtype): the caller then builds the reference's
+    dense [M,N] bias instead."""
+    up, down = self.svd_up, self.svd_down
+    if (x_dtype not in (torch.bfloat16, torch.float16) or up.dtype != x_dtype or down.dtype != x_dtype or min(up.shape) > 64
+            or max(down.shape) % 16 != 0 or os.environ.get("SDNQ_B200_SVD_FUSED", "1") in ("0", "false", "no")):
+        return None
+    cached = self.__dict__.get("_sdnq_svd_mm_cache")
+    if cached is not None and cached[0].matches(self, (up, down)):
+        return cached[1], cached[2]
+    down_rk, up_nr = _svd_operands(self)
+    r = down_rk.shape[0]
+    rp = 16 if r <= 16 else 32 if r <= 32 else 64
+    if rp != r:
+        down_rk = torch.nn.functional.pad(down_rk, (0, 0, 0, rp - r)).contiguous()
+        up_nr = torch.nn.functional.pad(up_nr, (0, rp - r)).contiguous()
+    self.__dict__["_sdnq_svd_mm_cache"] = (_StoredState(self, (up, down)), down_rk, up_nr)
+    return down_rk, up_nr
+
+
+def _svd_bias2d(self, x_rot):
+    """The reference's SVD term as a dense bias (linear_int8.py:57-62): used only where K7 + the rank-r accumulate do not apply."""
+    down, up = self.svd_down, self.svd_up
+    low = torch.mm(x_rot.to(down.dtype), down)
+    return torch.mm(low, up) if self.bias is None else torch.addmm(self.bias.to(down.dtype), low, up)
+
+
 def _w4a16_linear(self, x):
     d = self.sdnq_dequantizer
     N, K = d.matmul_nk()
@@ -364,27 +393,32 @@ def _w8a8_forward(self, input: torch.Tensor) -> torch.Tensor:
     op = matmul_operand(self)
     mm = d.quantized_matmul_dtype
     hg = d.hadamard_group_size if d.use_hadamard else 0
-    if op.packed is not None:
-        xq, sx, _, rowsum, x_rot = quantized_activations(_rows(input), mm, hg, op.zp is not None, self.svd_up is not None)
-        bias = self.bias
-        if self.svd_up is not None:
-            low = torch.mm(x_rot.to(self.svd_down.dtype), self.svd_down)
-            bias = torch.mm(low, self.svd_up) if self.bias is None else torch.addmm(self.bias.to(self.svd_down.dtype), low, self.svd_up)
-        out = ops.scaled_mm_packed(xq, op.wq, op.packed, d.original_shape[0], sx, op.sw, bias, input.dtype, rowsum=rowsum, zp=op.zp)
-        return out.view(*input.shape[:-1], out.shape[-1])
+    x2 = _rows(input)
     if self.svd_up is None:
-        if not _act_cache_on():       # one C call: K2 into the per-stream workspace + K1
+        if op.packed is None and not _act_cache_on():       # one C call: K2 into the per-stream workspace + K1
             return ops.linear_w8a8(input, op.wq, mm, op.sw, bias=self.bias, zp=op.zp, colsum=op.colsum, hadamard_group=hg, out_dtype=input.dtype)
-        xq, sx, zx, rowsum, _ = quantized_activations(_rows(input), mm, hg, op.zp is not None, False)
-        out = ops.scaled_mm(xq, op.wq, sx, op.sw, self.bias, input.dtype, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx)
+        xq, sx, zx, rowsum, _ = quantized_activations(x2, mm, hg, op.zp is not None, False)
+        if op.packed is not None:
+            out = ops.scaled_mm_packed(xq, op.wq, op.packed, d.original_shape[0], sx, op.sw, self.bias, input.dtype, rowsum=rowsum, zp=op.zp)
+        else:
+            out = ops.scaled_mm(xq, op.wq, sx, op.sw, self.bias, input.dtype, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx)
         return out.view(*input.shape[:-1], out.shape[-1])
-    # SVD branch: bias2d = bias + (x_rot @ svd_down[K,r]) @ svd_up[r,N] in the SVD dtype on the rotated, un-quantised
-    # activations (linear_int8.py:57-62); two skinny library GEMMs, the rest stays in our kernels.
-    xq, sx, zx, rowsum, x_rot = quantized_activations(_rows(input), mm, hg, op.zp is not None, True)
-    down, up = self.svd_down, self.svd_up
-    low = torch.mm(x_rot.to(down.dtype), down)
-    bias2d = torch.mm(low, up) if self.bias is None else torch.addmm(self.bias.to(down.dtype), low, up)
-    out = ops.scaled_mm(xq, op.wq, sx, op.sw, bias2d, input.dtype, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx)
+    # SVD branch (linear_int8.py:57-62): bias2d = bias + (x_rot @ svd_down[K,r]) @ svd_up[r,N] on the rotated, un-quantised activations
+    # in the SVD dtype.  K7 computes low = x_rot @ svd_down, K1 accumulates low @ svd_up per output tile on the tensor cores.
+    svd = _svd_mm_operands(self, input.dtype)
+    need_rot = hg != 0 or svd is None                       # without rotation x_rot is x itself: K2 does not write a copy of it
+    xq, sx, zx, rowsum, x_rot = quantized_activations(x2, mm, hg, op.zp is not None, need_rot)
+    if svd is None:
+        bias2d = _svd_bias2d(self, x_rot)
+        if op.packed is not None:
+            out = ops.scaled_mm_packed(xq, op.wq, op.packed, d.original_shape[0], sx, op.sw, bias2d, input.dtype, rowsum=rowsum, zp=op.zp)
+        else:
+            out = ops.scaled_mm(xq, op.wq, sx, op.sw, bias2d, input.dtype, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx)
+        return out.view(*input.shape[:-1], out.shape[-1])
+    down_rk, up_nr = svd
+    low = ops.svd_low(x_rot if hg != 0 else x2, down_rk)
+    out = ops.scaled_mm_svd(xq, op.wq, sx, op.sw, low, up_nr, self.bias, input.dtype, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx,
+                            packed_dtype=op.packed, N=d.original_shape[0])
     return out.view(*input.shape[:-1], out.shape[-1])
 
 
@@ -489,14 +523,17 @@ def _w8a8_conv_forward(self, input: torch.Tensor) -> torch.Tensor:
     svd = self.svd_up is not None
     xq, sx, zx, rowsum, x_rot, (B, Ho, Wo) = ops.conv_act_quant(x4, ksz, stride, padding, dilation, mm, hadamard_group=hg,
                                                                 want_rowsum=op.zp is not None, want_x_rot=svd)
-    bias = self.bias
-    if svd:                                                                       # conv_int8.py:56-61
-        low = torch.mm(x_rot.to(self.svd_down.dtype), self.svd_down)
-        bias = torch.mm(low, self.svd_up) if self.bias is None else torch.addmm(self.bias.to(self.svd_down.dtype), low, self.svd_up)
-    if op.packed is not None:
-        out = ops.scaled_mm_packed(xq, op.wq, op.packed, d.original_shape[0], sx, op.sw, bias, input.dtype, rowsum=rowsum, zp=op.zp)
+    svd_ops = _svd_mm_operands(self, input.dtype) if svd else None
+    if svd_ops is not None:                                                       # conv_int8.py:56-61 as K7 + the rank-r accumulate in K1
+        low = ops.svd_low(x_rot, svd_ops[0])
+        out = ops.scaled_mm_svd(xq, op.wq, sx, op.sw, low, svd_ops[1], self.bias, input.dtype, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx,
+                                packed_dtype=op.packed, N=d.original_shape[0])
     else:
-        out = ops.scaled_mm(xq, op.wq, sx, op.sw, bias, input.dtype, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx)
+        bias = _svd_bias2d(self, x_rot) if svd else self.bias
+        if op.packed is not None:
+            out = ops.scaled_mm_packed(xq, op.wq, op.packed, d.original_shape[0], sx, op.sw, bias, input.dtype, rowsum=rowsum, zp=op.zp)
+        else:
+            out = ops.scaled_mm(xq, op.wq, sx, op.sw, bias, input.dtype, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx)
     N = out.shape[-1]
     y = ops.rows_to_nchw(out, B, Ho * Wo)                                         # [B*L, N] -> [B, N, L] (conv_int8.py:83-89)
     return y.view(B, N, Wo) if nd == 1 else y.view(B, N, Ho, Wo)

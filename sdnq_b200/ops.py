@@ -318,6 +318,52 @@ def scaled_mm_packed(a: torch.Tensor, b_packed: torch.Tensor, weights_dtype: str
     return out
 
 
+def svd_low(x: torch.Tensor, svd_down_rk: torch.Tensor) -> torch.Tensor:
+    """K7.  x [M,K] bf16 / f16 (row stride a multiple of 8), svd_down_rk [r,K] contiguous of the same dtype -> low [M,r] = cast(x @ down^T)."""
+    _require_cuda(x, svd_down_rk)
+    M, K = x.shape
+    r = svd_down_rk.shape[0]
+    if svd_down_rk.dtype != x.dtype or not svd_down_rk.is_contiguous() or svd_down_rk.shape[1] != K:
+        raise _lib.SDNQKernelError("svd_low: svd_down must be a contiguous [r,K] tensor of the activation dtype")
+    if x.stride(-1) != 1 or x.stride(0) % 8 != 0 or x.data_ptr() % 16 != 0:
+        x = x.contiguous()
+    low = torch.empty((M, r), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().sdnq_b200_svd_low(_ptr(x), dtype_code(x.dtype), x.stride(0), _ptr(svd_down_rk), r, _ptr(low), M, K, _stream(x)))
+    return low
+
+
+def scaled_mm_svd(a: torch.Tensor, b: torch.Tensor, sx, sw, low: torch.Tensor, svd_up_nr: torch.Tensor, bias=None,
+                  out_dtype: torch.dtype = torch.bfloat16, rowsum=None, zp=None, colsum=None, zx=None,
+                  packed_dtype: str | None = None, N: int | None = None) -> torch.Tensor:
+    """K1 with the SVD rank-r term accumulated on the tensor cores: out = scaled_mm(...) + low @ svd_up_nr^T (added to the bias in f32).
+    b is the physical [N,K] operand, or (packed_dtype = 'int4' / 'uint4', N given) the stored packed weight."""
+    _require_cuda(a, b, low, svd_up_nr)
+    M, K = a.shape
+    N = b.shape[0] if packed_dtype is None else int(N)
+    r = svd_up_nr.shape[1]
+    if (low.dtype != svd_up_nr.dtype or tuple(low.shape) != (M, r) or tuple(svd_up_nr.shape) != (N, r)
+            or not low.is_contiguous() or not svd_up_nr.is_contiguous()):
+        raise _lib.SDNQKernelError("scaled_mm_svd: low [M,r] / svd_up [N,r] must be contiguous tensors of one 16-bit dtype")
+    out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    bias_ld, bias_code = 0, SDNQ_F32
+    if bias is not None:
+        bias = bias.contiguous()
+        bias_code = dtype_code(bias.dtype)
+        if bias.ndim == 2 and bias.shape[0] != 1:
+            bias_ld = bias.stride(0)
+    if packed_dtype is None:
+        assert b.shape[1] == K and a.is_contiguous() and b.is_contiguous()
+        ab, fmt = _operand_code(a.dtype, b), None
+    else:
+        ab, fmt = SDNQ_I8, weight_format(packed_dtype, b)
+    with torch.cuda.device(a.device):
+        check(_lib.load().sdnq_b200_scaled_mm_svd(_ptr(a), _ptr(b), ab, fmt, _ptr(sx), _ptr(sw), _ptr(bias), bias_code, bias_ld,
+                                                  _ptr(rowsum), _ptr(zp), _ptr(colsum), _ptr(zx), _ptr(low), _ptr(svd_up_nr), r,
+                                                  dtype_code(low.dtype), _ptr(out), dtype_code(out_dtype), M, N, K, _stream(a)))
+    return out
+
+
 def mm(a: torch.Tensor, b_nk: torch.Tensor) -> torch.Tensor:
     """plain int8 -> int32 / fp8 -> f32 matmul (int_mm_func / fp8_mm_func)."""
     _require_cuda(a, b_nk)

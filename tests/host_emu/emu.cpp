@@ -37,6 +37,7 @@ int64_t sdnq_b200_launch_count(int reset) {
     if (reset) sdnq::g_launches = 0;
     return v;
 }
+int64_t sdnq_b200_stream_capture_id(void*) { return 0; }      // the emulator has no streams: never capturing
 // the two CUDA runtime calls the launch code makes besides the launch itself
 const char* cudaGetErrorString(cudaError_t) { return "cuda runtime is not available in the host emulator"; }
 cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }

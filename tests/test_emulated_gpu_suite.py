@@ -278,3 +278,9 @@ def test_dynamic_quantization(kw):
         if "scaled_mm" not in str(e) and "linear_w8a8" not in str(e):
             raise
         pytest.skip("the model forward at the end of this case runs the tcgen05 GEMM: GPU only")
+
+
+# ---- K7 (svd_low.cu): the rank-r projection of the W8A8 SVD branch
+@emulated(K.test_svd_low, keep=lambda kw: kw["M"] * kw["K"] <= 130 * 2048)
+def test_svd_low(kw):
+    K.test_svd_low(**kw)

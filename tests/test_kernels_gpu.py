@@ -489,6 +489,85 @@ def test_scaled_mm_packed_int4(signed, M, N, K):
     np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=2e-6, atol=1e-5)
 
 
+# ----------------------------------------------------------------------------------------------- SVD branch of the W8A8 forwards (K7 + rank-r accumulate in K1)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,K,r", [(1, 16, 8), (77, 2048, 32), (130, 640, 16), (1024, 1280, 32), (333, 1296, 64), (40, 3072, 24), (16, 48, 32)])
+def test_svd_low(dtype, M, K, r):
+    """K7: low = cast(x @ svd_down^T) with f32 accumulation -- torch.mm's rounding point (linear_int8.py:59)."""
+    g = torch.Generator().manual_seed(M + K + r)
+    x = torch.randn(M, K, generator=g).to(dtype)
+    down = (torch.randn(r, K, generator=g) / K ** 0.5).to(dtype)
+    got = ops().svd_low(x.to(DEV), down.to(DEV)).cpu()
+    ref32 = x.double() @ down.double().t()
+    ref = ref32.to(dtype)
+    assert got.dtype == dtype and got.shape == (M, r)
+    # f32 accumulation in a different order than the f64 reference: the rounded results agree to one unit in the last place
+    err = (got.double() - ref32).abs()
+    ulp = torch.maximum(ref32.abs(), torch.tensor(1e-3, dtype=torch.float64)) * (2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10)
+    assert bool((err <= ulp).all()), float((err / ulp).max())
+    assert float((got != ref).float().mean()) < 0.02
+    # strided rows
+    xs = torch.randn(M, K + 8, generator=g).to(dtype).to(DEV)[:, :K]
+    got2 = ops().svd_low(xs, down.to(DEV)).cpu()
+    ref2 = (xs.cpu().double() @ down.double().t())
+    assert bool(((got2.double() - ref2).abs() <= torch.maximum(ref2.abs(), torch.tensor(1e-3, dtype=torch.float64)) * (2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10)).all())
+
+
+@pytest.mark.parametrize("kind", ["int8", "fp8", "uint8", "int4", "uint4"])
+@pytest.mark.parametrize("M,N,K,r", [(128, 128, 128, 32), (77, 640, 2048, 32), (300, 1288, 640, 16), (1000, 5120, 640, 64), (2048, 4096, 384, 32), (64, 136, 32, 32)])
+def test_scaled_mm_svd(kind, M, N, K, r):
+    """K1 with the rank-r second accumulate: out = fma(acc * sx, sw, zero-point terms + low @ svd_up^T + bias), the sum formed in f32."""
+    rng = np.random.default_rng(M + N + K + r + len(kind))
+    dt = torch.bfloat16
+    low = torch.from_numpy(rng.standard_normal((M, r)).astype(np.float32)).to(dt)
+    up = torch.from_numpy((rng.standard_normal((N, r)) / r ** 0.5).astype(np.float32)).to(dt)
+    sx = torch.from_numpy((rng.random(M) * 0.05 + 1e-3).astype(np.float32))
+    sw = torch.from_numpy((rng.random(N) * 0.01 + 1e-4).astype(np.float32))
+    bias = torch.from_numpy(rng.standard_normal(N).astype(np.float32)).to(dt)
+    svd32 = (low.double() @ up.double().t()).numpy()
+    kw = {}
+    extra = np.zeros((M, N), dtype=np.float64)
+    if kind in ("int4", "uint4"):
+        codes = rng.integers(0, 16, size=(N, K))
+        b = torch.from_numpy(O.pack_uint(codes, 4).astype(np.uint8))
+        wvals = codes - 8 if kind == "int4" else codes
+        a = torch.from_numpy(rng.integers(-128, 128, size=(M, K)).astype(np.int8))
+        acc = O.int_mm(a.numpy(), wvals.T.astype(np.int8)).astype(np.float64)
+        kw = dict(packed_dtype=kind, N=N)
+        if kind == "uint4":
+            zp = torch.from_numpy((rng.standard_normal(N) * 0.1).astype(np.float32))
+            rowsum = torch.from_numpy(a.numpy().astype(np.int64).sum(axis=1).astype(np.int32))
+            kw.update(zp=zp.to(DEV), rowsum=rowsum.to(DEV))
+            extra = rowsum.numpy().astype(np.float64)[:, None] * sx.numpy().astype(np.float64)[:, None] * zp.numpy().astype(np.float64)[None, :]
+    elif kind == "fp8":
+        a = torch.from_numpy(rng.standard_normal((M, K)).astype(np.float32)).to(torch.float8_e4m3fn)
+        b = torch.from_numpy(rng.standard_normal((N, K)).astype(np.float32)).to(torch.float8_e4m3fn)
+        acc = (a.double() @ b.double().t()).numpy()
+    else:
+        a = torch.from_numpy(rng.integers(-128, 128, size=(M, K)).astype(np.int8))
+        b = torch.from_numpy(rng.integers(-128, 128, size=(N, K)).astype(np.int8))
+        acc = O.int_mm(a.numpy(), b.numpy().T).astype(np.float64)
+        if kind == "uint8":            # asymmetric activations and weights: zero-point, column-sum and K * zx * zp terms
+            zp = torch.from_numpy((rng.standard_normal(N) * 0.1).astype(np.float32))
+            zx = torch.from_numpy((rng.standard_normal(M) * 0.1).astype(np.float32))
+            rowsum = torch.from_numpy(a.numpy().astype(np.int64).sum(axis=1).astype(np.int32))
+            colsum = torch.from_numpy(b.numpy().astype(np.int64).sum(axis=1).astype(np.int32))
+            kw.update(zp=zp.to(DEV), rowsum=rowsum.to(DEV), zx=zx.to(DEV), colsum=colsum.to(DEV))
+            f = lambda t: t.numpy().astype(np.float64)
+            extra = (f(rowsum)[:, None] * f(sx)[:, None] * f(zp)[None, :] + f(colsum)[None, :] * f(sw)[None, :] * f(zx)[:, None]
+                     + K * f(zx)[:, None] * f(zp)[None, :])
+    got = ops().scaled_mm_svd(a.to(DEV), b.to(DEV), sx.to(DEV), sw.to(DEV), low.to(DEV), up.to(DEV), bias.to(DEV), dt, **kw).float().cpu().numpy()
+    ref = acc * sx.numpy().astype(np.float64)[:, None] * sw.numpy().astype(np.float64)[None, :] + extra + svd32 + bias.double().numpy()[None, :]
+    mag = np.abs(acc * sx.numpy()[:, None] * sw.numpy()[None, :]) + np.abs(extra) + np.abs(svd32) + np.abs(bias.float().numpy())[None, :]
+    err = np.abs(got - ref)
+    bound = np.maximum(np.abs(ref), 1e-3) * 2.0 ** -8 + mag * 2e-6 + (mag * 3e-3 if kind == "fp8" else 0)   # half a bf16 ulp + f32 accumulation slack
+    assert np.all(err <= bound), float((err / bound).max())
+    # without a bias the SVD product alone is the addend
+    got_nb = ops().scaled_mm_svd(a.to(DEV), b.to(DEV), sx.to(DEV), sw.to(DEV), low.to(DEV), up.to(DEV), None, dt, **kw).float().cpu().numpy()
+    ref_nb = ref - bias.double().numpy()[None, :]
+    assert np.all(np.abs(got_nb - ref_nb) <= np.maximum(np.abs(ref_nb), 1e-3) * 2.0 ** -8 + mag * 2e-6 + (mag * 3e-3 if kind == "fp8" else 0))
+
+
 # ----------------------------------------------------------------------------------------------- fused quantise + GEMM (one launch)
 FUSED_SHAPES = [(1024, 1280, 1280), (4096, 640, 640), (77, 1280, 2048), (333, 136, 272), (1, 64, 32), (32, 8, 16), (128 * 5 + 7, 648, 5120),
                 (2500, 256, 4096 + 16), (148 * 2 + 1, 384, 16384)]
