@@ -420,6 +420,10 @@ def run_workload(name, args, world, rank, device, peaks, with_roofline=True):
     spec = WORKLOADS[name]
     local_rank = device.index
     stack = build_stack(name, device)
+    sib_groups = 0
+    if args.siblings != "off":      # what sdnq_post_load_quant does on a module tree, here on the (name, layer) list of the synthetic stack
+        from sdnq_b200 import fuse_named_siblings
+        sib_groups = fuse_named_siblings([(n, layer) for n, _, _, _, _, layer in stack], cross_attention_pool=8 if args.siblings == "pool" else 0)
     layers_meta = [(n, m, nn_, k, s) for n, m, nn_, k, s, _ in stack]
     flops_step = total_flops(layers_meta)
 
@@ -572,12 +576,28 @@ def run_workload(name, args, world, rank, device, peaks, with_roofline=True):
                     k2_srcs.append((m, k, key))
                     last = key
 
+            # the GEMM launches the step really makes: one per layer, or one per sibling group and input tensor
+            gemm_calls, seen = [], set()
+            for m, n, k, src, layer in mm_layers:
+                d = layer.sdnq_dequantizer
+                key = (src, d.quantized_matmul_dtype, d.hadamard_group_size if d.use_hadamard else 0)
+                group = layer.__dict__.get("_sdnq_siblings")
+                if group is not None and group.state is not None and not group.dead:
+                    if (id(group), src) not in seen:
+                        seen.add((id(group), src))
+                        gemm_calls.append((key, None, group.state))
+                else:
+                    gemm_calls.append((key, layer, None))
+
             def all_gemms():
-                for m, n, k, src, layer in mm_layers:
-                    d = layer.sdnq_dequantizer
-                    op = matmul_operand(layer)
-                    xq, sx, zx, rowsum, _ = pre[(src, d.quantized_matmul_dtype, d.hadamard_group_size if d.use_hadamard else 0)]
-                    ops.scaled_mm(xq, op.wq, sx, op.sw, layer.bias, torch.bfloat16, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx)
+                for key, layer, st in gemm_calls:
+                    xq, sx, zx, rowsum, _ = pre[key]
+                    if st is not None:
+                        ops.scaled_mm_grouped(xq, st["wq"], sx, st["sw"], st["starts"], st["ns"], st["bias"], torch.bfloat16, rowsum=rowsum,
+                                              zp=st["zp"], colsum=st["colsum"], zx=zx, packed_dtype=st["packed"])
+                    else:
+                        op = matmul_operand(layer)
+                        ops.scaled_mm(xq, op.wq, sx, op.sw, layer.bias, torch.bfloat16, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx)
 
             def all_act_quants():
                 for m, k, (src, mmd, hg) in k2_srcs:
@@ -586,6 +606,7 @@ def run_workload(name, args, world, rank, device, peaks, with_roofline=True):
             gemm_ms = graph_time(all_gemms)
             k2_ms = graph_time(all_act_quants)
             n_k2 = len(k2_srcs)
+            n_gemm = len(gemm_calls)
             gemm_flops = sum(2.0 * m * n * k for m, n, k, _, _ in mm_layers)
             k2_bytes = sum(3.0 * m * k for m, k, _ in k2_srcs)
             fp8 = spec["config"]["weights_dtype"].startswith("float")
@@ -611,7 +632,8 @@ def run_workload(name, args, world, rank, device, peaks, with_roofline=True):
                         "launches": n_gemm, "avg_launch_us": 1e3 * gemm_ms / max(n_gemm, 1), "share_of_step": gemm_ms / (gemm_ms + k2_ms),
                         "act_quant": {"bound": "hbm", "kernel": "act_quant_kernel (K2)", "achieved": k2_bytes / k2_ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
                                       "frac": k2_bytes / k2_ms / 1e6 / hbm_peak, "launches": n_k2, "avg_launch_us": 1e3 * k2_ms / max(n_k2, 1),
-                                      "launches_without_sibling_reuse": n_gemm}}
+                                      "launches_without_sibling_reuse": len(mm_layers)},
+                        "linears": len(mm_layers), "grouped_launches": sum(1 for c in gemm_calls if c[2] is not None)}
         elif dq_layers:
             roofline = dequant_path_roofline(dq_layers, acts, graph_time, hbm_peak, src_note, peaks_file, traffic, traffic_note)
 
@@ -622,7 +644,8 @@ def run_workload(name, args, world, rank, device, peaks, with_roofline=True):
     res = {"metric": "quantized_linear_tflops", "value": tfl, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "steps_per_s": 1e3 * args.steps / ms * world, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": spec["dtype"], "data": "synthetic", "config": workload_config(name, world),
-           "execution": "whole step captured in one CUDA graph, replayed per step; sibling projections share one activation-quantise launch",
+           "execution": "whole step captured in one CUDA graph, replayed per step; sibling projections (to_q / to_k / to_v, cross-attention to_k / to_v) "
+                        f"share one activation-quantise launch and one grouped GEMM launch (--siblings {args.siblings}: {sib_groups} groups)",
            "e2e": {"value": tfl_e2e, "unit": "TFLOP/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
            "gpu_launches": int(launches_per_step) * args.steps, "launches_per_step": int(launches_per_step),
            "clocks": clocks, "roofline": roofline}
@@ -723,6 +746,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=None, help=f"one of {sorted(WORKLOADS)}; default: {HEADLINE} with {list(NESTED)} nested under 'workloads'")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "gpu_reference"])
+    ap.add_argument("--siblings", default="block", choices=["off", "block", "pool"],
+                    help="grouped launches for sibling projections: per attention block (what sdnq_post_load_quant registers), "
+                         "'pool' also pools the cross-attention to_k / to_v pairs of 4 blocks that read the same encoder states")
     ap.add_argument("--no-nested", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")

@@ -292,6 +292,21 @@ SDNQ_API int sdnq_b200_scaled_mm_svd(const void* a, const void* b, int ab_dtype,
                                      const int32_t* colsum, const float* zx, const void* svd_low, const void* svd_up_nr, int svd_rank,
                                      int svd_dtype, void* out, int out_dtype, int64_t M, int64_t N, int64_t K, void* stream);
 
+/* ---- K1, grouped: several Linears that read the SAME activations (to_q / to_k / to_v of an attention block, the cross-attention
+ *      to_k / to_v pair, gate / up projections) as ONE launch.  The reference runs one scaled matmul per Linear
+ *      (linear_int8.py:100-125 each time); here the siblings' matmul operands are concatenated along N once, the quantised
+ *      activations are read by one persistent grid, and every sibling gets its own contiguous output -- per element exactly the
+ *      value sdnq_b200_scaled_mm / _packed produces for that sibling alone.
+ *   b_cat        the siblings' physical [N_g, K] operands (or, b_fmt = int4 / uint4: their packed rows) stacked; segment g starts at row
+ *                seg_start[g] (a multiple of 128; all multiples of 256 lets the kernel use 256-wide tiles and CTA pairs) and holds
+ *                seg_n[g] rows followed by zero rows up to seg_start[g+1];  seg_start has n_groups + 1 entries, the last = total rows
+ *   sw_cat, bias_cat, zp_cat, colsum_cat   the per-output-channel vectors laid out the same way (bias_cat / zp_cat / colsum_cat may be NULL)
+ *   outs[g]      [M, seg_n[g]] row-major of out_dtype;  1 <= n_groups <= 8;  other arguments as for sdnq_b200_scaled_mm */
+SDNQ_API int sdnq_b200_scaled_mm_grouped(const void* a, const void* b_cat, int ab_dtype, const sdnq_weight_format* b_fmt, const float* sx,
+                                         const float* sw_cat, const void* bias_cat, int bias_dtype, const int32_t* rowsum, const float* zp_cat,
+                                         const int32_t* colsum_cat, const float* zx, int n_groups, const int64_t* seg_start, const int64_t* seg_n,
+                                         void* const* outs, int out_dtype, int64_t M, int64_t K, void* stream);
+
 /* The same Linear as ONE kernel launch: the GEMM kernel row-quantises the activations itself (every CTA takes a share
  * of the rows: bulk copy to shared memory, warp-reduction amax, quantise, codes + scales to the workspace) and its TMA
  * producers pick the quantised strips up through release/acquire strip counters -- linear_int8.py:14-22 + 100-125 /

@@ -50,6 +50,8 @@ SIGNATURES = {
     "sdnq_b200_linear_w4a16": (_I, [_P, _I, _L, _P, _WF, _P, _P, _L, _P, _P, _I, _P, _I, _P, _L, _L, _L, _P]),
     "sdnq_b200_svd_low": (_I, [_P, _I, _L, _P, _I, _P, _L, _L, _P]),
     "sdnq_b200_scaled_mm_svd": (_I, [_P, _P, _I, _WF, _P, _P, _P, _I, _L, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _L, _L, _L, _P]),
+    "sdnq_b200_scaled_mm_grouped": (_I, [_P, _P, _I, _WF, _P, _P, _P, _I, _P, _P, _P, _P, _I, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
+                                         ctypes.POINTER(ctypes.c_void_p), _I, _L, _L, _P]),
     "sdnq_b200_linear_w8a8_workspace_bytes": (_Z, [_L, _L]),
     "sdnq_b200_linear_w8a8": (_I, [_P, _I, _L, _P, _I, _P, _P, _P, _P, _I, _I, _P, _I, _L, _L, _L, _P, _Z, _P]),
     "sdnq_b200_linear_w8a8_fused": (_I, [_P, _I, _L, _P, _I, _P, _P, _I, _P, _I, _L, _L, _L, _P, _Z, _P]),

@@ -65,8 +65,17 @@ struct GemmParams {
     uint8_t* fxq;
     float* fsx;
     int* fsync;       // [kSyncStrips] rows quantised per 128-row strip | [kSyncStrips] tiles that consumed the strip
+    // grouped launch (n_groups != 0): several Linears fed by the same activations in one launch.  B, sw, bias, zp and colsum are the
+    // siblings' tensors concatenated along N, each segment starting at grp_start[g] (a multiple of the tile width) and holding
+    // grp_n[g] real rows (zero rows fill the tail); N = grp_start[n_groups]; every sibling has its own contiguous [M, grp_n[g]] output
+    int n_groups;
+    int grp_start[9];
+    int grp_n[8];
+    void* grp_out[8];
 };
 constexpr int kSyncStrips = 512;
+constexpr int kMaxGroups = 8;
+struct OutMaps { CUtensorMap m[kMaxGroups]; };       // output tensor maps: m[0] for a plain launch, one per sibling for a grouped one
 
 // WB = storage bits of the B operand: 8 (int8 / fp8 tiles land in the ring directly by TMA) or 4 (packed int4 / uint4:
 // TMA stages the packed tile, four unpack warps expand it into the ring -- "unpack in the GEMM prologue").
@@ -120,7 +129,7 @@ __device__ __forceinline__ void load8_any(const void* p, int64_t i, int dtype, f
 template <int BN, bool kInt8, int OUT, bool kSimple, int WB, int XM, int CG, bool kSvd = false>
 __global__ void __launch_bounds__((Cfg<BN, WB, CG, kSvd>::kThreads), 1)
 gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_l,
+                 const __grid_constant__ OutMaps tmaps_o, const __grid_constant__ CUtensorMap tmap_l,
                  const __grid_constant__ CUtensorMap tmap_u, const GemmParams p) {
     using C = Cfg<BN, WB, CG, kSvd>;
     static_assert(!kSvd || (XM == 0 && !kSimple), "SVD tiles use the generic epilogue and the stand-alone activation quantiser");
@@ -173,7 +182,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_b);
-        ptx::prefetch_tmap(&tmap_o);
+        ptx::prefetch_tmap(&tmaps_o.m[0]);
         for (int s = 0; s < C::kStages; ++s) {
             ptx::mbar_init(full_bar(s), kPacked ? 1 + 4 : 1);     // TMA (A) [+ the four unpack warps (B)]
             ptx::mbar_init(empty_bar(s), 1);
@@ -469,6 +478,12 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1u;
             const int m0 = tile_m0(tile), n0 = (tile % num_n) * BN;
+            // grouped launch: the sibling this tile belongs to; its real columns end at n_end, its output starts at column n_base
+            int grp = 0;
+            while (grp + 1 < p.n_groups && n0 >= p.grp_start[grp + 1]) ++grp;
+            const int n_base = p.n_groups != 0 ? p.grp_start[grp] : 0;
+            const int n_end = p.n_groups != 0 ? n_base + p.grp_n[grp] : p.N;
+            const CUtensorMap* tmap_o = &tmaps_o.m[grp];
             const int mrow0 = m0 + q * 32;
             const int m = mrow0 + lane;
             const bool m_ok = m < p.M;
@@ -486,7 +501,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int c = threadIdx.x - 64; c < BN; c += 128) {
                     const int nc = n0 + c;
                     float sv = 0.f, bv = 0.f;
-                    if (nc < p.N) {
+                    if (nc < n_end) {
                         sv = p.sw[nc];
                         if (vec_bias)
                             bv = p.bias_dtype == SDNQ_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[nc])
@@ -505,7 +520,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll 1
             for (int cb = 0; cb < BN / CPB; ++cb) {
                 const int n = n0 + cb * CPB;
-                if (n >= p.N || mrow0 >= p.M) break;              // warp-uniform
+                if (n >= n_end || mrow0 >= p.M) break;            // warp-uniform
                 uint32_t r[CPB];
                 {
                     uint32_t (&r0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[0]);
@@ -532,7 +547,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     for (int c8 = 0; c8 < CPB / 8; ++c8) {        // groups of 8 columns
                         const int nc = n + 8 * c8;
                         float y[8];
-                        if (nc < p.N) {
+                        if (nc < n_end) {
                             float swv[8];
                             {
                                 const float4 s0 = *reinterpret_cast<const float4*>(s_sw + cb * CPB + 8 * c8);
@@ -641,7 +656,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 ptx::fence_proxy_async_smem();                    // generic-proxy smem writes -> visible to the TMA engine
                 __syncwarp();
                 if (lane == 0) {
-                    ptx::tma_store_2d(&tmap_o, buf, n, mrow0);
+                    ptx::tma_store_2d(tmap_o, buf, n - n_base, mrow0);
                     ptx::tma_store_commit();
                 }
                 ++blk;
@@ -730,13 +745,23 @@ int launch_gemm(const void* a, const void* b, const GemmParams& p, cudaStream_t 
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes); });
     SDNQ_REQUIRE(attr_err == cudaSuccess, SDNQ_ECUDA, "cudaFuncSetAttribute(max dynamic smem %d) failed: %s", C::kSmemBytes,
                  cudaGetErrorString(attr_err));
-    CUtensorMap ta, tb, to;
+    CUtensorMap ta, tb;
+    OutMaps to;
     int rc = make_tmap(&ta, a, p.M, p.K, 1, BM);
     if (rc != SDNQ_OK) return rc;
     rc = WB < 8 ? make_tmap(&tb, b, p.N, int64_t(p.K) * WB / 8, 1, BN, BK * WB / 8) : make_tmap(&tb, b, p.N, p.K, 1, BN / CG);
     if (rc != SDNQ_OK) return rc;
-    rc = make_tmap(&to, p.out, p.M, p.N, (OUT == OUT_BF16 || OUT == OUT_F16) ? 2 : 4, 32);
-    if (rc != SDNQ_OK) return rc;
+    constexpr int kOutElem = (OUT == OUT_BF16 || OUT == OUT_F16) ? 2 : 4;
+    if (p.n_groups == 0) {
+        rc = make_tmap(&to.m[0], p.out, p.M, p.N, kOutElem, 32);
+        if (rc != SDNQ_OK) return rc;
+    } else {
+        for (int g = 0; g < p.n_groups; ++g) {
+            SDNQ_REQUIRE(p.grp_start[g] % BN == 0, SDNQ_EINVAL, "grouped launch: segment %d starts at %d, not a multiple of the tile width %d", g, p.grp_start[g], BN);
+            rc = make_tmap(&to.m[g], p.grp_out[g], p.M, p.grp_n[g], kOutElem, 32);
+            if (rc != SDNQ_OK) return rc;
+        }
+    }
     CUtensorMap tl = ta, tu = ta;
     if (kSvd) {
         rc = make_tmap_svd(&tl, p.svd_low, p.M, p.svd_rank, BM);
@@ -810,10 +835,13 @@ int launch_gemm_out(const void* a, const void* b, const GemmParams& p, cudaStrea
 
 // Tile-N choice: the widest tile that still gives every SM work; BN=256 halves the per-MMA shared-memory
 // operand traffic relative to BN=128, so it wins whenever the grid is full either way.
-int pick_bn(int M, int N) {
+// seg_align != 0 (grouped launch): the segments of the concatenated operand start at multiples of seg_align (128 or 256), which
+// limits the tile width to its divisors.
+int pick_bn(int M, int N, int seg_align = 0) {
     const char* bn_env = getenv("SDNQ_B200_BN");      // tuning knob, read per call
     const int forced = bn_env ? atoi(bn_env) : 0;
-    if (forced == 128 || forced == 192 || forced == 256) return forced;
+    if (seg_align == 128) return 128;
+    if (forced == 128 || (forced == 192 && seg_align == 0) || forced == 256) return forced;
     const int sms = num_sms();
     const int num_m = (M + BM - 1) / BM;
     auto waves_eff = [&](int bn) {
@@ -822,12 +850,9 @@ int pick_bn(int M, int N) {
         return static_cast<double>(tiles) / (static_cast<double>(waves) * sms);
     };
     // relative per-tile efficiency of the narrower tiles (shared-memory operand traffic per MMA grows as BN shrinks)
-    const double e256 = waves_eff(256) * 1.00, e192 = waves_eff(192) * 0.94, e128 = waves_eff(128) * 0.90, e64 = waves_eff(64) * 0.70;
-    if (N <= 64) return 64;
-    if (e256 >= e192 && e256 >= e128 && e256 >= e64) return 256;
-    if (e192 >= e128 && e192 >= e64) return 192;
-    if (e128 >= e64) return 128;
-    return 64;
+    const double e256 = waves_eff(256) * 1.00, e192 = seg_align != 0 ? 0.0 : waves_eff(192) * 0.94, e128 = waves_eff(128) * 0.90;
+    if (e256 >= e192 && e256 >= e128) return 256;
+    return e192 >= e128 ? 192 : 128;
 }
 
 // CTA pairs (tcgen05 cta_group::2): 0 = use single-CTA MMAs, else the tile width.  SDNQ_B200_CG=1 / 2 forces the choice.
@@ -835,6 +860,8 @@ int pick_pair(const GemmParams& p) {
     const char* cg_env = getenv("SDNQ_B200_CG");      // read per call: tests and A/B tools flip it inside one process
     const int forced = cg_env ? atoi(cg_env) : 0;
     if (forced == 1 || p.raw || (p.out_dtype != SDNQ_BF16 && p.out_dtype != SDNQ_F16) || p.M <= BM) return 0;
+    for (int g = 1; g <= p.n_groups; ++g)
+        if (p.grp_start[g] % 256 != 0) return 0;                          // grouped segments on a 128 grid: 128-wide single-CTA tiles
     const char* bn_env = getenv("SDNQ_B200_BN");
     const int forced_bn = bn_env ? atoi(bn_env) : 0;
     const int pairs = num_sms() / 2;
@@ -899,7 +926,13 @@ int scaled_mm_impl(const void* a, const void* b, int ab_dtype, GemmParams p, cud
         if (pair_bn == 256) return i8 ? launch_gemm_pair<256, true>(a, b, p, st) : launch_gemm_pair<256, false>(a, b, p, st);
         return i8 ? launch_gemm_pair<128, true>(a, b, p, st) : launch_gemm_pair<128, false>(a, b, p, st);
     }
-    switch (pick_bn(p.M, p.N)) {
+    int seg_align = 0;
+    if (p.n_groups != 0) {
+        seg_align = 256;
+        for (int g = 0; g <= p.n_groups; ++g)
+            if (p.grp_start[g] % 256 != 0) seg_align = 128;
+    }
+    switch (pick_bn(p.M, p.N, seg_align)) {
         case 256: return i8 ? launch_gemm_out<256, true>(a, b, p, st) : launch_gemm_out<256, false>(a, b, p, st);
         case 192: return i8 ? launch_gemm_out<192, true>(a, b, p, st) : launch_gemm_out<192, false>(a, b, p, st);
         case 128: return i8 ? launch_gemm_out<128, true>(a, b, p, st) : launch_gemm_out<128, false>(a, b, p, st);
@@ -983,4 +1016,38 @@ extern "C" int sdnq_b200_scaled_mm_svd(const void* a, const void* b, int ab_dtyp
     GemmParams p{sx, sw, bias, bias_dtype, bias_ld, rowsum, zp, colsum, zx, out, out_dtype, (int)M, (int)N, (int)K, 0, w_sub,
                  ab_dtype == SDNQ_F8E5M2 ? 1u : 0u, svd_low, svd_up_nr, svd_rank, svd_dtype == SDNQ_BF16 ? 1u : 0u};
     return scaled_mm_impl(a, b, wbits == 4 ? SDNQ_I8 : ab_dtype, p, reinterpret_cast<cudaStream_t>(stream), wbits);
+}
+
+// ---- grouped scaled matmul: sibling projections (to_q / to_k / to_v ...) that read the same quantised activations, one launch
+extern "C" int sdnq_b200_scaled_mm_grouped(const void* a, const void* b_cat, int ab_dtype, const sdnq_weight_format* b_fmt, const float* sx,
+                                           const float* sw_cat, const void* bias_cat, int bias_dtype, const int32_t* rowsum, const float* zp_cat,
+                                           const int32_t* colsum_cat, const float* zx, int n_groups, const int64_t* seg_start, const int64_t* seg_n,
+                                           void* const* outs, int out_dtype, int64_t M, int64_t K, void* stream) {
+    SDNQ_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups, SDNQ_EUNSUPPORTED, "grouped launch: 1..%d siblings (got %d)", kMaxGroups, n_groups);
+    SDNQ_REQUIRE(seg_start && seg_n && outs, SDNQ_EINVAL, "NULL pointer");
+    SDNQ_REQUIRE(M < (1LL << 31) && K < (1LL << 31) && seg_start[n_groups] < (1LL << 31), SDNQ_EUNSUPPORTED, "dimension too large");
+    uint32_t w_sub = 0u;
+    int wbits = 8;
+    if (b_fmt != nullptr) {
+        SDNQ_REQUIRE(b_fmt->kind == SDNQ_W_INT && b_fmt->bits == 4, SDNQ_EUNSUPPORTED, "scaled_mm_grouped: packed weights must be int4 / uint4");
+        SDNQ_REQUIRE(b_fmt->is_unsigned == 0 || (zp_cat != nullptr && rowsum != nullptr), SDNQ_EINVAL, "uint4 weights need zp and rowsum");
+        w_sub = b_fmt->is_unsigned ? 0u : 0x08080808u;
+        wbits = 4;
+    }
+    GemmParams p{sx, sw_cat, bias_cat, bias_dtype, 0, rowsum, zp_cat, colsum_cat, zx, outs[0], out_dtype, (int)M, (int)seg_start[n_groups], (int)K, 0, w_sub,
+                 ab_dtype == SDNQ_F8E5M2 ? 1u : 0u};
+    p.n_groups = n_groups;
+    SDNQ_REQUIRE(seg_start[0] == 0, SDNQ_EINVAL, "grouped launch: the first segment starts at 0");
+    for (int g = 0; g < n_groups; ++g) {
+        SDNQ_REQUIRE(seg_n[g] > 0 && seg_n[g] % 8 == 0 && seg_start[g] % 128 == 0 && seg_start[g] + seg_n[g] <= seg_start[g + 1], SDNQ_EINVAL,
+                     "grouped launch: segment %d (start %lld, %lld rows) must start at a multiple of 128, hold a multiple of 8 rows and end before the next one",
+                     g, (long long)seg_start[g], (long long)seg_n[g]);
+        SDNQ_REQUIRE(outs[g] && (reinterpret_cast<uintptr_t>(outs[g]) & 15) == 0, SDNQ_EINVAL, "grouped launch: output %d is NULL or not 16-byte aligned", g);
+        p.grp_start[g] = (int)seg_start[g];
+        p.grp_n[g] = (int)seg_n[g];
+        p.grp_out[g] = outs[g];
+    }
+    SDNQ_REQUIRE(seg_start[n_groups] % 128 == 0, SDNQ_EINVAL, "grouped launch: the concatenated operand must end at a multiple of 128 rows");
+    p.grp_start[n_groups] = (int)seg_start[n_groups];
+    return scaled_mm_impl(a, b_cat, wbits == 4 ? SDNQ_I8 : ab_dtype, p, reinterpret_cast<cudaStream_t>(stream), wbits);
 }

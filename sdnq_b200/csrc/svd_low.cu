@@ -45,36 +45,55 @@ __global__ void __launch_bounds__(kThreads) svd_low_kernel(const LowArgs a) {
     float acc[kMaxNT][4];
 #pragma unroll
     for (int j = 0; j < kMaxNT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-    for (int s = warp; s < steps; s += kWarps) {
+    // one step = 64 columns of K: per lane 2 x 16 B of each of its two x rows and 2 x 16 B of each svd_down row it feeds.  The loads of
+    // step s + kWarps are issued before the MMAs of step s (register double buffer): a warp walks K / 512 dependent steps, and
+    // without the prefetch every one of them exposes a full L2 round trip.
+    struct Frag { uint4 xl0, xl1, xh0, xh1, d0[kMaxNT], d1[kMaxNT]; };
+    auto load = [&](int s, Frag& f) {
         const int k = s * 64 + 16 * t;
-        const bool live = k < a.K;                      // K % 16 == 0: a lane's 16 columns are all inside or all outside
-        uint4 xl0 = make_uint4(0u, 0u, 0u, 0u), xl1 = xl0, xh0 = xl0, xh1 = xl0;
+        const bool live = s < steps && k < a.K;          // K % 16 == 0: a lane's 16 columns are all inside or all outside
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        f.xl0 = f.xl1 = f.xh0 = f.xh1 = z;
         if (live && lo_ok) {
             const T* p = x + int64_t(row_lo) * a.ldx + k;
-            xl0 = *reinterpret_cast<const uint4*>(p);
-            xl1 = *reinterpret_cast<const uint4*>(p + 8);
+            f.xl0 = *reinterpret_cast<const uint4*>(p);
+            f.xl1 = *reinterpret_cast<const uint4*>(p + 8);
         }
         if (live && hi_ok) {
             const T* p = x + int64_t(row_hi) * a.ldx + k;
-            xh0 = *reinterpret_cast<const uint4*>(p);
-            xh1 = *reinterpret_cast<const uint4*>(p + 8);
+            f.xh0 = *reinterpret_cast<const uint4*>(p);
+            f.xh1 = *reinterpret_cast<const uint4*>(p + 8);
         }
 #pragma unroll
         for (int j = 0; j < kMaxNT; ++j) {
-            if (j < nt) {
-                uint4 d0 = make_uint4(0u, 0u, 0u, 0u), d1 = d0;
-                if (live) {
-                    const T* p = down + int64_t(8 * j + g) * a.K + k;      // B fragment: column n = g of this 8-column block
-                    d0 = *reinterpret_cast<const uint4*>(p);
-                    d1 = *reinterpret_cast<const uint4*>(p + 8);
-                }
-                // MMA i contracts the lane's elements [4i, 4i+4): slots (2t, 2t+1) <- elements 4i, 4i+1; (2t+8, 2t+9) <- 4i+2, 4i+3
-                hadtc::Half16<T>::mma(acc[j], xl0.x, xh0.x, xl0.y, xh0.y, d0.x, d0.y);
-                hadtc::Half16<T>::mma(acc[j], xl0.z, xh0.z, xl0.w, xh0.w, d0.z, d0.w);
-                hadtc::Half16<T>::mma(acc[j], xl1.x, xh1.x, xl1.y, xh1.y, d1.x, d1.y);
-                hadtc::Half16<T>::mma(acc[j], xl1.z, xh1.z, xl1.w, xh1.w, d1.z, d1.w);
+            f.d0[j] = f.d1[j] = z;
+            if (j < nt && live) {
+                const T* p = down + int64_t(8 * j + g) * a.K + k;      // B fragment: column n = g of this 8-column block
+                f.d0[j] = *reinterpret_cast<const uint4*>(p);
+                f.d1[j] = *reinterpret_cast<const uint4*>(p + 8);
             }
         }
+    };
+    auto contract = [&](const Frag& f) {
+#pragma unroll
+        for (int j = 0; j < kMaxNT; ++j) {
+            if (j < nt) {
+                // MMA i contracts the lane's elements [4i, 4i+4): slots (2t, 2t+1) <- elements 4i, 4i+1; (2t+8, 2t+9) <- 4i+2, 4i+3
+                hadtc::Half16<T>::mma(acc[j], f.xl0.x, f.xh0.x, f.xl0.y, f.xh0.y, f.d0[j].x, f.d0[j].y);
+                hadtc::Half16<T>::mma(acc[j], f.xl0.z, f.xh0.z, f.xl0.w, f.xh0.w, f.d0[j].z, f.d0[j].w);
+                hadtc::Half16<T>::mma(acc[j], f.xl1.x, f.xh1.x, f.xl1.y, f.xh1.y, f.d1[j].x, f.d1[j].y);
+                hadtc::Half16<T>::mma(acc[j], f.xl1.z, f.xh1.z, f.xl1.w, f.xh1.w, f.d1[j].z, f.d1[j].w);
+            }
+        }
+    };
+    Frag fa, fb;
+    load(warp, fa);
+    for (int s = warp; s < steps; s += 2 * kWarps) {
+        load(s + kWarps, fb);
+        contract(fa);
+        if (s + kWarps >= steps) break;
+        load(s + 2 * kWarps, fa);
+        contract(fb);
     }
     // ---- add the K-split partials up in warp 0
     if (warp > 0) {

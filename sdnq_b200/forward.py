@@ -17,7 +17,7 @@ from collections.abc import Callable
 
 import torch
 
-from . import ops
+from . import ops, siblings
 from .common import conv_transpose_types, conv_types, dtype_dict, embedding_types
 
 SMALL_M = 32     # rows below this use the dequant path, as upstream does (linear_int8.py:102-103)
@@ -395,6 +395,11 @@ def _w8a8_forward(self, input: torch.Tensor) -> torch.Tensor:
     hg = d.hadamard_group_size if d.use_hadamard else 0
     x2 = _rows(input)
     if self.svd_up is None:
+        group = self.__dict__.get("_sdnq_siblings")
+        if group is not None and siblings.siblings_enabled():      # to_q / to_k / to_v ...: one K2 + one grouped K1 launch for all of them
+            out = group.forward(self, x2, input.dtype)
+            if out is not None:
+                return out.view(*input.shape[:-1], out.shape[-1])
         if op.packed is None and not _act_cache_on():       # one C call: K2 into the per-stream workspace + K1
             return ops.linear_w8a8(input, op.wq, mm, op.sw, bias=self.bias, zp=op.zp, colsum=op.colsum, hadamard_group=hg, out_dtype=input.dtype)
         xq, sx, zx, rowsum, _ = quantized_activations(x2, mm, hg, op.zp is not None, False)

@@ -364,6 +364,33 @@ def scaled_mm_svd(a: torch.Tensor, b: torch.Tensor, sx, sw, low: torch.Tensor, s
     return out
 
 
+def scaled_mm_grouped(a: torch.Tensor, b_cat: torch.Tensor, sx, sw_cat, starts, ns, bias_cat=None, out_dtype: torch.dtype = torch.bfloat16,
+                      rowsum=None, zp=None, colsum=None, zx=None, packed_dtype: str | None = None) -> list:
+    """K1 over sibling projections in one launch.  a [M,K] codes; b_cat the siblings' [N_g,K] operands (or packed int4 / uint4 rows)
+    stacked, segment g at rows starts[g] .. starts[g] + ns[g] (starts has len(ns) + 1 entries, multiples of 128); per-channel
+    vectors laid out the same way.  Returns one contiguous [M, ns[g]] tensor per sibling."""
+    import ctypes
+    _require_cuda(a, b_cat)
+    M, K = a.shape
+    G = len(ns)
+    assert a.is_contiguous() and b_cat.is_contiguous() and len(starts) == G + 1 and b_cat.shape[0] == starts[-1]
+    outs = [torch.empty((M, n), dtype=out_dtype, device=a.device) for n in ns]
+    if packed_dtype is None:
+        assert b_cat.shape[1] == K
+        ab, fmt = _operand_code(a.dtype, b_cat), None
+    else:
+        ab, fmt = SDNQ_I8, weight_format(packed_dtype, b_cat)
+    bias_code = dtype_code(bias_cat.dtype) if bias_cat is not None else SDNQ_F32
+    starts_c = (ctypes.c_int64 * (G + 1))(*[int(v) for v in starts])
+    ns_c = (ctypes.c_int64 * G)(*[int(v) for v in ns])
+    outs_c = (ctypes.c_void_p * G)(*[o.data_ptr() for o in outs])
+    with torch.cuda.device(a.device):
+        check(_lib.load().sdnq_b200_scaled_mm_grouped(_ptr(a), _ptr(b_cat), ab, fmt, _ptr(sx), _ptr(sw_cat), _ptr(bias_cat), bias_code,
+                                                      _ptr(rowsum), _ptr(zp), _ptr(colsum), _ptr(zx), G, starts_c, ns_c, outs_c,
+                                                      dtype_code(out_dtype), M, K, _stream(a)))
+    return outs
+
+
 def mm(a: torch.Tensor, b_nk: torch.Tensor) -> torch.Tensor:
     """plain int8 -> int32 / fp8 -> f32 matmul (int_mm_func / fp8_mm_func)."""
     _require_cuda(a, b_nk)

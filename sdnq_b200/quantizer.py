@@ -383,4 +383,6 @@ def sdnq_post_load_quant(model: torch.nn.Module, *args, torch_dtype: torch.dtype
         except Exception:
             pass
     model.quantization_method = QuantizationMethod.SDNQ
+    from .siblings import fuse_sibling_projections
+    fuse_sibling_projections(model)          # to_q / to_k / to_v ...: registered now, their shared operand is built at the first forward
     return model

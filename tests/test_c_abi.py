@@ -124,7 +124,7 @@ def _ctype_of(c_type):
     from sdnq_b200._lib import Conv2dGeometry, WeightFormat
     table = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t, "constchar*": ctypes.c_char_p,
              "constsdnq_weight_format*": ctypes.POINTER(WeightFormat), "constsdnq_conv2d_geometry*": ctypes.POINTER(Conv2dGeometry),
-             "constint64_t*": ctypes.POINTER(ctypes.c_int64)}
+             "constint64_t*": ctypes.POINTER(ctypes.c_int64), "void*const*": ctypes.POINTER(ctypes.c_void_p)}
     if c_type in table:
         return table[c_type]
     assert c_type.endswith("*"), f"unmapped C type {c_type!r}"

@@ -331,3 +331,46 @@ def test_no_cpu_fallback_anywhere_on_the_forward(cfg, rows):
         layer(torch.randn(rows, 64, dtype=torch.bfloat16))
     with pytest.raises(SDNQKernelError, match="CUDA"):
         layer.dequantize()
+
+
+# ------------------------------------------------------------------------------------------------ sibling groups (registration only: no kernels)
+def test_sibling_projections_are_found_by_name():
+    import torch
+
+    from sdnq_b200 import SDNQConfig, fuse_named_siblings, sdnq_post_load_quant
+
+    class Attention(torch.nn.Module):
+        def __init__(self, dim, ctx=None):
+            super().__init__()
+            self.is_cross_attention = ctx is not None
+            self.to_q = torch.nn.Linear(dim, dim)
+            self.to_k = torch.nn.Linear(ctx or dim, dim)
+            self.to_v = torch.nn.Linear(ctx or dim, dim)
+            self.to_out = torch.nn.ModuleList([torch.nn.Linear(dim, dim)])
+
+    class Block(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.attn1 = Attention(128)
+            self.attn2 = Attention(128, ctx=256)
+            self.attn3 = Attention(128, ctx=128)          # cross-attention whose context is as wide as the hidden states
+
+    model = torch.nn.Sequential(Block(), Block()).to(torch.bfloat16)
+    model = sdnq_post_load_quant(model, weights_dtype="int8", use_quantized_matmul=True, add_skip_keys=False)
+    for blk in model:
+        g1 = blk.attn1.to_q.__dict__["_sdnq_siblings"]
+        assert [id(m) for m in g1.layers] == [id(blk.attn1.to_q), id(blk.attn1.to_k), id(blk.attn1.to_v)]
+        g2 = blk.attn2.to_k.__dict__["_sdnq_siblings"]
+        assert [id(m) for m in g2.layers] == [id(blk.attn2.to_k), id(blk.attn2.to_v)] and "_sdnq_siblings" not in blk.attn2.to_q.__dict__
+        g3 = blk.attn3.to_k.__dict__["_sdnq_siblings"]
+        assert len(g3.layers) == 2 and "_sdnq_siblings" not in blk.attn3.to_q.__dict__
+        assert "_sdnq_siblings" not in blk.attn1.to_out[0].__dict__
+    # flat (name, layer) lists; pooling the cross-attention pairs of several blocks
+    named = [(n, m) for n, m in model.named_modules() if m.__class__.__name__ == "SDNQLinear"]
+    assert fuse_named_siblings(named) == 6
+    assert fuse_named_siblings(named, cross_attention_pool=8) == 2 + 1 + 2          # attn1 x2, pooled attn2 (4 layers); by name alone attn3 looks like self-attention
+    pooled = model[0].attn2.to_k.__dict__["_sdnq_siblings"]
+    assert len(pooled.layers) == 4 and model[1].attn2.to_v.__dict__["_sdnq_siblings"] is pooled
+    # layers on the dequant path never join a group
+    plain = sdnq_post_load_quant(torch.nn.Sequential(Block()).to(torch.bfloat16), weights_dtype="int8", use_quantized_matmul=False, add_skip_keys=False)
+    assert all("_sdnq_siblings" not in m.__dict__ for m in plain.modules())

@@ -568,6 +568,67 @@ def test_scaled_mm_svd(kind, M, N, K, r):
     assert np.all(np.abs(got_nb - ref_nb) <= np.maximum(np.abs(ref_nb), 1e-3) * 2.0 ** -8 + mag * 2e-6 + (mag * 3e-3 if kind == "fp8" else 0))
 
 
+# ----------------------------------------------------------------------------------------------- grouped launch (sibling projections)
+@pytest.mark.parametrize("kind", ["int8", "int8_zp", "fp8", "uint8", "int4", "uint4"])
+@pytest.mark.parametrize("M,K,ns,align", [(1024, 1280, (1280, 1280, 1280), 256), (4096, 640, (640, 640, 640), 128), (77, 2048, (1280, 1280), 256),
+                                          (77, 2048, (640, 640), 128), (300, 384, (136, 1288, 8, 520), 128), (2048, 256, (3072, 3072, 3072, 12288), 256),
+                                          (130, 512, (256,) * 8, 256), (33, 64, (512, 256), 128)])
+def test_scaled_mm_grouped_equals_separate_launches(kind, M, K, ns, align):
+    """one grouped launch over the stacked sibling operands == every sibling's own scaled_mm, bit for bit."""
+    rng = np.random.default_rng(M + K + sum(ns) + len(kind))
+    packed = kind in ("int4", "uint4")
+    if packed and align == 256:
+        align = 128
+    starts = [0]
+    for n in ns:
+        starts.append(starts[-1] + (n + align - 1) // align * align)
+    Nt = starts[-1]
+    sx = torch.from_numpy((rng.random(M) * 0.05 + 1e-3).astype(np.float32)).to(DEV)
+    sw = torch.zeros(Nt)
+    bias = torch.zeros(Nt)
+    zp = torch.zeros(Nt)
+    colsum = torch.zeros(Nt, dtype=torch.int32)
+    if kind == "fp8":
+        a = torch.from_numpy(rng.standard_normal((M, K)).astype(np.float32)).to(torch.float8_e4m3fn).to(DEV)
+        b = torch.zeros((Nt, K), dtype=torch.float8_e4m3fn)
+    elif packed:
+        a = torch.from_numpy(rng.integers(-128, 128, size=(M, K)).astype(np.int8)).to(DEV)
+        b = torch.zeros((Nt, K // 2), dtype=torch.uint8)
+    else:
+        a = torch.from_numpy(rng.integers(-128, 128, size=(M, K)).astype(np.int8)).to(DEV)
+        b = torch.zeros((Nt, K), dtype=torch.int8)
+    for s, n in zip(starts, ns):
+        if kind == "fp8":
+            b[s:s + n] = torch.from_numpy(rng.standard_normal((n, K)).astype(np.float32)).to(torch.float8_e4m3fn)
+        elif packed:
+            b[s:s + n] = torch.from_numpy(rng.integers(0, 256, size=(n, K // 2)).astype(np.uint8))
+        else:
+            b[s:s + n] = torch.from_numpy(rng.integers(-128, 128, size=(n, K)).astype(np.int8))
+            colsum[s:s + n] = b[s:s + n].to(torch.int32).sum(dim=1, dtype=torch.int32)
+        sw[s:s + n] = torch.from_numpy((rng.random(n) * 0.01 + 1e-4).astype(np.float32))
+        bias[s:s + n] = torch.from_numpy(rng.standard_normal(n).astype(np.float32))
+        zp[s:s + n] = torch.from_numpy((rng.standard_normal(n) * 0.1).astype(np.float32))
+    b, sw, bias, zp, colsum = b.to(DEV), sw.to(DEV), bias.to(DEV), zp.to(DEV), colsum.to(DEV)
+    kw = {}
+    if kind in ("int8_zp", "uint8", "uint4"):
+        kw.update(zp=zp, rowsum=a.to(torch.int32).sum(dim=1, dtype=torch.int32))
+    if kind == "uint8":
+        kw.update(zx=torch.from_numpy((rng.standard_normal(M) * 0.1).astype(np.float32)).to(DEV), colsum=colsum)
+    pk = kind if packed else None
+    for out_dtype in (torch.bfloat16, torch.float32):
+        outs = ops().scaled_mm_grouped(a, b, sx, sw, starts, list(ns), bias, out_dtype, packed_dtype=pk, **kw)
+        assert len(outs) == len(ns)
+        for g, (s, n) in enumerate(zip(starts, ns)):
+            sub = {k: (v[s:s + n] if k in ("zp", "colsum") else v) for k, v in kw.items()}
+            if packed:
+                sub.pop("colsum", None)
+                one = ops().scaled_mm_packed(a, b[s:s + n].contiguous(), kind, n, sx, sw[s:s + n], bias[s:s + n], out_dtype, **sub)
+            else:
+                one = ops().scaled_mm(a, b[s:s + n].contiguous(), sx, sw[s:s + n], bias[s:s + n], out_dtype, **sub)
+            assert outs[g].shape == (M, n) and outs[g].is_contiguous()
+            assert torch.equal(outs[g], one), (g, float((outs[g].float() - one.float()).abs().max()))
+
+
 # ----------------------------------------------------------------------------------------------- fused quantise + GEMM (one launch)
 FUSED_SHAPES = [(1024, 1280, 1280), (4096, 640, 640), (77, 1280, 2048), (333, 136, 272), (1, 64, 32), (32, 8, 16), (128 * 5 + 7, 648, 5120),
                 (2500, 256, 4096 + 16), (148 * 2 + 1, 384, 16384)]

@@ -1,0 +1,112 @@
+"""Sibling projections as one grouped launch (sdnq_b200/siblings.py): bit-identical to the layers' own forwards, and safe when the
+guess about shared inputs is wrong."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+CONFIGS = {
+    "int8": dict(weights_dtype="int8", use_quantized_matmul=True),
+    "uint8": dict(weights_dtype="uint8", use_quantized_matmul=True),
+    "fp8_hadamard": dict(weights_dtype="float8_e4m3fn", use_quantized_matmul=True, use_hadamard=True, hadamard_group_size=128),
+    "int4_rowwise": dict(weights_dtype="int4", use_quantized_matmul=True, group_size=-1),
+    "uint4_g64": dict(weights_dtype="uint4", use_quantized_matmul=True, group_size=64),
+    "int6": dict(weights_dtype="int6", use_quantized_matmul=True),
+}
+
+
+def make_layers(cfg, K, ns, bias=True, seed=0):
+    from sdnq_b200 import SDNQConfig, sdnq_quantize_layer
+    torch.manual_seed(seed)
+    out = []
+    for n in ns:
+        lin = torch.nn.Linear(K, n, bias=bias).to(torch.bfloat16)
+        layer, _ = sdnq_quantize_layer(lin, SDNQConfig(**CONFIGS[cfg]))
+        out.append(layer.to(DEV))
+    return out
+
+
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+@pytest.mark.parametrize("M,K,ns", [(1024, 1280, (1280, 1280, 1280)), (77, 2048, (640, 640)), (300, 384, (256, 136, 520))])
+def test_grouped_forward_is_bit_identical(cfg, M, K, ns, monkeypatch):
+    from sdnq_b200 import group_siblings
+    layers = make_layers(cfg, K, ns)
+    x = torch.randn(2, M // 2, K, device=DEV, dtype=torch.bfloat16)
+    monkeypatch.setenv("SDNQ_B200_SIBLINGS", "0")
+    ref = [layer(x) for layer in layers]
+    monkeypatch.setenv("SDNQ_B200_SIBLINGS", "1")
+    group = group_siblings(layers)
+    assert group is not None
+    from sdnq_b200 import _lib
+    _lib.launch_count(reset=True)
+    got = [layer(x) for layer in layers]
+    launches = _lib.launch_count()
+    assert launches == 2, launches                       # one K2 + one grouped K1 for all siblings
+    for g, r in zip(got, ref):
+        assert g.shape == r.shape and g.is_contiguous() and torch.equal(g, r)
+    # a second round with a new tensor, called in another order
+    x2 = torch.randn(M, K, device=DEV, dtype=torch.bfloat16)
+    monkeypatch.setenv("SDNQ_B200_SIBLINGS", "0")
+    ref2 = [layer(x2) for layer in layers]
+    monkeypatch.setenv("SDNQ_B200_SIBLINGS", "1")
+    got2 = [layers[i](x2) for i in reversed(range(len(layers)))][::-1]
+    for g, r in zip(got2, ref2):
+        assert torch.equal(g, r)
+
+
+def test_wrong_guess_about_shared_inputs_is_only_slower(monkeypatch):
+    """to_q is fed the hidden states, to_k / to_v something else of the same width; inputs edited in place between calls."""
+    from sdnq_b200 import group_siblings
+    layers = make_layers("int8", 640, (640, 640, 640))
+    xa = torch.randn(256, 640, device=DEV, dtype=torch.bfloat16)
+    xb = torch.randn(256, 640, device=DEV, dtype=torch.bfloat16)
+    monkeypatch.setenv("SDNQ_B200_SIBLINGS", "0")
+    ref = [layers[0](xa), layers[1](xb), layers[2](xb)]
+    xa2 = xa * 2
+    ref_edit = layers[1](xa2)
+    monkeypatch.setenv("SDNQ_B200_SIBLINGS", "1")
+    assert group_siblings(layers) is not None
+    got = [layers[0](xa), layers[1](xb), layers[2](xb)]
+    for g, r in zip(got, ref):
+        assert torch.equal(g, r)
+    q = layers[0](xa)
+    xa.mul_(2)                                           # same storage, new version: the pending k / v results must not be served
+    assert torch.equal(layers[1](xa), ref_edit)
+    assert torch.equal(q, ref[0])
+    # small-M calls (rows < 32) bypass the group
+    xs = torch.randn(4, 640, device=DEV, dtype=torch.bfloat16)
+    monkeypatch.setenv("SDNQ_B200_SIBLINGS", "0")
+    r_small = layers[2](xs)
+    monkeypatch.setenv("SDNQ_B200_SIBLINGS", "1")
+    assert torch.equal(layers[2](xs), r_small)
+
+
+def test_group_follows_weight_replacement_and_graph_capture(monkeypatch):
+    from sdnq_b200 import group_siblings
+    layers = make_layers("int8", 1280, (1280, 1280))
+    assert group_siblings(layers) is not None
+    x = torch.randn(512, 1280, device=DEV, dtype=torch.bfloat16)
+    y0 = [layer(x) for layer in layers]
+    # replace one sibling's weight (what load_state_dict(assign=True) does): the shared operand is rebuilt
+    other = make_layers("int8", 1280, (1280,), seed=7)[0]
+    layers[1].weight = other.weight
+    layers[1].scale = other.scale
+    y1 = [layer(x) for layer in layers]
+    assert torch.equal(y1[0], y0[0]) and torch.equal(y1[1], other(x)) and not torch.equal(y1[1], y0[1])
+    # captured: both launches are in the graph, replay reproduces the eager result for new input contents
+    static_x = torch.randn(512, 1280, device=DEV, dtype=torch.bfloat16)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        [layer(static_x) for layer in layers]
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        outs = [layer(static_x) for layer in layers]
+    static_x.copy_(x)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], y1[0]) and torch.equal(outs[1], y1[1])
