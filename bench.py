@@ -746,9 +746,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=None, help=f"one of {sorted(WORKLOADS)}; default: {HEADLINE} with {list(NESTED)} nested under 'workloads'")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "gpu_reference"])
-    ap.add_argument("--siblings", default="block", choices=["off", "block", "pool"],
-                    help="grouped launches for sibling projections: per attention block (what sdnq_post_load_quant registers), "
-                         "'pool' also pools the cross-attention to_k / to_v pairs of 4 blocks that read the same encoder states")
+    ap.add_argument("--siblings", default="pool", choices=["off", "block", "pool"],
+                    help="grouped launches for sibling projections.  pool (what sdnq_post_load_quant registers): per attention block, and the "
+                         "cross-attention to_k / to_v pairs of 4 blocks that read the same encoder states in one launch; block: per block only")
     ap.add_argument("--no-nested", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")

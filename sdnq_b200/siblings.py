@@ -23,6 +23,7 @@ import torch
 from . import ops
 
 MAX_GROUP = 8            # siblings per launch (output tensor maps in the kernel's parameter block)
+_WASTE_LIMIT = 3         # consecutive launches with mostly unused outputs before a group is dissolved
 _REBUILD_LIMIT = 4       # a group whose stored tensors keep changing (CPU offload re-uploads them every step) is dissolved
 
 # children of one parent module that are fed the same tensor
@@ -58,6 +59,7 @@ class SiblingGroup:
         self.state = None            # (per-layer matmul operands the buffers were built from, buffers...)
         self.cache = None            # (key, input kept alive, outputs not yet handed out)
         self.rebuilds = 0
+        self.wasted = 0              # consecutive launches at least half of whose outputs were never picked up
         self.dead = False
 
     # ---- the concatenated operand -------------------------------------------------------------------------------------------
@@ -162,6 +164,14 @@ class SiblingGroup:
         outs = ops.scaled_mm_grouped(xq, st["wq"], sx, st["sw"], st["starts"], st["ns"], st["bias"], out_dtype, rowsum=rowsum, zp=st["zp"],
                                      colsum=st["colsum"], zx=zx, packed_dtype=st["packed"])
         y, outs[idx] = outs[idx], None
+        if c is not None:
+            # results of the previous launch that nobody asked for: the siblings are not fed the same tensor after all.  A group that
+            # keeps computing outputs for nothing is dissolved (its members go back to their own launches).
+            unused = sum(o is not None for o in c[2])
+            self.wasted = self.wasted + 1 if 2 * unused >= len(self.layers) else 0
+            if self.wasted > _WASTE_LIMIT:
+                self.dissolve()
+                return y
         self.cache = (key, x2, outs)
         return y
 
@@ -203,43 +213,54 @@ def _family_groups(children: dict):
             yield mods
 
 
-def fuse_sibling_projections(model: torch.nn.Module) -> int:
-    """Find sibling projections by their Diffusers / Transformers names under every parent module and register them as groups.
-    A cross-attention block whose to_q has the same input width as its to_k / to_v cannot be told apart from self-attention by
-    shape: it is recognised by the parent's `is_cross_attention` / `cross_attention_dim` attributes and only its to_k / to_v pair."""
-    count = 0
-    for parent in model.modules():
-        children = dict(parent.named_children())
-        cross = bool(getattr(parent, "is_cross_attention", False))
-        if cross:
-            children = {k: v for k, v in children.items() if k not in ("to_q", "q_proj", "query")}
-        for mods in _family_groups(children):
-            if group_siblings(mods) is not None:
+def _register(families, cross_attention_pool: int) -> int:
+    """families: lists of modules that share an input, in model order.  to_k / to_v style pairs whose input width differs from what
+    their block's query projection reads -- cross-attention: every such block of a UNet / DiT is handed the same
+    encoder_hidden_states tensor -- are pooled over up to cross_attention_pool layers of *different* blocks."""
+    count, pools = 0, {}
+    for mods, cross in families:
+        if cross and cross_attention_pool >= 4:
+            pools.setdefault(_signature(mods[0]), []).append(mods)
+        elif group_siblings(mods) is not None:
+            count += 1
+    per_group = max(1, min(cross_attention_pool, MAX_GROUP) // 2)
+    for pairs in pools.values():
+        for i in range(0, len(pairs), per_group):
+            if group_siblings([m for pair in pairs[i:i + per_group] for m in pair]) is not None:
                 count += 1
     return count
 
 
-def fuse_named_siblings(named_layers, cross_attention_pool: int = 0) -> int:
-    """The same for a flat list of (qualified name, layer) pairs.  cross_attention_pool > 0 additionally pools the to_k / to_v pairs
-    of up to that many *different* cross-attention blocks whose inputs have the same width into one group (every cross-attention
-    block of a UNet / DiT is handed the same encoder_hidden_states tensor)."""
+def _families(children: dict, cross_flag: bool):
+    """(modules, is_cross_attention_pair) for one parent's children."""
+    if cross_flag:
+        children = {k: v for k, v in children.items() if k not in ("to_q", "q_proj", "query")}
+    for mods in _family_groups(children):
+        q = next((children[n] for n in ("to_q", "q_proj", "query") if n in children and _eligible(children[n])), None)
+        cross = len(mods) == 2 and (cross_flag or (q is not None and q not in mods and _signature(q) != _signature(mods[0])))
+        yield mods, cross
+
+
+def fuse_sibling_projections(model: torch.nn.Module, cross_attention_pool: int = MAX_GROUP) -> int:
+    """Find sibling projections by their Diffusers / Transformers names under every parent module and register them as groups.
+    A cross-attention block whose to_q has the same input width as its to_k / to_v cannot be told apart from self-attention by
+    shape: it is recognised by the parent's `is_cross_attention` attribute.  Cross-attention to_k / to_v pairs are pooled over
+    cross_attention_pool layers (0: one group per block).  Wrong guesses cost time only, and a group whose results keep going
+    unused dissolves itself."""
+    fams = []
+    for parent in model.modules():
+        fams += list(_families(dict(parent.named_children()), bool(getattr(parent, "is_cross_attention", False))))
+    return _register(fams, cross_attention_pool)
+
+
+def fuse_named_siblings(named_layers, cross_attention_pool: int = MAX_GROUP) -> int:
+    """The same for a flat list of (qualified name, layer) pairs (no module attributes to look at: cross-attention is recognised
+    by the input width of to_k / to_v differing from to_q's)."""
     parents: dict = {}
     for name, layer in named_layers:
         parent, _, leaf = name.rpartition(".")
         parents.setdefault(parent, {})[leaf] = layer
-    count = 0
-    pools: dict = {}
-    for parent, children in parents.items():
-        for mods in _family_groups(children):
-            pair = len(mods) == 2 and cross_attention_pool > 1
-            if pair:
-                pools.setdefault(_signature(mods[0]), []).append(mods)
-            elif group_siblings(mods) is not None:
-                count += 1
-    per_group = max(1, min(cross_attention_pool, MAX_GROUP) // 2)
-    for pairs in pools.values():
-        for i in range(0, len(pairs), per_group):
-            mods = [m for pair in pairs[i:i + per_group] for m in pair]
-            if group_siblings(mods) is not None:
-                count += 1
-    return count
+    fams = []
+    for children in parents.values():
+        fams += list(_families(children, False))
+    return _register(fams, cross_attention_pool)

@@ -360,15 +360,21 @@ def test_sibling_projections_are_found_by_name():
     for blk in model:
         g1 = blk.attn1.to_q.__dict__["_sdnq_siblings"]
         assert [id(m) for m in g1.layers] == [id(blk.attn1.to_q), id(blk.attn1.to_k), id(blk.attn1.to_v)]
-        g2 = blk.attn2.to_k.__dict__["_sdnq_siblings"]
-        assert [id(m) for m in g2.layers] == [id(blk.attn2.to_k), id(blk.attn2.to_v)] and "_sdnq_siblings" not in blk.attn2.to_q.__dict__
-        g3 = blk.attn3.to_k.__dict__["_sdnq_siblings"]
-        assert len(g3.layers) == 2 and "_sdnq_siblings" not in blk.attn3.to_q.__dict__
+        assert "_sdnq_siblings" not in blk.attn2.to_q.__dict__ and "_sdnq_siblings" not in blk.attn3.to_q.__dict__
         assert "_sdnq_siblings" not in blk.attn1.to_out[0].__dict__
-    # flat (name, layer) lists; pooling the cross-attention pairs of several blocks
+    # cross-attention to_k / to_v: pooled over the blocks (every block is handed the same encoder states)
+    for name in ("attn2", "attn3"):
+        pooled = getattr(model[0], name).to_k.__dict__["_sdnq_siblings"]
+        assert [id(m) for m in pooled.layers] == [id(getattr(b, name).__getattr__(p)) for b in model for p in ("to_k", "to_v")]
+    # one group per block instead
+    from sdnq_b200 import fuse_sibling_projections
+    assert fuse_sibling_projections(model, cross_attention_pool=0) == 6
+    g2 = model[1].attn2.to_k.__dict__["_sdnq_siblings"]
+    assert [id(m) for m in g2.layers] == [id(model[1].attn2.to_k), id(model[1].attn2.to_v)]
+    # flat (name, layer) lists: no module attributes, cross-attention is recognised by the input width alone
     named = [(n, m) for n, m in model.named_modules() if m.__class__.__name__ == "SDNQLinear"]
-    assert fuse_named_siblings(named) == 6
-    assert fuse_named_siblings(named, cross_attention_pool=8) == 2 + 1 + 2          # attn1 x2, pooled attn2 (4 layers); by name alone attn3 looks like self-attention
+    assert fuse_named_siblings(named, cross_attention_pool=0) == 6
+    assert fuse_named_siblings(named) == 2 + 1 + 2          # attn1 x2, pooled attn2 (4 layers); by name and width attn3 looks like self-attention
     pooled = model[0].attn2.to_k.__dict__["_sdnq_siblings"]
     assert len(pooled.layers) == 4 and model[1].attn2.to_v.__dict__["_sdnq_siblings"] is pooled
     # layers on the dequant path never join a group

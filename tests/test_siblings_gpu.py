@@ -36,11 +36,12 @@ def test_grouped_forward_is_bit_identical(cfg, M, K, ns, monkeypatch):
     layers = make_layers(cfg, K, ns)
     x = torch.randn(2, M // 2, K, device=DEV, dtype=torch.bfloat16)
     monkeypatch.setenv("SDNQ_B200_SIBLINGS", "0")
-    ref = [layer(x) for layer in layers]
+    ref = [layer(x.clone()) for layer in layers]
     monkeypatch.setenv("SDNQ_B200_SIBLINGS", "1")
     group = group_siblings(layers)
     assert group is not None
     from sdnq_b200 import _lib
+    layers[0](x.clone())                                 # builds the stacked operand (copies: not counted below)
     _lib.launch_count(reset=True)
     got = [layer(x) for layer in layers]
     launches = _lib.launch_count()
@@ -110,3 +111,18 @@ def test_group_follows_weight_replacement_and_graph_capture(monkeypatch):
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(outs[0], y1[0]) and torch.equal(outs[1], y1[1])
+
+
+def test_group_with_unused_results_dissolves_itself(monkeypatch):
+    """a pooled group (to_k / to_v of two blocks) whose second block is never fed the same tensor stops computing for nothing."""
+    from sdnq_b200 import group_siblings
+    layers = make_layers("int8", 256, (256, 256, 256, 256))
+    group = group_siblings(layers)
+    assert group is not None
+    for i in range(8):
+        x = torch.randn(64, 256, device=DEV, dtype=torch.bfloat16)
+        monkeypatch.setenv("SDNQ_B200_SIBLINGS", "0")
+        ref = [layers[0](x), layers[1](x)]
+        monkeypatch.setenv("SDNQ_B200_SIBLINGS", "1")
+        assert torch.equal(layers[0](x), ref[0]) and torch.equal(layers[1](x), ref[1])
+    assert group.dead and all("_sdnq_siblings" not in layer.__dict__ for layer in layers)
