@@ -226,6 +226,35 @@ SDNQ_API int sdnq_b200_linear_w8a8(const void* x, int x_dtype, int64_t ldx, cons
                           void* out, int out_dtype, int64_t M, int64_t N, int64_t K,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- K3, batched: the weights of SEVERAL layers dequantised by one persistent launch.  The reference dequantises inside every
+ *      forward (layers/linear/forward.py:24-26 -> SDNQDequantizer.__call__, dequantizer.py:389-429); the weights are frozen, so the
+ *      host layer learns the order in which layers are called and dequantises the next few layers' weights together, ahead of
+ *      their GEMMs, on a side stream.  Every weight is still dequantised exactly once per use, with the arithmetic of
+ *      sdnq_b200_dequant (same kernel, a table of weights instead of one).
+ *   jobs         per weight: the arguments of sdnq_b200_dequant (no codebook, no Hadamard un-rotate) plus its output
+ *   host_table   sdnq_b200_dequant_batch_table_bytes(n_jobs) bytes of HOST memory the plan is written to; copy it to device memory
+ *                (128-byte aligned) once and pass that copy to every run.  The plan embeds the jobs' pointers: it stays valid
+ *                while those allocations do.
+ *   info         int32[4] filled by the plan, passed back to run
+ * Covers 4-bit integer weights with bf16 SVD factors (rank 16 / 32 / 64, stored K-major) and bf16 output; anything else: SDNQ_EUNSUPPORTED. */
+typedef struct sdnq_dequant_job {
+    const void* weight;
+    sdnq_weight_format fmt;
+    const float* scale;
+    const float* zero_point;
+    int64_t N, K, group_size;
+    const void* svd_up;
+    int64_t up_stride_n, up_stride_r;
+    const void* svd_down;
+    int64_t down_stride_r, down_stride_k;
+    int32_t svd_rank, svd_dtype;
+    void* out;
+    int32_t out_dtype, reserved;
+} sdnq_dequant_job;
+SDNQ_API size_t sdnq_b200_dequant_batch_table_bytes(int n_jobs);
+SDNQ_API int sdnq_b200_dequant_batch_plan(const sdnq_dequant_job* jobs, int n_jobs, void* host_table, int32_t* info);
+SDNQ_API int sdnq_b200_dequant_batch_run(const void* device_table, const int32_t* info, void* stream);
+
 /* ---- K5 small-M Linear on 8-bit weights ("W8A16 GEMV"):  the rows < 32 branch of every quantized-matmul forward
  *      (linear_int8.py:102-103, linear_uint8.py:107-108, linear_fp8.py:83-84: dequantise the weight, then F.linear) without
  *      materialising the dequantised weight:

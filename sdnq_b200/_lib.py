@@ -25,6 +25,15 @@ class WeightFormat(ctypes.Structure):
                 ("exponent", ctypes.c_int32), ("mantissa", ctypes.c_int32), ("word_bytes", ctypes.c_int32)]
 
 
+class DequantJob(ctypes.Structure):
+    _fields_ = [("weight", ctypes.c_void_p), ("fmt", WeightFormat), ("scale", ctypes.c_void_p), ("zero_point", ctypes.c_void_p),
+                ("N", ctypes.c_int64), ("K", ctypes.c_int64), ("group_size", ctypes.c_int64),
+                ("svd_up", ctypes.c_void_p), ("up_stride_n", ctypes.c_int64), ("up_stride_r", ctypes.c_int64),
+                ("svd_down", ctypes.c_void_p), ("down_stride_r", ctypes.c_int64), ("down_stride_k", ctypes.c_int64),
+                ("svd_rank", ctypes.c_int32), ("svd_dtype", ctypes.c_int32), ("out", ctypes.c_void_p),
+                ("out_dtype", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
 _P, _I, _L, _Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
 _WF = ctypes.POINTER(WeightFormat)
 
@@ -36,6 +45,9 @@ SIGNATURES = {
     "sdnq_b200_unpack": (_I, [_P, _WF, _P, _I, _L, _P]),
     "sdnq_b200_dequant": (_I, [_P, _WF, _P, _P, _I, _L, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _P, _I, _P]),
     "sdnq_b200_dequant_nd": (_I, [_P, _WF, _P, _P, _I, _I, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), _P, _I, _P, _I, _P]),
+    "sdnq_b200_dequant_batch_table_bytes": (_Z, [_I]),
+    "sdnq_b200_dequant_batch_plan": (_I, [_P, _I, _P, _P]),
+    "sdnq_b200_dequant_batch_run": (_I, [_P, _P, _P]),
     "sdnq_b200_requant": (_I, [_P, _WF, _P, _P, _I, _L, _L, _L, _I, _P, _P, _P, _P, _P]),
     "sdnq_b200_act_quant": (_I, [_P, _I, _L, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P]),
     "sdnq_b200_conv_act_quant": (_I, [_P, _I, ctypes.POINTER(Conv2dGeometry), _I, _I, _P, _P, _P, _P, _P, _P]),

@@ -17,7 +17,7 @@ from collections.abc import Callable
 
 import torch
 
-from . import ops, siblings
+from . import ops, prefetch, siblings
 from .common import conv_transpose_types, conv_types, dtype_dict, embedding_types
 
 SMALL_M = 32     # rows below this use the dequant path, as upstream does (linear_int8.py:102-103)
@@ -159,6 +159,11 @@ def _dequant_weight_overlapped(layer, input, skip_quantized_matmul):
         return _dequant_weight(layer, dtype, skip_quantized_matmul)
     main = torch.cuda.current_stream(input.device)
     side = _side_stream(input.device)
+    if dtype == torch.bfloat16 and prefetch.enabled() and prefetch.eligible(layer, dtype):
+        # the weights of this layer and of the ones that follow it in the learned call order, dequantised by one launch (prefetch.py)
+        W = prefetch.prefetcher(input.device).get(layer, bool(skip_quantized_matmul), main, side)
+        if W is not None:
+            return W
     # The side stream may run ahead of the main stream only while the stored tensors are provably the ones it has already been
     # ordered after: same tensor objects (weak references), same data pointers and versions, same module generation.  Anything
     # else -- a fresh load, .to(device) of an offloaded module (new Parameter objects in recycled memory), an in-place edit --

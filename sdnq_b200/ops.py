@@ -146,6 +146,83 @@ def dequant(weight, weights_dtype, scale, zero_point, N, K, group_size, out_dtyp
     return out
 
 
+class DequantBatch:
+    """A planned batched dequantisation: the device-side table of sdnq_b200_dequant_batch_plan, the [N,K] outputs it writes (views of
+    `slab`) and everything the embedded pointers refer to."""
+    __slots__ = ("table", "info", "outs", "keep", "device")
+
+    def __init__(self, table, info, outs, keep, device):
+        self.table, self.info, self.outs, self.keep, self.device = table, info, outs, keep, device
+
+
+def dequant_batch_bytes(shapes, out_dtype=torch.bfloat16) -> list:
+    """byte offsets of the [N,K] outputs of a batch inside one slab (256-byte aligned), plus the total"""
+    offs, pos = [], 0
+    esz = torch.empty((), dtype=out_dtype).element_size()
+    for n, k in shapes:
+        offs.append(pos)
+        pos += (n * k * esz + 255) // 256 * 256
+    return offs + [pos]
+
+
+def dequant_batch_plan(jobs, slab: torch.Tensor, out_dtype=torch.bfloat16) -> DequantBatch:
+    """jobs: dicts with the arguments of `dequant` (weight, weights_dtype, scale, zero_point, N, K, group_size, svd_up, svd_down,
+    svd_layout_matmul).  The outputs are laid out in `slab` (uint8, device) at the offsets of dequant_batch_bytes.  Synchronous
+    (uploads the plan): not to be called while the stream is being captured.  Raises SDNQKernelError if a job is not covered."""
+    import ctypes
+    lib = _lib.load()
+    n = len(jobs)
+    offs = dequant_batch_bytes([(j["N"], j["K"]) for j in jobs], out_dtype)
+    if offs[-1] > slab.numel() or slab.dtype != torch.uint8 or slab.data_ptr() % 256 != 0:
+        raise _lib.SDNQKernelError("dequant_batch_plan: the slab is too small or misaligned")
+    arr = (_lib.DequantJob * n)()
+    keep, outs = [], []
+    for i, j in enumerate(jobs):
+        e = dtype_dict[j["weights_dtype"]]
+        w = j["weight"].contiguous() if e["is_packed"] else physical_nk(j["weight"])
+        scale = j["scale"]
+        scale = scale.to(torch.float32).contiguous() if scale.dtype != torch.float32 or not scale.is_contiguous() else scale
+        zp = j.get("zero_point")
+        if zp is not None and (zp.dtype != torch.float32 or not zp.is_contiguous()):
+            zp = zp.to(torch.float32).contiguous()
+        up, down = j["svd_up"], j["svd_down"]
+        _require_cuda(w, scale, up, down)
+        N, K = int(j["N"]), int(j["K"])
+        out = slab[offs[i]:offs[i] + N * K * 2].view(out_dtype).view(N, K)
+        q = arr[i]
+        q.weight, q.fmt, q.scale, q.zero_point = w.data_ptr(), weight_format(j["weights_dtype"], w), scale.data_ptr(), _ptr(zp)
+        q.N, q.K, q.group_size = N, K, _group_args(scale, N, K, j["group_size"], False, e["num_bits"])
+        if j.get("svd_layout_matmul"):      # svd_up [r,N], svd_down [K,r]
+            q.svd_rank = up.shape[0]
+            q.svd_up, q.up_stride_n, q.up_stride_r = up.data_ptr(), up.stride(1), up.stride(0)
+            q.svd_down, q.down_stride_r, q.down_stride_k = down.data_ptr(), down.stride(1), down.stride(0)
+        else:                               # svd_up [N,r], svd_down [r,K]
+            q.svd_rank = up.shape[1]
+            q.svd_up, q.up_stride_n, q.up_stride_r = up.data_ptr(), up.stride(0), up.stride(1)
+            q.svd_down, q.down_stride_r, q.down_stride_k = down.data_ptr(), down.stride(0), down.stride(1)
+        q.svd_dtype, q.out, q.out_dtype = dtype_code(up.dtype), out.data_ptr(), dtype_code(out_dtype)
+        keep += [w, scale, zp, up, down]
+        outs.append(out)
+    nbytes = int(lib.sdnq_b200_dequant_batch_table_bytes(n))
+    host = torch.empty(nbytes + 128, dtype=torch.uint8)
+    hoff = (-host.data_ptr()) % 128
+    info = (ctypes.c_int32 * 4)()
+    check(lib.sdnq_b200_dequant_batch_plan(ctypes.addressof(arr), n, host.data_ptr() + hoff, ctypes.addressof(info)))
+    table = torch.empty(nbytes + 128, dtype=torch.uint8, device=slab.device)
+    doff = (-table.data_ptr()) % 128
+    table = table[doff:doff + nbytes]
+    table.copy_(host[hoff:hoff + nbytes])
+    torch.cuda.current_stream(slab.device).synchronize()
+    return DequantBatch(table, info, outs, keep + [slab], slab.device)
+
+
+def dequant_batch_run(plan: DequantBatch):
+    """one launch: every weight of the plan dequantised into its output (current stream of the plan's device)"""
+    import ctypes
+    with torch.cuda.device(plan.device):
+        check(_lib.load().sdnq_b200_dequant_batch_run(plan.table.data_ptr(), ctypes.addressof(plan.info), torch.cuda.current_stream(plan.device).cuda_stream))
+
+
 def dequant_nd(weight, weights_dtype, scale, zero_point, view_shape, out_dtype, use_codebook=False, addend=None) -> torch.Tensor:
     """K3 for convolution layers: broadcast dequant over the quantised view (scale / zero_point broadcastable to view_shape;
     codebook levels carry one extra trailing axis).  `addend` (same numel) is added in f32 before the cast."""

@@ -144,17 +144,18 @@ def test_ctypes_signatures_match_the_header_types():
 
 
 def test_struct_layouts_match_the_header():
-    from sdnq_b200._lib import Conv2dGeometry, WeightFormat
+    from sdnq_b200._lib import Conv2dGeometry, DequantJob, WeightFormat
     _, text = header_prototypes()
-    ctype = {"int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "int": ctypes.c_int}
-    for struct, cls in (("sdnq_weight_format", WeightFormat), ("sdnq_conv2d_geometry", Conv2dGeometry)):
+    ctype = {"int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "int": ctypes.c_int, "sdnq_weight_format": WeightFormat}
+    for struct, cls in (("sdnq_weight_format", WeightFormat), ("sdnq_conv2d_geometry", Conv2dGeometry), ("sdnq_dequant_job", DequantJob)):
         body = re.search(r"typedef\s+struct\s+" + struct + r"\s*\{(.*?)\}\s*" + struct + r"\s*;", text, flags=re.S).group(1)
         fields = []
         for decl in body.split(";"):
             decl = " ".join(decl.split())
             if decl:
-                typ, names = decl.split(" ", 1)
-                fields += [(n.strip(), ctype[typ]) for n in names.split(",")]
+                m = re.match(r"(.*?[\s\*])(\w+(?:\s*,\s*\w+)*)$", decl)          # type, then one or more names
+                typ = m.group(1).replace(" ", "")
+                fields += [(n.strip(), ctypes.c_void_p if typ.endswith("*") else ctype[typ]) for n in m.group(2).split(",")]
         assert [(n, t) for n, t in cls._fields_] == fields, f"{struct}: ctypes fields differ from the header"
 
 
