@@ -173,7 +173,7 @@ def dequant_batch_plan(jobs, slab: torch.Tensor, out_dtype=torch.bfloat16) -> De
     lib = _lib.load()
     n = len(jobs)
     offs = dequant_batch_bytes([(j["N"], j["K"]) for j in jobs], out_dtype)
-    if offs[-1] > slab.numel() or slab.dtype != torch.uint8 or slab.data_ptr() % 256 != 0:
+    if offs[-1] > slab.numel() or slab.dtype != torch.uint8 or slab.data_ptr() % 16 != 0:
         raise _lib.SDNQKernelError("dequant_batch_plan: the slab is too small or misaligned")
     arr = (_lib.DequantJob * n)()
     keep, outs = [], []
