@@ -64,15 +64,27 @@ __device__ __forceinline__ uint32_t pack16(T a, T b) {
 // [4l, 4l+4) and [128+4l, 128+4l+4) of a chunk (two coalesced 8-byte accesses) instead of [8l, 8l+8).
 template <typename T, int WPR, int MAXC, int MODE, bool kTC, bool kConv>
 __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC ? 4 : 5) : (kTC ? 2 : 3)) act_quant_kernel(const ActArgs a) {
-    constexpr int RPC = kWarps / WPR;                 // rows per CTA
-    __shared__ float s_a[RPC][WPR];
-    __shared__ float s_b[RPC][WPR];
-    __shared__ int s_sum[RPC][WPR];
+    constexpr int RPC = kWarps / WPR;                 // rows per CTA and pass
+    // the cross-warp exchange buffers alternate between passes of the row loop: one barrier per pass is enough
+    __shared__ float s_a2[2][RPC][WPR];
+    __shared__ float s_b2[2][RPC][WPR];
+    __shared__ int s_sum2[2][RPC][WPR];
     pdl_launch_dependents();      // the GEMM behind us may start its prologue / weight prefetch now
     pdl_wait();                   // x (and the workspace we overwrite) belong to the stream predecessor
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r_in = warp / WPR, w_in = warp % WPR;
-    const int64_t row = int64_t(blockIdx.x) * RPC + r_in;
+    const float hfac = a.hfac;
+    [[maybe_unused]] hadtc::Rotation<std::conditional_t<kTC, T, __nv_bfloat16>> rot;
+    if constexpr (kTC) rot.init(a.hadamard, lane);
+    // Row loop: the grid is a few CTAs per SM and every CTA walks row blocks blockIdx.x, blockIdx.x + gridDim.x, ... -- the per-CTA
+    // set-up (rotation constants, dependency wait, argument loads) is paid once, not once per pair of rows.
+    const int64_t nblk = (a.M + RPC - 1) / RPC;
+    int pass = 0;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x, pass ^= 1) {
+    float (&s_a)[RPC][WPR] = s_a2[pass];
+    float (&s_b)[RPC][WPR] = s_b2[pass];
+    int (&s_sum)[RPC][WPR] = s_sum2[pass];
+    const int64_t row = blk * RPC + r_in;
     const bool row_ok = row < a.M;
     const T* xrow = reinterpret_cast<const T*>(a.x) + (kConv ? 0 : row * a.ldx);
     const int K = static_cast<int>(a.K);
@@ -125,9 +137,6 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC
         }
     }
     float amax = 0.f, vmax = -INFINITY, vmin = INFINITY;
-    const float hfac = a.hfac;
-    [[maybe_unused]] hadtc::Rotation<std::conditional_t<kTC, T, __nv_bfloat16>> rot;
-    if constexpr (kTC) rot.init(a.hadamard, lane);
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
         float v[8];
@@ -249,6 +258,7 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC
         a.sx[row] = scale;
         if (a.zx != nullptr) a.zx[row] = zero;
     }
+    }   // row loop
 }
 
 // Rows longer than the register-resident kernel holds (K > 16384): one CTA per row, two passes over the row (statistics, then
@@ -376,7 +386,11 @@ int launch_long(const ActArgs& a, cudaStream_t st) {
 template <typename T, int WPR, int MAXC, bool kTC, bool kConv>
 int launch_mode(const ActArgs& a, cudaStream_t st) {
     constexpr int RPC = kWarps / WPR;
-    const unsigned blocks = static_cast<unsigned>((a.M + RPC - 1) / RPC);
+    const int64_t nblk = (a.M + RPC - 1) / RPC;
+    // a few waves of resident CTAs walk the row blocks (SDNQ_B200_ACTQ_GRID = CTAs per SM of grid; 0 = one CTA per row block)
+    static const int per_sm = [] { const char* e = getenv("SDNQ_B200_ACTQ_GRID"); return e != nullptr ? atoi(e) : 16; }();
+    const int64_t cap = per_sm > 0 ? int64_t(num_sms()) * per_sm : nblk;
+    const unsigned blocks = static_cast<unsigned>(nblk < cap ? nblk : cap);
     cudaError_t e;
     if (a.mode == SDNQ_I8) e = launch_pdl(act_quant_kernel<T, WPR, MAXC, SDNQ_I8, kTC, kConv>, dim3(blocks), dim3(kThreads), 0, st, a);
     else if (a.mode == SDNQ_U8) e = launch_pdl(act_quant_kernel<T, WPR, MAXC, SDNQ_U8, kTC, kConv>, dim3(blocks), dim3(kThreads), 0, st, a);

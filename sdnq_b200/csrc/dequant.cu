@@ -15,13 +15,10 @@
 namespace sdnq {
 
 size_t svd_batch_entry_bytes();
-int svd_batch_fill(void* host_entry, int tile_rows, int tile_start, const void* weight, const WFormat& f, const float* scale, const float* zp, int64_t N,
+int svd_batch_fill(void* host_entry, int tn, int tile_start, const void* weight, const WFormat& f, const float* scale, const float* zp, int64_t N,
                    int64_t K, int group32, int group_shift, int gpr32, int row_stride32, const void* up, int64_t up_sn, int64_t up_sr,
                    const void* down, int64_t down_sr, int64_t down_sk, int rank, int svd_dtype, void* out, int out_dtype, int* tiles);
-int svd_batch_run(const void* device_table, int n_entries, int total_tiles, int max_rank, cudaStream_t st);
-int dequant_svd_stream(const void* weight, const WFormat& f, const float* scale, const float* zp, int64_t N, int64_t K, int group32, int group_shift,
-                       int gpr32, int row_stride32, const void* up, int64_t up_sn, int64_t up_sr, const void* down, int64_t down_sr, int64_t down_sk,
-                       int rank, int svd_dtype, void* out, int out_dtype, cudaStream_t st);
+int svd_batch_run(const void* device_table, int n_entries, int total_tiles, int tn, int stage_rank, cudaStream_t st);
 int dequant_svd_tc(const void* weight, const WFormat& f, const float* scale, const float* zp, int64_t N, int64_t K, int group32, int group_shift,
                    int gpr32, int row_stride32, const void* up, int64_t up_sn, int64_t up_sr, const void* down, int64_t down_sr, int64_t down_sk,
                    int rank, int svd_dtype, void* out, int out_dtype, cudaStream_t st);
@@ -718,15 +715,8 @@ extern "C" int sdnq_b200_dequant(const void* weight, const sdnq_weight_format* f
     const char* svd_env = getenv("SDNQ_B200_SVD_TC");          // "0": keep the CUDA-core SVD update (A/B measurements), read per call
     if (svd_up != nullptr && hadamard_group == 0 && !codebook && !(svd_env != nullptr && svd_env[0] == '0')) {
         // rank-r correction on the tensor cores when the layout allows it (dequant_svd.cu); 1 = "not covered, use the generic kernel"
-        // SDNQ_B200_SVD_KERNEL=stream: the streaming mma.sync kernel (dequant_svd_stream.cu) instead of the TMEM one for a single weight
-        const char* kern = getenv("SDNQ_B200_SVD_KERNEL");
-        rc = 1;
-        if (kern != nullptr && kern[0] == 's')
-            rc = dequant_svd_stream(weight, a.f, scale, zero_point, N, K, a.group32, a.group_shift, a.gpr32, a.row_stride32, svd_up, up_stride_n, up_stride_r,
-                                    svd_down, down_stride_r, down_stride_k, svd_rank, svd_dtype, out, out_dtype, st);
-        if (rc == 1)
-            rc = dequant_svd_tc(weight, a.f, scale, zero_point, N, K, a.group32, a.group_shift, a.gpr32, a.row_stride32, svd_up, up_stride_n, up_stride_r,
-                                svd_down, down_stride_r, down_stride_k, svd_rank, svd_dtype, out, out_dtype, st);
+        rc = dequant_svd_tc(weight, a.f, scale, zero_point, N, K, a.group32, a.group_shift, a.gpr32, a.row_stride32, svd_up, up_stride_n, up_stride_r,
+                            svd_down, down_stride_r, down_stride_k, svd_rank, svd_dtype, out, out_dtype, st);
         if (rc != 1) return rc;
     }
     switch (out_dtype) {
@@ -742,7 +732,12 @@ extern "C" size_t sdnq_b200_dequant_batch_table_bytes(int n_jobs) { return n_job
 
 extern "C" int sdnq_b200_dequant_batch_plan(const sdnq_dequant_job* jobs, int n_jobs, void* host_table, int32_t* info) {
     SDNQ_REQUIRE(jobs && host_table && info && n_jobs > 0, SDNQ_EINVAL, "NULL pointer or empty batch");
-    const int tile_rows = 128;        // a warp walks a 128-row x 64-column tile in 16-row blocks (dequant_svd_stream.cu)
+    // tile width: narrow tiles keep several CTAs per SM busy on the latency chain TMA -> MMA -> TMEM -> epilogue (SDNQ_B200_SVD_BATCH_TN forces it)
+    int tn = 64;
+    if (const char* e = getenv("SDNQ_B200_SVD_BATCH_TN")) {
+        const int v = atoi(e);
+        if (v == 64 || v == 128 || v == 256) tn = v;
+    }
     int total = 0, max_rank = 0;
     uint8_t* entry = reinterpret_cast<uint8_t*>(host_table);
     for (int j = 0; j < n_jobs; ++j, entry += svd_batch_entry_bytes()) {
@@ -753,22 +748,22 @@ extern "C" int sdnq_b200_dequant_batch_plan(const sdnq_dequant_job* jobs, int n_
         SDNQ_REQUIRE(q.out != nullptr && (reinterpret_cast<uintptr_t>(q.out) & 15) == 0, SDNQ_EINVAL, "job %d: out must be a 16-byte aligned pointer", j);
         SDNQ_REQUIRE(q.svd_up != nullptr && q.svd_down != nullptr, SDNQ_EUNSUPPORTED, "job %d: batched dequantisation covers weights with SVD factors", j);
         int tiles = 0;
-        rc = svd_batch_fill(entry, tile_rows, total, q.weight, a.f, q.scale, q.zero_point, q.N, q.K, a.group32, a.group_shift, a.gpr32, a.row_stride32, q.svd_up,
+        rc = svd_batch_fill(entry, tn, total, q.weight, a.f, q.scale, q.zero_point, q.N, q.K, a.group32, a.group_shift, a.gpr32, a.row_stride32, q.svd_up,
                             q.up_stride_n, q.up_stride_r, q.svd_down, q.down_stride_r, q.down_stride_k, q.svd_rank, q.svd_dtype, q.out, q.out_dtype, &tiles);
-        if (rc == 1) return set_error(SDNQ_EUNSUPPORTED, "job %d: outside what the batched dequant kernel covers (int4 / uint4 codes, bf16 SVD "
-                                      "factors of rank 16 / 32 / 48 / 64 stored K-major, bf16 output, K %% 16 == 0)", j);
+        if (rc == 1) return set_error(SDNQ_EUNSUPPORTED, "job %d: outside what the batched tensor-core dequant kernel covers (int4 / uint4 codes, bf16 SVD "
+                                      "factors of rank 16 / 32 / 64 stored K-major, bf16 output, K %% 32 == 0)", j);
         if (rc != SDNQ_OK) return rc;
         total += tiles;
         max_rank = q.svd_rank > max_rank ? q.svd_rank : max_rank;
     }
-    info[0] = tile_rows; info[1] = total; info[2] = max_rank; info[3] = n_jobs;
+    info[0] = tn; info[1] = total; info[2] = max_rank; info[3] = n_jobs;
     return SDNQ_OK;
 }
 
 extern "C" int sdnq_b200_dequant_batch_run(const void* device_table, const int32_t* info, void* stream) {
-    SDNQ_REQUIRE(device_table && info && (reinterpret_cast<uintptr_t>(device_table) & 15) == 0, SDNQ_EINVAL, "device_table must be a 16-byte aligned device pointer");
-    SDNQ_REQUIRE(info[0] > 0 && info[1] > 0 && info[2] > 0 && info[3] > 0, SDNQ_EINVAL, "bad plan info");
-    return svd_batch_run(device_table, info[3], info[1], info[2], reinterpret_cast<cudaStream_t>(stream));
+    SDNQ_REQUIRE(device_table && info && (reinterpret_cast<uintptr_t>(device_table) & 127) == 0, SDNQ_EINVAL, "device_table must be a 128-byte aligned device pointer");
+    SDNQ_REQUIRE((info[0] == 64 || info[0] == 128 || info[0] == 256) && info[1] > 0 && info[2] > 0 && info[3] > 0, SDNQ_EINVAL, "bad plan info");
+    return svd_batch_run(device_table, info[3], info[1], info[0], info[2], reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int sdnq_b200_requant(const void* weight, const sdnq_weight_format* fmt, const float* scale, const float* zero_point,

@@ -14,6 +14,7 @@
 // (1, r) = physical [K, r] (r contiguous: K-major).  One TMA box row is r*2 bytes = the swizzle span (32 / 64 / 128 B).
 #include <cstdlib>
 #include <mutex>
+#include <new>
 
 #include "ptx.cuh"
 #include "unpack.cuh"
@@ -65,13 +66,29 @@ struct SvdArgs {
     int out_dtype;
 };
 
+// One weight of a launch: its three tensor maps, its arguments and where its tiles start in the launch's tile numbering.  A single
+// dequantisation passes one entry as a kernel parameter; a batched launch (several layers' weights dequantised ahead of their
+// GEMMs by one persistent grid) reads a table of them from global memory.
+struct alignas(128) BatchEntry {
+    CUtensorMap up, down, out;
+    SvdArgs a;
+    int tile_start;      // index of this weight's first tile in the launch
+    int num_n;           // tiles along K
+};
+
 template <int BITS, bool kBf16Out, int TN>
 __global__ void __launch_bounds__(kThreads, SvdCfg<TN>::kCtasPerSm)
-dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_constant__ CUtensorMap tmap_down,
-                   const __grid_constant__ CUtensorMap tmap_out, const SvdArgs a) {
+dequant_svd_kernel(const __grid_constant__ BatchEntry single, const BatchEntry* __restrict__ table, const int n_entries, const int total_tiles,
+                   const int stage_rank) {
     using SC = SvdCfg<TN>;
     constexpr int kPkBytes = SC::kPkBytes, kPkTotal = SC::kPkTotal, kScTotal = SC::kScTotal;
-    const int kStageA = stage_a_bytes(a.rank), kStageB = SC::stage_b_bytes(a.rank);
+    const BatchEntry* const tab = table != nullptr ? table : &single;
+    const int kStageA = stage_a_bytes(stage_rank), kStageB = SC::stage_b_bytes(stage_rank);      // stages sized for the largest rank of the launch
+    // tile t of the launch -> the entry it belongs to (t only grows in every role's loop, so the search resumes at `li`)
+    auto locate = [&](int t, int& li) -> const BatchEntry* {
+        while (li + 1 < n_entries && t >= tab[li + 1].tile_start) ++li;
+        return tab + li;
+    };
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = ptx::smem_u32(smem_raw);
     if ((smem_base & 1023u) != 0) __trap();
@@ -89,15 +106,9 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_m = (a.N + TM - 1) / TM, num_n = (a.K + TN - 1) / TN;
-    const int num_tiles = num_m * num_n;
-    const int row_bytes = a.rank * 2;                               // = swizzle span
-    const uint32_t stage_tx = static_cast<uint32_t>((TM + TN) * row_bytes);
+    const int num_tiles = total_tiles;
 
     if (warp == 0 && lane == 0) {
-        ptx::prefetch_tmap(&tmap_up);
-        ptx::prefetch_tmap(&tmap_down);
-        ptx::prefetch_tmap(&tmap_out);
         for (int s = 0; s < kStages; ++s) {
             ptx::mbar_init(full_bar(s), 1);
             ptx::mbar_init(empty_bar(s), 1);
@@ -123,12 +134,15 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            int li = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / num_n) * TM, n0 = (tile % num_n) * TN;
+                const BatchEntry* e = locate(tile, li);
+                const int local = tile - e->tile_start, num_n = e->num_n;
+                const int m0 = (local / num_n) * TM, n0 = (local % num_n) * TN;
                 ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-                ptx::mbar_arrive_expect_tx(full_bar(stage), stage_tx);
-                ptx::tma_load_2d(smem_a + stage * kStageA, &tmap_up, full_bar(stage), 0, m0);
-                ptx::tma_load_2d(smem_b + stage * kStageB, &tmap_down, full_bar(stage), 0, n0);
+                ptx::mbar_arrive_expect_tx(full_bar(stage), static_cast<uint32_t>((TM + TN) * e->a.rank * 2));
+                ptx::tma_load_2d(smem_a + stage * kStageA, &e->up, full_bar(stage), 0, m0);
+                ptx::tma_load_2d(smem_b + stage * kStageB, &e->down, full_bar(stage), 0, n0);
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
@@ -137,8 +151,10 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
             constexpr uint32_t idesc = ptx::make_idesc(1 /*f32 acc*/, 1 /*bf16*/, 1 /*bf16*/, TM, TN);
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
+            int it = 0, li = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int rank = locate(tile, li)->a.rank;
+                const int row_bytes = rank * 2;                        // = swizzle span
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1u;
                 ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
@@ -146,7 +162,7 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
                 ptx::tc_fence_after();
                 const uint64_t a_desc = ptx::make_smem_desc_kmajor(smem_a + stage * kStageA, row_bytes);
                 const uint64_t b_desc = ptx::make_smem_desc_kmajor(smem_b + stage * kStageB, row_bytes);
-                for (int k = 0; k < a.rank / 16; ++k)                 // 16 bf16 = 32 B per MMA along the contraction
+                for (int k = 0; k < rank / 16; ++k)                   // 16 bf16 = 32 B per MMA along the contraction
                     ptx::umma_f16(tmem_base + as * TN, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc, k != 0 ? 1u : 0u);
                 ptx::umma_commit(empty_bar(stage));
                 ptx::umma_commit(tfull_bar(as));
@@ -163,11 +179,15 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
         const uint32_t my_o = smem_o + uint32_t(ew) * (kStoreBufs * kStoreBlkBytes);
         const uint32_t pk_base = smem_pk + uint32_t(ew) * (2 * kPkBytes);              // [2 buffers][8 units][32 lanes][16 B]
         float* sc_base = s_scales + ew * (2 * SC::kScFloats);                           // [2 buffers][scale|zp][blocks][32 lanes]
-        const float bias = 8388608.0f - static_cast<float>(a.f.int_offset);
-        const bool blk_scales = a.gpr32 <= 1 || (a.group32 & 63) == 0;
+        // per-64-column scales can be staged ahead only when a scale group never ends inside a 64-column block
+        auto blk_scales_of = [](const SvdArgs& a) { return a.gpr32 <= 1 || (a.group32 & 63) == 0; };
 
-        auto prefetch = [&](int tile, int buf) {
-            const int m0 = (tile / num_n) * TM, n0 = (tile % num_n) * TN;
+        auto prefetch = [&](int tile, int buf, int& li) {
+            const BatchEntry* e = locate(tile, li);
+            const SvdArgs& a = e->a;
+            const bool blk_scales = blk_scales_of(a);
+            const int local = tile - e->tile_start, num_n = e->num_n;
+            const int m0 = (local / num_n) * TM, n0 = (local % num_n) * TN;
             const int n = m0 + q * 32 + lane;
             const bool row_ok = n < a.N;
 #pragma unroll
@@ -196,18 +216,24 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
             }
         };
 
-        int it = 0, blk = 0;
-        if (blockIdx.x < num_tiles) prefetch(blockIdx.x, 0);
+        int it = 0, blk = 0, li = 0, li_next = 0;
+        if (blockIdx.x < num_tiles) prefetch(blockIdx.x, 0, li_next);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1, buf = it & 1;
             const uint32_t aphase = (it >> 1) & 1u;
-            const int m0 = (tile / num_n) * TM, n0 = (tile % num_n) * TN;
+            const BatchEntry* e = locate(tile, li);
+            const SvdArgs a = e->a;                                        // this tile's weight (registers)
+            const CUtensorMap* tmap_out = &e->out;
+            const float bias = 8388608.0f - static_cast<float>(a.f.int_offset);
+            const bool blk_scales = blk_scales_of(a);
+            const int local = tile - e->tile_start, num_n = e->num_n;
+            const int m0 = (local / num_n) * TM, n0 = (local % num_n) * TN;
             const int mrow0 = m0 + q * 32;
             const int n = mrow0 + lane;
             const bool row_ok = n < a.N;
             const int next = tile + gridDim.x;
             if (next < num_tiles) {
-                prefetch(next, buf ^ 1);
+                prefetch(next, buf ^ 1, li_next);
                 asm volatile("cp.async.wait_group 1;" ::: "memory");      // this tile's codes have landed (own lane's data only)
             } else {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -247,21 +273,19 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
                             if (a.zp) z = a.zp[si];
                         }
                         const uint32_t lo = words[o] & 0x0F0F0F0Fu, hi = (words[o] >> 4) & 0x0F0F0F0Fu;
-                        float y[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const uint32_t src = (j & 1) ? hi : lo;
-                            const float qv = __uint_as_float(__byte_perm(src, 0x4B000000u, 0x7440 | (j >> 1))) - bias;
-                            float w = a.zp ? fmaf(qv, sc, z) : __fmul_rn(qv, sc);
-                            // result.to(svd dtype): round to bf16 (mantissa RNE on the f32 bit pattern, no conversion pipe)
-                            uint32_t wb = __float_as_uint(w);
-                            wb = (wb + 0x7FFFu + ((wb >> 16) & 1u)) & 0xFFFF0000u;
-                            y[j] = __uint_as_float(wb) + __uint_as_float(r[8 * o + j]);     // addmm_: f32 accumulate, rounded once below
-                        }
                         uint32_t w4[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            __nv_bfloat162 hh = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+                        for (int j = 0; j < 4; ++j) {                              // byte j of the word = elements 2j (low nibble), 2j + 1
+                            const float q0 = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7440 | j)) - bias;
+                            const float q1 = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7440 | j)) - bias;
+                            const float v0 = a.zp ? fmaf(q0, sc, z) : __fmul_rn(q0, sc);
+                            const float v1 = a.zp ? fmaf(q1, sc, z) : __fmul_rn(q1, sc);
+                            // result.to(svd dtype): one packed conversion rounds both to bf16, two bit operations bring them back to f32
+                            __nv_bfloat162 wb = __floats2bfloat162_rn(v0, v1);
+                            const uint32_t wbits = *reinterpret_cast<uint32_t*>(&wb);
+                            const float y0 = __uint_as_float(wbits << 16) + __uint_as_float(r[8 * o + 2 * j]);          // addmm_: f32 accumulate,
+                            const float y1 = __uint_as_float(wbits & 0xFFFF0000u) + __uint_as_float(r[8 * o + 2 * j + 1]);   // rounded once below
+                            __nv_bfloat162 hh = __floats2bfloat162_rn(y0, y1);
                             w4[j] = *reinterpret_cast<uint32_t*>(&hh);
                         }
                         const int c8 = h * 4 + o;
@@ -271,7 +295,7 @@ dequant_svd_kernel(const __grid_constant__ CUtensorMap tmap_up, const __grid_con
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    ptx::tma_store_2d(&tmap_out, sbuf, kb0, mrow0);
+                    ptx::tma_store_2d(tmap_out, sbuf, kb0, mrow0);
                     ptx::tma_store_commit();
                 }
                 ++blk;
@@ -324,27 +348,47 @@ int make_tmap16(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, i
     return SDNQ_OK;
 }
 
-template <int BITS, bool kBf16Out, int TN>
-int launch_svd(const SvdArgs& a, const void* up, int64_t up_pitch, const void* down, int64_t down_pitch, void* out, cudaStream_t st) {
+// fills one table entry (tensor maps, arguments, tile range) for tile width TN
+template <int TN>
+int fill_entry(BatchEntry* e, const SvdArgs& a, const void* up, int64_t up_pitch, const void* down, int64_t down_pitch, void* out, int tile_start) {
+    int rc = make_tmap16(&e->up, up, a.N, a.rank, up_pitch, a.rank, TM, a.rank * 2);
+    if (rc != SDNQ_OK) return rc;
+    rc = make_tmap16(&e->down, down, a.K, a.rank, down_pitch, a.rank, TN, a.rank * 2);
+    if (rc != SDNQ_OK) return rc;
+    rc = make_tmap16(&e->out, out, a.N, a.K, a.K, 64, 32, 128);
+    if (rc != SDNQ_OK) return rc;
+    e->a = a;
+    e->tile_start = tile_start;
+    e->num_n = (a.K + TN - 1) / TN;
+    return SDNQ_OK;
+}
+
+template <int TN>
+int launch_entries(const BatchEntry* single, const BatchEntry* device_table, int n_entries, int total_tiles, int stage_rank, cudaStream_t st) {
     constexpr int kSmemMax = SvdCfg<TN>::smem_bytes(kMaxRank);
-    const int kSmemBytes = SvdCfg<TN>::smem_bytes(a.rank);
+    const int kSmemBytes = SvdCfg<TN>::smem_bytes(stage_rank);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(dequant_svd_kernel<BITS, kBf16Out, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax); });
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(dequant_svd_kernel<4, true, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax); });
     SDNQ_REQUIRE(attr_err == cudaSuccess, SDNQ_ECUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
-    CUtensorMap tu, td, to;
-    int rc = make_tmap16(&tu, up, a.N, a.rank, up_pitch, a.rank, TM, a.rank * 2);
-    if (rc != SDNQ_OK) return rc;
-    rc = make_tmap16(&td, down, a.K, a.rank, down_pitch, a.rank, TN, a.rank * 2);
-    if (rc != SDNQ_OK) return rc;
-    rc = make_tmap16(&to, out, a.N, a.K, a.K, 64, 32, 128);
-    if (rc != SDNQ_OK) return rc;
-    const int tiles = ((a.N + TM - 1) / TM) * ((a.K + TN - 1) / TN);
-    const int slots = num_sms() * SvdCfg<TN>::ctas_per_sm(a.rank);
-    const int grid = tiles < slots ? tiles : slots;
-    cudaError_t e = launch_pdl(dequant_svd_kernel<BITS, kBf16Out, TN>, dim3(grid), dim3(kThreads), kSmemBytes, st, tu, td, to, a);
+    const int slots = num_sms() * SvdCfg<TN>::ctas_per_sm(stage_rank);
+    const int grid = total_tiles < slots ? total_tiles : slots;
+    static const BatchEntry kNone{};
+    cudaError_t e = launch_pdl(dequant_svd_kernel<4, true, TN>, dim3(grid), dim3(kThreads), kSmemBytes, st, single != nullptr ? *single : kNone,
+                               device_table, n_entries, total_tiles, stage_rank);
     if (e != cudaSuccess) return set_error(SDNQ_ECUDA, "launch of dequant_svd_kernel failed: %s", cudaGetErrorString(e));
     return check_launch("dequant_svd_kernel");
+}
+
+bool svd_tc_covers(const void* weight, const WFormat& f, int64_t N, int64_t K, int group32, const void* up, int64_t up_sn, int64_t up_sr,
+                   const void* down, int64_t down_sr, int64_t down_sk, int rank, int svd_dtype, int out_dtype) {
+    const bool rank_ok = rank == 16 || rank == 32 || rank == 64;
+    const bool layout_ok = up_sr == 1 && up_sn >= rank && up_sn % 8 == 0 && down_sr == 1 && down_sk >= rank && down_sk % 8 == 0;   // both K-major
+    const bool dtype_ok = svd_dtype == SDNQ_BF16 && out_dtype == SDNQ_BF16;        // bf16 model dtype (f16 operands would need kind::f16 f16 formats)
+    const bool group_ok = (group32 & 7) == 0 || group32 >= K;
+    const bool align_ok = (reinterpret_cast<uintptr_t>(up) & 15) == 0 && (reinterpret_cast<uintptr_t>(down) & 15) == 0 && K % 8 == 0;
+    const bool fmt_ok = f.kind == SDNQ_W_INT && f.bits == 4 && K % 32 == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0;   // 16 B cp.async units
+    return rank_ok && layout_ok && dtype_ok && group_ok && align_ok && fmt_ok && N * K < (int64_t(1) << 31);
 }
 
 }  // namespace
@@ -354,13 +398,7 @@ int launch_svd(const SvdArgs& a, const void* up, int64_t up_pitch, const void* d
 int dequant_svd_tc(const void* weight, const WFormat& f, const float* scale, const float* zp, int64_t N, int64_t K, int group32, int group_shift,
                    int gpr32, int row_stride32, const void* up, int64_t up_sn, int64_t up_sr, const void* down, int64_t down_sr, int64_t down_sk,
                    int rank, int svd_dtype, void* out, int out_dtype, cudaStream_t st) {
-    const bool rank_ok = rank == 16 || rank == 32 || rank == 64;
-    const bool layout_ok = up_sr == 1 && up_sn >= rank && up_sn % 8 == 0 && down_sr == 1 && down_sk >= rank && down_sk % 8 == 0;   // both K-major
-    const bool dtype_ok = svd_dtype == SDNQ_BF16 && out_dtype == SDNQ_BF16;        // bf16 model dtype (f16 operands would need kind::f16 f16 formats)
-    const bool group_ok = (group32 & 7) == 0 || group32 >= K;
-    const bool align_ok = (reinterpret_cast<uintptr_t>(up) & 15) == 0 && (reinterpret_cast<uintptr_t>(down) & 15) == 0 && K % 8 == 0;
-    const bool fmt_ok = f.kind == SDNQ_W_INT && f.bits == 4 && K % 32 == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0;   // 16 B cp.async units
-    if (!(rank_ok && layout_ok && dtype_ok && group_ok && align_ok && fmt_ok) || N * K >= (int64_t(1) << 31)) return 1;
+    if (!svd_tc_covers(weight, f, N, K, group32, up, up_sn, up_sr, down, down_sr, down_sk, rank, svd_dtype, out_dtype)) return 1;
     SvdArgs a{reinterpret_cast<const uint8_t*>(weight), scale, zp, static_cast<int>(N), static_cast<int>(K), group32, group_shift, gpr32, row_stride32, f, rank, out_dtype};
     // Narrow tiles (several CTAs per SM) for the small weights of a UNet, wider ones as the weight grows: measured on B200 over
     // the SD-XL int4 + SVD step: TN = 64 9.62 ms, 128 9.86 ms, 256 10.7 ms (SDNQ_B200_SVD_TN forces 64 / 128 / 256)
@@ -369,9 +407,43 @@ int dequant_svd_tc(const void* weight, const WFormat& f, const float* scale, con
         const int v = atoi(e);
         if (v == 64 || v == 128 || v == 256) tn = v;
     }
-    if (tn == 256) return launch_svd<4, true, 256>(a, up, up_sn, down, down_sk, out, st);
-    if (tn == 128) return launch_svd<4, true, 128>(a, up, up_sn, down, down_sk, out, st);
-    return launch_svd<4, true, 64>(a, up, up_sn, down, down_sk, out, st);
+    BatchEntry e;
+    const int num_m = static_cast<int>((N + TM - 1) / TM);
+    int rc;
+    if (tn == 256) rc = fill_entry<256>(&e, a, up, up_sn, down, down_sk, out, 0);
+    else if (tn == 128) rc = fill_entry<128>(&e, a, up, up_sn, down, down_sk, out, 0);
+    else rc = fill_entry<64>(&e, a, up, up_sn, down, down_sk, out, 0);
+    if (rc != SDNQ_OK) return rc;
+    const int tiles = num_m * e.num_n;
+    if (tn == 256) return launch_entries<256>(&e, nullptr, 1, tiles, rank, st);
+    if (tn == 128) return launch_entries<128>(&e, nullptr, 1, tiles, rank, st);
+    return launch_entries<64>(&e, nullptr, 1, tiles, rank, st);
+}
+
+// ---- batched launches: the weights of several layers dequantised by one persistent grid ------------------------------------------
+size_t svd_batch_entry_bytes() { return sizeof(BatchEntry); }
+
+// Appends the entry of one weight to a host-side table.  Returns 1 when the weight is outside what this kernel covers.
+int svd_batch_fill(void* host_entry, int tn, int tile_start, const void* weight, const WFormat& f, const float* scale, const float* zp, int64_t N,
+                   int64_t K, int group32, int group_shift, int gpr32, int row_stride32, const void* up, int64_t up_sn, int64_t up_sr,
+                   const void* down, int64_t down_sr, int64_t down_sk, int rank, int svd_dtype, void* out, int out_dtype, int* tiles) {
+    if (!svd_tc_covers(weight, f, N, K, group32, up, up_sn, up_sr, down, down_sr, down_sk, rank, svd_dtype, out_dtype)) return 1;
+    SvdArgs a{reinterpret_cast<const uint8_t*>(weight), scale, zp, static_cast<int>(N), static_cast<int>(K), group32, group_shift, gpr32, row_stride32, f, rank, out_dtype};
+    BatchEntry* e = new (host_entry) BatchEntry{};
+    int rc;
+    if (tn == 256) rc = fill_entry<256>(e, a, up, up_sn, down, down_sk, out, tile_start);
+    else if (tn == 128) rc = fill_entry<128>(e, a, up, up_sn, down, down_sk, out, tile_start);
+    else rc = fill_entry<64>(e, a, up, up_sn, down, down_sk, out, tile_start);
+    if (rc != SDNQ_OK) return rc;
+    *tiles = static_cast<int>((N + TM - 1) / TM) * e->num_n;
+    return SDNQ_OK;
+}
+
+int svd_batch_run(const void* device_table, int n_entries, int total_tiles, int tn, int stage_rank, cudaStream_t st) {
+    const BatchEntry* t = reinterpret_cast<const BatchEntry*>(device_table);
+    if (tn == 256) return launch_entries<256>(nullptr, t, n_entries, total_tiles, stage_rank, st);
+    if (tn == 128) return launch_entries<128>(nullptr, t, n_entries, total_tiles, stage_rank, st);
+    return launch_entries<64>(nullptr, t, n_entries, total_tiles, stage_rank, st);
 }
 
 }  // namespace sdnq

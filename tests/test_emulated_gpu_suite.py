@@ -20,7 +20,6 @@ import torch
 
 from tests import test_conv_gpu as C
 from tests import test_kernels_gpu as K
-from tests import test_prefetch_gpu as P
 from tests.host_emu import build_emu
 
 
@@ -40,7 +39,6 @@ def emulated_library():
     mp.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
     mp.setattr(K, "DEV", "cpu")
     mp.setattr(C, "DEV", "cpu")
-    mp.setattr(P, "DEV", "cpu")
     yield lib
     mp.undo()
 
@@ -287,9 +285,3 @@ def test_dynamic_quantization(kw):
 def test_svd_low(kw):
     K.test_svd_low(**kw)
 
-
-# ---- K3b (dequant_svd_stream.cu): the streaming SVD dequantiser, batched over a table of weights and on single weights, against the
-#      CUDA-core generic kernel (the emulator's dequant path for SVD layers)
-def test_batched_dequant_stream_kernel(monkeypatch):
-    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: type("S", (), {"cuda_stream": 0, "synchronize": lambda self: None})())
-    P.test_batched_dequant_kernel_equals_per_layer_kernel()

@@ -96,7 +96,10 @@ def test_group_follows_weight_replacement_and_graph_capture(monkeypatch):
     layers[1].weight = other.weight
     layers[1].scale = other.scale
     y1 = [layer(x) for layer in layers]
-    assert torch.equal(y1[0], y0[0]) and torch.equal(y1[1], other(x)) and not torch.equal(y1[1], y0[1])
+    monkeypatch.setenv("SDNQ_B200_SIBLINGS", "0")
+    alone = layers[1](x.clone())
+    monkeypatch.setenv("SDNQ_B200_SIBLINGS", "1")
+    assert torch.equal(y1[0], y0[0]) and torch.equal(y1[1], alone) and not torch.equal(y1[1], y0[1])
     # captured: both launches are in the graph, replay reproduces the eager result for new input contents
     static_x = torch.randn(512, 1280, device=DEV, dtype=torch.bfloat16)
     side = torch.cuda.Stream()
