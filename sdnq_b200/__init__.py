@@ -9,11 +9,11 @@ from .dequantizer import SDNQDequantizer  # noqa: F401
 from .forward import get_forward_func  # noqa: F401
 from .layers import (SDNQConv1d, SDNQConv2d, SDNQConv3d, SDNQConvTranspose1d, SDNQConvTranspose2d, SDNQConvTranspose3d,  # noqa: F401
                      SDNQLayer, SDNQLinear)
-from .loader import (apply_sdnq_options_to_model, load_sdnq_state_dict, post_process_model, save_sdnq_model)  # noqa: F401
+from .loader import (apply_sdnq_options_to_model, load_sdnq_model, load_sdnq_state_dict, post_process_model, save_sdnq_model)  # noqa: F401
 from .siblings import fuse_named_siblings, fuse_sibling_projections, group_siblings  # noqa: F401
 from .quantizer import (apply_sdnq_to_module, sdnq_post_load_quant, sdnq_quantize_layer,  # noqa: F401
                         sdnq_quantize_layer_weight)
 
 __version__ = "0.1.0"
-__all__ = ["apply_sdnq_options_to_model", "load_sdnq_state_dict", "post_process_model", "save_sdnq_model", "SDNQConfig", "SDNQDequantizer", "SDNQLayer", "SDNQLinear", "SDNQConv1d", "SDNQConv2d", "SDNQConv3d", "SDNQConvTranspose1d", "SDNQConvTranspose2d", "SDNQConvTranspose3d", "QuantizationMethod", "apply_sdnq_to_module", "dtype_dict",
+__all__ = ["apply_sdnq_options_to_model", "load_sdnq_model", "load_sdnq_state_dict", "post_process_model", "save_sdnq_model", "SDNQConfig", "SDNQDequantizer", "SDNQLayer", "SDNQLinear", "SDNQConv1d", "SDNQConv2d", "SDNQConv3d", "SDNQConvTranspose1d", "SDNQConvTranspose2d", "SDNQConvTranspose3d", "QuantizationMethod", "apply_sdnq_to_module", "dtype_dict",
            "fuse_named_siblings", "fuse_sibling_projections", "group_siblings", "get_forward_func", "sdnq_post_load_quant", "sdnq_quantize_layer", "sdnq_quantize_layer_weight", "sdnq_version"]

@@ -177,3 +177,98 @@ def load_sdnq_state_dict(model: torch.nn.Module, model_path: str, device=None, d
     if dtype is not None or dequantize_fp32 is not None or use_quantized_matmul is not None:
         model = apply_sdnq_options_to_model(model, dtype=dtype, dequantize_fp32=dequantize_fp32, use_quantized_matmul=use_quantized_matmul)
     return model
+
+
+def _resolve_model_class(model_config: dict):
+    name = model_config.get("_class_name") or model_config.get("architectures")
+    if isinstance(name, list):
+        name = name[0] if name else None
+    if name is None:
+        return None
+    for package in ("diffusers", "transformers"):
+        try:
+            module = __import__(package)
+        except ImportError:
+            continue
+        cls = getattr(module, name, None)
+        if cls is not None:
+            return cls
+    return None
+
+
+def _drop_quantization_config(config):
+    if hasattr(config, "quantization_config"):
+        try:
+            del config.quantization_config
+        except Exception:      # noqa: BLE001
+            pass
+    if hasattr(config, "pop"):
+        config.pop("quantization_config", None)
+    return config
+
+
+def load_sdnq_model(model_path: str, model_cls=None, file_name: str | None = None, dtype: torch.dtype | None = None, device="cpu",
+                    dequantize_fp32: bool | None = None, use_quantized_matmul: bool | None = None, model_config: dict | None = None,
+                    quantization_config=None, load_method: str = "safetensors") -> torch.nn.Module:
+    """Build `model_cls` without allocating its weights, swap in SDNQ modules from the stored quantization config, read the
+    safetensors shards (file_loader.load_files: 'safetensors' | 'threaded' | 'streamer') and assign them
+    (reference loader.py:82-196: same arguments, same order of steps).  The skeleton is created on the meta device, which is
+    what accelerate's init_empty_weights does."""
+    from .file_loader import load_files
+    config_path = os.path.join(model_path, "config.json")
+    qconfig_path = os.path.join(model_path, "quantization_config.json")
+    if model_config is None:
+        model_config = {}
+        if os.path.exists(config_path):
+            with open(config_path, encoding="utf-8") as f:
+                model_config = json.load(f)
+    if quantization_config is None:
+        if os.path.exists(qconfig_path):
+            with open(qconfig_path, encoding="utf-8") as f:
+                quantization_config = json.load(f)
+        else:
+            quantization_config = model_config.get("quantization_config")
+            if quantization_config is None:
+                raise ValueError(f"Cannot determine quantization_config for {model_path}, please provide quantization_config argument")
+    if not isinstance(quantization_config, SDNQConfig):
+        raw = dict(quantization_config)
+        for key in ("is_integer", "is_unsigned", "quant_method"):
+            raw.pop(key, None)
+        quantization_config = SDNQConfig(**raw)
+    if model_cls is None:
+        model_cls = _resolve_model_class(model_config)
+    if model_cls is None:
+        raise ValueError(f"Cannot determine model class for {model_path}, please provide model_cls argument")
+    with torch.device("meta"):
+        if hasattr(model_cls, "load_config") and hasattr(model_cls, "from_config"):        # Diffusers
+            model = model_cls.from_config(_drop_quantization_config(model_cls.load_config(model_path)))
+        elif hasattr(model_cls, "_from_config"):                                             # Transformers
+            import transformers
+            model = model_cls(_drop_quantization_config(transformers.AutoConfig.from_pretrained(model_path)))
+        else:                                                                                # a plain nn.Module taking its config as keywords
+            model = model_cls(**_drop_quantization_config(dict(model_config)))
+        model = sdnq_post_load_quant(model, torch_dtype=dtype, quantization_config=quantization_config, pre_quantized=True)
+    if file_name:
+        files = [os.path.join(model_path, file_name)]
+    else:
+        files = sorted(os.path.join(model_path, f) for f in os.listdir(model_path) if f.endswith(".safetensors"))
+    state = load_files(files, key_mapping=getattr(model, "_checkpoint_conversion_mapping", None), device=device, method=load_method)
+    tied = getattr(model, "_tied_weights_keys", None)
+    if isinstance(tied, dict):
+        for key, source in tied.items():
+            if source in state and key not in state:
+                state[key] = state[source]
+    model.load_state_dict(state, assign=True)
+    del state
+    model.quantization_config = quantization_config
+    if hasattr(model, "config"):
+        try:
+            model.config.quantization_config = quantization_config
+        except Exception:      # noqa: BLE001
+            pass
+    model = post_process_model(model)
+    if dtype is not None or dequantize_fp32 is not None or use_quantized_matmul is not None:
+        model = apply_sdnq_options_to_model(model, dtype=dtype, dequantize_fp32=dequantize_fp32, use_quantized_matmul=use_quantized_matmul)
+    from .siblings import fuse_sibling_projections
+    fuse_sibling_projections(model)
+    return model

@@ -313,6 +313,30 @@ def test_load_reference_written_checkpoint(name, tmp_path):
     save_sdnq_model(model, str(tmp_path))
     assert sorted(os.listdir(tmp_path)) == ["model.safetensors", "quantization_config.json"]
     check(load_sdnq_state_dict(toy_model.build(seed=7), str(tmp_path)))
+    # load_sdnq_model (reference loader.py:82-196): the model class is built without weights (meta device), the tensors come
+    # from the files -- every reader of file_loader.load_files must give the same model
+    from sdnq_b200 import load_sdnq_model
+    for method in ("safetensors", "threaded"):
+        loaded = load_sdnq_model(os.path.join(GOLDEN, "ckpt_" + name), model_cls=toy_model.Toy, model_config={}, load_method=method, dtype=torch.bfloat16)
+        check(loaded)
+        assert not any(p.is_meta for p in loaded.parameters())
+    with pytest.raises(ValueError, match="Unsupported loading method"):
+        load_sdnq_model(os.path.join(GOLDEN, "ckpt_" + name), model_cls=toy_model.Toy, model_config={}, load_method="carrier-pigeon")
+
+
+def test_file_loader_key_mapping_and_shards(tmp_path):
+    import torch
+    from safetensors.torch import save_file
+
+    from sdnq_b200.file_loader import load_files, map_keys
+    save_file({"model.a.weight": torch.arange(4.0), "b": torch.ones(2)}, str(tmp_path / "s1.safetensors"))
+    save_file({"model.c.weight": torch.zeros(3)}, str(tmp_path / "s2.safetensors"))
+    mapping = {r"^model\.": "", r"weight$": "w"}
+    assert map_keys("model.a.weight", mapping) == "a.weight"          # first matching pattern only
+    for method in ("safetensors", "threaded"):
+        sd = load_files([str(tmp_path / "s1.safetensors"), str(tmp_path / "s2.safetensors")], key_mapping=mapping, method=method)
+        assert sorted(sd) == ["a.weight", "b", "c.weight"] and torch.equal(sd["a.weight"], torch.arange(4.0))
+    assert sorted(load_files(str(tmp_path / "s2.safetensors"))) == ["model.c.weight"]
 
 
 @pytest.mark.parametrize("cfg", [dict(weights_dtype="int8", use_quantized_matmul=True), dict(weights_dtype="int4", group_size=32),
