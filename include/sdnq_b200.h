@@ -196,11 +196,16 @@ SDNQ_API int sdnq_b200_scaled_mm(const void* a, const void* b, int ab_dtype, con
                         void* out, int out_dtype, int64_t M, int64_t N, int64_t K, void* stream);
 
 /* ---- K1 with the packed-weight unpack fused into the GEMM (north_star "unpack + scale in the GEMM prologue"):
- *      linear_int8.py:38-44 (per-call unpack_int(...).t_() of a row-wise packed weight) + the scaled matmul above.
- * b_packed  [N, K*bits/8] packed row-wise int4 / uint4 storage exactly as the reference keeps it (packed_int/pack.py:273-276);
- *           TMA stages the packed tile in shared memory, four unpack warps expand it to int8 in the UMMA layout, the
- *           row-wise scale sw[n] (and, for uint4, the zero-point term rowsum[m]*sx[m]*zp[n]) is applied in the epilogue.
- * a, sx, bias, out as in sdnq_b200_scaled_mm (a is int8).  K % 32 == 0. */
+ *      linear_int8.py:38-44 / linear_fp8.py:38 (per-call unpack_int / unpack_float(...).t_() of a row-wise packed weight,
+ *      packed_int/unpack.py:233-372, packed_float.py:85-132) + the scaled matmul above.
+ * b_packed  [N, K*bits/8] row-wise packed storage exactly as the reference keeps it (packed_int/pack.py: octets of 8 codes in
+ *           `bits` bytes), bits = 2..7:
+ *             integer codes (int2..int7 / uint2..uint7)  with int8 activations  -> expanded to int8 (code - 2^(bits-1) for signed formats),
+ *             minifloat codes eXmY with X <= 4, Y <= 3   with e4m3 activations  -> expanded to the e4m3 byte of the same value.
+ *           TMA stages the packed tile in shared memory, four unpack warps expand it in the UMMA layout, the row-wise scale sw[n]
+ *           (and, for unsigned integers, the zero-point term rowsum[m]*sx[m]*zp[n]) is applied in the epilogue.  The result is, bit
+ *           for bit, sdnq_b200_unpack followed by sdnq_b200_scaled_mm -- without the N*K-byte expanded copy.
+ * a, sx, bias, out as in sdnq_b200_scaled_mm.  K * bits % 128 == 0 (16-byte row pitch). */
 SDNQ_API int sdnq_b200_scaled_mm_packed(const void* a, const void* b_packed, const sdnq_weight_format* b_fmt, const float* sx,
                                         const float* sw, const void* bias, int bias_dtype, int64_t bias_ld,
                                         const int32_t* rowsum, const float* zp, void* out, int out_dtype,

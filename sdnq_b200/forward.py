@@ -74,6 +74,22 @@ class _StoredState:
         return True
 
 
+def _prologue_unpack_ok(d, mm: str, K: int) -> bool:
+    """Can K1 expand this layer's stored packed weight in its prologue (sdnq_b200_scaled_mm_packed)?  SDNQ_B200_CACHE_UNPACKED=1
+    keeps the round-1 behaviour (expand once with the unpack kernel, cache the N*K-byte operand)."""
+    if not d.is_packed or os.environ.get("SDNQ_B200_CACHE_UNPACKED", "0").lower() not in ("0", "false", "no", ""):
+        return False
+    bits = d.num_bits
+    if not 2 <= bits <= 7 or (K * bits) % 128 != 0:              # 16-byte row pitch of the packed rows (TMA)
+        return False
+    if d.is_integer:
+        return mm == "int8"
+    info = dtype_dict[d.weights_dtype]
+    if mm != "float8_e4m3fn" or info.get("exponent", 9) > 4 or info.get("mantissa", 9) > 3:
+        return False
+    return True
+
+
 @torch.no_grad()
 def matmul_operand(layer) -> _MatmulOperand:
     """Build (once) and cache the matmul operand of a W8A8 layer.
@@ -96,9 +112,9 @@ def matmul_operand(layer) -> _MatmulOperand:
         raise NotImplementedError("sdnq_b200: packed convolution weights without re-quantisation have no W8A8 kernel")
     if d.re_quantize_for_matmul:
         wq, sw, zp, colsum = d.re_quantize_matmul_raw(w, s, z, want_colsum=uint8_mm)
-    elif (d.is_packed and d.is_integer and d.num_bits == 4 and mm == "int8" and K % 32 == 0
-          and os.environ.get("SDNQ_B200_CACHE_UNPACKED", "0").lower() in ("0", "false", "no", "")):
-        # row-wise int4 / uint4: keep the packed bytes, the GEMM unpacks them tile by tile in its prologue (no N*K-byte copy)
+    elif _prologue_unpack_ok(d, mm, K):
+        # row-wise packed weights (2..7-bit integers under an int8 matmul, eXmY minifloats that are subsets of e4m3 under an fp8 one):
+        # keep the packed bytes, the GEMM expands them tile by tile in its prologue (no N*K-byte copy)
         op = _MatmulOperand(w.contiguous(), _flat_f32(s), _flat_f32(z), None, key, packed=d.weights_dtype)
         layer.__dict__["_sdnq_mm_cache"] = op
         return op
@@ -415,7 +431,8 @@ def _w8a8_forward(self, input: torch.Tensor) -> torch.Tensor:
         return out.view(*input.shape[:-1], out.shape[-1])
     # SVD branch (linear_int8.py:57-62): bias2d = bias + (x_rot @ svd_down[K,r]) @ svd_up[r,N] on the rotated, un-quantised activations
     # in the SVD dtype.  K7 computes low = x_rot @ svd_down, K1 accumulates low @ svd_up per output tile on the tensor cores.
-    svd = _svd_mm_operands(self, input.dtype)
+    # (the rank-r accumulate exists for unpacked and 4-bit packed operands; other packed widths take the dense-bias form)
+    svd = _svd_mm_operands(self, input.dtype) if (op.packed is None or (d.is_integer and d.num_bits == 4)) else None
     need_rot = hg != 0 or svd is None                       # without rotation x_rot is x itself: K2 does not write a copy of it
     xq, sx, zx, rowsum, x_rot = quantized_activations(x2, mm, hg, op.zp is not None, need_rot)
     if svd is None:
@@ -533,7 +550,7 @@ def _w8a8_conv_forward(self, input: torch.Tensor) -> torch.Tensor:
     svd = self.svd_up is not None
     xq, sx, zx, rowsum, x_rot, (B, Ho, Wo) = ops.conv_act_quant(x4, ksz, stride, padding, dilation, mm, hadamard_group=hg,
                                                                 want_rowsum=op.zp is not None, want_x_rot=svd)
-    svd_ops = _svd_mm_operands(self, input.dtype) if svd else None
+    svd_ops = _svd_mm_operands(self, input.dtype) if svd and (op.packed is None or (d.is_integer and d.num_bits == 4)) else None
     if svd_ops is not None:                                                       # conv_int8.py:56-61 as K7 + the rank-r accumulate in K1
         low = ops.svd_low(x_rot, svd_ops[0])
         out = ops.scaled_mm_svd(xq, op.wq, sx, op.sw, low, svd_ops[1], self.bias, input.dtype, rowsum=rowsum, zp=op.zp, colsum=op.colsum, zx=zx,

@@ -21,6 +21,7 @@ import weakref
 import torch
 
 from . import ops
+from .common import dtype_dict
 
 MAX_GROUP = 8            # siblings per launch (output tensor maps in the kernel's parameter block)
 _WASTE_LIMIT = 3         # consecutive launches with mostly unused outputs before a group is dissolved
@@ -74,6 +75,8 @@ class SiblingGroup:
         if any(o.packed != packed or (o.zp is None) != (first.zp is None) or (o.colsum is None) != (first.colsum is None)
                or o.wq.dtype != first.wq.dtype or o.wq.device != first.wq.device for o in ops_now):
             return False
+        if packed is not None and dtype_dict[packed]["num_bits"] != 4:
+            return False                     # the grouped launch expands 4-bit codes only
         K = self.layers[0].sdnq_dequantizer.matmul_nk()[1]
         ns = [layer.sdnq_dequantizer.matmul_nk()[0] for layer in self.layers]
         if any(n % 8 for n in ns):

@@ -489,6 +489,43 @@ def test_scaled_mm_packed_int4(signed, M, N, K):
     np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=2e-6, atol=1e-5)
 
 
+@pytest.mark.parametrize("wd", ["int2", "uint2", "int3", "uint3", "int5", "uint5", "int6", "uint6", "int7", "uint7", "uint4", "float6_e3m2fn", "float7_e3m3fn",
+                                "float5_e2m2fn", "float4_e2m1fn", "float7_e4m2fn", "float6_e2m3fn", "float3_e1m1fn", "float5_e3m2fnu"])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (77, 640, 2048), (300, 1288, 640), (1000, 384, 1280)])
+def test_scaled_mm_packed_any_width(wd, M, N, K):
+    """2..7-bit integer / minifloat weights expanded by the GEMM's unpack warps == the unpack kernel's operand through the plain GEMM,
+    bit for bit (same codes, same accumulator, same epilogue)."""
+    from sdnq_b200.common import dtype_dict
+    info = dtype_dict.get(wd)
+    if info is None:
+        pytest.skip(f"{wd} is not a storage format of this build")
+    bits = info["num_bits"]
+    if (K * bits) % 128 != 0:
+        pytest.skip("row pitch of the packed rows is not a multiple of 16 bytes")
+    rng = np.random.default_rng(M + N + K + bits)
+    codes = rng.integers(0, 2 ** bits, size=(N, K))
+    packed = torch.from_numpy(O.pack_uint(codes, bits).astype(np.uint8)).to(DEV)
+    sx = torch.from_numpy((rng.random(M) * 0.05 + 1e-3).astype(np.float32)).to(DEV)
+    sw = torch.from_numpy((rng.random(N) * 0.01 + 1e-4).astype(np.float32)).to(DEV)
+    bias = torch.from_numpy(rng.standard_normal(N).astype(np.float32)).to(torch.bfloat16).to(DEV)
+    kw = {}
+    if info["is_integer"]:
+        a = torch.from_numpy(rng.integers(-128, 128, size=(M, K)).astype(np.int8)).to(DEV)
+        b = ops().unpack(packed, wd, (N, K), dtype=torch.int8)
+        if info["is_unsigned"]:
+            kw = dict(zp=torch.from_numpy((rng.standard_normal(N) * 0.1).astype(np.float32)).to(DEV), rowsum=a.to(torch.int32).sum(dim=1, dtype=torch.int32))
+        else:
+            assert int(b.min()) == -(2 ** (bits - 1)) and int(b.max()) == 2 ** (bits - 1) - 1
+    else:
+        a = torch.from_numpy(rng.standard_normal((M, K)).astype(np.float32)).to(torch.float8_e4m3fn).to(DEV)
+        b = ops().unpack(packed, wd, (N, K), dtype=torch.float8_e4m3fn)
+        assert torch.equal(b.float(), ops().unpack(packed, wd, (N, K), dtype=torch.float32))       # the format is a subset of e4m3
+    for out_dtype in (torch.bfloat16, torch.float32):
+        want = ops().scaled_mm(a, b, sx, sw, bias, out_dtype, **kw)
+        got = ops().scaled_mm_packed(a, packed, wd, N, sx, sw, bias, out_dtype, **kw)
+        assert torch.equal(got, want), float((got.float() - want.float()).abs().max())
+
+
 # ----------------------------------------------------------------------------------------------- SVD branch of the W8A8 forwards (K7 + rank-r accumulate in K1)
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("M,K,r", [(1, 16, 8), (77, 2048, 32), (130, 640, 16), (1024, 1280, 32), (333, 1296, 64), (40, 3072, 24), (16, 48, 32)])
