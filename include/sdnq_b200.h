@@ -260,6 +260,20 @@ SDNQ_API size_t sdnq_b200_dequant_batch_table_bytes(int n_jobs);
 SDNQ_API int sdnq_b200_dequant_batch_plan(const sdnq_dequant_job* jobs, int n_jobs, void* host_table, int32_t* info);
 SDNQ_API int sdnq_b200_dequant_batch_run(const void* device_table, const int32_t* info, void* stream);
 
+/* ---- K8 load-time quantisation of a weight: scale, round, clamp and pack in one pass (the middle of sdnq_quantize_layer_weight,
+ *      quantizer.py:236-253: quantize_weight, quant_utils.py:27-56, then pack_int, packed_int/__init__.py:76-80 + pack.py:201-321).
+ *   w            [N,K] row-major f32 / bf16 / f16 (after the optional Hadamard rotation / SVD subtraction, which stay host-side);
+ *                K % 8 == 0, 16-byte aligned
+ *   group_size   scale groups of that many consecutive weights along K (a multiple of 8 dividing K); <= 0 or >= K: row-wise
+ *   fmt          integer formats of 2..8 bits: symmetric  scale = amax / qmax,  q = round_half_even(w / scale)  for signed formats,
+ *                asymmetric  scale = (max - min) / qmax, zero_point = min,  q = round_half_even((w - zero_point) / scale)  for unsigned
+ *                ones; true f32 divisions, clamp to the format's range -- the arithmetic of the reference on the CPU, bit for bit
+ *   scale_dtype  SDNQ_F32, or SDNQ_BF16 / SDNQ_F16: scale and zero point are rounded to that type before the division (dequantize_fp32=False)
+ *   codes        bits < 8: N*K*bits/8 packed bytes (signed codes offset-binary);  bits == 8: N*K one-byte codes (int8 two's complement / uint8)
+ *   scale, zero_point   f32 [N * K / group_size]  (zero_point written for unsigned formats only) */
+SDNQ_API int sdnq_b200_quantize_weight(const void* w, int w_dtype, int64_t N, int64_t K, int64_t group_size, const sdnq_weight_format* fmt,
+                                       int scale_dtype, void* codes, float* scale, float* zero_point, void* stream);
+
 /* ---- K5 small-M Linear on 8-bit weights ("W8A16 GEMV"):  the rows < 32 branch of every quantized-matmul forward
  *      (linear_int8.py:102-103, linear_uint8.py:107-108, linear_fp8.py:83-84: dequantise the weight, then F.linear) without
  *      materialising the dequantised weight:

@@ -48,6 +48,7 @@ SIGNATURES = {
     "sdnq_b200_dequant_batch_table_bytes": (_Z, [_I]),
     "sdnq_b200_dequant_batch_plan": (_I, [_P, _I, _P, _P]),
     "sdnq_b200_dequant_batch_run": (_I, [_P, _P, _P]),
+    "sdnq_b200_quantize_weight": (_I, [_P, _I, _L, _L, _L, _WF, _I, _P, _P, _P, _P]),
     "sdnq_b200_requant": (_I, [_P, _WF, _P, _P, _I, _L, _L, _L, _I, _P, _P, _P, _P, _P]),
     "sdnq_b200_act_quant": (_I, [_P, _I, _L, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P]),
     "sdnq_b200_conv_act_quant": (_I, [_P, _I, ctypes.POINTER(Conv2dGeometry), _I, _I, _P, _P, _P, _P, _P, _P]),

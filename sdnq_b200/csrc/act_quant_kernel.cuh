@@ -388,7 +388,7 @@ int launch_mode(const ActArgs& a, cudaStream_t st) {
     constexpr int RPC = kWarps / WPR;
     const int64_t nblk = (a.M + RPC - 1) / RPC;
     // a few waves of resident CTAs walk the row blocks (SDNQ_B200_ACTQ_GRID = CTAs per SM of grid; 0 = one CTA per row block)
-    static const int per_sm = [] { const char* e = getenv("SDNQ_B200_ACTQ_GRID"); return e != nullptr ? atoi(e) : 16; }();
+    static const int per_sm = [] { const char* e = getenv("SDNQ_B200_ACTQ_GRID"); return e != nullptr ? atoi(e) : 32; }();
     const int64_t cap = per_sm > 0 ? int64_t(num_sms()) * per_sm : nblk;
     const unsigned blocks = static_cast<unsigned>(nblk < cap ? nblk : cap);
     cudaError_t e;

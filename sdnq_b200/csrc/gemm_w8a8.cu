@@ -134,7 +134,7 @@ int scaled_mm_impl(const void* a, const void* b, int ab_dtype, GemmParams p, cud
             SDNQ_REQUIRE(i8, SDNQ_EUNSUPPORTED, "packed integer weights need int8 activations");
             return launch_gemm_packed4(a, b, p, st);
         }
-        SDNQ_REQUIRE(p.svd_rank == 0 && p.n_groups == 0, SDNQ_EUNSUPPORTED, "SVD / grouped launches take 4-bit or unpacked weights");
+        SDNQ_REQUIRE(p.svd_rank == 0, SDNQ_EUNSUPPORTED, "the SVD accumulate takes 4-bit or unpacked weights");
         SDNQ_REQUIRE(p.pk_kind == 0 ? i8 : ab_dtype == SDNQ_F8E4M3, SDNQ_EUNSUPPORTED, "packed integer weights need int8 activations, packed minifloats float8_e4m3fn ones");
         return launch_gemm_packed_any(a, b, p, st);
     }
@@ -196,29 +196,39 @@ extern "C" int sdnq_b200_scaled_mm(const void* a, const void* b, int ab_dtype, c
     return scaled_mm_impl(a, b, ab_dtype, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int sdnq_b200_scaled_mm_packed(const void* a, const void* b_packed, const sdnq_weight_format* b_fmt, const float* sx, const float* sw,
-                                          const void* bias, int bias_dtype, int64_t bias_ld, const int32_t* rowsum, const float* zp, void* out,
-                                          int out_dtype, int64_t M, int64_t N, int64_t K, void* stream) {
-    SDNQ_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), SDNQ_EUNSUPPORTED, "dimension too large");
+// packed storage format -> the GEMM's prologue parameters; *ab = operand dtype of the activations, *wbits = storage bits
+static int packed_params(const sdnq_weight_format* b_fmt, const float* zp, const int32_t* rowsum, GemmParams& p, int* ab, int* wbits) {
     WFormat f;
     int rc = make_wformat(b_fmt, &f);
     if (rc != SDNQ_OK) return rc;
     SDNQ_REQUIRE(f.bits >= 2 && f.bits <= 7 && f.word_bytes == 1 && (f.kind == SDNQ_W_INT || f.kind == SDNQ_W_MINIFLOAT), SDNQ_EUNSUPPORTED,
-                 "scaled_mm_packed: 2..7-bit integer or minifloat weights are expanded in-kernel (got kind %d, %d bits)", f.kind, f.bits);
-    GemmParams p{sx, sw, bias, bias_dtype, bias_ld, rowsum, zp, nullptr, nullptr, out, out_dtype, (int)M, (int)N, (int)K, 0, 0u, 0u};
-    p.pk_bits = f.bits;
+                 "packed weights: 2..7-bit integer or minifloat codes are expanded in-kernel (got kind %d, %d bits)", f.kind, f.bits);
+    p.pk_bits = *wbits = f.bits;
     if (f.kind == SDNQ_W_INT) {
         SDNQ_REQUIRE(f.is_unsigned == 0 || (zp != nullptr && rowsum != nullptr), SDNQ_EINVAL, "unsigned integer weights need zp and rowsum");
         p.pk_kind = 0;
         p.w_sub = f.is_unsigned ? 0u : 0x01010101u * static_cast<uint32_t>(1 << (f.bits - 1));     // offset-binary -> two's complement
-        return scaled_mm_impl(a, b_packed, SDNQ_I8, p, reinterpret_cast<cudaStream_t>(stream), f.bits);
+        *ab = SDNQ_I8;
+        return SDNQ_OK;
     }
-    SDNQ_REQUIRE(f.exponent <= 4 && f.mantissa <= 3, SDNQ_EUNSUPPORTED, "scaled_mm_packed: e%dm%d is not a subset of e4m3", f.exponent, f.mantissa);
+    SDNQ_REQUIRE(f.exponent <= 4 && f.mantissa <= 3, SDNQ_EUNSUPPORTED, "packed weights: e%dm%d is not a subset of e4m3", f.exponent, f.mantissa);
     p.pk_kind = 1;
     p.pk_exp = f.exponent;
     p.pk_man = f.mantissa;
     p.pk_unsigned = f.is_unsigned;
-    return scaled_mm_impl(a, b_packed, SDNQ_F8E4M3, p, reinterpret_cast<cudaStream_t>(stream), f.bits);
+    *ab = SDNQ_F8E4M3;
+    return SDNQ_OK;
+}
+
+extern "C" int sdnq_b200_scaled_mm_packed(const void* a, const void* b_packed, const sdnq_weight_format* b_fmt, const float* sx, const float* sw,
+                                          const void* bias, int bias_dtype, int64_t bias_ld, const int32_t* rowsum, const float* zp, void* out,
+                                          int out_dtype, int64_t M, int64_t N, int64_t K, void* stream) {
+    SDNQ_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), SDNQ_EUNSUPPORTED, "dimension too large");
+    GemmParams p{sx, sw, bias, bias_dtype, bias_ld, rowsum, zp, nullptr, nullptr, out, out_dtype, (int)M, (int)N, (int)K, 0, 0u, 0u};
+    int ab = SDNQ_I8, wbits = 8;
+    int rc = packed_params(b_fmt, zp, rowsum, p, &ab, &wbits);
+    if (rc != SDNQ_OK) return rc;
+    return scaled_mm_impl(a, b_packed, ab, p, reinterpret_cast<cudaStream_t>(stream), wbits);
 }
 
 extern "C" int sdnq_b200_mm(const void* a, const void* b, int ab_dtype, void* out, int64_t M, int64_t N, int64_t K, void* stream) {
@@ -256,16 +266,13 @@ extern "C" int sdnq_b200_scaled_mm_grouped(const void* a, const void* b_cat, int
     SDNQ_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups, SDNQ_EUNSUPPORTED, "grouped launch: 1..%d siblings (got %d)", kMaxGroups, n_groups);
     SDNQ_REQUIRE(seg_start && seg_n && outs, SDNQ_EINVAL, "NULL pointer");
     SDNQ_REQUIRE(M < (1LL << 31) && K < (1LL << 31) && seg_start[n_groups] < (1LL << 31), SDNQ_EUNSUPPORTED, "dimension too large");
-    uint32_t w_sub = 0u;
+    GemmParams p{sx, sw_cat, bias_cat, bias_dtype, 0, rowsum, zp_cat, colsum_cat, zx, outs[0], out_dtype, (int)M, (int)seg_start[n_groups], (int)K, 0, 0u,
+                 ab_dtype == SDNQ_F8E5M2 ? 1u : 0u};
     int wbits = 8;
     if (b_fmt != nullptr) {
-        SDNQ_REQUIRE(b_fmt->kind == SDNQ_W_INT && b_fmt->bits == 4, SDNQ_EUNSUPPORTED, "scaled_mm_grouped: packed weights must be int4 / uint4");
-        SDNQ_REQUIRE(b_fmt->is_unsigned == 0 || (zp_cat != nullptr && rowsum != nullptr), SDNQ_EINVAL, "uint4 weights need zp and rowsum");
-        w_sub = b_fmt->is_unsigned ? 0u : 0x08080808u;
-        wbits = 4;
+        int rc = packed_params(b_fmt, zp_cat, rowsum, p, &ab_dtype, &wbits);
+        if (rc != SDNQ_OK) return rc;
     }
-    GemmParams p{sx, sw_cat, bias_cat, bias_dtype, 0, rowsum, zp_cat, colsum_cat, zx, outs[0], out_dtype, (int)M, (int)seg_start[n_groups], (int)K, 0, w_sub,
-                 ab_dtype == SDNQ_F8E5M2 ? 1u : 0u};
     p.n_groups = n_groups;
     SDNQ_REQUIRE(seg_start[0] == 0, SDNQ_EINVAL, "grouped launch: the first segment starts at 0");
     for (int g = 0; g < n_groups; ++g) {
@@ -279,5 +286,5 @@ extern "C" int sdnq_b200_scaled_mm_grouped(const void* a, const void* b_cat, int
     }
     SDNQ_REQUIRE(seg_start[n_groups] % 128 == 0, SDNQ_EINVAL, "grouped launch: the concatenated operand must end at a multiple of 128 rows");
     p.grp_start[n_groups] = (int)seg_start[n_groups];
-    return scaled_mm_impl(a, b_cat, wbits == 4 ? SDNQ_I8 : ab_dtype, p, reinterpret_cast<cudaStream_t>(stream), wbits);
+    return scaled_mm_impl(a, b_cat, ab_dtype, p, reinterpret_cast<cudaStream_t>(stream), wbits);
 }

@@ -265,6 +265,28 @@ def dequant_nd(weight, weights_dtype, scale, zero_point, view_shape, out_dtype, 
     return out
 
 
+def quantize_weight(w: torch.Tensor, weights_dtype: str, group_size: int = -1, scale_dtype: torch.dtype | None = None):
+    """K8.  w [N,K] f32 / bf16 / f16 -> (codes, scale [N, K/g] f32, zero_point [N, K/g] f32 | None): `codes` is the packed uint8
+    buffer (sub-byte formats) or the [N,K] int8 / uint8 code matrix (8-bit formats) exactly as quantize_weight + pack_int produce them."""
+    _require_cuda(w)
+    info = dtype_dict[weights_dtype]
+    if not info["is_integer"] or not 2 <= info["num_bits"] <= 8:
+        raise _lib.SDNQKernelError(f"quantize_weight: {weights_dtype!r} has no quantisation kernel (integer formats of 2..8 bits)")
+    N, K = w.shape
+    w = w.contiguous()
+    if w.data_ptr() % 16 != 0:
+        w = w.clone()
+    g = K if group_size <= 0 or group_size >= K else int(group_size)
+    bits = info["num_bits"]
+    codes = torch.empty((N, K), dtype=info["torch_dtype"], device=w.device) if bits == 8 else torch.empty(N * K * bits // 8, dtype=torch.uint8, device=w.device)
+    scale = torch.empty((N, K // g), dtype=torch.float32, device=w.device)
+    zp = torch.empty((N, K // g), dtype=torch.float32, device=w.device) if info["is_unsigned"] else None
+    with torch.cuda.device(w.device):
+        check(_lib.load().sdnq_b200_quantize_weight(_ptr(w), dtype_code(w.dtype), N, K, g, weight_format(weights_dtype), dtype_code(scale_dtype or torch.float32),
+                                                    _ptr(codes), _ptr(scale), _ptr(zp), _stream(w)))
+    return codes, scale, zp
+
+
 def requant(weight, weights_dtype, scale, zero_point, N, K, group_size, matmul_dtype, use_codebook=False, want_colsum=False):
     """K4.  Returns (wq [N,K] physical, sw [N], zw [N] | None, colsum [N] | None)."""
     _require_cuda(weight, scale)
@@ -456,7 +478,7 @@ def scaled_mm_grouped(a: torch.Tensor, b_cat: torch.Tensor, sx, sw_cat, starts, 
         assert b_cat.shape[1] == K
         ab, fmt = _operand_code(a.dtype, b_cat), None
     else:
-        ab, fmt = SDNQ_I8, weight_format(packed_dtype, b_cat)
+        ab, fmt = (SDNQ_I8 if a.dtype == torch.int8 else SDNQ_F8E4M3), weight_format(packed_dtype, b_cat)
     bias_code = dtype_code(bias_cat.dtype) if bias_cat is not None else SDNQ_F32
     starts_c = (ctypes.c_int64 * (G + 1))(*[int(v) for v in starts])
     ns_c = (ctypes.c_int64 * G)(*[int(v) for v in ns])

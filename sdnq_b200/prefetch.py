@@ -31,7 +31,7 @@ def enabled() -> bool:
 
 
 def _budget_bytes() -> int:
-    return max(16, int(os.environ.get("SDNQ_B200_PREFETCH_MB", "160"))) << 20
+    return max(16, int(os.environ.get("SDNQ_B200_PREFETCH_MB", "256"))) << 20
 
 
 def eligible(layer, dtype) -> bool:

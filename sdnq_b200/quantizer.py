@@ -59,6 +59,19 @@ def _fit_group_size(group_size: int, channel_size: int):
 
 
 @torch.no_grad()
+def _quant_kernel_ok(weight, winfo, is_linear, reduction_axes, use_codebook, stochastic) -> bool:
+    """K8 covers Linear weights on a CUDA device, integer formats of 2..8 bits, scale groups along K that are multiples of 8 (or
+    row-wise), round-to-nearest.  SDNQ_B200_QUANT_KERNEL=0 keeps the eager tensor ops."""
+    import os
+    if os.environ.get("SDNQ_B200_QUANT_KERNEL", "1") in ("0", "false", "no") or not weight.is_cuda or not is_linear or use_codebook or stochastic:
+        return False
+    if not winfo["is_integer"] or not 2 <= winfo["num_bits"] <= 8 or reduction_axes != -1 or weight.ndim not in (2, 3):
+        return False
+    if weight.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        return False
+    return weight.shape[-1] % 8 == 0
+
+
 def sdnq_quantize_layer_weight(
     weight: torch.Tensor,
     layer_class_name: str | None = None,
@@ -165,7 +178,25 @@ def sdnq_quantize_layer_weight(
     cast_scale = not (transpose_weights and not USE_TENSORWISE_FP8_MATMUL and not minfo["is_integer"])
     cast_to = scale_dtype if cast_scale else None
 
-    if use_codebook:
+    packed_by_kernel = False
+    if _quant_kernel_ok(weight, winfo, is_linear, reduction_axes, use_codebook, use_stochastic_rounding and not skip_sr):
+        # K8: scale + round + clamp + pack in one pass over the weight on the GPU (csrc/weight_quant.cu) -- the arithmetic of
+        # quantize_weight + pack_int below, bit for bit
+        from . import ops
+        view_shape = weight.shape
+        codes, scale, zero_point = ops.quantize_weight(weight.reshape(out_ch, -1), weights_dtype, group_size if num_groups > 1 else -1, cast_to)
+        scale = scale.view(*view_shape[:-1], 1)
+        zero_point = None if zero_point is None else zero_point.view(*view_shape[:-1], 1)
+        if cast_to is not None:
+            scale = scale.to(cast_to)
+            zero_point = None if zero_point is None else zero_point.to(cast_to)
+        if winfo["is_packed"]:
+            words = {2: 1, 4: 1, 3: 3, 5: 5, 6: 3, 7: 7}[winfo["num_bits"]]
+            packed_weight, packed_by_kernel = (codes if words == 1 else codes.view(-1, words)), True
+            weight = torch.empty(view_shape, dtype=torch.uint8, device="meta")       # only its shape is used below
+        else:
+            weight = codes.view(view_shape)
+    elif use_codebook:
         weight, scale = quantize_weight_codebook(weight, reduction_axes, weights_dtype, dtype=cast_to, steps=codebook_steps)
         zero_point = None
     else:
@@ -180,7 +211,9 @@ def sdnq_quantize_layer_weight(
         weight = prepare_weight_for_matmul(weight, matmul_dtype=quantized_matmul_dtype)
 
     quantized_weight_shape = weight.shape
-    if winfo["is_packed"]:
+    if packed_by_kernel:
+        weight = packed_weight
+    elif winfo["is_packed"]:
         weight = pack_int(weight, weights_dtype) if winfo["is_integer"] else pack_float(weight, weights_dtype)
     else:
         weight = weight.to(dtype=winfo["torch_dtype"])

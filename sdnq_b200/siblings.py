@@ -75,8 +75,6 @@ class SiblingGroup:
         if any(o.packed != packed or (o.zp is None) != (first.zp is None) or (o.colsum is None) != (first.colsum is None)
                or o.wq.dtype != first.wq.dtype or o.wq.device != first.wq.device for o in ops_now):
             return False
-        if packed is not None and dtype_dict[packed]["num_bits"] != 4:
-            return False                     # the grouped launch expands 4-bit codes only
         K = self.layers[0].sdnq_dequantizer.matmul_nk()[1]
         ns = [layer.sdnq_dequantizer.matmul_nk()[0] for layer in self.layers]
         if any(n % 8 for n in ns):
@@ -86,7 +84,7 @@ class SiblingGroup:
         for n in ns:
             starts.append(starts[-1] + (n + align - 1) // align * align)
         dev = first.wq.device
-        row_bytes = K // 2 if packed is not None else K
+        row_bytes = K * dtype_dict[packed]["num_bits"] // 8 if packed is not None else K
         wq_cat = torch.zeros((starts[-1], row_bytes), dtype=first.wq.dtype, device=dev)
 
         def cat_vec(vals, dtype):

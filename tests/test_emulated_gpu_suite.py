@@ -285,3 +285,14 @@ def test_dynamic_quantization(kw):
 def test_svd_low(kw):
     K.test_svd_low(**kw)
 
+
+
+# ---- K8 (weight_quant.cu): load-time quantise + pack against the host arithmetic and the reference fixtures
+@emulated(K.test_quantize_weight_matches_host_arithmetic, keep=lambda kw: kw["N"] * kw["K"] <= 33 * 640)
+def test_quantize_weight(kw):
+    K.test_quantize_weight_matches_host_arithmetic(**kw)
+
+
+@emulated(K.test_quantize_weight_reproduces_reference_fixture)
+def test_quantize_weight_fixture(kw):
+    K.test_quantize_weight_reproduces_reference_fixture(**kw)

@@ -526,6 +526,54 @@ def test_scaled_mm_packed_any_width(wd, M, N, K):
         assert torch.equal(got, want), float((got.float() - want.float()).abs().max())
 
 
+# ----------------------------------------------------------------------------------------------- load-time quantisation (K8)
+@pytest.mark.parametrize("wd", ["int8", "uint8", "int7", "uint7", "int6", "uint6", "int5", "uint5", "int4", "uint4", "int3", "uint3", "int2", "uint2"])
+@pytest.mark.parametrize("N,K,gs", [(64, 256, 32), (33, 640, 128), (16, 1024, -1), (5, 2048, 256), (7, 96, 8), (3, 4104, -1), (9, 1536, 512), (2, 64, 16)])
+def test_quantize_weight_matches_host_arithmetic(wd, N, K, gs):
+    """scale + round + clamp + pack in one kernel == quant_math.quantize_weight + packing.pack_int on the CPU (the reference's
+    arithmetic, pinned to its fixtures by tests/test_host_api.py): same packed bytes, same scales, same zero points."""
+    from sdnq_b200 import packing, quant_math
+    from sdnq_b200.common import dtype_dict
+    info = dtype_dict[wd]
+    g = torch.Generator().manual_seed(N * 7 + K + info["num_bits"])
+    for wdtype, scale_dtype in ((torch.float32, None), (torch.bfloat16, None), (torch.float32, torch.bfloat16)):
+        w = (torch.randn(N, K, generator=g) * torch.rand(N, 1, generator=g) * 3).to(wdtype)
+        w[0, : (K if gs <= 0 else gs)] = 0                                        # an all-zero group: 0 / 0 -> code of 0
+        w[-1, -1] = 1e4                                                           # an outlier
+        groups = 1 if gs <= 0 else K // gs
+        view = w.float().view(N, groups, K // groups)
+        q, s_ref, z_ref = quant_math.quantize_weight(view, -1, wd, dtype=scale_dtype)
+        want = packing.pack_int(q, wd).reshape(-1).view(torch.uint8) if info["is_packed"] else q.reshape(-1).view(torch.uint8)
+        codes, scale, zp = ops().quantize_weight(w.to(DEV), wd, gs, scale_dtype)
+        assert np.array_equal(scale.cpu().numpy().reshape(-1), s_ref.float().numpy().reshape(-1)), "scale"
+        if info["is_unsigned"]:
+            assert np.array_equal(zp.cpu().numpy().reshape(-1), z_ref.float().numpy().reshape(-1)), "zero point"
+        else:
+            assert zp is None and z_ref is None
+        assert np.array_equal(codes.cpu().reshape(-1).view(torch.uint8).numpy(), want.numpy()), "codes"
+
+
+@pytest.mark.parametrize("path", [p for p in LAYER_FILES if "small_m" not in p], ids=[i for p, i in zip(LAYER_FILES, LAYER_IDS) if "small_m" not in p])
+def test_quantize_weight_reproduces_reference_fixture(path):
+    """the stored `weight` / `scale` / `zero_point` bytes of a layer the reference quantised, from its float weight"""
+    t, z, meta = fixture_tensors(path)
+    d = meta["dequantizer"]
+    from sdnq_b200.common import dtype_dict
+    info = dtype_dict[d["weights_dtype"]]
+    if (not info["is_integer"] or info["num_bits"] < 2 or info["num_bits"] > 8 or d.get("use_hadamard") or d.get("use_codebook") or t["svd_up"] is not None
+            or d["group_size"] == -2):
+        pytest.skip("outside the first slice of the quantisation kernel (integer formats without rotation / SVD / codebook)")
+    N, K = meta["N"], meta["K"]
+    gs = d["group_size"]
+    codes, scale, zp = ops().quantize_weight(t["w_orig"].to(DEV), d["weights_dtype"], gs if gs > 0 else -1, None if t["scale"].dtype == torch.float32 else t["scale"].dtype)
+    stored = t["weight"]
+    stored = ops().physical_nk(stored) if stored.ndim == 2 and not info["is_packed"] else stored
+    assert np.array_equal(codes.cpu().reshape(-1).view(torch.uint8).numpy(), stored.contiguous().reshape(-1).view(torch.uint8).numpy())
+    assert np.array_equal(scale.cpu().numpy().reshape(-1), t["scale"].float().numpy().reshape(-1))
+    if t["zero_point"] is not None:
+        assert np.array_equal(zp.cpu().numpy().reshape(-1), t["zero_point"].float().numpy().reshape(-1))
+
+
 # ----------------------------------------------------------------------------------------------- SVD branch of the W8A8 forwards (K7 + rank-r accumulate in K1)
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("M,K,r", [(1, 16, 8), (77, 2048, 32), (130, 640, 16), (1024, 1280, 32), (333, 1296, 64), (40, 3072, 24), (16, 48, 32)])

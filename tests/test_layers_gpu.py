@@ -227,3 +227,47 @@ def test_dynamic_quantization_picks_the_reference_dtypes(name):
     x = torch.randn(40, 128, dtype=torch.bfloat16, device=DEV)
     y, yd = model.mid[0].ff(x), dense.mid[0].ff(x)
     assert float((y.float() - yd.float()).pow(2).mean().sqrt()) <= 0.1 * float(yd.float().pow(2).mean().sqrt())
+
+
+@pytest.mark.parametrize("cfg", [dict(weights_dtype="int8", use_quantized_matmul=True), dict(weights_dtype="uint8", use_quantized_matmul=True),
+                                 dict(weights_dtype="uint4"), dict(weights_dtype="int4", group_size=128, use_svd=True, svd_rank=32),
+                                 dict(weights_dtype="int6", use_quantized_matmul=True), dict(weights_dtype="int5", group_size=32),
+                                 dict(weights_dtype="uint3", group_size=64, dequantize_fp32=False), dict(weights_dtype="int2", group_size=16),
+                                 dict(weights_dtype="int8", use_quantized_matmul=True, use_hadamard=True, hadamard_group_size=128)],
+                         ids=lambda c: "_".join(str(v) for v in c.values()))
+def test_quantising_on_the_gpu_stores_what_the_cpu_path_stores(cfg, monkeypatch):
+    """sdnq_quantize_layer on a CUDA weight goes through K8 (scale + round + clamp + pack in one kernel); the stored tensors are the
+    ones the host arithmetic (the reference's, on the CPU) produces.  SVD layers: the factors come from a randomised decomposition, so the
+    comparison is made on the kernel's input (the residual weight) by running the eager ops on the same device."""
+    from sdnq_b200 import SDNQConfig, _lib, sdnq_quantize_layer
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(640, 384).to(torch.bfloat16)
+    if cfg.get("use_svd") or cfg.get("use_hadamard"):
+        ref_dev = DEV              # same device, eager ops vs kernel
+    else:
+        ref_dev = "cpu"
+    monkeypatch.setenv("SDNQ_B200_QUANT_KERNEL", "0")
+    torch.manual_seed(11)
+    ref, _ = sdnq_quantize_layer(copy.deepcopy(lin).to(ref_dev), SDNQConfig(**cfg))
+    monkeypatch.setenv("SDNQ_B200_QUANT_KERNEL", "1")
+    _lib.launch_count(reset=True)
+    torch.manual_seed(11)
+    got, _ = sdnq_quantize_layer(copy.deepcopy(lin).to(DEV), SDNQConfig(**cfg))
+    assert _lib.launch_count() >= 1
+    for name in ("weight", "scale", "zero_point"):
+        a, b = getattr(got, name), getattr(ref, name)
+        assert (a is None) == (b is None), name
+        if a is None:
+            continue
+        assert a.dtype == b.dtype and a.shape == b.shape and a.stride() == b.stride(), (name, a.dtype, b.dtype, a.shape, b.shape, a.stride(), b.stride())
+        if ref_dev == "cpu":
+            assert torch.equal(a.cpu(), b.cpu()), name
+        else:
+            # eager CUDA divides by a scalar through its reciprocal; the kernel divides: scales may differ in the last bit, codes by one
+            if a.is_floating_point():
+                assert torch.allclose(a.float(), b.float(), rtol=2e-7 if a.dtype == torch.float32 else 0, atol=0), name
+            else:
+                diff = (a.view(torch.uint8).int() - b.view(torch.uint8).int()).abs()
+                assert float((diff != 0).float().mean()) < 1e-3, name
+    x = torch.randn(64, 640, device=DEV, dtype=torch.bfloat16)
+    assert torch.isfinite(got(x)).all()
