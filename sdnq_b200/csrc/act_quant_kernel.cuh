@@ -63,7 +63,7 @@ __device__ __forceinline__ uint32_t pack16(T a, T b) {
 // kTC: the rotation runs on the tensor cores (hadamard_tc.cuh; 16-bit activations).  The lane then owns elements
 // [4l, 4l+4) and [128+4l, 128+4l+4) of a chunk (two coalesced 8-byte accesses) instead of [8l, 8l+8).
 template <typename T, int WPR, int MAXC, int MODE, bool kTC, bool kConv>
-__global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC ? 4 : 5) : (kTC ? 2 : 3)) act_quant_kernel(const ActArgs a) {
+__global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kConv ? (kTC ? 4 : 5) : 3) : (kTC ? 2 : 3)) act_quant_kernel(const ActArgs a) {
     constexpr int RPC = kWarps / WPR;                 // rows per CTA and pass
     // the cross-warp exchange buffers alternate between passes of the row loop: one barrier per pass is enough
     __shared__ float s_a2[2][RPC][WPR];
@@ -79,8 +79,35 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC
     // Row loop: the grid is a few CTAs per SM and every CTA walks row blocks blockIdx.x, blockIdx.x + gridDim.x, ... -- the per-CTA
     // set-up (rotation constants, dependency wait, argument loads) is paid once, not once per pair of rows.
     const int64_t nblk = (a.M + RPC - 1) / RPC;
+    // Linear rows of 16-bit activations: the NEXT row block's chunks are loaded before this one is reduced, quantised and stored
+    // (register double buffer), so the SM keeps loads in flight through the statistics barrier and the store phase -- without it
+    // every CTA alternates between a load burst and a phase with nothing outstanding, and the kernel sits at ~0.55 of the copy rate.
+    constexpr bool kPrefetch = !kConv && sizeof(T) == 2;
+    constexpr int kStep = WPR * 256;                                  // column distance between this warp's consecutive chunks
+    const int kb = w_in * 256 + lane * (kTC ? 4 : 8);                 // this lane's first column
+    auto load_linear = [&](int64_t blk_i, Held<T> (&h)[MAXC]) {
+        const int64_t row_i = blk_i * RPC + r_in;
+        const int lim_i = (blk_i < nblk && row_i < a.M) ? static_cast<int>(a.K) - kb : 0;
+        const T* xp_i = reinterpret_cast<const T*>(a.x) + row_i * a.ldx + kb;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            if constexpr (kTC) {
+                uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
+                if (c * kStep < lim_i) lo = *reinterpret_cast<const uint2*>(xp_i + c * kStep);
+                if (c * kStep + 128 < lim_i) hi = *reinterpret_cast<const uint2*>(xp_i + c * kStep + 128);
+                h[c].raw = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+                if (c * kStep < lim_i) h[c].load(xp_i + c * kStep);
+                else h[c].zero();
+            }
+        }
+    };
+    Held<T> held[MAXC];
+    [[maybe_unused]] Held<T> ahead[MAXC];
+    if constexpr (kPrefetch) load_linear(blockIdx.x, held);
     int pass = 0;
     for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x, pass ^= 1) {
+    if constexpr (kPrefetch) load_linear(blk + gridDim.x, ahead);
     float (&s_a)[RPC][WPR] = s_a2[pass];
     float (&s_b)[RPC][WPR] = s_b2[pass];
     int (&s_sum)[RPC][WPR] = s_sum2[pass];
@@ -100,16 +127,14 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC
 
     // Per-thread bases; inside the unrolled loops every address is base + a compile-time offset and every validity test is
     // one compare against a constant (hoisted by hand: under the register cap the compiler re-derived them per chunk).
-    constexpr int kStep = WPR * 256;                                  // column distance between this warp's consecutive chunks
-    const int kb = w_in * 256 + lane * (kTC ? 4 : 8);                 // this lane's first column
     const int lim = row_ok ? K - kb : 0;                              // chunk c holds data for this lane iff c * kStep < lim
     const int wlim = row_ok ? K - w_in * 256 : 0;                     // ... for this warp (uniform)
     const T* xp = xrow + (kConv ? 0 : kb);
     uint8_t* qp = a.xq + row * a.K + kb;
     T* rp = a.x_rot != nullptr ? reinterpret_cast<T*>(a.x_rot) + row * a.K + kb : nullptr;
 
-    Held<T> held[MAXC];
     // all loads of the row first (memory-level parallelism), statistics afterwards
+    if constexpr (!kPrefetch)
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
         if constexpr (kTC) {
@@ -257,6 +282,10 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC
     if (row_ok && w_in == 0 && lane == 0) {
         a.sx[row] = scale;
         if (a.zx != nullptr) a.zx[row] = zero;
+    }
+    if constexpr (kPrefetch) {
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) held[c] = ahead[c];
     }
     }   // row loop
 }

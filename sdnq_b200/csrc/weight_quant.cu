@@ -10,7 +10,7 @@
 // weights (one octet of the packed layout), the scale group is reduced with warp shuffles (groups of 8..256 weights) or by the
 // CTA (row-wise / wider groups, second read from L2), and the packed bytes are written directly: HBM traffic = the weight once
 // in its own dtype + bits/8 bytes per weight out.
-#include "common.cuh"
+#include "act_quant.cuh"     // actq::RowDivider: correctly rounded x / s with the reciprocal hoisted out of the element loop
 #include "unpack.cuh"
 
 namespace sdnq {
@@ -100,8 +100,11 @@ __device__ __forceinline__ void quantise_store(const WQArgs& a, int64_t oct, con
     uint32_t codes[8];
     const int offset = (a.packed && !a.is_unsigned) ? static_cast<int>(a.qmin) : 0;      // packed signed codes are offset-binary
 #pragma unroll
+    const actq::RowDivider divider(scale);
+    const bool safe = divider.safe();
     for (int i = 0; i < 8; ++i) {
-        float q = __fdiv_rn(a.is_unsigned ? __fsub_rn(v[i], zero) : v[i], scale);
+        const float num = a.is_unsigned ? __fsub_rn(v[i], zero) : v[i];
+        float q = safe ? divider.div<true>(num) : divider.div<false>(num);
         const bool nan = !(q == q);                             // 0 / 0 of an all-zero group: NaN survives round_ / clamp_, the int cast makes it 0
         q = fminf(fmaxf(rintf(q), a.qmin), a.qmax);
         const int c = nan ? 0 : static_cast<int>(q);

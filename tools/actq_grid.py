@@ -20,6 +20,6 @@ for (M, K, mode, hg) in [(16384, 3072, "float8_e4m3fn", 256), (18432, 3072, "flo
     t = graph_time(run) / count * 1e3
     print(f"grid={os.environ.get('SDNQ_B200_ACTQ_GRID')}: {M}x{K} {mode} hadamard={hg}: {t:8.2f} us  {3.0 * M * K / t / 1e6:6.2f} TB/s", flush=True)
 ''' % ROOT
-for grid in ("0", "4", "8", "16", "32"):
+for grid in ("0", "8", "32"):
     env = dict(os.environ, SDNQ_B200_ACTQ_GRID=grid)
     subprocess.run([sys.executable, "-c", CHILD], env=env, check=False)
