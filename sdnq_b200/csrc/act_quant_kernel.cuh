@@ -63,7 +63,7 @@ __device__ __forceinline__ uint32_t pack16(T a, T b) {
 // kTC: the rotation runs on the tensor cores (hadamard_tc.cuh; 16-bit activations).  The lane then owns elements
 // [4l, 4l+4) and [128+4l, 128+4l+4) of a chunk (two coalesced 8-byte accesses) instead of [8l, 8l+8).
 template <typename T, int WPR, int MAXC, int MODE, bool kTC, bool kConv>
-__global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kConv ? (kTC ? 4 : 5) : 3) : (kTC ? 2 : 3)) act_quant_kernel(const ActArgs a) {
+__global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kTC ? 4 : 5) : (kTC ? 2 : 3)) act_quant_kernel(const ActArgs a) {
     constexpr int RPC = kWarps / WPR;                 // rows per CTA and pass
     // the cross-warp exchange buffers alternate between passes of the row loop: one barrier per pass is enough
     __shared__ float s_a2[2][RPC][WPR];
@@ -79,10 +79,12 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 2 && MAXC <= 4) ? (kCo
     // Row loop: the grid is a few CTAs per SM and every CTA walks row blocks blockIdx.x, blockIdx.x + gridDim.x, ... -- the per-CTA
     // set-up (rotation constants, dependency wait, argument loads) is paid once, not once per pair of rows.
     const int64_t nblk = (a.M + RPC - 1) / RPC;
-    // Linear rows of 16-bit activations: the NEXT row block's chunks are loaded before this one is reduced, quantised and stored
+    // Long Linear rows of 16-bit activations: the NEXT row block's chunks are loaded before this one is reduced, quantised and stored
     // (register double buffer), so the SM keeps loads in flight through the statistics barrier and the store phase -- without it
     // every CTA alternates between a load burst and a phase with nothing outstanding, and the kernel sits at ~0.55 of the copy rate.
-    constexpr bool kPrefetch = !kConv && sizeof(T) == 2;
+    // Measured on B200 (tools/actq_grid.py): rows of 8k+ elements (one row per CTA, 6 chunks per warp) gain 15 % (3.05 -> 3.56 TB/s at
+    // 16384 x 12288 with Hadamard-256); the 4-chunk variants lose more to the extra registers (one resident CTA less) than they gain.
+    constexpr bool kPrefetch = !kConv && sizeof(T) == 2 && MAXC > 4;
     constexpr int kStep = WPR * 256;                                  // column distance between this warp's consecutive chunks
     const int kb = w_in * 256 + lane * (kTC ? 4 : 8);                 // this lane's first column
     auto load_linear = [&](int64_t blk_i, Held<T> (&h)[MAXC]) {
@@ -417,7 +419,8 @@ int launch_mode(const ActArgs& a, cudaStream_t st) {
     constexpr int RPC = kWarps / WPR;
     const int64_t nblk = (a.M + RPC - 1) / RPC;
     // a few waves of resident CTAs walk the row blocks (SDNQ_B200_ACTQ_GRID = CTAs per SM of grid; 0 = one CTA per row block)
-    static const int per_sm = [] { const char* e = getenv("SDNQ_B200_ACTQ_GRID"); return e != nullptr ? atoi(e) : 32; }();
+    static const int env_per_sm = [] { const char* e = getenv("SDNQ_B200_ACTQ_GRID"); return e != nullptr ? atoi(e) : -1; }();
+    const int per_sm = env_per_sm >= 0 ? env_per_sm : (!kConv && sizeof(T) == 2 && MAXC > 4 ? 8 : 32);      // long loops where the next row is prefetched
     const int64_t cap = per_sm > 0 ? int64_t(num_sms()) * per_sm : nblk;
     const unsigned blocks = static_cast<unsigned>(nblk < cap ? nblk : cap);
     cudaError_t e;
