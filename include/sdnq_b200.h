@@ -260,6 +260,19 @@ SDNQ_API size_t sdnq_b200_dequant_batch_table_bytes(int n_jobs);
 SDNQ_API int sdnq_b200_dequant_batch_plan(const sdnq_dequant_job* jobs, int n_jobs, void* host_table, int32_t* info);
 SDNQ_API int sdnq_b200_dequant_batch_run(const void* device_table, const int32_t* info, void* stream);
 
+/* ---- quantized embedding lookup (quantized_embedding / quantized_embedding_forward, layers/embedding/forward.py:14-104): the reference
+ *      unpacks the WHOLE table, indexes weight / scale / zero_point / svd_up with the token ids and dequantises the selected rows.
+ *      Here the dequant kernel reads stored row indices[n] for output row n directly (the table is never unpacked).
+ *   weight, fmt, scale, zero_point, codebook, group_size, svd_*, hadamard_group   the stored [V, D] table, as for sdnq_b200_dequant
+ *   indices      int64 [n_indices] on the device; an id outside [0, V) traps (torch raises a device-side assert)
+ *   embed_scale  result.mul_(embed_scale) on the rounded rows (1.0f: none)
+ *   out          [n_indices, D] row-major of out_dtype */
+SDNQ_API int sdnq_b200_embedding(const void* weight, const sdnq_weight_format* fmt, const float* scale, const float* zero_point, int codebook,
+                                 int64_t V, int64_t D, int64_t group_size, const void* svd_up, int64_t up_stride_n, int64_t up_stride_r,
+                                 const void* svd_down, int64_t down_stride_r, int64_t down_stride_k, int svd_rank, int svd_dtype,
+                                 int hadamard_group, const int64_t* indices, int64_t n_indices, float embed_scale, void* out, int out_dtype,
+                                 void* stream);
+
 /* ---- K8 load-time quantisation of a weight: scale, round, clamp and pack in one pass (the middle of sdnq_quantize_layer_weight,
  *      quantizer.py:236-253: quantize_weight, quant_utils.py:27-56, then pack_int, packed_int/__init__.py:76-80 + pack.py:201-321).
  *   w            [N,K] row-major f32 / bf16 / f16 (after the optional Hadamard rotation / SVD subtraction, which stay host-side);

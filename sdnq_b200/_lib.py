@@ -49,6 +49,7 @@ SIGNATURES = {
     "sdnq_b200_dequant_batch_plan": (_I, [_P, _I, _P, _P]),
     "sdnq_b200_dequant_batch_run": (_I, [_P, _P, _P]),
     "sdnq_b200_quantize_weight": (_I, [_P, _I, _L, _L, _L, _WF, _I, _P, _P, _P, _P]),
+    "sdnq_b200_embedding": (_I, [_P, _WF, _P, _P, _I, _L, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, ctypes.POINTER(ctypes.c_int64), _L, ctypes.c_float, _P, _I, _P]),
     "sdnq_b200_requant": (_I, [_P, _WF, _P, _P, _I, _L, _L, _L, _I, _P, _P, _P, _P, _P]),
     "sdnq_b200_act_quant": (_I, [_P, _I, _L, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P]),
     "sdnq_b200_conv_act_quant": (_I, [_P, _I, ctypes.POINTER(Conv2dGeometry), _I, _I, _P, _P, _P, _P, _P, _P]),

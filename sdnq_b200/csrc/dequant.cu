@@ -46,6 +46,10 @@ struct DequantArgs {
     // 32-bit copies for the hot kernel (N*K < 2^31 elements is enforced on the host)
     int K32, group32, group_shift;   // group_shift >= 0 when the group size is a power of two
     int gpr32, row_stride32;
+    // embedding lookup (quantized_embedding, layers/embedding/forward.py:14-68): output row n is stored row gather[n] of `src_rows`
+    const int64_t* gather;
+    int64_t src_rows;
+    float out_scale;        // embed_scale: result.mul_(embed_scale) in the result dtype (1 = none)
 };
 
 __device__ __forceinline__ float load_any(const void* p, int64_t i, int dtype) {
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, kPlain ? 5 : 3) dequant_kernel(const
     const int warp_global = blockIdx.x * kWarps + (threadIdx.x >> 5);
     const int warps_total = gridDim.x * kWarps;
     for (int t0 = warp_global; t0 < total_chunks; t0 += warps_total * U) {
-        int n[U], k[U];
+        int n[U], k[U], ns[U];
         bool live[U], valid[U];
         uint32_t raw[U][OctetWords<BITS>::N];
 #pragma unroll
@@ -128,7 +132,13 @@ __global__ void __launch_bounds__(kThreads, kPlain ? 5 : 3) dequant_kernel(const
             n[u] = live[u] ? static_cast<int>(static_cast<uint32_t>(t) / static_cast<uint32_t>(chunks_per_row)) : 0;
             k[u] = live[u] ? (t - n[u] * chunks_per_row) * 256 + lane * 8 : 0;
             valid[u] = live[u] && k[u] < a.K32;
-            if (valid[u]) load_octet_bytes<BITS>(a.weight, (int64_t(n[u]) * a.K32 + k[u]) >> 3, a.f.word_bytes, raw[u]);
+            ns[u] = n[u];
+            if (!kPlain && a.gather != nullptr && live[u]) {          // embedding lookup: the stored row this output row comes from
+                const int64_t g = a.gather[n[u]];
+                if (g < 0 || g >= a.src_rows) __trap();               // an index outside the table (torch raises a device-side assert here too)
+                ns[u] = static_cast<int>(g);
+            }
+            if (valid[u]) load_octet_bytes<BITS>(a.weight, (int64_t(ns[u]) * a.K32 + k[u]) >> 3, a.f.word_bytes, raw[u]);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -139,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, kPlain ? 5 : 3) dequant_kernel(const
                 float q[8];
                 decode_octet<BITS>(raw[u], codes);
                 codes_to_values<BITS>(codes, a.f, q);
-                scale_octet(a, n[u], k[u], q, codes, w);
+                scale_octet(a, ns[u], k[u], q, codes, w);
                 if constexpr (!kPlain) {
                     if (a.up != nullptr) {
                         // result.to(svd dtype).addmm_(svd_up, svd_down): f32 accumulate, one rounding (dequantizer.py:69-79)
@@ -147,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, kPlain ? 5 : 3) dequant_kernel(const
 #pragma unroll
                         for (int i = 0; i < 8; ++i) acc[i] = round_any(w[i], a.svd_dtype);
                         for (int j = 0; j < a.rank; ++j) {
-                            const float uj = load_any(a.up, int64_t(n[u]) * a.up_sn + j * a.up_sr, a.svd_dtype);
+                            const float uj = load_any(a.up, int64_t(ns[u]) * a.up_sn + j * a.up_sr, a.svd_dtype);
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
                                 acc[i] = fmaf(uj, load_any(a.down, j * a.down_sr + int64_t(k[u] + i) * a.down_sk, a.svd_dtype), acc[i]);
@@ -165,6 +175,10 @@ __global__ void __launch_bounds__(kThreads, kPlain ? 5 : 3) dequant_kernel(const
             if constexpr (!kPlain) {
                 if (a.hadamard) {   // un-rotate in the result dtype (dequantizer.py:82-83); whole warp participates
                     hadamard_warp_dyn(a.hadamard, w, hadamard_factor<OutT>(a.hadamard));
+                }
+                if (a.out_scale != 1.f) {                                 // embedding: result.mul_(embed_scale) on the rounded values
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) w[i] = ElemTraits<OutT>::round(__fmul_rn(ElemTraits<OutT>::round(w[i]), a.out_scale));
                 }
             }
             if (valid[u]) {
@@ -570,6 +584,7 @@ int fill_args(DequantArgs& a, const void* weight, const sdnq_weight_format* fmt,
     a.up = a.down = nullptr;
     a.up_sn = a.up_sr = a.down_sr = a.down_sk = 0;
     a.rank = 0; a.svd_dtype = SDNQ_BF16; a.hadamard = 0;
+    a.gather = nullptr; a.src_rows = N; a.out_scale = 1.f;
     return SDNQ_OK;
 }
 
@@ -594,7 +609,7 @@ static int launch_dequant(const DequantArgs& a, void* out, cudaStream_t st) {
     const char* dq_grid = getenv("SDNQ_B200_DQ_GRID");             // tuning knob (read per call): CTAs per SM of grid
     const int64_t cap = int64_t(num_sms()) * (dq_grid != nullptr && atoi(dq_grid) > 0 ? atoi(dq_grid) : 16);
     const unsigned grid = static_cast<unsigned>(want < cap ? (want > 0 ? want : 1) : cap);
-    const bool plain = a.up == nullptr && a.hadamard == 0;
+    const bool plain = a.up == nullptr && a.hadamard == 0 && a.gather == nullptr && a.out_scale == 1.f;
     cudaError_t e = cudaSuccess;
     const bool fast_int = plain && a.f.kind == SDNQ_W_INT && !a.codebook && ((a.group32 & 7) == 0 || a.group32 >= a.K32);
     // flat path: int4 / int8 in byte storage, groups inside rows, dense scale rows
@@ -607,7 +622,7 @@ static int launch_dequant(const DequantArgs& a, void* out, cudaStream_t st) {
     // rotated 8-bit weights without SVD: tensor-core un-rotate
     bool rot8 = false;
     if constexpr (sizeof(OutT) == 2) {
-        rot8 = a.hadamard != 0 && a.up == nullptr && !a.codebook && a.f.bits == 8 && a.f.word_bytes == 1 && a.K32 % 8 == 0 &&
+        rot8 = a.gather == nullptr && a.out_scale == 1.f && a.hadamard != 0 && a.up == nullptr && !a.codebook && a.f.bits == 8 && a.f.word_bytes == 1 && a.K32 % 8 == 0 &&
                ((a.group32 & 3) == 0 || a.group32 >= a.K32) && (reinterpret_cast<uintptr_t>(a.weight) & 3) == 0 &&
                (reinterpret_cast<uintptr_t>(out) & 7) == 0 && getenv("SDNQ_B200_HADAMARD_BUTTERFLY") == nullptr;
     }
@@ -764,6 +779,42 @@ extern "C" int sdnq_b200_dequant_batch_run(const void* device_table, const int32
     SDNQ_REQUIRE(device_table && info && (reinterpret_cast<uintptr_t>(device_table) & 127) == 0, SDNQ_EINVAL, "device_table must be a 128-byte aligned device pointer");
     SDNQ_REQUIRE((info[0] == 64 || info[0] == 128 || info[0] == 256) && info[1] > 0 && info[2] > 0 && info[3] > 0, SDNQ_EINVAL, "bad plan info");
     return svd_batch_run(device_table, info[3], info[1], info[0], info[2], reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- quantized embedding lookup: gather + dequantise the selected rows (layers/embedding/forward.py:14-68)
+extern "C" int sdnq_b200_embedding(const void* weight, const sdnq_weight_format* fmt, const float* scale, const float* zero_point, int codebook,
+                                   int64_t V, int64_t D, int64_t group_size, const void* svd_up, int64_t up_stride_n, int64_t up_stride_r,
+                                   const void* svd_down, int64_t down_stride_r, int64_t down_stride_k, int svd_rank, int svd_dtype,
+                                   int hadamard_group, const int64_t* indices, int64_t n_indices, float embed_scale, void* out, int out_dtype,
+                                   void* stream) {
+    DequantArgs a;
+    int rc = fill_args(a, weight, fmt, scale, zero_point, codebook, V, D, group_size);
+    if (rc != SDNQ_OK) return rc;
+    SDNQ_REQUIRE(indices != nullptr && n_indices >= 0, SDNQ_EINVAL, "indices pointer is NULL");
+    SDNQ_REQUIRE(out != nullptr && (reinterpret_cast<uintptr_t>(out) & 15) == 0, SDNQ_EINVAL, "out must be a 16-byte aligned pointer");
+    SDNQ_REQUIRE(hadamard_ok(hadamard_group), SDNQ_EUNSUPPORTED, "hadamard group %d: only powers of two in [4,256] are implemented", hadamard_group);
+    if (hadamard_group) SDNQ_REQUIRE(D % hadamard_group == 0, SDNQ_EINVAL, "hadamard group %d does not divide the embedding width", hadamard_group);
+    SDNQ_REQUIRE(n_indices * D < (int64_t(1) << 31), SDNQ_EUNSUPPORTED, "too many looked-up elements (%lld x %lld)", (long long)n_indices, (long long)D);
+    if (n_indices == 0) return SDNQ_OK;
+    if (svd_up != nullptr) {
+        SDNQ_REQUIRE(svd_down != nullptr && svd_rank > 0 && svd_rank <= 1024, SDNQ_EINVAL, "bad svd arguments (rank %d)", svd_rank);
+        SDNQ_REQUIRE(svd_dtype == SDNQ_BF16 || svd_dtype == SDNQ_F16 || svd_dtype == SDNQ_F32, SDNQ_EINVAL, "bad svd dtype");
+        a.up = svd_up; a.up_sn = up_stride_n; a.up_sr = up_stride_r;
+        a.down = svd_down; a.down_sr = down_stride_r; a.down_sk = down_stride_k;
+        a.rank = svd_rank; a.svd_dtype = svd_dtype;
+    }
+    a.hadamard = hadamard_group;
+    a.gather = indices;
+    a.src_rows = V;
+    a.N = n_indices;                       // rows of the output
+    a.out_scale = embed_scale;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (out_dtype) {
+        case SDNQ_BF16: return launch_dequant<__nv_bfloat16>(a, out, st);
+        case SDNQ_F16: return launch_dequant<__half>(a, out, st);
+        case SDNQ_F32: return launch_dequant<float>(a, out, st);
+        default: return set_error(SDNQ_EINVAL, "bad out_dtype %d", out_dtype);
+    }
 }
 
 extern "C" int sdnq_b200_requant(const void* weight, const sdnq_weight_format* fmt, const float* scale, const float* zero_point,

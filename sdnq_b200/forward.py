@@ -473,7 +473,25 @@ def _unsupported(name: str, what: str) -> Callable:
 
 quantized_linear_forward_fp16_matmul = _unsupported("quantized_linear_forward_fp16_matmul", "the float16 quantized matmul (quantized_matmul_dtype='float16')")
 quantized_conv_forward_fp16_matmul = _unsupported("quantized_conv_forward_fp16_matmul", "the float16 quantized conv matmul (quantized_matmul_dtype='float16')")
-quantized_embedding_forward = _unsupported("quantized_embedding_forward", "quantized embedding (quant_embedding=True)")
+
+
+@torch.no_grad()
+def quantized_embedding_forward(self, input: torch.Tensor) -> torch.Tensor:
+    """Quantized embedding (quant_embedding=True; reference layers/embedding/forward.py:14-104): the reference unpacks the whole table,
+    indexes weight / scale / zero point / svd_up with the token ids and dequantises those rows; K3 reads the stored rows of the
+    ids directly (the table is never unpacked) and applies scalar_embed_scale on the way out."""
+    d = self.sdnq_dequantizer
+    shape = tuple(d.result_shape) if d.result_shape is not None else tuple(d.original_shape)
+    if len(shape) != 2:
+        raise NotImplementedError(f"sdnq_b200: embedding tables are 2-D (got shape {shape})")
+    V, D = shape
+    embed_scale = getattr(self, "scalar_embed_scale", None)
+    if torch.is_tensor(embed_scale):
+        embed_scale = float(embed_scale)
+    un_rotate = d.hadamard_group_size if d.use_hadamard else 0
+    return ops.embedding(self.weight, d.weights_dtype, self.scale, self.zero_point, V, D, d.group_size, input, d.result_dtype,
+                         svd_up=self.svd_up, svd_down=self.svd_down, hadamard_group=un_rotate, use_codebook=d.use_codebook,
+                         embed_scale=1.0 if embed_scale is None else embed_scale)
 
 
 # ------------------------------------------------------------------------------------------------ convolutions

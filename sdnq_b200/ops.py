@@ -146,6 +146,34 @@ def dequant(weight, weights_dtype, scale, zero_point, N, K, group_size, out_dtyp
     return out
 
 
+def embedding(weight, weights_dtype, scale, zero_point, V, D, group_size, indices: torch.Tensor, out_dtype, svd_up=None, svd_down=None,
+              hadamard_group=0, use_codebook=False, embed_scale: float = 1.0) -> torch.Tensor:
+    """Quantized embedding lookup: rows `indices` (any shape, integer) of the stored [V, D] table, dequantised -> [*indices.shape, D].
+    Arguments as for `dequant` (svd factors in the plain layout: svd_up [V,r], svd_down [r,D])."""
+    import ctypes
+    _require_cuda(weight, scale, indices)
+    e = dtype_dict[weights_dtype]
+    w = weight.contiguous() if e["is_packed"] else physical_nk(weight)
+    scale = scale.to(torch.float32).contiguous() if scale.dtype != torch.float32 or not scale.is_contiguous() else scale
+    if zero_point is not None and (zero_point.dtype != torch.float32 or not zero_point.is_contiguous()):
+        zero_point = zero_point.to(torch.float32).contiguous()
+    idx = indices.reshape(-1).to(torch.int64).contiguous()
+    out = torch.empty((idx.numel(), D), dtype=out_dtype, device=w.device)
+    up_args, down_args, rank, svd_code = (None, 0, 0), (None, 0, 0), 0, SDNQ_BF16
+    if svd_up is not None:
+        rank = svd_up.shape[1]
+        up_args = (_ptr(svd_up), svd_up.stride(0), svd_up.stride(1))
+        down_args = (_ptr(svd_down), svd_down.stride(0), svd_down.stride(1))
+        svd_code = dtype_code(svd_up.dtype)
+    gs = _group_args(scale, V, D, group_size, use_codebook, e["num_bits"])
+    with torch.cuda.device(w.device):
+        check(_lib.load().sdnq_b200_embedding(_ptr(w), weight_format(weights_dtype, w), _ptr(scale), _ptr(zero_point), int(use_codebook), V, D, gs,
+                                              *up_args, *down_args, rank, svd_code, int(hadamard_group),
+                                              ctypes.cast(idx.data_ptr(), ctypes.POINTER(ctypes.c_int64)), idx.numel(), float(embed_scale),
+                                              _ptr(out), dtype_code(out_dtype), _stream(w)))
+    return out.view(*indices.shape, D)
+
+
 class DequantBatch:
     """A planned batched dequantisation: the device-side table of sdnq_b200_dequant_batch_plan, the [N,K] outputs it writes (views of
     `slab`) and everything the embedded pointers refer to."""

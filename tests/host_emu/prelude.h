@@ -1,3 +1,4 @@
+#include <cstdlib>
 // Host stand-ins for the CUDA device intrinsics used by the per-lane arithmetic in sdnq_b200/csrc/{common,unpack}.cuh, so that
 // g++ can compile those headers unchanged and tests/test_device_arithmetic_on_host.py can check the decode / convert
 // functions bit-for-bit against the oracle without a GPU.  Test infrastructure only; warp-collective code (shuffles) is
@@ -28,6 +29,7 @@
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 // PRMT in its default mode: result byte i = byte (selector nibble i & 7) of the 8-byte pool {y:x}; nibble bit 3 replicates the sign
+[[noreturn]] static inline void __trap() { std::abort(); }      // a device trap kills the context; on the host: abort
 static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
     const uint64_t pool = (uint64_t(y) << 32) | x;
     uint32_t r = 0;

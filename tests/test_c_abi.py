@@ -122,7 +122,7 @@ def header_prototypes():
 
 def _ctype_of(c_type):
     from sdnq_b200._lib import Conv2dGeometry, WeightFormat
-    table = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t, "constchar*": ctypes.c_char_p,
+    table = {"int": ctypes.c_int, "float": ctypes.c_float, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t, "constchar*": ctypes.c_char_p,
              "constsdnq_weight_format*": ctypes.POINTER(WeightFormat), "constsdnq_conv2d_geometry*": ctypes.POINTER(Conv2dGeometry),
              "constint64_t*": ctypes.POINTER(ctypes.c_int64), "void*const*": ctypes.POINTER(ctypes.c_void_p)}
     if c_type in table:

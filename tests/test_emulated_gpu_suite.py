@@ -296,3 +296,11 @@ def test_quantize_weight(kw):
 @emulated(K.test_quantize_weight_reproduces_reference_fixture)
 def test_quantize_weight_fixture(kw):
     K.test_quantize_weight_reproduces_reference_fixture(**kw)
+
+
+# ---- quantized embedding lookup (K3 with a row gather)
+@emulated(L.test_quantized_embedding_forward)
+def test_quantized_embedding(kw):
+    if kw["cfg"].get("use_svd"):
+        pytest.skip("the full-table reference of SVD layers goes through the tcgen05 SVD kernel on the GPU; on the emulator it takes minutes")
+    L.test_quantized_embedding_forward(**kw)

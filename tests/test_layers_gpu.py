@@ -271,3 +271,30 @@ def test_quantising_on_the_gpu_stores_what_the_cpu_path_stores(cfg, monkeypatch)
                 assert float((diff != 0).float().mean()) < 5e-3, name
     x = torch.randn(64, 640, device=DEV, dtype=torch.bfloat16)
     assert torch.isfinite(got(x)).all()
+
+
+@pytest.mark.parametrize("cfg", [dict(weights_dtype="int8"), dict(weights_dtype="uint4", group_size=32), dict(weights_dtype="int5", group_size=64),
+                                 dict(weights_dtype="int4", group_size=64, use_svd=True, svd_rank=16), dict(weights_dtype="int8", use_hadamard=True, hadamard_group_size=64),
+                                 dict(weights_dtype="float6_e3m2fn"), dict(weights_dtype="uint4", use_codebook=True, group_size=32)],
+                         ids=lambda c: "_".join(str(v) for v in c.values()))
+def test_quantized_embedding_forward(cfg):
+    """quant_embedding=True (reference layers/embedding/forward.py:14-104: index the unpacked table, dequantise the selected rows):
+    the gather + dequant kernel gives exactly the rows of the fully dequantised table (the K3 arithmetic the reference fixtures pin),
+    times scalar_embed_scale."""
+    from sdnq_b200 import SDNQConfig, sdnq_quantize_layer
+    torch.manual_seed(4)
+    emb = torch.nn.Embedding(1000, 256).to(torch.bfloat16)
+    layer, _ = sdnq_quantize_layer(copy.deepcopy(emb), SDNQConfig(quant_embedding=True, **cfg))
+    assert type(layer).__name__ == "SDNQEmbedding" and layer.forward_func.__name__ == "quantized_embedding_forward"
+    layer = layer.to(DEV)
+    ids = torch.randint(0, 1000, (3, 77), device=DEV)
+    ids[0, 0], ids[0, 1] = 0, 999
+    d = layer.sdnq_dequantizer
+    table = d(layer.weight, layer.scale, zero_point=layer.zero_point, svd_up=layer.svd_up, svd_down=layer.svd_down)
+    got = layer(ids)
+    assert got.shape == (3, 77, 256) and got.dtype == torch.bfloat16 and got.is_contiguous()
+    assert torch.equal(got, table[ids])
+    err = (got.float() - emb.weight.to(DEV).float()[ids]).abs().max()
+    assert float(err) < 0.25 * float(emb.weight.float().abs().max())                      # it is the embedding it was quantised from
+    layer.scalar_embed_scale = 16.0                                                         # Gemma-style scaled embeddings
+    assert torch.equal(layer(ids), table[ids].mul_(16.0))
