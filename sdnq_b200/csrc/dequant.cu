@@ -17,8 +17,8 @@ namespace sdnq {
 size_t svd_batch_entry_bytes();
 int svd_batch_fill(void* host_entry, int tn, int tile_start, const void* weight, const WFormat& f, const float* scale, const float* zp, int64_t N,
                    int64_t K, int group32, int group_shift, int gpr32, int row_stride32, const void* up, int64_t up_sn, int64_t up_sr,
-                   const void* down, int64_t down_sr, int64_t down_sk, int rank, int svd_dtype, void* out, int out_dtype, int* tiles);
-int svd_batch_run(const void* device_table, int n_entries, int total_tiles, int tn, int stage_rank, cudaStream_t st);
+                   const void* down, int64_t down_sr, int64_t down_sk, int rank, int svd_dtype, void* out, int out_dtype, int* tiles, int* traits);
+int svd_batch_run(const void* device_table, int n_entries, int total_tiles, int tn, int stage_rank, int traits, cudaStream_t st);
 int dequant_svd_tc(const void* weight, const WFormat& f, const float* scale, const float* zp, int64_t N, int64_t K, int group32, int group_shift,
                    int gpr32, int row_stride32, const void* up, int64_t up_sn, int64_t up_sr, const void* down, int64_t down_sr, int64_t down_sk,
                    int rank, int svd_dtype, void* out, int out_dtype, cudaStream_t st);
@@ -753,7 +753,7 @@ extern "C" int sdnq_b200_dequant_batch_plan(const sdnq_dequant_job* jobs, int n_
         const int v = atoi(e);
         if (v == 64 || v == 128 || v == 256) tn = v;
     }
-    int total = 0, max_rank = 0;
+    int total = 0, max_rank = 0, traits = 0;
     uint8_t* entry = reinterpret_cast<uint8_t*>(host_table);
     for (int j = 0; j < n_jobs; ++j, entry += svd_batch_entry_bytes()) {
         const sdnq_dequant_job& q = jobs[j];
@@ -764,21 +764,22 @@ extern "C" int sdnq_b200_dequant_batch_plan(const sdnq_dequant_job* jobs, int n_
         SDNQ_REQUIRE(q.svd_up != nullptr && q.svd_down != nullptr, SDNQ_EUNSUPPORTED, "job %d: batched dequantisation covers weights with SVD factors", j);
         int tiles = 0;
         rc = svd_batch_fill(entry, tn, total, q.weight, a.f, q.scale, q.zero_point, q.N, q.K, a.group32, a.group_shift, a.gpr32, a.row_stride32, q.svd_up,
-                            q.up_stride_n, q.up_stride_r, q.svd_down, q.down_stride_r, q.down_stride_k, q.svd_rank, q.svd_dtype, q.out, q.out_dtype, &tiles);
+                            q.up_stride_n, q.up_stride_r, q.svd_down, q.down_stride_r, q.down_stride_k, q.svd_rank, q.svd_dtype, q.out, q.out_dtype, &tiles, &traits);
         if (rc == 1) return set_error(SDNQ_EUNSUPPORTED, "job %d: outside what the batched tensor-core dequant kernel covers (int4 / uint4 codes, bf16 SVD "
                                       "factors of rank 16 / 32 / 64 stored K-major, bf16 output, K %% 32 == 0)", j);
         if (rc != SDNQ_OK) return rc;
         total += tiles;
         max_rank = q.svd_rank > max_rank ? q.svd_rank : max_rank;
     }
-    info[0] = tn; info[1] = total; info[2] = max_rank; info[3] = n_jobs;
+    info[0] = tn | (traits << 16); info[1] = total; info[2] = max_rank; info[3] = n_jobs;
     return SDNQ_OK;
 }
 
 extern "C" int sdnq_b200_dequant_batch_run(const void* device_table, const int32_t* info, void* stream) {
     SDNQ_REQUIRE(device_table && info && (reinterpret_cast<uintptr_t>(device_table) & 127) == 0, SDNQ_EINVAL, "device_table must be a 128-byte aligned device pointer");
-    SDNQ_REQUIRE((info[0] == 64 || info[0] == 128 || info[0] == 256) && info[1] > 0 && info[2] > 0 && info[3] > 0, SDNQ_EINVAL, "bad plan info");
-    return svd_batch_run(device_table, info[3], info[1], info[0], info[2], reinterpret_cast<cudaStream_t>(stream));
+    const int tn = info[0] & 0xFFFF, traits = info[0] >> 16;
+    SDNQ_REQUIRE((tn == 64 || tn == 128 || tn == 256) && info[1] > 0 && info[2] > 0 && info[3] > 0, SDNQ_EINVAL, "bad plan info");
+    return svd_batch_run(device_table, info[3], info[1], tn, info[2], traits, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ---- quantized embedding lookup: gather + dequantise the selected rows (layers/embedding/forward.py:14-68)

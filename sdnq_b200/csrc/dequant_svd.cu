@@ -76,7 +76,10 @@ struct alignas(128) BatchEntry {
     int num_n;           // tiles along K
 };
 
-template <int BITS, bool kBf16Out, int TN>
+// ZP / BLK: what the launch's weights have in common, decided on the host so that the element loop carries no per-weight branches --
+// ZP = 0 no weight has zero points, 1 every weight has, 2 mixed (decided per tile);  BLK = 1 every weight's scale groups cover whole
+// 64-column blocks (row-wise scales or groups that are multiples of 64: the scales are staged per block), 0 decided per tile.
+template <int BITS, bool kBf16Out, int TN, int ZP, int BLK>
 __global__ void __launch_bounds__(kThreads, SvdCfg<TN>::kCtasPerSm)
 dequant_svd_kernel(const __grid_constant__ BatchEntry single, const BatchEntry* __restrict__ table, const int n_entries, const int total_tiles,
                    const int stage_rank) {
@@ -185,7 +188,7 @@ dequant_svd_kernel(const __grid_constant__ BatchEntry single, const BatchEntry* 
         auto prefetch = [&](int tile, int buf, int& li) {
             const BatchEntry* e = locate(tile, li);
             const SvdArgs& a = e->a;
-            const bool blk_scales = blk_scales_of(a);
+            const bool blk_scales = BLK == 1 || blk_scales_of(a);
             const int local = tile - e->tile_start, num_n = e->num_n;
             const int m0 = (local / num_n) * TM, n0 = (local % num_n) * TN;
             const int n = m0 + q * 32 + lane;
@@ -208,7 +211,7 @@ dequant_svd_kernel(const __grid_constant__ BatchEntry single, const BatchEntry* 
                         const int g = a.gpr32 <= 1 ? 0 : (a.group_shift >= 0 ? (k >> a.group_shift) : static_cast<int>(static_cast<uint32_t>(k) / static_cast<uint32_t>(a.group32)));
                         const uint32_t si = static_cast<uint32_t>(n) * static_cast<uint32_t>(a.row_stride32) + g;
                         sc = a.scale[si];
-                        if (a.zp) z = a.zp[si];
+                        if (ZP == 1 || (ZP == 2 && a.zp)) z = a.zp[si];
                     }
                     sc_base[(buf * 2 + 0) * (SC::kBlocks * 32) + cb * 32 + lane] = sc;
                     sc_base[(buf * 2 + 1) * (SC::kBlocks * 32) + cb * 32 + lane] = z;
@@ -225,7 +228,8 @@ dequant_svd_kernel(const __grid_constant__ BatchEntry single, const BatchEntry* 
             const SvdArgs a = e->a;                                        // this tile's weight (registers)
             const CUtensorMap* tmap_out = &e->out;
             const float bias = 8388608.0f - static_cast<float>(a.f.int_offset);
-            const bool blk_scales = blk_scales_of(a);
+            const bool blk_scales = BLK == 1 || blk_scales_of(a);
+            const bool has_zp = ZP == 1 || (ZP == 2 && a.zp != nullptr);
             const int local = tile - e->tile_start, num_n = e->num_n;
             const int m0 = (local / num_n) * TM, n0 = (local % num_n) * TN;
             const int mrow0 = m0 + q * 32;
@@ -270,7 +274,7 @@ dequant_svd_kernel(const __grid_constant__ BatchEntry single, const BatchEntry* 
                             const int g = a.group_shift >= 0 ? (k >> a.group_shift) : static_cast<int>(static_cast<uint32_t>(k) / static_cast<uint32_t>(a.group32));
                             const uint32_t si = static_cast<uint32_t>(n) * static_cast<uint32_t>(a.row_stride32) + g;
                             sc = a.scale[si];
-                            if (a.zp) z = a.zp[si];
+                            if (has_zp) z = a.zp[si];
                         }
                         const uint32_t lo = words[o] & 0x0F0F0F0Fu, hi = (words[o] >> 4) & 0x0F0F0F0Fu;
                         uint32_t w4[4];
@@ -278,8 +282,8 @@ dequant_svd_kernel(const __grid_constant__ BatchEntry single, const BatchEntry* 
                         for (int j = 0; j < 4; ++j) {                              // byte j of the word = elements 2j (low nibble), 2j + 1
                             const float q0 = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7440 | j)) - bias;
                             const float q1 = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7440 | j)) - bias;
-                            const float v0 = a.zp ? fmaf(q0, sc, z) : __fmul_rn(q0, sc);
-                            const float v1 = a.zp ? fmaf(q1, sc, z) : __fmul_rn(q1, sc);
+                            const float v0 = has_zp ? fmaf(q0, sc, z) : __fmul_rn(q0, sc);
+                            const float v1 = has_zp ? fmaf(q1, sc, z) : __fmul_rn(q1, sc);
                             // result.to(svd dtype): one packed conversion rounds both to bf16, two bit operations bring them back to f32
                             __nv_bfloat162 wb = __floats2bfloat162_rn(v0, v1);
                             const uint32_t wbits = *reinterpret_cast<uint32_t*>(&wb);
@@ -363,22 +367,33 @@ int fill_entry(BatchEntry* e, const SvdArgs& a, const void* up, int64_t up_pitch
     return SDNQ_OK;
 }
 
-template <int TN>
-int launch_entries(const BatchEntry* single, const BatchEntry* device_table, int n_entries, int total_tiles, int stage_rank, cudaStream_t st) {
+template <int TN, int ZP, int BLK>
+int launch_variant(const BatchEntry* single, const BatchEntry* device_table, int n_entries, int total_tiles, int stage_rank, cudaStream_t st) {
     constexpr int kSmemMax = SvdCfg<TN>::smem_bytes(kMaxRank);
     const int kSmemBytes = SvdCfg<TN>::smem_bytes(stage_rank);
+    auto kernel = dequant_svd_kernel<4, true, TN, ZP, BLK>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(dequant_svd_kernel<4, true, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax); });
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax); });
     SDNQ_REQUIRE(attr_err == cudaSuccess, SDNQ_ECUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
     const int slots = num_sms() * SvdCfg<TN>::ctas_per_sm(stage_rank);
     const int grid = total_tiles < slots ? total_tiles : slots;
     static const BatchEntry kNone{};
-    cudaError_t e = launch_pdl(dequant_svd_kernel<4, true, TN>, dim3(grid), dim3(kThreads), kSmemBytes, st, single != nullptr ? *single : kNone,
-                               device_table, n_entries, total_tiles, stage_rank);
+    cudaError_t e = launch_pdl(kernel, dim3(grid), dim3(kThreads), kSmemBytes, st, single != nullptr ? *single : kNone, device_table, n_entries,
+                               total_tiles, stage_rank);
     if (e != cudaSuccess) return set_error(SDNQ_ECUDA, "launch of dequant_svd_kernel failed: %s", cudaGetErrorString(e));
     return check_launch("dequant_svd_kernel");
 }
+
+// traits: bit 0 = some weight has zero points, bit 1 = some weight has none, bit 2 = some weight's scale groups end inside a 64-column block
+template <int TN>
+int launch_entries(const BatchEntry* single, const BatchEntry* device_table, int n_entries, int total_tiles, int stage_rank, int traits, cudaStream_t st) {
+    if ((traits & 4) == 0 && (traits & 3) == 2) return launch_variant<TN, 0, 1>(single, device_table, n_entries, total_tiles, stage_rank, st);
+    if ((traits & 4) == 0 && (traits & 3) == 1) return launch_variant<TN, 1, 1>(single, device_table, n_entries, total_tiles, stage_rank, st);
+    return launch_variant<TN, 2, 0>(single, device_table, n_entries, total_tiles, stage_rank, st);
+}
+
+int entry_traits(const SvdArgs& a) { return (a.zp != nullptr ? 1 : 2) | ((a.gpr32 <= 1 || (a.group32 & 63) == 0) ? 0 : 4); }
 
 bool svd_tc_covers(const void* weight, const WFormat& f, int64_t N, int64_t K, int group32, const void* up, int64_t up_sn, int64_t up_sr,
                    const void* down, int64_t down_sr, int64_t down_sk, int rank, int svd_dtype, int out_dtype) {
@@ -415,9 +430,9 @@ int dequant_svd_tc(const void* weight, const WFormat& f, const float* scale, con
     else rc = fill_entry<64>(&e, a, up, up_sn, down, down_sk, out, 0);
     if (rc != SDNQ_OK) return rc;
     const int tiles = num_m * e.num_n;
-    if (tn == 256) return launch_entries<256>(&e, nullptr, 1, tiles, rank, st);
-    if (tn == 128) return launch_entries<128>(&e, nullptr, 1, tiles, rank, st);
-    return launch_entries<64>(&e, nullptr, 1, tiles, rank, st);
+    if (tn == 256) return launch_entries<256>(&e, nullptr, 1, tiles, rank, entry_traits(a), st);
+    if (tn == 128) return launch_entries<128>(&e, nullptr, 1, tiles, rank, entry_traits(a), st);
+    return launch_entries<64>(&e, nullptr, 1, tiles, rank, entry_traits(a), st);
 }
 
 // ---- batched launches: the weights of several layers dequantised by one persistent grid ------------------------------------------
@@ -426,7 +441,7 @@ size_t svd_batch_entry_bytes() { return sizeof(BatchEntry); }
 // Appends the entry of one weight to a host-side table.  Returns 1 when the weight is outside what this kernel covers.
 int svd_batch_fill(void* host_entry, int tn, int tile_start, const void* weight, const WFormat& f, const float* scale, const float* zp, int64_t N,
                    int64_t K, int group32, int group_shift, int gpr32, int row_stride32, const void* up, int64_t up_sn, int64_t up_sr,
-                   const void* down, int64_t down_sr, int64_t down_sk, int rank, int svd_dtype, void* out, int out_dtype, int* tiles) {
+                   const void* down, int64_t down_sr, int64_t down_sk, int rank, int svd_dtype, void* out, int out_dtype, int* tiles, int* traits) {
     if (!svd_tc_covers(weight, f, N, K, group32, up, up_sn, up_sr, down, down_sr, down_sk, rank, svd_dtype, out_dtype)) return 1;
     SvdArgs a{reinterpret_cast<const uint8_t*>(weight), scale, zp, static_cast<int>(N), static_cast<int>(K), group32, group_shift, gpr32, row_stride32, f, rank, out_dtype};
     BatchEntry* e = new (host_entry) BatchEntry{};
@@ -436,14 +451,15 @@ int svd_batch_fill(void* host_entry, int tn, int tile_start, const void* weight,
     else rc = fill_entry<64>(e, a, up, up_sn, down, down_sk, out, tile_start);
     if (rc != SDNQ_OK) return rc;
     *tiles = static_cast<int>((N + TM - 1) / TM) * e->num_n;
+    *traits |= entry_traits(a);
     return SDNQ_OK;
 }
 
-int svd_batch_run(const void* device_table, int n_entries, int total_tiles, int tn, int stage_rank, cudaStream_t st) {
+int svd_batch_run(const void* device_table, int n_entries, int total_tiles, int tn, int stage_rank, int traits, cudaStream_t st) {
     const BatchEntry* t = reinterpret_cast<const BatchEntry*>(device_table);
-    if (tn == 256) return launch_entries<256>(nullptr, t, n_entries, total_tiles, stage_rank, st);
-    if (tn == 128) return launch_entries<128>(nullptr, t, n_entries, total_tiles, stage_rank, st);
-    return launch_entries<64>(nullptr, t, n_entries, total_tiles, stage_rank, st);
+    if (tn == 256) return launch_entries<256>(nullptr, t, n_entries, total_tiles, stage_rank, traits, st);
+    if (tn == 128) return launch_entries<128>(nullptr, t, n_entries, total_tiles, stage_rank, traits, st);
+    return launch_entries<64>(nullptr, t, n_entries, total_tiles, stage_rank, traits, st);
 }
 
 }  // namespace sdnq

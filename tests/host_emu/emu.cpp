@@ -29,8 +29,8 @@ int dequant_svd_tc(const void*, const WFormat&, const float*, const float*, int6
 // batched K3s: same translation unit as dequant_svd_tc -- the plan reports "not covered"
 size_t svd_batch_entry_bytes() { return 512; }
 int svd_batch_fill(void*, int, int, const void*, const WFormat&, const float*, const float*, int64_t, int64_t, int, int, int, int, const void*, int64_t, int64_t,
-                   const void*, int64_t, int64_t, int, int, void*, int, int*) { return 1; }
-int svd_batch_run(const void*, int, int, int, int, cudaStream_t) { return set_error(SDNQ_EUNSUPPORTED, "the batched tensor-core dequant kernel is not emulated"); }
+                   const void*, int64_t, int64_t, int, int, void*, int, int*, int*) { return 1; }
+int svd_batch_run(const void*, int, int, int, int, int, cudaStream_t) { return set_error(SDNQ_EUNSUPPORTED, "the batched tensor-core dequant kernel is not emulated"); }
 }  // namespace sdnq
 
 extern "C" {
