@@ -229,7 +229,9 @@ def dequant_batch_plan(jobs, slab: torch.Tensor, out_dtype=torch.bfloat16) -> De
             q.svd_up, q.up_stride_n, q.up_stride_r = up.data_ptr(), up.stride(0), up.stride(1)
             q.svd_down, q.down_stride_r, q.down_stride_k = down.data_ptr(), down.stride(0), down.stride(1)
         q.svd_dtype, q.out, q.out_dtype = dtype_code(up.dtype), out.data_ptr(), dtype_code(out_dtype)
-        keep += [w, scale, zp, up, down]
+        # strong references only to what was created here (converted copies): the layer's own tensors are guarded by the caller's
+        # identity check (forward._StoredState) before every run, and a plan must not keep a deleted model's weights alive
+        keep += [t for t, src in ((w, j["weight"]), (scale, j["scale"]), (zp, j.get("zero_point"))) if t is not None and t is not src]
         outs.append(out)
     nbytes = int(lib.sdnq_b200_dequant_batch_table_bytes(n))
     host = torch.empty(nbytes + 128, dtype=torch.uint8)

@@ -46,7 +46,7 @@ def eligible(layer, dtype) -> bool:
 
 
 class _Batch:
-    __slots__ = ("plan", "entry", "states", "layers", "slab", "event", "tag", "left", "waited", "hits")
+    __slots__ = ("plan", "entry", "states", "layers", "slab", "event", "tag", "left", "waited", "hits", "streams")
 
 
 class _Planned:
@@ -90,7 +90,8 @@ class Prefetcher:
             lid = id(cur)
             if lid in seen or (chain and lid == self.first) or lid in self.ready:
                 break
-            if not eligible(cur, torch.bfloat16) or bool(cur.sdnq_dequantizer.use_quantized_matmul) != skip or not _stored_tensors(cur)[0].is_cuda:
+            if (not eligible(cur, torch.bfloat16) or bool(cur.sdnq_dequantizer.use_quantized_matmul) != skip
+                    or any(t is not None and t.device != self.device for t in _stored_tensors(cur))):
                 break
             N, K = cur.sdnq_dequantizer._linear_nk()
             size = (N * K * 2 + 255) // 256 * 256
@@ -156,15 +157,19 @@ class Prefetcher:
             return None
         b = _Batch()
         b.plan, b.entry, b.states, b.layers, b.slab, b.tag = entry.plans[k], entry, entry.states, [weakref.ref(layer) for layer in chain], k, tag
-        b.left, b.waited, b.hits = len(chain), False, 0
-        # the slab's previous readers (GEMMs already handed to the caller's stream) finish before it is rewritten; the weights were
-        # written by whatever the caller's stream did before as well
+        b.left, b.waited, b.hits, b.streams = len(chain), False, 0, {}
+        # the slab's previous readers (GEMMs already handed to the caller's stream -- and to any other stream its weights were handed
+        # out on) finish before it is rewritten; the weights were written by whatever the caller's stream did before as well
         side.wait_stream(main)
+        old = self.slab_busy[k]
+        if old is not None:
+            for st in old.streams.values():
+                if st.cuda_stream != main.cuda_stream:
+                    side.wait_stream(st)
         with torch.cuda.stream(side):
             ops.dequant_batch_run(b.plan)
             b.event = torch.cuda.Event()
             b.event.record(side)
-        old = self.slab_busy[k]
         if old is not None:                                   # entries of an abandoned batch must not be served from a rewritten slab
             self._drop(old)
         self.slab_busy[k] = b
@@ -205,8 +210,9 @@ class Prefetcher:
             b.hits += 1
             i = 0
         first_of_batch = not b.waited
-        if first_of_batch:
-            main.wait_event(b.event)                         # once per batch: everything in it is visible to the caller's stream from here on
+        if main.cuda_stream not in b.streams:
+            main.wait_event(b.event)                         # once per batch and stream: everything in it is visible to that stream from here on
+            b.streams[main.cuda_stream] = main
             b.waited = True
             self.current = b
         W = b.plan.outs[i]
