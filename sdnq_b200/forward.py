@@ -336,6 +336,12 @@ def quantized_linear_forward(self, input: torch.Tensor) -> torch.Tensor:
             return _small_m_packed_linear(self, input)
     elif _w4a16_ok(self, input):
         return _w4a16_linear(self, input)
+    else:
+        group = self.__dict__.get("_sdnq_siblings")
+        if type(group) is siblings.DequantSiblingGroup and siblings.siblings_enabled():      # to_q / to_k / to_v ...: one batched GEMM over their dequantised weights
+            out = group.forward(self, input)
+            if out is not None:
+                return out.view(*input.shape[:-1], out.shape[-1])
     return _dequant_linear(self, input, skip_quantized_matmul=False)
 
 
@@ -417,7 +423,7 @@ def _w8a8_forward(self, input: torch.Tensor) -> torch.Tensor:
     x2 = _rows(input)
     if self.svd_up is None:
         group = self.__dict__.get("_sdnq_siblings")
-        if group is not None and siblings.siblings_enabled():      # to_q / to_k / to_v ...: one K2 + one grouped K1 launch for all of them
+        if type(group) is siblings.SiblingGroup and siblings.siblings_enabled():      # to_q / to_k / to_v ...: one K2 + one grouped K1 launch for all of them
             out = group.forward(self, x2, input.dtype)
             if out is not None:
                 return out.view(*input.shape[:-1], out.shape[-1])

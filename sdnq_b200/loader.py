@@ -137,6 +137,8 @@ def apply_sdnq_options_to_model(model, dtype=None, dequantize_fp32=None, use_qua
             holder.use_quantized_matmul = use_quantized_matmul
         if dequantize_fp32 is not None:
             holder.dequantize_fp32 = dequantize_fp32
+    from .siblings import fuse_sibling_projections
+    fuse_sibling_projections(model)      # layers may have changed path (matmul on / off): register the sibling groups of the new state
     return model
 
 

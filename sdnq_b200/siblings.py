@@ -38,18 +38,27 @@ def siblings_enabled() -> bool:
     return os.environ.get("SDNQ_B200_SIBLINGS", "1") not in ("0", "false", "no")
 
 
-def _eligible(layer) -> bool:
+def _kind(layer):
+    """"mm": a Linear on the quantized-matmul path the grouped K1 launch covers; "dq": a Linear on the dequant path; None: neither"""
     d = getattr(layer, "sdnq_dequantizer", None)
-    if d is None or layer.__class__.__name__ != "SDNQLinear" or not d.use_quantized_matmul or d.is_conv:
-        return False
+    if d is None or layer.__class__.__name__ != "SDNQLinear" or d.is_conv or len(tuple(d.original_shape)) != 2:
+        return None
+    if not d.use_quantized_matmul:
+        return "dq"
     if getattr(layer, "svd_up", None) is not None or (layer.weight.ndim != 2 and not d.is_packed):
-        return False
-    return d.quantized_matmul_dtype in ("int8", "uint8", "float8_e4m3fn")
+        return None
+    return "mm" if d.quantized_matmul_dtype in ("int8", "uint8", "float8_e4m3fn") else None
+
+
+def _eligible(layer) -> bool:
+    return _kind(layer) == "mm"
 
 
 def _signature(layer):
     d = layer.sdnq_dequantizer
-    N, K = d.matmul_nk()
+    N, K = d.matmul_nk() if d.use_quantized_matmul else tuple(d.original_shape)
+    if not d.use_quantized_matmul:
+        return ("dq", N, K)                  # one batched library GEMM: the members' weights have one shape
     return (K, d.quantized_matmul_dtype, d.hadamard_group_size if d.use_hadamard else 0)
 
 
@@ -184,17 +193,83 @@ class SiblingGroup:
                 del layer.__dict__["_sdnq_siblings"]
 
 
+class DequantSiblingGroup(SiblingGroup):
+    """Siblings on the dequant path (use_quantized_matmul=False): the reference runs F.linear(x, dequantised weight, bias) per layer
+    (layers/linear/forward.py:24-26).  When the members' dequantised weights sit next to each other in memory -- they do when the
+    batched dequantiser (prefetch.py) produced them: consecutive layers of the learned call order are consecutive in its slab -- the
+    members' GEMMs run as ONE strided-batched library GEMM over that slab (weights [G, N, K], activations broadcast, outputs
+    [G, M, N]: every member's output is its own contiguous slice).  Otherwise every member runs its own F.linear, as before."""
+
+    def _stacked_bias(self, biases, N, like):
+        """[G, 1, N] biases (zeros for members without one) in the GEMM's dtype, rebuilt when a member's bias changes"""
+        marks = tuple(None if b is None else (id(b), b.data_ptr(), b._version if not b.is_inference() else 0) for b in biases) + (like.dtype, like.device)
+        if self.state is None or self.state[0] != marks:
+            stacked = torch.stack([torch.zeros(N, dtype=like.dtype, device=like.device) if b is None else b.detach().to(like.dtype) for b in biases]).unsqueeze(1)
+            self.state = (marks, stacked, list(biases))          # (the bias tensors are kept alive so that their ids stay theirs)
+        return self.state[1]
+
+    def forward(self, layer, input: torch.Tensor):
+        from .forward import _dequant_weight_overlapped, _version
+        if self.dead or not input.is_cuda:
+            return None
+        idx = self.index[id(layer)]
+        K = input.shape[-1]
+        x2 = input.reshape(-1, K)
+        stream = torch.cuda.current_stream(input.device).cuda_stream
+        key = (x2.data_ptr(), _version(input), tuple(x2.shape), tuple(x2.stride()), x2.dtype, input.device.index, stream, ops.capture_id(stream))
+        c = self.cache
+        if c is not None and c[0] == key and c[2][idx] is not None:
+            y, c[2][idx] = c[2][idx], None
+            if all(o is None for o in c[2]):
+                self.cache = None
+            return y
+        if any(_kind(sib) != "dq" for sib in self.layers) or len({_signature(sib) for sib in self.layers}) != 1:
+            self.dissolve()
+            return None
+        weights = [_dequant_weight_overlapped(sib, input, False) for sib in self.layers]
+        w0 = weights[0]
+        G, (N, Kw) = len(weights), w0.shape
+        step = weights[1].data_ptr() - w0.data_ptr() if G > 1 else 0
+        adjacent = (Kw == K and step > 0 and step % w0.element_size() == 0 and w0.is_contiguous()
+                    and all(w.shape == w0.shape and w.dtype == w0.dtype and w.is_contiguous() and w.untyped_storage().data_ptr() == w0.untyped_storage().data_ptr()
+                            and w.data_ptr() - w0.data_ptr() == i * step for i, w in enumerate(weights)))
+        biases = [sib.bias for sib in self.layers]
+        if adjacent:
+            w3 = w0.as_strided((G, N, K), (step // w0.element_size(), K, 1))
+            xb = x2.unsqueeze(0).expand(G, -1, -1)
+            if all(b is None for b in biases):
+                out3 = torch.bmm(xb, w3.transpose(1, 2))
+            else:
+                out3 = torch.baddbmm(self._stacked_bias(biases, N, w0), xb, w3.transpose(1, 2))
+            outs = [out3[i] for i in range(G)]
+        else:
+            outs = [torch.nn.functional.linear(x2, w, b) for w, b in zip(weights, biases)]
+        y, outs[idx] = outs[idx], None
+        if c is not None:
+            unused = sum(o is not None for o in c[2])
+            self.wasted = self.wasted + 1 if 2 * unused >= len(self.layers) else 0
+            if self.wasted > _WASTE_LIMIT:
+                self.dissolve()
+                return y
+        self.cache = (key, input, outs)
+        return y
+
+
 def group_siblings(layers) -> SiblingGroup | None:
-    """Register `layers` (SDNQLinear modules on the quantized-matmul path that are fed the same tensor) as one group.  Returns None
-    when they cannot share a launch (different K / matmul dtype / rotation, SVD layers, convolutions, fewer than two layers)."""
-    layers = [layer for layer in layers if _eligible(layer)]
+    """Register `layers` (SDNQLinear modules that are fed the same tensor) as one group: Linears on the quantized-matmul path share one
+    grouped K1 launch, Linears on the dequant path one batched library GEMM over their dequantised weights.  Returns None when they
+    cannot be grouped (different K / matmul dtype / rotation, SVD layers on the matmul path, convolutions, mixed paths, fewer than two)."""
+    kinds = {_kind(layer) for layer in layers}
+    if len(kinds) != 1 or None in kinds:
+        return None
+    layers = list(layers)
     if len(layers) < 2 or len(layers) > MAX_GROUP or len({_signature(layer) for layer in layers}) != 1 or len({id(layer) for layer in layers}) != len(layers):
         return None
     for layer in layers:
         old = layer.__dict__.get("_sdnq_siblings")
         if old is not None:
             old.dissolve()
-    group = SiblingGroup(layers)
+    group = SiblingGroup(layers) if kinds == {"mm"} else DequantSiblingGroup(layers)
     for layer in layers:
         layer.__dict__["_sdnq_siblings"] = group
     return group
@@ -206,7 +281,7 @@ def _family_groups(children: dict):
     for names in SIBLING_NAME_SETS:
         if all(n in children for n in names) and not any(n in used for n in names):
             mods = [children[n] for n in names]
-            if not all(_eligible(m) for m in mods):
+            if _kind(mods[0]) is None or any(_kind(m) != _kind(mods[0]) for m in mods):
                 continue
             if len({_signature(m) for m in mods}) != 1:
                 continue       # cross-attention: to_q reads the hidden states, to_k / to_v the encoder states (a later, smaller name set matches)
@@ -237,8 +312,9 @@ def _families(children: dict, cross_flag: bool):
     if cross_flag:
         children = {k: v for k, v in children.items() if k not in ("to_q", "q_proj", "query")}
     for mods in _family_groups(children):
-        q = next((children[n] for n in ("to_q", "q_proj", "query") if n in children and _eligible(children[n])), None)
-        cross = len(mods) == 2 and (cross_flag or (q is not None and q not in mods and _signature(q) != _signature(mods[0])))
+        q = next((children[n] for n in ("to_q", "q_proj", "query") if n in children and _kind(children[n]) is not None), None)
+        q_in = None if q is None else q.sdnq_dequantizer.original_shape[1]
+        cross = len(mods) == 2 and (cross_flag or (q is not None and q not in mods and q_in != mods[0].sdnq_dequantizer.original_shape[1]))
         yield mods, cross
 
 

@@ -401,6 +401,12 @@ def test_sibling_projections_are_found_by_name():
     assert fuse_named_siblings(named) == 2 + 1 + 2          # attn1 x2, pooled attn2 (4 layers); by name and width attn3 looks like self-attention
     pooled = model[0].attn2.to_k.__dict__["_sdnq_siblings"]
     assert len(pooled.layers) == 4 and model[1].attn2.to_v.__dict__["_sdnq_siblings"] is pooled
-    # layers on the dequant path never join a group
+    # layers on the dequant path form groups of their own kind (one batched library GEMM over their dequantised weights)
+    from sdnq_b200.siblings import DequantSiblingGroup, SiblingGroup
     plain = sdnq_post_load_quant(torch.nn.Sequential(Block()).to(torch.bfloat16), weights_dtype="int8", use_quantized_matmul=False, add_skip_keys=False)
-    assert all("_sdnq_siblings" not in m.__dict__ for m in plain.modules())
+    g = plain[0].attn1.to_q.__dict__["_sdnq_siblings"]
+    assert type(g) is DequantSiblingGroup and len(g.layers) == 3 and type(model[0].attn1.to_q.__dict__["_sdnq_siblings"]) is SiblingGroup
+    # flipping the matmul option re-registers the groups of the new state
+    from sdnq_b200 import apply_sdnq_options_to_model
+    flipped = apply_sdnq_options_to_model(plain, use_quantized_matmul=True)
+    assert type(flipped[0].attn1.to_q.__dict__["_sdnq_siblings"]) is SiblingGroup and g.dead

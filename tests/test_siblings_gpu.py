@@ -129,3 +129,47 @@ def test_group_with_unused_results_dissolves_itself(monkeypatch):
         monkeypatch.setenv("SDNQ_B200_SIBLINGS", "1")
         assert torch.equal(layers[0](x), ref[0]) and torch.equal(layers[1](x), ref[1])
     assert group.dead and all("_sdnq_siblings" not in layer.__dict__ for layer in layers)
+
+
+def test_dequant_path_siblings_share_one_batched_gemm(monkeypatch):
+    """to_q / to_k / to_v on the dequant path: once the batched dequantiser has put their weights next to each other, their three
+    F.linear calls become one strided-batched library GEMM; outputs equal the members' own F.linear up to the library's accumulation
+    order (different cuBLAS kernel: one bf16 ulp)."""
+    from sdnq_b200 import SDNQConfig, group_siblings, prefetch, sdnq_quantize_layer
+    from sdnq_b200.siblings import DequantSiblingGroup
+    torch.manual_seed(5)
+    cfg = SDNQConfig(weights_dtype="int4", group_size=128, use_svd=True, svd_rank=32, svd_steps=2)
+    qkv = [sdnq_quantize_layer(torch.nn.Linear(640, 640, bias=(i != 1)).to(torch.bfloat16), cfg)[0].to(DEV) for i in range(3)]
+    out_proj = sdnq_quantize_layer(torch.nn.Linear(640, 640).to(torch.bfloat16), cfg)[0].to(DEV)
+    x = torch.randn(2, 128, 640, device=DEV, dtype=torch.bfloat16)
+
+    def block(inp):
+        q, k, v = (layer(inp) for layer in qkv)
+        return out_proj(q + k + v), (q, k, v)
+
+    monkeypatch.setenv("SDNQ_B200_SIBLINGS", "0")
+    prefetch.reset()
+    ref, ref_qkv = block(x)
+    monkeypatch.setenv("SDNQ_B200_SIBLINGS", "1")
+    group = group_siblings(qkv)
+    assert type(group) is DequantSiblingGroup
+    calls = {"n": 0}
+    real_bmm, real_baddbmm = torch.bmm, torch.baddbmm
+    monkeypatch.setattr(torch, "bmm", lambda *a, **k: (calls.__setitem__("n", calls["n"] + 1), real_bmm(*a, **k))[1])
+    monkeypatch.setattr(torch, "baddbmm", lambda *a, **k: (calls.__setitem__("n", calls["n"] + 1), real_baddbmm(*a, **k))[1])
+    prefetch.reset()
+    for step in range(4):
+        calls["n"] = 0
+        got, got_qkv = block(x)
+        for g, r in zip(got_qkv + (got,), ref_qkv + (ref,)):
+            assert g.shape == r.shape and g.is_contiguous()
+            assert float((g.float() - r.float()).abs().max()) <= 2.0 ** -6 * float(r.float().abs().max()), step
+        if step >= 2:
+            assert calls["n"] == 1, (step, calls["n"])           # the three projections ran as one batched GEMM
+    # a member fed something else still gets the right answer
+    other = torch.randn(2, 128, 640, device=DEV, dtype=torch.bfloat16)
+    monkeypatch.setenv("SDNQ_B200_SIBLINGS", "0")
+    want = qkv[1](other)
+    monkeypatch.setenv("SDNQ_B200_SIBLINGS", "1")
+    qkv[0](x)
+    assert float((qkv[1](other).float() - want.float()).abs().max()) <= 2.0 ** -6 * float(want.float().abs().max())
