@@ -451,12 +451,20 @@ int launch(const ActArgs& a, cudaStream_t st) {
 template <typename T, bool kConv>
 int dispatch(const ActArgs& a, cudaStream_t st) {
     const int64_t chunks = (a.K + 255) / 256;
+    // (warps per row, chunks per warp): the unrolled chunk loops of the kernel carry the predicates of every slot, so rows that
+    // need 3 (6) chunks per warp -- K = 640 / 1280 / 2560 / 3072 / 5120 (12288): the SD-XL and FLUX widths -- get their own
+    // instantiations instead of idling through the 4th (7th, 8th) slot
     if (chunks <= 1) return launch<T, 1, 1, kConv>(a, st);
     if (chunks <= 2) return launch<T, 1, 2, kConv>(a, st);
+    if (chunks <= 3) return launch<T, 1, 3, kConv>(a, st);
     if (chunks <= 4) return launch<T, 1, 4, kConv>(a, st);
+    if (chunks <= 6) return launch<T, 2, 3, kConv>(a, st);
     if (chunks <= 8) return launch<T, 2, 4, kConv>(a, st);
+    if (chunks <= 12) return launch<T, 4, 3, kConv>(a, st);
     if (chunks <= 16) return launch<T, 4, 4, kConv>(a, st);
+    if (chunks <= 24) return launch<T, 8, 3, kConv>(a, st);
     if (chunks <= 32) return launch<T, 8, 4, kConv>(a, st);
+    if (chunks <= 48) return launch<T, 8, 6, kConv>(a, st);
     if (chunks <= 64) return launch<T, 8, 8, kConv>(a, st);
     return launch_long<T, kConv>(a, st);          // K > 16384: two-pass kernel
 }
