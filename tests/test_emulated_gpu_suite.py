@@ -288,7 +288,8 @@ def test_svd_low(kw):
 
 
 # ---- K8 (weight_quant.cu): load-time quantise + pack against the host arithmetic and the reference fixtures
-@emulated(K.test_quantize_weight_matches_host_arithmetic, keep=lambda kw: kw["N"] * kw["K"] <= 33 * 640)
+@emulated(K.test_quantize_weight_matches_host_arithmetic,
+          keep=lambda kw: kw["N"] * kw["K"] <= 33 * 640 and (kw["K"] != 1536 or kw["wd"] in ("int4", "uint8")))      # (the CTA-per-group kernel takes seconds per case here)
 def test_quantize_weight(kw):
     K.test_quantize_weight_matches_host_arithmetic(**kw)
 
