@@ -29,9 +29,10 @@ constexpr int TM = 128;         // weight rows per tile (TMEM lanes)
 // left a 1280 x 1280 weight on 50 SMs (7.7 us, the side stream could not hide it behind the 6 us GEMM of the previous layer).
 constexpr int kThreads = 192;
 constexpr int kStages = 2;
-constexpr int kStoreBufs = 2;
+// output staging blocks per epilogue warp: a 64-wide tile is one block per warp, so a second buffer would only cost the shared memory
+// that lets a 4th CTA live on the SM
+template <int TN> constexpr int store_bufs() { return TN == 64 ? 1 : 2; }
 constexpr int kStoreBlkBytes = 32 * 128;
-constexpr int kStoreBytes = 4 * kStoreBufs * kStoreBlkBytes;
 constexpr int kMaxRank = 64;
 // operand stages are sized by the layer's rank at launch: A = svd_up tile [128 x r], B = svd_down tile [TN x r] (r * 2 bytes per row)
 __host__ __device__ constexpr int stage_a_bytes(int rank) { return TM * rank * 2; }
@@ -43,12 +44,14 @@ template <int TN> struct SvdCfg {
     static constexpr int kBlocks = TN / 64;                           // 64-column store blocks per tile
     static constexpr int kScFloats = 2 * kBlocks * 32;                // (scale, zp) x blocks x 32 lanes, per warp and buffer
     static constexpr int kScTotal = 4 * 2 * kScFloats * 4;
+    static constexpr int kStoreBufs = store_bufs<TN>();
+    static constexpr int kStoreBytes = 4 * kStoreBufs * kStoreBlkBytes;
     static constexpr int kFixedBytes = kStoreBytes + kPkTotal + kScTotal + 256;
     __host__ __device__ static constexpr int smem_bytes(int rank) { return kStages * (stage_a_bytes(rank) + stage_b_bytes(rank)) + kFixedBytes; }
     // Two accumulator stages of TN columns: allocating exactly that (not all 512 columns) and keeping the CTA small lets several
     // CTAs share an SM, which is what hides the per-tile latency chain (TMA -> MMA -> TMEM -> epilogue)
     static constexpr int kTmemCols = 2 * TN;
-    static constexpr int kCtasPerSm = 512 / kTmemCols < 3 ? 512 / kTmemCols : 3;      // (launch bound: registers for up to 3 CTAs)
+    static constexpr int kCtasPerSm = 512 / kTmemCols < 4 ? 512 / kTmemCols : 4;      // (launch bound: registers for up to 4 CTAs)
     static int ctas_per_sm(int rank) {
         const int by_smem = (227 * 1024) / (smem_bytes(rank) + 1024);
         return by_smem < 1 ? 1 : by_smem < kCtasPerSm ? by_smem : kCtasPerSm;
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(kThreads, SvdCfg<TN>::kCtasPerSm)
 dequant_svd_kernel(const __grid_constant__ BatchEntry single, const BatchEntry* __restrict__ table, const int n_entries, const int total_tiles,
                    const int stage_rank) {
     using SC = SvdCfg<TN>;
-    constexpr int kPkBytes = SC::kPkBytes, kPkTotal = SC::kPkTotal, kScTotal = SC::kScTotal;
+    constexpr int kPkBytes = SC::kPkBytes, kPkTotal = SC::kPkTotal, kScTotal = SC::kScTotal, kStoreBufs = SC::kStoreBufs, kStoreBytes = SC::kStoreBytes;
     const BatchEntry* const tab = table != nullptr ? table : &single;
     const int kStageA = stage_a_bytes(stage_rank), kStageB = SC::stage_b_bytes(stage_rank);      // stages sized for the largest rank of the launch
     // tile t of the launch -> the entry it belongs to (t only grows in every role's loop, so the search resumes at `li`)
