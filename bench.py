@@ -499,21 +499,55 @@ def run_workload(name, args, world, rank, device, peaks, with_roofline=True):
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop(w0, w1) if rank == 0 else None
 
-    # ---- timed region 2: end to end with host buffers (pinned H2D of the step inputs, D2H of the step output)
+    # ---- timed region 2: end to end with host buffers.  Every step copies its inputs from pinned host memory and its output back to
+    # pinned host memory, all inside the timed region; as a serving loop would, the copies run on two copy streams through device staging
+    # buffers, so the H2D of step i+1 and the D2H of step i-1 overlap the compute of step i (the graph reads / writes its static buffers
+    # through a device-to-device copy on the compute stream).  The first H2D and the last D2H are not hidden and are inside the region.
     host_out = torch.empty(y_graph.shape, dtype=y_graph.dtype).pin_memory()
-    for _ in range(2):
-        for k_, v in host_inputs.items():
-            dev_in[k_].copy_(v, non_blocking=True)
-        run_step()
-        host_out.copy_(y_graph, non_blocking=True)
+    main_s = torch.cuda.current_stream()
+    h2d_s, d2h_s = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+    stage_in = {k_: torch.empty_like(v) for k_, v in dev_in.items()}
+    stage_out = torch.empty_like(y_graph)
+
+    def e2e_steps(n):
+        def upload(after=None):
+            with torch.cuda.stream(h2d_s):
+                if after is not None:
+                    h2d_s.wait_event(after)                    # the staging buffers have been read by the previous step
+                for k_, v in host_inputs.items():
+                    stage_in[k_].copy_(v, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(h2d_s)
+            return ev
+        h2d_s.wait_stream(main_s)
+        d2h_s.wait_stream(main_s)
+        landed, drained = upload(), None
+        for i in range(n):
+            main_s.wait_event(landed)                          # this step's inputs are in the staging buffers
+            for k_ in dev_in:
+                dev_in[k_].copy_(stage_in[k_], non_blocking=True)
+            taken = torch.cuda.Event()
+            taken.record(main_s)
+            if i + 1 < n:
+                landed = upload(after=taken)                   # next step's inputs travel while this step computes
+            run_step()
+            if drained is not None:
+                main_s.wait_event(drained)                     # the previous result has left the output staging buffer
+            stage_out.copy_(y_graph, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(main_s)
+            with torch.cuda.stream(d2h_s):
+                d2h_s.wait_event(ready)
+                host_out.copy_(stage_out, non_blocking=True)   # this step's result travels while the next step computes
+                drained = torch.cuda.Event()
+                drained.record(d2h_s)
+        main_s.wait_event(drained)                             # the last result is on the host before the region ends
+
+    e2e_steps(2)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(args.steps):
-        for k_, v in host_inputs.items():
-            dev_in[k_].copy_(v, non_blocking=True)
-        run_step()
-        host_out.copy_(y_graph, non_blocking=True)
+    e2e_steps(args.steps)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -646,7 +680,9 @@ def run_workload(name, args, world, rank, device, peaks, with_roofline=True):
            "vs_baseline": None, "dtype": spec["dtype"], "data": "synthetic", "config": workload_config(name, world),
            "execution": "whole step captured in one CUDA graph, replayed per step; sibling projections (to_q / to_k / to_v, cross-attention to_k / to_v) "
                         f"share one activation-quantise launch and one grouped GEMM launch (--siblings {args.siblings}: {sib_groups} groups)",
-           "e2e": {"value": tfl_e2e, "unit": "TFLOP/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "e2e": {"value": tfl_e2e, "unit": "TFLOP/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "copies": "pinned host <-> device staging buffers on two copy streams, overlapped with the neighbouring steps' compute; "
+                             "first upload and last download inside the timed region"},
            "gpu_launches": int(launches_per_step) * args.steps, "launches_per_step": int(launches_per_step),
            "clocks": clocks, "roofline": roofline}
     del graph, stack, acts
