@@ -13,15 +13,31 @@ from sdnq_b200 import _lib
 CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
 
 
-@pytest.mark.skipif(not os.path.exists(_lib.LIB_PATH) or not os.path.exists(CUOBJDUMP), reason="library not built or cuobjdump missing")
-def test_library_contains_tcgen05_tma_and_pair_instructions():
-    # the disassembly is ~400 MB of text: filter it in a pipe instead of holding it in Python
-    pattern = (r"arch = sm_[0-9a-z]+|UTC[A-Z]+MMA(\.2CTA)?|UTMALDG\.2D(\.2CTA)?|UTMASTG\.2D|LDTM\.x32|UTCBAR(\.2CTA\.MULTICAST)?|"
-               r"HMMA\.16816\.F32(\.BF16)?|MOVM\.16\.MT88|UCGABAR_ARV")
-    dump = subprocess.Popen([CUOBJDUMP, "-sass", _lib.LIB_PATH], stdout=subprocess.PIPE)
-    hits = subprocess.run(["grep", "-oE", pattern], stdin=dump.stdout, capture_output=True, text=True).stdout.split("\n")
-    dump.wait()
-    ops = collections.Counter(h.strip() for h in hits if h.strip())
+NVDISASM = shutil.which("nvdisasm") or "/usr/local/cuda/bin/nvdisasm"
+PATTERN = (r"UTC[A-Z]+MMA(\.2CTA)?|UTMALDG\.2D(\.2CTA)?|UTMASTG\.2D|LDTM\.x32|UTCBAR(\.2CTA\.MULTICAST)?|"
+           r"HMMA\.16816\.F32(\.BF16)?|MOVM\.16\.MT88|UCGABAR_ARV")
+
+
+def _count_ops(cubin):
+    dis = subprocess.Popen([NVDISASM, cubin], stdout=subprocess.PIPE)
+    hits = subprocess.run(["grep", "-oE", PATTERN], stdin=dis.stdout, capture_output=True, text=True).stdout.split("\n")
+    dis.wait()
+    return collections.Counter(h.strip() for h in hits if h.strip())
+
+
+@pytest.mark.skipif(not os.path.exists(_lib.LIB_PATH) or not os.path.exists(CUOBJDUMP) or not os.path.exists(NVDISASM),
+                    reason="library not built or cuobjdump / nvdisasm missing")
+def test_library_contains_tcgen05_tma_and_pair_instructions(tmp_path):
+    # the disassembly is several hundred MB of text: the embedded cubins (one per translation unit) are extracted and disassembled in
+    # parallel, each filtered in a pipe
+    from concurrent.futures import ThreadPoolExecutor
+    subprocess.run([CUOBJDUMP, "-xelf", "all", _lib.LIB_PATH], cwd=tmp_path, check=True, capture_output=True)
+    cubins = sorted(str(p) for p in tmp_path.glob("*.cubin"))
+    assert cubins, "no device code in the library"
+    ops = collections.Counter({f"arch = {os.path.basename(c).split('.')[-2]}": 1 for c in cubins})
+    with ThreadPoolExecutor(max_workers=min(16, len(cubins))) as pool:
+        for counted in pool.map(_count_ops, cubins):
+            ops.update(counted)
     assert set(k for k in ops if k.startswith("arch")) == {"arch = sm_100a"}, "the library must contain sm_100a code only"
     expect = {
         "UTCIMMA": "tcgen05.mma kind::i8 (K1 int8)", "UTCQMMA": "tcgen05.mma kind::f8f6f4 (K1 fp8)", "UTCHMMA": "tcgen05.mma kind::f16 (K3s SVD update)",
