@@ -195,6 +195,19 @@ SDNQ_API int sdnq_b200_scaled_mm(const void* a, const void* b, int ab_dtype, con
                         const int32_t* rowsum, const float* zp, const int32_t* colsum, const float* zx,
                         void* out, int out_dtype, int64_t M, int64_t N, int64_t K, void* stream);
 
+/* The same scaled matmul with a caller-owned workspace, which lets the library schedule "stream-K": int8 GEMMs whose 128 x 128 tiles
+ * would leave a large part of the last wave of SMs idle (SD-XL: 80 tiles on 148 SMs) split their k-blocks evenly over all SMs; partial
+ * 32-bit accumulators are parked in the workspace and added by the CTA that finishes the tile -- integer sums, so the output is
+ * bit-identical to sdnq_b200_scaled_mm.  The workspace (sdnq_b200_scaled_mm_workspace_bytes() bytes, 16-byte aligned) must be
+ * ZERO before its first use and belong to one stream at a time; the library leaves its flag area zero after every launch.
+ * workspace = NULL (or too small): exactly sdnq_b200_scaled_mm. */
+SDNQ_API size_t sdnq_b200_scaled_mm_workspace_bytes(void);
+SDNQ_API int sdnq_b200_scaled_mm_ws(const void* a, const void* b, int ab_dtype, const float* sx, const float* sw,
+                        const void* bias, int bias_dtype, int64_t bias_ld,
+                        const int32_t* rowsum, const float* zp, const int32_t* colsum, const float* zx,
+                        void* out, int out_dtype, int64_t M, int64_t N, int64_t K,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K1 with the packed-weight unpack fused into the GEMM (north_star "unpack + scale in the GEMM prologue"):
  *      linear_int8.py:38-44 / linear_fp8.py:38 (per-call unpack_int / unpack_float(...).t_() of a row-wise packed weight,
  *      packed_int/unpack.py:233-372, packed_float.py:85-132) + the scaled matmul above.

@@ -57,6 +57,8 @@ SIGNATURES = {
     "sdnq_b200_conv_act_quant_ws": (_I, [_P, _I, ctypes.POINTER(Conv2dGeometry), _I, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "sdnq_b200_rows_to_nchw": (_I, [_P, _P, _I, _L, _L, _L, _P]),
     "sdnq_b200_scaled_mm": (_I, [_P, _P, _I, _P, _P, _P, _I, _L, _P, _P, _P, _P, _P, _I, _L, _L, _L, _P]),
+    "sdnq_b200_scaled_mm_workspace_bytes": (_Z, []),
+    "sdnq_b200_scaled_mm_ws": (_I, [_P, _P, _I, _P, _P, _P, _I, _L, _P, _P, _P, _P, _P, _I, _L, _L, _L, _P, _Z, _P]),
     "sdnq_b200_scaled_mm_packed": (_I, [_P, _P, _WF, _P, _P, _P, _I, _L, _P, _P, _P, _I, _L, _L, _L, _P]),
     "sdnq_b200_mm": (_I, [_P, _P, _I, _P, _L, _L, _L, _P]),
     "sdnq_b200_linear_small_m": (_I, [_P, _I, _L, _P, _I, _P, _P, _P, _I, _P, _L, _L, _L, _P]),

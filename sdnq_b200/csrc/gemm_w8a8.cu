@@ -44,6 +44,36 @@ int launch_gemm_out(const void* a, const void* b, const GemmParams& p, cudaStrea
     }
 }
 
+// Stream-K (gemm_w8a8_kernel<..., kSK>): an int8 GEMM whose 128 x 128 tiles fill the last wave of SMs badly can split its k-blocks
+// evenly over all SMs instead.  Needs the caller's workspace (parked partial accumulators + flags).  SDNQ_B200_STREAMK=0 turns it
+// off, =1 forces it wherever it is legal (tests, A/B measurements).
+size_t stream_k_workspace_bytes() { return size_t(num_sms()) * BM * 128 * 4 + size_t(num_sms()) * 4 * sizeof(int); }
+
+bool use_stream_k(const GemmParams& p, bool i8, int wbits) {
+    const char* e = getenv("SDNQ_B200_STREAMK");       // read per call: tests flip it inside one process
+    const int mode = e != nullptr ? atoi(e) : -1;
+    if (mode == 0 || p.sk_ws == nullptr || !i8 || wbits != 8 || p.raw || p.svd_rank != 0 || p.n_groups != 0) return false;
+    if (p.out_dtype != SDNQ_BF16 && p.out_dtype != SDNQ_F16) return false;
+    const int sms = num_sms();
+    const int64_t tiles = int64_t((p.M + BM - 1) / BM) * ((p.N + 127) / 128), kb = (p.K + BK - 1) / BK;
+    if (tiles * kb < 2 * int64_t(sms) || tiles * kb >= (int64_t(1) << 30)) return false;      // at least two k-blocks per CTA
+    if (mode == 1) return true;
+    const int64_t waves = (tiles + sms - 1) / sms;
+    // Measured on B200 (profiles/r02_streamk_ab.log): a CTA streams ~100 GB/s of operands whatever the number of busy SMs (6 stages x
+    // 32 KB in flight against ~1.8 us of load latency), and a split tile pays a parked 64 KB accumulator, a flag round trip and an
+    // epilogue that nothing overlaps.  Splitting wins only for very deep tiles on a badly filled wave (1024 x 1280 x 10240: 23.6 ->
+    // 21.2 us); at SD-XL's K <= 5120 whole tiles are 2 - 5 us faster, so the automatic rule is narrow.
+    return tiles * 10 < waves * sms * 8 && tiles <= int64_t(sms) && kb >= 64;
+}
+
+template <bool kInt8>
+int launch_gemm_sk(const void* a, const void* b, const GemmParams& p, cudaStream_t st) {
+    const bool simple = !p.zp && !p.colsum && (p.bias == nullptr || p.bias_ld == 0);
+    if (p.out_dtype == SDNQ_BF16)
+        return simple ? launch_gemm<128, kInt8, OUT_BF16, true, 8, 0, 1, false, true>(a, b, p, st) : launch_gemm<128, kInt8, OUT_BF16, false, 8, 0, 1, false, true>(a, b, p, st);
+    return simple ? launch_gemm<128, kInt8, OUT_F16, true, 8, 0, 1, false, true>(a, b, p, st) : launch_gemm<128, kInt8, OUT_F16, false, 8, 0, 1, false, true>(a, b, p, st);
+}
+
 // Tile-N choice: the widest tile that still gives every SM work; BN=256 halves the per-MMA shared-memory
 // operand traffic relative to BN=128, so it wins whenever the grid is full either way.
 // seg_align != 0 (grouped launch): the segments of the concatenated operand start at multiples of seg_align (128 or 256), which
@@ -139,6 +169,7 @@ int scaled_mm_impl(const void* a, const void* b, int ab_dtype, GemmParams p, cud
         return launch_gemm_packed_any(a, b, p, st);
     }
     if (p.svd_rank != 0) return i8 ? launch_gemm_svd<true, 8>(a, b, p, st) : launch_gemm_svd<false, 8>(a, b, p, st);
+    if (use_stream_k(p, i8, wbits)) return launch_gemm_sk<true>(a, b, p, st);
     if (const int pair_bn = pick_pair(p); pair_bn != 0) {
         if (pair_bn == 256) return i8 ? launch_gemm_pair<256, true>(a, b, p, st) : launch_gemm_pair<256, false>(a, b, p, st);
         return i8 ? launch_gemm_pair<128, true>(a, b, p, st) : launch_gemm_pair<128, false>(a, b, p, st);
@@ -218,6 +249,21 @@ static int packed_params(const sdnq_weight_format* b_fmt, const float* zp, const
     p.pk_unsigned = f.is_unsigned;
     *ab = SDNQ_F8E4M3;
     return SDNQ_OK;
+}
+
+extern "C" size_t sdnq_b200_scaled_mm_workspace_bytes(void) { return stream_k_workspace_bytes(); }
+
+extern "C" int sdnq_b200_scaled_mm_ws(const void* a, const void* b, int ab_dtype, const float* sx, const float* sw, const void* bias,
+                                      int bias_dtype, int64_t bias_ld, const int32_t* rowsum, const float* zp, const int32_t* colsum,
+                                      const float* zx, void* out, int out_dtype, int64_t M, int64_t N, int64_t K, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+    SDNQ_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), SDNQ_EUNSUPPORTED, "dimension too large");
+    GemmParams p{sx, sw, bias, bias_dtype, bias_ld, rowsum, zp, colsum, zx, out, out_dtype, (int)M, (int)N, (int)K, 0, 0u, ab_dtype == SDNQ_F8E5M2 ? 1u : 0u};
+    if (workspace != nullptr && workspace_bytes >= stream_k_workspace_bytes() && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0) {
+        p.sk_flags = reinterpret_cast<int*>(workspace);                                              // [SMs][4], zero between launches
+        p.sk_ws = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + size_t(num_sms()) * 4 * sizeof(int));
+    }
+    return scaled_mm_impl(a, b, ab_dtype, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int sdnq_b200_scaled_mm_packed(const void* a, const void* b_packed, const sdnq_weight_format* b_fmt, const float* sx, const float* sw,

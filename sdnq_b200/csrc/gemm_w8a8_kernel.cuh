@@ -73,6 +73,9 @@ struct GemmParams {
     // packed weights of any width (WB == 7 instantiation): storage bits 2..7, integer codes (pk_kind 0: code - pk_sub per byte) or
     // minifloat codes (pk_kind 1: e<pk_exp>m<pk_man>, expanded to the e4m3 byte of the same value through a 128-entry table)
     int pk_bits, pk_kind, pk_exp, pk_man, pk_unsigned;
+    // stream-K (kSK instantiation): parked partial accumulators [CTA][128 x BN] of 32-bit words, and one flag per CTA and epilogue warp
+    uint32_t* sk_ws;
+    int* sk_flags;
     // grouped launch (n_groups != 0): several Linears fed by the same activations in one launch.  B, sw, bias, zp and colsum are the
     // siblings' tensors concatenated along N, each segment starting at grp_start[g] (a multiple of the tile width) and holding
     // grp_n[g] real rows (zero rows fill the tail); N = grp_start[n_groups]; every sibling has its own contiguous [M, grp_n[g]] output
@@ -185,7 +188,14 @@ __device__ __forceinline__ void load8_any(const void* p, int64_t i, int dtype, f
 // kSvd: the SVD branch of the W8A8 forwards (linear_int8.py:57-62).  The reference adds bias2d = bias + (x @ svd_down) @ svd_up as
 // a dense [M,N] bias; here the rank-r product low[128 x r] . svd_up[BN x r]^T of the tile is one more tcgen05.mma (kind::f16) after
 // the k-loop into its own f32 TMEM region, and the epilogue adds it to the bias in f32 before the fma.
-template <int BN, bool kInt8, int OUT, bool kSimple, int WB, int XM, int CG, bool kSvd = false>
+// kSK (stream-K): the launch's k-blocks (tile-major: tile 0's k-blocks, tile 1's, ...) are split EVENLY over the CTAs instead of
+// tile by tile, so a GEMM of 80 tiles keeps all 148 SMs loading and multiplying.  A CTA's share is a run of segments (tile, k-block
+// range).  A segment that starts inside a tile parks its raw accumulator in global memory and raises a flag; the CTA whose segment
+// holds the tile's FIRST k-block -- by construction the last segment of its run, while every parked piece of that tile is the first
+// segment of a higher-numbered CTA's run -- adds the parked pieces to its own accumulator and runs the epilogue.  Nobody waits for a
+// CTA that could be waiting itself; all CTAs are co-resident (grid = SMs, one CTA per SM).  int8 only: 32-bit integer partial sums
+// add up to exactly the accumulator of the un-split tile, so the output is bit-identical.
+template <int BN, bool kInt8, int OUT, bool kSimple, int WB, int XM, int CG, bool kSvd = false, bool kSK = false>
 __global__ void __launch_bounds__((Cfg<BN, WB, CG, kSvd>::kThreads), 1)
 gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ OutMaps tmaps_o, const __grid_constant__ CUtensorMap tmap_l,
@@ -193,6 +203,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     using C = Cfg<BN, WB, CG, kSvd>;
     static_assert(!kSvd || (XM == 0 && !kSimple), "SVD tiles use the generic epilogue and the stand-alone activation quantiser");
     static_assert(CG == 1 || XM == 0, "the fused quantiser runs with single-CTA MMAs");
+    static_assert(!kSK || (kInt8 && CG == 1 && WB == 8 && XM == 0 && !kSvd && OUT != OUT_RAW32), "stream-K: plain int8 single-CTA tiles");
     constexpr bool kPair = CG == 2;
     // CTA pair: rank 0 (the leader) issues the MMAs; tiles are numbered per pair (256 rows x BN columns)
     const uint32_t cta_rank = kPair ? ptx::cluster_ctarank() : 0u;
@@ -275,9 +286,34 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t tmem_base = *tmem_slot_ptr;
     pdl_launch_dependents();     // our own dependents may begin their prologue
 
-    // weight prefetch bookkeeping shared by the producer branch below
-    const int tile0 = tile_first;
-    const int npre = (!kPacked && tile0 < num_tiles) ? (num_kb < C::kStages ? num_kb : C::kStages) : 0;
+    // ---- work of this CTA as a run of segments (tile, k-blocks [kb0, kb1)): whole tiles, or (kSK) an even share of all k-blocks
+    struct Seg { int tile, kb0, kb1; };
+    const int64_t sk_total = int64_t(num_tiles) * num_kb;
+    auto sk_first_unit = [&](int cta) { return static_cast<int>(sk_total * cta / int(gridDim.x)); };
+    const int sk_u0 = kSK ? sk_first_unit(blockIdx.x) : 0, sk_u1 = kSK ? sk_first_unit(blockIdx.x + 1) : 0;
+    const int seg_start = kSK ? sk_u0 : tile_first;
+    auto seg_next = [&](int& cursor, Seg& sg) -> bool {
+        if constexpr (kSK) {
+            if (cursor >= sk_u1) return false;
+            sg.tile = cursor / num_kb;
+            sg.kb0 = cursor - sg.tile * num_kb;
+            sg.kb1 = min(num_kb, sg.kb0 + (sk_u1 - cursor));
+            cursor += sg.kb1 - sg.kb0;
+        } else {
+            if (cursor >= num_tiles) return false;
+            sg.tile = cursor;
+            sg.kb0 = 0;
+            sg.kb1 = num_kb;
+            cursor += tile_step;
+        }
+        return true;
+    };
+    // weight prefetch bookkeeping shared by the producer branch below: the first segment's first k-blocks
+    const int tile0 = kSK ? sk_u0 / num_kb : tile_first;
+    const int kb_first = kSK ? sk_u0 - tile0 * num_kb : 0;
+    const int first_len = kSK ? min(num_kb - kb_first, sk_u1 - sk_u0) : num_kb;
+    const bool has_work = kSK ? sk_u0 < sk_u1 : tile0 < num_tiles;
+    const int npre = (!kPacked && has_work) ? (first_len < C::kStages ? first_len : C::kStages) : 0;
     if constexpr (XM != 0) {
         // ======================================================== phase 1: quantise this CTA's share of the activation rows
         if (warp == 0 && lane == 0 && npre > 0) {                 // weights first: they do not depend on anything
@@ -408,7 +444,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const int nb0 = tile_nb0(tile0);
                     for (int s = 0; s < npre; ++s) {
                         expect_stage(s);
-                        tma_load(smem_b + s * C::kStageB, &tmap_b, load_bar(s), s * BK, nb0);
+                        tma_load(smem_b + s * C::kStageB, &tmap_b, load_bar(s), (kb_first + s) * BK, nb0);
                     }
                 }
                 pdl_wait();
@@ -416,16 +452,18 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (npre > 0) {
                 const int m0 = tile_m0(tile0);
                 acquire_strip(tile0 / num_n);
-                for (int s = 0; s < npre; ++s) tma_load(smem_a + s * C::kStageA, &tmap_a, load_bar(s), s * BK, m0);
+                for (int s = 0; s < npre; ++s) tma_load(smem_a + s * C::kStageA, &tmap_a, load_bar(s), (kb_first + s) * BK, m0);
             }
-            int stage = 0, pit = 0;
+            int stage = 0, pit = 0, cursor = seg_start;
             uint32_t phase = 0;
-            for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++pit) {
+            Seg sg;
+            for (; seg_next(cursor, sg); ++pit) {
+                const int tile = sg.tile;
                 const int m0 = tile_m0(tile), nb0 = tile_nb0(tile);
-                if (tile != tile0) acquire_strip(tile / num_n);
+                if (pit != 0) acquire_strip(tile / num_n);
                 load_svd_tiles(pit, m0, (tile % num_n) * BN);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    if (tile == tile0 && kb < npre) {             // already in flight (prefetched above)
+                for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+                    if (pit == 0 && kb < sg.kb0 + npre) {         // already in flight (prefetched above)
                         if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
                         continue;
                     }
@@ -447,14 +485,15 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             auto commit = [&](uint32_t bar) { if constexpr (kPair) ptx::umma_commit_pair(bar); else ptx::umma_commit(bar); };
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
+            int it = 0, cursor = seg_start;
+            Seg sg;
+            for (; seg_next(cursor, sg); ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1u;
                 ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);     // epilogue has drained this accumulator stage
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
                     ptx::mbar_wait(full_bar(stage), phase);       // TMA bytes have landed
                     ptx::tc_fence_after();
                     const uint64_t a_desc = ptx::make_smem_desc_sw128(smem_a + stage * C::kStageA);
@@ -464,10 +503,10 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         // advancing K inside the 128 B swizzle span = advancing the start address (>>4 units)
                         if constexpr (kPair)
                             ptx::umma_ss_pair<kInt8>(d_tmem, a_desc + uint64_t(k * UMMA_K >> 4), b_desc + uint64_t(k * UMMA_K >> 4), idesc,
-                                                     (kb | k) != 0 ? 1u : 0u);
+                                                     (kb != sg.kb0 || k != 0) ? 1u : 0u);
                         else
                             ptx::umma_ss<kInt8>(d_tmem, a_desc + uint64_t(k * UMMA_K >> 4), b_desc + uint64_t(k * UMMA_K >> 4), idesc,
-                                                (kb | k) != 0 ? 1u : 0u);
+                                                (kb != sg.kb0 || k != 0) ? 1u : 0u);
                     }
                     commit(empty_bar(stage));                     // smem slot free (in both CTAs of a pair) once these MMAs retire
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
@@ -546,11 +585,23 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         pdl_wait();                                               // sx / rowsum / bias may come from the predecessor
         const int q = warp & 3;                                   // TMEM lane quarter this warp may access
         const uint32_t my_o = smem_o + uint32_t(warp - 2) * (kStoreBufs * kStoreBlkBytes);
-        int it = 0, blk = 0;
-        for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
+        int it = 0, blk = 0, cursor = seg_start;
+        Seg sg;
+        for (; seg_next(cursor, sg); ++it) {
+            const int tile = sg.tile;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1u;
             const int m0 = tile_m0(tile), n0 = (tile % num_n) * BN;
+            // stream-K: 0 = the segment is the whole tile, 1 = it holds the tile's first k-block (collects the parked pieces and
+            // finishes the tile), 2 = it starts inside the tile (parks its accumulator)
+            [[maybe_unused]] const int sk_kind = !kSK ? 0 : sg.kb0 != 0 ? 2 : sg.kb1 != num_kb ? 1 : 0;
+            [[maybe_unused]] int sk_last = int(blockIdx.x);       // kind 1: CTAs blockIdx.x + 1 .. sk_last parked a piece of this tile
+            if constexpr (kSK) {
+                if (sk_kind == 1) {
+                    const int tile_end = (tile + 1) * num_kb;
+                    while (sk_last + 1 < int(gridDim.x) && sk_first_unit(sk_last + 1) < tile_end) ++sk_last;
+                }
+            }
             // grouped launch: the sibling this tile belongs to; its real columns end at n_end, its output starts at column n_base
             int grp = 0;
             while (grp + 1 < p.n_groups && n0 >= p.grp_start[grp + 1]) ++grp;
@@ -590,6 +641,19 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ptx::tc_fence_after();
             if (XM != 0 && m_ok) sxm = __ldcg(p.sx + m);          // written by phase 1 of some CTA of this grid: read it from L2, after the accumulator
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
+            if constexpr (kSK) {
+                if (sk_kind == 1) {                               // the parked pieces of this warp's rows have landed (whatever the rows hold)
+                    if (lane == 0) {
+                        for (int c2 = int(blockIdx.x) + 1; c2 <= sk_last; ++c2) {
+                            int spins = 0;
+                            while (ptx::ld_acquire_gpu(p.sk_flags + c2 * 4 + q) == 0) {
+                                if (++spins > (1 << 27)) __trap();    // seconds: a CTA of this grid never ran (not co-resident?)
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
 #pragma unroll 1
             for (int cb = 0; cb < BN / CPB; ++cb) {
                 const int n = n0 + cb * CPB;
@@ -609,6 +673,28 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     __syncwarp();
                 }
                 ptx::tmem_ld_wait();
+                if constexpr (kSK) {
+                    // parked pieces: [CTA][warp quarter][column block][16-byte chunk][lane] -- every access is a coalesced 512-byte row
+                    auto piece = [&](int cta) {
+                        return reinterpret_cast<uint4*>(p.sk_ws + size_t(cta) * (BM * BN)) + (size_t(q) * (BN / CPB) + cb) * (CPB / 4) * 32 + lane;
+                    };
+                    if (sk_kind == 2) {
+                        uint4* dst = piece(int(blockIdx.x));
+#pragma unroll
+                        for (int i = 0; i < CPB / 4; ++i) dst[i * 32] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+                        continue;
+                    }
+                    if (sk_kind == 1) {
+                        for (int c2 = int(blockIdx.x) + 1; c2 <= sk_last; ++c2) {
+                            const uint4* src = piece(c2);
+#pragma unroll
+                            for (int i = 0; i < CPB / 4; ++i) {
+                                const uint4 v = __ldcg(src + i * 32);
+                                r[4 * i] += v.x; r[4 * i + 1] += v.y; r[4 * i + 2] += v.z; r[4 * i + 3] += v.w;
+                            }
+                        }
+                    }
+                }
                 const uint32_t row_addr = buf + uint32_t(lane) * 128u;
                 if constexpr (OUT == OUT_RAW32) {
 #pragma unroll
@@ -734,6 +820,17 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 ++blk;
             }
+            if constexpr (kSK) {
+                if (sk_kind == 2) {                               // publish this warp's parked rows
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) ptx::red_release_gpu_add(p.sk_flags + int(blockIdx.x) * 4 + q, 1);
+                } else if (sk_kind == 1) {                        // re-arm the flags for the next launch on this workspace
+                    __syncwarp();
+                    if (lane == 0)
+                        for (int c2 = int(blockIdx.x) + 1; c2 <= sk_last; ++c2) p.sk_flags[c2 * 4 + q] = 0;
+                }
+            }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -809,10 +906,10 @@ int make_tmap_svd(CUtensorMap* map, const void* ptr, int64_t rows, int rank, int
     return SDNQ_OK;
 }
 
-template <int BN, bool kInt8, int OUT, bool kSimple, int WB = 8, int XM = 0, int CG = 1, bool kSvd = false>
+template <int BN, bool kInt8, int OUT, bool kSimple, int WB = 8, int XM = 0, int CG = 1, bool kSvd = false, bool kSK = false>
 int launch_gemm(const void* a, const void* b, const GemmParams& p, cudaStream_t st) {
     using C = Cfg<BN, WB, CG, kSvd>;
-    auto kernel = gemm_w8a8_kernel<BN, kInt8, OUT, kSimple, WB, XM, CG, kSvd>;
+    auto kernel = gemm_w8a8_kernel<BN, kInt8, OUT, kSimple, WB, XM, CG, kSvd, kSK>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes); });
@@ -846,7 +943,7 @@ int launch_gemm(const void* a, const void* b, const GemmParams& p, cudaStream_t 
     const int tiles = ((p.M + BM * CG - 1) / (BM * CG)) * ((p.N + BN - 1) / BN);      // CG == 2: 256-row tiles, one per CTA pair
     // fused quantiser: always one CTA per SM (CTAs without a tile still quantise their share of the rows)
     const int slots = num_sms() / CG;
-    const int grid = CG * ((XM != 0 || tiles >= slots) ? slots : tiles);
+    const int grid = CG * ((XM != 0 || kSK || tiles >= slots) ? slots : tiles);      // stream-K: every SM gets an even share of the k-blocks
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(C::kThreads);

@@ -422,10 +422,28 @@ def scaled_mm(a: torch.Tensor, b_nk: torch.Tensor, sx: torch.Tensor, sw: torch.T
         if bias.ndim == 2 and bias.shape[0] != 1:
             bias_ld = bias.stride(0)
     ab = _operand_code(a.dtype, b_nk)
+    stream = _stream(a)
+    ws = _gemm_workspace(a.device, stream) if ab == SDNQ_I8 else None      # stream-K scratch (int8 only)
     with torch.cuda.device(a.device):
-        check(lib.sdnq_b200_scaled_mm(_ptr(a), _ptr(b_nk), ab, _ptr(sx), _ptr(sw), _ptr(bias), bias_code, bias_ld,
-                                      _ptr(rowsum), _ptr(zp), _ptr(colsum), _ptr(zx), _ptr(out), dtype_code(out_dtype), M, N, K, _stream(a)))
+        check(lib.sdnq_b200_scaled_mm_ws(_ptr(a), _ptr(b_nk), ab, _ptr(sx), _ptr(sw), _ptr(bias), bias_code, bias_ld,
+                                         _ptr(rowsum), _ptr(zp), _ptr(colsum), _ptr(zx), _ptr(out), dtype_code(out_dtype), M, N, K,
+                                         _ptr(ws), 0 if ws is None else ws.numel(), stream))
     return out
+
+
+_GEMM_WS: dict = {}
+
+
+def _gemm_workspace(device, stream: int):
+    """Per (device, stream, graph capture) scratch of the stream-K schedule of K1 (parked partial accumulators + flags, zeroed once: the
+    kernel leaves the flags zero after every launch).  One launch at a time uses it: launches on one stream are ordered."""
+    key = (device.index, stream, capture_id(stream))      # a graph capture gets its own (allocated from the graph's pool, zeroed by a captured memset)
+    ws = _GEMM_WS.get(key)
+    if ws is None:
+        if len(_GEMM_WS) > 64:
+            _GEMM_WS.clear()
+        ws = _GEMM_WS[key] = torch.zeros(int(_lib.load().sdnq_b200_scaled_mm_workspace_bytes()), dtype=torch.uint8, device=device)
+    return ws
 
 
 def scaled_mm_packed(a: torch.Tensor, b_packed: torch.Tensor, weights_dtype: str, N: int, sx, sw, bias=None,

@@ -461,6 +461,39 @@ def test_dequant_svd_tensor_core_path(wd, bits, N, K, rank, gs):
     assert float((du > 1).float().mean()) < 1e-3 and float((du > 0).float().mean()) < 0.03
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 1280, 1280), (1024, 1280, 5120), (4096, 640, 640), (4096, 640, 2560), (77, 1280, 2048), (300, 1288, 640),
+                                   (513, 776, 4112), (128, 128, 38016), (1000, 5120, 640), (256, 256, 128)])
+@pytest.mark.parametrize("kind", ["int8", "int8_zp", "uint8", "mat_bias"])
+def test_stream_k_gemm_is_bit_identical(M, N, K, kind, monkeypatch):
+    """K1 with its k-blocks split evenly over all SMs (parked 32-bit partial accumulators, fixed up by the CTA that holds a tile's first
+    k-block) == whole-tile scheduling, bit for bit; repeated launches on one workspace (the flags are re-armed by the kernel)."""
+    rng = np.random.default_rng(M + N + K + len(kind))
+    a = torch.from_numpy(rng.integers(-128, 128, size=(M, K)).astype(np.int8)).to(DEV)
+    b = torch.from_numpy(rng.integers(-128, 128, size=(N, K)).astype(np.int8)).to(DEV)
+    sx = torch.from_numpy((rng.random(M) * 0.05 + 1e-3).astype(np.float32)).to(DEV)
+    sw = torch.from_numpy((rng.random(N) * 0.01 + 1e-4).astype(np.float32)).to(DEV)
+    bias = torch.from_numpy(rng.standard_normal(N).astype(np.float32)).to(torch.bfloat16).to(DEV)
+    kw = {}
+    if kind in ("int8_zp", "uint8"):
+        kw.update(zp=torch.from_numpy((rng.standard_normal(N) * 0.1).astype(np.float32)).to(DEV), rowsum=a.to(torch.int32).sum(dim=1, dtype=torch.int32))
+    if kind == "uint8":
+        kw.update(zx=torch.from_numpy((rng.standard_normal(M) * 0.1).astype(np.float32)).to(DEV), colsum=b.to(torch.int32).sum(dim=1, dtype=torch.int32))
+    if kind == "mat_bias":
+        bias = torch.from_numpy(rng.standard_normal((M, N)).astype(np.float32)).to(DEV)
+    for out_dtype in (torch.bfloat16, torch.float16):
+        monkeypatch.setenv("SDNQ_B200_STREAMK", "0")
+        want = ops().scaled_mm(a, b, sx, sw, bias, out_dtype, **kw)
+        monkeypatch.setenv("SDNQ_B200_STREAMK", "1")
+        for _ in range(3):
+            got = ops().scaled_mm(a, b, sx, sw, bias, out_dtype, **kw)
+            assert torch.equal(got, want), float((got.float() - want.float()).abs().max())
+    # the exact integer accumulator, through the scaled epilogue with unit scales
+    ones_m, ones_n = torch.ones(M, device=DEV), torch.ones(N, device=DEV)
+    acc = ops().scaled_mm(a[:, :256].contiguous(), b[:, :256].contiguous(), ones_m, ones_n, None, torch.float32)
+    if K >= 256:
+        assert np.array_equal(acc.cpu().numpy(), O.int_mm(a[:, :256].cpu().numpy(), b[:, :256].cpu().numpy().T).astype(np.float32))
+
+
 # ----------------------------------------------------------------------------------------------- GEMM with in-kernel int4 unpack
 @pytest.mark.parametrize("signed", [True, False])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 128), (77, 640, 2048), (300, 1288, 640), (1000, 5120, 640), (2048, 4096, 384), (64, 136, 32)])
