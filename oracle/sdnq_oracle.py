@@ -637,6 +637,90 @@ def conv_forward(layer: Layer, x, kernel_size, stride=1, padding=0, dilation=1, 
 # =============================================================================
 # fixture loader
 # =============================================================================
+# ------------------------------------------------------------------------------------------------ quantized attention (row f3)
+# Parity status of this block: the reference's attention is a Triton program and cannot run in the authoring container (no GPU),
+# so there are no committed fixtures for it; it is pinned on the GPU box instead -- tests/test_attention_gpu.py runs the
+# UNMODIFIED reference kernel (oracle/_ref, kernels/triton_atten.py) on the same inputs and checks both this restatement and the
+# CUDA kernel against it.  Without that test having run, read this block as "parity unpinned".
+
+def _cast16(x, dtype):
+    return np.asarray(x, F32).astype(np.float16).astype(F32) if dtype == "float16" else _cast(x, dtype)
+
+
+def quantize_attn(q, k, smooth_k=True, hadamard_group=0, matmul_dtype="int8", dtype="bfloat16"):
+    """kernels/triton_atten.py:443-487 for the Q.K^T operands.  q [Z,H,QN,HD], k [Z,KH,KN,HD] (f32 arrays holding `dtype` values)
+    -> (q_codes, q_scale [Z,H,QN], k_codes, k_scale [Z,KH,KN]); codes as f32 arrays (ints, or e4m3-representable values)."""
+    q = np.asarray(q, dtype=F32)
+    k = np.asarray(k, dtype=F32)
+    if smooth_k:                                                    # :456-461
+        k = (k - k.mean(axis=2, keepdims=True, dtype=F32)).astype(F32)
+    if hadamard_group:                                              # :462-466: q in its own dtype, k cast to the rotation's dtype
+        q = rotate_hadamard(q, hadamard_group, dtype)
+        k = rotate_hadamard(_cast16(k, dtype), hadamard_group, dtype)
+    quant = quantize_int_mm if matmul_dtype == "int8" else quantize_fp_mm       # :467-469
+    q_q, q_s = quant(q, axis=-1)
+    k_q, k_s = quant(k, axis=-1)
+    return q_q.astype(F32), q_s.reshape(q.shape[:-1]).astype(F32), k_q.astype(F32), k_s.reshape(k.shape[:-1]).astype(F32)
+
+
+def attn_fwd(q_q, k_q, v, q_scale, k_scale, mask=None, is_causal=False, sm_scale=1.0, block_m=128, block_n=128, dtype="bfloat16",
+             out_dtype="bfloat16", return_lse=False):
+    """sdnq_attn_kernel (kernels/triton_atten.py:143-335) with qk_is_quantized=1, pv_is_quantized=0, use_fp16_accum=0: a block-wise
+    restatement (the result depends on BLOCK_SIZE_N only through rounding).  q_q [Z,H,QN,HD], k_q [Z,KH,KN,HD] codes, v [Z,VH,KN,HDV]
+    values of `dtype`; mask: None, an integer / bool array (0 = masked out) or a float array (additive), broadcastable to [Z,H,QN,KN]."""
+    q_q, k_q, v = np.asarray(q_q, dtype=F32), np.asarray(k_q, dtype=F32), np.asarray(v, dtype=F32)
+    Z, H, QN, _ = q_q.shape
+    _, KH, KN, _ = k_q.shape
+    _, VH, _, HDV = v.shape
+    log2_scale = F32(F32(sm_scale) * F32(1.4426950408889634))      # :189-190
+    out = np.zeros((Z, H, QN, HDV), dtype=F32)
+    lse = np.zeros((Z, H, QN), dtype=F32)
+    if mask is not None:
+        mask = np.asarray(mask)
+        is_bool = mask.dtype.kind in "biu"
+        mask = np.broadcast_to(mask if is_bool else mask.astype(F32), (Z, H, QN, KN))
+    ninf = F32(-np.inf)
+    with np.errstate(invalid="ignore", over="ignore"):
+        for z in range(Z):
+            for h in range(H):
+                kh, vh = (h * KH) // H, (h * VH) // H               # :197-198
+                for m0 in range(0, QN, block_m):
+                    m1 = min(QN, m0 + block_m)
+                    rows = np.arange(m0, m1)
+                    qs = q_scale[z, h, m0:m1, None].astype(F32)
+                    m_i = np.full((m1 - m0,), ninf, dtype=F32)      # :231-233
+                    l_i = np.ones((m1 - m0,), dtype=F32)
+                    acc = np.zeros((m1 - m0, HDV), dtype=F32)
+                    for n0 in range(0, KN, block_n):
+                        if is_causal and m0 + block_m <= n0:       # :238-239
+                            continue
+                        n1 = min(KN, n0 + block_n)
+                        dot = (q_q[z, h, m0:m1].astype(np.float64) @ k_q[z, kh, n0:n1].astype(np.float64).T).astype(F32)
+                        qk = ((dot * qs) * k_scale[z, kh, None, n0:n1].astype(F32)) * log2_scale        # :264-273
+                        if is_causal:                               # :277-278
+                            qk = np.where(rows[:, None] >= np.arange(n0, n1)[None, :], qk, ninf)
+                        if mask is not None:                        # :279-283
+                            mk = mask[z, h, m0:m1, n0:n1]
+                            qk = np.where(mk != 0, qk, ninf) if is_bool else (qk + mk).astype(F32)
+                        m_ij = np.maximum(m_i, qk.max(axis=1))      # :286
+                        both = (m_i == ninf) & (m_ij == ninf)       # :287-294 (the do_mask form; identical without a mask)
+                        alpha = np.exp2(np.where(both, F32(0), m_i - m_ij)).astype(F32)
+                        qk = qk - np.where(m_ij == ninf, F32(0), m_ij)[:, None]
+                        pm = np.exp2(qk).astype(F32)                 # :295
+                        l_i = fma32(l_i, alpha, pm.sum(axis=1, dtype=F32))       # :296
+                        acc = acc * alpha[:, None]                  # :297
+                        pv = _cast16(pm, dtype).astype(np.float64) @ v[z, vh, n0:n1].astype(np.float64)   # :319-321 (p.to(v.dtype), f32 accumulate)
+                        acc = (acc + pv.astype(F32)).astype(F32)
+                        m_i = m_ij
+                    out[z, h, m0:m1] = acc * (F32(1) / l_i)[:, None]              # :324
+                    l = m_i + np.log2(l_i)                                        # :328-330
+                    if mask is not None:
+                        l = np.where(l == ninf, F32(0), l)
+                    lse[z, h, m0:m1] = l
+    out = _cast16(out, out_dtype)
+    return (out, _cast16(lse, out_dtype)) if return_lse else out
+
+
 def load_fixture(path):
     """tests/golden/layer_*.npz -> (Layer, arrays dict, meta dict).  `key__T` arrays are the physical
     [N,K] bytes of a K-major tensor and are turned back into the logical transposed view."""

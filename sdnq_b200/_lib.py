@@ -58,6 +58,10 @@ SIGNATURES = {
     "sdnq_b200_rows_to_nchw": (_I, [_P, _P, _I, _L, _L, _L, _P]),
     "sdnq_b200_scaled_mm": (_I, [_P, _P, _I, _P, _P, _P, _I, _L, _P, _P, _P, _P, _P, _I, _L, _L, _L, _P]),
     "sdnq_b200_scaled_mm_workspace_bytes": (_Z, []),
+    "sdnq_b200_attention_workspace_bytes": (_Z, [_L, _L, _L, _L]),
+    "sdnq_b200_attention": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _I, ctypes.POINTER(ctypes.c_int64), _P, _P, _I, _L, _L, _L, _L, _L, _L, _L, _L,
+                                 ctypes.c_float, _I, _P, _Z, _P]),
+    "sdnq_b200_smooth_k": (_I, [_P, _I, _L, _L, _L, _P, _I, _P]),
     "sdnq_b200_scaled_mm_ws": (_I, [_P, _P, _I, _P, _P, _P, _I, _L, _P, _P, _P, _P, _P, _I, _L, _L, _L, _P, _Z, _P]),
     "sdnq_b200_scaled_mm_packed": (_I, [_P, _P, _WF, _P, _P, _P, _I, _L, _P, _P, _P, _I, _L, _L, _L, _P]),
     "sdnq_b200_mm": (_I, [_P, _P, _I, _P, _L, _L, _L, _P]),

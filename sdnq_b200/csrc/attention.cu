@@ -1,0 +1,569 @@
+// K9: SDNQ quantized attention forward for sm_100a.
+//
+// What it computes is the reference's `sdnq_attn_kernel` (kernels/triton_atten.py:143-335, host side sdnq_atten_fwd :338-386):
+// for every (batch z, head h) and block of query rows, a flash-attention sweep over the keys with
+//     qk      = ((dot(q_q, k_q) * q_scale[m]) * k_scale[n]) * (sm_scale * log2 e)                 (:264-275)
+//     mask    : causal (m >= n), boolean (int8: 0 = drop) or additive float, keys past KN             (:277-285)
+//     online softmax in base 2 with running max m_i and sum l_i (l_i starts at 1, m_i at -inf)        (:231-233, 286-296)
+//     acc     = acc * alpha + dot(p.to(v.dtype), v)                                                   (:297-321, unquantised PV)
+//     out     = acc / l_i ; lse = m_i + log2(l_i)                                                     (:324-335)
+// with 1-byte q / k codes (int8 or float8_e4m3fn) and their per-row f32 scales as `quantize_attn` (:443-487) produces them.
+//
+// How (nothing like the Triton program): one CTA owns 128 query rows of one head and walks the keys in tiles of 128.
+//   warp 0      TMA producer: Q tile once, K tiles into a 3-deep ring, V^T tiles (two 64-key slabs) into a 2-deep ring
+//   warp 1      MMA issuer:  S_j = Q K_j^T  (tcgen05 kind::i8 / kind::f8f6f4, 128x128x128, accumulator in TMEM, double-buffered)
+//                            O_j = P_j V_j  (tcgen05 kind::f16, A = P_j written by the softmax warps into swizzled shared memory,
+//                                            B = V^T tile; fresh accumulator per tile, double-buffered)
+//   warps 2-9   softmax: thread = one query row (its TMEM lane) x one half of the tile's columns; two warps share a lane quarter.
+//               The row maximum is exchanged between the two halves through shared memory; each half keeps its own partial sum
+//               (same running maximum => the partial sums simply add at the end) and its own half of the output columns in
+//               registers: acc = acc * alpha + O_j is applied one tile late, while the tensor core already works on the next tile.
+// V is consumed K-major ([head_dim, keys]): a small transposing pre-pass writes V^T into the caller's workspace once per call.
+#include <mutex>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sdnq {
+namespace {
+
+constexpr int kBM = 128;                 // query rows per CTA
+constexpr int kBN = 128;                 // keys per tile
+constexpr int kKStages = 3;
+constexpr int kVStages = 2;
+constexpr int kTileQK = kBM * 128;       // one Q or K tile: 128 rows x 128 bytes (head dims < 128 are zero-filled by TMA)
+constexpr int kPTile = kBM * kBN * 2;    // P tile: two 64-key slabs of 128 rows x 128 bytes
+constexpr int kSoftmaxThreads = 256;
+constexpr int kThreads = 64 + kSoftmaxThreads;
+
+struct AttnParams {
+    const float* q_scale;
+    const float* k_scale;
+    void* out;
+    void* lse;
+    const void* mask;
+    int mask_kind;                       // 0 none, 1 int8 (0 = masked out), 2 f32 additive
+    int64_t mask_sz, mask_sh, mask_sq, mask_sk;
+    int Z, H, KH, VH, QN, KN;
+    int out_dtype;
+    int causal;
+    float log2_scale;                    // sm_scale * log2(e)
+};
+
+template <int HDV>
+struct AttnCfg {
+    static constexpr int kVStage = 2 * HDV * 128;         // two slabs of [HDV rows x 64 keys] 16-bit
+    static constexpr int kOffK = kTileQK;
+    static constexpr int kOffV = kOffK + kKStages * kTileQK;
+    static constexpr int kOffP = kOffV + kVStages * kVStage;
+    static constexpr int kOffTail = kOffP + 2 * kPTile;
+    static constexpr int kTailBytes = 2 * 128 * 4 + 2 * 2 * 128 * 4 + 32 * 8 + 16;
+    static constexpr int kSmemBytes = kOffTail + kTailBytes + 1024;       // + alignment slack
+};
+
+enum Bar { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + kKStages, V_FULL = K_EMPTY + kKStages, V_EMPTY = V_FULL + kVStages,
+           S_FULL = V_EMPTY + kVStages, S_EMPTY = S_FULL + 2, P_FULL = S_EMPTY + 2, P_EMPTY = P_FULL + 2, O_FULL = P_EMPTY + 2,
+           O_EMPTY = O_FULL + 2, NUM_BARS = O_EMPTY + 2 };
+static_assert(NUM_BARS <= 32, "barrier area");
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <bool kInt8, int HDV, bool kBf16>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
+    using C = AttnCfg<HDV>;
+    constexpr int HALF = HDV / 2;                          // output columns per softmax thread
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t raw = ptx::smem_u32(smem_dyn);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_dyn + (base - raw);
+    const uint32_t smem_q = base, smem_k = base + C::kOffK, smem_v = base + C::kOffV, smem_p = base + C::kOffP;
+    float* s_ks = reinterpret_cast<float*>(smem + C::kOffTail);          // [2][128] k_scale * log2_scale of the tile's keys
+    float* s_mx = s_ks + 2 * 128;                                        // [2][2][128] half-row maxima (tile parity, half, row)
+    const uint32_t bar_base = base + C::kOffTail + 2 * 128 * 4 + 2 * 2 * 128 * 4;
+    auto bar = [&](int i) { return bar_base + 8u * uint32_t(i); };
+    const uint32_t tmem_slot = bar_base + 32 * 8;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + (tmem_slot - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = int(blockIdx.x) * kBM;
+    const int h = blockIdx.y, z = blockIdx.z;
+    const int kh = int((int64_t(h) * p.KH) / p.H), vh = int((int64_t(h) * p.VH) / p.H);     // :197-198
+    const int64_t q_row0 = (int64_t(z) * p.H + h) * p.QN;                 // first row of this head in the [Z*H*QN, HD] view
+    const int64_t k_row0 = (int64_t(z) * p.KH + kh) * p.KN;
+    const int64_t vt_row0 = (int64_t(z) * p.VH + vh) * HDV;               // first row of this head in the [Z*VH*HDV, KN] view of V^T
+    const int num_kv = (p.KN + kBN - 1) / kBN;
+    const int T = p.causal ? min(num_kv, m0 / kBN + 1) : num_kv;          // :238-239: tiles starting past the block's last row are skipped
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_q);
+        ptx::prefetch_tmap(&tmap_k);
+        ptx::prefetch_tmap(&tmap_vt);
+        ptx::mbar_init(bar(Q_FULL), 1);
+        for (int s = 0; s < kKStages; ++s) { ptx::mbar_init(bar(K_FULL + s), 1); ptx::mbar_init(bar(K_EMPTY + s), 1); }
+        for (int s = 0; s < kVStages; ++s) { ptx::mbar_init(bar(V_FULL + s), 1); ptx::mbar_init(bar(V_EMPTY + s), 1); }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(bar(S_FULL + s), 1);
+            ptx::mbar_init(bar(S_EMPTY + s), kSoftmaxThreads);
+            ptx::mbar_init(bar(P_FULL + s), kSoftmaxThreads);
+            ptx::mbar_init(bar(P_EMPTY + s), 1);
+            ptx::mbar_init(bar(O_FULL + s), 1);
+            ptx::mbar_init(bar(O_EMPTY + s), kSoftmaxThreads);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_launch_dependents();
+    // TMEM columns: S_0 [0,128)  S_1 [128,256)  O_0 [256,256+HDV)  O_1 [384,384+HDV)
+    auto s_col = [&](int b) { return uint32_t(b) * 128u; };
+    auto o_col = [&](int b) { return 256u + uint32_t(b) * 128u; };
+
+    if (warp == 0) {
+        // ======================================================== TMA producer
+        if (lane == 0) {
+            pdl_wait();
+            ptx::mbar_arrive_expect_tx(bar(Q_FULL), kTileQK);
+            ptx::tma_load_2d(smem_q, &tmap_q, bar(Q_FULL), 0, int(q_row0 + m0));
+            for (int j = 0; j < T; ++j) {
+                const int ks = j % kKStages, ku = j / kKStages;
+                ptx::mbar_wait(bar(K_EMPTY + ks), (ku & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(bar(K_FULL + ks), kTileQK);
+                ptx::tma_load_2d(smem_k + ks * kTileQK, &tmap_k, bar(K_FULL + ks), 0, int(k_row0 + int64_t(j) * kBN));
+                const int vs = j % kVStages, vu = j / kVStages;
+                ptx::mbar_wait(bar(V_EMPTY + vs), (vu & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(bar(V_FULL + vs), C::kVStage);
+                ptx::tma_load_2d(smem_v + vs * C::kVStage, &tmap_vt, bar(V_FULL + vs), j * kBN, int(vt_row0));
+                ptx::tma_load_2d(smem_v + vs * C::kVStage + HDV * 128, &tmap_vt, bar(V_FULL + vs), j * kBN + 64, int(vt_row0));
+            }
+        }
+    } else if (warp == 1) {
+        // ======================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc_qk = kInt8 ? ptx::make_idesc(2, 1, 1, kBM, kBN) : ptx::make_idesc(1, 0, 0, kBM, kBN);
+            const uint32_t idesc_pv = ptx::make_idesc(1, kBf16 ? 1 : 0, kBf16 ? 1 : 0, kBM, HDV);
+            auto issue_qk = [&](int j) {
+                const int ks = j % kKStages, ku = j / kKStages, b = j & 1, u = j >> 1;
+                ptx::mbar_wait(bar(K_FULL + ks), ku & 1);
+                ptx::mbar_wait(bar(S_EMPTY + b), (u & 1) ^ 1);            // the softmax warps have read S of tile j - 2
+                ptx::tc_fence_after();
+                const uint64_t a_desc = ptx::make_smem_desc_sw128(smem_q);
+                const uint64_t b_desc = ptx::make_smem_desc_sw128(smem_k + ks * kTileQK);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    ptx::umma_ss<kInt8>(tmem_base + s_col(b), a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc_qk, k != 0 ? 1u : 0u);
+                ptx::umma_commit(bar(K_EMPTY + ks));
+                ptx::umma_commit(bar(S_FULL + b));
+            };
+            auto issue_pv = [&](int j) {
+                const int vs = j % kVStages, vu = j / kVStages, b = j & 1, u = j >> 1;
+                ptx::mbar_wait(bar(V_FULL + vs), vu & 1);
+                ptx::mbar_wait(bar(P_FULL + b), u & 1);                   // P_j is in shared memory
+                ptx::mbar_wait(bar(O_EMPTY + b), (u & 1) ^ 1);            // O of tile j - 2 has been folded into the registers
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const uint64_t a_desc = ptx::make_smem_desc_sw128(smem_p + b * kPTile + s * (kPTile / 2));
+                    const uint64_t b_desc = ptx::make_smem_desc_sw128(smem_v + vs * C::kVStage + s * (HDV * 128));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_f16(tmem_base + o_col(b), a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc_pv, (s | k) != 0 ? 1u : 0u);
+                }
+                ptx::umma_commit(bar(V_EMPTY + vs));
+                ptx::umma_commit(bar(P_EMPTY + b));
+                ptx::umma_commit(bar(O_FULL + b));
+            };
+            ptx::mbar_wait(bar(Q_FULL), 0);
+            issue_qk(0);
+            for (int j = 0; j < T; ++j) {
+                if (j + 1 < T) issue_qk(j + 1);
+                issue_pv(j);
+            }
+        }
+    } else {
+        // ======================================================== softmax / output (256 threads)
+        const int sw = warp - 2;                   // 0..7
+        const int q = warp & 3;                    // TMEM lane quarter this warp may read
+        const int half = sw >> 2;                  // which 64 of the tile's 128 columns (and which half of the output columns)
+        const int r = q * 32 + lane;               // row of the tile = TMEM lane
+        const int ts = sw * 32 + lane;             // 0..255
+        const int m = m0 + r;
+        const bool m_ok = m < p.QN;
+        pdl_wait();
+        const float qs = m_ok ? p.q_scale[q_row0 + m] : 0.f;
+        const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16);
+        const int64_t mask_row = p.mask_kind != 0 ? int64_t(z) * p.mask_sz + int64_t(h) * p.mask_sh + int64_t(m_ok ? m : 0) * p.mask_sq : 0;
+        float m_i = -INFINITY;
+        float l_i = half == 0 ? 1.0f : 0.0f;       // :232 (l_i = 1): held by the first half, the halves add up at the end
+        float alpha_pend = 0.f;
+        float acc[HALF];
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+
+        auto fold_o = [&](int b, int u, float alpha) {       // acc = acc * alpha + O_b            (:297, :321)
+            ptx::mbar_wait(bar(O_FULL + b), u & 1);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < HALF / 32; ++c) {
+                uint32_t o[32];
+                ptx::tmem_ld32(t_lane + o_col(b) + uint32_t(half * HALF + c * 32), o);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha, __uint_as_float(o[i]));
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(bar(O_EMPTY + b));
+        };
+
+        for (int j = 0; j < T; ++j) {
+            const int b = j & 1, u = j >> 1;
+            const int n0 = j * kBN;
+            if (ts < 128) {
+                const int n = n0 + ts;
+                s_ks[b * 128 + ts] = n < p.KN ? p.k_scale[k_row0 + n] * p.log2_scale : 0.f;
+            }
+            asm volatile("bar.sync 5, 256;" ::: "memory");
+            ptx::mbar_wait(bar(S_FULL + b), u & 1);
+            ptx::tc_fence_after();
+            float t[64];
+            {
+                uint32_t s0[32], s1[32];
+                ptx::tmem_ld32(t_lane + s_col(b) + uint32_t(half * 64), s0);
+                ptx::tmem_ld32(t_lane + s_col(b) + uint32_t(half * 64 + 32), s1);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(bar(S_EMPTY + b));
+                const float4* ks4 = reinterpret_cast<const float4*>(s_ks + b * 128 + half * 64);
+#pragma unroll
+                for (int i4 = 0; i4 < 16; ++i4) {
+                    const float4 kv = ks4[i4];
+                    const float kk[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = i4 * 4 + e;
+                        const uint32_t rv = i < 32 ? s0[i] : s1[i - 32];
+                        float a;
+                        if constexpr (kInt8) a = __int_as_float(0x4B400000 + static_cast<int>(rv)) - 12582912.0f;   // exact: |acc| < 2^22
+                        else a = __uint_as_float(rv);
+                        t[i] = (a * qs) * kk[e];
+                    }
+                }
+            }
+            // masks
+            const int col0 = n0 + half * 64;
+            if (p.mask_kind == 1) {
+                const int8_t* mk = reinterpret_cast<const int8_t*>(p.mask) + mask_row;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    const int n = col0 + i;
+                    if (n < p.KN && mk[int64_t(n) * p.mask_sk] == 0) t[i] = -INFINITY;
+                }
+            } else if (p.mask_kind == 2) {
+                const float* mk = reinterpret_cast<const float*>(p.mask) + mask_row;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    const int n = col0 + i;
+                    if (n < p.KN) t[i] += mk[int64_t(n) * p.mask_sk];
+                }
+            }
+            if (col0 + 64 > p.KN || (p.causal && col0 + 63 > m)) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    const int n = col0 + i;
+                    if (n >= p.KN || (p.causal && n > m)) t[i] = -INFINITY;
+                }
+            }
+            float mx = t[0];
+#pragma unroll
+            for (int i = 1; i < 64; ++i) mx = fmaxf(mx, t[i]);
+            s_mx[(b * 2 + half) * 128 + r] = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            mx = fmaxf(mx, s_mx[(b * 2 + (half ^ 1)) * 128 + r]);
+            const float m_new = fmaxf(m_i, mx);
+            // :287-294 -- one formula for both of the reference's branches: exp2(-inf - finite) = 0, and a row that has seen
+            // nothing but masked keys keeps alpha = 1, p = 0
+            const float alpha = m_new == -INFINITY ? 1.0f : fast_exp2(m_i - m_new);
+            const float m_use = m_new == -INFINITY ? 0.0f : m_new;
+            float sum = 0.f;
+            ptx::mbar_wait(bar(P_EMPTY + b), (u & 1) ^ 1);               // the MMAs of tile j - 2 have read this P buffer
+            const uint32_t p_row = smem_p + b * kPTile + half * (kPTile / 2) + uint32_t(r) * 128u;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float p0 = fast_exp2(t[c * 8 + 2 * e] - m_use), p1 = fast_exp2(t[c * 8 + 2 * e + 1] - m_use);
+                    sum += p0 + p1;
+                    if constexpr (kBf16) {
+                        __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+                        w[e] = *reinterpret_cast<uint32_t*>(&hh);
+                    } else {
+                        __half2 hh = __floats2half2_rn(p0, p1);
+                        w[e] = *reinterpret_cast<uint32_t*>(&hh);
+                    }
+                }
+                ptx::st_shared_v4(p_row + (uint32_t(c ^ (r & 7)) << 4), w[0], w[1], w[2], w[3]);
+            }
+            ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive(bar(P_FULL + b));
+            l_i = fmaf(l_i, alpha, sum);
+            m_i = m_new;
+            if (j > 0) fold_o(b ^ 1, (j - 1) >> 1, alpha_pend);
+            alpha_pend = alpha;
+        }
+        fold_o((T - 1) & 1, (T - 1) >> 1, alpha_pend);
+        // total row sum = the two halves' partial sums (same running maximum)
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");        // the last tile's s_mx reads are done
+        s_mx[half * 128 + r] = l_i;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        const float l_tot = l_i + s_mx[(half ^ 1) * 128 + r];
+        if (m_ok) {
+            const float inv = 1.0f / l_tot;                                // :324
+            const int64_t orow = (q_row0 + m) * HDV + half * HALF;
+            if (p.out_dtype == SDNQ_F32) {
+                float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow);
+#pragma unroll
+                for (int i = 0; i < HALF / 4; ++i) dst[i] = make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv);
+            } else {
+                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + orow);
+#pragma unroll
+                for (int i = 0; i < HALF / 8; ++i) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float a0 = acc[8 * i + 2 * e] * inv, a1 = acc[8 * i + 2 * e + 1] * inv;
+                        if (p.out_dtype == SDNQ_BF16) {
+                            __nv_bfloat162 hh = __floats2bfloat162_rn(a0, a1);
+                            w[e] = *reinterpret_cast<uint32_t*>(&hh);
+                        } else {
+                            __half2 hh = __floats2half2_rn(a0, a1);
+                            w[e] = *reinterpret_cast<uint32_t*>(&hh);
+                        }
+                    }
+                    dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            if (p.lse != nullptr && half == 0) {                           // :326-332
+                float l = m_i + log2f(l_tot);
+                if (p.mask_kind != 0 && l == -INFINITY) l = 0.f;
+                const int64_t li = q_row0 + m;
+                if (p.out_dtype == SDNQ_F32) reinterpret_cast<float*>(p.lse)[li] = l;
+                else if (p.out_dtype == SDNQ_BF16) reinterpret_cast<__nv_bfloat16*>(p.lse)[li] = __float2bfloat16_rn(l);
+                else reinterpret_cast<__half*>(p.lse)[li] = __float2half_rn(l);
+            }
+        }
+    }
+    // ---- teardown
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// V [R, N, HD] (16-bit) -> V^T [R, HD, ldt] (ldt >= N, multiple of 8); columns N..ldt are never read (the tensor map ends at N)
+__global__ void __launch_bounds__(256) transpose_v_kernel(const uint16_t* __restrict__ v, uint16_t* __restrict__ vt, int N, int HD, int64_t ldt) {
+    __shared__ uint16_t tile[32][34];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t rr = blockIdx.z;
+    const int n0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int n = n0 + i, d = d0 + tx;
+        tile[i][tx] = (n < N && d < HD) ? v[(rr * N + n) * HD + d] : uint16_t(0);
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int d = d0 + i, n = n0 + tx;
+        if (d < HD && n < N) vt[(rr * HD + d) * ldt + n] = tile[tx][i];
+    }
+}
+
+// smooth-K (triton_atten.py:456-461): k [R, N, HD] -> k.to(f32) - mean over the N tokens, written as f32 or in a 16-bit type.
+// One CTA per (batch, head); the head (N * HD elements) is read twice, the second time from L2.
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) smooth_k_kernel(const TIn* __restrict__ k, TOut* __restrict__ out, int N, int HD) {
+    __shared__ float s_part[256];
+    __shared__ float s_mean[256];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t head = int64_t(blockIdx.x) * N * HD;
+    const int tid = threadIdx.x;
+    const int lanes = HD < 256 ? HD : 256;           // threads along the channel axis (HD <= 256)
+    const int groups = 256 / lanes;                  // row groups
+    const int d = tid % lanes, g = tid / lanes;
+    float sum = 0.f;
+    if (g < groups)
+        for (int n = g; n < N; n += groups) sum += ElemTraits<TIn>::load(k[head + int64_t(n) * HD + d]);
+    s_part[tid] = g < groups ? sum : 0.f;
+    __syncthreads();
+    if (tid < lanes) {
+        float tot = 0.f;
+        for (int gg = 0; gg < groups; ++gg) tot += s_part[gg * lanes + tid];
+        s_mean[tid] = tot / static_cast<float>(N);
+    }
+    __syncthreads();
+    if (g < groups) {
+        const float mean = s_mean[d];
+        for (int n = g; n < N; n += groups) {
+            const int64_t i = head + int64_t(n) * HD + d;
+            const float val = ElemTraits<TIn>::load(k[i]) - mean;
+            if constexpr (sizeof(TOut) == 4) out[i] = val;
+            else if constexpr (std::is_same<TOut, __nv_bfloat16>::value) out[i] = __float2bfloat16_rn(val);
+            else out[i] = __float2half_rn(val);
+        }
+    }
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+// [rows, cols] matrix of elem_bytes-wide elements, row pitch pitch_bytes, box {128 bytes, box_rows}, 128-byte swizzle
+int make_tmap_sw128(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t pitch_bytes, int elem_bytes, int box_rows) {
+    EncodeTiledFn enc = encode_fn();
+    SDNQ_REQUIRE(enc != nullptr, SDNQ_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch_bytes)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SDNQ_REQUIRE(r == CUDA_SUCCESS, SDNQ_ECUDA, "cuTensorMapEncodeTiled (attention) failed with CUresult %d (rows=%lld cols=%lld pitch=%lld)",
+                 static_cast<int>(r), (long long)rows, (long long)cols, (long long)pitch_bytes);
+    return SDNQ_OK;
+}
+
+template <bool kInt8, int HDV, bool kBf16>
+int launch_attn(const void* q, const void* k, const void* vt, int64_t ldt, int HD, const AttnParams& p, cudaStream_t st) {
+    using C = AttnCfg<HDV>;
+    auto kernel = attn_fwd_kernel<kInt8, HDV, kBf16>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes); });
+    SDNQ_REQUIRE(attr_err == cudaSuccess, SDNQ_ECUDA, "cudaFuncSetAttribute(max dynamic smem %d) failed: %s", C::kSmemBytes, cudaGetErrorString(attr_err));
+    CUtensorMap tq, tk, tv;
+    int rc = make_tmap_sw128(&tq, q, int64_t(p.Z) * p.H * p.QN, HD, HD, 1, kBM);
+    if (rc != SDNQ_OK) return rc;
+    rc = make_tmap_sw128(&tk, k, int64_t(p.Z) * p.KH * p.KN, HD, HD, 1, kBN);
+    if (rc != SDNQ_OK) return rc;
+    rc = make_tmap_sw128(&tv, vt, int64_t(p.Z) * p.VH * HDV, p.KN, ldt * 2, 2, HDV);
+    if (rc != SDNQ_OK) return rc;
+    const dim3 grid((p.QN + kBM - 1) / kBM, p.H, p.Z);
+    SDNQ_CUDA_OK(launch_pdl(kernel, grid, dim3(kThreads), size_t(C::kSmemBytes), st, tq, tk, tv, p));
+    return check_launch("attn_fwd_kernel");
+}
+
+int64_t vt_pitch(int64_t KN) { return (KN + 7) / 8 * 8; }
+
+}  // namespace
+}  // namespace sdnq
+
+using namespace sdnq;
+
+extern "C" size_t sdnq_b200_attention_workspace_bytes(int64_t Z, int64_t VH, int64_t KN, int64_t HDV) {
+    if (Z <= 0 || VH <= 0 || KN <= 0 || HDV <= 0) return 0;
+    return static_cast<size_t>(Z * VH * HDV * vt_pitch(KN) * 2);
+}
+
+extern "C" int sdnq_b200_smooth_k(const void* k, int k_dtype, int64_t heads, int64_t N, int64_t HD, void* out, int out_dtype, void* stream) {
+    SDNQ_REQUIRE(k && out, SDNQ_EINVAL, "NULL pointer");
+    SDNQ_REQUIRE(heads >= 0 && N > 0 && HD > 0 && HD <= 256 && N < (1LL << 31) && heads < (1LL << 31), SDNQ_EUNSUPPORTED, "smooth_k: heads=%lld N=%lld HD=%lld (HD <= 256)",
+                 (long long)heads, (long long)N, (long long)HD);
+    if (heads == 0) return SDNQ_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const dim3 grid(static_cast<unsigned>(heads)), block(256);
+#define SDNQ_SMOOTH(TI, TO)                                                                                                   \
+    do {                                                                                                                      \
+        SDNQ_CUDA_OK(launch_pdl(smooth_k_kernel<TI, TO>, grid, block, 0, st, reinterpret_cast<const TI*>(k), reinterpret_cast<TO*>(out), int(N), int(HD))); \
+        return check_launch("smooth_k_kernel");                                                                               \
+    } while (0)
+    if (k_dtype == SDNQ_BF16 && out_dtype == SDNQ_F32) SDNQ_SMOOTH(__nv_bfloat16, float);
+    if (k_dtype == SDNQ_BF16 && out_dtype == SDNQ_BF16) SDNQ_SMOOTH(__nv_bfloat16, __nv_bfloat16);
+    if (k_dtype == SDNQ_F16 && out_dtype == SDNQ_F32) SDNQ_SMOOTH(__half, float);
+    if (k_dtype == SDNQ_F16 && out_dtype == SDNQ_F16) SDNQ_SMOOTH(__half, __half);
+    if (k_dtype == SDNQ_F32 && out_dtype == SDNQ_F32) SDNQ_SMOOTH(float, float);
+    if (k_dtype == SDNQ_F32 && out_dtype == SDNQ_BF16) SDNQ_SMOOTH(float, __nv_bfloat16);
+    if (k_dtype == SDNQ_F32 && out_dtype == SDNQ_F16) SDNQ_SMOOTH(float, __half);
+#undef SDNQ_SMOOTH
+    return set_error(SDNQ_EUNSUPPORTED, "smooth_k: dtype pair %d -> %d", k_dtype, out_dtype);
+}
+
+extern "C" int sdnq_b200_attention(const void* q, const void* k, const void* v, int qk_dtype, int v_dtype, const float* q_scale,
+                                   const float* k_scale, const void* mask, int mask_dtype, const int64_t* mask_strides, void* out,
+                                   void* lse, int out_dtype, int64_t Z, int64_t H, int64_t KH, int64_t VH, int64_t QN, int64_t KN,
+                                   int64_t HD, int64_t HDV, float sm_scale, int is_causal, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+    SDNQ_REQUIRE(q && k && v && q_scale && k_scale && out, SDNQ_EINVAL, "NULL pointer");
+    SDNQ_REQUIRE(qk_dtype == SDNQ_I8 || qk_dtype == SDNQ_F8E4M3, SDNQ_EUNSUPPORTED, "attention: q / k codes must be int8 or float8_e4m3fn (got %d)", qk_dtype);
+    SDNQ_REQUIRE(v_dtype == SDNQ_BF16 || v_dtype == SDNQ_F16, SDNQ_EUNSUPPORTED, "attention: v must be bf16 or f16 (got %d)", v_dtype);
+    SDNQ_REQUIRE(out_dtype == SDNQ_BF16 || out_dtype == SDNQ_F16 || out_dtype == SDNQ_F32, SDNQ_EINVAL, "attention: bad out dtype %d", out_dtype);
+    SDNQ_REQUIRE(Z > 0 && H > 0 && KH > 0 && VH > 0 && QN > 0 && KN > 0, SDNQ_EINVAL, "attention: bad shape");
+    SDNQ_REQUIRE(HD % 16 == 0 && HD >= 16 && HD <= 128, SDNQ_EUNSUPPORTED, "attention: head dim of q / k must be a multiple of 16 up to 128 (got %lld)", (long long)HD);
+    SDNQ_REQUIRE(HDV == 64 || HDV == 128, SDNQ_EUNSUPPORTED, "attention: head dim of v must be 64 or 128 (got %lld; pad as get_attn_inputs does)", (long long)HDV);
+    SDNQ_REQUIRE(Z * H * QN < (1LL << 31) && Z * KH * KN < (1LL << 31) && Z * VH * HDV < (1LL << 31) && Z < 65536 && H < 65536 && Z * VH < 65536, SDNQ_EUNSUPPORTED,
+                 "attention: too many rows for 32-bit TMA coordinates");
+    SDNQ_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out) |
+                   reinterpret_cast<uintptr_t>(workspace)) & 15) == 0, SDNQ_EINVAL, "attention: q, k, v, out and workspace must be 16-byte aligned");
+    SDNQ_REQUIRE(workspace && workspace_bytes >= sdnq_b200_attention_workspace_bytes(Z, VH, KN, HDV), SDNQ_EINVAL, "attention: workspace too small");
+    int mask_kind = 0;
+    if (mask != nullptr) {
+        SDNQ_REQUIRE(mask_strides != nullptr, SDNQ_EINVAL, "attention: mask without strides");
+        SDNQ_REQUIRE(mask_dtype == SDNQ_I8 || mask_dtype == SDNQ_F32, SDNQ_EUNSUPPORTED, "attention: mask must be int8 (boolean) or f32 (additive), got %d", mask_dtype);
+        mask_kind = mask_dtype == SDNQ_I8 ? 1 : 2;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t ldt = vt_pitch(KN);
+    {
+        const dim3 grid(static_cast<unsigned>((KN + 31) / 32), static_cast<unsigned>((HDV + 31) / 32), static_cast<unsigned>(Z * VH));
+        SDNQ_CUDA_OK(launch_pdl(transpose_v_kernel, grid, dim3(256), 0, st, reinterpret_cast<const uint16_t*>(v), reinterpret_cast<uint16_t*>(workspace),
+                                int(KN), int(HDV), ldt));
+        int rc = check_launch("transpose_v_kernel");
+        if (rc != SDNQ_OK) return rc;
+    }
+    AttnParams p{};
+    p.q_scale = q_scale;
+    p.k_scale = k_scale;
+    p.out = out;
+    p.lse = lse;
+    p.mask = mask;
+    p.mask_kind = mask_kind;
+    if (mask_kind != 0) { p.mask_sz = mask_strides[0]; p.mask_sh = mask_strides[1]; p.mask_sq = mask_strides[2]; p.mask_sk = mask_strides[3]; }
+    p.Z = int(Z); p.H = int(H); p.KH = int(KH); p.VH = int(VH); p.QN = int(QN); p.KN = int(KN);
+    p.out_dtype = out_dtype;
+    p.causal = is_causal ? 1 : 0;
+    p.log2_scale = sm_scale * 1.4426950408889634f;
+    const bool i8 = qk_dtype == SDNQ_I8, bf = v_dtype == SDNQ_BF16;
+#define SDNQ_ATTN(HDV_)                                                                                                        \
+    (i8 ? (bf ? launch_attn<true, HDV_, true>(q, k, workspace, ldt, int(HD), p, st) : launch_attn<true, HDV_, false>(q, k, workspace, ldt, int(HD), p, st))   \
+        : (bf ? launch_attn<false, HDV_, true>(q, k, workspace, ldt, int(HD), p, st) : launch_attn<false, HDV_, false>(q, k, workspace, ldt, int(HD), p, st)))
+    return HDV == 128 ? SDNQ_ATTN(128) : SDNQ_ATTN(64);
+#undef SDNQ_ATTN
+}

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(PKG, "libsdnq_b200.so")
-SOURCES = ["capi.cu", "dequant.cu", "dequant_nd.cu", "dequant_svd.cu", "act_quant.cu", "act_quant_conv.cu", "gemv_w8a16.cu", "gemv_packed.cu", "gemm_w8a8.cu", "gemm_w4a16.cu", "svd_low.cu", "gemm_w8a8_packed.cu", "weight_quant.cu"]
+SOURCES = ["capi.cu", "dequant.cu", "dequant_nd.cu", "dequant_svd.cu", "act_quant.cu", "act_quant_conv.cu", "gemv_w8a16.cu", "gemv_packed.cu", "gemm_w8a8.cu", "gemm_w4a16.cu", "svd_low.cu", "gemm_w8a8_packed.cu", "weight_quant.cu", "attention.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

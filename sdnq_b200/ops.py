@@ -174,6 +174,64 @@ def embedding(weight, weights_dtype, scale, zero_point, V, D, group_size, indice
     return out.view(*indices.shape, D)
 
 
+def smooth_k(k: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """k [..., N, HD] -> k.to(f32) - mean over the N tokens (quantize_attn, kernels/triton_atten.py:456-461), in out_dtype."""
+    _require_cuda(k)
+    k = k.contiguous()
+    N, HD = k.shape[-2], k.shape[-1]
+    heads = k.numel() // (N * HD) if k.numel() else 0
+    out = torch.empty(k.shape, dtype=out_dtype, device=k.device)
+    with torch.cuda.device(k.device):
+        check(_lib.load().sdnq_b200_smooth_k(_ptr(k), dtype_code(k.dtype), heads, N, HD, _ptr(out), dtype_code(out_dtype), _stream(k)))
+    return out
+
+
+def attention_fwd(q_q: torch.Tensor, k_q: torch.Tensor, v: torch.Tensor, q_scale: torch.Tensor, k_scale: torch.Tensor, attn_mask=None,
+                  is_causal: bool = False, sm_scale: float = 1.0, out_dtype: torch.dtype = torch.bfloat16, return_lse: bool = False):
+    """K9: sdnq_atten_fwd (kernels/triton_atten.py:338-386) for 1-byte q / k codes with per-row scales and a 16-bit v.
+    q_q [Z,H,QN,HD], k_q [Z,KH,KN,HD] int8 / float8_e4m3fn; q_scale [Z,H,QN], k_scale [Z,KH,KN] f32; v [Z,VH,KN,HDV] bf16 / f16;
+    attn_mask: None, or a 4-D int8 / bool (0 = masked out) or float (additive) tensor broadcastable to [Z,H,QN,KN].
+    -> (out [Z,H,QN,HDV], lse [Z,H,QN] | None)."""
+    import ctypes
+    _require_cuda(q_q, k_q, v, q_scale, k_scale)
+    if q_q.dtype != k_q.dtype or q_q.dtype not in (torch.int8, torch.float8_e4m3fn):
+        raise _lib.SDNQKernelError(f"attention: q / k codes must both be int8 or float8_e4m3fn (got {q_q.dtype}, {k_q.dtype})")
+    q_q, k_q, v = q_q.contiguous(), k_q.contiguous(), v.contiguous()
+    q_scale = q_scale.to(torch.float32).contiguous()
+    k_scale = k_scale.to(torch.float32).contiguous()
+    Z, H, QN, HD = q_q.shape
+    _, KH, KN, _ = k_q.shape
+    _, VH, VN, HDV = v.shape
+    if VN != KN or k_q.shape[0] != Z or v.shape[0] != Z or k_q.shape[3] != HD:
+        raise _lib.SDNQKernelError(f"attention: inconsistent shapes q {tuple(q_q.shape)} k {tuple(k_q.shape)} v {tuple(v.shape)}")
+    dev = q_q.device
+    mask_ptr, mask_code, strides = None, 0, None
+    if attn_mask is not None:
+        mk = attn_mask
+        if mk.dtype == torch.bool:
+            mk = mk.to(torch.int8)
+        elif mk.dtype != torch.int8:
+            mk = mk.to(torch.float32)
+        while mk.ndim < 4:
+            mk = mk.unsqueeze(0)
+        if mk.shape[-1] == 1 and KN != 1:
+            mk = mk.expand(-1, -1, -1, KN)
+        attn_mask = mk = mk.contiguous()                                                   # kept alive until the launch below
+        st = [mk.stride(i) if mk.shape[i] != 1 else 0 for i in range(4)]                  # triton_atten.py:370-376
+        strides = (ctypes.c_int64 * 4)(*st)
+        mask_ptr, mask_code = mk.data_ptr(), dtype_code(mk.dtype) if mk.dtype != torch.int8 else SDNQ_I8
+    out = torch.empty((Z, H, QN, HDV), dtype=out_dtype, device=dev)
+    lse = torch.empty((Z, H, QN), dtype=out_dtype, device=dev) if return_lse else None
+    lib = _lib.load()
+    ws_bytes = int(lib.sdnq_b200_attention_workspace_bytes(Z, VH, KN, HDV))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.sdnq_b200_attention(_ptr(q_q), _ptr(k_q), _ptr(v), SDNQ_I8 if q_q.dtype == torch.int8 else SDNQ_F8E4M3, dtype_code(v.dtype),
+                                      _ptr(q_scale), _ptr(k_scale), mask_ptr, mask_code, strides, _ptr(out), _ptr(lse), dtype_code(out_dtype),
+                                      Z, H, KH, VH, QN, KN, HD, HDV, float(sm_scale), int(bool(is_causal)), _ptr(ws), ws_bytes, _stream(q_q)))
+    return out, lse
+
+
 class DequantBatch:
     """A planned batched dequantisation: the device-side table of sdnq_b200_dequant_batch_plan, the [N,K] outputs it writes (views of
     `slab`) and everything the embedded pointers refer to."""

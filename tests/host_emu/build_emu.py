@@ -14,7 +14,8 @@ CSRC = os.path.join(ROOT, "sdnq_b200", "csrc")
 KERNEL_SOURCES = ["act_quant.cu", "act_quant_conv.cu", "dequant.cu", "dequant_nd.cu", "gemv_w8a16.cu", "gemv_packed.cu", "svd_low.cu", "weight_quant.cu"]
 # entry points of the real library that live in translation units the emulator cannot run (tcgen05 / TMA GEMM)
 NOT_EMULATED = {"sdnq_b200_scaled_mm", "sdnq_b200_scaled_mm_packed", "sdnq_b200_mm", "sdnq_b200_linear_w8a8",
-                "sdnq_b200_linear_w8a8_fused", "sdnq_b200_linear_w8a8_workspace_bytes", "sdnq_b200_linear_w4a16", "sdnq_b200_scaled_mm_svd", "sdnq_b200_scaled_mm_grouped", "sdnq_b200_scaled_mm_ws", "sdnq_b200_scaled_mm_workspace_bytes"}
+                "sdnq_b200_linear_w8a8_fused", "sdnq_b200_linear_w8a8_workspace_bytes", "sdnq_b200_linear_w4a16", "sdnq_b200_scaled_mm_svd", "sdnq_b200_scaled_mm_grouped", "sdnq_b200_scaled_mm_ws", "sdnq_b200_scaled_mm_workspace_bytes",
+                "sdnq_b200_attention", "sdnq_b200_attention_workspace_bytes", "sdnq_b200_smooth_k"}
 
 
 def _digest():
