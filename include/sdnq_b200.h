@@ -423,6 +423,16 @@ SDNQ_API int sdnq_b200_attention(const void* q, const void* k, const void* v, in
  *   type when the Hadamard rotation follows in that type, :463-466); HD <= 256 */
 SDNQ_API int sdnq_b200_smooth_k(const void* k, int k_dtype, int64_t heads, int64_t N, int64_t HD, void* out, int out_dtype, void* stream);
 
+/* ---- attention operand pre-pass without a rotation (quantize_attn, kernels/triton_atten.py:456-471):
+ * sdnq_b200_attn_colmean:  k [heads, N, HD] -> mean [heads, HD] f32, the per-channel token means smooth-K subtracts (:456-461)
+ * sdnq_b200_attn_quant:    x [rows, HD] (SDNQ_BF16 / SDNQ_F16 / SDNQ_F32), optionally minus mean[row / rows_per_head] in f32,
+ *                          -> per-row scale[rows] = amax / 127 (SDNQ_I8) or / 448 (SDNQ_F8E4M3) and 1-byte codes xq [rows, HD]
+ *                          (quantize_int_mm / quantize_fp_mm over the head dim, quant_utils.py:264-299; same exact division as K2)
+ * HD a power of two, 16 .. 256 (get_attn_inputs pads to one, :514-519) */
+SDNQ_API int sdnq_b200_attn_colmean(const void* k, int k_dtype, int64_t heads, int64_t N, int64_t HD, float* mean, void* stream);
+SDNQ_API int sdnq_b200_attn_quant(const void* x, int x_dtype, int64_t rows, int64_t HD, const float* mean, int64_t rows_per_head,
+                         int mm_dtype, void* xq, float* scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

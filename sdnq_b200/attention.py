@@ -45,6 +45,12 @@ def quantize_attn(q, k, v, smooth_k: bool = True, hadamard_group_size: int = 0, 
         raise NotImplementedError("sdnq_b200 attention: quantised P.V (pv_matmul_dtype) is not built yet")
     mm = _mm_dtype(matmul_dtype)
     G = int(hadamard_group_size)
+    HD = q.shape[-1]
+    if G == 0 and HD == k.shape[-1] and HD in (16, 32, 64, 128, 256):
+        # no rotation: one row-quantiser launch per operand (the channel means of smooth-K are subtracted inside it)
+        q_q, q_scale = ops.attn_quant(q, mm)
+        k_q, k_scale = ops.attn_quant(k, mm, smooth=smooth_k)
+        return q_q, q_scale, k_q, k_scale, v, None
     if smooth_k:
         # :456-461 (k - mean in f32); :463-466: with a rotation the result is cast to the rotation's dtype (= q's) first
         k = ops.smooth_k(k, q.dtype if G else torch.float32)

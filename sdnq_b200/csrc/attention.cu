@@ -21,6 +21,7 @@
 // V is consumed K-major ([head_dim, keys]): a small transposing pre-pass writes V^T into the caller's workspace once per call.
 #include <mutex>
 
+#include "act_quant.cuh"
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -34,7 +35,7 @@ constexpr int kVStages = 2;
 constexpr int kTileQK = kBM * 128;       // one Q or K tile: 128 rows x 128 bytes (head dims < 128 are zero-filled by TMA)
 constexpr int kPTile = kBM * kBN * 2;    // P tile: two 64-key slabs of 128 rows x 128 bytes
 constexpr int kSoftmaxThreads = 256;
-constexpr int kThreads = 64 + kSoftmaxThreads;
+constexpr int kThreads = 128 + kSoftmaxThreads;      // warps 0-3: TMA producer, MMA issuer, two idle (register donors); warps 4-11: softmax
 
 struct AttnParams {
     const float* q_scale;
@@ -57,7 +58,7 @@ struct AttnCfg {
     static constexpr int kOffV = kOffK + kKStages * kTileQK;
     static constexpr int kOffP = kOffV + kVStages * kVStage;
     static constexpr int kOffTail = kOffP + 2 * kPTile;
-    static constexpr int kTailBytes = 2 * 128 * 4 + 2 * 2 * 128 * 4 + 32 * 8 + 16;
+    static constexpr int kTailBytes = 8 * 64 * 4 + 2 * 2 * 128 * 4 + 32 * 8 + 16;
     static constexpr int kSmemBytes = kOffTail + kTailBytes + 1024;       // + alignment slack
 };
 
@@ -83,9 +84,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = smem_dyn + (base - raw);
     const uint32_t smem_q = base, smem_k = base + C::kOffK, smem_v = base + C::kOffV, smem_p = base + C::kOffP;
-    float* s_ks = reinterpret_cast<float*>(smem + C::kOffTail);          // [2][128] k_scale * log2_scale of the tile's keys
-    float* s_mx = s_ks + 2 * 128;                                        // [2][2][128] half-row maxima (tile parity, half, row)
-    const uint32_t bar_base = base + C::kOffTail + 2 * 128 * 4 + 2 * 2 * 128 * 4;
+    float* s_ks = reinterpret_cast<float*>(smem + C::kOffTail);          // [8 warps][64] k_scale * log2_scale of the warp's 64 keys
+    float* s_mx = s_ks + 8 * 64;                                         // [2][2][128] half-row maxima (tile parity, half, row)
+    const uint32_t bar_base = base + C::kOffTail + 8 * 64 * 4 + 2 * 2 * 128 * 4;
     auto bar = [&](int i) { return bar_base + 8u * uint32_t(i); };
     const uint32_t tmem_slot = bar_base + 32 * 8;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + (tmem_slot - base));
@@ -109,11 +110,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int s = 0; s < kVStages; ++s) { ptx::mbar_init(bar(V_FULL + s), 1); ptx::mbar_init(bar(V_EMPTY + s), 1); }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(bar(S_FULL + s), 1);
-            ptx::mbar_init(bar(S_EMPTY + s), kSoftmaxThreads);
-            ptx::mbar_init(bar(P_FULL + s), kSoftmaxThreads);
+            ptx::mbar_init(bar(S_EMPTY + s), kSoftmaxThreads / 32);      // one elected arrival per softmax warp
+            ptx::mbar_init(bar(P_FULL + s), kSoftmaxThreads / 32);
             ptx::mbar_init(bar(P_EMPTY + s), 1);
             ptx::mbar_init(bar(O_FULL + s), 1);
-            ptx::mbar_init(bar(O_EMPTY + s), kSoftmaxThreads);
+            ptx::mbar_init(bar(O_EMPTY + s), kSoftmaxThreads / 32);
         }
         ptx::fence_barrier_init();
     }
@@ -130,7 +131,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     auto s_col = [&](int b) { return uint32_t(b) * 128u; };
     auto o_col = [&](int b) { return 256u + uint32_t(b) * 128u; };
 
-    if (warp == 0) {
+    // the four control warps need a few dozen registers, the softmax threads ~220 (64 scores + 64 output columns + staging)
+    // (setmaxnreg sits at the top of each role's own branch: ptxas bounds every instruction by the smallest count that can reach it)
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+      if (warp == 0) {
         // ======================================================== TMA producer
         if (lane == 0) {
             pdl_wait();
@@ -148,7 +153,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 ptx::tma_load_2d(smem_v + vs * C::kVStage + HDV * 128, &tmap_vt, bar(V_FULL + vs), j * kBN + 64, int(vt_row0));
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         // ======================================================== MMA issuer
         if (lane == 0) {
             const uint32_t idesc_qk = kInt8 ? ptx::make_idesc(2, 1, 1, kBM, kBN) : ptx::make_idesc(1, 0, 0, kBM, kBN);
@@ -191,13 +196,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 issue_pv(j);
             }
         }
+      }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         // ======================================================== softmax / output (256 threads)
-        const int sw = warp - 2;                   // 0..7
+        const int sw = warp - 4;                   // 0..7
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
         const int half = sw >> 2;                  // which 64 of the tile's 128 columns (and which half of the output columns)
         const int r = q * 32 + lane;               // row of the tile = TMEM lane
-        const int ts = sw * 32 + lane;             // 0..255
         const int m = m0 + r;
         const bool m_ok = m < p.QN;
         pdl_wait();
@@ -223,17 +229,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha, __uint_as_float(o[i]));
             }
             ptx::tc_fence_before();
-            ptx::mbar_arrive(bar(O_EMPTY + b));
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar(O_EMPTY + b));
         };
 
+        // the warp's 64 key scales per tile travel global -> registers (one tile ahead) -> the warp's own strip of shared memory: a load
+        // issued in the tile it is needed in would put an L2 round trip in front of every tile, a CTA-wide staging barrier would
+        // keep all eight warps in lock-step (they then fight for the MUFU pipe at the same moment)
+        float* my_ks = s_ks + sw * 64;
+        auto load_ks = [&](int j, int e) { const int n = j * kBN + half * 64 + e * 32 + lane; return n < p.KN ? p.k_scale[k_row0 + n] : 0.f; };
+        float ks_a = load_ks(0, 0), ks_b = load_ks(0, 1);
         for (int j = 0; j < T; ++j) {
             const int b = j & 1, u = j >> 1;
             const int n0 = j * kBN;
-            if (ts < 128) {
-                const int n = n0 + ts;
-                s_ks[b * 128 + ts] = n < p.KN ? p.k_scale[k_row0 + n] * p.log2_scale : 0.f;
-            }
-            asm volatile("bar.sync 5, 256;" ::: "memory");
+            my_ks[lane] = ks_a * p.log2_scale;
+            my_ks[32 + lane] = ks_b * p.log2_scale;
+            __syncwarp();
+            if (j + 1 < T) { ks_a = load_ks(j + 1, 0); ks_b = load_ks(j + 1, 1); }
             ptx::mbar_wait(bar(S_FULL + b), u & 1);
             ptx::tc_fence_after();
             float t[64];
@@ -243,8 +255,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 ptx::tmem_ld32(t_lane + s_col(b) + uint32_t(half * 64 + 32), s1);
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
-                ptx::mbar_arrive(bar(S_EMPTY + b));
-                const float4* ks4 = reinterpret_cast<const float4*>(s_ks + b * 128 + half * 64);
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(bar(S_EMPTY + b));
+                const float4* ks4 = reinterpret_cast<const float4*>(my_ks);
 #pragma unroll
                 for (int i4 = 0; i4 < 16; ++i4) {
                     const float4 kv = ks4[i4];
@@ -259,6 +272,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                         t[i] = (a * qs) * kk[e];
                     }
                 }
+                __syncwarp();                                             // my_ks is rewritten at the top of the next tile
             }
             // masks
             const int col0 = n0 + half * 64;
@@ -284,9 +298,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     if (n >= p.KN || (p.causal && n > m)) t[i] = -INFINITY;
                 }
             }
-            float mx = t[0];
+            float mx4[4] = {t[0], t[1], t[2], t[3]};
 #pragma unroll
-            for (int i = 1; i < 64; ++i) mx = fmaxf(mx, t[i]);
+            for (int i = 4; i < 64; i += 4) {
+                mx4[0] = fmaxf(mx4[0], t[i]); mx4[1] = fmaxf(mx4[1], t[i + 1]); mx4[2] = fmaxf(mx4[2], t[i + 2]); mx4[3] = fmaxf(mx4[3], t[i + 3]);
+            }
+            float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             s_mx[(b * 2 + half) * 128 + r] = mx;
             asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
             mx = fmaxf(mx, s_mx[(b * 2 + (half ^ 1)) * 128 + r]);
@@ -295,7 +312,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             // nothing but masked keys keeps alpha = 1, p = 0
             const float alpha = m_new == -INFINITY ? 1.0f : fast_exp2(m_i - m_new);
             const float m_use = m_new == -INFINITY ? 0.0f : m_new;
-            float sum = 0.f;
+            float sum4[4] = {0.f, 0.f, 0.f, 0.f};
             ptx::mbar_wait(bar(P_EMPTY + b), (u & 1) ^ 1);               // the MMAs of tile j - 2 have read this P buffer
             const uint32_t p_row = smem_p + b * kPTile + half * (kPTile / 2) + uint32_t(r) * 128u;
 #pragma unroll
@@ -304,7 +321,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float p0 = fast_exp2(t[c * 8 + 2 * e] - m_use), p1 = fast_exp2(t[c * 8 + 2 * e + 1] - m_use);
-                    sum += p0 + p1;
+                    sum4[e] += p0 + p1;
                     if constexpr (kBf16) {
                         __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
                         w[e] = *reinterpret_cast<uint32_t*>(&hh);
@@ -316,8 +333,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 ptx::st_shared_v4(p_row + (uint32_t(c ^ (r & 7)) << 4), w[0], w[1], w[2], w[3]);
             }
             ptx::fence_proxy_async_smem();
-            ptx::mbar_arrive(bar(P_FULL + b));
-            l_i = fmaf(l_i, alpha, sum);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar(P_FULL + b));
+            l_i = fmaf(l_i, alpha, (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
             m_i = m_new;
             if (j > 0) fold_o(b ^ 1, (j - 1) >> 1, alpha_pend);
             alpha_pend = alpha;
@@ -425,6 +443,84 @@ __global__ void __launch_bounds__(256) smooth_k_kernel(const TIn* __restrict__ k
             if constexpr (sizeof(TOut) == 4) out[i] = val;
             else if constexpr (std::is_same<TOut, __nv_bfloat16>::value) out[i] = __float2bfloat16_rn(val);
             else out[i] = __float2half_rn(val);
+        }
+    }
+}
+
+// Per-head channel means for smooth-K: k [heads, N, HD] -> mean [heads, HD] f32 (sum in f32, / N).  One CTA per head; a lane owns
+// 8 consecutive channels, the 256 / (HD / 8) row groups of the CTA are reduced through shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256) attn_colmean_kernel(const T* __restrict__ k, float* __restrict__ mean, int N, int HD) {
+    __shared__ float s_part[256 * 8];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lpr = HD / 8, groups = 256 / lpr;
+    const int sub = threadIdx.x % lpr, g = threadIdx.x / lpr;
+    const T* src = k + int64_t(blockIdx.x) * N * HD + sub * 8;
+    float sum[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum[i] = 0.f;
+    for (int n = g; n < N; n += groups) {
+        actq::Held<T> hv;
+        hv.load(src + int64_t(n) * HD);
+        float v[8];
+        hv.get(v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sum[i] += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_part[threadIdx.x * 8 + i] = sum[i];
+    __syncthreads();
+    if (int(threadIdx.x) < HD) {
+        const int c = threadIdx.x, csub = c / 8, ci = c % 8;
+        float tot = 0.f;
+        for (int gg = 0; gg < groups; ++gg) tot += s_part[(gg * lpr + csub) * 8 + ci];
+        mean[int64_t(blockIdx.x) * HD + c] = tot / static_cast<float>(N);
+    }
+}
+
+// Row quantiser for attention operands (quantize_attn without a rotation, triton_atten.py:456-471): rows of HD = 8 * LPR values,
+// LPR lanes per row (32 / LPR rows per warp and step); optional smooth-K: the head's channel means are subtracted in f32 first.
+//   scale = amax / 127 (int8) or / 448 (e4m3); codes = the same exact-division quantiser as the Linear pre-pass (actq::quantise8)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) attn_rowquant_kernel(const T* __restrict__ x, const float* __restrict__ mean, int rows_per_head,
+                                                            int64_t rows, int HD, uint8_t* __restrict__ xq, float* __restrict__ scale) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lpr = HD / 8, rpw = 32 / lpr;
+    const int lane = threadIdx.x & 31, sub = lane % lpr;
+    const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t warps_total = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t r0 = warp_global * rpw; r0 < rows; r0 += warps_total * rpw) {
+        const int64_t row = r0 + lane / lpr;
+        const bool ok = row < rows;
+        float v[8];
+        if (ok) {
+            actq::Held<T> hv;
+            hv.load(x + row * HD + sub * 8);
+            hv.get(v);
+            if (mean != nullptr) {
+                const float* mp = mean + (row / rows_per_head) * HD + sub * 8;
+                const float4 m0 = *reinterpret_cast<const float4*>(mp), m1 = *reinterpret_cast<const float4*>(mp + 4);
+                v[0] -= m0.x; v[1] -= m0.y; v[2] -= m0.z; v[3] -= m0.w;
+                v[4] -= m1.x; v[5] -= m1.y; v[6] -= m1.z; v[7] -= m1.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+        float amax = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[i]));
+        for (int o = 1; o < lpr; o <<= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        const float sc = __fdiv_rn(amax, MODE == SDNQ_F8E4M3 ? 448.f : 127.f);
+        const actq::RowDivider divider(sc);
+        int unused = 0;
+        const uint2 codes = divider.safe() ? actq::quantise8<MODE, true>(v, divider, 0.f, false, unused)
+                                           : actq::quantise8<MODE, false>(v, divider, 0.f, false, unused);
+        if (ok) {
+            *reinterpret_cast<uint2*>(xq + row * HD + sub * 8) = codes;
+            if (sub == 0) scale[row] = sc;
         }
     }
 }
@@ -566,4 +662,46 @@ extern "C" int sdnq_b200_attention(const void* q, const void* k, const void* v, 
         : (bf ? launch_attn<false, HDV_, true>(q, k, workspace, ldt, int(HD), p, st) : launch_attn<false, HDV_, false>(q, k, workspace, ldt, int(HD), p, st)))
     return HDV == 128 ? SDNQ_ATTN(128) : SDNQ_ATTN(64);
 #undef SDNQ_ATTN
+}
+
+extern "C" int sdnq_b200_attn_colmean(const void* k, int k_dtype, int64_t heads, int64_t N, int64_t HD, float* mean, void* stream) {
+    SDNQ_REQUIRE(k && mean, SDNQ_EINVAL, "NULL pointer");
+    SDNQ_REQUIRE(heads >= 0 && heads < (1LL << 31) && N > 0 && N < (1LL << 31), SDNQ_EINVAL, "attn_colmean: bad shape");
+    SDNQ_REQUIRE(HD == 16 || HD == 32 || HD == 64 || HD == 128 || HD == 256, SDNQ_EUNSUPPORTED, "attn_colmean: head dim must be 16 .. 256, a power of two (got %lld)", (long long)HD);
+    SDNQ_REQUIRE((reinterpret_cast<uintptr_t>(k) & 15) == 0 && (reinterpret_cast<uintptr_t>(mean) & 15) == 0, SDNQ_EINVAL, "attn_colmean: pointers must be 16-byte aligned");
+    if (heads == 0) return SDNQ_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const dim3 grid(static_cast<unsigned>(heads)), block(256);
+    if (k_dtype == SDNQ_BF16) SDNQ_CUDA_OK(launch_pdl(attn_colmean_kernel<__nv_bfloat16>, grid, block, 0, st, reinterpret_cast<const __nv_bfloat16*>(k), mean, int(N), int(HD)));
+    else if (k_dtype == SDNQ_F16) SDNQ_CUDA_OK(launch_pdl(attn_colmean_kernel<__half>, grid, block, 0, st, reinterpret_cast<const __half*>(k), mean, int(N), int(HD)));
+    else if (k_dtype == SDNQ_F32) SDNQ_CUDA_OK(launch_pdl(attn_colmean_kernel<float>, grid, block, 0, st, reinterpret_cast<const float*>(k), mean, int(N), int(HD)));
+    else return set_error(SDNQ_EUNSUPPORTED, "attn_colmean: dtype %d", k_dtype);
+    return check_launch("attn_colmean_kernel");
+}
+
+extern "C" int sdnq_b200_attn_quant(const void* x, int x_dtype, int64_t rows, int64_t HD, const float* mean, int64_t rows_per_head, int mm_dtype,
+                                    void* xq, float* scale, void* stream) {
+    SDNQ_REQUIRE(x && xq && scale, SDNQ_EINVAL, "NULL pointer");
+    SDNQ_REQUIRE(rows >= 0 && (mean == nullptr || rows_per_head > 0), SDNQ_EINVAL, "attn_quant: bad shape");
+    SDNQ_REQUIRE(HD == 16 || HD == 32 || HD == 64 || HD == 128 || HD == 256, SDNQ_EUNSUPPORTED, "attn_quant: head dim must be 16 .. 256, a power of two (got %lld)", (long long)HD);
+    SDNQ_REQUIRE(mm_dtype == SDNQ_I8 || mm_dtype == SDNQ_F8E4M3, SDNQ_EUNSUPPORTED, "attn_quant: int8 or float8_e4m3fn codes (got %d)", mm_dtype);
+    SDNQ_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(xq) | reinterpret_cast<uintptr_t>(mean)) & 15) == 0, SDNQ_EINVAL, "attn_quant: pointers must be 16-byte aligned");
+    if (rows == 0) return SDNQ_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t rpw = 32 / (HD / 8), warps = (rows + rpw - 1) / rpw;
+    const int64_t want = (warps + 7) / 8, cap = int64_t(num_sms()) * 16;
+    const dim3 grid(static_cast<unsigned>(want < cap ? want : cap)), block(256);
+    const int rph = int(mean ? rows_per_head : 1);
+#define SDNQ_AQ(T, MODE)                                                                                                          \
+    do {                                                                                                                          \
+        SDNQ_CUDA_OK(launch_pdl(attn_rowquant_kernel<T, MODE>, grid, block, 0, st, reinterpret_cast<const T*>(x), mean, rph, rows, int(HD), \
+                                reinterpret_cast<uint8_t*>(xq), scale));                                                          \
+        return check_launch("attn_rowquant_kernel");                                                                              \
+    } while (0)
+    const bool i8 = mm_dtype == SDNQ_I8;
+    if (x_dtype == SDNQ_BF16) { if (i8) SDNQ_AQ(__nv_bfloat16, SDNQ_I8); else SDNQ_AQ(__nv_bfloat16, SDNQ_F8E4M3); }
+    if (x_dtype == SDNQ_F16) { if (i8) SDNQ_AQ(__half, SDNQ_I8); else SDNQ_AQ(__half, SDNQ_F8E4M3); }
+    if (x_dtype == SDNQ_F32) { if (i8) SDNQ_AQ(float, SDNQ_I8); else SDNQ_AQ(float, SDNQ_F8E4M3); }
+#undef SDNQ_AQ
+    return set_error(SDNQ_EUNSUPPORTED, "attn_quant: dtype %d", x_dtype);
 }

@@ -186,6 +186,26 @@ def smooth_k(k: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.T
     return out
 
 
+def attn_quant(x: torch.Tensor, matmul_dtype: str, smooth: bool = False):
+    """Attention operand pre-pass without a rotation: x [..., N, HD] -> (codes [..., N, HD], scale [..., N]); `smooth`: subtract the
+    per-(batch, head, channel) token means in f32 first (smooth-K).  quantize_attn, kernels/triton_atten.py:456-471."""
+    _require_cuda(x)
+    x = x.contiguous()
+    N, HD = x.shape[-2], x.shape[-1]
+    rows = x.numel() // HD
+    code = mm_code(matmul_dtype)
+    lib = _lib.load()
+    xq = torch.empty(x.shape, dtype=_MM_TORCH[code], device=x.device)
+    scale = torch.empty(x.shape[:-1], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        mean = None
+        if smooth:
+            mean = torch.empty((rows // N, HD), dtype=torch.float32, device=x.device)
+            check(lib.sdnq_b200_attn_colmean(_ptr(x), dtype_code(x.dtype), rows // N, N, HD, _ptr(mean), _stream(x)))
+        check(lib.sdnq_b200_attn_quant(_ptr(x), dtype_code(x.dtype), rows, HD, _ptr(mean), N, code, _ptr(xq), _ptr(scale), _stream(x)))
+    return xq, scale
+
+
 def attention_fwd(q_q: torch.Tensor, k_q: torch.Tensor, v: torch.Tensor, q_scale: torch.Tensor, k_scale: torch.Tensor, attn_mask=None,
                   is_causal: bool = False, sm_scale: float = 1.0, out_dtype: torch.dtype = torch.bfloat16, return_lse: bool = False):
     """K9: sdnq_atten_fwd (kernels/triton_atten.py:338-386) for 1-byte q / k codes with per-row scales and a 16-bit v.

@@ -15,7 +15,7 @@ KERNEL_SOURCES = ["act_quant.cu", "act_quant_conv.cu", "dequant.cu", "dequant_nd
 # entry points of the real library that live in translation units the emulator cannot run (tcgen05 / TMA GEMM)
 NOT_EMULATED = {"sdnq_b200_scaled_mm", "sdnq_b200_scaled_mm_packed", "sdnq_b200_mm", "sdnq_b200_linear_w8a8",
                 "sdnq_b200_linear_w8a8_fused", "sdnq_b200_linear_w8a8_workspace_bytes", "sdnq_b200_linear_w4a16", "sdnq_b200_scaled_mm_svd", "sdnq_b200_scaled_mm_grouped", "sdnq_b200_scaled_mm_ws", "sdnq_b200_scaled_mm_workspace_bytes",
-                "sdnq_b200_attention", "sdnq_b200_attention_workspace_bytes", "sdnq_b200_smooth_k"}
+                "sdnq_b200_attention", "sdnq_b200_attention_workspace_bytes", "sdnq_b200_smooth_k", "sdnq_b200_attn_colmean", "sdnq_b200_attn_quant"}
 
 
 def _digest():

@@ -162,11 +162,17 @@ CHILD = textwrap.dedent('''
                       SDNQ_TRITON_ATTEN_NUM_STAGES_LIST="2")
     sdnq = load_reference(SDNQ_DEVICE="cuda", SDNQ_USE_TORCH_COMPILE="0")
     from sdnq.kernels.triton_atten import sdnq_triton_atten
+    import triton
+    # the reference builds its TMA descriptors on the device (tl.make_tensor_descriptor), which needs a scratch allocator from the
+    # host program (Inductor installs one for compiled graphs; an eager caller has to) -- harness set-up, not a change to the reference
+    triton.set_allocator(lambda size, align, stream: torch.empty(size, dtype=torch.int8, device="cuda"))
     import numpy as np
     from oracle import sdnq_oracle as O
     import sdnq_b200
     out = {}
-    for name, (Z, H, KH, QN, KN, HD, causal, mm) in {"flux_like": (1, 4, 4, 640, 640, 128, False, "int8"), "sdxl_cross": (2, 5, 5, 512, 77, 64, False, "int8"),
+    # (KN = 77, SD-XL's real cross-attention length, is not in this list: the reference's own kernel dies there with "misaligned
+    #  address" -- its key-scale descriptor has a 4 * 77-byte head pitch -- and takes the CUDA context with it)
+    for name, (Z, H, KH, QN, KN, HD, causal, mm) in {"flux_like": (1, 4, 4, 640, 640, 128, False, "int8"), "sdxl_cross": (2, 5, 5, 512, 80, 64, False, "int8"),
                                                    "causal": (1, 2, 2, 384, 384, 64, True, "int8"), "fp8": (1, 2, 2, 256, 300, 128, False, "float8_e4m3fn")}.items():
         g = torch.Generator().manual_seed(QN)
         q = torch.randn(Z, H, QN, HD, generator=g).bfloat16().cuda()
