@@ -756,6 +756,151 @@ def dequant_path_roofline(dq_layers, acts, graph_time, hbm_peak, src_note, peaks
             "dequant_kernel": k3}
 
 
+# ------------------------------------------------------------------------------------------------ quantized attention
+ATTENTION = dict(name="flux_attention_int8", calls=57, heads=24, tokens=4608, head_dim=128, batch_per_gpu=4,
+                 describe="FLUX.1-dev joint attention with SDNQ quantized Q.K^T (int8 codes, smooth-K, 16-bit P.V = sdnq_triton_atten defaults): the "
+                          "57 attention calls (19 double + 38 single blocks) of one denoise step, 4 images per GPU, 24 heads x 4608 tokens x 128")
+
+
+def attention_reference_child():
+    """`--impl attention_reference`: the unmodified reference's Triton attention (oracle/_ref, full autotune space) on the same shape."""
+    import torch
+    sys.path.insert(0, ROOT)
+    a = ATTENTION
+    from oracle.ref_loader import load_reference
+    load_reference(SDNQ_DEVICE="cuda", SDNQ_USE_TORCH_COMPILE="0")
+    import triton
+    from sdnq.kernels.triton_atten import sdnq_triton_atten
+    triton.set_allocator(lambda size, align, stream: torch.empty(size, dtype=torch.int8, device="cuda"))       # device-side TMA descriptors
+    shape = (a["batch_per_gpu"], a["heads"], a["tokens"], a["head_dim"])
+    q, k, v = (torch.randn(shape, device="cuda").bfloat16() for _ in range(3))
+    with torch.no_grad():
+        for _ in range(2):
+            sdnq_triton_atten(q, k, v)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            sdnq_triton_atten(q, k, v)
+        e1.record()
+        e1.synchronize()
+    print("ATTN_REF " + json.dumps({"ms_per_call": e0.elapsed_time(e1) / 5}), flush=True)
+
+
+def run_attention_workload(args, world, rank, device, peaks):
+    """One denoise step's worth of quantized attention through the public entry point (`sdnq_attention`: pre-pass + K9), timed like
+    the Linear workloads: CUDA graph of the step, CUDA events, max over ranks; e2e adds the pinned H2D of one call's q / k / v and
+    the D2H of the last output.  FLOPs = 4 * batch * heads * tokens^2 * head_dim per call (Q.K^T + P.V)."""
+    import torch
+    import torch.distributed as dist
+
+    import sdnq_b200
+    from sdnq_b200 import _lib
+    a = ATTENTION
+    shape = (a["batch_per_gpu"], a["heads"], a["tokens"], a["head_dim"])
+    flops_step = a["calls"] * 4.0 * shape[0] * shape[1] * shape[2] * shape[2] * shape[3]
+    torch.manual_seed(200 + rank)
+    host = [torch.randn(shape, dtype=torch.bfloat16).pin_memory() for _ in range(3)]
+    # two input sets (2 x 340 MB > 126 MB L2), alternated call by call
+    sets = [[h.to(device, non_blocking=True) for h in host], [torch.randn(shape, device=device).bfloat16() for _ in range(3)]]
+    holder = {}
+
+    def step():
+        for i in range(a["calls"]):
+            q, k, v = sets[i & 1]
+            holder["y"] = sdnq_b200.sdnq_attention(q, k, v)
+        return holder["y"]
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    _lib.launch_count(reset=True)
+    step()
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        y_graph = step()
+    steps, warmup = max(3, min(args.steps, 10)), 3
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        e1.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n
+
+    for _ in range(warmup):
+        graph.replay()
+    sampler = ClockSampler(device.index) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    t0 = time.time()
+    ms = timed(graph.replay, steps)
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    out_host = torch.empty(shape, dtype=torch.bfloat16).pin_memory()
+
+    def e2e_step():
+        for h, d in zip(host, sets[0]):
+            d.copy_(h, non_blocking=True)
+        graph.replay()
+        out_host.copy_(y_graph, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e2e_step()
+    e2e_ms = timed(e2e_step, steps)
+    if rank != 0:
+        return None
+    tf = flops_step * world / ms / 1e9
+    res = {"metric": "quantized attention TFLOP/s (4*B*H*N^2*D per call)", "value": tf, "unit": "TFLOP/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8 Q.K^T / bf16 P.V", "data": "synthetic",
+           "config": {"workload": a["name"], "describe": a["describe"], "calls_per_step": a["calls"], "batch_per_gpu": a["batch_per_gpu"],
+                      "global_batch": a["batch_per_gpu"] * world, "parallelism": f"dp{world}",
+                      "l2": "two q/k/v sets of 340 MB alternate call by call (>> 126 MB L2)"},
+           "e2e": {"value": flops_step * world / e2e_ms / 1e9, "unit": "TFLOP/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 3 * host[0].numel() * 2,
+                   "d2h_bytes_per_step": out_host.numel() * 2, "copies": "one call's q / k / v in, the last call's output out (the other calls' operands come "
+                   "from on-device Linears in a real step)"},
+           "gpu_launches": launches_per_step * steps, "launches_per_step": launches_per_step, "clocks": clocks}
+    int8_peak, bf16_peak = peaks.get("int8_tflops"), None
+    try:
+        bf16_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops"))
+    except Exception:      # noqa: BLE001
+        pass
+    if int8_peak and bf16_peak:
+        peak = 2.0 / (1.0 / int8_peak + 1.0 / bf16_peak)
+        res["roofline"] = {"bound": "tensor", "kernel": "attn_fwd_kernel (K9: tcgen05 kind::i8 Q.K^T + kind::f16 P.V, softmax on CUDA cores / MUFU)",
+                           "achieved": flops_step / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": flops_step / ms / 1e9 / peak, "traffic": None,
+                           "peak_note": f"harmonic mean of the measured int8 ({int8_peak:.0f}) and bf16 ({bf16_peak:.0f}) dense peaks: half the FLOPs run at each; "
+                                        "the kernel's own bound is the softmax (16 MUFU.EX2 per clock and SM = 1024 clocks per 128x128 tile, see DESIGN.md K9); "
+                                        "achieved counts the whole call (pre-pass + V transpose + kernel)"}
+    if world == 1 and not args.no_gpu_reference:
+        ref = {"how": "unmodified reference (oracle/_ref) sdnq_triton_atten on one call's tensors, eager, full autotune space, 5 timed calls after 2 warm-ups; "
+                      "the harness installs a triton.set_allocator scratch allocator"}
+        try:
+            env = dict(os.environ, SDNQ_DEVICE="cuda")
+            pr = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "attention_reference"], capture_output=True, text=True, timeout=300, env=env)
+            ln = next((x for x in pr.stdout.splitlines() if x.startswith("ATTN_REF ")), None)
+            if ln is None:
+                ref["unavailable"] = (pr.stderr.strip().splitlines() or ["no output"])[-1][:300]
+            else:
+                ms_call = json.loads(ln[9:])["ms_per_call"]
+                ref.update(ms_per_call=ms_call, ms_per_step=ms_call * a["calls"], tflops=flops_step / (ms_call * a["calls"]) / 1e9, speedup=ms_call * a["calls"] / ms)
+        except Exception as ex:      # noqa: BLE001
+            ref["unavailable"] = f"{type(ex).__name__}: {ex}"[:300]
+        res["gpu_reference"] = ref
+    return res
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -782,6 +927,12 @@ def run_gpu_arm(args):
         r = run_workload(name, args, world, rank, device, peaks)
         if r is not None:
             sub[name] = r
+    attn = None
+    if nested and not args.no_attention:
+        try:
+            attn = run_attention_workload(args, world, rank, device, peaks)
+        except Exception as ex:      # noqa: BLE001  (a nested line must not take the headline down)
+            attn = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]} if rank == 0 else None
     if rank == 0:
         line["peaks"] = peaks
         if sub:
@@ -794,6 +945,8 @@ def run_gpu_arm(args):
                 _, _, sub[name]["cpu_baseline"] = cpu_reference_run(name, steps=1000, warmup=1, budget_s=6.0)
         if world == 1 and not args.no_gpu_reference:
             line["gpu_reference"] = gpu_reference([headline] + list(sub))
+        if attn is not None:
+            line.setdefault("workloads", {})[ATTENTION["name"]] = attn
         line["bench_seconds"] = round(time.time() - t_start, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -806,16 +959,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=None, help=f"one of {sorted(WORKLOADS)}; default: {HEADLINE} with {list(NESTED)} nested under 'workloads'")
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "gpu_reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "gpu_reference", "attention_reference"])
     ap.add_argument("--siblings", default="pool", choices=["off", "block", "pool"],
                     help="grouped launches for sibling projections.  pool (what sdnq_post_load_quant registers): per attention block, and the "
                          "cross-attention to_k / to_v pairs of 4 blocks that read the same encoder states in one launch; block: per block only")
     ap.add_argument("--no-nested", action="store_true")
+    ap.add_argument("--no-attention", action="store_true", help="skip the nested quantized-attention line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
     args = ap.parse_args()
     if args.impl == "gpu_reference":
         return run_gpu_reference_arm(args)
+    if args.impl == "attention_reference":
+        return attention_reference_child()
     if args.workload is not None and args.workload not in WORKLOADS:
         ap.error(f"unknown workload {args.workload!r}")
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

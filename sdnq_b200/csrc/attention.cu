@@ -143,11 +143,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             ptx::tma_load_2d(smem_q, &tmap_q, bar(Q_FULL), 0, int(q_row0 + m0));
             for (int j = 0; j < T; ++j) {
                 const int ks = j % kKStages, ku = j / kKStages;
-                ptx::mbar_wait(bar(K_EMPTY + ks), (ku & 1) ^ 1);
+                ptx::mbar_wait_relaxed(bar(K_EMPTY + ks), (ku & 1) ^ 1);
                 ptx::mbar_arrive_expect_tx(bar(K_FULL + ks), kTileQK);
                 ptx::tma_load_2d(smem_k + ks * kTileQK, &tmap_k, bar(K_FULL + ks), 0, int(k_row0 + int64_t(j) * kBN));
                 const int vs = j % kVStages, vu = j / kVStages;
-                ptx::mbar_wait(bar(V_EMPTY + vs), (vu & 1) ^ 1);
+                ptx::mbar_wait_relaxed(bar(V_EMPTY + vs), (vu & 1) ^ 1);
                 ptx::mbar_arrive_expect_tx(bar(V_FULL + vs), C::kVStage);
                 ptx::tma_load_2d(smem_v + vs * C::kVStage, &tmap_vt, bar(V_FULL + vs), j * kBN, int(vt_row0));
                 ptx::tma_load_2d(smem_v + vs * C::kVStage + HDV * 128, &tmap_vt, bar(V_FULL + vs), j * kBN + 64, int(vt_row0));
@@ -160,8 +160,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             const uint32_t idesc_pv = ptx::make_idesc(1, kBf16 ? 1 : 0, kBf16 ? 1 : 0, kBM, HDV);
             auto issue_qk = [&](int j) {
                 const int ks = j % kKStages, ku = j / kKStages, b = j & 1, u = j >> 1;
-                ptx::mbar_wait(bar(K_FULL + ks), ku & 1);
-                ptx::mbar_wait(bar(S_EMPTY + b), (u & 1) ^ 1);            // the softmax warps have read S of tile j - 2
+                ptx::mbar_wait_relaxed(bar(K_FULL + ks), ku & 1);
+                ptx::mbar_wait_relaxed(bar(S_EMPTY + b), (u & 1) ^ 1);            // the softmax warps have read S of tile j - 2
                 ptx::tc_fence_after();
                 const uint64_t a_desc = ptx::make_smem_desc_sw128(smem_q);
                 const uint64_t b_desc = ptx::make_smem_desc_sw128(smem_k + ks * kTileQK);
@@ -173,9 +173,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             };
             auto issue_pv = [&](int j) {
                 const int vs = j % kVStages, vu = j / kVStages, b = j & 1, u = j >> 1;
-                ptx::mbar_wait(bar(V_FULL + vs), vu & 1);
-                ptx::mbar_wait(bar(P_FULL + b), u & 1);                   // P_j is in shared memory
-                ptx::mbar_wait(bar(O_EMPTY + b), (u & 1) ^ 1);            // O of tile j - 2 has been folded into the registers
+                ptx::mbar_wait_relaxed(bar(V_FULL + vs), vu & 1);
+                ptx::mbar_wait_relaxed(bar(P_FULL + b), u & 1);                   // P_j is in shared memory
+                ptx::mbar_wait_relaxed(bar(O_EMPTY + b), (u & 1) ^ 1);            // O of tile j - 2 has been folded into the registers
                 ptx::tc_fence_after();
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
@@ -189,7 +189,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 ptx::umma_commit(bar(P_EMPTY + b));
                 ptx::umma_commit(bar(O_FULL + b));
             };
-            ptx::mbar_wait(bar(Q_FULL), 0);
+            ptx::mbar_wait_relaxed(bar(Q_FULL), 0);
             issue_qk(0);
             for (int j = 0; j < T; ++j) {
                 if (j + 1 < T) issue_qk(j + 1);
@@ -208,6 +208,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const bool m_ok = m < p.QN;
         pdl_wait();
         const float qs = m_ok ? p.q_scale[q_row0 + m] : 0.f;
+        // scores are kept as u = acc * k_scale' and the row's factor is applied inside the exponent: p = exp2(fma(u, rs, -m)).
+        // rs = q_scale (>= 0; an all-zero row has u == 0 everywhere, so 1 serves and keeps 0 * -inf out); additive masks live in
+        // the scaled domain, so with one of those the factor is applied first and rs = 1
+        const float rs = p.mask_kind == 2 ? 1.0f : (qs > 0.f ? qs : 1.0f);
+        const float pre = p.mask_kind == 2 ? qs : 1.0f;
         const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16);
         const int64_t mask_row = p.mask_kind != 0 ? int64_t(z) * p.mask_sz + int64_t(h) * p.mask_sh + int64_t(m_ok ? m : 0) * p.mask_sq : 0;
         float m_i = -INFINITY;
@@ -269,7 +274,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                         float a;
                         if constexpr (kInt8) a = __int_as_float(0x4B400000 + static_cast<int>(rv)) - 12582912.0f;   // exact: |acc| < 2^22
                         else a = __uint_as_float(rv);
-                        t[i] = (a * qs) * kk[e];
+                        t[i] = a * kk[e];
                     }
                 }
                 __syncwarp();                                             // my_ks is rewritten at the top of the next tile
@@ -288,6 +293,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 64; ++i) {
                     const int n = col0 + i;
+                    t[i] *= pre;
                     if (n < p.KN) t[i] += mk[int64_t(n) * p.mask_sk];
                 }
             }
@@ -307,7 +313,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             s_mx[(b * 2 + half) * 128 + r] = mx;
             asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
             mx = fmaxf(mx, s_mx[(b * 2 + (half ^ 1)) * 128 + r]);
-            const float m_new = fmaxf(m_i, mx);
+            const float m_new = fmaxf(m_i, mx * rs);
             // :287-294 -- one formula for both of the reference's branches: exp2(-inf - finite) = 0, and a row that has seen
             // nothing but masked keys keeps alpha = 1, p = 0
             const float alpha = m_new == -INFINITY ? 1.0f : fast_exp2(m_i - m_new);
@@ -320,7 +326,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 uint32_t w[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float p0 = fast_exp2(t[c * 8 + 2 * e] - m_use), p1 = fast_exp2(t[c * 8 + 2 * e + 1] - m_use);
+                    const float p0 = fast_exp2(fmaf(t[c * 8 + 2 * e], rs, -m_use)), p1 = fast_exp2(fmaf(t[c * 8 + 2 * e + 1], rs, -m_use));
                     sum4[e] += p0 + p1;
                     if constexpr (kBf16) {
                         __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);

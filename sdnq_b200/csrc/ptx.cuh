@@ -37,6 +37,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// for a control warp that shares its scheduler with compute warps: sleep between polls instead of spending issue slots on them
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) asm volatile("nanosleep.u32 64;");
+}
 
 // ------------------------------------------------------------------ clusters (CTA pairs for cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
