@@ -405,7 +405,10 @@ SDNQ_API int64_t sdnq_b200_launch_count(int reset);
  *      (:338-386) on the operands quantize_attn (:443-487) produces.
  *   q [Z,H,QN,HD], k [Z,KH,KN,HD]   contiguous 1-byte codes, qk_dtype SDNQ_I8 or SDNQ_F8E4M3; HD % 16 == 0, HD <= 128
  *   q_scale [Z,H,QN], k_scale [Z,KH,KN]   f32 per-row scales (quantize_int_mm / quantize_fp_mm over the head dim)
- *   v [Z,VH,KN,HDV]                 contiguous SDNQ_BF16 / SDNQ_F16 (the unquantised P.V of pv_matmul_dtype = None); HDV 64 or 128
+ *   v [Z,VH,KN,HDV]                 contiguous SDNQ_BF16 / SDNQ_F16 values with v_scale = NULL (the unquantised P.V of
+ *                                   pv_matmul_dtype = None, :319-321), or SDNQ_I8 / SDNQ_F8E4M3 codes with per-key scales
+ *                                   v_scale [Z,VH,KN] (quantised P.V, :298-318: P is scaled by v_scale, quantised per row and key
+ *                                   tile, and its row scale applied to the product); HDV 64 or 128
  *   mask                            NULL, or SDNQ_I8 (boolean: 0 = masked out) / SDNQ_F32 (additive) with 4 element strides over
  *                                   (z, h, q, k), 0 on broadcast axes (:370-376)
  *   out [Z,H,QN,HDV], lse [Z,H,QN] (optional: m + log2(l), :326-332) of out_dtype SDNQ_BF16 / SDNQ_F16 / SDNQ_F32
@@ -413,7 +416,7 @@ SDNQ_API int64_t sdnq_b200_launch_count(int reset);
  *   workspace   sdnq_b200_attention_workspace_bytes(Z, VH, KN, HDV) bytes, 16-byte aligned: V^T written by a pre-pass kernel */
 SDNQ_API size_t sdnq_b200_attention_workspace_bytes(int64_t Z, int64_t VH, int64_t KN, int64_t HDV);
 SDNQ_API int sdnq_b200_attention(const void* q, const void* k, const void* v, int qk_dtype, int v_dtype, const float* q_scale,
-                        const float* k_scale, const void* mask, int mask_dtype, const int64_t* mask_strides, void* out,
+                        const float* k_scale, const float* v_scale, const void* mask, int mask_dtype, const int64_t* mask_strides, void* out,
                         void* lse, int out_dtype, int64_t Z, int64_t H, int64_t KH, int64_t VH, int64_t QN, int64_t KN,
                         int64_t HD, int64_t HDV, float sm_scale, int is_causal, void* workspace, size_t workspace_bytes,
                         void* stream);

@@ -663,11 +663,24 @@ def quantize_attn(q, k, smooth_k=True, hadamard_group=0, matmul_dtype="int8", dt
     return q_q.astype(F32), q_s.reshape(q.shape[:-1]).astype(F32), k_q.astype(F32), k_s.reshape(k.shape[:-1]).astype(F32)
 
 
+def quantize_attn_v(v, hadamard_group=0, pv_matmul_dtype="int8", dtype="bfloat16"):
+    """kernels/triton_atten.py:478-483: v [Z,VH,KN,HDV] rotated like q / k (in the rotation's dtype) when they are, then quantised per
+    key over the head dim -> (v_codes as f32, v_scale [Z,VH,KN])."""
+    v = np.asarray(v, dtype=F32)
+    if hadamard_group:
+        v = rotate_hadamard(_cast16(v, dtype), hadamard_group, dtype)
+    quant = quantize_int_mm if pv_matmul_dtype == "int8" else quantize_fp_mm
+    v_q, v_s = quant(v, axis=-1)
+    return v_q.astype(F32), v_s.reshape(v.shape[:-1]).astype(F32)
+
+
 def attn_fwd(q_q, k_q, v, q_scale, k_scale, mask=None, is_causal=False, sm_scale=1.0, block_m=128, block_n=128, dtype="bfloat16",
-             out_dtype="bfloat16", return_lse=False):
-    """sdnq_attn_kernel (kernels/triton_atten.py:143-335) with qk_is_quantized=1, pv_is_quantized=0, use_fp16_accum=0: a block-wise
-    restatement (the result depends on BLOCK_SIZE_N only through rounding).  q_q [Z,H,QN,HD], k_q [Z,KH,KN,HD] codes, v [Z,VH,KN,HDV]
-    values of `dtype`; mask: None, an integer / bool array (0 = masked out) or a float array (additive), broadcastable to [Z,H,QN,KN]."""
+             out_dtype="bfloat16", return_lse=False, v_scale=None, pv_matmul_dtype=None):
+    """sdnq_attn_kernel (kernels/triton_atten.py:143-335) with qk_is_quantized=1, use_fp16_accum=0: a block-wise restatement (without
+    quantised P.V the result depends on BLOCK_SIZE_N only through rounding; with it, P's row scale is taken per key block, :298-318, so
+    block_n is part of the function: 128 is the CUDA kernel's key tile).  q_q [Z,H,QN,HD], k_q [Z,KH,KN,HD] codes, v [Z,VH,KN,HDV]
+    values of `dtype`, or with v_scale [Z,VH,KN] the codes of pv_matmul_dtype ("int8" / "float8_e4m3fn"); mask: None, an integer / bool
+    array (0 = masked out) or a float array (additive), broadcastable to [Z,H,QN,KN]."""
     q_q, k_q, v = np.asarray(q_q, dtype=F32), np.asarray(k_q, dtype=F32), np.asarray(v, dtype=F32)
     Z, H, QN, _ = q_q.shape
     _, KH, KN, _ = k_q.shape
@@ -709,8 +722,21 @@ def attn_fwd(q_q, k_q, v, q_scale, k_scale, mask=None, is_causal=False, sm_scale
                         pm = np.exp2(qk).astype(F32)                 # :295
                         l_i = fma32(l_i, alpha, pm.sum(axis=1, dtype=F32))       # :296
                         acc = acc * alpha[:, None]                  # :297
-                        pv = _cast16(pm, dtype).astype(np.float64) @ v[z, vh, n0:n1].astype(np.float64)   # :319-321 (p.to(v.dtype), f32 accumulate)
-                        acc = (acc + pv.astype(F32)).astype(F32)
+                        if v_scale is not None:                     # :298-318
+                            pq = (pm * v_scale[z, vh, None, n0:n1].astype(F32)).astype(F32)
+                            p_scale = pq.max(axis=1)[:, None].astype(F32)
+                            p_scale = (p_scale * F32(1.0 / 127.0 if pv_matmul_dtype == "int8" else 1.0 / 448.0)).astype(F32)
+                            p_scale = np.where(p_scale <= F32(2e-38), F32(1), p_scale).astype(F32)
+                            inv = (F32(1) / p_scale).astype(F32)
+                            if pv_matmul_dtype == "int8":
+                                codes = np.floor(fma32(pq, inv, F32(0.5)))
+                            else:
+                                codes = e4m3fn_round((pq * inv).astype(F32))
+                            dot = (codes.astype(np.float64) @ v[z, vh, n0:n1].astype(np.float64)).astype(F32)
+                            acc = fma32(dot, p_scale, acc)
+                        else:
+                            pv = _cast16(pm, dtype).astype(np.float64) @ v[z, vh, n0:n1].astype(np.float64)   # :319-321 (p.to(v.dtype), f32 accumulate)
+                            acc = (acc + pv.astype(F32)).astype(F32)
                         m_i = m_ij
                     out[z, h, m0:m1] = acc * (F32(1) / l_i)[:, None]              # :324
                     l = m_i + np.log2(l_i)                                        # :328-330

@@ -59,7 +59,7 @@ SIGNATURES = {
     "sdnq_b200_scaled_mm": (_I, [_P, _P, _I, _P, _P, _P, _I, _L, _P, _P, _P, _P, _P, _I, _L, _L, _L, _P]),
     "sdnq_b200_scaled_mm_workspace_bytes": (_Z, []),
     "sdnq_b200_attention_workspace_bytes": (_Z, [_L, _L, _L, _L]),
-    "sdnq_b200_attention": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _I, ctypes.POINTER(ctypes.c_int64), _P, _P, _I, _L, _L, _L, _L, _L, _L, _L, _L,
+    "sdnq_b200_attention": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _I, ctypes.POINTER(ctypes.c_int64), _P, _P, _I, _L, _L, _L, _L, _L, _L, _L, _L,
                                  ctypes.c_float, _I, _P, _Z, _P]),
     "sdnq_b200_attn_colmean": (_I, [_P, _I, _L, _L, _L, _P, _P]),
     "sdnq_b200_attn_quant": (_I, [_P, _I, _L, _L, _P, _L, _I, _P, _P, _P]),

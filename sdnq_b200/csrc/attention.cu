@@ -33,13 +33,13 @@ constexpr int kBN = 128;                 // keys per tile
 constexpr int kKStages = 3;
 constexpr int kVStages = 2;
 constexpr int kTileQK = kBM * 128;       // one Q or K tile: 128 rows x 128 bytes (head dims < 128 are zero-filled by TMA)
-constexpr int kPTile = kBM * kBN * 2;    // P tile: two 64-key slabs of 128 rows x 128 bytes
 constexpr int kSoftmaxThreads = 256;
 constexpr int kThreads = 128 + kSoftmaxThreads;      // warps 0-3: TMA producer, MMA issuer, two idle (register donors); warps 4-11: softmax
 
 struct AttnParams {
     const float* q_scale;
     const float* k_scale;
+    const float* v_scale;                // quantised P.V only: per-key scales of the v codes
     void* out;
     void* lse;
     const void* mask;
@@ -51,14 +51,16 @@ struct AttnParams {
     float log2_scale;                    // sm_scale * log2(e)
 };
 
-template <int HDV>
+// PV: 0 = 16-bit P and V (pv_matmul_dtype = None), 1 = int8 codes, 2 = e4m3 codes (per-tile row scale of P, per-key scale of V)
+template <int HDV, int PV>
 struct AttnCfg {
-    static constexpr int kVStage = 2 * HDV * 128;         // two slabs of [HDV rows x 64 keys] 16-bit
+    static constexpr int kVStage = (PV == 0 ? 2 : 1) * HDV * 128;    // [HDV rows x 128 keys]: two 64-key slabs of 16-bit values, or one slab of bytes
+    static constexpr int kPTile = (PV == 0 ? 2 : 1) * kBM * 128;     // P tile, same slab structure
     static constexpr int kOffK = kTileQK;
     static constexpr int kOffV = kOffK + kKStages * kTileQK;
     static constexpr int kOffP = kOffV + kVStages * kVStage;
     static constexpr int kOffTail = kOffP + 2 * kPTile;
-    static constexpr int kTailBytes = 8 * 64 * 4 + 2 * 2 * 128 * 4 + 32 * 8 + 16;
+    static constexpr int kTailBytes = 8 * 64 * 4 + 8 * 64 * 4 + 2 * 2 * 2 * 128 * 4 + 32 * 8 + 16;
     static constexpr int kSmemBytes = kOffTail + kTailBytes + 1024;       // + alignment slack
 };
 
@@ -73,11 +75,12 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-template <bool kInt8, int HDV, bool kBf16>
+template <bool kInt8, int HDV, bool kBf16, int PV>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
-    using C = AttnCfg<HDV>;
+    using C = AttnCfg<HDV, PV>;
+    constexpr int kPTile = C::kPTile;
     constexpr int HALF = HDV / 2;                          // output columns per softmax thread
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t raw = ptx::smem_u32(smem_dyn);
@@ -85,8 +88,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     uint8_t* smem = smem_dyn + (base - raw);
     const uint32_t smem_q = base, smem_k = base + C::kOffK, smem_v = base + C::kOffV, smem_p = base + C::kOffP;
     float* s_ks = reinterpret_cast<float*>(smem + C::kOffTail);          // [8 warps][64] k_scale * log2_scale of the warp's 64 keys
-    float* s_mx = s_ks + 8 * 64;                                         // [2][2][128] half-row maxima (tile parity, half, row)
-    const uint32_t bar_base = base + C::kOffTail + 8 * 64 * 4 + 2 * 2 * 128 * 4;
+    float* s_vs = s_ks + 8 * 64;                                         // [8 warps][64] v_scale of the warp's 64 keys (quantised P.V)
+    float* s_mx = s_vs + 8 * 64;                                         // [2][2][128] half-row maxima (tile parity, half, row)
+    float* s_px = s_mx + 2 * 2 * 128;                                    // [2][2][128] half-row maxima of p * v_scale (quantised P.V)
+    const uint32_t bar_base = base + C::kOffTail + 8 * 64 * 4 + 8 * 64 * 4 + 2 * 2 * 2 * 128 * 4;
     auto bar = [&](int i) { return bar_base + 8u * uint32_t(i); };
     const uint32_t tmem_slot = bar_base + 32 * 8;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + (tmem_slot - base));
@@ -150,14 +155,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 ptx::mbar_wait_relaxed(bar(V_EMPTY + vs), (vu & 1) ^ 1);
                 ptx::mbar_arrive_expect_tx(bar(V_FULL + vs), C::kVStage);
                 ptx::tma_load_2d(smem_v + vs * C::kVStage, &tmap_vt, bar(V_FULL + vs), j * kBN, int(vt_row0));
-                ptx::tma_load_2d(smem_v + vs * C::kVStage + HDV * 128, &tmap_vt, bar(V_FULL + vs), j * kBN + 64, int(vt_row0));
+                if constexpr (PV == 0) ptx::tma_load_2d(smem_v + vs * C::kVStage + HDV * 128, &tmap_vt, bar(V_FULL + vs), j * kBN + 64, int(vt_row0));
             }
         }
       } else if (warp == 1) {
         // ======================================================== MMA issuer
         if (lane == 0) {
             const uint32_t idesc_qk = kInt8 ? ptx::make_idesc(2, 1, 1, kBM, kBN) : ptx::make_idesc(1, 0, 0, kBM, kBN);
-            const uint32_t idesc_pv = ptx::make_idesc(1, kBf16 ? 1 : 0, kBf16 ? 1 : 0, kBM, HDV);
+            const uint32_t idesc_pv = PV == 0 ? ptx::make_idesc(1, kBf16 ? 1 : 0, kBf16 ? 1 : 0, kBM, HDV)
+                                      : PV == 1 ? ptx::make_idesc(2, 1, 1, kBM, HDV) : ptx::make_idesc(1, 0, 0, kBM, HDV);
             auto issue_qk = [&](int j) {
                 const int ks = j % kKStages, ku = j / kKStages, b = j & 1, u = j >> 1;
                 ptx::mbar_wait_relaxed(bar(K_FULL + ks), ku & 1);
@@ -177,13 +183,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 ptx::mbar_wait_relaxed(bar(P_FULL + b), u & 1);                   // P_j is in shared memory
                 ptx::mbar_wait_relaxed(bar(O_EMPTY + b), (u & 1) ^ 1);            // O of tile j - 2 has been folded into the registers
                 ptx::tc_fence_after();
+                if constexpr (PV == 0) {
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const uint64_t a_desc = ptx::make_smem_desc_sw128(smem_p + b * kPTile + s * (kPTile / 2));
-                    const uint64_t b_desc = ptx::make_smem_desc_sw128(smem_v + vs * C::kVStage + s * (HDV * 128));
+                    for (int s = 0; s < 2; ++s) {
+                        const uint64_t a_desc = ptx::make_smem_desc_sw128(smem_p + b * kPTile + s * (kPTile / 2));
+                        const uint64_t b_desc = ptx::make_smem_desc_sw128(smem_v + vs * C::kVStage + s * (HDV * 128));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ptx::umma_f16(tmem_base + o_col(b), a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc_pv, (s | k) != 0 ? 1u : 0u);
+                    }
+                } else {                                                  // 1-byte P and V: the 128 keys are one 128-byte slab, four K = 32 MMAs
+                    const uint64_t a_desc = ptx::make_smem_desc_sw128(smem_p + b * kPTile);
+                    const uint64_t b_desc = ptx::make_smem_desc_sw128(smem_v + vs * C::kVStage);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        ptx::umma_f16(tmem_base + o_col(b), a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc_pv, (s | k) != 0 ? 1u : 0u);
+                        ptx::umma_ss<PV == 1>(tmem_base + o_col(b), a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc_pv, k != 0 ? 1u : 0u);
                 }
                 ptx::umma_commit(bar(V_EMPTY + vs));
                 ptx::umma_commit(bar(P_EMPTY + b));
@@ -218,11 +232,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         float m_i = -INFINITY;
         float l_i = half == 0 ? 1.0f : 0.0f;       // :232 (l_i = 1): held by the first half, the halves add up at the end
         float alpha_pend = 0.f;
+        [[maybe_unused]] float ps_pend = 1.f;      // quantised P.V: the pending tile's row scale of P
         float acc[HALF];
 #pragma unroll
         for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
 
-        auto fold_o = [&](int b, int u, float alpha) {       // acc = acc * alpha + O_b            (:297, :321)
+        auto fold_o = [&](int b, int u, float alpha, [[maybe_unused]] float ps) {       // acc = acc * alpha + O_b [* p_scale]   (:297, :307, :321)
             ptx::mbar_wait(bar(O_FULL + b), u & 1);
             ptx::tc_fence_after();
 #pragma unroll
@@ -231,7 +246,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 ptx::tmem_ld32(t_lane + o_col(b) + uint32_t(half * HALF + c * 32), o);
                 ptx::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha, __uint_as_float(o[i]));
+                for (int i = 0; i < 32; ++i) {
+                    if constexpr (PV == 0) acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha, __uint_as_float(o[i]));
+                    else if constexpr (PV == 1) acc[c * 32 + i] = fmaf(__int_as_float(0x4B400000 + static_cast<int>(o[i])) - 12582912.0f, ps, acc[c * 32 + i] * alpha);
+                    else acc[c * 32 + i] = fmaf(__uint_as_float(o[i]), ps, acc[c * 32 + i] * alpha);
+                }
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -244,13 +263,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         float* my_ks = s_ks + sw * 64;
         auto load_ks = [&](int j, int e) { const int n = j * kBN + half * 64 + e * 32 + lane; return n < p.KN ? p.k_scale[k_row0 + n] : 0.f; };
         float ks_a = load_ks(0, 0), ks_b = load_ks(0, 1);
+        [[maybe_unused]] float* my_vs = s_vs + sw * 64;
+        const int64_t v_row0 = (int64_t(z) * p.VH + vh) * p.KN;
+        auto load_vs = [&](int j, int e) { const int n = j * kBN + half * 64 + e * 32 + lane; return (PV != 0 && n < p.KN) ? p.v_scale[v_row0 + n] : 0.f; };
+        [[maybe_unused]] float vs_a = load_vs(0, 0), vs_b = load_vs(0, 1);
         for (int j = 0; j < T; ++j) {
             const int b = j & 1, u = j >> 1;
             const int n0 = j * kBN;
             my_ks[lane] = ks_a * p.log2_scale;
             my_ks[32 + lane] = ks_b * p.log2_scale;
+            if constexpr (PV != 0) { my_vs[lane] = vs_a; my_vs[32 + lane] = vs_b; }
             __syncwarp();
-            if (j + 1 < T) { ks_a = load_ks(j + 1, 0); ks_b = load_ks(j + 1, 1); }
+            if (j + 1 < T) {
+                ks_a = load_ks(j + 1, 0); ks_b = load_ks(j + 1, 1);
+                if constexpr (PV != 0) { vs_a = load_vs(j + 1, 0); vs_b = load_vs(j + 1, 1); }
+            }
             ptx::mbar_wait(bar(S_FULL + b), u & 1);
             ptx::tc_fence_after();
             float t[64];
@@ -320,33 +347,80 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             const float m_use = m_new == -INFINITY ? 0.0f : m_new;
             float sum4[4] = {0.f, 0.f, 0.f, 0.f};
             ptx::mbar_wait(bar(P_EMPTY + b), (u & 1) ^ 1);               // the MMAs of tile j - 2 have read this P buffer
-            const uint32_t p_row = smem_p + b * kPTile + half * (kPTile / 2) + uint32_t(r) * 128u;
+            [[maybe_unused]] float ps = 1.f;
+            if constexpr (PV == 0) {
+                const uint32_t p_row = smem_p + b * kPTile + half * (kPTile / 2) + uint32_t(r) * 128u;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                uint32_t w[4];
+                for (int c = 0; c < 8; ++c) {
+                    uint32_t w[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float p0 = fast_exp2(fmaf(t[c * 8 + 2 * e], rs, -m_use)), p1 = fast_exp2(fmaf(t[c * 8 + 2 * e + 1], rs, -m_use));
-                    sum4[e] += p0 + p1;
-                    if constexpr (kBf16) {
-                        __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
-                        w[e] = *reinterpret_cast<uint32_t*>(&hh);
-                    } else {
-                        __half2 hh = __floats2half2_rn(p0, p1);
-                        w[e] = *reinterpret_cast<uint32_t*>(&hh);
+                    for (int e = 0; e < 4; ++e) {
+                        const float p0 = fast_exp2(fmaf(t[c * 8 + 2 * e], rs, -m_use)), p1 = fast_exp2(fmaf(t[c * 8 + 2 * e + 1], rs, -m_use));
+                        sum4[e] += p0 + p1;
+                        if constexpr (kBf16) {
+                            __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+                            w[e] = *reinterpret_cast<uint32_t*>(&hh);
+                        } else {
+                            __half2 hh = __floats2half2_rn(p0, p1);
+                            w[e] = *reinterpret_cast<uint32_t*>(&hh);
+                        }
+                    }
+                    ptx::st_shared_v4(p_row + (uint32_t(c ^ (r & 7)) << 4), w[0], w[1], w[2], w[3]);
+                }
+            } else {
+                // :298-318: p *= v_scale; p_scale = rowmax(p) / 127 (or / 448), 1 if it underflows; codes = floor(p / p_scale + 0.5)
+                // (int8) or the e4m3 rounding of p / p_scale.  The row maximum spans both halves of the tile: a second exchange.
+                const float4* vs4 = reinterpret_cast<const float4*>(my_vs);
+                float px4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i4 = 0; i4 < 16; ++i4) {
+                    const float4 vv = vs4[i4];
+                    const float vk[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float pe = fast_exp2(fmaf(t[i4 * 4 + e], rs, -m_use));
+                        sum4[e] += pe;
+                        t[i4 * 4 + e] = pe * vk[e];
+                        px4[e] = fmaxf(px4[e], t[i4 * 4 + e]);
                     }
                 }
-                ptx::st_shared_v4(p_row + (uint32_t(c ^ (r & 7)) << 4), w[0], w[1], w[2], w[3]);
+                float px = fmaxf(fmaxf(px4[0], px4[1]), fmaxf(px4[2], px4[3]));
+                s_px[(b * 2 + half) * 128 + r] = px;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                px = fmaxf(px, s_px[(b * 2 + (half ^ 1)) * 128 + r]);
+                ps = px * (PV == 1 ? (1.0f / 127.0f) : (1.0f / 448.0f));
+                if (ps <= 2e-38f) ps = 1.0f;
+                const float inv = __fdiv_rn(1.0f, ps);
+                const uint32_t p_row = smem_p + b * kPTile + uint32_t(r) * 128u;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {                             // 16 codes per 16-byte chunk
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float* tv = &t[c * 16 + e * 4];
+                        if constexpr (PV == 1) {
+                            const int c0 = __float2int_rd(fmaf(tv[0], inv, 0.5f)), c1 = __float2int_rd(fmaf(tv[1], inv, 0.5f));
+                            const int c2 = __float2int_rd(fmaf(tv[2], inv, 0.5f)), c3 = __float2int_rd(fmaf(tv[3], inv, 0.5f));
+                            w[e] = uint32_t(c0 & 0xFF) | (uint32_t(c1 & 0xFF) << 8) | (uint32_t(c2 & 0xFF) << 16) | (uint32_t(c3 & 0xFF) << 24);
+                        } else {
+                            const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(tv[0] * inv, tv[1] * inv), __NV_SATFINITE, __NV_E4M3);
+                            const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(tv[2] * inv, tv[3] * inv), __NV_SATFINITE, __NV_E4M3);
+                            w[e] = lo | (hi << 16);
+                        }
+                    }
+                    ptx::st_shared_v4(p_row + (uint32_t((half * 4 + c) ^ (r & 7)) << 4), w[0], w[1], w[2], w[3]);
+                }
             }
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar(P_FULL + b));
             l_i = fmaf(l_i, alpha, (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
             m_i = m_new;
-            if (j > 0) fold_o(b ^ 1, (j - 1) >> 1, alpha_pend);
+            if (j > 0) fold_o(b ^ 1, (j - 1) >> 1, alpha_pend, ps_pend);
             alpha_pend = alpha;
+            ps_pend = ps;
         }
-        fold_o((T - 1) & 1, (T - 1) >> 1, alpha_pend);
+        fold_o((T - 1) & 1, (T - 1) >> 1, alpha_pend, ps_pend);
         // total row sum = the two halves' partial sums (same running maximum)
         asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");        // the last tile's s_mx reads are done
         s_mx[half * 128 + r] = l_i;
@@ -398,9 +472,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
 }
 
-// V [R, N, HD] (16-bit) -> V^T [R, HD, ldt] (ldt >= N, multiple of 8); columns N..ldt are never read (the tensor map ends at N)
-__global__ void __launch_bounds__(256) transpose_v_kernel(const uint16_t* __restrict__ v, uint16_t* __restrict__ vt, int N, int HD, int64_t ldt) {
-    __shared__ uint16_t tile[32][34];
+// V [R, N, HD] (16-bit values or 1-byte codes) -> V^T [R, HD, ldt] (row pitch ldt >= N, 16-byte multiple); columns N..ldt are never
+// read (the tensor map ends at N)
+template <typename E>
+__global__ void __launch_bounds__(256) transpose_v_kernel(const E* __restrict__ v, E* __restrict__ vt, int N, int HD, int64_t ldt) {
+    __shared__ E tile[32][32 + 4 / sizeof(E)];
     pdl_launch_dependents();
     pdl_wait();
     const int64_t rr = blockIdx.z;
@@ -408,7 +484,7 @@ __global__ void __launch_bounds__(256) transpose_v_kernel(const uint16_t* __rest
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int i = ty; i < 32; i += 8) {
         const int n = n0 + i, d = d0 + tx;
-        tile[i][tx] = (n < N && d < HD) ? v[(rr * N + n) * HD + d] : uint16_t(0);
+        tile[i][tx] = (n < N && d < HD) ? v[(rr * N + n) * HD + d] : E(0);
     }
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
@@ -563,10 +639,10 @@ int make_tmap_sw128(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
     return SDNQ_OK;
 }
 
-template <bool kInt8, int HDV, bool kBf16>
+template <bool kInt8, int HDV, bool kBf16, int PV>
 int launch_attn(const void* q, const void* k, const void* vt, int64_t ldt, int HD, const AttnParams& p, cudaStream_t st) {
-    using C = AttnCfg<HDV>;
-    auto kernel = attn_fwd_kernel<kInt8, HDV, kBf16>;
+    using C = AttnCfg<HDV, PV>;
+    auto kernel = attn_fwd_kernel<kInt8, HDV, kBf16, PV>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes); });
@@ -576,14 +652,14 @@ int launch_attn(const void* q, const void* k, const void* vt, int64_t ldt, int H
     if (rc != SDNQ_OK) return rc;
     rc = make_tmap_sw128(&tk, k, int64_t(p.Z) * p.KH * p.KN, HD, HD, 1, kBN);
     if (rc != SDNQ_OK) return rc;
-    rc = make_tmap_sw128(&tv, vt, int64_t(p.Z) * p.VH * HDV, p.KN, ldt * 2, 2, HDV);
+    rc = make_tmap_sw128(&tv, vt, int64_t(p.Z) * p.VH * HDV, p.KN, ldt * (PV == 0 ? 2 : 1), PV == 0 ? 2 : 1, HDV);
     if (rc != SDNQ_OK) return rc;
     const dim3 grid((p.QN + kBM - 1) / kBM, p.H, p.Z);
     SDNQ_CUDA_OK(launch_pdl(kernel, grid, dim3(kThreads), size_t(C::kSmemBytes), st, tq, tk, tv, p));
     return check_launch("attn_fwd_kernel");
 }
 
-int64_t vt_pitch(int64_t KN) { return (KN + 7) / 8 * 8; }
+int64_t vt_pitch(int64_t KN, int elem_bytes) { const int64_t per = 16 / elem_bytes; return (KN + per - 1) / per * per; }
 
 }  // namespace
 }  // namespace sdnq
@@ -592,7 +668,7 @@ using namespace sdnq;
 
 extern "C" size_t sdnq_b200_attention_workspace_bytes(int64_t Z, int64_t VH, int64_t KN, int64_t HDV) {
     if (Z <= 0 || VH <= 0 || KN <= 0 || HDV <= 0) return 0;
-    return static_cast<size_t>(Z * VH * HDV * vt_pitch(KN) * 2);
+    return static_cast<size_t>(Z * VH * HDV * vt_pitch(KN, 2) * 2);       // (covers the 1-byte layout too)
 }
 
 extern "C" int sdnq_b200_smooth_k(const void* k, int k_dtype, int64_t heads, int64_t N, int64_t HD, void* out, int out_dtype, void* stream) {
@@ -619,13 +695,16 @@ extern "C" int sdnq_b200_smooth_k(const void* k, int k_dtype, int64_t heads, int
 }
 
 extern "C" int sdnq_b200_attention(const void* q, const void* k, const void* v, int qk_dtype, int v_dtype, const float* q_scale,
-                                   const float* k_scale, const void* mask, int mask_dtype, const int64_t* mask_strides, void* out,
+                                   const float* k_scale, const float* v_scale, const void* mask, int mask_dtype, const int64_t* mask_strides, void* out,
                                    void* lse, int out_dtype, int64_t Z, int64_t H, int64_t KH, int64_t VH, int64_t QN, int64_t KN,
                                    int64_t HD, int64_t HDV, float sm_scale, int is_causal, void* workspace, size_t workspace_bytes,
                                    void* stream) {
     SDNQ_REQUIRE(q && k && v && q_scale && k_scale && out, SDNQ_EINVAL, "NULL pointer");
     SDNQ_REQUIRE(qk_dtype == SDNQ_I8 || qk_dtype == SDNQ_F8E4M3, SDNQ_EUNSUPPORTED, "attention: q / k codes must be int8 or float8_e4m3fn (got %d)", qk_dtype);
-    SDNQ_REQUIRE(v_dtype == SDNQ_BF16 || v_dtype == SDNQ_F16, SDNQ_EUNSUPPORTED, "attention: v must be bf16 or f16 (got %d)", v_dtype);
+    SDNQ_REQUIRE(v_dtype == SDNQ_BF16 || v_dtype == SDNQ_F16 || v_dtype == SDNQ_I8 || v_dtype == SDNQ_F8E4M3, SDNQ_EUNSUPPORTED,
+                 "attention: v must be bf16 / f16 values or int8 / float8_e4m3fn codes (got %d)", v_dtype);
+    const int pv = v_dtype == SDNQ_I8 ? 1 : v_dtype == SDNQ_F8E4M3 ? 2 : 0;
+    SDNQ_REQUIRE((pv != 0) == (v_scale != nullptr), SDNQ_EINVAL, "attention: v_scale goes with 1-byte v codes, and only with them");
     SDNQ_REQUIRE(out_dtype == SDNQ_BF16 || out_dtype == SDNQ_F16 || out_dtype == SDNQ_F32, SDNQ_EINVAL, "attention: bad out dtype %d", out_dtype);
     SDNQ_REQUIRE(Z > 0 && H > 0 && KH > 0 && VH > 0 && QN > 0 && KN > 0, SDNQ_EINVAL, "attention: bad shape");
     SDNQ_REQUIRE(HD % 16 == 0 && HD >= 16 && HD <= 128, SDNQ_EUNSUPPORTED, "attention: head dim of q / k must be a multiple of 16 up to 128 (got %lld)", (long long)HD);
@@ -642,17 +721,22 @@ extern "C" int sdnq_b200_attention(const void* q, const void* k, const void* v, 
         mask_kind = mask_dtype == SDNQ_I8 ? 1 : 2;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int64_t ldt = vt_pitch(KN);
+    const int64_t ldt = vt_pitch(KN, pv == 0 ? 2 : 1);
     {
         const dim3 grid(static_cast<unsigned>((KN + 31) / 32), static_cast<unsigned>((HDV + 31) / 32), static_cast<unsigned>(Z * VH));
-        SDNQ_CUDA_OK(launch_pdl(transpose_v_kernel, grid, dim3(256), 0, st, reinterpret_cast<const uint16_t*>(v), reinterpret_cast<uint16_t*>(workspace),
-                                int(KN), int(HDV), ldt));
+        if (pv == 0)
+            SDNQ_CUDA_OK(launch_pdl(transpose_v_kernel<uint16_t>, grid, dim3(256), 0, st, reinterpret_cast<const uint16_t*>(v), reinterpret_cast<uint16_t*>(workspace),
+                                    int(KN), int(HDV), ldt));
+        else
+            SDNQ_CUDA_OK(launch_pdl(transpose_v_kernel<uint8_t>, grid, dim3(256), 0, st, reinterpret_cast<const uint8_t*>(v), reinterpret_cast<uint8_t*>(workspace),
+                                    int(KN), int(HDV), ldt));
         int rc = check_launch("transpose_v_kernel");
         if (rc != SDNQ_OK) return rc;
     }
     AttnParams p{};
     p.q_scale = q_scale;
     p.k_scale = k_scale;
+    p.v_scale = v_scale;
     p.out = out;
     p.lse = lse;
     p.mask = mask;
@@ -663,10 +747,12 @@ extern "C" int sdnq_b200_attention(const void* q, const void* k, const void* v, 
     p.causal = is_causal ? 1 : 0;
     p.log2_scale = sm_scale * 1.4426950408889634f;
     const bool i8 = qk_dtype == SDNQ_I8, bf = v_dtype == SDNQ_BF16;
+#define SDNQ_ATTN_PV(HDV_, BF_, PV_)                                                                                           \
+    (i8 ? launch_attn<true, HDV_, BF_, PV_>(q, k, workspace, ldt, int(HD), p, st) : launch_attn<false, HDV_, BF_, PV_>(q, k, workspace, ldt, int(HD), p, st))
 #define SDNQ_ATTN(HDV_)                                                                                                        \
-    (i8 ? (bf ? launch_attn<true, HDV_, true>(q, k, workspace, ldt, int(HD), p, st) : launch_attn<true, HDV_, false>(q, k, workspace, ldt, int(HD), p, st))   \
-        : (bf ? launch_attn<false, HDV_, true>(q, k, workspace, ldt, int(HD), p, st) : launch_attn<false, HDV_, false>(q, k, workspace, ldt, int(HD), p, st)))
+    (pv == 1 ? SDNQ_ATTN_PV(HDV_, true, 1) : pv == 2 ? SDNQ_ATTN_PV(HDV_, true, 2) : bf ? SDNQ_ATTN_PV(HDV_, true, 0) : SDNQ_ATTN_PV(HDV_, false, 0))
     return HDV == 128 ? SDNQ_ATTN(128) : SDNQ_ATTN(64);
+#undef SDNQ_ATTN_PV
 #undef SDNQ_ATTN
 }
 

@@ -207,7 +207,8 @@ def attn_quant(x: torch.Tensor, matmul_dtype: str, smooth: bool = False):
 
 
 def attention_fwd(q_q: torch.Tensor, k_q: torch.Tensor, v: torch.Tensor, q_scale: torch.Tensor, k_scale: torch.Tensor, attn_mask=None,
-                  is_causal: bool = False, sm_scale: float = 1.0, out_dtype: torch.dtype = torch.bfloat16, return_lse: bool = False):
+                  is_causal: bool = False, sm_scale: float = 1.0, out_dtype: torch.dtype = torch.bfloat16, return_lse: bool = False,
+                  v_scale: torch.Tensor | None = None):
     """K9: sdnq_atten_fwd (kernels/triton_atten.py:338-386) for 1-byte q / k codes with per-row scales and a 16-bit v.
     q_q [Z,H,QN,HD], k_q [Z,KH,KN,HD] int8 / float8_e4m3fn; q_scale [Z,H,QN], k_scale [Z,KH,KN] f32; v [Z,VH,KN,HDV] bf16 / f16;
     attn_mask: None, or a 4-D int8 / bool (0 = masked out) or float (additive) tensor broadcastable to [Z,H,QN,KN].
@@ -216,6 +217,14 @@ def attention_fwd(q_q: torch.Tensor, k_q: torch.Tensor, v: torch.Tensor, q_scale
     _require_cuda(q_q, k_q, v, q_scale, k_scale)
     if q_q.dtype != k_q.dtype or q_q.dtype not in (torch.int8, torch.float8_e4m3fn):
         raise _lib.SDNQKernelError(f"attention: q / k codes must both be int8 or float8_e4m3fn (got {q_q.dtype}, {k_q.dtype})")
+    v_is_codes = v.dtype in (torch.int8, torch.float8_e4m3fn)
+    if v_is_codes != (v_scale is not None):
+        raise _lib.SDNQKernelError(f"attention: v_scale goes with int8 / float8_e4m3fn v codes, and only with them (v is {v.dtype})")
+    if v_scale is not None:
+        _require_cuda(v_scale)
+        v_scale = v_scale.to(torch.float32).contiguous()
+        if tuple(v_scale.shape) != tuple(v.shape[:-1]):
+            raise _lib.SDNQKernelError(f"attention: v_scale {tuple(v_scale.shape)} does not match v {tuple(v.shape)}")
     q_q, k_q, v = q_q.contiguous(), k_q.contiguous(), v.contiguous()
     q_scale = q_scale.to(torch.float32).contiguous()
     k_scale = k_scale.to(torch.float32).contiguous()
@@ -247,7 +256,7 @@ def attention_fwd(q_q: torch.Tensor, k_q: torch.Tensor, v: torch.Tensor, q_scale
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         check(lib.sdnq_b200_attention(_ptr(q_q), _ptr(k_q), _ptr(v), SDNQ_I8 if q_q.dtype == torch.int8 else SDNQ_F8E4M3, dtype_code(v.dtype),
-                                      _ptr(q_scale), _ptr(k_scale), mask_ptr, mask_code, strides, _ptr(out), _ptr(lse), dtype_code(out_dtype),
+                                      _ptr(q_scale), _ptr(k_scale), _ptr(v_scale), mask_ptr, mask_code, strides, _ptr(out), _ptr(lse), dtype_code(out_dtype),
                                       Z, H, KH, VH, QN, KN, HD, HDV, float(sm_scale), int(bool(is_causal)), _ptr(ws), ws_bytes, _stream(q_q)))
     return out, lse
 

@@ -70,6 +70,56 @@ def test_attention_kernel_matches_oracle(case, mm):
     assert np.abs(got16.float().cpu().numpy() - ref).max() <= 1e-2 * np.abs(ref).max()
 
 
+PV_CASES = [CASES[0], CASES[1], CASES[2], CASES[3], CASES[4]]
+
+
+@pytest.mark.parametrize("pv,tol", [("int8", 4e-3), ("float8_e4m3fn", 1e-2)])
+@pytest.mark.parametrize("mm", ["int8", "float8_e4m3fn"])
+@pytest.mark.parametrize("case", PV_CASES, ids=[str(c) for c in PV_CASES])
+def test_attention_kernel_quantised_pv_matches_oracle(case, mm, pv, tol):
+    """quantised P.V (kernels/triton_atten.py:298-318): identical q / k / v codes, the oracle run with K9's key tile (block_n = 128: P's
+    row scale is per key block).  Tolerance: f32 output, max |err| <= 4e-3 (int8 P) / 1e-2 (e4m3 P: one code step is 6 % of p) * max
+    |ref| -- the kernel's exp2 is the hardware approximation, so single codes of P may land on the other side of a rounding boundary."""
+    Z, H, KH, QN, KN, HD, HDV = case
+    q, k, v = _inputs(Z, H, KH, QN, KN, HD, HDV, seed=QN + KN + 1)
+    (qq, qs, kq, ks), (tq, tqs, tk, tks) = _codes(q, k, mm)
+    vq, vs = O.quantize_attn_v(v.float().numpy(), pv_matmul_dtype=pv)
+    tv = torch.from_numpy(vq).to(torch.int8 if pv == "int8" else torch.float8_e4m3fn).to(DEV)
+    sm = HD ** -0.5
+    causal = QN == KN
+    ref, ref_lse = O.attn_fwd(qq, kq, vq, qs, ks, sm_scale=sm, is_causal=causal, out_dtype="float32", return_lse=True, v_scale=vs, pv_matmul_dtype=pv)
+    got, lse = ops().attention_fwd(tq, tk, tv, tqs, tks, sm_scale=sm, is_causal=causal, out_dtype=torch.float32, return_lse=True,
+                                   v_scale=torch.from_numpy(vs).to(DEV))
+    err = np.abs(got.cpu().numpy() - ref).max()
+    assert err <= tol * np.abs(ref).max(), (err, np.abs(ref).max())
+    assert np.abs(lse.cpu().numpy() - ref_lse).max() <= 1e-3 * max(1.0, np.abs(ref_lse).max())
+
+
+def test_attention_quantised_pv_with_mask():
+    Z, H, KH, QN, KN, HD, HDV = 2, 2, 1, 200, 333, 64, 64
+    q, k, v = _inputs(Z, H, KH, QN, KN, HD, HDV, seed=21)
+    (qq, qs, kq, ks), (tq, tqs, tk, tks) = _codes(q, k, "int8")
+    vq, vs = O.quantize_attn_v(v.float().numpy(), pv_matmul_dtype="int8")
+    g = torch.Generator().manual_seed(6)
+    mask = torch.rand(1, 1, QN, KN, generator=g) > 0.5
+    mask[:, :, 7] = False                              # a fully masked row
+    mask[:, :, 130:140, :256] = False                  # rows whose first two key tiles are fully masked
+    ref = O.attn_fwd(qq, kq, vq, qs, ks, mask=mask.numpy(), sm_scale=0.125, out_dtype="float32", v_scale=vs, pv_matmul_dtype="int8")
+    got, _ = ops().attention_fwd(tq, tk, torch.from_numpy(vq).to(torch.int8).to(DEV), tqs, tks, attn_mask=mask.to(DEV), sm_scale=0.125,
+                                 out_dtype=torch.float32, v_scale=torch.from_numpy(vs).to(DEV))
+    assert np.abs(got.cpu().numpy() - ref).max() <= 4e-3 * np.abs(ref).max()
+
+
+def test_attention_v_scale_goes_with_codes_only():
+    from sdnq_b200 import _lib
+    q, k, v = _inputs(1, 1, 1, 64, 64, 64, 64, seed=2)
+    _, (tq, tqs, tk, tks) = _codes(q, k, "int8")
+    with pytest.raises(_lib.SDNQKernelError):
+        ops().attention_fwd(tq, tk, v.to(DEV), tqs, tks, v_scale=torch.ones(1, 1, 64, device=DEV))
+    with pytest.raises(_lib.SDNQKernelError):
+        ops().attention_fwd(tq, tk, tk, tqs, tks)
+
+
 @pytest.mark.parametrize("kind", ["causal", "bool", "additive", "bool_rows_fully_masked", "broadcast_key_padding"])
 def test_attention_kernel_masks(kind):
     Z, H, KH, QN, KN, HD, HDV = 2, 2, 2, 200, 333, 64, 64
@@ -135,6 +185,23 @@ def test_sdnq_attention_end_to_end(shape, hadamard, mm, tol):
     assert rel <= tol, rel
 
 
+@pytest.mark.parametrize("pv,tol", [("int8", 4e-2), ("float8_e4m3fn", 8e-2)])
+@pytest.mark.parametrize("hadamard", [False, True])
+@pytest.mark.parametrize("shape", [(2, 4, 4, 333, 333, 64), (1, 24, 24, 1024, 1024, 128), (1, 8, 2, 512, 77, 40)])
+def test_sdnq_attention_quantised_pv_end_to_end(shape, hadamard, pv, tol):
+    """sdnq_attention(pv_matmul_dtype=...) vs fp32 softmax attention: relative L2 <= 4e-2 (int8 P.V) / 8e-2 (e4m3 P.V, 3 mantissa bits on
+    both operands); with a rotation v is rotated before its quantisation and the output rotated back (triton_atten.py:480, :604-607)"""
+    import sdnq_b200
+    Z, H, KH, QN, KN, HD = shape
+    q, k, v = _inputs(Z, H, KH, QN, KN, HD, HD, seed=QN + 3)
+    got = sdnq_b200.sdnq_attention(q.to(DEV), k.to(DEV), v.to(DEV), use_hadamard=hadamard, matmul_dtype="int8", pv_matmul_dtype=pv)
+    assert got.shape == (Z, H, QN, HD) and got.dtype == torch.bfloat16
+    rep = H // KH
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float().to(DEV), k.float().repeat_interleave(rep, 1).to(DEV), v.float().repeat_interleave(rep, 1).to(DEV))
+    rel = float((got.float() - ref).norm() / ref.norm())
+    assert rel <= tol, rel
+
+
 def test_sdnq_attention_quantised_operands_match_oracle():
     """the pre-pass (smooth-K kernel + K2 with rotation) produces the oracle's codes (rotated values: +-1 code, as for the Linear path)"""
     from sdnq_b200 import attention
@@ -172,17 +239,29 @@ CHILD = textwrap.dedent('''
     out = {}
     # (KN = 77, SD-XL's real cross-attention length, is not in this list: the reference's own kernel dies there with "misaligned
     #  address" -- its key-scale descriptor has a 4 * 77-byte head pitch -- and takes the CUDA context with it)
-    for name, (Z, H, KH, QN, KN, HD, causal, mm) in {"flux_like": (1, 4, 4, 640, 640, 128, False, "int8"), "sdxl_cross": (2, 5, 5, 512, 80, 64, False, "int8"),
-                                                   "causal": (1, 2, 2, 384, 384, 64, True, "int8"), "fp8": (1, 2, 2, 256, 300, 128, False, "float8_e4m3fn")}.items():
+    for name, (Z, H, KH, QN, KN, HD, causal, mm, *pv) in {"flux_like": (1, 4, 4, 640, 640, 128, False, "int8"), "sdxl_cross": (2, 5, 5, 512, 80, 64, False, "int8"),
+                                                   "causal": (1, 2, 2, 384, 384, 64, True, "int8"), "fp8": (1, 2, 2, 256, 300, 128, False, "float8_e4m3fn"),
+                                                   "pv_int8": (1, 4, 4, 640, 640, 128, False, "int8", "int8"),
+                                                   "pv_fp8": (1, 2, 2, 256, 320, 64, False, "int8", "float8_e4m3fn")}.items():
+        pv = pv[0] if pv else None
         g = torch.Generator().manual_seed(QN)
         q = torch.randn(Z, H, QN, HD, generator=g).bfloat16().cuda()
         k = (torch.randn(Z, KH, KN, HD, generator=g) + 0.5).bfloat16().cuda()
         v = torch.randn(Z, KH, KN, HD, generator=g).bfloat16().cuda()
         with torch.no_grad():
-            ref = sdnq_triton_atten(q, k, v, is_causal=causal, matmul_dtype=mm).float()
-            got = sdnq_b200.sdnq_attention(q, k, v, is_causal=causal, matmul_dtype=mm).float()
+            try:
+                ref = sdnq_triton_atten(q, k, v, is_causal=causal, matmul_dtype=mm, pv_matmul_dtype=pv).float()
+                torch.cuda.synchronize()
+            except Exception as e:      # a configuration the reference's own Triton program cannot compile / run here: recorded, not compared
+                out[name] = {"reference_error": repr(e)[:300]}
+                break                   # (a device-side fault leaves the context unusable: nothing after it can be trusted)
+            got = sdnq_b200.sdnq_attention(q, k, v, is_causal=causal, matmul_dtype=mm, pv_matmul_dtype=pv).float()
         qq, qs, kq, ks = O.quantize_attn(q.float().cpu().numpy(), k.float().cpu().numpy(), smooth_k=True, matmul_dtype=mm)
-        orc = torch.from_numpy(O.attn_fwd(qq, kq, v.float().cpu().numpy(), qs, ks, is_causal=causal, sm_scale=HD ** -0.5, block_n=32)).cuda()
+        if pv:          # P's row scale is per key block: the oracle at the reference's BLOCK_SIZE_N pins the restatement, K9 uses 128
+            vq, vs = O.quantize_attn_v(v.float().cpu().numpy(), pv_matmul_dtype=pv)
+            orc = torch.from_numpy(O.attn_fwd(qq, kq, vq, qs, ks, is_causal=causal, sm_scale=HD ** -0.5, block_n=32, v_scale=vs, pv_matmul_dtype=pv)).cuda()
+        else:
+            orc = torch.from_numpy(O.attn_fwd(qq, kq, v.float().cpu().numpy(), qs, ks, is_causal=causal, sm_scale=HD ** -0.5, block_n=32)).cuda()
         scale = float(ref.abs().max())
         out[name] = {"kernel_vs_reference": float((got - ref).abs().max()) / scale, "oracle_vs_reference": float((orc - ref).abs().max()) / scale,
                      "rel_l2": float((got - ref).norm() / ref.norm())}
@@ -200,6 +279,14 @@ def test_attention_matches_the_unmodified_reference_kernel():
         pytest.skip("the reference's Triton attention does not run on this box: " + r.stderr.strip().splitlines()[-1][:300])
     assert line is not None, r.stderr[-3000:]
     res = json.loads(line[len("RESULT "):])
+    assert "reference_error" not in res.get("flux_like", {}) and "flux_like" in res, res
     for name, e in res.items():
+        if "reference_error" in e:
+            assert name.startswith("pv_"), (name, e)      # only the quantised-P.V cases may be beyond the reference's own kernel here
+            continue
         # bf16 outputs, different key-block sizes (128 here, <= 64 in the reference's autotune space): a few bf16 ulps of the largest value
-        assert e["kernel_vs_reference"] <= 2e-2 and e["oracle_vs_reference"] <= 2e-2 and e["rel_l2"] <= 1e-2, (name, e)
+        # quantised P.V: P's codes depend on the key-block size, so the kernel (128) differs from the reference (32) by quantisation noise
+        # of P, while the oracle at block_n = 32 must still sit on the reference
+        loose = name.startswith("pv_")
+        assert e["oracle_vs_reference"] <= 2e-2, (name, e)
+        assert e["kernel_vs_reference"] <= (8e-2 if loose else 2e-2) and e["rel_l2"] <= (4e-2 if loose else 1e-2), (name, e)

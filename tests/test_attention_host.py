@@ -60,7 +60,7 @@ def test_hadamard_group_rule_matches_oracle():
             assert get_hadamard_group_size(channel, group) == O.hadamard_group_size(channel, group)
 
 
-@pytest.mark.parametrize("kwargs", [dict(do_quantize=False), dict(use_fp16_accum=True), dict(pv_matmul_dtype="int8"), dict(matmul_dtype="fp16"),
+@pytest.mark.parametrize("kwargs", [dict(do_quantize=False), dict(use_fp16_accum=True), dict(pv_matmul_dtype="float16"), dict(matmul_dtype="fp16"),
                                     dict(matmul_dtype="disabled")])
 def test_unsupported_attention_options_fail_loudly(kwargs):
     import sdnq_b200
@@ -75,3 +75,22 @@ def test_attention_needs_a_gpu_tensor():
     q = torch.zeros(1, 1, 4, 64, dtype=torch.bfloat16)
     with pytest.raises((_lib.SDNQKernelError, RuntimeError)):
         sdnq_b200.sdnq_attention(q, q, q)
+
+
+def test_oracle_quantised_pv_is_close_to_the_unquantised_result():
+    """the P.V branch of the restatement (kernels/triton_atten.py:298-318): int8 / e4m3 codes of p * v_scale with a per-block row scale
+    stay within the quantisation noise of the 16-bit P.V, for both key-block sizes used in the GPU tests (the reference's 32, K9's 128)"""
+    rng = np.random.default_rng(0)
+    Z, H, QN, KN, HD = 1, 2, 70, 200, 32
+    q = O.bf16_round(rng.standard_normal((Z, H, QN, HD)).astype(np.float32))
+    k = O.bf16_round(rng.standard_normal((Z, H, KN, HD)).astype(np.float32))
+    v = O.bf16_round(rng.standard_normal((Z, H, KN, HD)).astype(np.float32))
+    qq, qs, kq, ks = O.quantize_attn(q, k, matmul_dtype="int8")
+    base = O.attn_fwd(qq, kq, v, qs, ks, sm_scale=HD ** -0.5, out_dtype="float32")
+    for pv, tol in (("int8", 2e-2), ("float8_e4m3fn", 6e-2)):
+        vq, vs = O.quantize_attn_v(v, pv_matmul_dtype=pv)
+        assert vs.shape == (Z, H, KN)
+        for bn in (32, 128):
+            got = O.attn_fwd(qq, kq, vq, qs, ks, sm_scale=HD ** -0.5, out_dtype="float32", block_n=bn, v_scale=vs, pv_matmul_dtype=pv)
+            rel = np.linalg.norm(got - base) / np.linalg.norm(base)
+            assert rel <= tol, (pv, bn, rel)

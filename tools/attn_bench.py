@@ -2,7 +2,7 @@
 (bf16, the library yardstick) and -- when oracle/_ref imports and its Triton program compiles on this box -- the reference's own
 `sdnq_triton_atten` with its full autotune space.  FLOPs = 4 * Z * H * QN * KN * HD (Q.K^T + P.V).
 
-    python tools/attn_bench.py [--no-reference]"""
+    python tools/attn_bench.py [--no-reference] [--pv]"""
 import argparse
 import os
 import sys
@@ -36,6 +36,7 @@ def timed(fn, iters=20, warmup=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-reference", action="store_true")
+    ap.add_argument("--pv", action="store_true", help="also time quantised P.V (pv_matmul_dtype = int8 / float8_e4m3fn, Q.K^T int8)")
     args = ap.parse_args()
     import sdnq_b200
     from sdnq_b200 import attention, ops
@@ -62,6 +63,12 @@ def main():
             t_k = timed(lambda: ops.attention_fwd(qq, kq, v, qs, ks, sm_scale=HD ** -0.5))
             t_e = timed(lambda: sdnq_b200.sdnq_attention(q, k, v, matmul_dtype=mm))
             line.append(f"{mm[:4]}: kernel+V^T {t_k:8.1f} us = {flops / t_k * 1e-6:6.0f} TF/s, with pre-pass {t_e:8.1f} us = {flops / t_e * 1e-6:6.0f} TF/s |")
+        if args.pv:
+            for pv in ("int8", "float8_e4m3fn"):
+                qq, qs, kq, ks, vq, vs = attention.quantize_attn(q, k, v, matmul_dtype="int8", pv_matmul_dtype=pv)
+                t_k = timed(lambda: ops.attention_fwd(qq, kq, vq, qs, ks, sm_scale=HD ** -0.5, v_scale=vs))
+                t_e = timed(lambda: sdnq_b200.sdnq_attention(q, k, v, matmul_dtype="int8", pv_matmul_dtype=pv))
+                line.append(f"P.V {pv[:4]}: kernel+V^T {t_k:8.1f} us = {flops / t_k * 1e-6:6.0f} TF/s, with pre-pass {t_e:8.1f} us = {flops / t_e * 1e-6:6.0f} TF/s |")
         t_s = timed(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))
         line.append(f"torch SDPA bf16 {t_s:8.1f} us = {flops / t_s * 1e-6:6.0f} TF/s |")
         if ref_fn is not None:
