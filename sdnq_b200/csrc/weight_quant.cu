@@ -10,6 +10,8 @@
 // weights (one octet of the packed layout), the scale group is reduced with warp shuffles (groups of 8..256 weights) or by the
 // CTA (row-wise / wider groups, second read from L2), and the packed bytes are written directly: HBM traffic = the weight once
 // in its own dtype + bits/8 bytes per weight out.
+#include <cmath>
+
 #include "act_quant.cuh"     // actq::RowDivider: correctly rounded x / s with the reciprocal hoisted out of the element loop
 #include "unpack.cuh"
 
@@ -24,6 +26,7 @@ struct WQArgs {
     int64_t octets;         // N*K / 8
     int oct_per_group;      // scale group size / 8
     int bits, is_unsigned, packed;      // packed = 0: one byte per code (int8 / uint8 storage), no offset
+    int kind, exponent, mantissa;       // sdnq_wkind; float kinds: qmin / qmax are the format's smallest / largest value
     float qmin, qmax;
     int scale_dtype;        // SDNQ_F32: keep; SDNQ_BF16 / SDNQ_F16: round scale (and zero point) to that type first (dequantize_fp32=False)
     uint8_t* out;
@@ -95,20 +98,57 @@ __device__ __forceinline__ void group_scale(const WQArgs& a, float amax, float v
     scale = round_scale(scale, a.scale_dtype);
 }
 
+// pack_float (packed_float.py:26-82) on one clamped value: the reference's own bit arithmetic, which is not plain round-to-nearest --
+// a normal is rounded up when the top four dropped mantissa bits exceed one half (strictly), a value below the smallest normal becomes
+// round_half_even(|x| * 2^M / min_normal) mantissa steps, then sign / exponent / mantissa are squeezed into `bits` bits.
+__device__ __forceinline__ uint32_t encode_minifloat(float x, int E, int M, int bits, int is_unsigned) {
+    const int drop = 23 - M;
+    int xi = static_cast<int>(__float_as_uint(x));
+    const int top4 = (-(1 << (drop - 4))) & ~(-(1 << drop));
+    if ((xi & top4) > (1 << (drop - 1))) xi += (1 << drop);
+    if (E < 8) {
+        const float min_normal = __uint_as_float(static_cast<uint32_t>(127 + 2 - (1 << (E - 1))) << 23);          // 2^(2 - 2^(E-1))
+        const float ax = fabsf(__uint_as_float(static_cast<uint32_t>(xi)));
+        if (ax < min_normal) {
+            const float steps = rintf(__fmul_rn(ax, __fdiv_rn(static_cast<float>(1 << M), min_normal)));
+            xi = (xi & static_cast<int>(0x80000000u)) | (static_cast<int>(steps) << drop);
+        }
+    }
+    xi >>= drop;                                                // arithmetic, as torch's int32 shift
+    const int sign_mask = is_unsigned ? (1 << (bits - 1)) : (1 << (bits - 1)) + (1 << (bits - 2));
+    return static_cast<uint32_t>((((xi >> (8 - E)) & sign_mask) | (xi & ~sign_mask)) & ((1 << bits) - 1));
+}
+
 template <int BITS>
 __device__ __forceinline__ void quantise_store(const WQArgs& a, int64_t oct, const float (&v)[8], float scale, float zero) {
     uint32_t codes[8];
     const int offset = (a.packed && !a.is_unsigned) ? static_cast<int>(a.qmin) : 0;      // packed signed codes are offset-binary
-#pragma unroll
     const actq::RowDivider divider(scale);
     const bool safe = divider.safe();
-    for (int i = 0; i < 8; ++i) {
-        const float num = a.is_unsigned ? __fsub_rn(v[i], zero) : v[i];
-        float q = safe ? divider.div<true>(num) : divider.div<false>(num);
-        const bool nan = !(q == q);                             // 0 / 0 of an all-zero group: NaN survives round_ / clamp_, the int cast makes it 0
-        q = fminf(fmaxf(rintf(q), a.qmin), a.qmax);
-        const int c = nan ? 0 : static_cast<int>(q);
-        codes[i] = static_cast<uint32_t>(c - offset) & 0xFFu;
+    if (a.kind == SDNQ_W_INT) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float num = a.is_unsigned ? __fsub_rn(v[i], zero) : v[i];
+            float q = safe ? divider.div<true>(num) : divider.div<false>(num);
+            const bool nan = !(q == q);                         // 0 / 0 of an all-zero group: NaN survives round_ / clamp_, the int cast makes it 0
+            q = fminf(fmaxf(rintf(q), a.qmin), a.qmax);
+            const int c = nan ? 0 : static_cast<int>(q);
+            codes[i] = static_cast<uint32_t>(c - offset) & 0xFFu;
+        }
+    } else {
+        // float formats (quant_utils.py:47-55): nan_to_num_ (NaN -> 0, +-inf -> +-FLT_MAX), clamp to the format's range, then the cast
+        // to torch.float8_e4m3fn / float8_e5m2 (round to nearest even) or pack_float's encoder for the eXmY minifloats
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float num = a.is_unsigned ? __fsub_rn(v[i], zero) : v[i];
+            float q = safe ? divider.div<true>(num) : divider.div<false>(num);
+            if (!(q == q)) q = 0.f;
+            else if (q == 0.f) q = copysignf(0.f, num);         // the divider's residual step loses the sign of a zero quotient; x / s keeps it (-0 encodes as 0x80)
+            q = fminf(fmaxf(q, a.qmin), a.qmax);                // (+-inf land on the range ends, as FLT_MAX would)
+            if (a.kind == SDNQ_W_FP8_E4M3FN) codes[i] = __nv_cvt_float_to_fp8(q, __NV_SATFINITE, __NV_E4M3);
+            else if (a.kind == SDNQ_W_FP8_E5M2) codes[i] = __nv_cvt_float_to_fp8(q, __NV_SATFINITE, __NV_E5M2);
+            else codes[i] = encode_minifloat(q, a.exponent, a.mantissa, a.bits, a.is_unsigned);
+        }
     }
     uint8_t bytes[BITS];
     encode_octet<BITS>(codes, bytes);
@@ -206,7 +246,9 @@ extern "C" int sdnq_b200_quantize_weight(const void* w, int w_dtype, int64_t N, 
     int rc = make_wformat(fmt, &f);
     if (rc != SDNQ_OK) return rc;
     SDNQ_REQUIRE(w && codes && scale, SDNQ_EINVAL, "NULL pointer");
-    SDNQ_REQUIRE(f.kind == SDNQ_W_INT && f.word_bytes == 1 && f.bits >= 2, SDNQ_EUNSUPPORTED, "quantize_weight: integer formats of 2..8 bits (got kind %d, %d bits)", f.kind, f.bits);
+    SDNQ_REQUIRE(f.word_bytes == 1 && f.bits >= 2 && f.bits <= 8, SDNQ_EUNSUPPORTED, "quantize_weight: formats of 2..8 bits (got kind %d, %d bits)", f.kind, f.bits);
+    const bool is_float = f.kind != SDNQ_W_INT;
+    if (is_float) SDNQ_REQUIRE(f.exponent >= 1 && f.exponent <= 8 && f.mantissa >= 0 && f.mantissa <= 15, SDNQ_EINVAL, "quantize_weight: bad minifloat e%dm%d", f.exponent, f.mantissa);
     SDNQ_REQUIRE(w_dtype == SDNQ_F32 || w_dtype == SDNQ_BF16 || w_dtype == SDNQ_F16, SDNQ_EINVAL, "bad weight dtype %d", w_dtype);
     SDNQ_REQUIRE(scale_dtype == SDNQ_F32 || scale_dtype == SDNQ_BF16 || scale_dtype == SDNQ_F16, SDNQ_EINVAL, "bad scale dtype %d", scale_dtype);
     SDNQ_REQUIRE(N > 0 && K > 0 && K % 8 == 0, SDNQ_EUNSUPPORTED, "quantize_weight: K (=%lld) must be a positive multiple of 8", (long long)K);
@@ -215,10 +257,18 @@ extern "C" int sdnq_b200_quantize_weight(const void* w, int w_dtype, int64_t N, 
     SDNQ_REQUIRE(!f.is_unsigned || zero_point != nullptr, SDNQ_EINVAL, "unsigned formats need a zero_point output");
     SDNQ_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(codes) & 7) == 0, SDNQ_EINVAL, "w must be 16-byte and codes 8-byte aligned");
     const int64_t octets = N * K / 8;
-    const float qmax = f.is_unsigned ? static_cast<float>((1 << f.bits) - 1) : static_cast<float>((1 << (f.bits - 1)) - 1);
-    const float qmin = f.is_unsigned ? 0.f : -static_cast<float>(1 << (f.bits - 1));
-    WQArgs a{w, w_dtype, octets, static_cast<int>(group_size / 8), f.bits, f.is_unsigned, f.bits < 8 ? 1 : 0, qmin, qmax, scale_dtype,
-             reinterpret_cast<uint8_t*>(codes), scale, f.is_unsigned ? zero_point : nullptr};
+    float qmax = f.is_unsigned ? static_cast<float>((1 << f.bits) - 1) : static_cast<float>((1 << (f.bits - 1)) - 1);
+    float qmin = f.is_unsigned ? 0.f : -static_cast<float>(1 << (f.bits - 1));
+    if (f.kind == SDNQ_W_FP8_E4M3FN) { qmax = 448.f; qmin = -448.f; }
+    else if (f.kind == SDNQ_W_FP8_E5M2) { qmax = 57344.f; qmin = -57344.f; }
+    else if (is_float) {
+        // "fn" minifloats use every exponent code (common.py:16-334): max = (2 - 2^-M) * 2^(2^E - 1 - bias), bias = 2^(E-1) - 1
+        const int bias = (1 << (f.exponent - 1)) - 1;
+        qmax = std::ldexp(2.0f - std::ldexp(1.0f, -f.mantissa), (1 << f.exponent) - 1 - bias);
+        qmin = f.is_unsigned ? 0.f : -qmax;
+    }
+    WQArgs a{w, w_dtype, octets, static_cast<int>(group_size / 8), f.bits, f.is_unsigned, (f.bits < 8 && !is_float) ? 1 : 0, f.kind, f.exponent, f.mantissa,
+             qmin, qmax, scale_dtype, reinterpret_cast<uint8_t*>(codes), scale, f.is_unsigned ? zero_point : nullptr};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int T = a.oct_per_group;
     const bool narrow = T <= 32 && (T & (T - 1)) == 0;

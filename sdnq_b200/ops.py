@@ -384,18 +384,20 @@ def dequant_nd(weight, weights_dtype, scale, zero_point, view_shape, out_dtype, 
 
 def quantize_weight(w: torch.Tensor, weights_dtype: str, group_size: int = -1, scale_dtype: torch.dtype | None = None):
     """K8.  w [N,K] f32 / bf16 / f16 -> (codes, scale [N, K/g] f32, zero_point [N, K/g] f32 | None): `codes` is the packed uint8
-    buffer (sub-byte formats) or the [N,K] int8 / uint8 code matrix (8-bit formats) exactly as quantize_weight + pack_int produce them."""
+    buffer (sub-byte formats) or the [N,K] code matrix (8-bit formats) exactly as quantize_weight + pack_int / pack_float produce them
+    (integer formats, torch.float8_e4m3fn / float8_e5m2, and the eXmY minifloats of packed_float.py)."""
     _require_cuda(w)
     info = dtype_dict[weights_dtype]
-    if not info["is_integer"] or not 2 <= info["num_bits"] <= 8:
-        raise _lib.SDNQKernelError(f"quantize_weight: {weights_dtype!r} has no quantisation kernel (integer formats of 2..8 bits)")
+    if not 2 <= info["num_bits"] <= 8 or not (info["is_integer"] or info["is_packed"] or info["torch_dtype"] in (torch.float8_e4m3fn, torch.float8_e5m2)):
+        raise _lib.SDNQKernelError(f"quantize_weight: {weights_dtype!r} has no quantisation kernel (integer and float formats of 2..8 bits)")
     N, K = w.shape
     w = w.contiguous()
     if w.data_ptr() % 16 != 0:
         w = w.clone()
     g = K if group_size <= 0 or group_size >= K else int(group_size)
     bits = info["num_bits"]
-    codes = torch.empty((N, K), dtype=info["torch_dtype"], device=w.device) if bits == 8 else torch.empty(N * K * bits // 8, dtype=torch.uint8, device=w.device)
+    # 8-bit formats: the [N,K] code matrix in the storage dtype (int8 / uint8 / float8_*; uint8 for the 8-bit eXmY minifloats)
+    codes = torch.empty((N, K), dtype=info["storage_dtype"], device=w.device) if bits == 8 else torch.empty(N * K * bits // 8, dtype=torch.uint8, device=w.device)
     scale = torch.empty((N, K // g), dtype=torch.float32, device=w.device)
     zp = torch.empty((N, K // g), dtype=torch.float32, device=w.device) if info["is_unsigned"] else None
     with torch.cuda.device(w.device):

@@ -60,12 +60,14 @@ def _fit_group_size(group_size: int, channel_size: int):
 
 @torch.no_grad()
 def _quant_kernel_ok(weight, winfo, is_linear, reduction_axes, use_codebook, stochastic) -> bool:
-    """K8 covers Linear weights on a CUDA device, integer formats of 2..8 bits, scale groups along K that are multiples of 8 (or
-    row-wise), round-to-nearest.  SDNQ_B200_QUANT_KERNEL=0 keeps the eager tensor ops."""
+    """K8 covers Linear weights on a CUDA device, integer and float formats of 2..8 bits (intN / uintN, float8_e4m3fn / e5m2, the
+    packed eXmY minifloats), scale groups along K that are multiples of 8 (or row-wise), round-to-nearest.  SDNQ_B200_QUANT_KERNEL=0 keeps the eager tensor ops."""
     import os
     if os.environ.get("SDNQ_B200_QUANT_KERNEL", "1") in ("0", "false", "no") or not weight.is_cuda or not is_linear or use_codebook or stochastic:
         return False
-    if not winfo["is_integer"] or not 2 <= winfo["num_bits"] <= 8 or reduction_axes != -1 or weight.ndim not in (2, 3):
+    if not 2 <= winfo["num_bits"] <= 8 or reduction_axes != -1 or weight.ndim not in (2, 3):
+        return False
+    if not (winfo["is_integer"] or winfo["is_packed"] or winfo["torch_dtype"] in (torch.float8_e4m3fn, torch.float8_e5m2)):
         return False
     if weight.dtype not in (torch.float32, torch.bfloat16, torch.float16):
         return False
@@ -181,7 +183,7 @@ def sdnq_quantize_layer_weight(
     packed_by_kernel = False
     if _quant_kernel_ok(weight, winfo, is_linear, reduction_axes, use_codebook, use_stochastic_rounding and not skip_sr):
         # K8: scale + round + clamp + pack in one pass over the weight on the GPU (csrc/weight_quant.cu) -- the arithmetic of
-        # quantize_weight + pack_int below, bit for bit
+        # quantize_weight + pack_int / pack_float below, bit for bit
         from . import ops
         view_shape = weight.shape
         codes, scale, zero_point = ops.quantize_weight(weight.reshape(out_ch, -1), weights_dtype, group_size if num_groups > 1 else -1, cast_to)
@@ -191,8 +193,11 @@ def sdnq_quantize_layer_weight(
             scale = scale.to(cast_to)
             zero_point = None if zero_point is None else zero_point.to(cast_to)
         if winfo["is_packed"]:
-            words = {2: 1, 4: 1, 3: 3, 5: 5, 6: 3, 7: 7}[winfo["num_bits"]]
-            packed_weight, packed_by_kernel = (codes if words == 1 else codes.view(-1, words)), True
+            words = {2: 1, 4: 1, 3: 3, 5: 5, 6: 3, 7: 7, 8: 0}[winfo["num_bits"]]
+            if words == 0:                       # 8-bit eXmY minifloats: one uint8 code per weight, in the weight's own shape (pack_float)
+                packed_weight, packed_by_kernel = codes.view(view_shape), True
+            else:
+                packed_weight, packed_by_kernel = (codes if words == 1 else codes.view(-1, words)), True
             weight = torch.empty(view_shape, dtype=torch.uint8, device="meta")       # only its shape is used below
         else:
             weight = codes.view(view_shape)

@@ -294,6 +294,12 @@ def test_quantize_weight(kw):
     K.test_quantize_weight_matches_host_arithmetic(**kw)
 
 
+@emulated(K.test_quantize_weight_float_formats_match_host_arithmetic,
+          keep=lambda kw: kw["N"] * kw["K"] <= 33 * 640 and (kw["K"] != 1536 or kw["wd"] in ("float6_e3m2fn", "float8_e4m3fn")))
+def test_quantize_weight_float_formats(kw):
+    K.test_quantize_weight_float_formats_match_host_arithmetic(**kw)
+
+
 @emulated(K.test_quantize_weight_reproduces_reference_fixture)
 def test_quantize_weight_fixture(kw):
     K.test_quantize_weight_reproduces_reference_fixture(**kw)

@@ -586,6 +586,40 @@ def test_quantize_weight_matches_host_arithmetic(wd, N, K, gs):
         assert np.array_equal(codes.cpu().reshape(-1).view(torch.uint8).numpy(), want.numpy()), "codes"
 
 
+FLOAT_WD = ["float8_e4m3fn", "float8_e5m2", "float8_e4m3fn_sdnq", "float8_e5m2fn", "float8_e3m4fn", "float8_e4m4fnu", "float7_e3m3fn", "float7_e4m2fn",
+            "float7_e2m5fnu", "float6_e3m2fn", "float6_e2m3fn", "float6_e1m4fn", "float5_e2m2fn", "float5_e4m0fn", "float4_e2m1fn", "float4_e3m0fn",
+            "float4_e2m2fnu", "float3_e2m0fn", "float3_e1m1fn", "float2_e1m0fn"]
+
+
+@pytest.mark.parametrize("wd", FLOAT_WD)
+@pytest.mark.parametrize("N,K,gs", [(64, 256, 32), (33, 640, 128), (16, 1024, -1), (7, 96, 8), (3, 4104, -1), (9, 1536, 512)])
+def test_quantize_weight_float_formats_match_host_arithmetic(wd, N, K, gs):
+    """the float formats through K8: scale + divide + nan_to_num + clamp + (cast to torch.float8_* | pack_float's bit arithmetic) + pack
+    == quant_math.quantize_weight + packing.pack_float on the CPU (packed_float.py:26-82, pinned to the reference's float fixtures by
+    tests/test_host_api.py): same bytes, same scales, same zero points"""
+    from sdnq_b200 import packing, quant_math
+    from sdnq_b200.common import dtype_dict
+    info = dtype_dict[wd]
+    g = torch.Generator().manual_seed(N * 5 + K + info["num_bits"] + info["mantissa"])
+    for wdtype, scale_dtype in ((torch.float32, None), (torch.bfloat16, None), (torch.float32, torch.bfloat16)):
+        w = (torch.randn(N, K, generator=g) * torch.rand(N, 1, generator=g) * 3).to(wdtype)
+        w[0, : (K if gs <= 0 else gs)] = 0                                        # an all-zero group: 0 / 0 -> 0
+        w[-1, -1] = 1e4                                                           # an outlier: the rest of its group lands in the subnormals
+        w[1, :8] = torch.tensor([1e-30, -1e-30, 0.0, -0.0, 1e-3, -1e-3, 2.5e-1, -2.5e-1]).to(wdtype)
+        groups = 1 if gs <= 0 else K // gs
+        view = w.float().view(N, groups, K // groups)
+        q, s_ref, z_ref = quant_math.quantize_weight(view, -1, wd, dtype=scale_dtype)
+        want = packing.pack_float(q, wd).reshape(-1).view(torch.uint8) if info["is_packed"] else q.reshape(-1).view(torch.uint8)
+        codes, scale, zp = ops().quantize_weight(w.to(DEV), wd, gs, scale_dtype)
+        assert np.array_equal(scale.cpu().numpy().reshape(-1), s_ref.float().numpy().reshape(-1)), "scale"
+        if info["is_unsigned"]:
+            assert np.array_equal(zp.cpu().numpy().reshape(-1), z_ref.float().numpy().reshape(-1)), "zero point"
+        else:
+            assert zp is None and z_ref is None
+        got = codes.cpu().reshape(-1).view(torch.uint8).numpy()
+        assert np.array_equal(got, want.numpy()), f"codes: {int((got != want.numpy()).sum())} bytes differ"
+
+
 @pytest.mark.parametrize("path", [p for p in LAYER_FILES if "small_m" not in p], ids=[i for p, i in zip(LAYER_FILES, LAYER_IDS) if "small_m" not in p])
 def test_quantize_weight_reproduces_reference_fixture(path):
     """the stored `weight` / `scale` / `zero_point` bytes of a layer the reference quantised, from its float weight"""
@@ -593,9 +627,9 @@ def test_quantize_weight_reproduces_reference_fixture(path):
     d = meta["dequantizer"]
     from sdnq_b200.common import dtype_dict
     info = dtype_dict[d["weights_dtype"]]
-    if (not info["is_integer"] or info["num_bits"] < 2 or info["num_bits"] > 8 or d.get("use_hadamard") or d.get("use_codebook") or t["svd_up"] is not None
+    if (info["num_bits"] < 2 or info["num_bits"] > 8 or d.get("use_hadamard") or d.get("use_codebook") or t["svd_up"] is not None
             or d["group_size"] == -2):
-        pytest.skip("outside the first slice of the quantisation kernel (integer formats without rotation / SVD / codebook)")
+        pytest.skip("outside the quantisation kernel (2..8-bit formats without rotation / SVD / codebook)")
     N, K = meta["N"], meta["K"]
     gs = d["group_size"]
     codes, scale, zp = ops().quantize_weight(t["w_orig"].to(DEV), d["weights_dtype"], gs if gs > 0 else -1, None if t["scale"].dtype == torch.float32 else t["scale"].dtype)

@@ -233,7 +233,10 @@ def test_dynamic_quantization_picks_the_reference_dtypes(name):
                                  dict(weights_dtype="uint4"), dict(weights_dtype="int4", group_size=128, use_svd=True, svd_rank=32),
                                  dict(weights_dtype="int6", use_quantized_matmul=True), dict(weights_dtype="int5", group_size=32),
                                  dict(weights_dtype="uint3", group_size=64, dequantize_fp32=False), dict(weights_dtype="int2", group_size=16),
-                                 dict(weights_dtype="int8", use_quantized_matmul=True, use_hadamard=True, hadamard_group_size=128)],
+                                 dict(weights_dtype="int8", use_quantized_matmul=True, use_hadamard=True, hadamard_group_size=128),
+                                 dict(weights_dtype="float8_e4m3fn", use_quantized_matmul=True), dict(weights_dtype="float8_e5m2", group_size=64),
+                                 dict(weights_dtype="float6_e3m2fn", use_quantized_matmul=True), dict(weights_dtype="float4_e2m1fn", group_size=32),
+                                 dict(weights_dtype="float8_e4m3fn_sdnq"), dict(weights_dtype="float7_e3m4fnu", group_size=128)],
                          ids=lambda c: "_".join(str(v) for v in c.values()))
 def test_quantising_on_the_gpu_stores_what_the_cpu_path_stores(cfg, monkeypatch):
     """sdnq_quantize_layer on a CUDA weight goes through K8 (scale + round + clamp + pack in one kernel); the stored tensors are the
@@ -261,6 +264,8 @@ def test_quantising_on_the_gpu_stores_what_the_cpu_path_stores(cfg, monkeypatch)
             continue
         assert a.dtype == b.dtype and a.shape == b.shape and a.stride() == b.stride(), (name, a.dtype, b.dtype, a.shape, b.shape, a.stride(), b.stride())
         if ref_dev == "cpu":
+            if a.element_size() == 1:
+                a, b = a.view(torch.uint8), b.view(torch.uint8)          # (float8 tensors: compare the bytes)
             assert torch.equal(a.cpu(), b.cpu()), name
         else:
             # eager CUDA divides by a scalar through its reciprocal; the kernel divides: scales may differ in the last bit, codes by one
