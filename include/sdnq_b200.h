@@ -287,15 +287,21 @@ SDNQ_API int sdnq_b200_embedding(const void* weight, const sdnq_weight_format* f
                                  void* stream);
 
 /* ---- K8 load-time quantisation of a weight: scale, round, clamp and pack in one pass (the middle of sdnq_quantize_layer_weight,
- *      quantizer.py:236-253: quantize_weight, quant_utils.py:27-56, then pack_int, packed_int/__init__.py:76-80 + pack.py:201-321).
+ *      quantizer.py:236-253: quantize_weight, quant_utils.py:27-56, then pack_int, packed_int/__init__.py:76-80 + pack.py:201-321,
+ *      or pack_float, packed_float.py:26-82).
  *   w            [N,K] row-major f32 / bf16 / f16 (after the optional Hadamard rotation / SVD subtraction, which stay host-side);
  *                K % 8 == 0, 16-byte aligned
  *   group_size   scale groups of that many consecutive weights along K (a multiple of 8 dividing K); <= 0 or >= K: row-wise
  *   fmt          integer formats of 2..8 bits: symmetric  scale = amax / qmax,  q = round_half_even(w / scale)  for signed formats,
  *                asymmetric  scale = (max - min) / qmax, zero_point = min,  q = round_half_even((w - zero_point) / scale)  for unsigned
- *                ones; true f32 divisions, clamp to the format's range -- the arithmetic of the reference on the CPU, bit for bit
+ *                ones; true f32 divisions, clamp to the format's range -- the arithmetic of the reference on the CPU, bit for bit.
+ *                Float formats of 2..8 bits (SDNQ_W_FP8_E4M3FN, SDNQ_W_FP8_E5M2, SDNQ_W_MINIFLOAT signed "fn" / unsigned "fnu"):
+ *                the same scales over the format's largest value, q = nan_to_num(w / scale) clamped to the range, then the cast
+ *                to torch.float8_* (round to nearest even) or pack_float's own bit arithmetic (packed_float.py:26-82: normals round
+ *                up when the top four dropped mantissa bits exceed one half, subnormals are round_half_even(|q| * 2^M / min_normal))
  *   scale_dtype  SDNQ_F32, or SDNQ_BF16 / SDNQ_F16: scale and zero point are rounded to that type before the division (dequantize_fp32=False)
- *   codes        bits < 8: N*K*bits/8 packed bytes (signed codes offset-binary);  bits == 8: N*K one-byte codes (int8 two's complement / uint8)
+ *   codes        bits < 8: N*K*bits/8 packed bytes (signed integer codes offset-binary);  bits == 8: N*K one-byte codes (int8 two's
+ *                complement / uint8 / float8 bit patterns / 8-bit minifloat codes)
  *   scale, zero_point   f32 [N * K / group_size]  (zero_point written for unsigned formats only) */
 SDNQ_API int sdnq_b200_quantize_weight(const void* w, int w_dtype, int64_t N, int64_t K, int64_t group_size, const sdnq_weight_format* fmt,
                                        int scale_dtype, void* codes, float* scale, float* zero_point, void* stream);
