@@ -37,6 +37,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-reference", action="store_true")
     ap.add_argument("--pv", action="store_true", help="also time quantised P.V (pv_matmul_dtype = int8 / float8_e4m3fn, Q.K^T int8)")
+    ap.add_argument("--shapes", type=int, default=len(SHAPES), help="only the first N shapes")
     args = ap.parse_args()
     import sdnq_b200
     from sdnq_b200 import attention, ops
@@ -51,7 +52,7 @@ def main():
             triton.set_allocator(lambda size, align, stream: torch.empty(size, dtype=torch.int8, device="cuda"))
         except Exception as e:      # noqa: BLE001
             print(f"reference attention not importable: {type(e).__name__}: {e}")
-    for name, (Z, H, QN, KN, HD) in SHAPES.items():
+    for name, (Z, H, QN, KN, HD) in list(SHAPES.items())[:args.shapes]:
         g = torch.Generator(device="cuda").manual_seed(0)
         q = torch.randn(Z, H, QN, HD, device="cuda", generator=g).bfloat16()
         k = (torch.randn(Z, H, KN, HD, device="cuda", generator=g) + 0.5).bfloat16()
