@@ -75,13 +75,32 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-template <bool kInt8, int HDV, bool kBf16, int PV>
+#ifndef SDNQ_ATTN_POLY_PAIRS
+#define SDNQ_ATTN_POLY_PAIRS 1          // of every four score pairs, how many take the FMA-pipe exponential (measured: profiles/r02_attention_exp_phase_experiments.md)
+#endif
+// 2^x for x <= 0 on the FMA pipe (no MUFU): n = round(x) through the 1.5 * 2^23 magic add, a degree-3 minimax polynomial of 2^f on
+// f = x - n in [-0.5, 0.5] (relative error 7.5e-5, far below the 16-bit rounding of P), n added to the exponent field.  x is clamped at
+// -125 so the exponent stays normal: a padded key (-inf) gets 2.4e-38 instead of 0, and meets a zero-filled V row.
+__device__ __forceinline__ float poly_exp2(float x) {
+    x = fmaxf(x, -125.0f);
+    const float xr = x + 12582912.0f;
+    const float f = x - (xr - 12582912.0f);
+    float pl = fmaf(0.05517210811376572f, f, 0.2426111400127411f);
+    pl = fmaf(pl, f, 0.6932608485221863f);
+    pl = fmaf(pl, f, 0.9999280571937561f);
+    return __int_as_float(__float_as_int(pl) + (__float_as_int(xr) << 23));
+}
+
+// kMask: the call has a mask tensor or is causal; the plain instantiation carries none of that code in its key loop
+template <bool kInt8, int HDV, bool kBf16, int PV, bool kMask>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
     using C = AttnCfg<HDV, PV>;
     constexpr int kPTile = C::kPTile;
     constexpr int HALF = HDV / 2;                          // output columns per softmax thread
+    const int mask_kind = kMask ? p.mask_kind : 0;
+    const bool causal = kMask && p.causal != 0;
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t raw = ptx::smem_u32(smem_dyn);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -104,7 +123,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int64_t k_row0 = (int64_t(z) * p.KH + kh) * p.KN;
     const int64_t vt_row0 = (int64_t(z) * p.VH + vh) * HDV;               // first row of this head in the [Z*VH*HDV, KN] view of V^T
     const int num_kv = (p.KN + kBN - 1) / kBN;
-    const int T = p.causal ? min(num_kv, m0 / kBN + 1) : num_kv;          // :238-239: tiles starting past the block's last row are skipped
+    const int T = causal ? min(num_kv, m0 / kBN + 1) : num_kv;          // :238-239: tiles starting past the block's last row are skipped
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_q);
@@ -225,10 +244,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         // scores are kept as u = acc * k_scale' and the row's factor is applied inside the exponent: p = exp2(fma(u, rs, -m)).
         // rs = q_scale (>= 0; an all-zero row has u == 0 everywhere, so 1 serves and keeps 0 * -inf out); additive masks live in
         // the scaled domain, so with one of those the factor is applied first and rs = 1
-        const float rs = p.mask_kind == 2 ? 1.0f : (qs > 0.f ? qs : 1.0f);
-        const float pre = p.mask_kind == 2 ? qs : 1.0f;
+        const float rs = mask_kind == 2 ? 1.0f : (qs > 0.f ? qs : 1.0f);
+        const float pre = mask_kind == 2 ? qs : 1.0f;
         const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16);
-        const int64_t mask_row = p.mask_kind != 0 ? int64_t(z) * p.mask_sz + int64_t(h) * p.mask_sh + int64_t(m_ok ? m : 0) * p.mask_sq : 0;
+        const int64_t mask_row = mask_kind != 0 ? int64_t(z) * p.mask_sz + int64_t(h) * p.mask_sh + int64_t(m_ok ? m : 0) * p.mask_sq : 0;
         float m_i = -INFINITY;
         float l_i = half == 0 ? 1.0f : 0.0f;       // :232 (l_i = 1): held by the first half, the halves add up at the end
         float alpha_pend = 0.f;
@@ -308,14 +327,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             }
             // masks
             const int col0 = n0 + half * 64;
-            if (p.mask_kind == 1) {
+            if (mask_kind == 1) {
                 const int8_t* mk = reinterpret_cast<const int8_t*>(p.mask) + mask_row;
 #pragma unroll
                 for (int i = 0; i < 64; ++i) {
                     const int n = col0 + i;
                     if (n < p.KN && mk[int64_t(n) * p.mask_sk] == 0) t[i] = -INFINITY;
                 }
-            } else if (p.mask_kind == 2) {
+            } else if (mask_kind == 2) {
                 const float* mk = reinterpret_cast<const float*>(p.mask) + mask_row;
 #pragma unroll
                 for (int i = 0; i < 64; ++i) {
@@ -324,11 +343,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     if (n < p.KN) t[i] += mk[int64_t(n) * p.mask_sk];
                 }
             }
-            if (col0 + 64 > p.KN || (p.causal && col0 + 63 > m)) {
+            if (col0 + 64 > p.KN || (causal && col0 + 63 > m)) {
 #pragma unroll
                 for (int i = 0; i < 64; ++i) {
                     const int n = col0 + i;
-                    if (n >= p.KN || (p.causal && n > m)) t[i] = -INFINITY;
+                    if (n >= p.KN || (causal && n > m)) t[i] = -INFINITY;
                 }
             }
             float mx4[4] = {t[0], t[1], t[2], t[3]};
@@ -355,7 +374,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     uint32_t w[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float p0 = fast_exp2(fmaf(t[c * 8 + 2 * e], rs, -m_use)), p1 = fast_exp2(fmaf(t[c * 8 + 2 * e + 1], rs, -m_use));
+                        // the exponentials are MUFU-bound (16 / clock / SM) with issue slots to spare: without a mask (no -inf scores
+                        // except padded keys, which meet zero-filled V rows) a share of them is computed on the FMA pipe instead
+                        const bool kPoly = !kMask && e >= 4 - SDNQ_ATTN_POLY_PAIRS;      // (a compile-time constant once the loop is unrolled)
+                        const float x0 = fmaf(t[c * 8 + 2 * e], rs, -m_use), x1 = fmaf(t[c * 8 + 2 * e + 1], rs, -m_use);
+                        const float p0 = kPoly ? poly_exp2(x0) : fast_exp2(x0), p1 = kPoly ? poly_exp2(x1) : fast_exp2(x1);
                         sum4[e] += p0 + p1;
                         if constexpr (kBf16) {
                             __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
@@ -454,7 +477,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             }
             if (p.lse != nullptr && half == 0) {                           // :326-332
                 float l = m_i + log2f(l_tot);
-                if (p.mask_kind != 0 && l == -INFINITY) l = 0.f;
+                if (mask_kind != 0 && l == -INFINITY) l = 0.f;
                 const int64_t li = q_row0 + m;
                 if (p.out_dtype == SDNQ_F32) reinterpret_cast<float*>(p.lse)[li] = l;
                 else if (p.out_dtype == SDNQ_BF16) reinterpret_cast<__nv_bfloat16*>(p.lse)[li] = __float2bfloat16_rn(l);
@@ -639,10 +662,10 @@ int make_tmap_sw128(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
     return SDNQ_OK;
 }
 
-template <bool kInt8, int HDV, bool kBf16, int PV>
-int launch_attn(const void* q, const void* k, const void* vt, int64_t ldt, int HD, const AttnParams& p, cudaStream_t st) {
+template <bool kInt8, int HDV, bool kBf16, int PV, bool kMask>
+int launch_attn_m(const void* q, const void* k, const void* vt, int64_t ldt, int HD, const AttnParams& p, cudaStream_t st) {
     using C = AttnCfg<HDV, PV>;
-    auto kernel = attn_fwd_kernel<kInt8, HDV, kBf16, PV>;
+    auto kernel = attn_fwd_kernel<kInt8, HDV, kBf16, PV, kMask>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes); });
@@ -657,6 +680,12 @@ int launch_attn(const void* q, const void* k, const void* vt, int64_t ldt, int H
     const dim3 grid((p.QN + kBM - 1) / kBM, p.H, p.Z);
     SDNQ_CUDA_OK(launch_pdl(kernel, grid, dim3(kThreads), size_t(C::kSmemBytes), st, tq, tk, tv, p));
     return check_launch("attn_fwd_kernel");
+}
+
+template <bool kInt8, int HDV, bool kBf16, int PV>
+int launch_attn(const void* q, const void* k, const void* vt, int64_t ldt, int HD, const AttnParams& p, cudaStream_t st) {
+    return (p.mask_kind != 0 || p.causal != 0) ? launch_attn_m<kInt8, HDV, kBf16, PV, true>(q, k, vt, ldt, HD, p, st)
+                                               : launch_attn_m<kInt8, HDV, kBf16, PV, false>(q, k, vt, ldt, HD, p, st);
 }
 
 int64_t vt_pitch(int64_t KN, int elem_bytes) { const int64_t per = 16 / elem_bytes; return (KN + per - 1) / per * per; }
