@@ -516,11 +516,41 @@ __global__ void __launch_bounds__(256) transpose_v_kernel(const E* __restrict__ 
     }
 }
 
+// The 16-bit case in 64 x 64 tiles: a lane moves two values at a time (4-byte loads along the head dim, 4-byte stores along the keys),
+// so both sides of the transposition touch full 128-byte lines; HD % 64 == 0, v 4-byte aligned.
+__global__ void __launch_bounds__(256) transpose_v16_kernel(const uint16_t* __restrict__ v, uint16_t* __restrict__ vt, int N, int HD, int64_t ldt) {
+    __shared__ uint16_t tile[64][65];                // odd pitch: the column reads of the store phase fall on 32 different banks
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t rr = blockIdx.z;
+    const int n0 = blockIdx.x * 64, d0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = ty; i < 64; i += 8) {
+        const int n = n0 + i;
+        const uint32_t w = n < N ? *reinterpret_cast<const uint32_t*>(v + (rr * N + n) * HD + d0 + 2 * tx) : 0u;
+        tile[i][2 * tx] = static_cast<uint16_t>(w);
+        tile[i][2 * tx + 1] = static_cast<uint16_t>(w >> 16);
+    }
+    __syncthreads();
+    const int n = n0 + 2 * tx;
+    if (n < N) {
+#pragma unroll
+        for (int i = ty; i < 64; i += 8) {
+            const uint32_t w = uint32_t(tile[2 * tx][i]) | (uint32_t(tile[2 * tx + 1][i]) << 16);
+            *reinterpret_cast<uint32_t*>(vt + (rr * HD + d0 + i) * ldt + n) = w;      // (an odd N: the pair's second half is 0 and lands in the row padding)
+        }
+    }
+}
+
 // smooth-K (triton_atten.py:456-461): k [R, N, HD] -> k.to(f32) - mean over the N tokens, written as f32 or in a 16-bit type.
-// One CTA per (batch, head); the head (N * HD elements) is read twice, the second time from L2.
+// A cluster of kMeanSplit CTAs per (batch, head): each sums a contiguous eighth of the tokens, every CTA adds the eight partial rows
+// through distributed shared memory in rank order (so all hold the same mean), then subtracts it from its own tokens (second read from L2).
+constexpr int kMeanSplit = 8;
 template <typename TIn, typename TOut>
-__global__ void __launch_bounds__(256) smooth_k_kernel(const TIn* __restrict__ k, TOut* __restrict__ out, int N, int HD) {
+__global__ void __cluster_dims__(1, kMeanSplit, 1) __launch_bounds__(256) smooth_k_kernel(const TIn* __restrict__ k, TOut* __restrict__ out, int N, int HD) {
     __shared__ float s_part[256];
+    __shared__ float s_tot[256];
     __shared__ float s_mean[256];
     pdl_launch_dependents();
     pdl_wait();
@@ -529,20 +559,33 @@ __global__ void __launch_bounds__(256) smooth_k_kernel(const TIn* __restrict__ k
     const int lanes = HD < 256 ? HD : 256;           // threads along the channel axis (HD <= 256)
     const int groups = 256 / lanes;                  // row groups
     const int d = tid % lanes, g = tid / lanes;
+    const int chunk = (N + kMeanSplit - 1) / kMeanSplit;
+    const int n_begin = int(blockIdx.y) * chunk, n_end = min(N, n_begin + chunk);
     float sum = 0.f;
     if (g < groups)
-        for (int n = g; n < N; n += groups) sum += ElemTraits<TIn>::load(k[head + int64_t(n) * HD + d]);
+        for (int n = n_begin + g; n < n_end; n += groups) sum += ElemTraits<TIn>::load(k[head + int64_t(n) * HD + d]);
     s_part[tid] = g < groups ? sum : 0.f;
     __syncthreads();
     if (tid < lanes) {
         float tot = 0.f;
         for (int gg = 0; gg < groups; ++gg) tot += s_part[gg * lanes + tid];
+        s_tot[tid] = tot;
+    }
+    ptx::cluster_sync();
+    if (tid < lanes) {
+        float tot = 0.f;
+#pragma unroll
+        for (int rk = 0; rk < kMeanSplit; ++rk) {
+            float part;
+            asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(part) : "r"(ptx::mapa(ptx::smem_u32(&s_tot[tid]), uint32_t(rk))));
+            tot += part;
+        }
         s_mean[tid] = tot / static_cast<float>(N);
     }
-    __syncthreads();
+    ptx::cluster_sync();                             // (also: no CTA leaves while a peer may still read its partial row)
     if (g < groups) {
         const float mean = s_mean[d];
-        for (int n = g; n < N; n += groups) {
+        for (int n = n_begin + g; n < n_end; n += groups) {
             const int64_t i = head + int64_t(n) * HD + d;
             const float val = ElemTraits<TIn>::load(k[i]) - mean;
             if constexpr (sizeof(TOut) == 4) out[i] = val;
@@ -557,7 +600,6 @@ __global__ void __launch_bounds__(256) smooth_k_kernel(const TIn* __restrict__ k
 // per thread, the 256 / (HD / 8) row groups of the CTA reduced through shared memory), CTA 0 of the cluster adds the eight partial rows
 // through distributed shared memory in rank order -- deterministic, no workspace, and 8 x heads CTAs instead of heads (one CTA per
 // head with one load in flight ran at 1.0 TB/s: 112 us of a 1.6 ms FLUX call).
-constexpr int kMeanSplit = 8;
 template <typename T>
 __global__ void __cluster_dims__(1, kMeanSplit, 1) __launch_bounds__(256)
 attn_colmean_kernel(const T* __restrict__ k, float* __restrict__ mean, int N, int HD) {
@@ -738,7 +780,7 @@ extern "C" int sdnq_b200_smooth_k(const void* k, int k_dtype, int64_t heads, int
                  (long long)heads, (long long)N, (long long)HD);
     if (heads == 0) return SDNQ_OK;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const dim3 grid(static_cast<unsigned>(heads)), block(256);
+    const dim3 grid(static_cast<unsigned>(heads), kMeanSplit), block(256);
 #define SDNQ_SMOOTH(TI, TO)                                                                                                   \
     do {                                                                                                                      \
         SDNQ_CUDA_OK(launch_pdl(smooth_k_kernel<TI, TO>, grid, block, 0, st, reinterpret_cast<const TI*>(k), reinterpret_cast<TO*>(out), int(N), int(HD))); \
@@ -785,7 +827,11 @@ extern "C" int sdnq_b200_attention(const void* q, const void* k, const void* v, 
     const int64_t ldt = vt_pitch(KN, pv == 0 ? 2 : 1);
     {
         const dim3 grid(static_cast<unsigned>((KN + 31) / 32), static_cast<unsigned>((HDV + 31) / 32), static_cast<unsigned>(Z * VH));
-        if (pv == 0)
+        if (pv == 0 && HDV % 64 == 0 && (reinterpret_cast<uintptr_t>(v) & 3) == 0) {
+            const dim3 grid64(static_cast<unsigned>((KN + 63) / 64), static_cast<unsigned>(HDV / 64), static_cast<unsigned>(Z * VH));
+            SDNQ_CUDA_OK(launch_pdl(transpose_v16_kernel, grid64, dim3(256), 0, st, reinterpret_cast<const uint16_t*>(v), reinterpret_cast<uint16_t*>(workspace),
+                                    int(KN), int(HDV), ldt));
+        } else if (pv == 0)
             SDNQ_CUDA_OK(launch_pdl(transpose_v_kernel<uint16_t>, grid, dim3(256), 0, st, reinterpret_cast<const uint16_t*>(v), reinterpret_cast<uint16_t*>(workspace),
                                     int(KN), int(HDV), ldt));
         else
