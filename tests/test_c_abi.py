@@ -169,6 +169,7 @@ def test_integration_stub_binds_against_the_built_library(lib):
     assert '"libsdnq_b200.so"' in stub
     ns = {}
     exec(compile(stub.replace('"libsdnq_b200.so"', repr(_lib.LIB_PATH)), "INTEGRATION.md:b200.py", "exec"), ns)
+    exec(compile(next(b for b in blocks if "sdnq/kernels/b200_atten.py" in b), "INTEGRATION.md:b200_atten.py", "exec"), ns)      # the attention launch
     protos, _ = header_prototypes()
     bound = 0
     for name, (_, params) in protos.items():
@@ -181,8 +182,8 @@ def test_integration_stub_binds_against_the_built_library(lib):
             want = _ctype_of(c)
             want = ctypes.c_void_p if isinstance(want, type) and issubclass(want, ctypes._Pointer) else want
             assert a is want, f"INTEGRATION.md stub: {name} parameter {i}: {c} bound as {a}"
-    assert bound >= 2
-    for fn in ("sdnq_scaled_mm", "quantize_int_mm_input"):
+    assert bound >= 4 and ns["_lib"].sdnq_b200_attention.argtypes is not None
+    for fn in ("sdnq_scaled_mm", "quantize_int_mm_input", "sdnq_atten_fwd"):
         assert callable(ns[fn])
     assert [ns[k] for k in ("F32", "BF16", "F16", "I8", "U8", "F8E4M3", "I32")] == \
         [_lib.SDNQ_F32, _lib.SDNQ_BF16, _lib.SDNQ_F16, _lib.SDNQ_I8, _lib.SDNQ_U8, _lib.SDNQ_F8E4M3, _lib.SDNQ_I32]
