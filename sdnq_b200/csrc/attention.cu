@@ -33,8 +33,18 @@ constexpr int kBN = 128;                 // keys per tile
 constexpr int kKStages = 3;
 constexpr int kVStages = 2;
 constexpr int kTileQK = kBM * 128;       // one Q or K tile: 128 rows x 128 bytes (head dims < 128 are zero-filled by TMA)
-constexpr int kSoftmaxThreads = 256;
-constexpr int kThreads = 128 + kSoftmaxThreads;      // warps 0-3: TMA producer, MMA issuer, two idle (register donors); warps 4-11: softmax
+#ifndef SDNQ_ATTN_PARTS
+#define SDNQ_ATTN_PARTS 2          // 4 (16 softmax warps, 32 columns each) measured 5 % slower: profiles/r02_attention_exp_phase_experiments.md
+#endif
+constexpr int kParts = SDNQ_ATTN_PARTS;              // softmax threads per query row: each owns 128 / kParts of a tile's key columns
+constexpr int kCPT = kBN / kParts;                   // score columns per softmax thread
+constexpr int kSoftmaxThreads = 128 * kParts;
+constexpr int kThreads = 128 + kSoftmaxThreads;      // warps 0-3: TMA producer, MMA issuer, two idle (register donors); then 4 * kParts softmax warps
+// setmaxnreg moves registers inside the CTA's own allocation (kThreads x the launch count: 168 at 384 threads, 96 at 640): what the four
+// control warps give up must cover what the softmax warps take, or the .inc waits for ever
+constexpr int kLaunchRegs = kParts == 2 ? 168 : 96, kCtrlRegs = kParts == 2 ? 48 : 32, kSoftmaxRegs = kParts == 2 ? 224 : 112;
+static_assert(128 * (kLaunchRegs - kCtrlRegs) >= 128 * kParts * (kSoftmaxRegs - kLaunchRegs), "setmaxnreg budget");
+static_assert(kParts == 2 || kParts == 4, "column parts per row");
 
 struct AttnParams {
     const float* q_scale;
@@ -60,7 +70,7 @@ struct AttnCfg {
     static constexpr int kOffV = kOffK + kKStages * kTileQK;
     static constexpr int kOffP = kOffV + kVStages * kVStage;
     static constexpr int kOffTail = kOffP + 2 * kPTile;
-    static constexpr int kTailBytes = 8 * 64 * 4 + 8 * 64 * 4 + 2 * 2 * 2 * 128 * 4 + 32 * 8 + 16;
+    static constexpr int kTailBytes = 4 * kParts * kCPT * 4 * 2 + 2 * 2 * kParts * 128 * 4 + 32 * 8 + 16;
     static constexpr int kSmemBytes = kOffTail + kTailBytes + 1024;       // + alignment slack
 };
 
@@ -98,7 +108,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
     using C = AttnCfg<HDV, PV>;
     constexpr int kPTile = C::kPTile;
-    constexpr int HALF = HDV / 2;                          // output columns per softmax thread
+    constexpr int HALF = HDV / kParts;                     // output columns per softmax thread
     const int mask_kind = kMask ? p.mask_kind : 0;
     const bool causal = kMask && p.causal != 0;
     extern __shared__ uint8_t smem_dyn[];
@@ -106,11 +116,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = smem_dyn + (base - raw);
     const uint32_t smem_q = base, smem_k = base + C::kOffK, smem_v = base + C::kOffV, smem_p = base + C::kOffP;
-    float* s_ks = reinterpret_cast<float*>(smem + C::kOffTail);          // [8 warps][64] k_scale * log2_scale of the warp's 64 keys
-    float* s_vs = s_ks + 8 * 64;                                         // [8 warps][64] v_scale of the warp's 64 keys (quantised P.V)
-    float* s_mx = s_vs + 8 * 64;                                         // [2][2][128] half-row maxima (tile parity, half, row)
-    float* s_px = s_mx + 2 * 2 * 128;                                    // [2][2][128] half-row maxima of p * v_scale (quantised P.V)
-    const uint32_t bar_base = base + C::kOffTail + 8 * 64 * 4 + 8 * 64 * 4 + 2 * 2 * 2 * 128 * 4;
+    float* s_ks = reinterpret_cast<float*>(smem + C::kOffTail);          // [softmax warps][kCPT] k_scale * log2_scale of the warp's keys
+    float* s_vs = s_ks + 4 * kParts * kCPT;                              // [softmax warps][kCPT] v_scale of the warp's keys (quantised P.V)
+    float* s_mx = s_vs + 4 * kParts * kCPT;                              // [2][kParts][128] part-row maxima (tile parity, part, row)
+    float* s_px = s_mx + 2 * kParts * 128;                               // [2][kParts][128] part-row maxima of p * v_scale (quantised P.V)
+    const uint32_t bar_base = base + C::kOffTail + 4 * kParts * kCPT * 4 * 2 + 2 * 2 * kParts * 128 * 4;
     auto bar = [&](int i) { return bar_base + 8u * uint32_t(i); };
     const uint32_t tmem_slot = bar_base + 32 * 8;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + (tmem_slot - base));
@@ -158,7 +168,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // the four control warps need a few dozen registers, the softmax threads ~220 (64 scores + 64 output columns + staging)
     // (setmaxnreg sits at the top of each role's own branch: ptxas bounds every instruction by the smallest count that can reach it)
     if (warp < 4) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs));
       if (warp == 0) {
         // ======================================================== TMA producer
         if (lane == 0) {
@@ -231,11 +241,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSoftmaxRegs));
         // ======================================================== softmax / output (256 threads)
-        const int sw = warp - 4;                   // 0..7
+        const int sw = warp - 4;                   // 0 .. 4 * kParts - 1
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
-        const int half = sw >> 2;                  // which 64 of the tile's 128 columns (and which half of the output columns)
+        const int half = sw >> 2;                  // column part: which kCPT of the tile's 128 columns (and which share of the output columns)
         const int r = q * 32 + lane;               // row of the tile = TMEM lane
         const int m = m0 + r;
         const bool m_ok = m < p.QN;
@@ -259,16 +269,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         auto fold_o = [&](int b, int u, float alpha, [[maybe_unused]] float ps) {       // acc = acc * alpha + O_b [* p_scale]   (:297, :307, :321)
             ptx::mbar_wait(bar(O_FULL + b), u & 1);
             ptx::tc_fence_after();
+            constexpr int OW = HALF < 32 ? HALF : 32;                    // columns per tcgen05.ld
 #pragma unroll
-            for (int c = 0; c < HALF / 32; ++c) {
-                uint32_t o[32];
-                ptx::tmem_ld32(t_lane + o_col(b) + uint32_t(half * HALF + c * 32), o);
+            for (int c = 0; c < HALF / OW; ++c) {
+                uint32_t o[OW];
+                if constexpr (OW == 32) ptx::tmem_ld32(t_lane + o_col(b) + uint32_t(half * HALF + c * 32), o);
+                else ptx::tmem_ld16(t_lane + o_col(b) + uint32_t(half * HALF), o);
                 ptx::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if constexpr (PV == 0) acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha, __uint_as_float(o[i]));
-                    else if constexpr (PV == 1) acc[c * 32 + i] = fmaf(__int_as_float(0x4B400000 + static_cast<int>(o[i])) - 12582912.0f, ps, acc[c * 32 + i] * alpha);
-                    else acc[c * 32 + i] = fmaf(__uint_as_float(o[i]), ps, acc[c * 32 + i] * alpha);
+                for (int i = 0; i < OW; ++i) {
+                    if constexpr (PV == 0) acc[c * OW + i] = fmaf(acc[c * OW + i], alpha, __uint_as_float(o[i]));
+                    else if constexpr (PV == 1) acc[c * OW + i] = fmaf(__int_as_float(0x4B400000 + static_cast<int>(o[i])) - 12582912.0f, ps, acc[c * OW + i] * alpha);
+                    else acc[c * OW + i] = fmaf(__uint_as_float(o[i]), ps, acc[c * OW + i] * alpha);
                 }
             }
             ptx::tc_fence_before();
@@ -279,19 +291,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         // the warp's 64 key scales per tile travel global -> registers (one tile ahead) -> the warp's own strip of shared memory: a load
         // issued in the tile it is needed in would put an L2 round trip in front of every tile, a CTA-wide staging barrier would
         // keep all eight warps in lock-step (they then fight for the MUFU pipe at the same moment)
-        float* my_ks = s_ks + sw * 64;
-        auto load_ks = [&](int j, int e) { const int n = j * kBN + half * 64 + e * 32 + lane; return n < p.KN ? p.k_scale[k_row0 + n] : 0.f; };
-        float ks_a = load_ks(0, 0), ks_b = load_ks(0, 1);
-        [[maybe_unused]] float* my_vs = s_vs + sw * 64;
+        float* my_ks = s_ks + sw * kCPT;
+        auto load_ks = [&](int j, int e) { const int n = j * kBN + half * kCPT + e * 32 + lane; return (e * 32 < kCPT && n < p.KN) ? p.k_scale[k_row0 + n] : 0.f; };
+        float ks_a = load_ks(0, 0), ks_b = load_ks(0, 1);                 // (ks_b / vs_b: the second 32 keys of a 64-column part, unused with 32)
+        [[maybe_unused]] float* my_vs = s_vs + sw * kCPT;
         const int64_t v_row0 = (int64_t(z) * p.VH + vh) * p.KN;
-        auto load_vs = [&](int j, int e) { const int n = j * kBN + half * 64 + e * 32 + lane; return (PV != 0 && n < p.KN) ? p.v_scale[v_row0 + n] : 0.f; };
+        auto load_vs = [&](int j, int e) { const int n = j * kBN + half * kCPT + e * 32 + lane; return (PV != 0 && e * 32 < kCPT && n < p.KN) ? p.v_scale[v_row0 + n] : 0.f; };
         [[maybe_unused]] float vs_a = load_vs(0, 0), vs_b = load_vs(0, 1);
         for (int j = 0; j < T; ++j) {
             const int b = j & 1, u = j >> 1;
             const int n0 = j * kBN;
             my_ks[lane] = ks_a * p.log2_scale;
-            my_ks[32 + lane] = ks_b * p.log2_scale;
-            if constexpr (PV != 0) { my_vs[lane] = vs_a; my_vs[32 + lane] = vs_b; }
+            if constexpr (kCPT == 64) my_ks[32 + lane] = ks_b * p.log2_scale;
+            if constexpr (PV != 0) { my_vs[lane] = vs_a; if constexpr (kCPT == 64) my_vs[32 + lane] = vs_b; }
             __syncwarp();
             if (j + 1 < T) {
                 ks_a = load_ks(j + 1, 0); ks_b = load_ks(j + 1, 1);
@@ -299,24 +311,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             }
             ptx::mbar_wait(bar(S_FULL + b), u & 1);
             ptx::tc_fence_after();
-            float t[64];
+            float t[kCPT];
             {
-                uint32_t s0[32], s1[32];
-                ptx::tmem_ld32(t_lane + s_col(b) + uint32_t(half * 64), s0);
-                ptx::tmem_ld32(t_lane + s_col(b) + uint32_t(half * 64 + 32), s1);
+                uint32_t s0[32];
+                [[maybe_unused]] uint32_t s1[32];
+                ptx::tmem_ld32(t_lane + s_col(b) + uint32_t(half * kCPT), s0);
+                if constexpr (kCPT == 64) ptx::tmem_ld32(t_lane + s_col(b) + uint32_t(half * kCPT + 32), s1);
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(bar(S_EMPTY + b));
                 const float4* ks4 = reinterpret_cast<const float4*>(my_ks);
 #pragma unroll
-                for (int i4 = 0; i4 < 16; ++i4) {
+                for (int i4 = 0; i4 < kCPT / 4; ++i4) {
                     const float4 kv = ks4[i4];
                     const float kk[4] = {kv.x, kv.y, kv.z, kv.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int i = i4 * 4 + e;
-                        const uint32_t rv = i < 32 ? s0[i] : s1[i - 32];
+                        const uint32_t rv = i < 32 ? s0[i & 31] : s1[i & 31];
                         float a;
                         if constexpr (kInt8) a = __int_as_float(0x4B400000 + static_cast<int>(rv)) - 12582912.0f;   // exact: |acc| < 2^22
                         else a = __uint_as_float(rv);
@@ -326,39 +339,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 __syncwarp();                                             // my_ks is rewritten at the top of the next tile
             }
             // masks
-            const int col0 = n0 + half * 64;
+            const int col0 = n0 + half * kCPT;
             if (mask_kind == 1) {
                 const int8_t* mk = reinterpret_cast<const int8_t*>(p.mask) + mask_row;
 #pragma unroll
-                for (int i = 0; i < 64; ++i) {
+                for (int i = 0; i < kCPT; ++i) {
                     const int n = col0 + i;
                     if (n < p.KN && mk[int64_t(n) * p.mask_sk] == 0) t[i] = -INFINITY;
                 }
             } else if (mask_kind == 2) {
                 const float* mk = reinterpret_cast<const float*>(p.mask) + mask_row;
 #pragma unroll
-                for (int i = 0; i < 64; ++i) {
+                for (int i = 0; i < kCPT; ++i) {
                     const int n = col0 + i;
                     t[i] *= pre;
                     if (n < p.KN) t[i] += mk[int64_t(n) * p.mask_sk];
                 }
             }
-            if (col0 + 64 > p.KN || (causal && col0 + 63 > m)) {
+            if (col0 + kCPT > p.KN || (causal && col0 + kCPT - 1 > m)) {
 #pragma unroll
-                for (int i = 0; i < 64; ++i) {
+                for (int i = 0; i < kCPT; ++i) {
                     const int n = col0 + i;
                     if (n >= p.KN || (causal && n > m)) t[i] = -INFINITY;
                 }
             }
             float mx4[4] = {t[0], t[1], t[2], t[3]};
 #pragma unroll
-            for (int i = 4; i < 64; i += 4) {
+            for (int i = 4; i < kCPT; i += 4) {
                 mx4[0] = fmaxf(mx4[0], t[i]); mx4[1] = fmaxf(mx4[1], t[i + 1]); mx4[2] = fmaxf(mx4[2], t[i + 2]); mx4[3] = fmaxf(mx4[3], t[i + 3]);
             }
             float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-            s_mx[(b * 2 + half) * 128 + r] = mx;
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-            mx = fmaxf(mx, s_mx[(b * 2 + (half ^ 1)) * 128 + r]);
+            s_mx[(b * kParts + half) * 128 + r] = mx;
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * kParts) : "memory");
+#pragma unroll
+            for (int o = 1; o < kParts; ++o) mx = fmaxf(mx, s_mx[(b * kParts + ((half + o) & (kParts - 1))) * 128 + r]);
             const float m_new = fmaxf(m_i, mx * rs);
             // :287-294 -- one formula for both of the reference's branches: exp2(-inf - finite) = 0, and a row that has seen
             // nothing but masked keys keeps alpha = 1, p = 0
@@ -368,9 +382,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             ptx::mbar_wait(bar(P_EMPTY + b), (u & 1) ^ 1);               // the MMAs of tile j - 2 have read this P buffer
             [[maybe_unused]] float ps = 1.f;
             if constexpr (PV == 0) {
-                const uint32_t p_row = smem_p + b * kPTile + half * (kPTile / 2) + uint32_t(r) * 128u;
+                // the thread's kCPT columns inside the two 64-key slabs of the tile: slab (half * kCPT) / 64, first 16-byte chunk ((half * kCPT) % 64) / 8
+                const uint32_t p_row = smem_p + b * kPTile + uint32_t((half * kCPT) / 64) * (kPTile / 2) + uint32_t(r) * 128u;
+                const uint32_t cb = uint32_t(((half * kCPT) % 64) / 8);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
+                for (int c = 0; c < kCPT / 8; ++c) {
                     uint32_t w[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -388,7 +404,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                             w[e] = *reinterpret_cast<uint32_t*>(&hh);
                         }
                     }
-                    ptx::st_shared_v4(p_row + (uint32_t(c ^ (r & 7)) << 4), w[0], w[1], w[2], w[3]);
+                    ptx::st_shared_v4(p_row + (((cb + uint32_t(c)) ^ uint32_t(r & 7)) << 4), w[0], w[1], w[2], w[3]);
                 }
             } else {
                 // :298-318: p *= v_scale; p_scale = rowmax(p) / 127 (or / 448), 1 if it underflows; codes = floor(p / p_scale + 0.5)
@@ -396,7 +412,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 const float4* vs4 = reinterpret_cast<const float4*>(my_vs);
                 float px4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int i4 = 0; i4 < 16; ++i4) {
+                for (int i4 = 0; i4 < kCPT / 4; ++i4) {
                     const float4 vv = vs4[i4];
                     const float vk[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
@@ -408,15 +424,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     }
                 }
                 float px = fmaxf(fmaxf(px4[0], px4[1]), fmaxf(px4[2], px4[3]));
-                s_px[(b * 2 + half) * 128 + r] = px;
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-                px = fmaxf(px, s_px[(b * 2 + (half ^ 1)) * 128 + r]);
+                s_px[(b * kParts + half) * 128 + r] = px;
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * kParts) : "memory");
+#pragma unroll
+                for (int o = 1; o < kParts; ++o) px = fmaxf(px, s_px[(b * kParts + ((half + o) & (kParts - 1))) * 128 + r]);
                 ps = px * (PV == 1 ? (1.0f / 127.0f) : (1.0f / 448.0f));
                 if (ps <= 2e-38f) ps = 1.0f;
                 const float inv = __fdiv_rn(1.0f, ps);
                 const uint32_t p_row = smem_p + b * kPTile + uint32_t(r) * 128u;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {                             // 16 codes per 16-byte chunk
+                for (int c = 0; c < kCPT / 16; ++c) {                     // 16 codes per 16-byte chunk
                     uint32_t w[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -431,7 +448,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                             w[e] = lo | (hi << 16);
                         }
                     }
-                    ptx::st_shared_v4(p_row + (uint32_t((half * 4 + c) ^ (r & 7)) << 4), w[0], w[1], w[2], w[3]);
+                    ptx::st_shared_v4(p_row + (uint32_t((half * (kCPT / 16) + c) ^ (r & 7)) << 4), w[0], w[1], w[2], w[3]);
                 }
             }
             ptx::fence_proxy_async_smem();
@@ -445,10 +462,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         fold_o((T - 1) & 1, (T - 1) >> 1, alpha_pend, ps_pend);
         // total row sum = the two halves' partial sums (same running maximum)
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");        // the last tile's s_mx reads are done
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * kParts) : "memory");        // the last tile's s_mx reads are done
         s_mx[half * 128 + r] = l_i;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-        const float l_tot = l_i + s_mx[(half ^ 1) * 128 + r];
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * kParts) : "memory");
+        float l_tot = 0.f;
+#pragma unroll
+        for (int o = 0; o < kParts; ++o) l_tot += s_mx[o * 128 + r];      // the same order in every part: all of a row's threads divide by the same sum
         if (m_ok) {
             const float inv = 1.0f / l_tot;                                // :324
             const int64_t orow = (q_row0 + m) * HDV + half * HALF;
@@ -742,7 +761,16 @@ int launch_attn_m(const void* q, const void* k, const void* vt, int64_t ldt, int
     auto kernel = attn_fwd_kernel<kInt8, HDV, kBf16, PV, kMask>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes); });
+    static int launch_regs = 0;
+    std::call_once(once, [&] {
+        attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+        cudaFuncAttributes fa{};
+        if (attr_err == cudaSuccess) attr_err = cudaFuncGetAttributes(&fa, kernel);
+        launch_regs = fa.numRegs;
+    });
+    // the register hand-over inside the kernel is sized for this count: a different one (another compiler) could leave setmaxnreg.inc waiting
+    SDNQ_REQUIRE(attr_err != cudaSuccess || launch_regs == kLaunchRegs, SDNQ_ECUDA, "attn_fwd_kernel was compiled to %d registers per thread, the setmaxnreg budget assumes %d",
+                 launch_regs, kLaunchRegs);
     SDNQ_REQUIRE(attr_err == cudaSuccess, SDNQ_ECUDA, "cudaFuncSetAttribute(max dynamic smem %d) failed: %s", C::kSmemBytes, cudaGetErrorString(attr_err));
     CUtensorMap tq, tk, tv;
     int rc = make_tmap_sw128(&tq, q, int64_t(p.Z) * p.H * p.QN, HD, HD, 1, kBM);
