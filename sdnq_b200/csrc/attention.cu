@@ -14,11 +14,16 @@
 //   warp 1      MMA issuer:  S_j = Q K_j^T  (tcgen05 kind::i8 / kind::f8f6f4, 128x128x128, accumulator in TMEM, double-buffered)
 //                            O_j = P_j V_j  (tcgen05 kind::f16, A = P_j written by the softmax warps into swizzled shared memory,
 //                                            B = V^T tile; fresh accumulator per tile, double-buffered)
-//   warps 2-9   softmax: thread = one query row (its TMEM lane) x one half of the tile's columns; two warps share a lane quarter.
-//               The row maximum is exchanged between the two halves through shared memory; each half keeps its own partial sum
-//               (same running maximum => the partial sums simply add at the end) and its own half of the output columns in
-//               registers: acc = acc * alpha + O_j is applied one tile late, while the tensor core already works on the next tile.
-// V is consumed K-major ([head_dim, keys]): a small transposing pre-pass writes V^T into the caller's workspace once per call.
+//   warps 2-3   idle: they only donate their registers (setmaxnreg)
+//   warps 4-11  softmax: thread = one query row (its TMEM lane) x one of kParts = 2 column parts of the tile; the warps of a lane
+//               quarter exchange their part-row maxima through shared memory; each keeps its own partial sum (same running maximum
+//               => the partial sums simply add at the end) and its own share of the output columns in registers:
+//               acc = acc * alpha + O_j is applied one tile late, while the tensor core already works on the next tile.
+//               Quantised P.V (:298-318, template parameter PV): p * v_scale, a second exchange for its row maximum, 1-byte codes of
+//               P written in place of the 16-bit values, O_j scaled by the tile's p_scale when it is folded.
+//               Instantiations without a mask tensor / causality (kMask = false) carry no mask code in the key loop and compute a
+//               quarter of their exponentials on the FMA pipe (poly_exp2) instead of the MUFU pipe.
+// V is consumed K-major ([head_dim, keys]): a transposing pre-pass writes V^T into the caller's workspace once per call.
 #include <mutex>
 
 #include "act_quant.cuh"
