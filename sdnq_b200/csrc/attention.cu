@@ -444,9 +444,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     for (int e = 0; e < 4; ++e) {
                         const float* tv = &t[c * 16 + e * 4];
                         if constexpr (PV == 1) {
-                            const int c0 = __float2int_rd(fmaf(tv[0], inv, 0.5f)), c1 = __float2int_rd(fmaf(tv[1], inv, 0.5f));
-                            const int c2 = __float2int_rd(fmaf(tv[2], inv, 0.5f)), c3 = __float2int_rd(fmaf(tv[3], inv, 0.5f));
-                            w[e] = uint32_t(c0 & 0xFF) | (uint32_t(c1 & 0xFF) << 8) | (uint32_t(c2 & 0xFF) << 16) | (uint32_t(c3 & 0xFF) << 24);
+                            // floor(p / p_scale + 0.5) in [0, 127] without F2I (which shares the MUFU pipe's rate with the exponentials):
+                            // a round-down add of 2^23 leaves the integer in the low mantissa bits, PRMT gathers the four low bytes
+                            const uint32_t b0 = __float_as_uint(__fadd_rd(fmaf(tv[0], inv, 0.5f), 8388608.0f)), b1 = __float_as_uint(__fadd_rd(fmaf(tv[1], inv, 0.5f), 8388608.0f));
+                            const uint32_t b2 = __float_as_uint(__fadd_rd(fmaf(tv[2], inv, 0.5f), 8388608.0f)), b3 = __float_as_uint(__fadd_rd(fmaf(tv[3], inv, 0.5f), 8388608.0f));
+                            w[e] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
                         } else {
                             const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(tv[0] * inv, tv[1] * inv), __NV_SATFINITE, __NV_E4M3);
                             const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(tv[2] * inv, tv[3] * inv), __NV_SATFINITE, __NV_E4M3);
