@@ -284,7 +284,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < OW; ++i) {
                     if constexpr (PV == 0) acc[c * OW + i] = fmaf(acc[c * OW + i], alpha, __uint_as_float(o[i]));
-                    else if constexpr (PV == 1) acc[c * OW + i] = fmaf(__int_as_float(0x4B400000 + static_cast<int>(o[i])) - 12582912.0f, ps, acc[c * OW + i] * alpha);
+                    else if constexpr (PV == 1) acc[c * OW + i] = fmaf(__int2float_rn(static_cast<int>(o[i])), ps, acc[c * OW + i] * alpha);
                     else acc[c * OW + i] = fmaf(__uint_as_float(o[i]), ps, acc[c * OW + i] * alpha);
                 }
             }
@@ -336,7 +336,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                         const int i = i4 * 4 + e;
                         const uint32_t rv = i < 32 ? s0[i & 31] : s1[i & 31];
                         float a;
-                        if constexpr (kInt8) a = __int_as_float(0x4B400000 + static_cast<int>(rv)) - 12582912.0f;   // exact: |acc| < 2^22
+                        if constexpr (kInt8) a = __int2float_rn(static_cast<int>(rv));      // I2FP: one issue slot (the magic-number add takes two)
                         else a = __uint_as_float(rv);
                         t[i] = a * kk[e];
                     }
