@@ -105,6 +105,18 @@ __device__ __forceinline__ float poly_exp2(float x) {
     pl = fmaf(pl, f, 0.9999280571937561f);
     return __int_as_float(__float_as_int(pl) + (__float_as_int(xr) << 23));
 }
+// the same for a pair of scores with the packed f32x2 instructions (FADD2 / FFMA2: one issue slot for both)
+__device__ __forceinline__ float2 poly_exp2x2(float2 x) {
+    x = make_float2(fmaxf(x.x, -125.0f), fmaxf(x.y, -125.0f));
+    const float2 magic = make_float2(12582912.0f, 12582912.0f);
+    const float2 xr = __fadd2_rn(x, magic);
+    const float2 n = __fadd2_rn(xr, make_float2(-12582912.0f, -12582912.0f));
+    const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+    float2 pl = __ffma2_rn(make_float2(0.05517210811376572f, 0.05517210811376572f), f, make_float2(0.2426111400127411f, 0.2426111400127411f));
+    pl = __ffma2_rn(pl, f, make_float2(0.6932608485221863f, 0.6932608485221863f));
+    pl = __ffma2_rn(pl, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+    return make_float2(__int_as_float(__float_as_int(pl.x) + (__float_as_int(xr.x) << 23)), __int_as_float(__float_as_int(pl.y) + (__float_as_int(xr.y) << 23)));
+}
 
 // kMask: the call has a mask tensor or is causal; the plain instantiation carries none of that code in its key loop
 template <bool kInt8, int HDV, bool kBf16, int PV, bool kMask>
@@ -283,8 +295,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < OW; ++i) {
-                    if constexpr (PV == 0) acc[c * OW + i] = fmaf(acc[c * OW + i], alpha, __uint_as_float(o[i]));
-                    else if constexpr (PV == 1) acc[c * OW + i] = fmaf(__int2float_rn(static_cast<int>(o[i])), ps, acc[c * OW + i] * alpha);
+                    if constexpr (PV == 0) {
+                        if (i & 1) continue;                              // pairs: FFMA2
+                        const float2 a2 = __ffma2_rn(make_float2(acc[c * OW + i], acc[c * OW + i + 1]), make_float2(alpha, alpha),
+                                                     make_float2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])));
+                        acc[c * OW + i] = a2.x;
+                        acc[c * OW + i + 1] = a2.y;
+                    } else if constexpr (PV == 1) acc[c * OW + i] = fmaf(__int2float_rn(static_cast<int>(o[i])), ps, acc[c * OW + i] * alpha);
                     else acc[c * OW + i] = fmaf(__uint_as_float(o[i]), ps, acc[c * OW + i] * alpha);
                 }
             }
@@ -332,13 +349,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     const float4 kv = ks4[i4];
                     const float kk[4] = {kv.x, kv.y, kv.z, kv.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
+                    for (int e = 0; e < 4; e += 2) {                      // two scores per FMUL2 (packed f32x2: one issue slot)
                         const int i = i4 * 4 + e;
-                        const uint32_t rv = i < 32 ? s0[i & 31] : s1[i & 31];
-                        float a;
-                        if constexpr (kInt8) a = __int2float_rn(static_cast<int>(rv));      // I2FP: one issue slot (the magic-number add takes two)
-                        else a = __uint_as_float(rv);
-                        t[i] = a * kk[e];
+                        const uint32_t rv0 = i < 32 ? s0[i & 31] : s1[i & 31], rv1 = i < 32 ? s0[(i + 1) & 31] : s1[(i + 1) & 31];
+                        float2 a;
+                        if constexpr (kInt8) a = make_float2(__int2float_rn(static_cast<int>(rv0)), __int2float_rn(static_cast<int>(rv1)));      // I2FP: one issue slot (the magic-number add takes two)
+                        else a = make_float2(__uint_as_float(rv0), __uint_as_float(rv1));
+                        const float2 tt = __fmul2_rn(a, make_float2(kk[e], kk[e + 1]));
+                        t[i] = tt.x;
+                        t[i + 1] = tt.y;
                     }
                 }
                 __syncwarp();                                             // my_ks is rewritten at the top of the next tile
@@ -384,6 +403,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             const float alpha = m_new == -INFINITY ? 1.0f : fast_exp2(m_i - m_new);
             const float m_use = m_new == -INFINITY ? 0.0f : m_new;
             float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+            [[maybe_unused]] float2 sum2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};      // 16-bit P.V: pair sums (FADD2)
             ptx::mbar_wait(bar(P_EMPTY + b), (u & 1) ^ 1);               // the MMAs of tile j - 2 have read this P buffer
             [[maybe_unused]] float ps = 1.f;
             if constexpr (PV == 0) {
@@ -398,9 +418,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                         // the exponentials are MUFU-bound (16 / clock / SM) with issue slots to spare: without a mask (no -inf scores
                         // except padded keys, which meet zero-filled V rows) a share of them is computed on the FMA pipe instead
                         const bool kPoly = !kMask && e >= 4 - SDNQ_ATTN_POLY_PAIRS;      // (a compile-time constant once the loop is unrolled)
-                        const float x0 = fmaf(t[c * 8 + 2 * e], rs, -m_use), x1 = fmaf(t[c * 8 + 2 * e + 1], rs, -m_use);
-                        const float p0 = kPoly ? poly_exp2(x0) : fast_exp2(x0), p1 = kPoly ? poly_exp2(x1) : fast_exp2(x1);
-                        sum4[e] += p0 + p1;
+                        const float2 x = __ffma2_rn(make_float2(t[c * 8 + 2 * e], t[c * 8 + 2 * e + 1]), make_float2(rs, rs), make_float2(-m_use, -m_use));
+                        float p0, p1;
+                        if (kPoly) {
+                            const float2 pp = poly_exp2x2(x);
+                            p0 = pp.x;
+                            p1 = pp.y;
+                        } else {
+                            p0 = fast_exp2(x.x);
+                            p1 = fast_exp2(x.y);
+                        }
+                        sum2[e & 1] = __fadd2_rn(sum2[e & 1], make_float2(p0, p1));
                         if constexpr (kBf16) {
                             __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
                             w[e] = *reinterpret_cast<uint32_t*>(&hh);
@@ -461,7 +489,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar(P_FULL + b));
-            l_i = fmaf(l_i, alpha, (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+            if constexpr (PV == 0) l_i = fmaf(l_i, alpha, (sum2[0].x + sum2[0].y) + (sum2[1].x + sum2[1].y));
+            else l_i = fmaf(l_i, alpha, (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
             m_i = m_new;
             if (j > 0) fold_o(b ^ 1, (j - 1) >> 1, alpha_pend, ps_pend);
             alpha_pend = alpha;
