@@ -283,16 +283,17 @@ dequant_svd_kernel(const __grid_constant__ BatchEntry single, const BatchEntry* 
                         uint32_t w4[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {                              // byte j of the word = elements 2j (low nibble), 2j + 1
-                            const float q0 = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7440 | j)) - bias;
-                            const float q1 = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7440 | j)) - bias;
-                            const float v0 = has_zp ? fmaf(q0, sc, z) : __fmul_rn(q0, sc);
-                            const float v1 = has_zp ? fmaf(q1, sc, z) : __fmul_rn(q1, sc);
+                            // the element pair goes through the packed f32x2 forms (FADD2 / FMUL2 / FFMA2: IEEE per component, one issue
+                            // slot for both -- this epilogue is issue-bound)
+                            const float2 q = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7440 | j)),
+                                                                    __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7440 | j))), make_float2(-bias, -bias));
+                            const float2 v = has_zp ? __ffma2_rn(q, make_float2(sc, sc), make_float2(z, z)) : __fmul2_rn(q, make_float2(sc, sc));
                             // result.to(svd dtype): one packed conversion rounds both to bf16, two bit operations bring them back to f32
-                            __nv_bfloat162 wb = __floats2bfloat162_rn(v0, v1);
+                            __nv_bfloat162 wb = __floats2bfloat162_rn(v.x, v.y);
                             const uint32_t wbits = *reinterpret_cast<uint32_t*>(&wb);
-                            const float y0 = __uint_as_float(wbits << 16) + __uint_as_float(r[8 * o + 2 * j]);          // addmm_: f32 accumulate,
-                            const float y1 = __uint_as_float(wbits & 0xFFFF0000u) + __uint_as_float(r[8 * o + 2 * j + 1]);   // rounded once below
-                            __nv_bfloat162 hh = __floats2bfloat162_rn(y0, y1);
+                            const float2 y = __fadd2_rn(make_float2(__uint_as_float(wbits << 16), __uint_as_float(wbits & 0xFFFF0000u)),      // addmm_: f32 accumulate,
+                                                        make_float2(__uint_as_float(r[8 * o + 2 * j]), __uint_as_float(r[8 * o + 2 * j + 1])));   // rounded once below
+                            __nv_bfloat162 hh = __floats2bfloat162_rn(y.x, y.y);
                             w4[j] = *reinterpret_cast<uint32_t*>(&hh);
                         }
                         const int c8 = h * 4 + o;
