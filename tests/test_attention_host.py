@@ -94,3 +94,16 @@ def test_oracle_quantised_pv_is_close_to_the_unquantised_result():
             got = O.attn_fwd(qq, kq, vq, qs, ks, sm_scale=HD ** -0.5, out_dtype="float32", block_n=bn, v_scale=vs, pv_matmul_dtype=pv)
             rel = np.linalg.norm(got - base) / np.linalg.norm(base)
             assert rel <= tol, (pv, bn, rel)
+
+
+def test_pv_matmul_dtype_aliases_follow_the_reference():
+    """triton_atten.py:454-455 ("enabled" / "uint8" -> int8) and :478 (None / "auto" / "none" / "no" / "disabled": unquantised P.V)"""
+    from sdnq_b200.attention import _pv_dtype
+    for off in (None, "auto", "none", "no", "disabled"):
+        assert _pv_dtype(off) is None
+    for alias in ("enabled", "uint8", "int8"):
+        assert _pv_dtype(alias) == "int8"
+    for alias in ("fp8", "float8_e4m3fn"):
+        assert _pv_dtype(alias) == "float8_e4m3fn"
+    with pytest.raises(NotImplementedError):
+        _pv_dtype("float16")
